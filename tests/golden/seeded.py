@@ -1,0 +1,183 @@
+"""Deterministic inputs / weights for the golden parity cases.
+
+Shared by oracle/gen_golden.py (which runs the UNMODIFIED reference on these tensors in the build
+container and stores its outputs under tests/golden/*.pt) and by the tests (which rebuild the same
+tensors from the seed and compare oracle / CUDA results with the stored reference outputs).
+Only seeds and reference OUTPUTS are committed; a checksum of the regenerated inputs guards against
+RNG drift between torch versions.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict
+
+import torch
+
+GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def gen(seed: int) -> torch.Generator:
+    return torch.Generator().manual_seed(seed)
+
+
+def randn(g, *shape, scale=1.0, shift=0.0):
+    return torch.randn(*shape, generator=g) * scale + shift
+
+
+def uniform(g, *shape, lo=-1.0, hi=1.0):
+    return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+
+def reseed_state_dict(sd: Dict[str, torch.Tensor], seed: int) -> Dict[str, torch.Tensor]:
+    """Fill a reference-shaped state dict with seeded, non-degenerate values (sorted key order)."""
+    g = gen(seed)
+    out = {}
+    for k in sorted(sd):
+        v = sd[k]
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.tensor(3)
+        elif k.endswith("running_mean"):
+            out[k] = uniform(g, *v.shape, lo=-0.2, hi=0.2)
+        elif k.endswith("running_var"):
+            out[k] = uniform(g, *v.shape, lo=0.5, hi=1.5)
+        elif ".bn." in k and k.endswith("weight"):
+            out[k] = uniform(g, *v.shape, lo=0.3, hi=0.7)
+        elif ".bn." in k and k.endswith("bias"):
+            out[k] = uniform(g, *v.shape, lo=-0.1, hi=0.1)
+        elif k.endswith("anchors") or "dfl" in k:
+            out[k] = v.clone()
+        elif k.endswith("w.0.conv.weight") or (".w." in k and k.endswith("conv.weight")):
+            out[k] = uniform(g, *v.shape, lo=0.1, hi=0.5)
+        elif v.dim() == 4:  # conv weight [co, ci/g, k, k]
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            b = 1.5 / math.sqrt(fan_in)
+            out[k] = uniform(g, *v.shape, lo=-b, hi=b)
+        elif v.dim() == 1:  # conv bias
+            out[k] = uniform(g, *v.shape, lo=-0.1, hi=0.1)
+        else:
+            out[k] = uniform(g, *v.shape)
+    return out
+
+
+def checksum(*tensors) -> float:
+    s = 0.0
+    for t in tensors:
+        t = t.double().flatten()
+        s += float((t * torch.arange(1, t.numel() + 1, dtype=torch.float64).remainder(97.0)).sum())
+    return s
+
+
+def sd_checksum(sd) -> float:
+    return checksum(*[sd[k].float() for k in sorted(sd)])
+
+
+def pack_spikes(s: torch.Tensor) -> torch.Tensor:
+    """{0,1} float tensor -> uint8 bit-packed (storage only)."""
+    import numpy as np
+    return torch.from_numpy(np.packbits(s.numpy().astype("uint8").reshape(-1)))
+
+
+def unpack_spikes(p: torch.Tensor, shape) -> torch.Tensor:
+    import numpy as np
+    n = 1
+    for d in shape:
+        n *= d
+    return torch.from_numpy(np.unpackbits(p.numpy())[:n].astype("float32")).reshape(*shape)
+
+
+def block_cfg(kind: str, cout: int, k: int = 3, s: int = 1):
+    """Single-layer model dict understood by the oracle's plan_model/init_state_dict."""
+    args = [cout, s] if kind == "BasicBlock_1" else [cout, k, s]
+    return dict(nc=3, depth_multiple=1.0, width_multiple=1.0, anchors=2,
+                backbone=[[-1, 1, kind, args]], head=[])
+
+
+# name -> spec.  T, N small; channel counts are multiples of 64 like every in-scope layer.
+LIF_CASES = {
+    "lif_c64_t4": dict(T=4, N=2, C=64, H=10, W=12, seed=101),
+    "lif_c128_t4": dict(T=4, N=1, C=128, H=7, W=9, seed=102),
+    "lif_c64_t1": dict(T=1, N=2, C=64, H=6, W=6, seed=103),
+    "lif_c64_t5": dict(T=5, N=1, C=64, H=8, W=8, seed=104),
+    "lif_c64_t8": dict(T=8, N=1, C=64, H=5, W=7, seed=105),
+}
+CONV_CASES = {
+    # binary (spike) inputs
+    "conv3_s1_64_128": dict(T=4, N=2, ci=64, co=128, k=3, s=1, p=1, H=10, W=12, spikes=True, seed=201),
+    "conv3_s2_64_64": dict(T=4, N=2, ci=64, co=64, k=3, s=2, p=1, H=12, W=10, spikes=True, seed=202),
+    "conv1_s1_128_64": dict(T=4, N=2, ci=128, co=64, k=1, s=1, p=0, H=6, W=8, spikes=True, seed=203),
+    "conv3_s1_192_256": dict(T=2, N=1, ci=192, co=256, k=3, s=1, p=1, H=9, W=9, spikes=True, seed=204),
+    # real inputs
+    "stem7_s2_3_64": dict(T=4, N=2, ci=3, co=64, k=7, s=2, p=3, H=32, W=32, spikes=False, seed=205),
+    "head1_128_24_bias": dict(T=4, N=2, ci=128, co=24, k=1, s=1, p=0, H=8, W=8, spikes=False, bias=True, seed=206),
+}
+BN_CASES = {
+    "bn_c64": dict(T=4, N=2, C=64, H=6, W=8, seed=301),
+}
+BLOCK_CASES = {
+    "bb2_64_128_s2": dict(kind="BasicBlock_2", cin=64, cout=128, k=3, s=2, T=4, N=2, H=12, W=12, seed=401),
+    "bb2_128_128_s1": dict(kind="BasicBlock_2", cin=128, cout=128, k=3, s=1, T=4, N=2, H=8, W=8, seed=402),
+    "bb2_128_64_k1": dict(kind="BasicBlock_2", cin=128, cout=64, k=1, s=1, T=4, N=2, H=8, W=8, seed=403),
+    "cr2_64_128_s2": dict(kind="Concat_res2", cin=64, cout=128, k=3, s=2, T=4, N=2, H=12, W=12, seed=404),
+    "bb1_128_64_s1": dict(kind="BasicBlock_1", cin=128, cout=64, k=3, s=1, T=4, N=1, H=6, W=6, seed=405),
+}
+MODEL_CASES = {
+    "tiny_64": dict(cfg="tiny", T=4, N=2, H=64, W=64, seed=501),
+}
+
+
+def lif_inputs(spec):
+    g = gen(spec["seed"])
+    C = spec["C"]
+    x = randn(g, spec["T"], spec["N"], C, spec["H"], spec["W"], scale=0.5, shift=0.1)
+    dw_w = uniform(g, C, 1, 3, 3, lo=-1 / 3, hi=1 / 3)
+    dw_b = uniform(g, C, lo=-1 / 3, hi=1 / 3)
+    b = 1.0 / math.sqrt(C)
+    pw_w = uniform(g, C, C, 1, 1, lo=-b, hi=b)
+    pw_b = uniform(g, C, lo=-b, hi=b)
+    gout = randn(g, *x.shape)
+    return dict(x=x, dw_w=dw_w, dw_b=dw_b, pw_w=pw_w, pw_b=pw_b, gout=gout)
+
+
+def conv_inputs(spec):
+    g = gen(spec["seed"])
+    shape = (spec["T"], spec["N"], spec["ci"], spec["H"], spec["W"])
+    if spec["spikes"]:
+        x = (torch.rand(*shape, generator=g) < 0.2).float()
+    else:
+        x = torch.rand(*shape, generator=g)
+    fan_in = spec["ci"] * spec["k"] ** 2
+    b = 1.0 / math.sqrt(fan_in)
+    w = uniform(g, spec["co"], spec["ci"], spec["k"], spec["k"], lo=-b, hi=b)
+    bias = uniform(g, spec["co"], lo=-b, hi=b) if spec.get("bias") else None
+    return dict(x=x, w=w, b=bias)
+
+
+def bn_inputs(spec):
+    g = gen(spec["seed"])
+    C = spec["C"]
+    x = randn(g, spec["T"], spec["N"], C, spec["H"], spec["W"], scale=1.3, shift=0.4)
+    sd = {"bn.weight": uniform(g, C, lo=0.3, hi=0.7), "bn.bias": uniform(g, C, lo=-0.1, hi=0.1),
+          "bn.running_mean": uniform(g, C, lo=-0.2, hi=0.2), "bn.running_var": uniform(g, C, lo=0.5, hi=1.5),
+          "bn.num_batches_tracked": torch.tensor(3)}
+    return dict(x=x, sd=sd)
+
+
+def block_inputs(spec, oracle):
+    """oracle: the ecs_oracle module (for key/shape bookkeeping only)."""
+    cfg = block_cfg(spec["kind"], spec["cout"], spec["k"], spec["s"])
+    sd = reseed_state_dict(oracle.init_state_dict(cfg, spec["T"], ch=spec["cin"]), spec["seed"])
+    g = gen(spec["seed"] + 7)
+    x = randn(g, spec["T"], spec["N"], spec["cin"], spec["H"], spec["W"], scale=0.5, shift=0.1)
+    return dict(cfg=cfg, sd=sd, x=x)
+
+
+def model_inputs(spec, oracle, cfg):
+    sd = reseed_state_dict(oracle.init_state_dict(cfg, spec["T"]), spec["seed"])
+    stride = oracle.detect_strides(cfg)
+    for k in sd:  # Detect keeps its anchors in grid units (models/yolo.py:230)
+        if k.endswith("anchors"):
+            sd[k] = sd[k] / stride.view(-1, 1, 1)
+    g = gen(spec["seed"] + 7)
+    x = torch.rand(spec["N"], 3, spec["H"], spec["W"], generator=g)
+    return dict(sd=sd, x=x, stride=stride)
