@@ -1,0 +1,50 @@
+"""Builds libecsy.so (sm_100a) in-tree with nvcc.  No JIT cache: the .so travels with the repo snapshot."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "lib", "libecsy.so")
+SOURCES = ["cabi.cu", "elementwise.cu", "conv_misc.cu", "lif.cu", "umma_gemm.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _stale(out, deps):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "ecsy.h"))
+    objs, procs = [], []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            cmd = ["nvcc", *FLAGS, "-c", s, "-o", o]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(f"---- {src}\n{out}")
+        with open(os.path.join(objdir, src + ".log"), "w") as f:
+            f.write(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    if force or procs or _stale(LIB, objs):
+        subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-lcudart", "-Xlinker", "--no-undefined",
+                               "-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,184 @@
+// Weight packing, im2col for real-valued inputs, the generic SIMT convolution (odd shapes:
+// grouped convs, Cout not a multiple of 64) and the C-ABI convolution entry points.
+#include "ecsy_common.cuh"
+#include "../../include/ecsy.h"
+#include "umma_gemm.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work, int per_block, int max_blocks) {
+  int64_t g = (work + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+// w [Co][Ci][kh][kw] fp32 -> out [splits][Co][Kpad] bf16 with k = (ky*kw + kx)*Ci + ci (hi plane,
+// then the bf16 residual plane): hi + lo carries 16 mantissa bits of every weight.
+__global__ void k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Co, int Ci, int kh,
+                              int kw, int Kpad, int splits) {
+  const int64_t total = (int64_t)Co * Kpad;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const int K = kh * kw * Ci;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int k = static_cast<int>(i % Kpad);
+    const int co = static_cast<int>(i / Kpad);
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / Ci, ci = k - tap * Ci;
+      v = w[((int64_t)co * Ci + ci) * (kh * kw) + tap];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (splits == 2) out[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// A[m][k] (bf16 hi [+ lo]) for a real-valued NHWC input; m = output pixel, k = (ky*kw+kx)*Ci + ci,
+// zero padded to Kpad.  Each thread writes 8 consecutive k (16 bytes per plane).
+__global__ void k_im2col(const float* __restrict__ x, int64_t x_imgs, __nv_bfloat16* __restrict__ a_hi,
+                         __nv_bfloat16* __restrict__ a_lo, int64_t imgs, int H, int W, int Ci, int Ho, int Wo, int kh,
+                         int kw, int stride, int pad, int Kpad) {
+  const int k8 = Kpad >> 3;
+  const int64_t total = imgs * Ho * Wo * k8;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const int K = kh * kw * Ci;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int j = static_cast<int>(i % k8);
+    int64_t m = i / k8;
+    const int wo = static_cast<int>(m % Wo);
+    const int ho = static_cast<int>((m / Wo) % Ho);
+    const int64_t img = m / ((int64_t)Wo * Ho);
+    const float* src = x + (img % x_imgs) * (int64_t)H * W * Ci;
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = j * 8 + u;
+      float val = 0.f;
+      if (k < K) {
+        const int tap = k / Ci, ci = k - tap * Ci;
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int hi = ho * stride - pad + ky, wi = wo * stride - pad + kx;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = src[((int64_t)hi * W + wi) * Ci + ci];
+      }
+      v[u] = val;
+    }
+    uint32_t hi4[4], lo4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
+      hi4[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
+      lo4[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    reinterpret_cast<uint4*>(a_hi)[i] = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+    if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[i] = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+  }
+}
+
+// Generic direct convolution, fp32 FMA: one thread per (output pixel, output channel).
+// w: [kh][kw][Ci/g][Co] fp32.  (Snn_Conv2d on real inputs with odd shapes: Detect.m 1x1 + bias,
+// models/yolo.py:73; grouped DDetect convs, models/yolo_snn.py:100-107.)
+__global__ void k_simt_conv(const float* __restrict__ x, int64_t x_imgs, const float* __restrict__ w,
+                            const float* __restrict__ bias, float bias_mul, const float* __restrict__ scale,
+                            const float* __restrict__ shift, float* __restrict__ out, int64_t imgs, int H, int W,
+                            int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int pad, int groups) {
+  const int64_t total = imgs * Ho * Wo * Co;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const int cig = Ci / groups, cog = Co / groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int co = static_cast<int>(i % Co);
+    int64_t m = i / Co;
+    const int wo = static_cast<int>(m % Wo);
+    const int ho = static_cast<int>((m / Wo) % Ho);
+    const int64_t img = m / ((int64_t)Wo * Ho);
+    const float* src = x + (img % x_imgs) * (int64_t)H * W * Ci + (co / cog) * cig;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int hi = ho * stride - pad + ky;
+      if (hi < 0 || hi >= H) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int wi = wo * stride - pad + kx;
+        if (wi < 0 || wi >= W) continue;
+        const float* xp = src + ((int64_t)hi * W + wi) * Ci;
+        const float* wp = w + ((int64_t)(ky * kw + kx) * cig) * Co + co;
+        for (int ci = 0; ci < cig; ++ci) acc = fmaf(xp[ci], wp[(int64_t)ci * Co], acc);
+      }
+    }
+    if (bias != nullptr) acc += bias[co] * bias_mul;
+    if (scale != nullptr) acc = fmaf(acc, scale[co], shift[co]);
+    out[i] = acc;
+  }
+}
+
+}  // namespace
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int ecsy_pack_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh, int kw, int Kpad,
+                                     int splits, void* stream) {
+  ECSY_CHECK_ARG(w && out_bf16 && Co > 0 && Ci > 0 && kh > 0 && kw > 0, "pack_conv_weight: bad arguments");
+  ECSY_CHECK_ARG(Kpad % 64 == 0 && Kpad >= kh * kw * Ci && (splits == 1 || splits == 2), "pack_conv_weight: Kpad/splits");
+  k_pack_weight<<<grid_for((int64_t)Co * Kpad, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(out_bf16), Co, Ci, kh, kw, Kpad, splits);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed, int splits, float* out,
+                                   const float* scale, const float* shift, const float* residual, int64_t res_imgs,
+                                   int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                   void* stream) {
+  ECSY_CHECK_ARG(spikes && w_packed && out && imgs > 0 && H > 0 && W > 0, "spike_conv_fwd: bad arguments");
+  ECSY_CHECK_ARG((scale == nullptr) == (shift == nullptr), "spike_conv_fwd: scale/shift pair");
+  ECSY_CHECK_ARG(!residual || (res_imgs > 0 && imgs % res_imgs == 0), "spike_conv_fwd: residual image count");
+  ECSY_CHECK_ARG(imgs < (1 << 24), "spike_conv_fwd: too many images");
+  return ecsy_umma_spike_conv(spikes, w_packed, splits, out, scale, shift, residual, res_imgs, (int)imgs, H, W, Cin,
+                              Cout, k, stride, pad, STREAM(stream));
+}
+
+extern "C" size_t ecsy_real_conv_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                          int groups, int splits) {
+  if (groups != 1 || Cout % 64 != 0) return 0;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int64_t Kpad = ((int64_t)k * k * Cin + 63) / 64 * 64;
+  return static_cast<size_t>(imgs * Ho * Wo * Kpad * 2 * splits + 512);
+}
+
+// Real-valued-input convolution.  groups == 1 and Cout % 64 == 0: im2col (bf16 hi[/lo]) + tcgen05 GEMM with
+// `w_packed` ([splits][Cout][Kpad] bf16); otherwise the SIMT kernel with `w_simt` ([kh][kw][Ci/g][Co] fp32).
+extern "C" int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_packed, const float* w_simt, int splits,
+                                  const float* bias, float bias_mul, const float* scale, const float* shift, float* out,
+                                  int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad, int groups,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  ECSY_CHECK_ARG(x && out && imgs > 0 && x_imgs > 0 && imgs % x_imgs == 0, "real_conv_fwd: bad arguments");
+  ECSY_CHECK_ARG((scale == nullptr) == (shift == nullptr), "real_conv_fwd: scale/shift pair");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  ECSY_CHECK_ARG(Ho > 0 && Wo > 0, "real_conv_fwd: empty output");
+  if (groups == 1 && Cout % 64 == 0 && w_packed != nullptr && bias == nullptr) {
+    const int Kpad = (k * k * Cin + 63) / 64 * 64;
+    const int64_t M = imgs * Ho * Wo;
+    const size_t need = ecsy_real_conv_ws_bytes(imgs, H, W, Cin, Cout, k, stride, pad, groups, splits);
+    if (ws == nullptr || ws_bytes < need) {
+      ecsy_set_error("real_conv_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+      return ECSY_ERR_WS;
+    }
+    uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
+    __nv_bfloat16* a_lo = splits == 2 ? a_hi + M * Kpad : nullptr;
+    k_im2col<<<grid_for(M * (Kpad / 8), kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+        x, x_imgs, a_hi, a_lo, imgs, H, W, Cin, Ho, Wo, k, k, stride, pad, Kpad);
+    ECSY_LAUNCH_CHECK();
+    return ecsy_umma_dense(a_hi, a_lo, M, Kpad, w_packed, splits, out, Cout, scale, shift, nullptr, 0, STREAM(stream));
+  }
+  ECSY_CHECK_ARG(w_simt != nullptr, "real_conv_fwd: this shape needs the SIMT weight layout");
+  ECSY_CHECK_ARG(groups >= 1 && Cin % groups == 0 && Cout % groups == 0, "real_conv_fwd: groups");
+  const int64_t total = imgs * Ho * Wo * Cout;
+  k_simt_conv<<<grid_for(total, kThreads, ecsy_num_sms() * 16), kThreads, 0, STREAM(stream)>>>(
+      x, x_imgs, w_simt, bias, bias_mul, scale, shift, out, imgs, H, W, Cin, Ho, Wo, Cout, k, k, stride, pad, groups);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}

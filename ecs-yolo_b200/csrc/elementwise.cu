@@ -1,0 +1,586 @@
+// Streaming (HBM-bound) kernels of the spiking hot path: layout conversion, spike bit-packing,
+// the first LIF step, tdBN statistics, affine+add, max-pool, nearest upsample / concat, T-fusion
+// and the Stack-A / Stack-B head decodes.  All activations are NHWC fp32 ("[imgs][H][W][C]"),
+// spikes are one bit per channel packed along C ("[imgs][H][W][C/32]" uint32, bit c&31 of word c>>5).
+#include "ecsy_common.cuh"
+#include "../../include/ecsy.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work, int per_block, int max_blocks) {
+  int64_t g = (work + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW <-> NHWC (edge of the model only).  32x32 smem transpose per image over (C, HW).
+// ------------------------------------------------------------------------------------------
+__global__ void k_transpose_inner(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+  // per image: in [R][Cc] -> out [Cc][R]
+  __shared__ float tile[32][33];
+  const int64_t img = blockIdx.z;
+  const float* src = in + img * (int64_t)R * Cc;
+  float* dst = out + img * (int64_t)R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = src[(int64_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) dst[(int64_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// spikes pack / unpack.  One warp packs 32 channels of one pixel per ballot.
+// ------------------------------------------------------------------------------------------
+__global__ void k_pack(const float* __restrict__ x, uint32_t* __restrict__ bits, int64_t words, float thresh) {
+  // word w covers elements [32w, 32w+32); lane l reads element 32w+l
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < words; w += nwarps) {
+    float v = x[w * 32 + lane];
+    uint32_t b = __ballot_sync(0xffffffffu, v > thresh);
+    if (lane == 0) bits[w] = b;
+  }
+}
+
+__global__ void k_unpack(const uint32_t* __restrict__ bits, float* __restrict__ x, int64_t words) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < words; w += nwarps) {
+    uint32_t b = bits[w];
+    x[w * 32 + lane] = (b >> lane) & 1u ? 1.0f : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LIF step 0 (models/common.py:271,275): mem_0 = x_0 (+ optional per-channel affine = folded tdBN),
+// spike_0 = mem_0 > thresh.  Each thread owns 4 channels of one pixel; 8 lanes assemble one word.
+// ------------------------------------------------------------------------------------------
+__global__ void k_lif_first(const float* __restrict__ x, const float* __restrict__ scale,
+                            const float* __restrict__ shift, float* __restrict__ mem,
+                            uint32_t* __restrict__ bits, int64_t n4, int C, float thresh) {
+  // n4 = pixels*C/4 ; total threads padded to a multiple of 8 lanes per word by construction (C%32==0)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
+    if (scale != nullptr) {
+      int c = static_cast<int>((i * 4) % C);
+      float4 s = *reinterpret_cast<const float4*>(scale + c);
+      float4 b = *reinterpret_cast<const float4*>(shift + c);
+      v.x = ecsy::add_rn(ecsy::mul_rn(v.x, s.x), b.x);
+      v.y = ecsy::add_rn(ecsy::mul_rn(v.y, s.y), b.y);
+      v.z = ecsy::add_rn(ecsy::mul_rn(v.z, s.z), b.z);
+      v.w = ecsy::add_rn(ecsy::mul_rn(v.w, s.w), b.w);
+    }
+    if (mem != nullptr) reinterpret_cast<float4*>(mem)[i] = v;
+    uint32_t nib = (v.x > thresh ? 1u : 0u) | (v.y > thresh ? 2u : 0u) | (v.z > thresh ? 4u : 0u) |
+                   (v.w > thresh ? 8u : 0u);
+    // 8 consecutive lanes hold the 8 nibbles of one 32-channel word (n4 is a multiple of 8 and the
+    // loop stride is a multiple of 32, so all lanes of a word-group are active together)
+    const int sub = threadIdx.x & 7;
+    uint32_t w = nib << (4 * sub);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if (sub == 0) bits[i >> 3] = w;
+  }
+}
+
+// Plain (uncoupled) LIF step t>=1 with an externally supplied feedback term; used by the
+// per-timestep pipeline when the ECS GEMM epilogue is not fused (debug / cross-check path):
+// mem_t = mem_{t-1}*decay*(1-s_{t-1}) + x_t + fecs_{t-1}
+__global__ void k_lif_step(const float* __restrict__ x, const float* __restrict__ scale,
+                           const float* __restrict__ shift, const float* __restrict__ fecs,
+                           float* __restrict__ mem, const uint32_t* __restrict__ bits_prev,
+                           uint32_t* __restrict__ bits, int64_t n4, int C, float thresh, float decay) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
+    if (scale != nullptr) {
+      int c = static_cast<int>((i * 4) % C);
+      float4 s = *reinterpret_cast<const float4*>(scale + c);
+      float4 b = *reinterpret_cast<const float4*>(shift + c);
+      v.x = ecsy::add_rn(ecsy::mul_rn(v.x, s.x), b.x);
+      v.y = ecsy::add_rn(ecsy::mul_rn(v.y, s.y), b.y);
+      v.z = ecsy::add_rn(ecsy::mul_rn(v.z, s.z), b.z);
+      v.w = ecsy::add_rn(ecsy::mul_rn(v.w, s.w), b.w);
+    }
+    float4 m = reinterpret_cast<const float4*>(mem)[i];
+    float4 f = fecs ? reinterpret_cast<const float4*>(fecs)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int sub = threadIdx.x & 7;
+    uint32_t pw = bits_prev[i >> 3] >> (4 * sub);
+    float4 o;
+    o.x = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.x, decay), (pw & 1u) ? 0.f : 1.f), v.x), f.x);
+    o.y = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.y, decay), (pw & 2u) ? 0.f : 1.f), v.y), f.y);
+    o.z = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.z, decay), (pw & 4u) ? 0.f : 1.f), v.z), f.z);
+    o.w = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.w, decay), (pw & 8u) ? 0.f : 1.f), v.w), f.w);
+    reinterpret_cast<float4*>(mem)[i] = o;
+    uint32_t nib = (o.x > thresh ? 1u : 0u) | (o.y > thresh ? 2u : 0u) | (o.z > thresh ? 4u : 0u) |
+                   (o.w > thresh ? 8u : 0u);
+    uint32_t w = nib << (4 * sub);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if (sub == 0) bits[i >> 3] = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ECS spread, depthwise half (models/common.py:289-294 spread[0]): A[p][c] = b[c] + sum_tap
+// bit(p+tap, c) * w[tap][c], written as bf16 hi (+ lo residual) rows for the point-wise GEMM.
+// One thread: one pixel x 8 channels (one byte of spikes per tap); 9 taps, zero padding.
+// ------------------------------------------------------------------------------------------
+__global__ void k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*[9][C]*/,
+                            const float* __restrict__ dw_b, __nv_bfloat16* __restrict__ a_hi,
+                            __nv_bfloat16* __restrict__ a_lo, int N, int H, int W, int C) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)N * H * W * c8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(bits);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int j = static_cast<int>(i % c8);
+    const int64_t p = i / c8;
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const int c0 = j * 8;
+    float acc[8];
+    {
+      float4 b0 = *reinterpret_cast<const float4*>(dw_b + c0);
+      float4 b1 = *reinterpret_cast<const float4*>(dw_b + c0 + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ww = w + kx - 1;
+        if (ww < 0 || ww >= W) continue;
+        const uint32_t m = bytes[(p + (int64_t)(ky - 1) * W + (kx - 1)) * (C >> 3) + j];
+        if (m == 0) continue;
+        const float* wt = dw_w + (ky * 3 + kx) * C + c0;
+        float4 w0 = *reinterpret_cast<const float4*>(wt);
+        float4 w1 = *reinterpret_cast<const float4*>(wt + 4);
+        // accumulation order = tap order of the reference's 3x3 kernel (row-major), fp32
+        if (m & 1u) acc[0] += w0.x;
+        if (m & 2u) acc[1] += w0.y;
+        if (m & 4u) acc[2] += w0.z;
+        if (m & 8u) acc[3] += w0.w;
+        if (m & 16u) acc[4] += w1.x;
+        if (m & 32u) acc[5] += w1.y;
+        if (m & 64u) acc[6] += w1.z;
+        if (m & 128u) acc[7] += w1.w;
+      }
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * q]), h1 = __float2bfloat16_rn(acc[2 * q + 1]);
+      hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * q] - __bfloat162float(h0));
+      __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * q + 1] - __bfloat162float(h1));
+      lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    reinterpret_cast<uint4*>(a_hi)[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tdBN statistics (models/common.py:674-679 -> BatchNorm3d over N,T,H,W): per-channel mean and
+// biased variance of x[rows][C].  Stage 1: each block reduces a row range to partial (sum, sumsq)
+// in double; stage 2: one thread per channel combines.  Deterministic (no atomics).
+// ------------------------------------------------------------------------------------------
+__global__ void k_bn_partial(const float* __restrict__ x, int64_t rows, int C, int64_t rows_per_block,
+                             double* __restrict__ part /*[blocks][2][C]*/) {
+  extern __shared__ double sred[];  // [nty][2][C]
+  const int c4 = C >> 2;
+  const int tpr = c4;                // threads per row (C <= 1024 -> <= 256)
+  const int nty = blockDim.x / tpr;  // rows in flight
+  const int tq = threadIdx.x % tpr, ty = threadIdx.x / tpr;
+  const int64_t r0 = blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (ty < nty) {
+    float fs[4] = {0, 0, 0, 0}, fq[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int64_t r = r0 + ty; r < r1; r += nty) {
+      float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x + r * C) + tq);
+      fs[0] += v.x; fs[1] += v.y; fs[2] += v.z; fs[3] += v.w;
+      fq[0] += v.x * v.x; fq[1] += v.y * v.y; fq[2] += v.z * v.z; fq[3] += v.w * v.w;
+      if (++cnt == 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s[k] += fs[k]; q[k] += fq[k]; fs[k] = 0; fq[k] = 0; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s[k] += fs[k]; q[k] += fq[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sred[(ty * 2 + 0) * C + tq * 4 + k] = s[k];
+      sred[(ty * 2 + 1) * C + tq * 4 + k] = q[k];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    double a = 0;
+    for (int y = 0; y < nty; ++y) a += sred[y * 2 * C + c];
+    part[(int64_t)blockIdx.x * 2 * C + c] = a;
+  }
+}
+
+__global__ void k_bn_final(const double* __restrict__ part, int blocks, int C, double inv_count,
+                           float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int b = 0; b < blocks; ++b) {
+    s += part[(int64_t)b * 2 * C + c];
+    q += part[(int64_t)b * 2 * C + C + c];
+  }
+  const double m = s * inv_count;
+  double v = q * inv_count - m * m;
+  if (v < 0) v = 0;
+  mean[c] = static_cast<float>(m);
+  var[c] = static_cast<float>(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// out = a*sa + ba (+ b*sb + bb): block output in training mode, where the two tdBN normalisations
+// feeding the membrane shortcut are applied on the fly (models/common.py:1216).  `*_mod`: number of
+// distinct images in the source (N for a T-broadcast tensor, imgs otherwise).
+// ------------------------------------------------------------------------------------------
+__global__ void k_affine_add(const float* __restrict__ a, int64_t a_mod, const float* __restrict__ sa,
+                             const float* __restrict__ ba, const float* __restrict__ b, int64_t b_mod,
+                             const float* __restrict__ sb, const float* __restrict__ bb,
+                             float* __restrict__ out, int64_t imgs, int64_t hwc4, int C) {
+  const int64_t total = imgs * hwc4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t img = i / hwc4, rem = i - img * hwc4;
+    const int c = static_cast<int>((rem * 4) % C);
+    float4 v = reinterpret_cast<const float4*>(a)[(img % a_mod) * hwc4 + rem];
+    if (sa != nullptr) {
+      float4 s = *reinterpret_cast<const float4*>(sa + c), t = *reinterpret_cast<const float4*>(ba + c);
+      v.x = v.x * s.x + t.x; v.y = v.y * s.y + t.y; v.z = v.z * s.z + t.z; v.w = v.w * s.w + t.w;
+    }
+    if (b != nullptr) {
+      float4 u = reinterpret_cast<const float4*>(b)[(img % b_mod) * hwc4 + rem];
+      if (sb != nullptr) {
+        float4 s = *reinterpret_cast<const float4*>(sb + c), t = *reinterpret_cast<const float4*>(bb + c);
+        u.x = u.x * s.x + t.x; u.y = u.y * s.y + t.y; u.z = u.z * s.z + t.z; u.w = u.w * s.w + t.w;
+      }
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Resample into a channel slice of the output: s x s max-pool (MaxPool3d((1,s,s)), common.py:1209),
+// nearest up-sampling by u (Sample, common.py:856-868) or plain copy (Concat, common.py:1764),
+// optionally with a per-channel affine on the source (a pending tdBN normalisation).
+// ------------------------------------------------------------------------------------------
+__global__ void k_resample(const float* __restrict__ in, int64_t in_mod, const float* __restrict__ sc,
+                           const float* __restrict__ sh, float* __restrict__ out, int64_t imgs, int Hi,
+                           int Wi, int C, int Ho, int Wo, int Ctot, int coff, int pool, int up) {
+  const int c4 = C >> 2;
+  const int64_t total = imgs * Ho * Wo * c4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int q = static_cast<int>(i % c4);
+    int64_t p = i / c4;
+    const int wo = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int ho = static_cast<int>(p % Ho);
+    const int64_t img = p / Ho;
+    const float* src = in + ((img % in_mod) * Hi * Wi) * (int64_t)C + q * 4;
+    float4 v;
+    if (pool > 1) {
+      v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      for (int dy = 0; dy < pool; ++dy)
+        for (int dx = 0; dx < pool; ++dx) {
+          float4 u = *reinterpret_cast<const float4*>(src + ((int64_t)(ho * pool + dy) * Wi + (wo * pool + dx)) * C);
+          v.x = fmaxf(v.x, u.x); v.y = fmaxf(v.y, u.y); v.z = fmaxf(v.z, u.z); v.w = fmaxf(v.w, u.w);
+        }
+    } else {
+      v = *reinterpret_cast<const float4*>(src + ((int64_t)(ho / up) * Wi + (wo / up)) * C);
+    }
+    if (sc != nullptr) {
+      // affine AFTER the max is only valid for non-negative scales; callers pass sc only when pool==1
+      float4 s = *reinterpret_cast<const float4*>(sc + q * 4), t = *reinterpret_cast<const float4*>(sh + q * 4);
+      v.x = v.x * s.x + t.x; v.y = v.y * s.y + t.y; v.z = v.z * s.z + t.z; v.w = v.w * s.w + t.w;
+    }
+    *reinterpret_cast<float4*>(out + (((img * Ho + ho) * Wo + wo) * (int64_t)Ctot + coff + q * 4)) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weighted reduction over T: out[n][...] = (sum_t w[t] * x[t][n][...]) / div.  Conv_7 (the learned
+// T->1 Conv3d, common.py:549-562) commutes with Detect's per-step 1x1 conv, so Stack A reduces the
+// real features first; DDetect's mean over T (yolo_snn.py:115-116) uses w = 1, div = T.
+// ------------------------------------------------------------------------------------------
+__global__ void k_tsum(const float* __restrict__ x, const float* __restrict__ w, float div,
+                       float* __restrict__ out, int T, int64_t per_t4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_t4; i += stride) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      float4 v = reinterpret_cast<const float4*>(x)[t * per_t4 + i];
+      const float wt = w ? w[t] : 1.0f;
+      a.x += wt * v.x; a.y += wt * v.y; a.z += wt * v.z; a.w += wt * v.w;
+    }
+    a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stack-A Detect decode (models/yolo.py:110-146).  y: [N][H][W][na*no] (channel = a*no + o).
+// raw: [N][na][H][W][no]; z (eval only): [N][rows_total][no] at row offset row_off.
+// ------------------------------------------------------------------------------------------
+__global__ void k_detect_decode(const float* __restrict__ y, float* __restrict__ raw, float* __restrict__ z,
+                                const float* __restrict__ anchors /*[na][2], grid units*/, float stride_px,
+                                int N, int H, int W, int na, int no, int64_t rows_total, int64_t row_off) {
+  const int64_t total = (int64_t)N * H * W * na * no;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    // iterate in raw-output order so stores coalesce
+    int o = static_cast<int>(i % no);
+    int64_t p = i / no;
+    const int w = static_cast<int>(p % W); p /= W;
+    const int h = static_cast<int>(p % H); p /= H;
+    const int a = static_cast<int>(p % na);
+    const int64_t n = p / na;
+    const float v = y[(((n * H + h) * W + w) * na + a) * (int64_t)no + o];
+    raw[i] = v;
+    if (z != nullptr) {
+      float sg = 1.0f / (1.0f + expf(-v));
+      float r;
+      if (o == 0) r = (sg * 2.0f - 0.5f + static_cast<float>(w)) * stride_px;
+      else if (o == 1) r = (sg * 2.0f - 0.5f + static_cast<float>(h)) * stride_px;
+      else if (o == 2 || o == 3) {
+        float t = sg * 2.0f;
+        r = t * t * (anchors[a * 2 + (o - 2)] * stride_px);
+      } else r = sg;
+      z[(n * rows_total + row_off + ((int64_t)a * H + h) * W + w) * no + o] = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stack-B DDetect decode (models/yolo_snn.py:118-127, common.py:312-323, anchor_generator.py:8-32).
+// box: [N][H][W][64] (4 sides x 16 bins), cls: [N][H][W][nc], both already averaged over T.
+// xs: [N][64+nc][H][W] (reference-shaped raw level output);
+// y (eval): [N][4+nc][A_total] at anchor offset a_off.
+// ------------------------------------------------------------------------------------------
+__global__ void k_ddetect_decode(const float* __restrict__ box, const float* __restrict__ cls,
+                                 float* __restrict__ xs, float* __restrict__ yout, float stride_px, int N,
+                                 int H, int W, int nc, int64_t a_total, int64_t a_off) {
+  const int no = 64 + nc;
+  const int64_t total = (int64_t)N * H * W;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int w = static_cast<int>(i % W);
+    const int h = static_cast<int>((i / W) % H);
+    const int64_t n = i / ((int64_t)W * H);
+    const float* b = box + i * 64;
+    const float* c = cls + i * nc;
+    float d[4];
+    for (int s = 0; s < 4; ++s) {
+      float mx = -INFINITY;
+      for (int k = 0; k < 16; ++k) mx = fmaxf(mx, b[s * 16 + k]);
+      float den = 0.f, num = 0.f;
+      for (int k = 0; k < 16; ++k) {
+        float e = expf(b[s * 16 + k] - mx);
+        den += e;
+        num += e * static_cast<float>(k);
+      }
+      d[s] = num / den;
+    }
+    float* xo = xs + (n * no) * (int64_t)H * W + (int64_t)h * W + w;
+    for (int k = 0; k < 64; ++k) xo[(int64_t)k * H * W] = b[k];
+    for (int k = 0; k < nc; ++k) xo[(int64_t)(64 + k) * H * W] = c[k];
+    if (yout != nullptr) {
+      const float ax = static_cast<float>(w) + 0.5f, ay = static_cast<float>(h) + 0.5f;
+      const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+      float* yo = yout + n * (4 + nc) * a_total + a_off + (int64_t)h * W + w;
+      yo[0] = (x1 + x2) / 2.0f * stride_px;
+      yo[a_total] = (y1 + y2) / 2.0f * stride_px;
+      yo[2 * a_total] = (x2 - x1) * stride_px;
+      yo[3 * a_total] = (y2 - y1) * stride_px;
+      for (int k = 0; k < nc; ++k) yo[(int64_t)(4 + k) * a_total] = 1.0f / (1.0f + expf(-c[k]));
+    }
+  }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int ecsy_nchw_to_nhwc_f32(const float* in, float* out, int64_t imgs, int C, int H, int W, void* stream) {
+  ECSY_CHECK_ARG(in && out && imgs > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
+  ECSY_CHECK_ARG(imgs <= 65535, "nchw_to_nhwc: more than 65535 images per call");
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, static_cast<unsigned>(imgs)), block(32, 8);
+  k_transpose_inner<<<grid, block, 0, STREAM(stream)>>>(in, out, C, H * W);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_nhwc_to_nchw_f32(const float* in, float* out, int64_t imgs, int C, int H, int W, void* stream) {
+  ECSY_CHECK_ARG(in && out && imgs > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad arguments");
+  ECSY_CHECK_ARG(imgs <= 65535, "nhwc_to_nchw: more than 65535 images per call");
+  dim3 grid((C + 31) / 32, (H * W + 31) / 32, static_cast<unsigned>(imgs)), block(32, 8);
+  k_transpose_inner<<<grid, block, 0, STREAM(stream)>>>(in, out, H * W, C);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_spikes_pack(const float* x_nhwc, uint32_t* bits, int64_t pixels, int C, float thresh, void* stream) {
+  ECSY_CHECK_ARG(x_nhwc && bits && pixels > 0 && C > 0 && C % 32 == 0, "spikes_pack: C must be a multiple of 32");
+  const int64_t words = pixels * (C / 32);
+  k_pack<<<grid_for(words, kThreads / 32, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(x_nhwc, bits, words, thresh);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_spikes_unpack(const uint32_t* bits, float* x_nhwc, int64_t pixels, int C, void* stream) {
+  ECSY_CHECK_ARG(x_nhwc && bits && pixels > 0 && C > 0 && C % 32 == 0, "spikes_unpack: C must be a multiple of 32");
+  const int64_t words = pixels * (C / 32);
+  k_unpack<<<grid_for(words, kThreads / 32, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(bits, x_nhwc, words);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+// Internal launchers shared with lif.cu -------------------------------------------------------
+int ecsy_launch_lif_first(const float* x, const float* scale, const float* shift, float* mem, uint32_t* bits,
+                          int64_t pixels, int C, float thresh, cudaStream_t st) {
+  const int64_t n4 = pixels * C / 4;
+  k_lif_first<<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(x, scale, shift, mem, bits, n4, C, thresh);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+int ecsy_launch_lif_step(const float* x, const float* scale, const float* shift, const float* fecs, float* mem,
+                         const uint32_t* bits_prev, uint32_t* bits, int64_t pixels, int C, float thresh,
+                         float decay, cudaStream_t st) {
+  const int64_t n4 = pixels * C / 4;
+  k_lif_step<<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(x, scale, shift, fecs, mem, bits_prev,
+                                                                             bits, n4, C, thresh, decay);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
+                          __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st) {
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  k_spread_dw<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" size_t ecsy_tdbn_stats_ws_bytes(int64_t rows, int C) {
+  int64_t blocks = (rows + 255) / 256;
+  const int64_t cap = (int64_t)ecsy_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<size_t>(blocks) * 2 * C * sizeof(double);
+}
+
+extern "C" int ecsy_tdbn_stats(const float* x, int64_t rows, int C, float* mean, float* var_biased, void* ws,
+                               size_t ws_bytes, void* stream) {
+  ECSY_CHECK_ARG(x && mean && var_biased && rows > 0, "tdbn_stats: bad arguments");
+  ECSY_CHECK_ARG(C % 4 == 0 && C >= 4 && C <= 1024, "tdbn_stats: C=%d must be a multiple of 4 in [4,1024]", C);
+  const size_t need = ecsy_tdbn_stats_ws_bytes(rows, C);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("tdbn_stats: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  const int blocks = static_cast<int>(need / (2 * C * sizeof(double)));
+  const int64_t rpb = (rows + blocks - 1) / blocks;
+  const int nty = kThreads / (C / 4);
+  const size_t smem = static_cast<size_t>(nty) * 2 * C * sizeof(double);
+  ECSY_CUDA(cudaFuncSetAttribute(k_bn_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  k_bn_partial<<<blocks, kThreads, smem, STREAM(stream)>>>(x, rows, C, rpb, static_cast<double*>(ws));
+  ECSY_LAUNCH_CHECK();
+  k_bn_final<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(static_cast<const double*>(ws), blocks, C,
+                                                           1.0 / static_cast<double>(rows), mean, var_biased);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_affine_add(const float* a, int64_t a_imgs, const float* sa, const float* ba, const float* b,
+                               int64_t b_imgs, const float* sb, const float* bb, float* out, int64_t imgs,
+                               int64_t hw, int C, void* stream) {
+  ECSY_CHECK_ARG(a && out && imgs > 0 && hw > 0 && C % 4 == 0, "affine_add: bad arguments");
+  ECSY_CHECK_ARG(a_imgs > 0 && imgs % a_imgs == 0 && (!b || (b_imgs > 0 && imgs % b_imgs == 0)),
+                 "affine_add: source image counts must divide imgs");
+  ECSY_CHECK_ARG((sa == nullptr) == (ba == nullptr) && (sb == nullptr) == (bb == nullptr), "affine_add: scale/shift pairs");
+  const int64_t hwc4 = hw * C / 4;
+  k_affine_add<<<grid_for(imgs * hwc4, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+      a, a_imgs, sa, ba, b, b ? b_imgs : 1, sb, bb, out, imgs, hwc4, C);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_resample(const float* in, int64_t in_imgs, const float* scale, const float* shift, float* out,
+                             int64_t imgs, int Hi, int Wi, int C, int Ctot, int coff, int pool, int up, void* stream) {
+  ECSY_CHECK_ARG(in && out && imgs > 0 && in_imgs > 0 && imgs % in_imgs == 0, "resample: bad image counts");
+  ECSY_CHECK_ARG(C % 4 == 0 && Ctot % 4 == 0 && coff % 4 == 0 && coff + C <= Ctot, "resample: channel slice");
+  ECSY_CHECK_ARG(pool >= 1 && up >= 1 && !(pool > 1 && up > 1), "resample: pool/up");
+  ECSY_CHECK_ARG(!(pool > 1 && scale), "resample: affine with max-pool is not supported");
+  ECSY_CHECK_ARG((scale == nullptr) == (shift == nullptr), "resample: scale/shift pair");
+  const int Ho = pool > 1 ? Hi / pool : Hi * up, Wo = pool > 1 ? Wi / pool : Wi * up;
+  ECSY_CHECK_ARG(Ho > 0 && Wo > 0, "resample: empty output");
+  const int64_t total = imgs * Ho * Wo * (C / 4);
+  k_resample<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+      in, in_imgs, scale, shift, out, imgs, Hi, Wi, C, Ho, Wo, Ctot, coff, pool, up);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_tsum(const float* x, const float* w, float div, float* out, int T, int64_t per_t, void* stream) {
+  ECSY_CHECK_ARG(x && out && T > 0 && per_t > 0 && per_t % 4 == 0 && div != 0.f, "tsum: bad arguments");
+  k_tsum<<<grid_for(per_t / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(x, w, div, out, T, per_t / 4);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_detect_decode(const float* y, float* raw, float* z, const float* anchors, float stride_px, int N,
+                                  int H, int W, int na, int no, int64_t rows_total, int64_t row_off, void* stream) {
+  ECSY_CHECK_ARG(y && raw && N > 0 && H > 0 && W > 0 && na > 0 && no > 4, "detect_decode: bad arguments");
+  ECSY_CHECK_ARG(!z || (anchors && row_off + (int64_t)na * H * W <= rows_total), "detect_decode: z slice");
+  const int64_t total = (int64_t)N * H * W * na * no;
+  k_detect_decode<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+      y, raw, z, anchors, stride_px, N, H, W, na, no, rows_total, row_off);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_ddetect_decode(const float* box, const float* cls, float* xs, float* y, float stride_px, int N,
+                                   int H, int W, int nc, int64_t a_total, int64_t a_off, void* stream) {
+  ECSY_CHECK_ARG(box && cls && xs && N > 0 && H > 0 && W > 0 && nc > 0, "ddetect_decode: bad arguments");
+  ECSY_CHECK_ARG(!y || a_off + (int64_t)H * W <= a_total, "ddetect_decode: y slice");
+  const int64_t total = (int64_t)N * H * W;
+  k_ddetect_decode<<<grid_for(total, 128, ecsy_num_sms() * 8), 128, 0, STREAM(stream)>>>(box, cls, xs, y, stride_px, N, H,
+                                                                                      W, nc, a_total, a_off);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}

@@ -1,0 +1,76 @@
+// ECS-LIF forward (mem_update, models/common.py:236-309) as a per-timestep pipeline:
+//   step 0        : k_lif_first            mem_0 = x_0, s_0 = mem_0 > thresh          (streaming)
+//   step t -> t+1 : k_spread_dw            A = dw3x3(s_t) + b as bf16 hi[/lo]          (streaming)
+//                   k_umma_gemm<kEpiEcs>   e_t = alpha*(A*Wpw^T + b) + kappa*e_{t-1};  f_t = beta*tanh(e_t);
+//                                          mem_{t+1} = mem_t*decay*(1-s_t) + x_{t+1} + f_t; s_{t+1}
+// Spikes leave as bit-packed words; membrane / ECS state live in the caller-provided workspace.
+#include "ecsy_common.cuh"
+#include "../../include/ecsy.h"
+#include "umma_gemm.h"
+
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+extern "C" size_t ecsy_lif_ecs_ws_bytes(int T, int64_t N, int H, int W, int C, int splits) {
+  const size_t mc = static_cast<size_t>(N) * H * W * C;
+  size_t b = 512;
+  b += 2 * align256(mc * 4);                    // mem, ecs
+  b += static_cast<size_t>(splits) * align256(mc * 2);  // dw output planes
+  (void)T;
+  return b;
+}
+
+extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
+                                const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b,
+                                int splits, uint32_t* spikes, float* mem_save, int T, int64_t N, int H, int W, int C,
+                                float thresh, float decay, float alpha, float beta, float kappa, void* ws,
+                                size_t ws_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ECSY_CHECK_ARG(x && spikes && T >= 1 && N > 0 && H > 0 && W > 0, "lif_ecs_fwd: bad arguments");
+  ECSY_CHECK_ARG(C % 64 == 0, "lif_ecs_fwd: C=%d must be a multiple of 64", C);
+  ECSY_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "lif_ecs_fwd: scale/shift pair");
+  ECSY_CHECK_ARG(splits == 1 || splits == 2, "lif_ecs_fwd: splits must be 1 or 2");
+  ECSY_CHECK_ARG(T == 1 || (dw_w && dw_b && pw_packed && pw_b), "lif_ecs_fwd: spread weights missing");
+  const int64_t M = N * H * W;
+  ECSY_CHECK_ARG(N * H < (1LL << 31) && M * (C / 8) < (1LL << 40), "lif_ecs_fwd: tensor too large");
+  const size_t mc = static_cast<size_t>(M) * C;
+  const size_t need = ecsy_lif_ecs_ws_bytes(T, N, H, W, C, splits);
+  if (T > 1 && (ws == nullptr || ws_bytes < need)) {
+    ecsy_set_error("lif_ecs_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  float* mem = reinterpret_cast<float*>(p); p += align256(mc * 4);
+  float* ecs = reinterpret_cast<float*>(p); p += align256(mc * 4);
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(p); p += align256(mc * 2);
+  __nv_bfloat16* a_lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
+  const int64_t words = M * (C / 32);
+
+  float* mem0 = mem_save ? mem_save : (T > 1 ? mem : nullptr);
+  int rc = ecsy_launch_lif_first(x, in_scale, in_shift, mem0, spikes, M, C, thresh, st);
+  if (rc) return rc;
+  for (int t = 0; t + 1 < T; ++t) {
+    rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, a_hi, a_lo, (int)N, H, W, C, st);
+    if (rc) return rc;
+    EcsStepArgs s{};
+    s.x_next = x + (t + 1) * x_tstride;
+    s.in_scale = in_scale; s.in_shift = in_shift; s.pw_b = pw_b;
+    if (mem_save) {
+      // keep every membrane for the backward pass: read step t, write step t+1
+      s.mem = mem_save + (size_t)t * mc;
+      s.mem_save = mem_save + (size_t)(t + 1) * mc;
+      s.store_mem = 0;
+      s.ecs = ecs;
+    } else {
+      s.mem = mem; s.mem_save = nullptr; s.ecs = ecs;
+      s.store_mem = (t + 2 < T) ? 1 : 0;
+    }
+    s.store_ecs = (t + 2 < T) ? 1 : 0;
+    s.bits_t = spikes + t * words;
+    s.bits_next = spikes + (t + 1) * words;
+    s.first = (t == 0) ? 1 : 0;
+    s.thresh = thresh; s.decay = decay; s.alpha = alpha; s.beta = beta; s.kappa = kappa;
+    rc = ecsy_umma_ecs_step(a_hi, a_lo, M, C, pw_packed, splits, s, st);
+    if (rc) return rc;
+  }
+  return ECSY_OK;
+}

@@ -1,0 +1,626 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine of the spiking hot path (sm_100a).
+//
+// One persistent, warp-specialised kernel template computes D[128 x BN] tiles as
+//     D = A[128 x K] * B[BN x K]^T      (bf16 operands, fp32 accumulation in TMEM)
+// with
+//   A_MODE = kASpikes : A rows are output pixels of a convolution over BIT-PACKED spikes
+//                       ([imgs][H][W][Cin/32] uint32).  Expander warps stage the tile's spike patch
+//                       (with halo, zero padding) in shared memory once and materialise the bf16
+//                       {0,1} operand tile for every (tap, 64-channel slab) K block directly in the
+//                       128-byte-swizzled UMMA layout -- spikes never exist as bf16/fp32 in HBM.
+//                       (Snn_Conv2d on spikes, models/common.py:593-624.)
+//   A_MODE = kATma    : A is a row-major bf16 matrix [M][K] in HBM loaded by TMA (ECS point-wise
+//                       spread, im2col'ed real-input convolutions).
+//   B                 : packed weights [B_SPLIT*Cout][K] bf16 (hi plane, optional lo residual plane),
+//                       loaded by TMA.  With B_SPLIT=2 (and A_SPLIT=2 for real-valued A) the products
+//                       A_hi*B_hi + A_lo*B_hi + A_hi*B_lo reproduce fp32 weights to ~2^-17.
+//   EPI = kEpiConv    : y = acc*scale[c] + shift[c] (+ residual) -> fp32 NHWC   (tdBN folded)
+//   EPI = kEpiEcs     : ECS-LIF step: ecs/tanh feedback, membrane charge, threshold, bit-packed
+//                       spikes of step t+1 (models/common.py:263-281).
+//
+// Warp roles: 0-3 epilogue (TMEM lane quarter = warp id), 4 TMA producer, 5 MMA issuer + TMEM
+// allocator, 6-9 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
+// full/empty mbarriers; two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of
+// tile i+1.
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "ecsy_common.cuh"
+#include "../../include/ecsy.h"
+#include "umma_gemm.h"
+
+using namespace ecsy;
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct SharedCtl {
+  uint64_t full_a[kMaxStages];
+  uint64_t full_b[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+// ---- epilogue parameter blocks ----
+struct EpiConv {
+  float* out;             // [rows][ldc]
+  const float* scale;     // [Cout] or null
+  const float* shift;     // [Cout] or null
+  const float* residual;  // [res_rows][ldc] or null
+  int64_t res_rows;       // rows in residual (T-broadcast sources repeat)
+  int ldc;                // Cout
+};
+
+struct EpiEcs {
+  const float* x_next;     // [M][C] input current of step t+1
+  const float* in_scale;   // optional folded tdBN on x
+  const float* in_shift;
+  const float* pw_b;       // [C]
+  float* mem;              // [M][C] membrane of step t (in) -> t+1 (out)
+  float* ecs;              // [M][C] ECS state e_{t-1} (in) -> e_t (out)
+  const uint32_t* bits_t;  // spikes of step t   [M][C/32]
+  uint32_t* bits_next;     // spikes of step t+1 [M][C/32]
+  float* mem_save;         // optional: membrane of step t+1 kept for the backward pass
+  int C;
+  int first;               // e_{t-1} == 0 (t == 0): do not read ecs
+  int store_mem;           // another step follows: write the membrane back in place
+  int store_ecs;           // another step follows: write the ECS state back
+  float thresh, decay, alpha, beta, kappa;
+};
+
+struct SpikeGeom {
+  const uint32_t* bits;  // [imgs][H][W][Cw]
+  int imgs, H, W, Cw;    // Cw = Cin/32
+  int Ho, Wo;
+  int kh, kw, stride, pad;
+  int tn_b, th_b, tw_b;              // tile box (powers of two, product 128)
+  int tn_sh, th_sh, tw_sh;           // log2 of the above
+  int tiles_h, tiles_w;              // tiles per image dimension (tiles over imgs = m_tiles/(tiles_h*tiles_w))
+  int Hp, Wp, PP;                    // patch rows/cols per image, patch pixels per tile
+  int nslab;                         // Cin/64
+};
+
+struct GemmArgs {
+  int m_tiles, n_tiles, kb_total, stages;
+  int64_t M;       // valid rows (kATma) / unused (kASpikes)
+  uint32_t patch_off;  // byte offset of the patch buffer in dynamic smem
+};
+
+template <int EPI>
+struct EpiSel;
+template <>
+struct EpiSel<0> { using type = EpiConv; };
+template <>
+struct EpiSel<1> { using type = EpiEcs; };
+
+constexpr int kATma = 0, kASpikes = 1;
+constexpr int kEpiConv = 0, kEpiEcs = 1;
+
+__device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
+  // bit0 -> low bf16 (1.0 = 0x3F80), bit1 -> high bf16
+  return ((x & 1u) | ((x & 2u) << 15)) * 0x3F80u;
+}
+
+template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
+__global__ void __launch_bounds__(A_MODE == kASpikes ? 320 : 192, 1)
+k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+            const __grid_constant__ CUtensorMap tm_b, const GemmArgs g, const SpikeGeom sg,
+            const typename EpiSel<EPI>::type ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled operand tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = A_SPLIT * kATileBytes + B_SPLIT * kBTileBytes;
+  constexpr int kTmemCols = 2 * BN;  // two accumulator buffers: 128, 256 or 512 columns
+  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + (size_t)g.stages * kStageBytes);
+  uint32_t* patch = reinterpret_cast<uint32_t*>(smem + g.patch_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_b);
+    if (A_MODE == kATma) {
+      tma_prefetch_desc(&tm_a0);
+      if (A_SPLIT == 2) tma_prefetch_desc(&tm_a1);
+    }
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&ctl->full_a[s], 128);
+      mbar_init(&ctl->full_b[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->tmem_full[b], 1);
+      mbar_init(&ctl->tmem_empty[b], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 4) {
+    // =============================== TMA producer ===============================
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* st = smem + (size_t)stage * kStageBytes;
+          constexpr uint32_t tx = (A_MODE == kATma ? A_SPLIT * kATileBytes : 0) + B_SPLIT * kBTileBytes;
+          mbar_arrive_expect_tx(&ctl->full_b[stage], tx);
+          if (A_MODE == kATma) {
+            tma_load_2d(st, &tm_a0, &ctl->full_b[stage], kb * 64, m_tile * 128);
+            if (A_SPLIT == 2) tma_load_2d(st + kATileBytes, &tm_a1, &ctl->full_b[stage], kb * 64, m_tile * 128);
+          }
+#pragma unroll
+          for (int bs = 0; bs < B_SPLIT; ++bs)
+            tma_load_2d(st + A_SPLIT * kATileBytes + bs * kBTileBytes, &tm_b, &ctl->full_b[stage], kb * 64,
+                        bs * (g.n_tiles * BN) + n_tile * BN);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[buf], bphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        mbar_wait(&ctl->full_b[stage], phase);
+        if (A_MODE == kASpikes) mbar_wait(&ctl->full_a[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint32_t b_addr = a_addr + A_SPLIT * kATileBytes;
+          uint32_t acc = kb > 0 ? 1u : 0u;
+#pragma unroll
+          for (int combo = 0; combo < A_SPLIT + B_SPLIT - 1; ++combo) {
+            // combos: (A0,B0) [, (A1,B0)] [, (A0,B1)]  -- the lo*lo term is below fp32 resolution
+            const int as = (A_SPLIT == 2 && combo == 1) ? 1 : 0;
+            const int bs = (B_SPLIT == 2 && combo == A_SPLIT) ? 1 : 0;
+            const uint64_t da = umma_desc_sw128(a_addr + as * kATileBytes);
+            const uint64_t db = umma_desc_sw128(b_addr + bs * kBTileBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row (encoded >> 4)
+              umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&ctl->empty[stage]);
+          if (kb == g.kb_total - 1) umma_commit(&ctl->tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 6) {
+    // =============================== spike expanders ===============================
+    if constexpr (A_MODE == kASpikes) {
+      const int r = threadIdx.x - 192;  // tile row 0..127
+      const int w_l = r & (sg.tw_b - 1);
+      const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
+      const int n_l = r >> (sg.tw_sh + sg.th_sh);
+      const int pp_base = (n_l * sg.Hp + h_l * sg.stride) * sg.Wp + w_l * sg.stride;
+      const int Cw = sg.Cw;
+      const int patch_words = sg.PP * Cw;
+      const int tiles_hw = sg.tiles_h * sg.tiles_w;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / g.n_tiles;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        const int img0 = tn * sg.tn_b;
+        const int hi0 = th * sg.th_b * sg.stride - sg.pad;
+        const int wi0 = tw * sg.tw_b * sg.stride - sg.pad;
+        // all expanders finished reading the previous tile's patch
+        named_bar_sync(1, 128);
+        for (int base = 0; base < patch_words; base += 4 * 128) {
+          // four independent global loads in flight per thread before the dependent smem stores
+          uint32_t v[4];
+          int dst[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * 128 + r;
+            v[u] = 0;
+            dst[u] = -1;
+            if (idx < patch_words) {
+              const int cw = idx % Cw;
+              const int pp = idx / Cw;
+              const int wp = pp % sg.Wp;
+              const int t2 = pp / sg.Wp;
+              const int hp = t2 % sg.Hp;
+              const int nl = t2 / sg.Hp;
+              const int img = img0 + nl, hi = hi0 + hp, wi = wi0 + wp;
+              if (img < sg.imgs && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
+                v[u] = __ldg(sg.bits + (((int64_t)img * sg.H + hi) * sg.W + wi) * Cw + cw);
+              dst[u] = (((cw >> 1) * sg.PP + pp) << 1) + (cw & 1);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (dst[u] >= 0) patch[dst[u]] = v[u];
+        }
+        named_bar_sync(1, 128);
+        int slab = 0, ky = 0, kx = 0;
+        for (int kb = 0; kb < g.kb_total; ++kb) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          const int pp = pp_base + ky * sg.Wp + kx;
+          const uint2 wd = *reinterpret_cast<const uint2*>(patch + ((slab * sg.PP + pp) << 1));
+          uint8_t* row = smem + (size_t)stage * kStageBytes + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t byte = ((j < 4 ? wd.x : wd.y) >> (8 * (j & 3))) & 0xFFu;
+            uint4 o;
+            o.x = bits2_to_bf16x2(byte);
+            o.y = bits2_to_bf16x2(byte >> 2);
+            o.z = bits2_to_bf16x2(byte >> 4);
+            o.w = bits2_to_bf16x2(byte >> 6);
+            *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&ctl->full_a[stage]);
+          if (++slab == sg.nslab) {
+            slab = 0;
+            if (++kx == sg.kw) { kx = 0; ++ky; }
+          }
+          if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-3) ===============================
+    const int row = warp * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      // output row of this thread
+      int64_t pix;
+      bool valid;
+      if (A_MODE == kASpikes) {
+        const int tiles_hw = sg.tiles_h * sg.tiles_w;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        const int w_l = row & (sg.tw_b - 1);
+        const int h_l = (row >> sg.tw_sh) & (sg.th_b - 1);
+        const int n_l = row >> (sg.tw_sh + sg.th_sh);
+        const int img = tn * sg.tn_b + n_l, ho = th * sg.th_b + h_l, wo = tw * sg.tw_b + w_l;
+        valid = img < sg.imgs && ho < sg.Ho && wo < sg.Wo;
+        pix = ((int64_t)img * sg.Ho + ho) * sg.Wo + wo;
+      } else {
+        pix = (int64_t)m_tile * 128 + row;
+        valid = pix < g.M;
+      }
+      mbar_wait(&ctl->tmem_full[buf], bphase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c0, v);
+        tmem_ld_wait();
+        const int n0 = n_tile * BN + c0;
+        if constexpr (EPI == kEpiConv) {
+          const EpiConv& e = ep;
+          if (valid) {
+            float* dst = e.out + pix * e.ldc + n0;
+            const float* res = e.residual ? e.residual + (pix % e.res_rows) * e.ldc + n0 : nullptr;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              if (e.scale != nullptr) {
+                const float4 s = *reinterpret_cast<const float4*>(e.scale + n0 + 4 * q);
+                const float4 b = *reinterpret_cast<const float4*>(e.shift + n0 + 4 * q);
+                o.x = fmaf(o.x, s.x, b.x); o.y = fmaf(o.y, s.y, b.y);
+                o.z = fmaf(o.z, s.z, b.z); o.w = fmaf(o.w, s.w, b.w);
+              }
+              if (res != nullptr) {
+                const float4 rr = *reinterpret_cast<const float4*>(res + 4 * q);
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              }
+              *reinterpret_cast<float4*>(dst + 4 * q) = o;
+            }
+          }
+        } else {
+          const EpiEcs& e = ep;
+          if (valid) {
+            const int64_t off = pix * e.C + n0;
+            const uint32_t sprev = e.bits_t[pix * (e.C >> 5) + (n0 >> 5)];
+            uint32_t snext = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 xv = *reinterpret_cast<const float4*>(e.x_next + off + 4 * q);
+              if (e.in_scale != nullptr) {
+                const float4 s = *reinterpret_cast<const float4*>(e.in_scale + n0 + 4 * q);
+                const float4 b = *reinterpret_cast<const float4*>(e.in_shift + n0 + 4 * q);
+                xv.x = add_rn(mul_rn(xv.x, s.x), b.x); xv.y = add_rn(mul_rn(xv.y, s.y), b.y);
+                xv.z = add_rn(mul_rn(xv.z, s.z), b.z); xv.w = add_rn(mul_rn(xv.w, s.w), b.w);
+              }
+              const float4 mv = *reinterpret_cast<const float4*>(e.mem + off + 4 * q);
+              float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!e.first) ev = *reinterpret_cast<const float4*>(e.ecs + off + 4 * q);
+              const float4 pb = *reinterpret_cast<const float4*>(e.pw_b + n0 + 4 * q);
+              float xin[4] = {xv.x, xv.y, xv.z, xv.w};
+              float mo[4] = {mv.x, mv.y, mv.z, mv.w};
+              float eo[4] = {ev.x, ev.y, ev.z, ev.w};
+              float bb[4] = {pb.x, pb.y, pb.z, pb.w};
+              float mn[4], en[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float s_acc = add_rn(__uint_as_float(v[4 * q + k]), bb[k]);       // spread(spike)
+                en[k] = add_rn(mul_rn(e.alpha, s_acc), mul_rn(e.kappa, eo[k]));        // common.py:277
+                const float fecs = mul_rn(e.beta, tanhf(en[k]));                       // common.py:278
+                const float keep = ((sprev >> (4 * q + k)) & 1u) ? 0.f : 1.f;          // 1 - spike
+                mn[k] = add_rn(add_rn(mul_rn(mul_rn(mo[k], e.decay), keep), xin[k]), fecs);  // :306-309
+                snext |= (mn[k] > e.thresh ? 1u : 0u) << (4 * q + k);
+              }
+              if (e.store_mem)
+                *reinterpret_cast<float4*>(e.mem + off + 4 * q) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+              if (e.store_ecs)
+                *reinterpret_cast<float4*>(e.ecs + off + 4 * q) = make_float4(en[0], en[1], en[2], en[3]);
+              if (e.mem_save != nullptr)
+                *reinterpret_cast<float4*>(e.mem_save + off + 4 * q) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+            }
+            e.bits_next[pix * (e.C >> 5) + (n0 >> 5)] = snext;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&ctl->tmem_empty[buf]);
+    }
+  }
+
+  // teardown: everyone done with TMEM before the allocating warp frees it
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+std::mutex g_tm_mu;
+std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> g_tm_cache;
+
+}  // namespace
+
+// 2-D bf16 row-major [rows][cols] tensor map with a {64, box_rows} box, 128-byte swizzle, zero OOB fill.
+int ecsy_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out) {
+  ECSY_CHECK_ARG(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: pointer must be 16-byte aligned");
+  ECSY_CHECK_ARG(cols % 8 == 0 && box_rows >= 1 && box_rows <= 256, "tensor map: cols %% 8, box rows <= 256");
+  auto key = std::make_tuple(ptr, rows, cols, box_rows);
+  {
+    std::lock_guard<std::mutex> lk(g_tm_mu);
+    auto it = g_tm_cache.find(key);
+    if (it != g_tm_cache.end()) {
+      *out = it->second;
+      return ECSY_OK;
+    }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    ecsy_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECSY_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ecsy_set_error("cuTensorMapEncodeTiled failed with %d (rows=%llu cols=%llu box=%u)", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return ECSY_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  if (g_tm_cache.size() > 4096) g_tm_cache.clear();
+  g_tm_cache[key] = *out;
+  return ECSY_OK;
+}
+
+namespace {
+
+constexpr int kSmemLimit = 227 * 1024;
+
+template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
+int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmArgs g, const SpikeGeom& sg,
+               const typename EpiSel<EPI>::type& ep, int patch_bytes, cudaStream_t st) {
+  constexpr int stage_bytes = A_SPLIT * kATileBytes + B_SPLIT * BN * 128;
+  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 64 + patch_bytes;
+  int stages = (kSmemLimit - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    ecsy_set_error("umma gemm: shared memory budget allows only %d stage(s) (patch %d bytes)", stages, patch_bytes);
+    return ECSY_ERR_UNSUPPORTED;
+  }
+  g.stages = stages;
+  const uint32_t ctl_off = (uint32_t)stages * stage_bytes;
+  g.patch_off = (ctl_off + (uint32_t)sizeof(SharedCtl) + 63u) & ~63u;
+  const int smem = 1024 + (int)g.patch_off + patch_bytes;
+  auto kern = k_umma_gemm<BN, A_MODE, A_SPLIT, B_SPLIT, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_done = true;
+  }
+  int grid = g.m_tiles * g.n_tiles;
+  const int sms = ecsy_num_sms();
+  if (grid > sms) grid = sms;
+  kern<<<grid, A_MODE == kASpikes ? 320 : 192, smem, st>>>(a0, a1, b, g, sg, ep);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+template <int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
+int launch_bn(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmArgs& g,
+              const SpikeGeom& sg, const typename EpiSel<EPI>::type& ep, int patch_bytes, cudaStream_t st) {
+  switch (BN) {
+    case 64: return launch_one<64, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
+    case 128: return launch_one<128, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
+    case 256: return launch_one<256, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
+  }
+  ecsy_set_error("umma gemm: unsupported BN=%d", BN);
+  return ECSY_ERR_UNSUPPORTED;
+}
+
+int ilog2(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+}  // namespace
+
+int ecsy_pick_bn(int cout, int splits) {
+  // wide tiles amortise the A expansion; the split-weight mode doubles the B tile, so cap at 128
+  const int cap = splits == 2 ? 128 : 256;
+  for (int bn = cap; bn >= 64; bn >>= 1)
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
+// Spike convolution: out[imgs][Ho][Wo][Cout] = conv(spikes, W) (*scale + shift) (+ residual)
+int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits, float* out, const float* scale,
+                         const float* shift, const float* residual, int64_t res_imgs, int imgs, int H, int W, int Cin,
+                         int Cout, int k, int stride, int pad, cudaStream_t st) {
+  ECSY_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "spike_conv: Cin=%d must be a multiple of 64", Cin);
+  const int BN = ecsy_pick_bn(Cout, splits);
+  ECSY_CHECK_ARG(BN != 0, "spike_conv: Cout=%d must be a multiple of 64", Cout);
+  ECSY_CHECK_ARG(splits == 1 || splits == 2, "spike_conv: splits must be 1 or 2");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  ECSY_CHECK_ARG(Ho > 0 && Wo > 0, "spike_conv: empty output");
+  // choose the 128-pixel tile box (tn, th, tw): least padding waste, then widest rows, within the patch budget
+  SpikeGeom sg{};
+  double best = 1e30;
+  const int Cw = Cin / 32;
+  for (int tw = 1; tw <= 128; tw <<= 1)
+    for (int th = 1; th * tw <= 128; th <<= 1) {
+      const int tn = 128 / (tw * th);
+      const int64_t cov = (int64_t)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th * ((imgs + tn - 1) / tn) * tn;
+      const int Hp = (th - 1) * stride + k, Wp = (tw - 1) * stride + k;
+      const int64_t patch_bytes = (int64_t)tn * Hp * Wp * Cw * 4;
+      if (patch_bytes > 72 * 1024) continue;
+      const double score = (double)cov * (1.0 + 1e-3 * (double)patch_bytes / (128.0 * Cw * 4)) - 1e-6 * tw;
+      if (score < best) {
+        best = score;
+        sg.tn_b = tn; sg.th_b = th; sg.tw_b = tw;
+        sg.Hp = Hp; sg.Wp = Wp; sg.PP = tn * Hp * Wp;
+      }
+    }
+  ECSY_CHECK_ARG(best < 1e30, "spike_conv: no tile shape fits the shared-memory patch budget");
+  sg.bits = bits; sg.imgs = imgs; sg.H = H; sg.W = W; sg.Cw = Cw; sg.Ho = Ho; sg.Wo = Wo;
+  sg.kh = k; sg.kw = k; sg.stride = stride; sg.pad = pad;
+  sg.tn_sh = ilog2(sg.tn_b); sg.th_sh = ilog2(sg.th_b); sg.tw_sh = ilog2(sg.tw_b);
+  sg.tiles_h = (Ho + sg.th_b - 1) / sg.th_b; sg.tiles_w = (Wo + sg.tw_b - 1) / sg.tw_b;
+  sg.nslab = Cin / 64;
+  GemmArgs g{};
+  g.m_tiles = ((imgs + sg.tn_b - 1) / sg.tn_b) * sg.tiles_h * sg.tiles_w;
+  g.n_tiles = Cout / BN;
+  g.kb_total = k * k * sg.nslab;
+  g.M = 0;
+  const int K = k * k * Cin;
+  CUtensorMap tb, dummy{};
+  int rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)splits * Cout, (uint64_t)K, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout};
+  const int patch_bytes = sg.PP * Cw * 4;
+  if (splits == 1) return launch_bn<kASpikes, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
+  return launch_bn<kASpikes, 1, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
+}
+
+// Dense GEMM on a bf16 A matrix (hi [+ lo]) : out[M][Cout] = A * W^T (*scale + shift) (+ residual)
+int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
+                    int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
+                    cudaStream_t st) {
+  ECSY_CHECK_ARG(K % 64 == 0 && M > 0, "dense gemm: K=%d must be a multiple of 64", K);
+  const int BN = ecsy_pick_bn(Cout, splits);
+  ECSY_CHECK_ARG(BN != 0, "dense gemm: Cout=%d must be a multiple of 64", Cout);
+  ECSY_CHECK_ARG((splits == 2) == (a_lo != nullptr), "dense gemm: lo plane required iff splits == 2");
+  CUtensorMap ta0, ta1{}, tb;
+  int rc = ecsy_tensor_map_bf16(a_hi, (uint64_t)M, (uint64_t)K, 128, &ta0);
+  if (rc) return rc;
+  if (a_lo) {
+    rc = ecsy_tensor_map_bf16(a_lo, (uint64_t)M, (uint64_t)K, 128, &ta1);
+    if (rc) return rc;
+  }
+  rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)splits * Cout, (uint64_t)K, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  GemmArgs g{};
+  g.m_tiles = (int)((M + 127) / 128);
+  g.n_tiles = Cout / BN;
+  g.kb_total = K / 64;
+  g.M = M;
+  SpikeGeom sg{};
+  EpiConv e{out, scale, shift, residual, residual ? res_rows : M, Cout};
+  if (splits == 1) return launch_bn<kATma, 1, 1, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+  return launch_bn<kATma, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+}
+
+// One fused ECS-LIF step: point-wise spread GEMM + feedback + membrane update + threshold.
+int ecsy_umma_ecs_step(const void* a_hi, const void* a_lo, int64_t M, int C, const void* pw_packed, int splits,
+                       const EcsStepArgs& s, cudaStream_t st) {
+  ECSY_CHECK_ARG(C % 64 == 0 && M > 0, "ecs step: C=%d must be a multiple of 64", C);
+  const int BN = ecsy_pick_bn(C, splits);
+  ECSY_CHECK_ARG((splits == 2) == (a_lo != nullptr), "ecs step: lo plane required iff splits == 2");
+  CUtensorMap ta0, ta1{}, tb;
+  int rc = ecsy_tensor_map_bf16(a_hi, (uint64_t)M, (uint64_t)C, 128, &ta0);
+  if (rc) return rc;
+  if (a_lo) {
+    rc = ecsy_tensor_map_bf16(a_lo, (uint64_t)M, (uint64_t)C, 128, &ta1);
+    if (rc) return rc;
+  }
+  rc = ecsy_tensor_map_bf16(pw_packed, (uint64_t)splits * C, (uint64_t)C, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  GemmArgs g{};
+  g.m_tiles = (int)((M + 127) / 128);
+  g.n_tiles = C / BN;
+  g.kb_total = C / 64;
+  g.M = M;
+  SpikeGeom sg{};
+  EpiEcs e{s.x_next, s.in_scale, s.in_shift, s.pw_b, s.mem, s.ecs, s.bits_t, s.bits_next, s.mem_save, C,
+           s.first, s.store_mem, s.store_ecs, s.thresh, s.decay, s.alpha, s.beta, s.kappa};
+  if (splits == 1) return launch_bn<kATma, 1, 1, kEpiEcs>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+  return launch_bn<kATma, 2, 2, kEpiEcs>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+}

@@ -1,0 +1,41 @@
+// Internal (non-ABI) interface of the tcgen05 GEMM engine, shared between translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct EcsStepArgs {
+  const float* x_next;
+  const float* in_scale;
+  const float* in_shift;
+  const float* pw_b;
+  float* mem;
+  float* ecs;
+  const uint32_t* bits_t;
+  uint32_t* bits_next;
+  float* mem_save;
+  int first;
+  int store_mem;
+  int store_ecs;
+  float thresh, decay, alpha, beta, kappa;
+};
+
+int ecsy_pick_bn(int cout, int splits);
+int ecsy_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out);
+int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits, float* out, const float* scale,
+                         const float* shift, const float* residual, int64_t res_imgs, int imgs, int H, int W, int Cin,
+                         int Cout, int k, int stride, int pad, cudaStream_t st);
+int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
+                    int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
+                    cudaStream_t st);
+int ecsy_umma_ecs_step(const void* a_hi, const void* a_lo, int64_t M, int C, const void* pw_packed, int splits,
+                       const EcsStepArgs& s, cudaStream_t st);
+
+// elementwise.cu launchers used by lif.cu
+int ecsy_launch_lif_first(const float* x, const float* scale, const float* shift, float* mem, uint32_t* bits,
+                          int64_t pixels, int C, float thresh, cudaStream_t st);
+int ecsy_launch_lif_step(const float* x, const float* scale, const float* shift, const float* fecs, float* mem,
+                         const uint32_t* bits_prev, uint32_t* bits, int64_t pixels, int C, float thresh, float decay,
+                         cudaStream_t st);
+int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
+                          __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st);

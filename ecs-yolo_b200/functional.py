@@ -1,0 +1,338 @@
+"""Tensor-level host wrappers over the C ABI (include/ecsy.h).
+
+PyTorch is plumbing here: device memory (caching allocator), streams, tiny [C]-vector math.  Every
+heavy operation is one C-ABI call into libecsy.so; nothing falls back to torch ops or the CPU.
+
+Internal layout: real activations are fp32 NHWC ``[Tp, N, H, W, C]`` with Tp == T or
+Tp == 1 (a T-broadcast tensor: the direct-coded image repeats every timestep, models/yolo.py:248-251);
+spikes are bit-packed int32 ``[T, N, H, W, C/32]``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+# models/common.py:37-39 -- module-level "config" of the reference, read at call time
+thresh = 0.5
+lens = 0.5
+decay = 0.25
+
+_state = {"splits": 2}
+
+
+def set_precision(mode: str) -> None:
+    """'parity': weights as bf16 hi+lo pairs (2 MMAs, ~fp32 weights; spikes are exact in bf16);
+    'fast': single bf16 plane."""
+    if mode not in ("parity", "fast"):
+        raise ValueError(mode)
+    _state["splits"] = 2 if mode == "parity" else 1
+
+
+def get_splits() -> int:
+    return _state["splits"]
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda):
+            raise RuntimeError("ecs-yolo_b200 operators need CUDA tensors: there is no CPU fallback")
+
+
+class Act:
+    """Real-valued activation in the internal NHWC layout."""
+    __slots__ = ("data", "T")
+
+    def __init__(self, data: torch.Tensor, T: int):
+        assert data.dim() == 5 and data.dtype == torch.float32 and data.is_contiguous()
+        assert data.shape[0] in (1, T)
+        self.data, self.T = data, T
+
+    Tp = property(lambda s: s.data.shape[0])
+    N = property(lambda s: s.data.shape[1])
+    H = property(lambda s: s.data.shape[2])
+    W = property(lambda s: s.data.shape[3])
+    C = property(lambda s: s.data.shape[4])
+    imgs = property(lambda s: s.T * s.data.shape[1])
+    src_imgs = property(lambda s: s.data.shape[0] * s.data.shape[1])
+
+    @property
+    def tstride(self) -> int:
+        return 0 if (self.Tp == 1 and self.T > 1) else self.N * self.H * self.W * self.C
+
+    def to_ref(self) -> torch.Tensor:
+        """Reference-shaped logical view [T, N, C, H, W] over the NHWC memory (no copy)."""
+        v = self.data.permute(0, 1, 4, 2, 3)
+        return v.expand(self.T, -1, -1, -1, -1) if self.Tp != self.T else v
+
+    @staticmethod
+    def from_ref(x: torch.Tensor) -> "Act":
+        """Accepts a reference tensor [T, N, C, H, W]; zero-copy when it already is an NHWC view."""
+        _chk_cuda(x)
+        if x.dim() != 5:
+            raise ValueError(f"expected [T,N,C,H,W], got {tuple(x.shape)}")
+        T = x.shape[0]
+        x = x.float() if x.dtype != torch.float32 else x
+        src = x[:1] if (x.stride(0) == 0 and T > 1) else x
+        nhwc = src.permute(0, 1, 3, 4, 2)
+        if nhwc.is_contiguous():
+            return Act(nhwc, T)
+        src = src.contiguous()
+        Tp, N, Cc, H, W = src.shape
+        out = torch.empty(Tp, N, H, W, Cc, device=x.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().ecsy_nchw_to_nhwc_f32(_p(src), _p(out), Tp * N, Cc, H, W, _st()), "nchw_to_nhwc")
+        return Act(out, T)
+
+    def full(self) -> "Act":
+        """Materialise a T-broadcast tensor."""
+        if self.Tp == self.T:
+            return self
+        return Act(self.data.expand(self.T, -1, -1, -1, -1).contiguous(), self.T)
+
+
+class Spikes:
+    """Bit-packed spike train [T, N, H, W, C/32] (int32 words)."""
+    __slots__ = ("bits", "C")
+
+    def __init__(self, bits: torch.Tensor, C: int):
+        self.bits, self.C = bits, C
+
+    T = property(lambda s: s.bits.shape[0])
+    N = property(lambda s: s.bits.shape[1])
+    H = property(lambda s: s.bits.shape[2])
+    W = property(lambda s: s.bits.shape[3])
+
+    def to_act(self) -> Act:
+        T, N, H, W, _ = self.bits.shape
+        out = torch.empty(T, N, H, W, self.C, device=self.bits.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().ecsy_spikes_unpack(_p(self.bits), _p(out), T * N * H * W, self.C, _st()), "spikes_unpack")
+        return Act(out, T)
+
+    @staticmethod
+    def from_act(a: Act, th: Optional[float] = None) -> "Spikes":
+        a = a.full()
+        bits = torch.empty(a.T, a.N, a.H, a.W, a.C // 32, device=a.data.device, dtype=torch.int32)
+        _cabi.check(_cabi.lib().ecsy_spikes_pack(_p(a.data), _p(bits), a.T * a.N * a.H * a.W, a.C,
+                                                 thresh if th is None else th, _st()), "spikes_pack")
+        return Spikes(bits, a.C)
+
+
+# ------------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor, splits: int) -> torch.Tensor:
+    """[Co, Ci, kh, kw] fp32 -> [splits, Co, Kpad] bf16 (hi, lo planes), k = (ky*kw+kx)*Ci + ci."""
+    _chk_cuda(w)
+    w = w.detach().float().contiguous()
+    Co, Ci, kh, kw = w.shape
+    Kpad = (Ci * kh * kw + 63) // 64 * 64
+    out = torch.empty(splits, Co, Kpad, device=w.device, dtype=torch.bfloat16)
+    _cabi.check(_cabi.lib().ecsy_pack_conv_weight(_p(w), _p(out), Co, Ci, kh, kw, Kpad, splits, _st()),
+                "pack_conv_weight")
+    return out
+
+
+@dataclass
+class ConvW:
+    """Device-side forms of one Snn_Conv2d weight."""
+    packed: Optional[torch.Tensor]  # [splits, Co, Kpad] bf16 for the tcgen05 paths
+    simt: Optional[torch.Tensor]    # [kh, kw, Ci/g, Co] fp32 for the SIMT path
+    bias: Optional[torch.Tensor]
+    co: int
+    ci: int
+    k: int
+    stride: int
+    pad: int
+    groups: int
+    splits: int
+
+
+def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, umma: bool, simt: bool) -> ConvW:
+    splits = get_splits()
+    Co, Cig, kh, kw = weight.shape
+    packed = pack_conv_weight(weight, splits) if umma else None
+    sw = weight.detach().float().permute(2, 3, 1, 0).contiguous() if simt else None
+    b = bias.detach().float().contiguous() if bias is not None else None
+    return ConvW(packed, sw, b, Co, Cig * groups, kh, stride, pad, groups, splits)
+
+
+@dataclass
+class LifW:
+    dw_w: torch.Tensor   # [9, C]
+    dw_b: torch.Tensor   # [C]
+    pw: torch.Tensor     # [splits, C, C] bf16
+    pw_b: torch.Tensor   # [C]
+    splits: int
+
+
+def make_lif_w(dw_w, dw_b, pw_w, pw_b) -> LifW:
+    splits = get_splits()
+    C = dw_w.shape[0]
+    return LifW(dw_w.detach().float().reshape(C, 9).t().contiguous(), dw_b.detach().float().contiguous(),
+                pack_conv_weight(pw_w, splits), pw_b.detach().float().contiguous(), splits)
+
+
+# ------------------------------------------------------------------------------------------------
+# operators
+# ------------------------------------------------------------------------------------------------
+def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+            ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25, save_mem: bool = False):
+    """mem_update.forward (models/common.py:252-283) -> bit-packed spikes (and membranes if save_mem)."""
+    T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
+    dev = x.data.device
+    bits = torch.empty(T, N, H, W, C // 32, device=dev, dtype=torch.int32)
+    mem = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
+    L = _cabi.lib()
+    splits = w.splits if w is not None else 1
+    nws = L.ecsy_lif_ecs_ws_bytes(T, N, H, W, C, splits) if T > 1 else 0
+    ws = torch.empty(max(nws, 16), device=dev, dtype=torch.uint8)
+    sc, sh = affine if affine is not None else (None, None)
+    if T > 1 and w is None:
+        raise RuntimeError("lif_ecs: spread weights required for T > 1")
+    _cabi.check(L.ecsy_lif_ecs_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
+                                   _p(w.dw_w) if w else None, _p(w.dw_b) if w else None,
+                                   _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits,
+                                   _p(bits), _p(mem), T, N, H, W, C, float(thresh), float(decay), float(alpha),
+                                   float(beta), float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(), _st()), "lif_ecs_fwd")
+    sp = Spikes(bits, C)
+    return (sp, mem) if save_mem else sp
+
+
+def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[Act] = None) -> Act:
+    """Snn_Conv2d on spikes (models/common.py:609-624) with optional folded tdBN and shortcut add."""
+    T, N, H, W = s.T, s.N, s.H, s.W
+    if w.groups != 1 or w.packed is None:
+        raise RuntimeError("spike_conv: grouped / unpacked weights go through real_conv on unpacked spikes")
+    Ho = (H + 2 * w.pad - w.k) // w.stride + 1
+    Wo = (W + 2 * w.pad - w.k) // w.stride + 1
+    out = torch.empty(T, N, Ho, Wo, w.co, device=s.bits.device, dtype=torch.float32)
+    if residual is not None:
+        assert (residual.N, residual.H, residual.W, residual.C) == (N, Ho, Wo, w.co), "residual shape"
+    _cabi.check(_cabi.lib().ecsy_spike_conv_fwd(
+        _p(s.bits), _p(w.packed), w.splits, _p(out), _p(scale), _p(shift),
+        _p(residual.data) if residual is not None else None, residual.src_imgs if residual is not None else 0,
+        T * N, H, W, s.C, w.co, w.k, w.stride, w.pad, _st()), "spike_conv_fwd")
+    return Act(out, T)
+
+
+def real_conv(x: Act, w: ConvW, scale=None, shift=None, bias_mul: float = 1.0) -> Act:
+    """Snn_Conv2d on a real-valued input.  A T-broadcast input is convolved once."""
+    Tp, N, H, W = x.Tp, x.N, x.H, x.W
+    Ho = (H + 2 * w.pad - w.k) // w.stride + 1
+    Wo = (W + 2 * w.pad - w.k) // w.stride + 1
+    out = torch.empty(Tp, N, Ho, Wo, w.co, device=x.data.device, dtype=torch.float32)
+    L = _cabi.lib()
+    use_umma = w.packed is not None and w.groups == 1 and w.co % 64 == 0 and w.bias is None
+    nws = L.ecsy_real_conv_ws_bytes(Tp * N, H, W, w.ci, w.co, w.k, w.stride, w.pad, w.groups, w.splits) if use_umma else 0
+    ws = torch.empty(max(nws, 16), device=x.data.device, dtype=torch.uint8)
+    if not use_umma and w.simt is None:
+        raise RuntimeError("real_conv: SIMT weight layout missing")
+    _cabi.check(L.ecsy_real_conv_fwd(_p(x.data), Tp * N, _p(w.packed) if use_umma else None, _p(w.simt), w.splits,
+                                     _p(w.bias), float(bias_mul), _p(scale), _p(shift), _p(out), Tp * N, H, W, w.ci,
+                                     w.co, w.k, w.stride, w.pad, w.groups, _p(ws), ws.numel(), _st()), "real_conv_fwd")
+    return Act(out, x.T)
+
+
+def bn_stats(y: Act) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-channel mean / biased variance over (T, N, H, W)."""
+    rows = y.Tp * y.N * y.H * y.W
+    C = y.C
+    dev = y.data.device
+    mean = torch.empty(C, device=dev, dtype=torch.float32)
+    var = torch.empty(C, device=dev, dtype=torch.float32)
+    L = _cabi.lib()
+    ws = torch.empty(L.ecsy_tdbn_stats_ws_bytes(rows, C), device=dev, dtype=torch.uint8)
+    _cabi.check(L.ecsy_tdbn_stats(_p(y.data), rows, C, _p(mean), _p(var), _p(ws), ws.numel(), _st()), "tdbn_stats")
+    return mean, var
+
+
+def affine_add(a: Act, sa=None, ba=None, b: Optional[Act] = None, sb=None, bb=None) -> Act:
+    T = a.T
+    Tp = T if (a.Tp == T or (b is not None and b.Tp == T)) else 1
+    out = torch.empty(Tp, a.N, a.H, a.W, a.C, device=a.data.device, dtype=torch.float32)
+    if b is not None:
+        assert (b.N, b.H, b.W, b.C) == (a.N, a.H, a.W, a.C), "affine_add shapes"
+    _cabi.check(_cabi.lib().ecsy_affine_add(_p(a.data), a.src_imgs, _p(sa), _p(ba),
+                                            _p(b.data) if b is not None else None, b.src_imgs if b is not None else 0,
+                                            _p(sb), _p(bb), _p(out), Tp * a.N, a.H * a.W, a.C, _st()), "affine_add")
+    return Act(out, T)
+
+
+def resample_into(x: Act, out: torch.Tensor, coff: int, pool: int = 1, up: int = 1, scale=None, shift=None) -> None:
+    """max-pool / nearest-up / copy `x` into channels [coff, coff + x.C) of out [Tp, N, Ho, Wo, Ctot]."""
+    imgs = out.shape[0] * out.shape[1]
+    _cabi.check(_cabi.lib().ecsy_resample(_p(x.data), x.src_imgs, _p(scale), _p(shift), _p(out), imgs, x.H, x.W, x.C,
+                                          out.shape[4], coff, pool, up, _st()), "resample")
+
+
+def maxpool(x: Act, s: int) -> Act:
+    if s == 1:
+        return x
+    out = torch.empty(x.Tp, x.N, x.H // s, x.W // s, x.C, device=x.data.device, dtype=torch.float32)
+    resample_into(x, out, 0, pool=s)
+    return Act(out, x.T)
+
+
+def upsample(x: Act, s: int) -> Act:
+    out = torch.empty(x.Tp, x.N, x.H * s, x.W * s, x.C, device=x.data.device, dtype=torch.float32)
+    resample_into(x, out, 0, up=s)
+    return Act(out, x.T)
+
+
+def concat_channels(xs, pool: int = 1) -> Act:
+    T = xs[0].T
+    Tp = T if any(a.Tp == T for a in xs) else 1
+    Ct = sum(a.C for a in xs)
+    a0 = xs[0]
+    out = torch.empty(Tp, a0.N, a0.H // pool, a0.W // pool, Ct, device=a0.data.device, dtype=torch.float32)
+    off = 0
+    for a in xs:
+        resample_into(a, out, off, pool=pool)
+        off += a.C
+    return Act(out, T)
+
+
+def tsum(x: Act, w: Optional[torch.Tensor], div: float) -> torch.Tensor:
+    """[T, N, H, W, C] -> [N, H, W, C]: (sum_t w[t] x[t]) / div."""
+    x = x.full()
+    out = torch.empty(x.N, x.H, x.W, x.C, device=x.data.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ecsy_tsum(_p(x.data), _p(w), float(div), _p(out), x.T, out.numel(), _st()), "tsum")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """[imgs, H, W, C] -> [imgs, C, H, W] contiguous."""
+    n, H, W, C = x.shape
+    out = torch.empty(n, C, H, W, device=x.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ecsy_nhwc_to_nchw_f32(_p(x), _p(out), n, C, H, W, _st()), "nhwc_to_nchw")
+    return out
+
+
+def detect_decode(y: torch.Tensor, na: int, no: int, anchors: torch.Tensor, stride_px: float, z: Optional[torch.Tensor],
+                  row_off: int) -> torch.Tensor:
+    """y: [N, H, W, na*no] -> raw [N, na, H, W, no]; fills z rows if given."""
+    N, H, W, _ = y.shape
+    raw = torch.empty(N, na, H, W, no, device=y.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ecsy_detect_decode(_p(y), _p(raw), _p(z), _p(anchors), float(stride_px), N, H, W, na, no,
+                                               z.shape[1] if z is not None else 0, row_off, _st()), "detect_decode")
+    return raw
+
+
+def ddetect_decode(box: torch.Tensor, cls: torch.Tensor, stride_px: float, y: Optional[torch.Tensor], a_off: int):
+    N, H, W, _ = box.shape
+    nc = cls.shape[3]
+    xs = torch.empty(N, 64 + nc, H, W, device=box.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ecsy_ddetect_decode(_p(box), _p(cls), _p(xs), _p(y), float(stride_px), N, H, W, nc,
+                                                y.shape[2] if y is not None else 0, a_off, _st()), "ddetect_decode")
+    return xs

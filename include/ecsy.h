@@ -1,0 +1,108 @@
+/* ecsy.h -- C ABI of the B200-native ECS-YOLO spiking hot path (libecsy.so, sm_100a).
+ *
+ * Drop-in boundary for the reference's PyTorch operator calls on the time-unrolled spiking backbone
+ * and detection heads (mowanggui/ECS-YOLO, models/common.py, models/yolo.py, models/yolo_snn.py).
+ * Every entry point cites the reference interface it replaces.  Conventions:
+ *   - plain pointers + sizes, no framework types; all pointers are DEVICE pointers;
+ *   - the caller owns every buffer including workspaces (size via the *_ws_bytes queries); the library
+ *     allocates nothing and keeps no state beyond cached TMA descriptors keyed by pointer/shape;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*), no hidden synchronisation;
+ *   - return 0 on success, a negative code otherwise; ecsy_last_error() (thread-local) explains;
+ *   - there is no CPU fallback.
+ * Layouts: real activations are fp32 NHWC "[imgs][H][W][C]" with imgs = T*N (t-major); spikes are
+ * bit-packed along C: uint32 "[imgs][H][W][C/32]", bit (c & 31) of word (c >> 5).
+ * A source with `*_imgs` < imgs is broadcast over T (image index taken modulo `*_imgs`): the direct-coded
+ * input of Model.forward (models/yolo.py:248-251) repeats the same image every timestep.
+ */
+#ifndef ECSY_H_
+#define ECSY_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECSY_ABI_VERSION 1
+
+const char* ecsy_last_error(void);
+int ecsy_abi_version(void);
+int ecsy_sm_count(void);
+
+/* ---- layout at the model edge (reference tensors are NCHW per timestep, models/common.py:619-624) ---- */
+int ecsy_nchw_to_nhwc_f32(const float* in, float* out, int64_t imgs, int C, int H, int W, void* stream);
+int ecsy_nhwc_to_nchw_f32(const float* in, float* out, int64_t imgs, int C, int H, int W, void* stream);
+/* ActFun.forward (models/common.py:61-64): bit = x > thresh.  unpack gives the {0,1} float tensor back. */
+int ecsy_spikes_pack(const float* x_nhwc, uint32_t* bits, int64_t pixels, int C, float thresh, void* stream);
+int ecsy_spikes_unpack(const uint32_t* bits, float* x_nhwc, int64_t pixels, int C, void* stream);
+
+/* ---- weights: nn.Conv2d weight [Co][Ci][kh][kw] fp32 (Snn_Conv2d.weight, mem_update.spread[1].weight)
+ *      -> [splits][Co][Kpad] bf16, k = (ky*kw+kx)*Ci + ci; plane 0 = bf16(w), plane 1 = bf16(w - plane 0). */
+int ecsy_pack_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh, int kw, int Kpad, int splits,
+                          void* stream);
+
+/* ---- mem_update.forward (models/common.py:252-283): ECS-LIF over T steps.
+ * x: [T][N][H][W][C] real input current (t stride `x_tstride` elements; 0 = same tensor every step),
+ * optional per-channel affine on x (a folded tdBN), dw_w: spread[0].weight as [9][C], dw_b: [C],
+ * pw_packed: spread[1].weight packed by ecsy_pack_conv_weight (Kpad = C), pw_b: [C].
+ * spikes: [T][N][H][W][C/32] out.  mem_save (optional): [T][N][H][W][C] membranes for the backward pass. */
+size_t ecsy_lif_ecs_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
+int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
+                     const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b, int splits,
+                     uint32_t* spikes, float* mem_save, int T, int64_t N, int H, int W, int C, float thresh,
+                     float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Snn_Conv2d.forward on spikes (models/common.py:609-624), tcgen05 implicit GEMM.
+ * out[imgs][Ho][Wo][Cout] = conv(spikes, W) * scale[c] + shift[c] (+ residual).  scale/shift: folded
+ * eval-mode tdBN (models/common.py:674-679) or NULL; residual: the membrane shortcut (common.py:1216). */
+int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed, int splits, float* out, const float* scale,
+                        const float* shift, const float* residual, int64_t res_imgs, int64_t imgs, int H, int W,
+                        int Cin, int Cout, int k, int stride, int pad, void* stream);
+
+/* ---- Snn_Conv2d.forward on REAL inputs: stem Conv_1 (common.py:409-425), Conv (common.py:362-375),
+ * Detect.m (yolo.py:73), DDetect cv2/cv3[-1] (yolo_snn.py:100-107).  groups == 1 && Cout % 64 == 0 && no bias:
+ * im2col + tcgen05 GEMM (needs w_packed + workspace); otherwise SIMT with w_simt = [kh][kw][Ci/g][Co] fp32.
+ * bias is added as bias * bias_mul (Detect fuses Conv_7's sum of T weights into the bias). */
+size_t ecsy_real_conv_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad, int groups,
+                               int splits);
+int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_packed, const float* w_simt, int splits,
+                       const float* bias, float bias_mul, const float* scale, const float* shift, float* out,
+                       int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad, int groups, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* ---- batch_norm_2d / batch_norm_2d1 (models/common.py:668-700,753-758): per-channel mean and biased
+ * variance over all rows = T*N*H*W of x[rows][C] (train mode).  Normalisation itself is applied as a
+ * per-channel affine by the consumers (lif in_scale, conv scale, affine_add). */
+size_t ecsy_tdbn_stats_ws_bytes(int64_t rows, int C);
+int ecsy_tdbn_stats(const float* x, int64_t rows, int C, float* mean, float* var_biased, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* ---- block output `residual_function(x) + shortcut(x)` (models/common.py:1074,1216,1484) with the pending
+ * tdBN affines of both operands: out = a*sa+ba (+ b*sb+bb). */
+int ecsy_affine_add(const float* a, int64_t a_imgs, const float* sa, const float* ba, const float* b, int64_t b_imgs,
+                    const float* sb, const float* bb, float* out, int64_t imgs, int64_t hw, int C, void* stream);
+
+/* ---- nn.MaxPool3d((1,s,s)) (common.py:1209,1481), Sample nearest x`up` (common.py:856-868), Concat on the
+ * channel axis (common.py:1764): resample `in` into channels [coff, coff+C) of out[imgs][Ho][Wo][Ctot]. */
+int ecsy_resample(const float* in, int64_t in_imgs, const float* scale, const float* shift, float* out, int64_t imgs,
+                  int Hi, int Wi, int C, int Ctot, int coff, int pool, int up, void* stream);
+
+/* ---- reduction over T: out = (sum_t w[t] * x[t]) / div.  Conv_7 (common.py:549-562, w = Conv3d weight) and
+ * DDetect's mean over T (yolo_snn.py:115-116, w = NULL, div = T). */
+int ecsy_tsum(const float* x, const float* w, float div, float* out, int T, int64_t per_t, void* stream);
+
+/* ---- Detect.forward view/permute + eval decode (models/yolo.py:110-146).  y: [N][H][W][na*no];
+ * raw: [N][na][H][W][no]; z (NULL in training): rows [row_off, row_off + na*H*W) of [N][rows_total][no]. */
+int ecsy_detect_decode(const float* y, float* raw, float* z, const float* anchors, float stride_px, int N, int H,
+                       int W, int na, int no, int64_t rows_total, int64_t row_off, void* stream);
+
+/* ---- DDetect.forward concat + DFL + dist2bbox + sigmoid (models/yolo_snn.py:115-127, common.py:312-323,
+ * utils/tal/anchor_generator.py:8-32).  box: [N][H][W][64], cls: [N][H][W][nc] (means over T);
+ * xs: [N][64+nc][H][W]; y (NULL in training): anchors [a_off, a_off + H*W) of [N][4+nc][a_total]. */
+int ecsy_ddetect_decode(const float* box, const float* cls, float* xs, float* y, float stride_px, int N, int H, int W,
+                        int nc, int64_t a_total, int64_t a_off, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECSY_H_ */

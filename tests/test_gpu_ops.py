@@ -1,0 +1,192 @@
+"""GPU parity tests of the individual C-ABI operators against the golden reference outputs
+(tests/golden, produced by the unmodified reference) and the CPU oracle."""
+import pytest
+import torch
+
+import ecs_oracle as O
+import seeded as S
+from util import agree, ecsy, load_golden, nhwc, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_layout_and_bits_roundtrip():
+    E = ecsy()
+    F, Act, Spikes = E.functional, E.functional.Act, E.functional.Spikes
+    g = S.gen(1)
+    x = torch.rand(3, 2, 64, 5, 7, generator=g)
+    a = Act.from_ref(x.cuda())
+    assert torch.equal(a.data.cpu(), x.permute(0, 1, 3, 4, 2).contiguous())
+    back = F.nhwc_to_nchw(a.data.reshape(6, 5, 7, 64)).cpu().reshape(3, 2, 64, 5, 7)
+    assert torch.equal(back, x)
+    sp = Spikes.from_act(a)
+    ref = (x > 0.5).float()
+    assert torch.equal(sp.to_act().to_ref().cpu(), ref)
+    # broadcast over T is detected and kept as one frame
+    xb = x[:1].cuda().expand(4, -1, -1, -1, -1)
+    ab = Act.from_ref(xb)
+    assert ab.Tp == 1 and ab.T == 4 and ab.tstride == 0
+    assert torch.equal(ab.to_ref().cpu(), xb.cpu())
+
+
+@pytest.mark.parametrize("mode,tol", [("parity", 2e-5), ("fast", 6e-3)])
+@pytest.mark.parametrize("name", [n for n, s in S.CONV_CASES.items() if s["spikes"]])
+def test_spike_conv(name, mode, tol):
+    E = ecsy()
+    F = E.functional
+    F.set_precision(mode)
+    try:
+        spec, gold = S.CONV_CASES[name], load_golden(name)
+        inp = S.conv_inputs(spec)
+        sp = F.Spikes.from_act(F.Act.from_ref(inp["x"].cuda()))
+        w = F.make_conv_w(inp["w"].cuda(), None, spec["s"], spec["p"], 1, True, False)
+        out = F.spike_conv(sp, w).to_ref().cpu()
+        err = rel_l2(out, gold["out"])
+        assert err < tol, f"{name} {mode}: rel-L2 {err:.3e}"
+        # epilogue: folded affine + residual (T-broadcast residual too)
+        co = spec["co"]
+        sc = torch.rand(co, generator=S.gen(5)) + 0.5
+        sh = torch.rand(co, generator=S.gen(6)) - 0.5
+        res = torch.randn(*gold["out"].shape, generator=S.gen(7))
+        out2 = F.spike_conv(sp, w, sc.cuda(), sh.cuda(), F.Act.from_ref(res.cuda())).to_ref().cpu()
+        want = gold["out"] * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1) + res
+        assert rel_l2(out2, want) < tol
+        resb = res[:1].cuda().expand(res.shape[0], -1, -1, -1, -1)
+        out3 = F.spike_conv(sp, w, None, None, F.Act.from_ref(resb)).to_ref().cpu()
+        assert rel_l2(out3, gold["out"] + res[:1]) < tol
+    finally:
+        F.set_precision("parity")
+
+
+@pytest.mark.parametrize("name", [n for n, s in S.CONV_CASES.items() if not s["spikes"]])
+def test_real_conv(name):
+    E = ecsy()
+    F = E.functional
+    spec, gold = S.CONV_CASES[name], load_golden(name)
+    inp = S.conv_inputs(spec)
+    a = F.Act.from_ref(inp["x"].cuda())
+    b = inp["b"].cuda() if inp["b"] is not None else None
+    w = F.make_conv_w(inp["w"].cuda(), b, spec["s"], spec["p"], 1, spec["co"] % 64 == 0, True)
+    out = F.real_conv(a, w).to_ref().cpu()
+    err = rel_l2(out, gold["out"])
+    assert err < 2e-5, f"{name}: rel-L2 {err:.3e}"
+    # SIMT path on the same problem
+    w2 = F.make_conv_w(inp["w"].cuda(), b, spec["s"], spec["p"], 1, False, True)
+    out2 = F.real_conv(a, w2).to_ref().cpu()
+    assert rel_l2(out2, gold["out"]) < 2e-6
+    # a T-broadcast input is convolved once and stays broadcast
+    ab = F.Act.from_ref(inp["x"][:1].cuda().expand(spec["T"], -1, -1, -1, -1))
+    ob = F.real_conv(ab, w)
+    assert ob.Tp == 1 and rel_l2(ob.to_ref().cpu()[2], gold["out"][0]) < 2e-5
+
+
+def test_grouped_conv_simt():
+    E = ecsy()
+    F = E.functional
+    g = S.gen(11)
+    x = torch.randn(2, 1, 64, 6, 6, generator=g)
+    w = torch.randn(64, 16, 3, 3, generator=g) * 0.1
+    want = O.snn_conv2d(x, w, None, 1, 1, 4)
+    cw = F.make_conv_w(w.cuda(), None, 1, 1, 4, False, True)
+    got = F.real_conv(F.Act.from_ref(x.cuda()), cw).to_ref().cpu()
+    assert rel_l2(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("C,rows", [(64, 1000), (384, 517), (1024, 300), (128, 70000)])
+def test_bn_stats(C, rows):
+    E = ecsy()
+    F = E.functional
+    x = torch.randn(1, 1, rows, 1, C, generator=S.gen(C)) * 1.7 + 0.3
+    mean, var = F.bn_stats(F.Act(x.cuda().contiguous(), 1))
+    xd = x.double().reshape(rows, C)
+    assert torch.allclose(mean.cpu().double(), xd.mean(0), atol=1e-6)
+    assert torch.allclose(var.cpu().double(), xd.var(0, unbiased=False), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(S.BN_CASES))
+def test_tdbn_module(name):
+    E = ecsy()
+    spec, gold = S.BN_CASES[name], load_golden(name)
+    for cls, tag in [(E.common.batch_norm_2d, "bn1"), (E.common.batch_norm_2d1, "bn2")]:
+        inp = S.bn_inputs(spec)
+        m = cls(spec["C"])
+        m.load_state_dict(inp["sd"])
+        m = m.cuda().train()
+        out = m(inp["x"].cuda()).cpu()
+        assert rel_l2(out, gold[tag + "_train"]) < 1e-5
+        for k, v in gold[tag + "_sd_after"].items():
+            assert torch.allclose(m.state_dict()[k].cpu().float(), v.float(), rtol=1e-5, atol=1e-6), k
+        m.eval()
+        assert rel_l2(m(inp["x"].cuda()).cpu(), gold[tag + "_eval"]) < 1e-5
+
+
+def test_resample_concat_tsum():
+    E = ecsy()
+    F = E.functional
+    g = S.gen(21)
+    a = torch.randn(2, 2, 64, 8, 6, generator=g)
+    b = torch.randn(2, 2, 128, 4, 3, generator=g)
+    A, B = F.Act.from_ref(a.cuda()), F.Act.from_ref(b.cuda())
+    assert torch.equal(F.maxpool(A, 2).to_ref().cpu(), O.maxpool_hw(a, 2))
+    assert torch.equal(F.upsample(B, 2).to_ref().cpu(), O.sample_nearest(b, 2))
+    cat = F.concat_channels([F.upsample(B, 2), A]).to_ref().cpu()
+    assert torch.equal(cat, torch.cat([O.sample_nearest(b, 2), a], 2))
+    pc = F.concat_channels([A, A], pool=2).to_ref().cpu()
+    assert torch.equal(pc, O.maxpool_hw(torch.cat([a, a], 2), 2))
+    w = torch.tensor([0.3, -0.2])
+    ts = F.tsum(A, w.cuda(), 1.0).cpu()
+    want = (a * w.view(2, 1, 1, 1, 1)).sum(0).permute(0, 2, 3, 1)
+    assert torch.allclose(ts, want, atol=1e-6)
+    sa, ba = torch.rand(64) + 0.5, torch.rand(64)
+    out = F.affine_add(A, sa.cuda(), ba.cuda(), A, None, None).to_ref().cpu()
+    assert torch.allclose(out, a * sa.view(1, 1, -1, 1, 1) + ba.view(1, 1, -1, 1, 1) + a, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode,min_agree", [("parity", 0.9995), ("fast", 0.995)])
+@pytest.mark.parametrize("name", list(S.LIF_CASES))
+def test_lif_ecs(name, mode, min_agree):
+    """Spikes must agree with the reference at >= 99.9 % of positions (north star); parity mode is
+    held to 99.95 %, and to exact equality where no membrane sits within 1e-4 of the threshold."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision(mode)
+    try:
+        spec, gold = S.LIF_CASES[name], load_golden(name)
+        inp = S.lif_inputs(spec)
+        w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+        sp = F.lif_ecs(F.Act.from_ref(inp["x"].cuda()), w)
+        got = sp.to_act().to_ref().cpu()
+        ref = S.unpack_spikes(gold["spikes"], got.shape)
+        frac = agree(got, ref)
+        assert frac >= min_agree, f"{name} {mode}: spike agreement {frac:.6f}"
+        assert abs(float(got.mean()) - gold["rate"]) < 5e-3
+        if mode == "parity":
+            rec = {}
+            O.ecs_lif(inp["x"], inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"], record=rec)
+            mem = torch.stack(rec["mem"])
+            safe = (mem - 0.5).abs() > 1e-4
+            # only compare positions whose whole history is unambiguous up to that step
+            first_bad = (~safe).flatten(1).any(1).float().argmax() if (~safe).any() else None
+            upto = spec["T"] if first_bad is None or safe.flatten(1).all(1).all() else int(first_bad)
+            assert torch.equal(got[:max(upto, 1)][safe[:max(upto, 1)]], ref[:max(upto, 1)][safe[:max(upto, 1)]])
+    finally:
+        F.set_precision("parity")
+
+
+def test_lif_affine_and_broadcast():
+    """Folded tdBN on the input current and a T-broadcast input equal the explicit computation."""
+    E = ecsy()
+    F = E.functional
+    spec = S.LIF_CASES["lif_c64_t4"]
+    inp = S.lif_inputs(spec)
+    w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+    sc = torch.rand(64, generator=S.gen(3)) + 0.5
+    sh = torch.rand(64, generator=S.gen(4)) * 0.2
+    x = inp["x"]
+    got = F.lif_ecs(F.Act.from_ref(x.cuda()), w, (sc.cuda(), sh.cuda())).to_act().to_ref().cpu()
+    want = O.ecs_lif(x * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1), inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
+    assert agree(got, want) > 0.999
+    xb = x[:1].expand(4, -1, -1, -1, -1)
+    gotb = F.lif_ecs(F.Act.from_ref(xb.cuda()), w).to_act().to_ref().cpu()
+    wantb = O.ecs_lif(xb.contiguous(), inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
+    assert agree(gotb, wantb) > 0.999
