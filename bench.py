@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- SNN-YOLO images/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                      # our CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1              # reference algorithm on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- EMS-ResNet34 SNN-YOLO (cfg/resnet34.yaml), T=4,
+inference, per-GPU batch 64, synthetic 640x640 images, default-init weights with momentum-1 calibrated
+tdBN, bf16 tensor-core operands with fp32 accumulation.  A "step" is one forward
+pass over one batch.  `value`: inputs resident in HBM; `e2e`: Model.forward called with a pinned HOST
+batch, H2D copy and D2H read of the decoded detections inside the timed region.  Batch-sharded over
+ranks with no data-path collective (weak scaling).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 7 and r[3 + j] == "Active" for r in self.rows)]
+        mx = max(float(r[1]) for r in self.rows if len(r) >= 7)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def load_cfg(name):
+    return yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", name + ".yaml")))
+
+
+def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads):
+    """Times the oracle port of the reference's CPU path (torch fp32, all host threads) on a bounded
+    sample of the same workload: `sample_imgs` images per step."""
+    import ecs_oracle as O
+    torch.set_num_threads(threads)
+    cfg = load_cfg(model_name)
+    sd = O.init_state_dict(cfg, T, seed=0)
+    stride = O.detect_strides(cfg)
+    for k in sd:
+        if k.endswith("anchors"):
+            sd[k] = sd[k] / stride.view(-1, 1, 1)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(sample_imgs, 3, img, img, generator=g)
+    with torch.no_grad():
+        O.BN_MOMENTUM = 1.0
+        O.forward(cfg, sd, x, T, True, stride=stride)   # calibration pass (train-mode tdBN) == warm-up 0
+        O.BN_MOMENTUM = 0.1
+        for _ in range(max(warmup - 1, 0)):
+            O.forward(cfg, sd, x, T, False, stride=stride)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.forward(cfg, sd, x, T, False, stride=stride)
+        dt = time.perf_counter() - t0
+    return sample_imgs * steps / dt, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="resnet34")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--img", type=int, default=640)
+    ap.add_argument("--T", type=int, default=4)
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1, help="images per CPU step")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+    workload = f"EMS-{args.model} SNN-YOLO T={args.T} inference, batch {args.batch}/GPU, synthetic {args.img}x{args.img}"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(args.steps, 1)
+        ips, spstep = cpu_reference(args.model, args.T, args.img, args.cpu_sample, steps, max(args.warmup, 1), threads)
+        line = {"impl": "reference", "metric": "images/s", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "sample": f"{args.cpu_sample} image(s) per step"},
+                "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                                 "sample": f"{args.cpu_sample} image(s)/step of the same workload, oracle port "
+                                           "(torch fp32 CPU) of the reference forward"},
+                "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = os.path.join(ROOT, "ecs-yolo_b200", "lib", "libecsy.so")
+    if not os.path.exists(lib) and rank == 0:
+        import __graft_entry__
+        __graft_entry__.build()
+    if dist is not None:
+        dist.barrier()
+    E = importlib.import_module("ecs-yolo_b200")
+    F = E.functional
+    E.set_precision(args.precision)
+    E.common.time_window = args.T
+
+    torch.manual_seed(0)
+    model = E.yolo.Model(E.cfg_path(args.model)).cuda()
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.rand(args.batch, 3, args.img, args.img, generator=g).pin_memory()
+    x = x_host.cuda()
+
+    # momentum-1 calibration of every tdBN on the seed batch, then eval
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(x)
+    model.eval()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            z, _ = model(x)
+        barrier()
+        F.launches["n"] = 0
+        for k in F.flops:
+            F.flops[k] = 0.0
+        F.profile_begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            ev0.record()
+            for _ in range(args.steps):
+                z, _ = model(x)
+            ev1.record()
+            barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        per_op = F.profile_end()
+        launches = F.launches["n"]
+        flops = dict(F.flops)
+
+        # end to end: pinned host batch -> H2D -> forward -> D2H of the decoded detections
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            xd = x_host.to("cuda", non_blocking=True)
+            zz, _ = model(xd)
+            z_host = zz.cpu()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    imgs = args.batch * world * args.steps
+    pk = peaks()
+    conv_ms = per_op.get("spike_conv", 0.0) / args.steps
+    conv_tf = flops["spike_conv"] / args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    line = {
+        "metric": "images/s", "value": imgs / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "model_cfg": f"cfg/{args.model}.yaml", "T": args.T,
+                   "global_batch": args.batch * world, "precision": args.precision,
+                   "accumulate": "fp32", "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
+                   "weights": "default init (seed 0), tdBN calibrated with momentum 1.0 on the seed batch"},
+        "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": z_host.numel() * 4},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": {"kernel": "k_umma_gemm<spikes,conv> (spike implicit-GEMM conv, tcgen05)", "bound": "tensor",
+                     "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                     "frac": conv_tf / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                     "algorithmic_gflop_per_step": flops["spike_conv"] / args.steps / 1e9,
+                     "kernel_ms_per_step": conv_ms},
+        "breakdown_ms_per_step": {k: v / args.steps for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
+        "dense_tflops_whole_step": (flops["spike_conv"] + flops["ecs_pw"] + flops["real_conv"]) / args.steps
+                                   / (ms_total / args.steps * 1e-3) / 1e12,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ips, _ = cpu_reference(args.model, args.T, args.img, args.cpu_sample, 2, 1, threads)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_sample} image(s)/step x 2 steps of the same workload, oracle "
+                                          "port (torch fp32 CPU) of the reference forward"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

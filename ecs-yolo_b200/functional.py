@@ -23,6 +23,44 @@ decay = 0.25
 
 _state = {"splits": 2}
 
+# ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
+launches = {"n": 0}
+_prof = {"on": False, "events": []}
+flops = {"spike_conv": 0.0, "ecs_pw": 0.0, "real_conv": 0.0}
+
+
+def profile_begin():
+    _prof["on"], _prof["events"] = True, []
+
+
+def profile_end():
+    """-> {op: milliseconds}; call after a synchronize."""
+    _prof["on"] = False
+    out = {}
+    for name, a, b in _prof["events"]:
+        out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+    _prof["events"] = []
+    return out
+
+
+class _timed:
+    def __init__(self, name, n_launch):
+        self.name, self.n = name, n_launch
+
+    def __enter__(self):
+        launches["n"] += self.n
+        if _prof["on"]:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof["on"]:
+            self.b.record()
+            _prof["events"].append((self.name, self.a, self.b))
+        return False
+
 
 def set_precision(mode: str) -> None:
     """'parity': weights as bf16 hi+lo pairs (2 MMAs, ~fp32 weights; spikes are exact in bf16);
@@ -91,7 +129,8 @@ class Act:
         src = src.contiguous()
         Tp, N, Cc, H, W = src.shape
         out = torch.empty(Tp, N, H, W, Cc, device=x.device, dtype=torch.float32)
-        _cabi.check(_cabi.lib().ecsy_nchw_to_nhwc_f32(_p(src), _p(out), Tp * N, Cc, H, W, _st()), "nchw_to_nhwc")
+        with _timed("layout", 1):
+            _cabi.check(_cabi.lib().ecsy_nchw_to_nhwc_f32(_p(src), _p(out), Tp * N, Cc, H, W, _st()), "nchw_to_nhwc")
         return Act(out, T)
 
     def full(self) -> "Act":
@@ -200,7 +239,9 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     sc, sh = affine if affine is not None else (None, None)
     if T > 1 and w is None:
         raise RuntimeError("lif_ecs: spread weights required for T > 1")
-    _cabi.check(L.ecsy_lif_ecs_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
+    flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
+    with _timed("lif_ecs", 1 + 2 * (T - 1)):
+        _cabi.check(L.ecsy_lif_ecs_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
                                    _p(w.dw_w) if w else None, _p(w.dw_b) if w else None,
                                    _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits,
                                    _p(bits), _p(mem), T, N, H, W, C, float(thresh), float(decay), float(alpha),
@@ -219,10 +260,12 @@ def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[A
     out = torch.empty(T, N, Ho, Wo, w.co, device=s.bits.device, dtype=torch.float32)
     if residual is not None:
         assert (residual.N, residual.H, residual.W, residual.C) == (N, Ho, Wo, w.co), "residual shape"
-    _cabi.check(_cabi.lib().ecsy_spike_conv_fwd(
-        _p(s.bits), _p(w.packed), w.splits, _p(out), _p(scale), _p(shift),
-        _p(residual.data) if residual is not None else None, residual.src_imgs if residual is not None else 0,
-        T * N, H, W, s.C, w.co, w.k, w.stride, w.pad, _st()), "spike_conv_fwd")
+    flops["spike_conv"] += 2.0 * T * N * Ho * Wo * w.co * s.C * w.k * w.k
+    with _timed("spike_conv", 1):
+        _cabi.check(_cabi.lib().ecsy_spike_conv_fwd(
+            _p(s.bits), _p(w.packed), w.splits, _p(out), _p(scale), _p(shift),
+            _p(residual.data) if residual is not None else None, residual.src_imgs if residual is not None else 0,
+            T * N, H, W, s.C, w.co, w.k, w.stride, w.pad, _st()), "spike_conv_fwd")
     return Act(out, T)
 
 
@@ -238,9 +281,11 @@ def real_conv(x: Act, w: ConvW, scale=None, shift=None, bias_mul: float = 1.0) -
     ws = torch.empty(max(nws, 16), device=x.data.device, dtype=torch.uint8)
     if not use_umma and w.simt is None:
         raise RuntimeError("real_conv: SIMT weight layout missing")
-    _cabi.check(L.ecsy_real_conv_fwd(_p(x.data), Tp * N, _p(w.packed) if use_umma else None, _p(w.simt), w.splits,
-                                     _p(w.bias), float(bias_mul), _p(scale), _p(shift), _p(out), Tp * N, H, W, w.ci,
-                                     w.co, w.k, w.stride, w.pad, w.groups, _p(ws), ws.numel(), _st()), "real_conv_fwd")
+    flops["real_conv"] += 2.0 * Tp * N * Ho * Wo * w.co * (w.ci // w.groups) * w.k * w.k
+    with _timed("real_conv", 2 if use_umma else 1):
+        _cabi.check(L.ecsy_real_conv_fwd(_p(x.data), Tp * N, _p(w.packed) if use_umma else None, _p(w.simt), w.splits,
+                                         _p(w.bias), float(bias_mul), _p(scale), _p(shift), _p(out), Tp * N, H, W, w.ci,
+                                         w.co, w.k, w.stride, w.pad, w.groups, _p(ws), ws.numel(), _st()), "real_conv_fwd")
     return Act(out, x.T)
 
 
@@ -253,7 +298,8 @@ def bn_stats(y: Act) -> Tuple[torch.Tensor, torch.Tensor]:
     var = torch.empty(C, device=dev, dtype=torch.float32)
     L = _cabi.lib()
     ws = torch.empty(L.ecsy_tdbn_stats_ws_bytes(rows, C), device=dev, dtype=torch.uint8)
-    _cabi.check(L.ecsy_tdbn_stats(_p(y.data), rows, C, _p(mean), _p(var), _p(ws), ws.numel(), _st()), "tdbn_stats")
+    with _timed("tdbn_stats", 2):
+        _cabi.check(L.ecsy_tdbn_stats(_p(y.data), rows, C, _p(mean), _p(var), _p(ws), ws.numel(), _st()), "tdbn_stats")
     return mean, var
 
 
@@ -263,17 +309,19 @@ def affine_add(a: Act, sa=None, ba=None, b: Optional[Act] = None, sb=None, bb=No
     out = torch.empty(Tp, a.N, a.H, a.W, a.C, device=a.data.device, dtype=torch.float32)
     if b is not None:
         assert (b.N, b.H, b.W, b.C) == (a.N, a.H, a.W, a.C), "affine_add shapes"
-    _cabi.check(_cabi.lib().ecsy_affine_add(_p(a.data), a.src_imgs, _p(sa), _p(ba),
-                                            _p(b.data) if b is not None else None, b.src_imgs if b is not None else 0,
-                                            _p(sb), _p(bb), _p(out), Tp * a.N, a.H * a.W, a.C, _st()), "affine_add")
+    with _timed("affine_add", 1):
+        _cabi.check(_cabi.lib().ecsy_affine_add(_p(a.data), a.src_imgs, _p(sa), _p(ba),
+                                                _p(b.data) if b is not None else None, b.src_imgs if b is not None else 0,
+                                                _p(sb), _p(bb), _p(out), Tp * a.N, a.H * a.W, a.C, _st()), "affine_add")
     return Act(out, T)
 
 
 def resample_into(x: Act, out: torch.Tensor, coff: int, pool: int = 1, up: int = 1, scale=None, shift=None) -> None:
     """max-pool / nearest-up / copy `x` into channels [coff, coff + x.C) of out [Tp, N, Ho, Wo, Ctot]."""
     imgs = out.shape[0] * out.shape[1]
-    _cabi.check(_cabi.lib().ecsy_resample(_p(x.data), x.src_imgs, _p(scale), _p(shift), _p(out), imgs, x.H, x.W, x.C,
-                                          out.shape[4], coff, pool, up, _st()), "resample")
+    with _timed("resample", 1):
+        _cabi.check(_cabi.lib().ecsy_resample(_p(x.data), x.src_imgs, _p(scale), _p(shift), _p(out), imgs, x.H, x.W, x.C,
+                                              out.shape[4], coff, pool, up, _st()), "resample")
 
 
 def maxpool(x: Act, s: int) -> Act:
@@ -307,7 +355,8 @@ def tsum(x: Act, w: Optional[torch.Tensor], div: float) -> torch.Tensor:
     """[T, N, H, W, C] -> [N, H, W, C]: (sum_t w[t] x[t]) / div."""
     x = x.full()
     out = torch.empty(x.N, x.H, x.W, x.C, device=x.data.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ecsy_tsum(_p(x.data), _p(w), float(div), _p(out), x.T, out.numel(), _st()), "tsum")
+    with _timed("tsum", 1):
+        _cabi.check(_cabi.lib().ecsy_tsum(_p(x.data), _p(w), float(div), _p(out), x.T, out.numel(), _st()), "tsum")
     return out
 
 
@@ -324,8 +373,9 @@ def detect_decode(y: torch.Tensor, na: int, no: int, anchors: torch.Tensor, stri
     """y: [N, H, W, na*no] -> raw [N, na, H, W, no]; fills z rows if given."""
     N, H, W, _ = y.shape
     raw = torch.empty(N, na, H, W, no, device=y.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ecsy_detect_decode(_p(y), _p(raw), _p(z), _p(anchors), float(stride_px), N, H, W, na, no,
-                                               z.shape[1] if z is not None else 0, row_off, _st()), "detect_decode")
+    with _timed("detect_decode", 1):
+        _cabi.check(_cabi.lib().ecsy_detect_decode(_p(y), _p(raw), _p(z), _p(anchors), float(stride_px), N, H, W, na, no,
+                                                   z.shape[1] if z is not None else 0, row_off, _st()), "detect_decode")
     return raw
 
 
