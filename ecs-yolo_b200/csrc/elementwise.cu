@@ -4,6 +4,7 @@
 // spikes are one bit per channel packed along C ("[imgs][H][W][C/32]" uint32, bit c&31 of word c>>5).
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
+#include "umma_gemm.h"
 
 namespace {
 
@@ -69,10 +70,14 @@ __global__ void k_unpack(const uint32_t* __restrict__ bits, float* __restrict__ 
 __global__ void k_lif_first(const float* __restrict__ x, const float* __restrict__ scale,
                             const float* __restrict__ shift, float* __restrict__ mem,
                             uint32_t* __restrict__ bits, int64_t n4, int C, float thresh) {
-  // n4 = pixels*C/4 ; total threads padded to a multiple of 8 lanes per word by construction (C%32==0)
+  // n4 = pixels*C/4 is a multiple of 8 (C % 32 == 0), so the 8 lanes that assemble one word are
+  // always active together; the shuffles below only exchange data inside such 8-lane groups.
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
+  const int64_t n4_round = (n4 + 31) & ~int64_t(31);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4_round; i += stride) {
+    const bool ok = i < n4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
     if (scale != nullptr) {
       int c = static_cast<int>((i * 4) % C);
       float4 s = *reinterpret_cast<const float4*>(scale + c);
@@ -82,56 +87,68 @@ __global__ void k_lif_first(const float* __restrict__ x, const float* __restrict
       v.z = ecsy::add_rn(ecsy::mul_rn(v.z, s.z), b.z);
       v.w = ecsy::add_rn(ecsy::mul_rn(v.w, s.w), b.w);
     }
-    if (mem != nullptr) reinterpret_cast<float4*>(mem)[i] = v;
+    if (ok && mem != nullptr) reinterpret_cast<float4*>(mem)[i] = v;
     uint32_t nib = (v.x > thresh ? 1u : 0u) | (v.y > thresh ? 2u : 0u) | (v.z > thresh ? 4u : 0u) |
                    (v.w > thresh ? 8u : 0u);
-    // 8 consecutive lanes hold the 8 nibbles of one 32-channel word (n4 is a multiple of 8 and the
-    // loop stride is a multiple of 32, so all lanes of a word-group are active together)
     const int sub = threadIdx.x & 7;
     uint32_t w = nib << (4 * sub);
     w |= __shfl_xor_sync(0xffffffffu, w, 1);
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    if (sub == 0) bits[i >> 3] = w;
+    if (ok && sub == 0) bits[i >> 3] = w;
   }
 }
 
-// Plain (uncoupled) LIF step t>=1 with an externally supplied feedback term; used by the
-// per-timestep pipeline when the ECS GEMM epilogue is not fused (debug / cross-check path):
-// mem_t = mem_{t-1}*decay*(1-s_{t-1}) + x_t + fecs_{t-1}
-__global__ void k_lif_step(const float* __restrict__ x, const float* __restrict__ scale,
-                           const float* __restrict__ shift, const float* __restrict__ fecs,
-                           float* __restrict__ mem, const uint32_t* __restrict__ bits_prev,
-                           uint32_t* __restrict__ bits, int64_t n4, int C, float thresh, float decay) {
+// ECS-LIF step t -> t+1 (models/common.py:263-281, 306-309), streaming half: consumes the point-wise
+// spread GEMM output and produces e_t, mem_{t+1}, s_{t+1}:
+//   e_t     = alpha*(spread + b) + kappa*e_{t-1}
+//   f_t     = beta*tanh(e_t)
+//   mem_t+1 = mem_t*decay*(1 - s_t) + x_{t+1} + f_t ;  s_{t+1} = mem_{t+1} > thresh
+// Every product / sum is rounded separately, in the reference's evaluation order.
+__global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
-    if (scale != nullptr) {
-      int c = static_cast<int>((i * 4) % C);
-      float4 s = *reinterpret_cast<const float4*>(scale + c);
-      float4 b = *reinterpret_cast<const float4*>(shift + c);
-      v.x = ecsy::add_rn(ecsy::mul_rn(v.x, s.x), b.x);
-      v.y = ecsy::add_rn(ecsy::mul_rn(v.y, s.y), b.y);
-      v.z = ecsy::add_rn(ecsy::mul_rn(v.z, s.z), b.z);
-      v.w = ecsy::add_rn(ecsy::mul_rn(v.w, s.w), b.w);
-    }
-    float4 m = reinterpret_cast<const float4*>(mem)[i];
-    float4 f = fecs ? reinterpret_cast<const float4*>(fecs)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4_round; i += stride) {
+    const bool ok = i < n4;
+    uint32_t nib = 0;
     const int sub = threadIdx.x & 7;
-    uint32_t pw = bits_prev[i >> 3] >> (4 * sub);
-    float4 o;
-    o.x = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.x, decay), (pw & 1u) ? 0.f : 1.f), v.x), f.x);
-    o.y = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.y, decay), (pw & 2u) ? 0.f : 1.f), v.y), f.y);
-    o.z = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.z, decay), (pw & 4u) ? 0.f : 1.f), v.z), f.z);
-    o.w = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(m.w, decay), (pw & 8u) ? 0.f : 1.f), v.w), f.w);
-    reinterpret_cast<float4*>(mem)[i] = o;
-    uint32_t nib = (o.x > thresh ? 1u : 0u) | (o.y > thresh ? 2u : 0u) | (o.z > thresh ? 4u : 0u) |
-                   (o.w > thresh ? 8u : 0u);
+    if (ok) {
+      const int c = static_cast<int>((i * 4) % C);
+      float4 xv = ecsy::ldg_stream(reinterpret_cast<const float4*>(p.x_next) + i);
+      if (p.in_scale != nullptr) {
+        const float4 s = *reinterpret_cast<const float4*>(p.in_scale + c);
+        const float4 b = *reinterpret_cast<const float4*>(p.in_shift + c);
+        xv.x = ecsy::add_rn(ecsy::mul_rn(xv.x, s.x), b.x);
+        xv.y = ecsy::add_rn(ecsy::mul_rn(xv.y, s.y), b.y);
+        xv.z = ecsy::add_rn(ecsy::mul_rn(xv.z, s.z), b.z);
+        xv.w = ecsy::add_rn(ecsy::mul_rn(xv.w, s.w), b.w);
+      }
+      const float4 sv = ecsy::ldg_stream(reinterpret_cast<const float4*>(p.spread) + i);
+      const float4 mv = reinterpret_cast<const float4*>(p.mem_in)[i];
+      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!p.first) ev = reinterpret_cast<const float4*>(p.ecs)[i];
+      const float4 pb = *reinterpret_cast<const float4*>(p.pw_b + c);
+      const uint32_t pw = p.bits_t[i >> 3] >> (4 * sub);
+      const float xin[4] = {xv.x, xv.y, xv.z, xv.w}, sp[4] = {sv.x, sv.y, sv.z, sv.w};
+      const float mo[4] = {mv.x, mv.y, mv.z, mv.w}, eo[4] = {ev.x, ev.y, ev.z, ev.w};
+      const float bb[4] = {pb.x, pb.y, pb.z, pb.w};
+      float mn[4], en[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float s_acc = ecsy::add_rn(sp[k], bb[k]);
+        en[k] = ecsy::add_rn(ecsy::mul_rn(p.alpha, s_acc), ecsy::mul_rn(p.kappa, eo[k]));
+        const float fecs = ecsy::mul_rn(p.beta, tanhf(en[k]));
+        const float keep = ((pw >> k) & 1u) ? 0.f : 1.f;
+        mn[k] = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(mo[k], p.decay), keep), xin[k]), fecs);
+        nib |= (mn[k] > p.thresh ? 1u : 0u) << k;
+      }
+      if (p.mem_out != nullptr) reinterpret_cast<float4*>(p.mem_out)[i] = make_float4(mn[0], mn[1], mn[2], mn[3]);
+      if (p.store_ecs) reinterpret_cast<float4*>(p.ecs)[i] = make_float4(en[0], en[1], en[2], en[3]);
+    }
     uint32_t w = nib << (4 * sub);
     w |= __shfl_xor_sync(0xffffffffu, w, 1);
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    if (sub == 0) bits[i >> 3] = w;
+    if (ok && sub == 0) p.bits_next[i >> 3] = w;
   }
 }
 
@@ -478,12 +495,10 @@ int ecsy_launch_lif_first(const float* x, const float* scale, const float* shift
   return ECSY_OK;
 }
 
-int ecsy_launch_lif_step(const float* x, const float* scale, const float* shift, const float* fecs, float* mem,
-                         const uint32_t* bits_prev, uint32_t* bits, int64_t pixels, int C, float thresh,
-                         float decay, cudaStream_t st) {
+int ecsy_launch_ecs_step(const EcsStep& p, int64_t pixels, int C, cudaStream_t st) {
   const int64_t n4 = pixels * C / 4;
-  k_lif_step<<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(x, scale, shift, fecs, mem, bits_prev,
-                                                                             bits, n4, C, thresh, decay);
+  const int64_t n4_round = (n4 + 31) & ~int64_t(31);
+  k_ecs_step<<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(p, n4, n4_round, C);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }

@@ -1,8 +1,9 @@
 // ECS-LIF forward (mem_update, models/common.py:236-309) as a per-timestep pipeline:
 //   step 0        : k_lif_first            mem_0 = x_0, s_0 = mem_0 > thresh          (streaming)
 //   step t -> t+1 : k_spread_dw            A = dw3x3(s_t) + b as bf16 hi[/lo]          (streaming)
-//                   k_umma_gemm<kEpiEcs>   e_t = alpha*(A*Wpw^T + b) + kappa*e_{t-1};  f_t = beta*tanh(e_t);
-//                                          mem_{t+1} = mem_t*decay*(1-s_t) + x_{t+1} + f_t; s_{t+1}
+//                   k_umma_gemm (tcgen05)  S = A * Wpw^T                               (tensor cores)
+//                   k_ecs_step             e_t = alpha*(S + b) + kappa*e_{t-1};  f_t = beta*tanh(e_t);
+//                                          mem_{t+1} = mem_t*decay*(1-s_t) + x_{t+1} + f_t; s_{t+1}   (streaming)
 // Spikes leave as bit-packed words; membrane / ECS state live in the caller-provided workspace.
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
@@ -13,7 +14,7 @@ static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 extern "C" size_t ecsy_lif_ecs_ws_bytes(int T, int64_t N, int H, int W, int C, int splits) {
   const size_t mc = static_cast<size_t>(N) * H * W * C;
   size_t b = 512;
-  b += 2 * align256(mc * 4);                    // mem, ecs
+  b += 3 * align256(mc * 4);                    // mem, ecs, spread
   b += static_cast<size_t>(splits) * align256(mc * 2);  // dw output planes
   (void)T;
   return b;
@@ -41,6 +42,7 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
   uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
   float* mem = reinterpret_cast<float*>(p); p += align256(mc * 4);
   float* ecs = reinterpret_cast<float*>(p); p += align256(mc * 4);
+  float* spread = reinterpret_cast<float*>(p); p += align256(mc * 4);
   __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(p); p += align256(mc * 2);
   __nv_bfloat16* a_lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
   const int64_t words = M * (C / 32);
@@ -51,25 +53,27 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
   for (int t = 0; t + 1 < T; ++t) {
     rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, a_hi, a_lo, (int)N, H, W, C, st);
     if (rc) return rc;
-    EcsStepArgs s{};
+    rc = ecsy_umma_dense(a_hi, a_lo, M, C, pw_packed, splits, spread, C, nullptr, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    EcsStep s{};
+    s.spread = spread; s.pw_b = pw_b;
     s.x_next = x + (t + 1) * x_tstride;
-    s.in_scale = in_scale; s.in_shift = in_shift; s.pw_b = pw_b;
-    if (mem_save) {
-      // keep every membrane for the backward pass: read step t, write step t+1
-      s.mem = mem_save + (size_t)t * mc;
-      s.mem_save = mem_save + (size_t)(t + 1) * mc;
-      s.store_mem = 0;
-      s.ecs = ecs;
+    s.in_scale = in_scale; s.in_shift = in_shift;
+    const bool more = t + 2 < T;
+    if (mem_save) {  // keep every membrane for the backward pass: read step t, write step t+1
+      s.mem_in = mem_save + (size_t)t * mc;
+      s.mem_out = mem_save + (size_t)(t + 1) * mc;
     } else {
-      s.mem = mem; s.mem_save = nullptr; s.ecs = ecs;
-      s.store_mem = (t + 2 < T) ? 1 : 0;
+      s.mem_in = mem;
+      s.mem_out = more ? mem : nullptr;
     }
-    s.store_ecs = (t + 2 < T) ? 1 : 0;
+    s.ecs = ecs;
+    s.store_ecs = more ? 1 : 0;
     s.bits_t = spikes + t * words;
     s.bits_next = spikes + (t + 1) * words;
     s.first = (t == 0) ? 1 : 0;
     s.thresh = thresh; s.decay = decay; s.alpha = alpha; s.beta = beta; s.kappa = kappa;
-    rc = ecsy_umma_ecs_step(a_hi, a_lo, M, C, pw_packed, splits, s, st);
+    rc = ecsy_launch_ecs_step(s, M, C, st);
     if (rc) return rc;
   }
   return ECSY_OK;

@@ -15,8 +15,6 @@
 //                       loaded by TMA.  With B_SPLIT=2 (and A_SPLIT=2 for real-valued A) the products
 //                       A_hi*B_hi + A_lo*B_hi + A_hi*B_lo reproduce fp32 weights to ~2^-17.
 //   EPI = kEpiConv    : y = acc*scale[c] + shift[c] (+ residual) -> fp32 NHWC   (tdBN folded)
-//   EPI = kEpiEcs     : ECS-LIF step: ecs/tanh feedback, membrane charge, threshold, bit-packed
-//                       spikes of step t+1 (models/common.py:263-281).
 //
 // Warp roles: 0-3 epilogue (TMEM lane quarter = warp id), 4 TMA producer, 5 MMA issuer + TMEM
 // allocator, 6-9 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
@@ -57,23 +55,6 @@ struct EpiConv {
   int ldc;                // Cout
 };
 
-struct EpiEcs {
-  const float* x_next;     // [M][C] input current of step t+1
-  const float* in_scale;   // optional folded tdBN on x
-  const float* in_shift;
-  const float* pw_b;       // [C]
-  float* mem;              // [M][C] membrane of step t (in) -> t+1 (out)
-  float* ecs;              // [M][C] ECS state e_{t-1} (in) -> e_t (out)
-  const uint32_t* bits_t;  // spikes of step t   [M][C/32]
-  uint32_t* bits_next;     // spikes of step t+1 [M][C/32]
-  float* mem_save;         // optional: membrane of step t+1 kept for the backward pass
-  int C;
-  int first;               // e_{t-1} == 0 (t == 0): do not read ecs
-  int store_mem;           // another step follows: write the membrane back in place
-  int store_ecs;           // another step follows: write the ECS state back
-  float thresh, decay, alpha, beta, kappa;
-};
-
 struct SpikeGeom {
   const uint32_t* bits;  // [imgs][H][W][Cw]
   int imgs, H, W, Cw;    // Cw = Cin/32
@@ -96,11 +77,9 @@ template <int EPI>
 struct EpiSel;
 template <>
 struct EpiSel<0> { using type = EpiConv; };
-template <>
-struct EpiSel<1> { using type = EpiEcs; };
 
 constexpr int kATma = 0, kASpikes = 1;
-constexpr int kEpiConv = 0, kEpiEcs = 1;
+constexpr int kEpiConv = 0;
 
 __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
   // bit0 -> low bf16 (1.0 = 0x3F80), bit1 -> high bf16
@@ -341,48 +320,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
               *reinterpret_cast<float4*>(dst + 4 * q) = o;
             }
           }
-        } else {
-          const EpiEcs& e = ep;
-          if (valid) {
-            const int64_t off = pix * e.C + n0;
-            const uint32_t sprev = e.bits_t[pix * (e.C >> 5) + (n0 >> 5)];
-            uint32_t snext = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 xv = *reinterpret_cast<const float4*>(e.x_next + off + 4 * q);
-              if (e.in_scale != nullptr) {
-                const float4 s = *reinterpret_cast<const float4*>(e.in_scale + n0 + 4 * q);
-                const float4 b = *reinterpret_cast<const float4*>(e.in_shift + n0 + 4 * q);
-                xv.x = add_rn(mul_rn(xv.x, s.x), b.x); xv.y = add_rn(mul_rn(xv.y, s.y), b.y);
-                xv.z = add_rn(mul_rn(xv.z, s.z), b.z); xv.w = add_rn(mul_rn(xv.w, s.w), b.w);
-              }
-              const float4 mv = *reinterpret_cast<const float4*>(e.mem + off + 4 * q);
-              float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (!e.first) ev = *reinterpret_cast<const float4*>(e.ecs + off + 4 * q);
-              const float4 pb = *reinterpret_cast<const float4*>(e.pw_b + n0 + 4 * q);
-              float xin[4] = {xv.x, xv.y, xv.z, xv.w};
-              float mo[4] = {mv.x, mv.y, mv.z, mv.w};
-              float eo[4] = {ev.x, ev.y, ev.z, ev.w};
-              float bb[4] = {pb.x, pb.y, pb.z, pb.w};
-              float mn[4], en[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float s_acc = add_rn(__uint_as_float(v[4 * q + k]), bb[k]);       // spread(spike)
-                en[k] = add_rn(mul_rn(e.alpha, s_acc), mul_rn(e.kappa, eo[k]));        // common.py:277
-                const float fecs = mul_rn(e.beta, tanhf(en[k]));                       // common.py:278
-                const float keep = ((sprev >> (4 * q + k)) & 1u) ? 0.f : 1.f;          // 1 - spike
-                mn[k] = add_rn(add_rn(mul_rn(mul_rn(mo[k], e.decay), keep), xin[k]), fecs);  // :306-309
-                snext |= (mn[k] > e.thresh ? 1u : 0u) << (4 * q + k);
-              }
-              if (e.store_mem)
-                *reinterpret_cast<float4*>(e.mem + off + 4 * q) = make_float4(mn[0], mn[1], mn[2], mn[3]);
-              if (e.store_ecs)
-                *reinterpret_cast<float4*>(e.ecs + off + 4 * q) = make_float4(en[0], en[1], en[2], en[3]);
-              if (e.mem_save != nullptr)
-                *reinterpret_cast<float4*>(e.mem_save + off + 4 * q) = make_float4(mn[0], mn[1], mn[2], mn[3]);
-            }
-            e.bits_next[pix * (e.C >> 5) + (n0 >> 5)] = snext;
-          }
         }
       }
       tc_fence_before_sync();
@@ -598,29 +535,3 @@ int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const 
   return launch_bn<kATma, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
 }
 
-// One fused ECS-LIF step: point-wise spread GEMM + feedback + membrane update + threshold.
-int ecsy_umma_ecs_step(const void* a_hi, const void* a_lo, int64_t M, int C, const void* pw_packed, int splits,
-                       const EcsStepArgs& s, cudaStream_t st) {
-  ECSY_CHECK_ARG(C % 64 == 0 && M > 0, "ecs step: C=%d must be a multiple of 64", C);
-  const int BN = ecsy_pick_bn(C, splits);
-  ECSY_CHECK_ARG((splits == 2) == (a_lo != nullptr), "ecs step: lo plane required iff splits == 2");
-  CUtensorMap ta0, ta1{}, tb;
-  int rc = ecsy_tensor_map_bf16(a_hi, (uint64_t)M, (uint64_t)C, 128, &ta0);
-  if (rc) return rc;
-  if (a_lo) {
-    rc = ecsy_tensor_map_bf16(a_lo, (uint64_t)M, (uint64_t)C, 128, &ta1);
-    if (rc) return rc;
-  }
-  rc = ecsy_tensor_map_bf16(pw_packed, (uint64_t)splits * C, (uint64_t)C, (uint32_t)BN, &tb);
-  if (rc) return rc;
-  GemmArgs g{};
-  g.m_tiles = (int)((M + 127) / 128);
-  g.n_tiles = C / BN;
-  g.kb_total = C / 64;
-  g.M = M;
-  SpikeGeom sg{};
-  EpiEcs e{s.x_next, s.in_scale, s.in_shift, s.pw_b, s.mem, s.ecs, s.bits_t, s.bits_next, s.mem_save, C,
-           s.first, s.store_mem, s.store_ecs, s.thresh, s.decay, s.alpha, s.beta, s.kappa};
-  if (splits == 1) return launch_bn<kATma, 1, 1, kEpiEcs>(BN, ta0, ta1, tb, g, sg, e, 0, st);
-  return launch_bn<kATma, 2, 2, kEpiEcs>(BN, ta0, ta1, tb, g, sg, e, 0, st);
-}

@@ -4,22 +4,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-struct EcsStepArgs {
-  const float* x_next;
-  const float* in_scale;
-  const float* in_shift;
-  const float* pw_b;
-  float* mem;
-  float* ecs;
-  const uint32_t* bits_t;
-  uint32_t* bits_next;
-  float* mem_save;
-  int first;
-  int store_mem;
-  int store_ecs;
-  float thresh, decay, alpha, beta, kappa;
-};
-
 int ecsy_pick_bn(int cout, int splits);
 int ecsy_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out);
 int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits, float* out, const float* scale,
@@ -28,14 +12,24 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
 int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
                     int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
                     cudaStream_t st);
-int ecsy_umma_ecs_step(const void* a_hi, const void* a_lo, int64_t M, int C, const void* pw_packed, int splits,
-                       const EcsStepArgs& s, cudaStream_t st);
 
 // elementwise.cu launchers used by lif.cu
 int ecsy_launch_lif_first(const float* x, const float* scale, const float* shift, float* mem, uint32_t* bits,
                           int64_t pixels, int C, float thresh, cudaStream_t st);
-int ecsy_launch_lif_step(const float* x, const float* scale, const float* shift, const float* fecs, float* mem,
-                         const uint32_t* bits_prev, uint32_t* bits, int64_t pixels, int C, float thresh, float decay,
-                         cudaStream_t st);
+struct EcsStep {
+  const float* spread;     // [M][C] pw(dw(s_t)) without bias (GEMM output)
+  const float* pw_b;       // [C]
+  const float* x_next;     // [M][C] input current of step t+1
+  const float* in_scale;   // optional folded tdBN on x
+  const float* in_shift;
+  const float* mem_in;     // membrane of step t
+  float* mem_out;          // membrane of step t+1 (may alias mem_in; NULL = last step, not stored)
+  float* ecs;              // e_{t-1} in (unless first), e_t out (if store_ecs)
+  const uint32_t* bits_t;  // spikes of step t
+  uint32_t* bits_next;     // spikes of step t+1
+  int first, store_ecs;
+  float thresh, decay, alpha, beta, kappa;
+};
+int ecsy_launch_ecs_step(const EcsStep& s, int64_t pixels, int C, cudaStream_t st);
 int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
                           __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st);

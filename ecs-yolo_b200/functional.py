@@ -240,7 +240,7 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     if T > 1 and w is None:
         raise RuntimeError("lif_ecs: spread weights required for T > 1")
     flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
-    with _timed("lif_ecs", 1 + 2 * (T - 1)):
+    with _timed("lif_ecs", 1 + 3 * (T - 1)):
         _cabi.check(L.ecsy_lif_ecs_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
                                    _p(w.dw_w) if w else None, _p(w.dw_b) if w else None,
                                    _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits,
