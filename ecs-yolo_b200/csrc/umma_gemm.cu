@@ -17,7 +17,7 @@
 //   EPI = kEpiConv    : y = acc*scale[c] + shift[c] (+ residual) -> fp32 NHWC   (tdBN folded)
 //
 // Warp roles: 0-3 epilogue (TMEM lane quarter = warp id), 4 TMA producer, 5 MMA issuer + TMEM
-// allocator, 6-9 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
+// allocator, 6-7 spike patch loaders, 8-15 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
 // full/empty mbarriers; two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 #include <map>
@@ -34,6 +34,9 @@ namespace {
 
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kLoadWarps = 2;              // spike patch loader warps (run one tile ahead)
+constexpr int kExpWarps = 8;               // spike expander warps, grouped per pipeline stage
+constexpr int kSpikeThreads = 192 + (kLoadWarps + kExpWarps) * 32;
 
 struct SharedCtl {
   uint64_t full_a[kMaxStages];
@@ -41,6 +44,8 @@ struct SharedCtl {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t patch_full[2];
+  uint64_t patch_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -70,7 +75,9 @@ struct SpikeGeom {
 struct GemmArgs {
   int m_tiles, n_tiles, kb_total, stages;
   int64_t M;       // valid rows (kATma) / unused (kASpikes)
-  uint32_t patch_off;  // byte offset of the patch buffer in dynamic smem
+  uint32_t patch_off;  // byte offset of the two patch buffers in dynamic smem
+  uint32_t patch_stride;  // bytes between the two patch buffers
+  int wpg;             // expander warps per stage group (kExpWarps / stages)
 };
 
 template <int EPI>
@@ -87,7 +94,7 @@ __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
 }
 
 template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
-__global__ void __launch_bounds__(A_MODE == kASpikes ? 320 : 192, 1)
+__global__ void __launch_bounds__(A_MODE == kASpikes ? kSpikeThreads : 192, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
             const __grid_constant__ CUtensorMap tm_b, const GemmArgs g, const SpikeGeom sg,
             const typename EpiSel<EPI>::type ep) {
@@ -98,7 +105,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
   constexpr int kStageBytes = A_SPLIT * kATileBytes + B_SPLIT * kBTileBytes;
   constexpr int kTmemCols = 2 * BN;  // two accumulator buffers: 128, 256 or 512 columns
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + (size_t)g.stages * kStageBytes);
-  uint32_t* patch = reinterpret_cast<uint32_t*>(smem + g.patch_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,15 +117,23 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       if (A_SPLIT == 2) tma_prefetch_desc(&tm_a1);
     }
     for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&ctl->full_a[s], 128);
+      mbar_init(&ctl->full_a[s], g.wpg);
       mbar_init(&ctl->full_b[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ctl->tmem_full[b], 1);
       mbar_init(&ctl->tmem_empty[b], 128);
+      mbar_init(&ctl->patch_full[b], kLoadWarps);
+      mbar_init(&ctl->patch_empty[b], kExpWarps);
     }
     mbar_fence_init();
+  }
+  // byte -> eight bf16 {0,1} lookup table for the expanders
+  __shared__ uint4 lut[A_MODE == kASpikes ? 256 : 1];
+  if (A_MODE == kASpikes) {
+    for (int e = threadIdx.x; e < 256; e += blockDim.x)
+      lut[e] = make_uint4(bits2_to_bf16x2(e), bits2_to_bf16x2(e >> 2), bits2_to_bf16x2(e >> 4), bits2_to_bf16x2(e >> 6));
   }
   if (warp == 5) tmem_alloc<kTmemCols>(&ctl->tmem_base);
   tc_fence_before_sync();
@@ -189,19 +203,20 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 6) {
-    // =============================== spike expanders ===============================
+  } else if (warp >= 6 && warp < 6 + kLoadWarps) {
+    // =============================== spike patch loaders ===============================
+    // Stage the tile's bit patch (with halo; zero padding and image edges -> 0) one tile ahead of the
+    // expanders.  Patch layout: [slab = 64 channels][patch pixel][2 words].
     if constexpr (A_MODE == kASpikes) {
-      const int r = threadIdx.x - 192;  // tile row 0..127
-      const int w_l = r & (sg.tw_b - 1);
-      const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
-      const int n_l = r >> (sg.tw_sh + sg.th_sh);
-      const int pp_base = (n_l * sg.Hp + h_l * sg.stride) * sg.Wp + w_l * sg.stride;
+      const int lt = threadIdx.x - 192;  // 0 .. 63
+      constexpr int kLT = kLoadWarps * 32;
       const int Cw = sg.Cw;
       const int patch_words = sg.PP * Cw;
       const int tiles_hw = sg.tiles_h * sg.tiles_w;
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        uint32_t* patch = reinterpret_cast<uint32_t*>(smem + g.patch_off + buf * g.patch_stride);
         const int m_tile = tile / g.n_tiles;
         const int tn = m_tile / tiles_hw;
         const int rem = m_tile - tn * tiles_hw;
@@ -209,15 +224,14 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
         const int img0 = tn * sg.tn_b;
         const int hi0 = th * sg.th_b * sg.stride - sg.pad;
         const int wi0 = tw * sg.tw_b * sg.stride - sg.pad;
-        // all expanders finished reading the previous tile's patch
-        named_bar_sync(1, 128);
-        for (int base = 0; base < patch_words; base += 4 * 128) {
-          // four independent global loads in flight per thread before the dependent smem stores
-          uint32_t v[4];
-          int dst[4];
+        mbar_wait(&ctl->patch_empty[buf], ph ^ 1);
+        for (int base = 0; base < patch_words; base += 8 * kLT) {
+          // eight independent global loads in flight per thread before the dependent smem stores
+          uint32_t v[8];
+          int dst[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * 128 + r;
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * kLT + lt;
             v[u] = 0;
             dst[u] = -1;
             if (idx < patch_words) {
@@ -234,34 +248,70 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 8; ++u)
             if (dst[u] >= 0) patch[dst[u]] = v[u];
         }
-        named_bar_sync(1, 128);
-        int slab = 0, ky = 0, kx = 0;
-        for (int kb = 0; kb < g.kb_total; ++kb) {
-          mbar_wait(&ctl->empty[stage], phase ^ 1);
-          const int pp = pp_base + ky * sg.Wp + kx;
-          const uint2 wd = *reinterpret_cast<const uint2*>(patch + ((slab * sg.PP + pp) << 1));
-          uint8_t* row = smem + (size_t)stage * kStageBytes + r * 128;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->patch_full[buf]);
+      }
+    }
+  } else if (warp >= 6 + kLoadWarps) {
+    // =============================== spike expanders ===============================
+    // Stage group g (= pipeline stage g) owns every K block c with c % stages == g, so `stages` K blocks
+    // are expanded concurrently and one block's latency chain (wait, LDS, STS, proxy fence, arrive) never
+    // sits on the critical path.  Each lane materialises whole 128-byte rows: 64 {0,1} bf16 values from
+    // two patch words via the byte LUT, written in the 128-byte-swizzled K-major layout.
+    if constexpr (A_MODE == kASpikes) {
+      const int ew = warp - 6 - kLoadWarps;    // 0 .. 7
+      const int S = g.stages;
+      const int grp = ew / g.wpg, sub = ew - grp * g.wpg;
+      const int rows_per_warp = 128 / g.wpg;   // 128, 64 or 32
+      const int nrow = rows_per_warp >> 5;     // rows per lane: 4, 2 or 1
+      int pp_base[4];
+      uint32_t row_off[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t byte = ((j < 4 ? wd.x : wd.y) >> (8 * (j & 3))) & 0xFFu;
-            uint4 o;
-            o.x = bits2_to_bf16x2(byte);
-            o.y = bits2_to_bf16x2(byte >> 2);
-            o.z = bits2_to_bf16x2(byte >> 4);
-            o.w = bits2_to_bf16x2(byte >> 6);
-            *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = o;
+      for (int i = 0; i < 4; ++i) {
+        const int r = sub * rows_per_warp + i * 32 + lane;
+        const int w_l = r & (sg.tw_b - 1);
+        const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
+        const int n_l = r >> (sg.tw_sh + sg.th_sh);
+        pp_base[i] = (n_l * sg.Hp + h_l * sg.stride) * sg.Wp + w_l * sg.stride;
+        row_off[i] = (uint32_t)r * 128u;
+      }
+      const uint32_t sw = (uint32_t)(lane & 7);  // r & 7 == lane & 7 for every row of this lane
+      uint8_t* tile_a = smem + (size_t)grp * kStageBytes;
+      uint32_t it = 0, cbase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        const uint32_t* patch = reinterpret_cast<const uint32_t*>(smem + g.patch_off + buf * g.patch_stride);
+        mbar_wait(&ctl->patch_full[buf], ph);
+        int kb = (int)((grp + S - (cbase % S)) % S);
+        for (; kb < g.kb_total; kb += S) {
+          const uint32_t c = cbase + kb;
+          mbar_wait(&ctl->empty[grp], ((c / S) & 1) ^ 1);
+          const int tap = kb / sg.nslab, slab = kb - tap * sg.nslab;
+          const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
+          const int tap_off = ky * sg.Wp + kx;
+          const uint32_t* pslab = patch + ((size_t)slab * sg.PP << 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < nrow) {
+              const uint2 wd = *reinterpret_cast<const uint2*>(pslab + ((pp_base[i] + tap_off) << 1));
+              uint8_t* row = tile_a + row_off[i];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t byte = ((j < 4 ? wd.x : wd.y) >> (8 * (j & 3))) & 0xFFu;
+                *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = lut[byte];
+              }
+            }
           }
           fence_proxy_async_smem();
-          mbar_arrive(&ctl->full_a[stage]);
-          if (++slab == sg.nslab) {
-            slab = 0;
-            if (++kx == sg.kw) { kx = 0; ++ky; }
-          }
-          if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->full_a[grp]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->patch_empty[buf]);
+        cbase += g.kb_total;
       }
     }
   } else {
@@ -405,27 +455,34 @@ template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
 int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmArgs g, const SpikeGeom& sg,
                const typename EpiSel<EPI>::type& ep, int patch_bytes, cudaStream_t st) {
   constexpr int stage_bytes = A_SPLIT * kATileBytes + B_SPLIT * BN * 128;
-  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 64 + patch_bytes;
-  int stages = (kSmemLimit - fixed) / stage_bytes;
+  auto kern = k_umma_gemm<BN, A_MODE, A_SPLIT, B_SPLIT, EPI>;
+  static int dyn_limit = 0;  // opt-in dynamic shared memory = 227 KB minus the kernel's static usage
+  if (dyn_limit == 0) {
+    cudaFuncAttributes fa;
+    ECSY_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const int lim = kSmemLimit - (int)fa.sharedSizeBytes;
+    ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    dyn_limit = lim;
+  }
+  const int patch_stride = (patch_bytes + 63) & ~63;
+  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 64 + 2 * patch_stride + 64;
+  int stages = (dyn_limit - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (A_MODE == kASpikes) stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : (stages >= 2 ? 2 : 0));
   if (stages < 2) {
     ecsy_set_error("umma gemm: shared memory budget allows only %d stage(s) (patch %d bytes)", stages, patch_bytes);
     return ECSY_ERR_UNSUPPORTED;
   }
   g.stages = stages;
+  g.wpg = A_MODE == kASpikes ? kExpWarps / stages : 1;
   const uint32_t ctl_off = (uint32_t)stages * stage_bytes;
   g.patch_off = (ctl_off + (uint32_t)sizeof(SharedCtl) + 63u) & ~63u;
-  const int smem = 1024 + (int)g.patch_off + patch_bytes;
-  auto kern = k_umma_gemm<BN, A_MODE, A_SPLIT, B_SPLIT, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_done = true;
-  }
+  g.patch_stride = (uint32_t)patch_stride;
+  const int smem = 1024 + (int)g.patch_off + 2 * patch_stride;
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, A_MODE == kASpikes ? 320 : 192, smem, st>>>(a0, a1, b, g, sg, ep);
+  kern<<<grid, A_MODE == kASpikes ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }
@@ -478,7 +535,7 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
       const int64_t cov = (int64_t)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th * ((imgs + tn - 1) / tn) * tn;
       const int Hp = (th - 1) * stride + k, Wp = (tw - 1) * stride + k;
       const int64_t patch_bytes = (int64_t)tn * Hp * Wp * Cw * 4;
-      if (patch_bytes > 72 * 1024) continue;
+      if (patch_bytes > 36 * 1024) continue;  // two patch buffers (the loaders run one tile ahead)
       const double score = (double)cov * (1.0 + 1e-3 * (double)patch_bytes / (128.0 * Cw * 4)) - 1e-6 * tw;
       if (score < best) {
         best = score;
