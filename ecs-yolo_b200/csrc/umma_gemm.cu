@@ -4,9 +4,9 @@
 //     D = A[128 x K] * B[BN x K]^T      (bf16 operands, fp32 accumulation in TMEM)
 // with
 //   A_MODE = kASpikes : A rows are output pixels of a convolution over BIT-PACKED spikes
-//                       ([imgs][H][W][Cin/32] uint32).  Expander warps stage the tile's spike patch
-//                       (with halo, zero padding) in shared memory once and materialise the bf16
-//                       {0,1} operand tile for every (tap, 64-channel slab) K block directly in the
+//                       ([imgs][H][W][Cin/32] uint32).  Expander warps read the 64 spike bits of every
+//                       (pixel + tap, 64-channel slab) from the bit tensor (8 bytes per operand row and K
+//                       block, L2-resident) and materialise the bf16 {0,1} operand tile directly in the
 //                       128-byte-swizzled UMMA layout -- spikes never exist as bf16/fp32 in HBM.
 //                       (Snn_Conv2d on spikes, models/common.py:593-624.)
 //   A_MODE = kATma    : A is a row-major bf16 matrix [M][K] in HBM loaded by TMA (ECS point-wise
@@ -17,7 +17,7 @@
 //   EPI = kEpiConv    : y = acc*scale[c] + shift[c] (+ residual) -> fp32 NHWC   (tdBN folded)
 //
 // Warp roles: 0-3 epilogue (TMEM lane quarter = warp id), 4 TMA producer, 5 MMA issuer + TMEM
-// allocator, 6-7 spike patch loaders, 8-15 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
+// allocator, 6-13 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
 // full/empty mbarriers; two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 #include <map>
@@ -34,9 +34,8 @@ namespace {
 
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kLoadWarps = 2;              // spike patch loader warps (run one tile ahead)
 constexpr int kExpWarps = 8;               // spike expander warps, grouped per pipeline stage
-constexpr int kSpikeThreads = 192 + (kLoadWarps + kExpWarps) * 32;
+constexpr int kSpikeThreads = 192 + kExpWarps * 32;
 
 struct SharedCtl {
   uint64_t full_a[kMaxStages];
@@ -44,8 +43,6 @@ struct SharedCtl {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t patch_full[2];
-  uint64_t patch_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -75,8 +72,6 @@ struct SpikeGeom {
 struct GemmArgs {
   int m_tiles, n_tiles, kb_total, stages;
   int64_t M;       // valid rows (kATma) / unused (kASpikes)
-  uint32_t patch_off;  // byte offset of the two patch buffers in dynamic smem
-  uint32_t patch_stride;  // bytes between the two patch buffers
   int wpg;             // expander warps per stage group (kExpWarps / stages)
 };
 
@@ -124,16 +119,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ctl->tmem_full[b], 1);
       mbar_init(&ctl->tmem_empty[b], 128);
-      mbar_init(&ctl->patch_full[b], kLoadWarps);
-      mbar_init(&ctl->patch_empty[b], kExpWarps);
     }
     mbar_fence_init();
-  }
-  // byte -> eight bf16 {0,1} lookup table for the expanders
-  __shared__ uint4 lut[A_MODE == kASpikes ? 256 : 1];
-  if (A_MODE == kASpikes) {
-    for (int e = threadIdx.x; e < 256; e += blockDim.x)
-      lut[e] = make_uint4(bits2_to_bf16x2(e), bits2_to_bf16x2(e >> 2), bits2_to_bf16x2(e >> 4), bits2_to_bf16x2(e >> 6));
   }
   if (warp == 5) tmem_alloc<kTmemCols>(&ctl->tmem_base);
   tc_fence_before_sync();
@@ -203,115 +190,92 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 6 && warp < 6 + kLoadWarps) {
-    // =============================== spike patch loaders ===============================
-    // Stage the tile's bit patch (with halo; zero padding and image edges -> 0) one tile ahead of the
-    // expanders.  Patch layout: [slab = 64 channels][patch pixel][2 words].
-    if constexpr (A_MODE == kASpikes) {
-      const int lt = threadIdx.x - 192;  // 0 .. 63
-      constexpr int kLT = kLoadWarps * 32;
-      const int Cw = sg.Cw;
-      const int patch_words = sg.PP * Cw;
-      const int tiles_hw = sg.tiles_h * sg.tiles_w;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        uint32_t* patch = reinterpret_cast<uint32_t*>(smem + g.patch_off + buf * g.patch_stride);
-        const int m_tile = tile / g.n_tiles;
-        const int tn = m_tile / tiles_hw;
-        const int rem = m_tile - tn * tiles_hw;
-        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
-        const int img0 = tn * sg.tn_b;
-        const int hi0 = th * sg.th_b * sg.stride - sg.pad;
-        const int wi0 = tw * sg.tw_b * sg.stride - sg.pad;
-        mbar_wait(&ctl->patch_empty[buf], ph ^ 1);
-        for (int base = 0; base < patch_words; base += 8 * kLT) {
-          // eight independent global loads in flight per thread before the dependent smem stores
-          uint32_t v[8];
-          int dst[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * kLT + lt;
-            v[u] = 0;
-            dst[u] = -1;
-            if (idx < patch_words) {
-              const int cw = idx % Cw;
-              const int pp = idx / Cw;
-              const int wp = pp % sg.Wp;
-              const int t2 = pp / sg.Wp;
-              const int hp = t2 % sg.Hp;
-              const int nl = t2 / sg.Hp;
-              const int img = img0 + nl, hi = hi0 + hp, wi = wi0 + wp;
-              if (img < sg.imgs && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
-                v[u] = __ldg(sg.bits + (((int64_t)img * sg.H + hi) * sg.W + wi) * Cw + cw);
-              dst[u] = (((cw >> 1) * sg.PP + pp) << 1) + (cw & 1);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (dst[u] >= 0) patch[dst[u]] = v[u];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->patch_full[buf]);
-      }
-    }
-  } else if (warp >= 6 + kLoadWarps) {
+  } else if (warp >= 6) {
     // =============================== spike expanders ===============================
     // Stage group g (= pipeline stage g) owns every K block c with c % stages == g, so `stages` K blocks
-    // are expanded concurrently and one block's latency chain (wait, LDS, STS, proxy fence, arrive) never
-    // sits on the critical path.  Each lane materialises whole 128-byte rows: 64 {0,1} bf16 values from
-    // two patch words via the byte LUT, written in the 128-byte-swizzled K-major layout.
+    // are expanded concurrently and one block's latency chain (wait, load, STS, proxy fence, arrive) never
+    // sits on the critical path.  Each lane materialises whole 128-byte rows: the 64 spike bits of
+    // (pixel + tap, 64-channel slab) are read straight from the bit-packed tensor (L2-resident, 8 bytes per
+    // row and K block, prefetched one K block ahead; zero padding = predicated-off load) and written as 64
+    // {0,1} bf16 values in the 128-byte-swizzled K-major layout.
     if constexpr (A_MODE == kASpikes) {
-      const int ew = warp - 6 - kLoadWarps;    // 0 .. 7
-      const int S = g.stages;
+      const int ew = warp - 6;                 // 0 .. 7
+      const uint32_t S = (uint32_t)g.stages;
       const int grp = ew / g.wpg, sub = ew - grp * g.wpg;
       const int rows_per_warp = 128 / g.wpg;   // 128, 64 or 32
       const int nrow = rows_per_warp >> 5;     // rows per lane: 4, 2 or 1
-      int pp_base[4];
+      int n_l[4], h_l[4], w_l[4];
       uint32_t row_off[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = sub * rows_per_warp + i * 32 + lane;
-        const int w_l = r & (sg.tw_b - 1);
-        const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
-        const int n_l = r >> (sg.tw_sh + sg.th_sh);
-        pp_base[i] = (n_l * sg.Hp + h_l * sg.stride) * sg.Wp + w_l * sg.stride;
+        w_l[i] = r & (sg.tw_b - 1);
+        h_l[i] = (r >> sg.tw_sh) & (sg.th_b - 1);
+        n_l[i] = r >> (sg.tw_sh + sg.th_sh);
         row_off[i] = (uint32_t)r * 128u;
       }
       const uint32_t sw = (uint32_t)(lane & 7);  // r & 7 == lane & 7 for every row of this lane
       uint8_t* tile_a = smem + (size_t)grp * kStageBytes;
-      uint32_t it = 0, cbase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        const uint32_t* patch = reinterpret_cast<const uint32_t*>(smem + g.patch_off + buf * g.patch_stride);
-        mbar_wait(&ctl->patch_full[buf], ph);
-        int kb = (int)((grp + S - (cbase % S)) % S);
-        for (; kb < g.kb_total; kb += S) {
-          const uint32_t c = cbase + kb;
-          mbar_wait(&ctl->empty[grp], ((c / S) & 1) ^ 1);
-          const int tap = kb / sg.nslab, slab = kb - tap * sg.nslab;
-          const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
-          const int tap_off = ky * sg.Wp + kx;
-          const uint32_t* pslab = patch + ((size_t)slab * sg.PP << 1);
+      const int tiles_hw = sg.tiles_h * sg.tiles_w;
+      const uint32_t kbt = (uint32_t)g.kb_total;
+      const uint32_t my_tiles = blockIdx.x < (uint32_t)total_tiles
+                                    ? (uint32_t)(total_tiles - 1 - (int)blockIdx.x) / gridDim.x + 1 : 0u;
+      const uint32_t c_end = my_tiles * kbt;
+
+      auto load_rows = [&](uint32_t c, uint2 (&wd)[4]) {
+        const uint32_t ti = c / kbt;
+        const int kb = (int)(c - ti * kbt);
+        const int tile = (int)blockIdx.x + (int)ti * (int)gridDim.x;
+        const int m_tile = tile / g.n_tiles;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        const int tap = kb / sg.nslab, slab = kb - tap * sg.nslab;
+        const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
+        const int img0 = tn * sg.tn_b;
+        const int hi0 = th * sg.th_b * sg.stride - sg.pad + ky;
+        const int wi0 = tw * sg.tw_b * sg.stride - sg.pad + kx;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nrow) {
-              const uint2 wd = *reinterpret_cast<const uint2*>(pslab + ((pp_base[i] + tap_off) << 1));
-              uint8_t* row = tile_a + row_off[i];
+        for (int i = 0; i < 4; ++i) {
+          wd[i] = make_uint2(0u, 0u);
+          if (i < nrow) {
+            const int img = img0 + n_l[i], hi = hi0 + h_l[i] * sg.stride, wi = wi0 + w_l[i] * sg.stride;
+            if (img < sg.imgs && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
+              wd[i] = __ldg(reinterpret_cast<const uint2*>(
+                  sg.bits + (((int64_t)img * sg.H + hi) * sg.W + wi) * sg.Cw + slab * 2));
+          }
+        }
+      };
+
+      uint32_t c = (uint32_t)grp;
+      uint2 cur[4];
+      if (c < c_end) load_rows(c, cur);
+      while (c < c_end) {
+        uint2 nxt[4];
+        if (c + S < c_end) load_rows(c + S, nxt);
+        mbar_wait(&ctl->empty[grp], ((c / S) & 1) ^ 1);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t byte = ((j < 4 ? wd.x : wd.y) >> (8 * (j & 3))) & 0xFFu;
-                *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = lut[byte];
-              }
+        for (int i = 0; i < 4; ++i) {
+          if (i < nrow) {
+            uint8_t* row = tile_a + row_off[i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t byte = ((j < 4 ? cur[i].x : cur[i].y) >> (8 * (j & 3))) & 0xFFu;
+              uint4 o;
+              o.x = bits2_to_bf16x2(byte);
+              o.y = bits2_to_bf16x2(byte >> 2);
+              o.z = bits2_to_bf16x2(byte >> 4);
+              o.w = bits2_to_bf16x2(byte >> 6);
+              *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = o;
             }
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->full_a[grp]);
         }
+        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->patch_empty[buf]);
-        cbase += g.kb_total;
+        if (lane == 0) mbar_arrive(&ctl->full_a[grp]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        c += S;
       }
     }
   } else {
@@ -464,8 +428,8 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
     ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     dyn_limit = lim;
   }
-  const int patch_stride = (patch_bytes + 63) & ~63;
-  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 64 + 2 * patch_stride + 64;
+  (void)patch_bytes;
+  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 128;
   int stages = (dyn_limit - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (A_MODE == kASpikes) stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : (stages >= 2 ? 2 : 0));
@@ -476,9 +440,7 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   g.stages = stages;
   g.wpg = A_MODE == kASpikes ? kExpWarps / stages : 1;
   const uint32_t ctl_off = (uint32_t)stages * stage_bytes;
-  g.patch_off = (ctl_off + (uint32_t)sizeof(SharedCtl) + 63u) & ~63u;
-  g.patch_stride = (uint32_t)patch_stride;
-  const int smem = 1024 + (int)g.patch_off + 2 * patch_stride;
+  const int smem = 1024 + (int)ctl_off + (int)sizeof(SharedCtl) + 64;
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
@@ -535,7 +497,6 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
       const int64_t cov = (int64_t)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th * ((imgs + tn - 1) / tn) * tn;
       const int Hp = (th - 1) * stride + k, Wp = (tw - 1) * stride + k;
       const int64_t patch_bytes = (int64_t)tn * Hp * Wp * Cw * 4;
-      if (patch_bytes > 36 * 1024) continue;  // two patch buffers (the loaders run one tile ahead)
       const double score = (double)cov * (1.0 + 1e-3 * (double)patch_bytes / (128.0 * Cw * 4)) - 1e-6 * tw;
       if (score < best) {
         best = score;
