@@ -155,63 +155,92 @@ __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C)
 // ------------------------------------------------------------------------------------------
 // ECS spread, depthwise half (models/common.py:289-294 spread[0]): A[p][c] = b[c] + sum_tap
 // bit(p+tap, c) * w[tap][c], written as bf16 hi (+ lo residual) rows for the point-wise GEMM.
-// One thread: one pixel x 8 channels (one byte of spikes per tap); 9 taps, zero padding.
+// A thread owns 8 channels (one spike byte per pixel) with its 72 weights + 8 biases in registers and
+// slides a 3x3 byte window along a run of kDwRun pixels of one image row (3 byte loads per pixel);
+// zero padding = zero bytes.  fp32 accumulation in tap order (row-major 3x3).
 // ------------------------------------------------------------------------------------------
-__global__ void k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*[9][C]*/,
-                            const float* __restrict__ dw_b, __nv_bfloat16* __restrict__ a_hi,
-                            __nv_bfloat16* __restrict__ a_lo, int N, int H, int W, int C) {
+constexpr int kDwRun = 16;
+
+__global__ void __launch_bounds__(256)
+k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*[9][C]*/,
+            const float* __restrict__ dw_b, __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo,
+            int N, int H, int W, int C) {
   const int c8 = C >> 3;
-  const int64_t total = (int64_t)N * H * W * c8;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(bits);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int j = static_cast<int>(i % c8);
-    const int64_t p = i / c8;
-    const int w = static_cast<int>(p % W);
-    const int h = static_cast<int>((p / W) % H);
-    const int c0 = j * 8;
-    float acc[8];
-    {
-      float4 b0 = *reinterpret_cast<const float4*>(dw_b + c0);
-      float4 b1 = *reinterpret_cast<const float4*>(dw_b + c0 + 4);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
+  const int nseg = (W + kDwRun - 1) / kDwRun;
+  const int64_t items = (int64_t)N * H * nseg * c8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;   // a multiple of c8 (host guarantees)
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cg = static_cast<int>(i0 % c8);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(bits) + cg;
+  float w[72], bias[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = *reinterpret_cast<const float4*>(dw_w + t * C + cg * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(dw_w + t * C + cg * 8 + 4);
+    w[t * 8 + 0] = w0.x; w[t * 8 + 1] = w0.y; w[t * 8 + 2] = w0.z; w[t * 8 + 3] = w0.w;
+    w[t * 8 + 4] = w1.x; w[t * 8 + 5] = w1.y; w[t * 8 + 6] = w1.z; w[t * 8 + 7] = w1.w;
+  }
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(dw_b + cg * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(dw_b + cg * 8 + 4);
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
+  for (int64_t i = i0; i < items; i += stride) {
+    int64_t run = i / c8;
+    const int seg = static_cast<int>(run % nseg);
+    run /= nseg;
+    const int h = static_cast<int>(run % H);
+    const int64_t img = run / H;
+    const int x0 = seg * kDwRun;
+    const int x1 = min(x0 + kDwRun, W);
+    const uint8_t* rowp[3];
+    bool rok[3];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int hh = h + ky - 1;
-      if (hh < 0 || hh >= H) continue;
+      rok[ky] = hh >= 0 && hh < H;
+      rowp[ky] = bytes + ((img * H + (rok[ky] ? hh : h)) * W) * (int64_t)c8;
+    }
+    uint32_t win[3][3];  // [ky][kx]: columns x-1, x, x+1
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ww = w + kx - 1;
-        if (ww < 0 || ww >= W) continue;
-        const uint32_t m = bytes[(p + (int64_t)(ky - 1) * W + (kx - 1)) * (C >> 3) + j];
-        if (m == 0) continue;
-        const float* wt = dw_w + (ky * 3 + kx) * C + c0;
-        float4 w0 = *reinterpret_cast<const float4*>(wt);
-        float4 w1 = *reinterpret_cast<const float4*>(wt + 4);
-        // accumulation order = tap order of the reference's 3x3 kernel (row-major), fp32
-        if (m & 1u) acc[0] += w0.x;
-        if (m & 2u) acc[1] += w0.y;
-        if (m & 4u) acc[2] += w0.z;
-        if (m & 8u) acc[3] += w0.w;
-        if (m & 16u) acc[4] += w1.x;
-        if (m & 32u) acc[5] += w1.y;
-        if (m & 64u) acc[6] += w1.z;
-        if (m & 128u) acc[7] += w1.w;
+    for (int ky = 0; ky < 3; ++ky) {
+      win[ky][0] = 0;
+      win[ky][1] = (rok[ky] && x0 - 1 >= 0) ? rowp[ky][(int64_t)(x0 - 1) * c8] : 0u;
+      win[ky][2] = rok[ky] ? rowp[ky][(int64_t)x0 * c8] : 0u;
+    }
+    for (int x = x0; x < x1; ++x) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[ky][0] = win[ky][1];
+        win[ky][1] = win[ky][2];
+        win[ky][2] = (rok[ky] && x + 1 < W) ? rowp[ky][(int64_t)(x + 1) * c8] : 0u;
       }
-    }
-    uint32_t hi[4], lo[4];
+      float acc[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * q]), h1 = __float2bfloat16_rn(acc[2 * q + 1]);
-      hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * q] - __bfloat162float(h0));
-      __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * q + 1] - __bfloat162float(h1));
-      lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      for (int k = 0; k < 8; ++k) acc[k] = bias[k];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t m = win[ky][kx];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (m & (1u << k)) acc[k] += w[(ky * 3 + kx) * 8 + k];
+        }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * q]), h1 = __float2bfloat16_rn(acc[2 * q + 1]);
+        hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * q] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * q + 1] - __bfloat162float(h1));
+        lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      const int64_t o = ((img * H + h) * W + x) * (int64_t)c8 + cg;
+      reinterpret_cast<uint4*>(a_hi)[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    reinterpret_cast<uint4*>(a_hi)[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -262,18 +291,27 @@ __global__ void k_bn_partial(const float* __restrict__ x, int64_t rows, int C, i
 
 __global__ void k_bn_final(const double* __restrict__ part, int blocks, int C, double inv_count,
                            float* __restrict__ mean, float* __restrict__ var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel: lanes stride over the per-block partials, fixed-order shuffle reduction
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0, q = 0;
-  for (int b = 0; b < blocks; ++b) {
+  for (int b = lane; b < blocks; b += 32) {
     s += part[(int64_t)b * 2 * C + c];
     q += part[(int64_t)b * 2 * C + C + c];
   }
-  const double m = s * inv_count;
-  double v = q * inv_count - m * m;
-  if (v < 0) v = 0;
-  mean[c] = static_cast<float>(m);
-  var[c] = static_cast<float>(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double m = s * inv_count;
+    double v = q * inv_count - m * m;
+    if (v < 0) v = 0;
+    mean[c] = static_cast<float>(m);
+    var[c] = static_cast<float>(v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -505,8 +543,18 @@ int ecsy_launch_ecs_step(const EcsStep& p, int64_t pixels, int C, cudaStream_t s
 
 int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
                           __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st) {
-  const int64_t total = (int64_t)N * H * W * (C / 8);
-  k_spread_dw<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
+  const int c8 = C / 8;
+  if (c8 < 1 || c8 > 256) {
+    ecsy_set_error("spread_dw: C=%d out of range", C);
+    return ECSY_ERR_ARG;
+  }
+  // block size: a multiple of c8 (every thread keeps one channel group for all of its work items)
+  int lcm = c8;
+  while (lcm % 32 != 0) lcm += c8;
+  const int bd = lcm <= 256 ? (256 / lcm) * lcm : (256 / c8) * c8;
+  const int nseg = (W + kDwRun - 1) / kDwRun;
+  const int64_t items = (int64_t)N * H * nseg * c8;
+  k_spread_dw<<<grid_for(items, bd, ecsy_num_sms() * 4), bd, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }
@@ -535,7 +583,7 @@ extern "C" int ecsy_tdbn_stats(const float* x, int64_t rows, int C, float* mean,
   ECSY_CUDA(cudaFuncSetAttribute(k_bn_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   k_bn_partial<<<blocks, kThreads, smem, STREAM(stream)>>>(x, rows, C, rpb, static_cast<double*>(ws));
   ECSY_LAUNCH_CHECK();
-  k_bn_final<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(static_cast<const double*>(ws), blocks, C,
+  k_bn_final<<<(C * 32 + 255) / 256, 256, 0, STREAM(stream)>>>(static_cast<const double*>(ws), blocks, C,
                                                            1.0 / static_cast<double>(rows), mean, var_biased);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
