@@ -13,6 +13,7 @@ module-level global; ``mem_update.spread`` is created when the owning block is c
 channel count is known there) instead of on the first forward; no autograd graph is recorded yet
 (forward/inference and train-mode statistics only).
 """
+# NOTE: `Conv.conv` sees a REAL input (models/common.py:372), so it takes the im2col + tcgen05 path.
 from __future__ import annotations
 
 import weakref
@@ -81,14 +82,23 @@ class mem_update(nn.Module):
         return _cached(self, "lif", (dw.weight, dw.bias, pw.weight, pw.bias),
                        lambda: F_.make_lif_w(dw.weight, dw.bias, pw.weight, pw.bias))
 
+    def analog(self, x: Act, affine=None) -> Act:
+        """act=True: real-valued silu(mem) outputs (class Conv)."""
+        if self.spread is None:
+            self._init_spread(x.C, x.data.device)
+        return F_.lif_silu(x, self._weights(), affine, self.ecs_tau, self.alpha, self.beta,
+                           inplace=bool(getattr(self.actFun, "inplace", False)))
+
     def spikes(self, x: Act, affine=None) -> Spikes:
         if self.act:
-            raise NotImplementedError("mem_update(act=True) (SiLU 'analog spikes', class Conv) is not ported yet")
+            raise RuntimeError("mem_update(act=True) produces real values: use analog()")
         if self.spread is None:
             self._init_spread(x.C, x.data.device)
         return F_.lif_ecs(x, self._weights(), affine, self.ecs_tau, self.alpha, self.beta)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.act:
+            return self.analog(Act.from_ref(x)).to_ref()
         sp = self.spikes(Act.from_ref(x))
         return _tag_spikes(sp.to_act().to_ref(), sp)
 
@@ -108,13 +118,13 @@ class Snn_Conv2d(nn.Conv2d):
         return k[0], s[0], p[0]
 
     def umma_ok(self) -> bool:
-        return self.groups == 1 and self.out_channels % 64 == 0 and self.bias is None
+        return self.out_channels % 64 == 0 and self.bias is None
 
     def _w(self) -> F_.ConvW:
         k, s, p = self._geom()
-        umma = self.groups == 1 and self.out_channels % 64 == 0
+        umma = self.out_channels % 64 == 0 and self.in_channels % 64 == 0
         return _cached(self, "conv", (self.weight, self.bias),
-                       lambda: F_.make_conv_w(self.weight, self.bias, s, p, self.groups, umma, True))
+                       lambda: F_.make_conv_w(self.weight, self.bias, s, p, self.groups, umma, True, densify=True))
 
     def conv_spikes(self, sp: Spikes, scale=None, shift=None, residual: Optional[Act] = None) -> Act:
         if self.umma_ok() and self.in_channels % 64 == 0:
@@ -151,6 +161,8 @@ class BatchNorm3d2(nn.BatchNorm3d):
 class _tdbn(nn.Module):
     """Threshold-dependent BN over (N, T, H, W) (models/common.py:668-691)."""
 
+    stat_updates = 1  # DDetect evaluates its branches twice per forward (models/yolo_snn.py:115-116)
+
     def scale_shift(self, y: Act):
         """Per-channel (scale, shift) with y_norm = y*scale + shift; updates running stats in training."""
         bn = self.bn
@@ -159,10 +171,11 @@ class _tdbn(nn.Module):
             with torch.no_grad():
                 if bn.track_running_stats:
                     n = float(y.T * y.N * y.H * y.W)
-                    bn.num_batches_tracked += 1
-                    m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                    bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
-                    bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1.0, 1.0))
+                    for _ in range(self.stat_updates):
+                        bn.num_batches_tracked += 1
+                        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                        bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
+                        bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1.0, 1.0))
                 scale = bn.weight * torch.rsqrt(var + bn.eps)
                 shift = bn.bias - mean * scale
             return scale.contiguous(), shift.contiguous()
@@ -332,8 +345,11 @@ class Conv_B(nn.Module):
         self.bn = batch_norm_2d(c2)
         self.act._init_spread(c1)
 
-    def run(self, a: Act) -> Act:
+    def run(self, a: Act, defer_affine: bool = False):
+        """-> Act, or (raw Act, (scale, shift)) in training when the caller applies the tdBN affine itself."""
         y, aff = _lif_conv_bn(self.act, self.conv, self.bn, a)
+        if defer_affine:
+            return y, aff
         return y if aff is None else F_.affine_add(y, aff[0], aff[1])
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -358,7 +374,12 @@ class Conv(nn.Module):
         self.act._init_spread(c2)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("Conv (SiLU analog-spike neuron, Stack B) is not ported yet")
+        a = Act.from_ref(x)
+        if self.bn.bn.training:
+            y = self.conv.conv_real(a)
+            return self.act.analog(y, self.bn.scale_shift(y)).to_ref()
+        sc, sh = self.bn.scale_shift(None)
+        return self.act.analog(self.conv.conv_real(a, sc, sh)).to_ref()
 
 
 class Conv_7(nn.Module):

@@ -37,33 +37,40 @@ __global__ void k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __rest
 }
 
 // A[m][k] (bf16 hi [+ lo]) for a real-valued NHWC input; m = output pixel, k = (ky*kw+kx)*Ci + ci,
-// zero padded to Kpad.  Each thread writes 8 consecutive k (16 bytes per plane).
+// zero padded to Kpad.  Each thread writes 8 consecutive k (16 bytes per plane).  The k -> (dy, dx, ci)
+// decomposition is tabulated once per block in shared memory (no per-element divisions).
 __global__ void k_im2col(const float* __restrict__ x, int64_t x_imgs, __nv_bfloat16* __restrict__ a_hi,
                          __nv_bfloat16* __restrict__ a_lo, int64_t imgs, int H, int W, int Ci, int Ho, int Wo, int kh,
                          int kw, int stride, int pad, int Kpad) {
+  extern __shared__ int2 ktab[];  // [Kpad]: {dy*W*Ci + dx*Ci + ci, (dy << 16) | dx}, dy = -1 marks padding
+  const int K = kh * kw * Ci;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    if (k < K) {
+      const int tap = k / Ci, ci = k - tap * Ci;
+      const int ky = tap / kw, kx = tap - ky * kw;
+      ktab[k] = make_int2((ky * W + kx) * Ci + ci, (ky << 16) | kx);
+    } else {
+      ktab[k] = make_int2(0, -1);
+    }
+  }
+  __syncthreads();
   const int k8 = Kpad >> 3;
   const int64_t total = imgs * Ho * Wo * k8;
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
-  const int K = kh * kw * Ci;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
     const int j = static_cast<int>(i % k8);
     int64_t m = i / k8;
     const int wo = static_cast<int>(m % Wo);
     const int ho = static_cast<int>((m / Wo) % Ho);
     const int64_t img = m / ((int64_t)Wo * Ho);
-    const float* src = x + (img % x_imgs) * (int64_t)H * W * Ci;
+    const int hi0 = ho * stride - pad, wi0 = wo * stride - pad;
+    const float* src = x + (img % x_imgs) * (int64_t)H * W * Ci + ((int64_t)hi0 * W + wi0) * Ci;
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int k = j * 8 + u;
-      float val = 0.f;
-      if (k < K) {
-        const int tap = k / Ci, ci = k - tap * Ci;
-        const int ky = tap / kw, kx = tap - ky * kw;
-        const int hi = ho * stride - pad + ky, wi = wo * stride - pad + kx;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = src[((int64_t)hi * W + wi) * Ci + ci];
-      }
-      v[u] = val;
+      const int2 e = ktab[j * 8 + u];
+      const int hi = hi0 + (e.y >> 16), wi = wi0 + (e.y & 0xFFFF);
+      v[u] = (e.y >= 0 && hi >= 0 && hi < H && wi >= 0 && wi < W) ? __ldg(src + e.x) : 0.f;
     }
     uint32_t hi4[4], lo4[4];
 #pragma unroll
@@ -169,7 +176,8 @@ extern "C" int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_
     uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
     __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
     __nv_bfloat16* a_lo = splits == 2 ? a_hi + M * Kpad : nullptr;
-    k_im2col<<<grid_for(M * (Kpad / 8), kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+    ECSY_CHECK_ARG(Kpad * 8 <= 48 * 1024, "real_conv_fwd: K=%d too large for the im2col table", Kpad);
+    k_im2col<<<grid_for(M * (Kpad / 8), kThreads, ecsy_num_sms() * 8), kThreads, Kpad * sizeof(int2), STREAM(stream)>>>(
         x, x_imgs, a_hi, a_lo, imgs, H, W, Cin, Ho, Wo, k, k, stride, pad, Kpad);
     ECSY_LAUNCH_CHECK();
     return ecsy_umma_dense(a_hi, a_lo, M, Kpad, w_packed, splits, out, Cout, scale, shift, nullptr, 0, STREAM(stream));

@@ -245,6 +245,138 @@ k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*
 }
 
 // ------------------------------------------------------------------------------------------
+// SiLU "analog spike" neuron: mem_update(act=True) inside class Conv (models/common.py:362-375, 263-281).
+// The neuron output is silu(mem) (real valued) and feeds the spread convs and the reset term.
+// `inplace` reproduces the reference models, whose initialize_weights() switches nn.SiLU to in-place
+// (utils/torch_utils.py:165-166) so that mem_old = mem.clone() captures silu(mem).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+__global__ void k_silu_first(const float* __restrict__ x, const float* __restrict__ scale,
+                             const float* __restrict__ shift, float* __restrict__ out, float* __restrict__ mem,
+                             int64_t n4, int C) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
+    if (scale != nullptr) {
+      const int c = static_cast<int>((i * 4) % C);
+      const float4 s = *reinterpret_cast<const float4*>(scale + c);
+      const float4 b = *reinterpret_cast<const float4*>(shift + c);
+      v.x = ecsy::add_rn(ecsy::mul_rn(v.x, s.x), b.x);
+      v.y = ecsy::add_rn(ecsy::mul_rn(v.y, s.y), b.y);
+      v.z = ecsy::add_rn(ecsy::mul_rn(v.z, s.z), b.z);
+      v.w = ecsy::add_rn(ecsy::mul_rn(v.w, s.w), b.w);
+    }
+    if (mem != nullptr) reinterpret_cast<float4*>(mem)[i] = v;
+    reinterpret_cast<float4*>(out)[i] = make_float4(silu_f(v.x), silu_f(v.y), silu_f(v.z), silu_f(v.w));
+  }
+}
+
+struct SiluStep {
+  const float* spread;
+  const float* pw_b;
+  const float* x_next;
+  const float* in_scale;
+  const float* in_shift;
+  const float* mem_old;   // mem_{t} (or silu(mem_t) when in-place) ; may alias out_prev
+  float* mem_out;         // raw membrane of step t+1 (NULL when in-place: out_next doubles as mem_old)
+  float* ecs;
+  const float* out_prev;  // silu(mem_t)
+  float* out_next;        // silu(mem_{t+1})
+  int first, store_ecs;
+  float decay, alpha, beta, kappa;
+};
+
+__global__ void k_silu_step(const SiluStep p, int64_t n4, int C) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = static_cast<int>((i * 4) % C);
+    float4 xv = ecsy::ldg_stream(reinterpret_cast<const float4*>(p.x_next) + i);
+    if (p.in_scale != nullptr) {
+      const float4 s = *reinterpret_cast<const float4*>(p.in_scale + c);
+      const float4 b = *reinterpret_cast<const float4*>(p.in_shift + c);
+      xv.x = ecsy::add_rn(ecsy::mul_rn(xv.x, s.x), b.x);
+      xv.y = ecsy::add_rn(ecsy::mul_rn(xv.y, s.y), b.y);
+      xv.z = ecsy::add_rn(ecsy::mul_rn(xv.z, s.z), b.z);
+      xv.w = ecsy::add_rn(ecsy::mul_rn(xv.w, s.w), b.w);
+    }
+    const float4 sv = reinterpret_cast<const float4*>(p.spread)[i];
+    const float4 mv = reinterpret_cast<const float4*>(p.mem_old)[i];
+    const float4 ov = reinterpret_cast<const float4*>(p.out_prev)[i];
+    float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!p.first) ev = reinterpret_cast<const float4*>(p.ecs)[i];
+    const float4 pb = *reinterpret_cast<const float4*>(p.pw_b + c);
+    const float xin[4] = {xv.x, xv.y, xv.z, xv.w}, sp[4] = {sv.x, sv.y, sv.z, sv.w};
+    const float mo[4] = {mv.x, mv.y, mv.z, mv.w}, eo[4] = {ev.x, ev.y, ev.z, ev.w};
+    const float so[4] = {ov.x, ov.y, ov.z, ov.w}, bb[4] = {pb.x, pb.y, pb.z, pb.w};
+    float mn[4], en[4], on[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float s_acc = ecsy::add_rn(sp[k], bb[k]);
+      en[k] = ecsy::add_rn(ecsy::mul_rn(p.alpha, s_acc), ecsy::mul_rn(p.kappa, eo[k]));
+      const float fecs = ecsy::mul_rn(p.beta, tanhf(en[k]));
+      const float keep = 1.0f - so[k];
+      mn[k] = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(mo[k], p.decay), keep), xin[k]), fecs);
+      on[k] = silu_f(mn[k]);
+    }
+    if (p.mem_out != nullptr) reinterpret_cast<float4*>(p.mem_out)[i] = make_float4(mn[0], mn[1], mn[2], mn[3]);
+    if (p.store_ecs) reinterpret_cast<float4*>(p.ecs)[i] = make_float4(en[0], en[1], en[2], en[3]);
+    reinterpret_cast<float4*>(p.out_next)[i] = make_float4(on[0], on[1], on[2], on[3]);
+  }
+}
+
+// Depthwise 3x3 (pad 1, bias) of a REAL-valued [N][H][W][C] tensor -> bf16 hi (+lo) GEMM operand rows.
+__global__ void k_dw_real(const float* __restrict__ s, const float* __restrict__ dw_w /*[9][C]*/,
+                          const float* __restrict__ dw_b, __nv_bfloat16* __restrict__ a_hi,
+                          __nv_bfloat16* __restrict__ a_lo, int N, int H, int W, int C) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)N * H * W * c8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int j = static_cast<int>(i % c8);
+    const int64_t pix = i / c8;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    float acc[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(dw_b + j * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(dw_b + j * 8 + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ww = w + kx - 1;
+        if (ww < 0 || ww >= W) continue;
+        const float* sp = s + (pix + (int64_t)(ky - 1) * W + (kx - 1)) * C + j * 8;
+        const float* wt = dw_w + (ky * 3 + kx) * C + j * 8;
+        const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(wt), w1 = *reinterpret_cast<const float4*>(wt + 4);
+        acc[0] = fmaf(s0.x, w0.x, acc[0]); acc[1] = fmaf(s0.y, w0.y, acc[1]);
+        acc[2] = fmaf(s0.z, w0.z, acc[2]); acc[3] = fmaf(s0.w, w0.w, acc[3]);
+        acc[4] = fmaf(s1.x, w1.x, acc[4]); acc[5] = fmaf(s1.y, w1.y, acc[5]);
+        acc[6] = fmaf(s1.z, w1.z, acc[6]); acc[7] = fmaf(s1.w, w1.w, acc[7]);
+      }
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * q]), h1 = __float2bfloat16_rn(acc[2 * q + 1]);
+      hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * q] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * q + 1] - __bfloat162float(h1));
+      lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    reinterpret_cast<uint4*>(a_hi)[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // tdBN statistics (models/common.py:674-679 -> BatchNorm3d over N,T,H,W): per-channel mean and
 // biased variance of x[rows][C].  Stage 1: each block reduces a row range to partial (sum, sumsq)
 // in double; stage 2: one thread per channel combines.  Deterministic (no atomics).
@@ -645,5 +777,67 @@ extern "C" int ecsy_ddetect_decode(const float* box, const float* cls, float* xs
   k_ddetect_decode<<<grid_for(total, 128, ecsy_num_sms() * 8), 128, 0, STREAM(stream)>>>(box, cls, xs, y, stride_px, N, H,
                                                                                       W, nc, a_total, a_off);
   ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+// ---- mem_update(act=True).forward (models/common.py:252-283 with self.act, class Conv :362-375) ----
+static inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
+
+extern "C" size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, int splits) {
+  const size_t mc = static_cast<size_t>(N) * H * W * C;
+  (void)T;
+  return 512 + 3 * al256(mc * 4) + static_cast<size_t>(splits) * al256(mc * 2);
+}
+
+extern "C" int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
+                                 const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b,
+                                 int splits, float* out, int inplace, int T, int64_t N, int H, int W, int C,
+                                 float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  cudaStream_t st = STREAM(stream);
+  ECSY_CHECK_ARG(x && out && T >= 1 && N > 0 && H > 0 && W > 0, "lif_silu_fwd: bad arguments");
+  ECSY_CHECK_ARG(C % 64 == 0, "lif_silu_fwd: C=%d must be a multiple of 64", C);
+  ECSY_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "lif_silu_fwd: scale/shift pair");
+  ECSY_CHECK_ARG(splits == 1 || splits == 2, "lif_silu_fwd: splits must be 1 or 2");
+  ECSY_CHECK_ARG(T == 1 || (dw_w && dw_b && pw_packed && pw_b), "lif_silu_fwd: spread weights missing");
+  const int64_t M = N * H * W;
+  const size_t mc = static_cast<size_t>(M) * C;
+  const size_t need = ecsy_lif_silu_ws_bytes(T, N, H, W, C, splits);
+  if (T > 1 && (ws == nullptr || ws_bytes < need)) {
+    ecsy_set_error("lif_silu_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  float* mem = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  float* ecs = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  float* spread = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
+  __nv_bfloat16* a_lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
+  const int64_t n4 = M * C / 4;
+  const int grid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
+  k_silu_first<<<grid, kThreads, 0, st>>>(x, in_scale, in_shift, out, (T > 1 && !inplace) ? mem : nullptr, n4, C);
+  ECSY_LAUNCH_CHECK();
+  for (int t = 0; t + 1 < T; ++t) {
+    const float* out_t = out + (size_t)t * mc;
+    k_dw_real<<<grid_for(M * (C / 8), kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(out_t, dw_w, dw_b, a_hi, a_lo,
+                                                                                     (int)N, H, W, C);
+    ECSY_LAUNCH_CHECK();
+    int rc = ecsy_umma_dense(a_hi, a_lo, M, C, pw_packed, splits, spread, C, nullptr, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    SiluStep s{};
+    s.spread = spread; s.pw_b = pw_b;
+    s.x_next = x + (t + 1) * x_tstride;
+    s.in_scale = in_scale; s.in_shift = in_shift;
+    const bool more = t + 2 < T;
+    s.mem_old = inplace ? out_t : mem;
+    s.mem_out = (!inplace && more) ? mem : nullptr;
+    s.ecs = ecs; s.store_ecs = more ? 1 : 0;
+    s.out_prev = out_t;
+    s.out_next = out + (size_t)(t + 1) * mc;
+    s.first = t == 0 ? 1 : 0;
+    s.decay = decay; s.alpha = alpha; s.beta = beta; s.kappa = kappa;
+    k_silu_step<<<grid, kThreads, 0, st>>>(s, n4, C);
+    ECSY_LAUNCH_CHECK();
+  }
   return ECSY_OK;
 }

@@ -195,11 +195,31 @@ class ConvW:
     pad: int
     groups: int
     splits: int
+    dense_groups: bool = False   # `packed` holds the block-diagonal dense form of a grouped weight
 
 
-def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, umma: bool, simt: bool) -> ConvW:
+def densify_grouped(weight: torch.Tensor, groups: int) -> torch.Tensor:
+    """[Co, Ci/g, kh, kw] grouped weight -> equivalent dense [Co, Ci, kh, kw] (zeros across groups), so a
+    grouped spike conv (DDetect cv2, models/yolo_snn.py:100-103) runs on the tensor-core path unchanged."""
+    Co, Cig, kh, kw = weight.shape
+    dense = torch.zeros(Co, Cig * groups, kh, kw, device=weight.device, dtype=torch.float32)
+    cog = Co // groups
+    for g in range(groups):
+        dense[g * cog:(g + 1) * cog, g * Cig:(g + 1) * Cig] = weight[g * cog:(g + 1) * cog].detach().float()
+    return dense
+
+
+def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, umma: bool, simt: bool,
+                densify: bool = False) -> ConvW:
     splits = get_splits()
     Co, Cig, kh, kw = weight.shape
+    if densify and groups > 1:
+        packed = pack_conv_weight(densify_grouped(weight, groups), splits) if umma else None
+        sw = weight.detach().float().permute(2, 3, 1, 0).contiguous() if simt else None
+        b = bias.detach().float().contiguous() if bias is not None else None
+        cw = ConvW(packed, sw, b, Co, Cig * groups, kh, stride, pad, groups, splits)
+        cw.dense_groups = True
+        return cw
     packed = pack_conv_weight(weight, splits) if umma else None
     sw = weight.detach().float().permute(2, 3, 1, 0).contiguous() if simt else None
     b = bias.detach().float().contiguous() if bias is not None else None
@@ -250,10 +270,33 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     return (sp, mem) if save_mem else sp
 
 
+def lif_silu(x: Act, w: Optional[LifW], affine=None, ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25,
+             inplace: bool = True) -> Act:
+    """mem_update(act=True).forward (models/common.py:252-283): real-valued silu(mem_t) outputs."""
+    T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
+    dev = x.data.device
+    out = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32)
+    L = _cabi.lib()
+    splits = w.splits if w is not None else 1
+    nws = L.ecsy_lif_silu_ws_bytes(T, N, H, W, C, splits) if T > 1 else 0
+    ws = torch.empty(max(nws, 16), device=dev, dtype=torch.uint8)
+    sc, sh = affine if affine is not None else (None, None)
+    if T > 1 and w is None:
+        raise RuntimeError("lif_silu: spread weights required for T > 1")
+    flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
+    with _timed("lif_silu", 1 + 3 * (T - 1)):
+        _cabi.check(L.ecsy_lif_silu_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
+                                        _p(w.dw_w) if w else None, _p(w.dw_b) if w else None,
+                                        _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits, _p(out),
+                                        1 if inplace else 0, T, N, H, W, C, float(decay), float(alpha), float(beta),
+                                        float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(), _st()), "lif_silu_fwd")
+    return Act(out, T)
+
+
 def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[Act] = None) -> Act:
     """Snn_Conv2d on spikes (models/common.py:609-624) with optional folded tdBN and shortcut add."""
     T, N, H, W = s.T, s.N, s.H, s.W
-    if w.groups != 1 or w.packed is None:
+    if (w.groups != 1 and not w.dense_groups) or w.packed is None:
         raise RuntimeError("spike_conv: grouped / unpacked weights go through real_conv on unpacked spikes")
     Ho = (H + 2 * w.pad - w.k) // w.stride + 1
     Wo = (W + 2 * w.pad - w.k) // w.stride + 1

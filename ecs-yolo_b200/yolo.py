@@ -60,7 +60,8 @@ class Detect(nn.Module):
             cw = _cached(conv, "detw", (conv.weight, conv.bias, wt), lambda: F_.make_conv_w(
                 conv.weight, conv.bias * wt.detach().sum(), 1, 0, 1, False, True))
             y = F_.real_conv(Act(feat.unsqueeze(0), 1), cw).data[0]      # [N,H,W,na*no]
-            stride_i = float(self.stride[i]) if z is not None else 1.0
+            st = getattr(self, "_strides", None)
+            stride_i = (st[i] if st else float(self.stride[i])) if z is not None else 1.0
             x[i] = F_.detect_decode(y, self.na, self.no, self.anchors[i].contiguous(), stride_i, z, off)
             off += self.na * y.shape[1] * y.shape[2]
         return x if self.training else (z, x)
@@ -95,7 +96,11 @@ class Model(nn.Module):
             if (a[-1] - a[0]).sign() != (m.stride[-1] - m.stride[0]).sign():
                 m.anchors[:] = m.anchors.flip(0)
             self.stride = m.stride
+            m._strides = [float(v) for v in m.stride]
             self._initialize_biases()
+        for mod in self.modules():  # utils/torch_utils.py:157-166 initialize_weights
+            if isinstance(mod, nn.SiLU):
+                mod.inplace = True
 
     def forward(self, x, augment=False, profile=False, visualize=False):
         """x: [N,3,H,W] image (direct coding: the same frame every timestep, yolo.py:248-251 -- kept as
@@ -134,7 +139,7 @@ class Model(nn.Module):
 _CHANNEL_MODULES = ("Conv", "Conv_1", "Conv_2", "Conv_B", "BasicBlock_1", "BasicBlock_2", "Concat_res2")
 
 
-def parse_model(d, ch, use_cupy=False):
+def parse_model(d, ch, use_cupy=False, heads=None):
     """YAML rows [from, number, module, args] -> nn.Sequential (models/yolo.py:434-553 for the in-scope
     module types).  Also returns each layer's total stride for the Detect strides."""
     anchors, nc, gd, gw = d['anchors'], d['nc'], d['depth_multiple'], d['width_multiple']
@@ -142,6 +147,8 @@ def parse_model(d, ch, use_cupy=False):
     no = na * (nc + 5)
     ns = {k: getattr(common, k) for k in dir(common)}
     ns.update(Detect=Detect, nn=nn)
+    ns.update(heads or {})
+    head_types = tuple((heads or {}).values())
     layers, save, c2 = [], [], ch[-1]
     red = []
     for i, (f, n, m, args) in enumerate(d['backbone'] + d['head']):
@@ -175,6 +182,8 @@ def parse_model(d, ch, use_cupy=False):
             args.append([ch[x] for x in f])
             if isinstance(args[1], int):
                 args[1] = [list(range(args[1] * 2))] * len(f)
+        elif head_types and m in head_types:
+            args.append([ch[x] for x in f])
         elif m is common.Sample:
             c2 = ch[f]
             r = base // int(args[1])

@@ -52,6 +52,15 @@ int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, c
                      uint32_t* spikes, float* mem_save, int T, int64_t N, int H, int W, int C, float thresh,
                      float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- mem_update(act=True).forward: the SiLU "analog spike" neuron of class Conv (models/common.py:362-375,
+ * 252-283).  out: [T][N][H][W][C] fp32 = silu(mem_t).  inplace != 0 reproduces the reference models, where
+ * initialize_weights() makes nn.SiLU in-place so that mem_old holds silu(mem) (utils/torch_utils.py:165-166). */
+size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
+int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
+                      const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b, int splits,
+                      float* out, int inplace, int T, int64_t N, int H, int W, int C, float decay, float alpha,
+                      float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Snn_Conv2d.forward on spikes (models/common.py:609-624), tcgen05 implicit GEMM.
  * out[imgs][Ho][Wo][Cout] = conv(spikes, W) * scale[c] + shift[c] (+ residual).  scale/shift: folded
  * eval-mode tdBN (models/common.py:674-679) or NULL; residual: the membrane shortcut (common.py:1216). */

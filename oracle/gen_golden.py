@@ -155,6 +155,68 @@ def main():
                         bn_calibrated={k: v.clone() for k, v in m.state_dict().items()
                                        if "running" in k or "tracked" in k}))
 
+    # ---------------- Stack B: SiLU neuron, Conv, DDetect, whole model ----------------
+    for name, spec in S.SILU_CASES.items():
+        C, Y, SN = ref_shim.load(spec["T"])
+        inp = S.lif_inputs(spec)
+        m = C.mem_update(act=True)
+        m.InitEcsSpread(inp["x"][0])
+        m.actFun.inplace = spec["inplace"]
+        with torch.no_grad():
+            m.spread[0].weight.copy_(inp["dw_w"]); m.spread[0].bias.copy_(inp["dw_b"])
+            m.spread[1].weight.copy_(inp["pw_w"]); m.spread[1].bias.copy_(inp["pw_b"])
+            out = m(inp["x"].clone())
+        save(name, dict(spec=spec, chk=S.checksum(*[inp[k] for k in sorted(inp)]), out=out))
+    for name, spec in S.CONVSILU_CASES.items():
+        C, Y, SN = ref_shim.load(spec["T"])
+        inp = S.convsilu_inputs(spec, O)
+        m = C.Conv(spec["cin"], spec["cout"], spec["k"], spec["s"])
+        m.act.actFun.inplace = True   # as inside a built model (initialize_weights)
+        m.train()
+        with torch.no_grad():
+            m(torch.zeros_like(inp["x"]))
+        m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+        with torch.no_grad():
+            out_train = m(inp["x"].clone())
+            m.eval()
+            out_eval = m(inp["x"].clone())
+        save(name, dict(spec=spec, chk=S.sd_checksum(inp["sd"]) + S.checksum(inp["x"]), out_train=out_train,
+                        out_eval=out_eval))
+    for name, spec in S.DDETECT_CASES.items():
+        C, Y, SN = ref_shim.load(spec["T"])
+        inp = S.ddetect_inputs(spec, O)
+        m = SN.DDetect(spec["nc"], spec["ch"])
+        m.stride = inp["stride"]
+        m.train()
+        with torch.no_grad():
+            m([torch.zeros_like(f) for f in inp["feats"]])
+        m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+        with torch.no_grad():
+            out_train = m([f.clone() for f in inp["feats"]])
+            bn_after = {"model.0." + k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+            m.eval()
+            y, xs = m([f.clone() for f in inp["feats"]])
+        save(name, dict(spec=spec, chk=S.sd_checksum(inp["sd"]) + S.checksum(*inp["feats"]),
+                        out_train=[o.clone() for o in out_train], bn_after=bn_after, y_eval=y, xs_eval=[o.clone() for o in xs]))
+    for name, spec in S.MODEL_B_CASES.items():
+        C, Y, SN = ref_shim.load(spec["T"])
+        path = os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")
+        cfg = yaml.safe_load(open(path))
+        inp = S.model_inputs(spec, O, cfg)
+        m = SN.DetectionModel(path)
+        m.load_state_dict(inp["sd"])
+        assert torch.equal(m.stride, inp["stride"])
+        rates = {}
+        hooks = [mod.register_forward_hook(lambda mod_, i_, o_, n_=n_: rates.__setitem__(n_, float(o_.mean())) or None)
+                 for n_, mod in m.named_modules() if isinstance(mod, C.mem_update)]
+        m.train()
+        with torch.no_grad():
+            out_train = [o.clone() for o in m(inp["x"])]
+        rates_train = dict(rates)
+        bn_after = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+        save(name, dict(spec=spec, chk=S.sd_checksum(inp["sd"]) + S.checksum(inp["x"]), out_train=out_train,
+                        rates_train=rates_train, bn_after=bn_after))
+
 
 if __name__ == "__main__":
     main()

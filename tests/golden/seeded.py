@@ -124,6 +124,20 @@ BLOCK_CASES = {
 MODEL_CASES = {
     "tiny_64": dict(cfg="tiny", T=4, N=2, H=64, W=64, seed=501),
 }
+# Stack B
+SILU_CASES = {
+    "silu_c64_t4_inplace": dict(T=4, N=2, C=64, H=6, W=8, seed=601, inplace=True),
+    "silu_c64_t4": dict(T=4, N=1, C=64, H=5, W=5, seed=602, inplace=False),
+}
+CONVSILU_CASES = {
+    "convsilu_128_64": dict(T=4, N=2, cin=128, cout=64, k=3, s=1, H=6, W=6, seed=611),
+}
+DDETECT_CASES = {
+    "ddetect_128": dict(T=4, N=2, ch=(128, 128), nc=3, H=8, W=8, seed=621),
+}
+MODEL_B_CASES = {
+    "tiny_b_64": dict(cfg="tiny_b", T=4, N=2, H=64, W=64, seed=631),
+}
 
 
 def lif_inputs(spec):
@@ -181,3 +195,29 @@ def model_inputs(spec, oracle, cfg):
     g = gen(spec["seed"] + 7)
     x = torch.rand(spec["N"], 3, spec["H"], spec["W"], generator=g)
     return dict(sd=sd, x=x, stride=stride)
+
+
+def convsilu_inputs(spec, oracle):
+    cfg = dict(nc=3, depth_multiple=1.0, width_multiple=1.0, anchors=2,
+               backbone=[[-1, 1, "Conv", [spec["cout"], spec["k"], spec["s"]]]], head=[])
+    sd = reseed_state_dict(oracle.init_state_dict(cfg, spec["T"], ch=spec["cin"]), spec["seed"])
+    g = gen(spec["seed"] + 7)
+    x = randn(g, spec["T"], spec["N"], spec["cin"], spec["H"], spec["W"], scale=0.6, shift=0.1)
+    return dict(cfg=cfg, sd=sd, x=x)
+
+
+def ddetect_inputs(spec, oracle):
+    """State dict of a bare DDetect head under the prefix 'model.0.' plus real-valued P4/P5 features."""
+    cfg = dict(nc=spec["nc"], depth_multiple=1.0, width_multiple=1.0, anchors=2, backbone=[],
+               head=[[[-1, -1], 1, "DDetect", ["nc"]]])
+    # build the key set by hand: plan_model needs channel bookkeeping for the 'from' layers
+    full = dict(nc=spec["nc"], depth_multiple=1.0, width_multiple=1.0, anchors=2,
+                backbone=[[-1, 1, "Conv_1", [spec["ch"][0], 1, 1]], [-1, 1, "Conv_1", [spec["ch"][1], 1, 1]]],
+                head=[[[0, 1], 1, "DDetect", ["nc"]]])
+    sd_all = oracle.init_state_dict(full, spec["T"], ch=3)
+    sd = {k.replace("model.2.", "model.0."): v for k, v in sd_all.items() if k.startswith("model.2.")}
+    sd = reseed_state_dict(sd, spec["seed"])
+    g = gen(spec["seed"] + 7)
+    feats = [randn(g, spec["T"], spec["N"], spec["ch"][0], spec["H"], spec["W"], scale=0.6, shift=0.1),
+             randn(g, spec["T"], spec["N"], spec["ch"][1], spec["H"] // 2, spec["W"] // 2, scale=0.6, shift=0.1)]
+    return dict(sd=sd, feats=feats, stride=torch.tensor([8.0, 16.0]))

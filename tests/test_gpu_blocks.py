@@ -171,3 +171,75 @@ def test_model_tiny(name):
     with torch.no_grad():
         zt, _ = det([gold["head_feats"][i].cuda() for i in det.f])
     assert rel_l2(zt.cpu(), gold["z_eval"]) < 1e-5
+
+
+# ---------------------------------------------------------------- Stack B
+@pytest.mark.parametrize("name", list(S.SILU_CASES))
+def test_silu_neuron(name):
+    E = ecsy()
+    F = E.functional
+    spec, gold = S.SILU_CASES[name], load_golden(name)
+    inp = S.lif_inputs(spec)
+    w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+    out = F.lif_silu(F.Act.from_ref(inp["x"].cuda()), w, inplace=spec["inplace"]).to_ref().cpu()
+    e = rel_l2(out, gold["out"])
+    assert e < 2e-5, e
+
+
+@pytest.mark.parametrize("name", list(S.CONVSILU_CASES))
+def test_conv_silu(name):
+    E = ecsy()
+    spec, gold = S.CONVSILU_CASES[name], load_golden(name)
+    inp = S.convsilu_inputs(spec, O)
+    m = E.common.Conv(spec["cin"], spec["cout"], spec["k"], spec["s"])
+    m.act.actFun.inplace = True
+    m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+    m = m.cuda().train()
+    with torch.no_grad():
+        e1 = rel_l2(m(inp["x"].cuda()).cpu(), gold["out_train"])
+        m.eval()
+        e2 = rel_l2(m(inp["x"].cuda()).cpu(), gold["out_eval"])
+    assert e1 < 5e-5 and e2 < 5e-5, (e1, e2)
+
+
+@pytest.mark.parametrize("name", list(S.DDETECT_CASES))
+def test_ddetect(name):
+    E = ecsy()
+    spec, gold = S.DDETECT_CASES[name], load_golden(name)
+    inp = S.ddetect_inputs(spec, O)
+    m = E.yolo_snn.DDetect(spec["nc"], spec["ch"])
+    m.stride = inp["stride"]
+    m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+    m = m.cuda().train()
+    with torch.no_grad():
+        out = m([f.cuda() for f in inp["feats"]])
+    # teacher-forced branch outputs: two LIF layers deep, near-threshold flips allowed at the 1e-3 level
+    for a, b in zip(out, gold["out_train"]):
+        assert rel_l2(a.cpu(), b) < 1e-3
+    sd = m.state_dict()
+    for k, v in gold["bn_after"].items():   # momentum applied twice per forward (double evaluation)
+        assert torch.allclose(sd[k[len("model.0."):]].cpu().float(), v.float(), rtol=1e-3, atol=1e-5), k
+    m.eval()
+    with torch.no_grad():
+        y, xs = m([f.cuda() for f in inp["feats"]])
+    assert rel_l2(y.cpu(), gold["y_eval"]) < 2e-3
+    for a, b in zip(xs, gold["xs_eval"]):
+        assert rel_l2(a.cpu(), b) < 2e-3
+
+
+@pytest.mark.parametrize("name", list(S.MODEL_B_CASES))
+def test_model_b_tiny(name):
+    E = ecsy()
+    spec, gold = S.MODEL_B_CASES[name], load_golden(name)
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")))
+    inp = S.model_inputs(spec, O, cfg)
+    m = E.yolo_snn.DetectionModel(E.cfg_path(spec["cfg"]))
+    m.load_state_dict(inp["sd"])
+    m = m.cuda().train()
+    with torch.no_grad():
+        out = m(inp["x"].cuda())
+    errs = [rel_l2(a.cpu(), b) for a, b in zip(out, gold["out_train"])]
+    assert max(errs) < 5e-2, errs
+    sd = m.state_dict()
+    for k, v in gold["bn_after"].items():
+        assert torch.allclose(sd[k].cpu().float(), v.float(), rtol=5e-3, atol=5e-4), k
