@@ -122,7 +122,7 @@ class Snn_Conv2d(nn.Conv2d):
 
     def _w(self) -> F_.ConvW:
         k, s, p = self._geom()
-        umma = self.out_channels % 64 == 0 and self.in_channels % 64 == 0
+        umma = self.out_channels % 64 == 0
         return _cached(self, "conv", (self.weight, self.bias),
                        lambda: F_.make_conv_w(self.weight, self.bias, s, p, self.groups, umma, True, densify=True))
 

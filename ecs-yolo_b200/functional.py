@@ -320,6 +320,8 @@ def real_conv(x: Act, w: ConvW, scale=None, shift=None, bias_mul: float = 1.0) -
     out = torch.empty(Tp, N, Ho, Wo, w.co, device=x.data.device, dtype=torch.float32)
     L = _cabi.lib()
     use_umma = w.packed is not None and w.groups == 1 and w.co % 64 == 0 and w.bias is None
+    if w.splits == 2 and w.ci < 64 and w.simt is not None:
+        use_umma = False  # parity mode: the tiny-K stem runs in plain fp32 (the 3-term bf16 split leaves ~6e-6)
     nws = L.ecsy_real_conv_ws_bytes(Tp * N, H, W, w.ci, w.co, w.k, w.stride, w.pad, w.groups, w.splits) if use_umma else 0
     ws = torch.empty(max(nws, 16), device=x.data.device, dtype=torch.uint8)
     if not use_umma and w.simt is None:
