@@ -19,8 +19,12 @@ SIGNATURES = {
     "ecsy_spikes_unpack": (_i, [_p, _p, _l, _i, _p]),
     "ecsy_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_lif_ecs_ws_bytes": (_z, [_i, _l, _i, _i, _i, _i]),
-    "ecsy_lif_ecs_fwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _l, _i, _i, _i,
+    "ecsy_lif_ecs_fwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _l, _i, _i, _i,
                               _f, _f, _f, _f, _f, _p, _z, _p]),
+    "ecsy_lif_ecs_bwd_ws_bytes": (_z, [_i, _l, _i, _i, _i, _i]),
+    "ecsy_lif_ecs_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i,
+                              _f, _f, _f, _f, _f, _f, _p, _z, _p]),
+    "ecsy_colsum2": (_i, [_p, _p, _l, _l, _i, _p, _p, _p, _z, _p]),
     "ecsy_lif_silu_ws_bytes": (_z, [_i, _l, _i, _i, _i, _i]),
     "ecsy_lif_silu_fwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _l, _i, _i, _i,
                                _f, _f, _f, _f, _p, _z, _p]),
@@ -34,6 +38,7 @@ SIGNATURES = {
     "ecsy_resample": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_tsum": (_i, [_p, _p, _f, _p, _i, _l, _p]),
     "ecsy_detect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _l, _l, _p]),
+    "ecsy_xty_bf16": (_i, [_p, _p, _p, _p, _l, _i, _i, _f, _p, _p]),
     "ecsy_ddetect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _l, _l, _p]),
 }
 

@@ -170,6 +170,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }
+// Same, for an MN-major operand tile as TMA writes a {64 elements, rows} box of a row-major [rows][cols]
+// matrix whose ROWS are the contraction index: 128-byte rows = 64 consecutive M/N elements of one k,
+// 8-row swizzle atoms 1024 bytes apart along k (SBO), 64-element M/N blocks `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4)                              // D format fp32
@@ -177,6 +189,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (1u << 10)                           // B format bf16
          | (static_cast<uint32_t>(N >> 3) << 17)  // N / 8
          | (static_cast<uint32_t>(M >> 4) << 24); // M / 16
+}
+// Both operands MN-major (contraction index is the slow axis of both tiles).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -143,6 +143,7 @@ __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C)
       }
       if (p.mem_out != nullptr) reinterpret_cast<float4*>(p.mem_out)[i] = make_float4(mn[0], mn[1], mn[2], mn[3]);
       if (p.store_ecs) reinterpret_cast<float4*>(p.ecs)[i] = make_float4(en[0], en[1], en[2], en[3]);
+      if (p.ecs_save != nullptr) reinterpret_cast<float4*>(p.ecs_save)[i] = make_float4(en[0], en[1], en[2], en[3]);
     }
     uint32_t w = nib << (4 * sub);
     w |= __shfl_xor_sync(0xffffffffu, w, 1);

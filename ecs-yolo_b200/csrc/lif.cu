@@ -22,7 +22,7 @@ extern "C" size_t ecsy_lif_ecs_ws_bytes(int T, int64_t N, int H, int W, int C, i
 
 extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                                 const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b,
-                                int splits, uint32_t* spikes, float* mem_save, int T, int64_t N, int H, int W, int C,
+                                int splits, uint32_t* spikes, float* mem_save, float* ecs_save, int T, int64_t N, int H, int W, int C,
                                 float thresh, float decay, float alpha, float beta, float kappa, void* ws,
                                 size_t ws_bytes, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -69,6 +69,7 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
     }
     s.ecs = ecs;
     s.store_ecs = more ? 1 : 0;
+    s.ecs_save = ecs_save ? ecs_save + (size_t)t * mc : nullptr;
     s.bits_t = spikes + t * words;
     s.bits_next = spikes + (t + 1) * words;
     s.first = (t == 0) ? 1 : 0;

@@ -1,0 +1,311 @@
+// Surrogate-gradient BPTT through the ECS-LIF neuron (backward of mem_update, models/common.py:236-309 with
+// ActFun.backward :66-79; derivation in SURVEY.md Appendix B).  Membranes m_t and ECS traces e_t are NOT kept
+// from the training forward: the caller re-runs ecsy_lif_ecs_fwd with mem_save / ecs_save right before this
+// call (recompute instead of store), so only the layer input and the spike bits live across the step.
+//
+// Reverse scan t = T-1 .. 0 with carries gm = dL/dm_{t+1}, ge = dL/de_{t+1}:
+//   ge_t = gm*beta*(1 - tanh(e_t)^2) + kappa*ge                                  k_lif_bwd_pre      (streaming)
+//   G1   = ge_t * Wpw                      (point-wise spread, transposed)        k_umma_gemm        (tcgen05)
+//   dWpw += alpha * ge_t^T * dw(s_t)       (contraction over pixels)              k_umma_xty         (tcgen05, MN-major)
+//   db_pw, db_dw, dWdw += alpha * per-channel pixel sums                          k_lif_bwd_reduce   (streaming)
+//   gs_t = gout_t + alpha * dw^T(G1);  gm_t = gs_t*sigma'(m_t) + gm*decay*(1 - s_t);  gx_t = gm_t
+//                                                                                 k_lif_bwd_post     (streaming)
+#include "ecsy_common.cuh"
+#include "../../include/ecsy.h"
+#include "umma_gemm.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work, int per_block, int max_blocks) {
+  int64_t g = (work + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
+         ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+
+// ge_t = gm_next*beta*(1-tanh^2(e_t)) + kappa*ge_next  -> fp32 carry (in place) + bf16 hi/lo GEMM operand
+__global__ void k_lif_bwd_pre(const float* __restrict__ gm_next, const float* __restrict__ ecs_t,
+                              float* __restrict__ ge /*in: ge_next (if has_next), out: ge_t*/, int has_next,
+                              __nv_bfloat16* __restrict__ ge_hi, __nv_bfloat16* __restrict__ ge_lo, int64_t n4,
+                              float beta, float kappa) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g = reinterpret_cast<const float4*>(gm_next)[i];
+    const float4 e = reinterpret_cast<const float4*>(ecs_t)[i];
+    float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_next) n = reinterpret_cast<const float4*>(ge)[i];
+    float th;
+    float4 o;
+    th = tanhf(e.x); o.x = g.x * beta * (1.0f - th * th) + kappa * n.x;
+    th = tanhf(e.y); o.y = g.y * beta * (1.0f - th * th) + kappa * n.y;
+    th = tanhf(e.z); o.z = g.z * beta * (1.0f - th * th) + kappa * n.z;
+    th = tanhf(e.w); o.w = g.w * beta * (1.0f - th * th) + kappa * n.w;
+    reinterpret_cast<float4*>(ge)[i] = o;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+    reinterpret_cast<uint2*>(ge_hi)[i] =
+        make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
+                   (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
+    if (ge_lo != nullptr)
+      reinterpret_cast<uint2*>(ge_lo)[i] =
+          make_uint2(pack_bf16x2(o.x - __bfloat162float(h0), o.y - __bfloat162float(h1)),
+                     pack_bf16x2(o.z - __bfloat162float(h2), o.w - __bfloat162float(h3)));
+  }
+}
+
+// Per-channel pixel sums for the spread parameter gradients: acc[0][c] = sum ge, acc[1][c] = sum G1,
+// acc[2+tap][c] = sum_p G1[p][c] * s_t[p + off(tap)][c].  Double atomics into a [11][C] scratch.
+__global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __restrict__ g1,
+                                 const uint32_t* __restrict__ bits, double* __restrict__ acc, int N, int H, int W,
+                                 int C) {
+  const int c4 = C >> 2;
+  const int tq = threadIdx.x % c4;         // channel quad (blockDim is a multiple of c4)
+  const int ty = threadIdx.x / c4, nty = blockDim.x / c4;
+  const int64_t pixels = (int64_t)N * H * W;
+  float s[11][4];
+#pragma unroll
+  for (int a = 0; a < 11; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[a][k] = 0.f;
+  const int64_t per_block = (pixels + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per_block;
+  const int64_t p1 = p0 + per_block < pixels ? p0 + per_block : pixels;
+  const int Cw = C >> 5;
+  for (int64_t p = p0 + ty; p < p1; p += nty) {
+    const float4 a = reinterpret_cast<const float4*>(ge + p * C)[tq];
+    const float4 b = reinterpret_cast<const float4*>(g1 + p * C)[tq];
+    s[0][0] += a.x; s[0][1] += a.y; s[0][2] += a.z; s[0][3] += a.w;
+    s[1][0] += b.x; s[1][1] += b.y; s[1][2] += b.z; s[1][3] += b.w;
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ww = w + kx - 1;
+        if (ww < 0 || ww >= W) continue;
+        const uint32_t word = bits[(p + (int64_t)(ky - 1) * W + (kx - 1)) * Cw + (tq >> 3)];
+        const uint32_t nib = (word >> (4 * (tq & 7))) & 0xFu;
+        const int t = 2 + ky * 3 + kx;
+        if (nib & 1u) s[t][0] += b.x;
+        if (nib & 2u) s[t][1] += b.y;
+        if (nib & 4u) s[t][2] += b.z;
+        if (nib & 8u) s[t][3] += b.w;
+      }
+    }
+  }
+  if (ty < nty) {
+#pragma unroll
+    for (int a = 0; a < 11; ++a)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(acc + (int64_t)a * C + tq * 4 + k, (double)s[a][k]);
+  }
+}
+
+// outputs += alpha * acc ; layouts: g_pw_b [C], g_dw_b [C], g_dw_w [9][C]
+__global__ void k_lif_bwd_reduce_final(const double* __restrict__ acc, float* __restrict__ g_pw_b,
+                                       float* __restrict__ g_dw_b, float* __restrict__ g_dw_w, int C, float alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 11 * C) return;
+  const int a = i / C, c = i - a * C;
+  const float v = alpha * static_cast<float>(acc[i]);
+  if (a == 0) g_pw_b[c] += v;
+  else if (a == 1) g_dw_b[c] += v;
+  else g_dw_w[(a - 2) * C + c] += v;
+}
+
+// gs = gout + alpha*dw^T(G1); gm = gs*sigma'(m_t) + gm_next*decay*(1-s_t); writes gm carry and gx[t].
+__global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*null at t=T-1*/,
+                               const float* __restrict__ dw_w, const float* __restrict__ mem_t,
+                               const uint32_t* __restrict__ bits_t, float* __restrict__ gm /*in: next, out: t*/,
+                               int has_next, float* __restrict__ gx, int N, int H, int W, int C, float thresh,
+                               float lens, float decay, float alpha) {
+  const int c4 = C >> 2;
+  const int64_t total = (int64_t)N * H * W * c4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float inv = 1.0f / (2.0f * lens);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int q = static_cast<int>(i % c4);
+    const int64_t p = i / c4;
+    float4 gs = reinterpret_cast<const float4*>(gout)[i];
+    if (g1 != nullptr) {
+      const int w = static_cast<int>(p % W);
+      const int h = static_cast<int>((p / W) % H);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h - (ky - 1);   // s[q] feeds out[q - off(tap)]
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ww = w - (kx - 1);
+          if (ww < 0 || ww >= W) continue;
+          const float4 g = reinterpret_cast<const float4*>(g1 + (p - (int64_t)(ky - 1) * W - (kx - 1)) * C)[q];
+          const float4 wt = *reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * C + q * 4);
+          acc.x = fmaf(g.x, wt.x, acc.x); acc.y = fmaf(g.y, wt.y, acc.y);
+          acc.z = fmaf(g.z, wt.z, acc.z); acc.w = fmaf(g.w, wt.w, acc.w);
+        }
+      }
+      gs.x = fmaf(alpha, acc.x, gs.x); gs.y = fmaf(alpha, acc.y, gs.y);
+      gs.z = fmaf(alpha, acc.z, gs.z); gs.w = fmaf(alpha, acc.w, gs.w);
+    }
+    const float4 m = reinterpret_cast<const float4*>(mem_t)[i];
+    float4 o;
+    o.x = fabsf(m.x - thresh) < lens ? gs.x * inv : 0.f;
+    o.y = fabsf(m.y - thresh) < lens ? gs.y * inv : 0.f;
+    o.z = fabsf(m.z - thresh) < lens ? gs.z * inv : 0.f;
+    o.w = fabsf(m.w - thresh) < lens ? gs.w * inv : 0.f;
+    if (has_next) {
+      const float4 gn = reinterpret_cast<const float4*>(gm)[i];
+      const uint32_t nib = (bits_t[p * (C >> 5) + (q >> 3)] >> (4 * (q & 7))) & 0xFu;
+      o.x += (nib & 1u) ? 0.f : gn.x * decay;
+      o.y += (nib & 2u) ? 0.f : gn.y * decay;
+      o.z += (nib & 4u) ? 0.f : gn.z * decay;
+      o.w += (nib & 8u) ? 0.f : gn.w * decay;
+    }
+    reinterpret_cast<float4*>(gm)[i] = o;
+    reinterpret_cast<float4*>(gx)[i] = o;
+  }
+}
+
+// per-channel sums over rows: sum_g[c] = sum g, sum_gx[c] = sum g*x  (tdBN / folded-affine backward)
+__global__ void k_colsum2(const float* __restrict__ g, const float* __restrict__ x, int64_t rows, int64_t x_rows,
+                          int C, double* __restrict__ acc /*[2][C]*/) {
+  const int c4 = C >> 2;
+  const int tq = threadIdx.x % c4, ty = threadIdx.x / c4, nty = blockDim.x / c4;
+  const int64_t per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * per_block;
+  const int64_t r1 = r0 + per_block < rows ? r0 + per_block : rows;
+  double sg[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+  float fg[4] = {0, 0, 0, 0}, fx[4] = {0, 0, 0, 0};
+  int cnt = 0;
+  for (int64_t r = r0 + ty; r < r1; r += nty) {
+    const float4 a = reinterpret_cast<const float4*>(g + r * C)[tq];
+    const float4 b = reinterpret_cast<const float4*>(x + (r % x_rows) * C)[tq];
+    fg[0] += a.x; fg[1] += a.y; fg[2] += a.z; fg[3] += a.w;
+    fx[0] += a.x * b.x; fx[1] += a.y * b.y; fx[2] += a.z * b.z; fx[3] += a.w * b.w;
+    if (++cnt == 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sg[k] += fg[k]; sx[k] += fx[k]; fg[k] = 0; fx[k] = 0; }
+      cnt = 0;
+    }
+  }
+  if (ty < nty) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(acc + tq * 4 + k, sg[k] + fg[k]);
+      atomicAdd(acc + C + tq * 4 + k, sx[k] + fx[k]);
+    }
+  }
+}
+
+__global__ void k_d2f(const double* __restrict__ a, float* __restrict__ o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = static_cast<float>(a[i]);
+}
+
+}  // namespace
+
+static inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
+
+extern "C" size_t ecsy_lif_ecs_bwd_ws_bytes(int T, int64_t N, int H, int W, int C, int splits) {
+  const size_t mc = static_cast<size_t>(N) * H * W * C;
+  (void)T;
+  // gm, ge, G1 (fp32) + ge planes + dw planes (bf16) + reduction scratch
+  return 512 + 3 * al256(mc * 4) + 2 * static_cast<size_t>(splits) * al256(mc * 2) + al256(11 * (size_t)C * 8);
+}
+
+extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const float* mem, const float* ecs,
+                                const float* dw_w, const float* dw_b, const void* pwT_packed, int splits, float* gx,
+                                float* g_dw_w, float* g_dw_b, float* g_pw_w, float* g_pw_b, int T, int64_t N, int H,
+                                int W, int C, float thresh, float lens, float decay, float alpha, float beta,
+                                float kappa, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ECSY_CHECK_ARG(gout && spikes && mem && gx && T >= 1 && N > 0 && H > 0 && W > 0, "lif_ecs_bwd: bad arguments");
+  ECSY_CHECK_ARG(C % 64 == 0 && C <= 1024, "lif_ecs_bwd: C=%d must be a multiple of 64, <= 1024", C);
+  ECSY_CHECK_ARG(splits == 1 || splits == 2, "lif_ecs_bwd: splits must be 1 or 2");
+  ECSY_CHECK_ARG(T == 1 || (ecs && dw_w && dw_b && pwT_packed && g_dw_w && g_dw_b && g_pw_w && g_pw_b),
+                 "lif_ecs_bwd: spread tensors missing");
+  const int64_t M = N * H * W;
+  const size_t mc = static_cast<size_t>(M) * C;
+  const size_t need = ecsy_lif_ecs_bwd_ws_bytes(T, N, H, W, C, splits);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("lif_ecs_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  float* gm = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  float* ge = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  float* g1 = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  __nv_bfloat16* ge_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
+  __nv_bfloat16* ge_lo = nullptr;
+  if (splits == 2) { ge_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2); }
+  __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
+  __nv_bfloat16* d_lo = nullptr;
+  if (splits == 2) { d_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2); }
+  double* acc = reinterpret_cast<double*>(p);
+  const int64_t words = M * (C / 32);
+  const int64_t n4 = M * C / 4;
+  const int egrid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
+  const int c4 = C / 4;
+  const int rbd = (256 / c4) * c4;  // reduce kernels: block size a multiple of c4 (C <= 1024 -> c4 <= 256)
+
+  for (int t = T - 1; t >= 0; --t) {
+    const bool spread = t <= T - 2;
+    const bool has_next = t < T - 1;
+    if (spread) {
+      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gm, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta,
+                                                kappa);
+      ECSY_LAUNCH_CHECK();
+      int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
+      if (rc) return rc;
+      rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, d_hi, d_lo, (int)N, H, W, C, st);
+      if (rc) return rc;
+      rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
+      if (rc) return rc;
+      ECSY_CUDA(cudaMemsetAsync(acc, 0, 11 * (size_t)C * sizeof(double), st));
+      k_lif_bwd_reduce<<<grid_for(M, 64, ecsy_num_sms() * 4), rbd, 0, st>>>(ge, g1, spikes + t * words, acc, (int)N, H, W,
+                                                                        C);
+      ECSY_LAUNCH_CHECK();
+      k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(acc, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      ECSY_LAUNCH_CHECK();
+    }
+    k_lif_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
+                                               spikes + t * words, gm, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H,
+                                               W, C, thresh, lens, decay, alpha);
+    ECSY_LAUNCH_CHECK();
+  }
+  return ECSY_OK;
+}
+
+// sum_g[c] = sum_rows g[r][c]; sum_gx[c] = sum_rows g[r][c]*x[r % x_rows][c]   (tdBN / affine backward)
+extern "C" int ecsy_colsum2(const float* g, const float* x, int64_t rows, int64_t x_rows, int C, float* sum_g,
+                            float* sum_gx, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ECSY_CHECK_ARG(g && x && sum_g && sum_gx && rows > 0 && x_rows > 0, "colsum2: bad arguments");
+  ECSY_CHECK_ARG(C % 4 == 0 && C <= 1024, "colsum2: C=%d", C);
+  if (ws == nullptr || ws_bytes < 2 * (size_t)C * 8 + 256) {
+    ecsy_set_error("colsum2: workspace too small");
+    return ECSY_ERR_WS;
+  }
+  double* acc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  ECSY_CUDA(cudaMemsetAsync(acc, 0, 2 * (size_t)C * sizeof(double), st));
+  const int c4 = C / 4;
+  const int bd = (256 / c4) * c4;
+  k_colsum2<<<grid_for(rows, 64, ecsy_num_sms() * 4), bd, 0, st>>>(g, x, rows, x_rows, C, acc);
+  ECSY_LAUNCH_CHECK();
+  k_d2f<<<(C + 255) / 256, 256, 0, st>>>(acc, sum_g, C);
+  ECSY_LAUNCH_CHECK();
+  k_d2f<<<(C + 255) / 256, 256, 0, st>>>(acc + C, sum_gx, C);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}

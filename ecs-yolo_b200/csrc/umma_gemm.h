@@ -25,6 +25,7 @@ struct EcsStep {
   const float* mem_in;     // membrane of step t
   float* mem_out;          // membrane of step t+1 (may alias mem_in; NULL = last step, not stored)
   float* ecs;              // e_{t-1} in (unless first), e_t out (if store_ecs)
+  float* ecs_save;         // optional copy of e_t kept for the backward pass
   const uint32_t* bits_t;  // spikes of step t
   uint32_t* bits_next;     // spikes of step t+1
   int first, store_ecs;
@@ -33,3 +34,6 @@ struct EcsStep {
 int ecsy_launch_ecs_step(const EcsStep& s, int64_t pixels, int C, cudaStream_t st);
 int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
                           __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st);
+
+int ecsy_umma_xty(const void* p_hi, const void* p_lo, const void* q_hi, const void* q_lo, int64_t rows, int Ca, int Cb,
+                  float alpha, float* out, cudaStream_t st);

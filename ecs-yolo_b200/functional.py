@@ -247,11 +247,13 @@ def make_lif_w(dw_w, dw_b, pw_w, pw_b) -> LifW:
 # ------------------------------------------------------------------------------------------------
 def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
             ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25, save_mem: bool = False):
-    """mem_update.forward (models/common.py:252-283) -> bit-packed spikes (and membranes if save_mem)."""
+    """mem_update.forward (models/common.py:252-283) -> bit-packed spikes; with save_mem also the membranes
+    m_t [T,...] and ECS traces e_t [T-1,...] (the backward's recompute pass)."""
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
     bits = torch.empty(T, N, H, W, C // 32, device=dev, dtype=torch.int32)
     mem = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
+    ecs = torch.empty(max(T - 1, 1), N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
     L = _cabi.lib()
     splits = w.splits if w is not None else 1
     nws = L.ecsy_lif_ecs_ws_bytes(T, N, H, W, C, splits) if T > 1 else 0
@@ -264,10 +266,47 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
         _cabi.check(L.ecsy_lif_ecs_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
                                    _p(w.dw_w) if w else None, _p(w.dw_b) if w else None,
                                    _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits,
-                                   _p(bits), _p(mem), T, N, H, W, C, float(thresh), float(decay), float(alpha),
+                                   _p(bits), _p(mem), _p(ecs), T, N, H, W, C, float(thresh), float(decay), float(alpha),
                                    float(beta), float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(), _st()), "lif_ecs_fwd")
     sp = Spikes(bits, C)
-    return (sp, mem) if save_mem else sp
+    return (sp, mem, ecs) if save_mem else sp
+
+
+def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, affine=None, ecs_tau: float = 5.0,
+                alpha: float = 0.75, beta: float = 0.25):
+    """Surrogate-gradient BPTT of lif_ecs.  gout: [T,N,H,W,C] dL/dspikes.  Re-runs the forward to recompute the
+    membranes / ECS traces, then the reverse scan.  Returns (g_in [T,N,H,W,C] wrt the affine-applied input
+    current, g_dw_w [C,1,3,3], g_dw_b [C], g_pw_w [C,C,1,1], g_pw_b [C])."""
+    T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
+    dev = x.data.device
+    sp, mem, ecs = lif_ecs(x, w, affine, ecs_tau, alpha, beta, save_mem=True)
+    gout = gout.contiguous()
+    gx = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32)
+    g_dw_w = torch.zeros(9, C, device=dev, dtype=torch.float32)
+    g_dw_b = torch.zeros(C, device=dev, dtype=torch.float32)
+    g_pw_w = torch.zeros(C, C, device=dev, dtype=torch.float32)
+    g_pw_b = torch.zeros(C, device=dev, dtype=torch.float32)
+    pwT = pack_conv_weight(pw_weight.detach().reshape(C, C).t().contiguous().reshape(C, C, 1, 1), w.splits)
+    L = _cabi.lib()
+    ws = torch.empty(L.ecsy_lif_ecs_bwd_ws_bytes(T, N, H, W, C, w.splits), device=dev, dtype=torch.uint8)
+    with _timed("lif_ecs_bwd", 1 + 7 * (T - 1)):
+        _cabi.check(L.ecsy_lif_ecs_bwd(_p(gout), _p(sp.bits), _p(mem), _p(ecs), _p(w.dw_w), _p(w.dw_b), _p(pwT), w.splits,
+                                       _p(gx), _p(g_dw_w), _p(g_dw_b), _p(g_pw_w), _p(g_pw_b), T, N, H, W, C,
+                                       float(thresh), float(lens), float(decay), float(alpha), float(beta),
+                                       float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(), _st()), "lif_ecs_bwd")
+    return gx, g_dw_w.t().reshape(C, 1, 3, 3).contiguous(), g_dw_b, g_pw_w.reshape(C, C, 1, 1), g_pw_b
+
+
+def colsum2(g: torch.Tensor, x: torch.Tensor, C: int):
+    """sum_r g[r,c], sum_r g[r,c]*x[r mod x_rows, c] for [rows, C]-flattened NHWC tensors."""
+    rows, xr = g.numel() // C, x.numel() // C
+    sg = torch.empty(C, device=g.device, dtype=torch.float32)
+    sgx = torch.empty(C, device=g.device, dtype=torch.float32)
+    ws = torch.empty(16 * C + 512, device=g.device, dtype=torch.uint8)
+    with _timed("colsum2", 3):
+        _cabi.check(_cabi.lib().ecsy_colsum2(_p(g), _p(x), rows, xr, C, _p(sg), _p(sgx), _p(ws), ws.numel(), _st()),
+                    "colsum2")
+    return sg, sgx
 
 
 def lif_silu(x: Act, w: Optional[LifW], affine=None, ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25,

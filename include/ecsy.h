@@ -45,11 +45,13 @@ int ecsy_pack_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh
  * x: [T][N][H][W][C] real input current (t stride `x_tstride` elements; 0 = same tensor every step),
  * optional per-channel affine on x (a folded tdBN), dw_w: spread[0].weight as [9][C], dw_b: [C],
  * pw_packed: spread[1].weight packed by ecsy_pack_conv_weight (Kpad = C), pw_b: [C].
- * spikes: [T][N][H][W][C/32] out.  mem_save (optional): [T][N][H][W][C] membranes for the backward pass. */
+ * spikes: [T][N][H][W][C/32] out.  mem_save / ecs_save (optional): membranes m_t [T][..][C] and ECS traces e_t
+ * [T-1][..][C], written when the backward pass re-runs the forward (recompute instead of store). */
 size_t ecsy_lif_ecs_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
 int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                      const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b, int splits,
-                     uint32_t* spikes, float* mem_save, int T, int64_t N, int H, int W, int C, float thresh,
+                     uint32_t* spikes, float* mem_save, float* ecs_save, int T, int64_t N, int H, int W, int C,
+                     float thresh,
                      float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- mem_update(act=True).forward: the SiLU "analog spike" neuron of class Conv (models/common.py:362-375,
@@ -110,6 +112,28 @@ int ecsy_detect_decode(const float* y, float* raw, float* z, const float* anchor
  * xs: [N][64+nc][H][W]; y (NULL in training): anchors [a_off, a_off + H*W) of [N][4+nc][a_total]. */
 int ecsy_ddetect_decode(const float* box, const float* cls, float* xs, float* y, float stride_px, int N, int H, int W,
                         int nc, int64_t a_total, int64_t a_off, void* stream);
+
+/* ---- backward of mem_update.forward: surrogate-gradient BPTT (ActFun.backward, models/common.py:66-79; autograd
+ * through :263-281).  gout: dL/dspikes [T][N][H][W][C]; spikes / mem / ecs: from a re-run of ecsy_lif_ecs_fwd with
+ * mem_save + ecs_save; pwT_packed: ecsy_pack_conv_weight of spread[1].weight TRANSPOSED ([ci][co]).
+ * gx: dL/d(input current) [T][..][C]; g_dw_w [9][C], g_dw_b [C], g_pw_w [C][C] (co-major), g_pw_b [C] are ACCUMULATED. */
+size_t ecsy_lif_ecs_bwd_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
+int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const float* mem, const float* ecs, const float* dw_w,
+                     const float* dw_b, const void* pwT_packed, int splits, float* gx, float* g_dw_w, float* g_dw_b,
+                     float* g_pw_w, float* g_pw_b, int T, int64_t N, int H, int W, int C, float thresh, float lens,
+                     float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- per-channel sums for the tdBN / folded-affine backward: sum_g[c] = sum_r g[r][c], sum_gx[c] = sum_r
+ * g[r][c] * x[r mod x_rows][c] (autograd of nn.BatchNorm3d inside batch_norm_2d, models/common.py:674-679).
+ * ws: at least 16*C + 256 bytes. */
+int ecsy_colsum2(const float* g, const float* x, int64_t rows, int64_t x_rows, int C, float* sum_g, float* sum_gx,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---- weight-gradient contraction over rows (pixels): out[Ca][Cb] += alpha * sum_p P[p][ca] * Q[p][cb],
+ * P/Q row-major bf16 (hi planes + optional lo residual planes).  Replaces autograd's conv2d weight backward for
+ * the ECS point-wise spread (mem_update.spread[1], models/common.py:295-297) -- tcgen05 with MN-major operands. */
+int ecsy_xty_bf16(const void* p_hi, const void* p_lo, const void* q_hi, const void* q_lo, int64_t rows, int Ca, int Cb,
+                  float alpha, float* out, void* stream);
 
 #ifdef __cplusplus
 }
