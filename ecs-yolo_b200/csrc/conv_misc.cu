@@ -86,6 +86,29 @@ __global__ void k_im2col(const float* __restrict__ x, int64_t x_imgs, __nv_bfloa
   }
 }
 
+// fp32 -> bf16 hi (+ lo residual) planes
+__global__ void k_f32_to_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                              int64_t n4) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += gs) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    reinterpret_cast<uint2*>(hi)[i] =
+        make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
+                   (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
+    if (lo != nullptr) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+      const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2));
+      const __nv_bfloat16 l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+      reinterpret_cast<uint2*>(lo)[i] =
+          make_uint2((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16),
+                     (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
+    }
+  }
+}
+
 // Generic direct convolution, fp32 FMA: one thread per (output pixel, output channel).
 // w: [kh][kw][Ci/g][Co] fp32.  (Snn_Conv2d on real inputs with odd shapes: Detect.m 1x1 + bias,
 // models/yolo.py:73; grouped DDetect convs, models/yolo_snn.py:100-107.)
@@ -125,6 +148,12 @@ __global__ void k_simt_conv(const float* __restrict__ x, int64_t x_imgs, const f
 
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 
+int ecsy_launch_f32_to_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st) {
+  k_f32_to_bf16<<<grid_for(n / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(x, hi, lo, n / 4);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
 extern "C" int ecsy_pack_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh, int kw, int Kpad,
                                      int splits, void* stream) {
   ECSY_CHECK_ARG(w && out_bf16 && Co > 0 && Ci > 0 && kh > 0 && kw > 0, "pack_conv_weight: bad arguments");
@@ -150,6 +179,8 @@ extern "C" int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed,
 extern "C" size_t ecsy_real_conv_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                                           int groups, int splits) {
   if (groups != 1 || Cout % 64 != 0) return 0;
+  if (Cin % 64 == 0 && stride == 1)  // implicit GEMM over bf16 planes of the input, no im2col buffer
+    return static_cast<size_t>(imgs) * H * W * Cin * 2 * splits + 1024;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t Kpad = ((int64_t)k * k * Cin + 63) / 64 * 64;
   return static_cast<size_t>(imgs * Ho * Wo * Kpad * 2 * splits + 512);
@@ -165,6 +196,22 @@ extern "C" int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_
   ECSY_CHECK_ARG((scale == nullptr) == (shift == nullptr), "real_conv_fwd: scale/shift pair");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   ECSY_CHECK_ARG(Ho > 0 && Wo > 0, "real_conv_fwd: empty output");
+  if (groups == 1 && Cout % 64 == 0 && w_packed != nullptr && bias == nullptr && Cin % 64 == 0 && stride == 1) {
+    const size_t need = ecsy_real_conv_ws_bytes(imgs, H, W, Cin, Cout, k, stride, pad, groups, splits);
+    if (ws == nullptr || ws_bytes < need) {
+      ecsy_set_error("real_conv_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+      return ECSY_ERR_WS;
+    }
+    ECSY_CHECK_ARG(x_imgs == imgs, "real_conv_fwd: broadcast inputs are convolved once by the caller");
+    const int64_t n = imgs * H * W * (int64_t)Cin;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(base);
+    __nv_bfloat16* a_lo = splits == 2 ? a_hi + n : nullptr;
+    int rc = ecsy_launch_f32_to_bf16(x, a_hi, a_lo, n, STREAM(stream));
+    if (rc) return rc;
+    return ecsy_umma_conv_bf16(a_hi, a_lo, w_packed, splits, out, scale, shift, nullptr, 0, (int)imgs, H, W, Cin, Cout, k,
+                               pad, STREAM(stream));
+  }
   if (groups == 1 && Cout % 64 == 0 && w_packed != nullptr && bias == nullptr) {
     const int Kpad = (k * k * Cin + 63) / 64 * 64;
     const int64_t M = imgs * Ho * Wo;

@@ -11,6 +11,10 @@
 //                       (Snn_Conv2d on spikes, models/common.py:593-624.)
 //   A_MODE = kATma    : A is a row-major bf16 matrix [M][K] in HBM loaded by TMA (ECS point-wise
 //                       spread, im2col'ed real-input convolutions).
+//   A_MODE = kATma4   : A rows are output pixels of a stride-1 convolution over a REAL-valued bf16 NHWC tensor
+//                       (hi [+ lo] planes): every (tap, 64-channel slab) K block is one 4-D TMA box
+//                       {64 ch, tw, th, tn} shifted by the tap, out-of-bounds = zero padding.  No im2col
+//                       buffer.  (Snn_Conv2d on real inputs, class Conv; conv input-gradients.)
 //   B                 : packed weights [B_SPLIT*Cout][K] bf16 (hi plane, optional lo residual plane),
 //                       loaded by TMA.  With B_SPLIT=2 (and A_SPLIT=2 for real-valued A) the products
 //                       A_hi*B_hi + A_lo*B_hi + A_hi*B_lo reproduce fp32 weights to ~2^-17.
@@ -80,7 +84,7 @@ struct EpiSel;
 template <>
 struct EpiSel<0> { using type = EpiConv; };
 
-constexpr int kATma = 0, kASpikes = 1;
+constexpr int kATma = 0, kASpikes = 1, kATma4 = 2;
 constexpr int kEpiConv = 0;
 
 __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
@@ -107,7 +111,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tm_b);
-    if (A_MODE == kATma) {
+    if (A_MODE == kATma || A_MODE == kATma4) {
       tma_prefetch_desc(&tm_a0);
       if (A_SPLIT == 2) tma_prefetch_desc(&tm_a1);
     }
@@ -133,15 +137,29 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+      int img0 = 0, h0 = 0, w0 = 0;
+      if (A_MODE == kATma4) {
+        const int tiles_hw = sg.tiles_h * sg.tiles_w;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        img0 = tn * sg.tn_b; h0 = th * sg.th_b - sg.pad; w0 = tw * sg.tw_b - sg.pad;
+      }
+      int slab = 0, ky = 0, kx = 0;
       for (int kb = 0; kb < g.kb_total; ++kb) {
         mbar_wait(&ctl->empty[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* st = smem + (size_t)stage * kStageBytes;
-          constexpr uint32_t tx = (A_MODE == kATma ? A_SPLIT * kATileBytes : 0) + B_SPLIT * kBTileBytes;
+          constexpr uint32_t tx = (A_MODE != kASpikes ? A_SPLIT * kATileBytes : 0) + B_SPLIT * kBTileBytes;
           mbar_arrive_expect_tx(&ctl->full_b[stage], tx);
           if (A_MODE == kATma) {
             tma_load_2d(st, &tm_a0, &ctl->full_b[stage], kb * 64, m_tile * 128);
             if (A_SPLIT == 2) tma_load_2d(st + kATileBytes, &tm_a1, &ctl->full_b[stage], kb * 64, m_tile * 128);
+          }
+          if (A_MODE == kATma4) {
+            tma_load_4d(st, &tm_a0, &ctl->full_b[stage], slab * 64, w0 + kx, h0 + ky, img0);
+            if (A_SPLIT == 2)
+              tma_load_4d(st + kATileBytes, &tm_a1, &ctl->full_b[stage], slab * 64, w0 + kx, h0 + ky, img0);
           }
 #pragma unroll
           for (int bs = 0; bs < B_SPLIT; ++bs)
@@ -149,6 +167,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
                         bs * (g.n_tiles * BN) + n_tile * BN);
         }
         __syncwarp();
+        if (A_MODE == kATma4) {
+          if (++slab == sg.nslab) {
+            slab = 0;
+            if (++kx == sg.kw) { kx = 0; ++ky; }
+          }
+        }
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -288,7 +312,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       // output row of this thread
       int64_t pix;
       bool valid;
-      if (A_MODE == kASpikes) {
+      if (A_MODE == kASpikes || A_MODE == kATma4) {
         const int tiles_hw = sg.tiles_h * sg.tiles_w;
         const int tn = m_tile / tiles_hw;
         const int rem = m_tile - tn * tiles_hw;
@@ -411,6 +435,29 @@ int ecsy_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t
   return ECSY_OK;
 }
 
+// 4-D bf16 NHWC [imgs][H][W][C] tensor map with a {64, tw, th, tn} box, 128-byte swizzle, zero OOB fill.
+int ecsy_tensor_map_bf16_nhwc(const void* ptr, int imgs, int H, int W, int C, int tn, int th, int tw, CUtensorMap* out) {
+  ECSY_CHECK_ARG(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && C % 8 == 0, "nhwc tensor map: alignment");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    ecsy_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECSY_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)imgs};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ecsy_set_error("cuTensorMapEncodeTiled(4d) failed with %d (imgs=%d H=%d W=%d C=%d box=%d,%d,%d)", (int)r, imgs, H, W,
+                   C, tn, th, tw);
+    return ECSY_ERR_CUDA;
+  }
+  return ECSY_OK;
+}
+
 namespace {
 
 constexpr int kSmemLimit = 227 * 1024;
@@ -469,6 +516,25 @@ int ilog2(int v) {
 
 }  // namespace
 
+// choose the 128-pixel tile box (tn, th, tw), powers of two: least padding waste, then widest rows
+static bool pick_tile_box(SpikeGeom& sg, int imgs, int Ho, int Wo, int Cw, int k, int stride) {
+  double best = 1e30;
+  for (int tw = 1; tw <= 128; tw <<= 1)
+    for (int th = 1; th * tw <= 128; th <<= 1) {
+      const int tn = 128 / (tw * th);
+      const int64_t cov = (int64_t)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th * ((imgs + tn - 1) / tn) * tn;
+      const int Hp = (th - 1) * stride + k, Wp = (tw - 1) * stride + k;
+      const int64_t patch_bytes = (int64_t)tn * Hp * Wp * Cw * 4;
+      const double score = (double)cov * (1.0 + 1e-3 * (double)patch_bytes / (128.0 * Cw * 4)) - 1e-6 * tw;
+      if (score < best) {
+        best = score;
+        sg.tn_b = tn; sg.th_b = th; sg.tw_b = tw;
+        sg.Hp = Hp; sg.Wp = Wp; sg.PP = tn * Hp * Wp;
+      }
+    }
+  return best < 1e30;
+}
+
 int ecsy_pick_bn(int cout, int splits) {
   // wide tiles amortise the A expansion; the split-weight mode doubles the B tile, so cap at 128
   const int cap = splits == 2 ? 128 : 256;
@@ -487,24 +553,12 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   ECSY_CHECK_ARG(splits == 1 || splits == 2, "spike_conv: splits must be 1 or 2");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   ECSY_CHECK_ARG(Ho > 0 && Wo > 0, "spike_conv: empty output");
-  // choose the 128-pixel tile box (tn, th, tw): least padding waste, then widest rows, within the patch budget
   SpikeGeom sg{};
-  double best = 1e30;
+  if (!pick_tile_box(sg, imgs, Ho, Wo, Cin / 32, k, stride)) {
+    ecsy_set_error("spike_conv: no tile shape found");
+    return ECSY_ERR_ARG;
+  }
   const int Cw = Cin / 32;
-  for (int tw = 1; tw <= 128; tw <<= 1)
-    for (int th = 1; th * tw <= 128; th <<= 1) {
-      const int tn = 128 / (tw * th);
-      const int64_t cov = (int64_t)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th * ((imgs + tn - 1) / tn) * tn;
-      const int Hp = (th - 1) * stride + k, Wp = (tw - 1) * stride + k;
-      const int64_t patch_bytes = (int64_t)tn * Hp * Wp * Cw * 4;
-      const double score = (double)cov * (1.0 + 1e-3 * (double)patch_bytes / (128.0 * Cw * 4)) - 1e-6 * tw;
-      if (score < best) {
-        best = score;
-        sg.tn_b = tn; sg.th_b = th; sg.tw_b = tw;
-        sg.Hp = Hp; sg.Wp = Wp; sg.PP = tn * Hp * Wp;
-      }
-    }
-  ECSY_CHECK_ARG(best < 1e30, "spike_conv: no tile shape fits the shared-memory patch budget");
   sg.bits = bits; sg.imgs = imgs; sg.H = H; sg.W = W; sg.Cw = Cw; sg.Ho = Ho; sg.Wo = Wo;
   sg.kh = k; sg.kw = k; sg.stride = stride; sg.pad = pad;
   sg.tn_sh = ilog2(sg.tn_b); sg.th_sh = ilog2(sg.th_b); sg.tw_sh = ilog2(sg.tw_b);
@@ -553,3 +607,41 @@ int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const 
   return launch_bn<kATma, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
 }
 
+
+// Stride-1 convolution over a REAL-valued bf16 NHWC tensor (hi [+ lo] planes), implicit GEMM with 4-D TMA.
+int ecsy_umma_conv_bf16(const void* a_hi, const void* a_lo, const void* w_packed, int splits, float* out,
+                        const float* scale, const float* shift, const float* residual, int64_t res_imgs, int imgs, int H,
+                        int W, int Cin, int Cout, int k, int pad, cudaStream_t st) {
+  ECSY_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "conv_bf16: Cin=%d must be a multiple of 64", Cin);
+  const int BN = ecsy_pick_bn(Cout, splits);
+  ECSY_CHECK_ARG(BN != 0, "conv_bf16: Cout=%d must be a multiple of 64", Cout);
+  ECSY_CHECK_ARG((splits == 2) == (a_lo != nullptr), "conv_bf16: lo plane required iff splits == 2");
+  const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
+  ECSY_CHECK_ARG(Ho > 0 && Wo > 0, "conv_bf16: empty output");
+  SpikeGeom sg{};
+  if (!pick_tile_box(sg, imgs, Ho, Wo, Cin / 32, k, 1)) {
+    ecsy_set_error("conv_bf16: no tile shape found");
+    return ECSY_ERR_ARG;
+  }
+  sg.bits = nullptr; sg.imgs = imgs; sg.H = H; sg.W = W; sg.Cw = Cin / 32; sg.Ho = Ho; sg.Wo = Wo;
+  sg.kh = k; sg.kw = k; sg.stride = 1; sg.pad = pad;
+  sg.tn_sh = ilog2(sg.tn_b); sg.th_sh = ilog2(sg.th_b); sg.tw_sh = ilog2(sg.tw_b);
+  sg.tiles_h = (Ho + sg.th_b - 1) / sg.th_b; sg.tiles_w = (Wo + sg.tw_b - 1) / sg.tw_b;
+  sg.nslab = Cin / 64;
+  GemmArgs g{};
+  g.m_tiles = ((imgs + sg.tn_b - 1) / sg.tn_b) * sg.tiles_h * sg.tiles_w;
+  g.n_tiles = Cout / BN;
+  g.kb_total = k * k * sg.nslab;
+  CUtensorMap ta0, ta1{}, tb;
+  int rc = ecsy_tensor_map_bf16_nhwc(a_hi, imgs, H, W, Cin, sg.tn_b, sg.th_b, sg.tw_b, &ta0);
+  if (rc) return rc;
+  if (a_lo) {
+    rc = ecsy_tensor_map_bf16_nhwc(a_lo, imgs, H, W, Cin, sg.tn_b, sg.th_b, sg.tw_b, &ta1);
+    if (rc) return rc;
+  }
+  rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)splits * Cout, (uint64_t)k * k * Cin, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout};
+  if (splits == 1) return launch_bn<kATma4, 1, 1, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+  return launch_bn<kATma4, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+}

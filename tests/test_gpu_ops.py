@@ -190,3 +190,26 @@ def test_lif_affine_and_broadcast():
     gotb = F.lif_ecs(F.Act.from_ref(xb.cuda()), w).to_act().to_ref().cpu()
     wantb = O.ecs_lif(xb.contiguous(), inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
     assert agree(gotb, wantb) > 0.999
+
+
+@pytest.mark.parametrize("ci,co,k,H,W,N,T", [(64, 128, 3, 10, 12, 2, 2), (128, 64, 1, 7, 9, 1, 3), (192, 256, 3, 20, 20, 3, 1)])
+@pytest.mark.parametrize("mode,tol", [("parity", 2e-5), ("fast", 8e-3)])
+def test_real_conv_implicit(ci, co, k, H, W, N, T, mode, tol):
+    """Stride-1 real-input conv: bf16 planes + 4-D TMA implicit GEMM (no im2col buffer)."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision(mode)
+    try:
+        g = S.gen(ci + co + k)
+        x = torch.randn(T, N, ci, H, W, generator=g)
+        w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+        want = O.snn_conv2d(x, w, None, 1, k // 2)
+        cw = F.make_conv_w(w.cuda(), None, 1, k // 2, 1, True, False)
+        sc = torch.rand(co, generator=g) + 0.5
+        sh = torch.rand(co, generator=g)
+        got = F.real_conv(F.Act.from_ref(x.cuda()), cw, sc.cuda(), sh.cuda()).to_ref().cpu()
+        want = want * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1)
+        err = rel_l2(got, want)
+        assert err < tol, err
+    finally:
+        F.set_precision("parity")
