@@ -109,6 +109,40 @@ __global__ void k_f32_to_bf16(const float* __restrict__ x, __nv_bfloat16* __rest
   }
 }
 
+// Zero-insertion ("dilation") of an output gradient for the input-gradient of a strided conv:
+// up[img][h'][w'][c] = gy[img][h'/s][w'/s][c] if both divide and are in range, else 0  -> bf16 hi (+ lo).
+__global__ void k_dilate_to_bf16(const float* __restrict__ gy, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int64_t imgs, int Ho, int Wo, int C, int Hu, int Wu,
+                                 int s) {
+  const int c4 = C >> 2;
+  const int64_t total = imgs * Hu * Wu * c4;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int q = static_cast<int>(i % c4);
+    int64_t p = i / c4;
+    const int wu = static_cast<int>(p % Wu); p /= Wu;
+    const int hu = static_cast<int>(p % Hu);
+    const int64_t img = p / Hu;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hu % s == 0 && wu % s == 0 && hu / s < Ho && wu / s < Wo)
+      v = reinterpret_cast<const float4*>(gy + (((img * Ho + hu / s) * Wo + wu / s) * (int64_t)C))[q];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    reinterpret_cast<uint2*>(hi)[i] =
+        make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
+                   (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
+    if (lo != nullptr) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+      const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2));
+      const __nv_bfloat16 l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+      reinterpret_cast<uint2*>(lo)[i] =
+          make_uint2((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16),
+                     (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
+    }
+  }
+}
+
 // Generic direct convolution, fp32 FMA: one thread per (output pixel, output channel).
 // w: [kh][kw][Ci/g][Co] fp32.  (Snn_Conv2d on real inputs with odd shapes: Detect.m 1x1 + bias,
 // models/yolo.py:73; grouped DDetect convs, models/yolo_snn.py:100-107.)
@@ -236,4 +270,106 @@ extern "C" int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_
       x, x_imgs, w_simt, bias, bias_mul, scale, shift, out, imgs, H, W, Cin, Ho, Wo, Cout, k, k, stride, pad, groups);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
+}
+
+// ---- backward of Snn_Conv2d (autograd of F.conv2d, models/common.py:623) ------------------------------------
+static inline size_t al256c(size_t v) { return (v + 255) & ~size_t(255); }
+
+extern "C" size_t ecsy_conv_dgrad_ws_bytes(int64_t imgs, int H, int W, int Cout, int k, int stride, int pad,
+                                           int splits) {
+  const int Hu = H - k + 1 + 2 * pad, Wu = W - k + 1 + 2 * pad;
+  (void)stride;
+  return 512 + static_cast<size_t>(splits) * al256c(static_cast<size_t>(imgs) * Hu * Wu * Cout * 2);
+}
+
+// Input gradient: gx[imgs][H][W][Cin] = conv_transpose(gy[imgs][Ho][Wo][Cout], W).  wT_packed is
+// ecsy_pack_conv_weight of the flipped, transposed weight W'[ci][co][ky][kx] = W[co][ci][k-1-ky][k-1-kx].
+extern "C" int ecsy_conv_dgrad(const float* gy, const void* wT_packed, int splits, float* gx, int64_t imgs, int H, int W,
+                               int Cin, int Cout, int k, int stride, int pad, void* ws, size_t ws_bytes, void* stream) {
+  ECSY_CHECK_ARG(gy && wT_packed && gx && imgs > 0, "conv_dgrad: bad arguments");
+  ECSY_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "conv_dgrad: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+  ECSY_CHECK_ARG(splits == 1 || splits == 2, "conv_dgrad: splits");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int Hu = H - k + 1 + 2 * pad, Wu = W - k + 1 + 2 * pad;   // zero-inserted gradient extent
+  ECSY_CHECK_ARG(Hu >= (Ho - 1) * stride + 1 && Wu >= (Wo - 1) * stride + 1, "conv_dgrad: geometry");
+  const size_t need = ecsy_conv_dgrad_ws_bytes(imgs, H, W, Cout, k, stride, pad, splits);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("conv_dgrad: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  const size_t n = static_cast<size_t>(imgs) * Hu * Wu * Cout;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(base + al256c(n * 2)) : nullptr;
+  if (stride == 1 && Hu == Ho && Wu == Wo) {
+    int rc = ecsy_launch_f32_to_bf16(gy, hi, lo, (int64_t)n, STREAM(stream));
+    if (rc) return rc;
+  } else {
+    k_dilate_to_bf16<<<grid_for((int64_t)n / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+        gy, hi, lo, imgs, Ho, Wo, Cout, Hu, Wu, stride);
+    ECSY_LAUNCH_CHECK();
+  }
+  return ecsy_umma_conv_bf16(hi, lo, wT_packed, splits, gx, nullptr, nullptr, nullptr, 0, (int)imgs, Hu, Wu, Cout, Cin, k,
+                             k - 1 - pad, STREAM(stream));
+}
+
+extern "C" size_t ecsy_spike_conv_wgrad_ws_bytes(int64_t imgs, int Ho, int Wo, int Cout, int splits) {
+  return 512 + static_cast<size_t>(splits) * al256c(static_cast<size_t>(imgs) * Ho * Wo * Cout * 2);
+}
+
+// Weight gradient of a spike conv: dw[Cout][(ky*kw+kx)*Cin + ci] += sum_pixels gy * spikes (accumulated).
+extern "C" int ecsy_spike_conv_wgrad(const float* gy, const uint32_t* spikes, float* dw, int64_t imgs, int H, int W,
+                                     int Cin, int Cout, int k, int stride, int pad, int splits, void* ws,
+                                     size_t ws_bytes, void* stream) {
+  ECSY_CHECK_ARG(gy && spikes && dw && imgs > 0, "spike_conv_wgrad: bad arguments");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const size_t need = ecsy_spike_conv_wgrad_ws_bytes(imgs, Ho, Wo, Cout, splits);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("spike_conv_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  const size_t n = static_cast<size_t>(imgs) * Ho * Wo * Cout;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(base + al256c(n * 2)) : nullptr;
+  int rc = ecsy_launch_f32_to_bf16(gy, hi, lo, (int64_t)n, STREAM(stream));
+  if (rc) return rc;
+  return ecsy_umma_spike_wgrad(hi, lo, spikes, dw, (int)imgs, H, W, Cin, Cout, k, stride, pad, STREAM(stream));
+}
+
+extern "C" size_t ecsy_real_conv_wgrad_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                                int splits) {
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const size_t M = static_cast<size_t>(imgs) * Ho * Wo;
+  const size_t Kpad = (static_cast<size_t>(k) * k * Cin + 63) / 64 * 64;
+  return 1024 + static_cast<size_t>(splits) * (al256c(M * Kpad * 2) + al256c(M * Cout * 2));
+}
+
+// Weight gradient of a real-input conv (stem Conv_1, class Conv): dw[Cout][Kpad] += gy^T * im2col(x).
+extern "C" int ecsy_real_conv_wgrad(const float* gy, const float* x, int64_t x_imgs, float* dw, int64_t imgs, int H,
+                                    int W, int Cin, int Cout, int k, int stride, int pad, int splits, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  ECSY_CHECK_ARG(gy && x && dw && imgs > 0 && x_imgs > 0 && imgs % x_imgs == 0, "real_conv_wgrad: bad arguments");
+  ECSY_CHECK_ARG(Cout % 64 == 0, "real_conv_wgrad: Cout=%d must be a multiple of 64", Cout);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int Kpad = (k * k * Cin + 63) / 64 * 64;
+  const int64_t M = imgs * Ho * Wo;
+  const size_t need = ecsy_real_conv_wgrad_ws_bytes(imgs, H, W, Cin, Cout, k, stride, pad, splits);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("real_conv_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  ECSY_CHECK_ARG(Kpad * 8 <= 48 * 1024, "real_conv_wgrad: K=%d too large for the im2col table", Kpad);
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256c((size_t)M * Kpad * 2);
+  __nv_bfloat16* a_lo = nullptr;
+  if (splits == 2) { a_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256c((size_t)M * Kpad * 2); }
+  __nv_bfloat16* g_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256c((size_t)M * Cout * 2);
+  __nv_bfloat16* g_lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
+  k_im2col<<<grid_for(M * (Kpad / 8), kThreads, ecsy_num_sms() * 8), kThreads, Kpad * sizeof(int2), STREAM(stream)>>>(
+      x, x_imgs, a_hi, a_lo, imgs, H, W, Cin, Ho, Wo, k, k, stride, pad, Kpad);
+  ECSY_LAUNCH_CHECK();
+  int rc = ecsy_launch_f32_to_bf16(gy, g_hi, g_lo, M * Cout, STREAM(stream));
+  if (rc) return rc;
+  return ecsy_umma_xty(g_hi, g_lo, a_hi, a_lo, M, Cout, Kpad, 1.0f, dw, STREAM(stream));
 }

@@ -375,6 +375,220 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------------
+// Weight gradient of the spike convolution:  dW[co][(tap, ci)] += sum_pixels gy[p][co] * s[p*stride + tap - pad][ci]
+// The contraction runs over PIXELS, i.e. over the rows of both operands, so both are fed to the tensor
+// core as MN-major tiles: A = gy tile [128 pixels x 128 co] (bf16 hi [+ lo], 4-D TMA boxes in the tile's
+// pixel order), B = the SAME expanded spike tile the forward kernel builds ([128 pixels x 64 channels] for
+// one (tap, slab)), reinterpreted.  A CTA owns one 128-co tile, `bpc` (tap, slab) blocks (bpc*64 TMEM
+// columns) and a slice of the pixel tiles; the accumulators stay in TMEM until the slice is done and are
+// then added to dW with red.global.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgStages = 4;
+
+struct WgCtl {
+  uint64_t a_full[2], a_empty[2];
+  uint64_t b_full[kWgStages], b_empty[kWgStages];
+  uint64_t done;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct WgArgs {
+  int m_tiles;      // pixel tiles
+  int splits_m;     // CTAs along the pixel tiles
+  int bpc;          // (tap, slab) blocks per CTA
+  int Cout, K;      // dW is [Cout][K]
+  float* dw;
+};
+
+template <int G_SPLIT>
+__global__ void __launch_bounds__(kSpikeThreads, 1)
+k_umma_wgrad(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_g1, const WgArgs g,
+             const SpikeGeom sg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kABuf = G_SPLIT * 2 * kATileBytes;   // planes x two 64-co blocks x (128 rows x 128 B)
+  uint8_t* a_smem = smem;                             // 2 buffers
+  uint8_t* b_smem = smem + 2 * kABuf;                 // kWgStages x 16 KB
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(b_smem + kWgStages * kATileBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * 128;
+  const int blk0 = blockIdx.z * g.bpc;
+  const int per = (g.m_tiles + g.splits_m - 1) / g.splits_m;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(t_begin + per, g.m_tiles);
+  const int ntiles = max(t_end - t_begin, 0);
+  constexpr int kWpg = kExpWarps / kWgStages;  // expander warps per stage group
+
+  if (warp == 4 && lane == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->a_full[b], 1); mbar_init(&ctl->a_empty[b], 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&ctl->b_full[s], kWpg); mbar_init(&ctl->b_empty[s], 1); }
+    mbar_init(&ctl->done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<512>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int tiles_hw = sg.tiles_h * sg.tiles_w;
+
+  if (warp == 4) {
+    // ---- TMA: gy tiles (two 64-co blocks per plane), one per pixel tile ----
+    for (int i = 0; i < ntiles; ++i) {
+      const uint32_t ab = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&ctl->a_empty[ab], ph ^ 1);
+      if (lane == 0) {
+        const int m_tile = t_begin + i;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        uint8_t* dst = a_smem + ab * kABuf;
+        mbar_arrive_expect_tx(&ctl->a_full[ab], (uint32_t)kABuf);
+#pragma unroll
+        for (int sp = 0; sp < G_SPLIT; ++sp) {
+          const CUtensorMap* tm = sp == 0 ? &tm_g0 : &tm_g1;
+          tma_load_4d(dst + sp * 2 * kATileBytes, tm, &ctl->a_full[ab], co0, tw * sg.tw_b, th * sg.th_b, tn * sg.tn_b);
+          tma_load_4d(dst + sp * 2 * kATileBytes + kATileBytes, tm, &ctl->a_full[ab], co0 + 64, tw * sg.tw_b,
+                      th * sg.th_b, tn * sg.tn_b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer ----
+    const uint32_t idesc = umma_idesc_bf16_mn(128, 64);
+    uint32_t c = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      const uint32_t ab = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&ctl->a_full[ab], ph);
+      for (int b = 0; b < g.bpc; ++b, ++c) {
+        const uint32_t stage = c % kWgStages, sph = (c / kWgStages) & 1;
+        mbar_wait(&ctl->b_full[stage], sph);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(a_smem + ab * kABuf);
+          const uint32_t b_addr = smem_u32(b_smem + stage * kATileBytes);
+          uint32_t acc = i > 0 ? 1u : 0u;
+#pragma unroll
+          for (int sp = 0; sp < G_SPLIT; ++sp) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // 128 pixels = 8 K steps of 16 rows (2048 bytes each)
+              const uint64_t da = umma_desc_sw128_mn(a_addr + sp * 2 * kATileBytes + k * 2048, kATileBytes);
+              const uint64_t db = umma_desc_sw128_mn(b_addr + k * 2048, kATileBytes);
+              umma_f16(tmem_base + b * 64, da, db, idesc, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&ctl->b_empty[stage]);
+          if (b == g.bpc - 1) {
+            umma_commit(&ctl->a_empty[ab]);
+            if (i == ntiles - 1) umma_commit(&ctl->done);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 6) {
+    // ---- spike expanders (same tile the forward conv builds; stage group = stage) ----
+    const int ew = warp - 6;
+    const int grp = ew / kWpg, sub = ew - grp * kWpg;
+    constexpr int rows_per_warp = 128 / kWpg;
+    constexpr int nrow = rows_per_warp >> 5;
+    int n_l[nrow], h_l[nrow], w_l[nrow];
+    uint32_t row_off[nrow];
+#pragma unroll
+    for (int i = 0; i < nrow; ++i) {
+      const int r = sub * rows_per_warp + i * 32 + lane;
+      w_l[i] = r & (sg.tw_b - 1);
+      h_l[i] = (r >> sg.tw_sh) & (sg.th_b - 1);
+      n_l[i] = r >> (sg.tw_sh + sg.th_sh);
+      row_off[i] = (uint32_t)r * 128u;
+    }
+    const uint32_t sw = (uint32_t)(lane & 7);
+    uint8_t* tile_b = b_smem + (size_t)grp * kATileBytes;
+    const uint32_t c_end = (uint32_t)ntiles * (uint32_t)g.bpc;
+
+    auto load_rows = [&](uint32_t c, uint2 (&wd)[nrow]) {
+      const uint32_t ti = c / (uint32_t)g.bpc;
+      const int blk = blk0 + (int)(c - ti * g.bpc);
+      const int m_tile = t_begin + (int)ti;
+      const int tn = m_tile / tiles_hw;
+      const int rem = m_tile - tn * tiles_hw;
+      const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+      const int tap = blk / sg.nslab, slab = blk - tap * sg.nslab;
+      const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
+      const int img0 = tn * sg.tn_b;
+      const int hi0 = th * sg.th_b * sg.stride - sg.pad + ky;
+      const int wi0 = tw * sg.tw_b * sg.stride - sg.pad + kx;
+#pragma unroll
+      for (int i = 0; i < nrow; ++i) {
+        wd[i] = make_uint2(0u, 0u);
+        const int img = img0 + n_l[i], hi = hi0 + h_l[i] * sg.stride, wi = wi0 + w_l[i] * sg.stride;
+        if (img < sg.imgs && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
+          wd[i] = __ldg(reinterpret_cast<const uint2*>(sg.bits + (((int64_t)img * sg.H + hi) * sg.W + wi) * sg.Cw + slab * 2));
+      }
+    };
+
+    uint32_t c = (uint32_t)grp;
+    uint2 cur[nrow];
+    if (c < c_end) load_rows(c, cur);
+    while (c < c_end) {
+      uint2 nxt[nrow];
+      if (c + kWgStages < c_end) load_rows(c + kWgStages, nxt);
+      mbar_wait(&ctl->b_empty[grp], ((c / kWgStages) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < nrow; ++i) {
+        uint8_t* row = tile_b + row_off[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t byte = ((j < 4 ? cur[i].x : cur[i].y) >> (8 * (j & 3))) & 0xFFu;
+          uint4 o;
+          o.x = bits2_to_bf16x2(byte);
+          o.y = bits2_to_bf16x2(byte >> 2);
+          o.z = bits2_to_bf16x2(byte >> 4);
+          o.w = bits2_to_bf16x2(byte >> 6);
+          *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->b_full[grp]);
+#pragma unroll
+      for (int i = 0; i < nrow; ++i) cur[i] = nxt[i];
+      c += kWgStages;
+    }
+  } else {
+    // ---- epilogue: TMEM -> red.global into dW[co][k] ----
+    if (ntiles > 0) {
+      mbar_wait(&ctl->done, 0);
+      tc_fence_after_sync();
+      const int co = co0 + warp * 32 + lane;
+      for (int b = 0; b < g.bpc; ++b) {
+        const int blk = blk0 + b;
+        const int tap = blk / sg.nslab, slab = blk - tap * sg.nslab;
+        const int kbase = (tap * sg.nslab + slab) * 64;
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + b * 64 + c0, v);
+          tmem_ld_wait();
+          if (co < g.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(g.dw + (int64_t)co * g.K + kbase + c0 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -644,4 +858,53 @@ int ecsy_umma_conv_bf16(const void* a_hi, const void* a_lo, const void* w_packed
   EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout};
   if (splits == 1) return launch_bn<kATma4, 1, 1, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
   return launch_bn<kATma4, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+}
+
+// dW[Cout][k*k*Cin] (fp32, accumulated) for a spike convolution; gy as bf16 planes [imgs][Ho][Wo][Cout].
+int ecsy_umma_spike_wgrad(const void* gy_hi, const void* gy_lo, const uint32_t* bits, float* dw, int imgs, int H, int W,
+                          int Cin, int Cout, int k, int stride, int pad, cudaStream_t st) {
+  ECSY_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "spike_wgrad: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  SpikeGeom sg{};
+  if (!pick_tile_box(sg, imgs, Ho, Wo, Cin / 32, k, stride)) {
+    ecsy_set_error("spike_wgrad: no tile shape found");
+    return ECSY_ERR_ARG;
+  }
+  sg.bits = bits; sg.imgs = imgs; sg.H = H; sg.W = W; sg.Cw = Cin / 32; sg.Ho = Ho; sg.Wo = Wo;
+  sg.kh = k; sg.kw = k; sg.stride = stride; sg.pad = pad;
+  sg.tn_sh = ilog2(sg.tn_b); sg.th_sh = ilog2(sg.th_b); sg.tw_sh = ilog2(sg.tw_b);
+  sg.tiles_h = (Ho + sg.th_b - 1) / sg.th_b; sg.tiles_w = (Wo + sg.tw_b - 1) / sg.tw_b;
+  sg.nslab = Cin / 64;
+  WgArgs g{};
+  g.m_tiles = ((imgs + sg.tn_b - 1) / sg.tn_b) * sg.tiles_h * sg.tiles_w;
+  const int nblk = k * k * sg.nslab;
+  int bpc = 8;
+  while (nblk % bpc != 0) --bpc;
+  g.bpc = bpc; g.Cout = Cout; g.K = k * k * Cin; g.dw = dw;
+  const int co_tiles = (Cout + 127) / 128, groups = nblk / bpc;
+  int sm = (2 * ecsy_num_sms()) / (co_tiles * groups);
+  if (sm < 1) sm = 1;
+  if (sm > g.m_tiles) sm = g.m_tiles;
+  g.splits_m = sm;
+  CUtensorMap t0, t1{};
+  int rc = ecsy_tensor_map_bf16_nhwc(gy_hi, imgs, Ho, Wo, Cout, sg.tn_b, sg.th_b, sg.tw_b, &t0);
+  if (rc) return rc;
+  const int gsplit = gy_lo ? 2 : 1;
+  if (gy_lo) {
+    rc = ecsy_tensor_map_bf16_nhwc(gy_lo, imgs, Ho, Wo, Cout, sg.tn_b, sg.th_b, sg.tw_b, &t1);
+    if (rc) return rc;
+  }
+  const int smem = 1024 + 2 * gsplit * 2 * kATileBytes + kWgStages * kATileBytes + (int)sizeof(WgCtl) + 64;
+  dim3 grid((unsigned)sm, co_tiles, groups);
+  if (gsplit == 1) {
+    static bool d1 = false;
+    if (!d1) { ECSY_CUDA(cudaFuncSetAttribute(k_umma_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); d1 = true; }
+    k_umma_wgrad<1><<<grid, kSpikeThreads, smem, st>>>(t0, t1, g, sg);
+  } else {
+    static bool d2 = false;
+    if (!d2) { ECSY_CUDA(cudaFuncSetAttribute(k_umma_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); d2 = true; }
+    k_umma_wgrad<2><<<grid, kSpikeThreads, smem, st>>>(t0, t1, g, sg);
+  }
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
 }

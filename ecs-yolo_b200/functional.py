@@ -297,6 +297,61 @@ def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, af
     return gx, g_dw_w.t().reshape(C, 1, 3, 3).contiguous(), g_dw_b, g_pw_w.reshape(C, C, 1, 1), g_pw_b
 
 
+def pack_dgrad_weight(weight: torch.Tensor, splits: int) -> torch.Tensor:
+    """Forward-form packing of the flipped, transposed weight: W'[ci][co][ky][kx] = W[co][ci][k-1-ky][k-1-kx]."""
+    wt = weight.detach().float().flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    return pack_conv_weight(wt, splits)
+
+
+def conv_dgrad(gy: torch.Tensor, wT_packed: torch.Tensor, splits: int, H: int, W: int, Cin: int, k: int, stride: int,
+               pad: int) -> torch.Tensor:
+    """gy: [T,N,Ho,Wo,Co] fp32 NHWC -> gx [T,N,H,W,Cin] (input gradient of Snn_Conv2d)."""
+    T, N, Ho, Wo, Co = gy.shape
+    gy = gy.contiguous()
+    gx = torch.empty(T, N, H, W, Cin, device=gy.device, dtype=torch.float32)
+    L = _cabi.lib()
+    ws = torch.empty(L.ecsy_conv_dgrad_ws_bytes(T * N, H, W, Co, k, stride, pad, splits), device=gy.device, dtype=torch.uint8)
+    flops["conv_bwd"] = flops.get("conv_bwd", 0.0) + 2.0 * T * N * H * W * Cin * Co * k * k
+    with _timed("conv_dgrad", 2):
+        _cabi.check(L.ecsy_conv_dgrad(_p(gy), _p(wT_packed), splits, _p(gx), T * N, H, W, Cin, Co, k, stride, pad,
+                                      _p(ws), ws.numel(), _st()), "conv_dgrad")
+    return gx
+
+
+def spike_conv_wgrad(gy: torch.Tensor, s: Spikes, k: int, stride: int, pad: int) -> torch.Tensor:
+    """gy: [T,N,Ho,Wo,Co] fp32, s: the conv's input spikes -> dW [Co, Ci, k, k]."""
+    T, N, Ho, Wo, Co = gy.shape
+    gy = gy.contiguous()
+    Ci = s.C
+    dw = torch.zeros(Co, k * k * Ci, device=gy.device, dtype=torch.float32)
+    L = _cabi.lib()
+    splits = get_splits()
+    ws = torch.empty(L.ecsy_spike_conv_wgrad_ws_bytes(T * N, Ho, Wo, Co, splits), device=gy.device, dtype=torch.uint8)
+    flops["conv_bwd"] = flops.get("conv_bwd", 0.0) + 2.0 * T * N * Ho * Wo * Ci * Co * k * k
+    with _timed("conv_wgrad", 2):
+        _cabi.check(L.ecsy_spike_conv_wgrad(_p(gy), _p(s.bits), _p(dw), T * N, s.H, s.W, Ci, Co, k, stride, pad, splits,
+                                            _p(ws), ws.numel(), _st()), "spike_conv_wgrad")
+    return dw.reshape(Co, k, k, Ci).permute(0, 3, 1, 2).contiguous()
+
+
+def real_conv_wgrad(gy: torch.Tensor, x: Act, k: int, stride: int, pad: int) -> torch.Tensor:
+    """gy: [Tp,N,Ho,Wo,Co] fp32 (already summed over T for a T-broadcast input), x: the conv's real input."""
+    Tp, N, Ho, Wo, Co = gy.shape
+    assert Tp == x.Tp
+    gy = gy.contiguous()
+    Ci = x.C
+    Kpad = (k * k * Ci + 63) // 64 * 64
+    dw = torch.zeros(Co, Kpad, device=gy.device, dtype=torch.float32)
+    L = _cabi.lib()
+    splits = get_splits()
+    ws = torch.empty(L.ecsy_real_conv_wgrad_ws_bytes(Tp * N, x.H, x.W, Ci, Co, k, stride, pad, splits), device=gy.device,
+                     dtype=torch.uint8)
+    with _timed("conv_wgrad", 3):
+        _cabi.check(L.ecsy_real_conv_wgrad(_p(gy), _p(x.data), Tp * N, _p(dw), Tp * N, x.H, x.W, Ci, Co, k, stride, pad,
+                                           splits, _p(ws), ws.numel(), _st()), "real_conv_wgrad")
+    return dw[:, :k * k * Ci].reshape(Co, k, k, Ci).permute(0, 3, 1, 2).contiguous()
+
+
 def colsum2(g: torch.Tensor, x: torch.Tensor, C: int):
     """sum_r g[r,c], sum_r g[r,c]*x[r mod x_rows, c] for [rows, C]-flattened NHWC tensors."""
     rows, xr = g.numel() // C, x.numel() // C

@@ -123,6 +123,22 @@ int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const float* mem
                      float* g_pw_w, float* g_pw_b, int T, int64_t N, int H, int W, int C, float thresh, float lens,
                      float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- backward of Snn_Conv2d.forward (autograd of F.conv2d, models/common.py:623).
+ * dgrad: gx[imgs][H][W][Cin] from gy[imgs][Ho][Wo][Cout]; wT_packed = ecsy_pack_conv_weight of the flipped,
+ * transposed weight W'[ci][co][ky][kx] = W[co][ci][k-1-ky][k-1-kx] (strided convs: zero-inserted gradient).
+ * wgrad (spike input): dw[Cout][(ky*kw+kx)*Cin+ci] += gy^T * im2col(spikes), pixel contraction on tcgen05 with
+ * MN-major operands; wgrad (real input): dw[Cout][Kpad] += gy^T * im2col(x). */
+size_t ecsy_conv_dgrad_ws_bytes(int64_t imgs, int H, int W, int Cout, int k, int stride, int pad, int splits);
+int ecsy_conv_dgrad(const float* gy, const void* wT_packed, int splits, float* gx, int64_t imgs, int H, int W, int Cin,
+                    int Cout, int k, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
+size_t ecsy_spike_conv_wgrad_ws_bytes(int64_t imgs, int Ho, int Wo, int Cout, int splits);
+int ecsy_spike_conv_wgrad(const float* gy, const uint32_t* spikes, float* dw, int64_t imgs, int H, int W, int Cin,
+                          int Cout, int k, int stride, int pad, int splits, void* ws, size_t ws_bytes, void* stream);
+size_t ecsy_real_conv_wgrad_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                     int splits);
+int ecsy_real_conv_wgrad(const float* gy, const float* x, int64_t x_imgs, float* dw, int64_t imgs, int H, int W, int Cin,
+                         int Cout, int k, int stride, int pad, int splits, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- per-channel sums for the tdBN / folded-affine backward: sum_g[c] = sum_r g[r][c], sum_gx[c] = sum_r
  * g[r][c] * x[r mod x_rows][c] (autograd of nn.BatchNorm3d inside batch_norm_2d, models/common.py:674-679).
  * ws: at least 16*C + 256 bytes. */

@@ -63,3 +63,58 @@ def test_colsum2():
     sg, sgx = F.colsum2(g, x, 128)
     assert torch.allclose(sg.cpu(), g.double().sum(0).float().cpu(), rtol=1e-5, atol=1e-4)
     assert torch.allclose(sgx.cpu(), (g.double() * x.double()).sum(0).float().cpu(), rtol=1e-5, atol=1e-4)
+
+
+CONV_BWD = [  # ci, co, k, s, H, W, N, T
+    (64, 128, 3, 1, 10, 12, 2, 2), (64, 64, 3, 2, 12, 10, 2, 2), (128, 64, 1, 1, 6, 8, 2, 2),
+    (192, 256, 3, 1, 9, 9, 1, 2), (128, 256, 3, 2, 16, 16, 3, 1), (512, 128, 3, 1, 8, 8, 2, 1)]
+
+
+@pytest.mark.parametrize("ci,co,k,s,H,W,N,T", CONV_BWD)
+@pytest.mark.parametrize("mode,tol", [("parity", 3e-5), ("fast", 8e-3)])
+def test_spike_conv_backward(ci, co, k, s, H, W, N, T, mode, tol):
+    """dgrad + wgrad of the spike conv vs torch autograd of F.conv2d (fp32 reference)."""
+    import torch.nn.functional as tF
+    E = ecsy()
+    F = E.functional
+    F.set_precision(mode)
+    try:
+        g = S.gen(ci * 7 + co + k + s)
+        x = (torch.rand(T, N, ci, H, W, generator=g) < 0.2).float()
+        w = (torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5)
+        p = k // 2
+        xr = x.reshape(T * N, ci, H, W).clone().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        y = tF.conv2d(xr, wr, None, s, p)
+        gy = torch.randn(*y.shape, generator=g)
+        y.backward(gy)
+        Ho, Wo = y.shape[2], y.shape[3]
+        gy_nhwc = gy.reshape(T, N, co, Ho, Wo).permute(0, 1, 3, 4, 2).contiguous().cuda()
+        sp = F.Spikes.from_act(F.Act.from_ref(x.cuda()))
+        dw = F.spike_conv_wgrad(gy_nhwc, sp, k, s, p).cpu()
+        e_w = rel_l2(dw, wr.grad)
+        wT = F.pack_dgrad_weight(w.cuda(), F.get_splits())
+        gx = F.conv_dgrad(gy_nhwc, wT, F.get_splits(), H, W, ci, k, s, p).cpu()
+        want_gx = xr.grad.reshape(T, N, ci, H, W).permute(0, 1, 3, 4, 2)
+        e_x = rel_l2(gx, want_gx)
+        assert e_w < tol and e_x < tol, f"wgrad {e_w:.3e} dgrad {e_x:.3e}"
+    finally:
+        F.set_precision("parity")
+
+
+def test_real_conv_wgrad():
+    import torch.nn.functional as tF
+    E = ecsy()
+    F = E.functional
+    g = S.gen(99)
+    for (ci, co, k, s, H, W, N) in [(3, 64, 7, 2, 32, 32, 2), (128, 64, 3, 1, 6, 6, 2)]:
+        x = torch.rand(N, ci, H, W, generator=g)
+        w = torch.randn(co, ci, k, k, generator=g).requires_grad_(True)
+        y = tF.conv2d(x, w, None, s, k // 2)
+        gy = torch.randn(*y.shape, generator=g)
+        y.backward(gy)
+        a = F.Act.from_ref(x.unsqueeze(0).cuda())
+        gyn = gy.permute(0, 2, 3, 1).contiguous().unsqueeze(0).cuda()
+        dw = F.real_conv_wgrad(gyn, a, k, s, k // 2).cpu()
+        e = rel_l2(dw, w.grad)
+        assert e < 3e-5, e
