@@ -42,6 +42,8 @@ SIGNATURES = {
     "ecsy_tdbn_stats": (_i, [_p, _l, _i, _p, _p, _p, _z, _p]),
     "ecsy_affine_add": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _p, _l, _l, _i, _p]),
     "ecsy_resample": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ecsy_maxpool_bwd": (_i, [_p, _l, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
+    "ecsy_sumpool_slice": (_i, [_p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_tsum": (_i, [_p, _p, _f, _p, _i, _l, _p]),
     "ecsy_detect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _l, _l, _p]),
     "ecsy_xty_bf16": (_i, [_p, _p, _p, _p, _l, _i, _i, _f, _p, _p]),

@@ -1,0 +1,283 @@
+"""Manual backward of the fused train-mode chains, exposed as torch.autograd.Functions per block.
+
+The reference gets its backward from PyTorch autograd through every aten op of the time loop
+(SURVEY section 8 row a11).  Here each block's backward is an explicit chain of C-ABI calls:
+
+    tdBN backward   : ecsy_colsum2 (sum g, sum g*y) + ecsy_affine_add (g_y = A*g + B*y + C per channel)
+    conv backward   : ecsy_spike_conv_wgrad / ecsy_real_conv_wgrad, ecsy_conv_dgrad          (tcgen05)
+    neuron backward : ecsy_lif_ecs_bwd -- surrogate-gradient BPTT, forward recomputed, not stored
+    resampling      : ecsy_maxpool_bwd, ecsy_sumpool_slice
+
+torch.autograd only connects the blocks (and runs the tiny Detect head, < 0.1 % of the FLOPs).
+Gradients between chains are "w.r.t. the normalised tensor", so a chain's tdBN backward consumes
+exactly what the next chain's neuron backward produces.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import functional as F_
+from .functional import Act
+
+
+def _params(mod) -> list:
+    return [p for p in mod.parameters()]
+
+
+def _grad_tuple(mod, grads: Dict[int, torch.Tensor]):
+    out = []
+    for p in _params(mod):
+        g = grads.get(id(p))
+        if g is not None and g.shape != p.shape:
+            g = g.reshape(p.shape)
+        out.append(g)
+    return tuple(out)
+
+
+def _acc(grads, p, g):
+    grads[id(p)] = g if id(p) not in grads else grads[id(p)] + g
+
+
+# ------------------------------------------------------------------------------------------------
+# tdBN (train mode)
+# ------------------------------------------------------------------------------------------------
+def bn_train_fwd(bn_mod, y: Act):
+    """-> (scale, shift, mean, rstd); updates running statistics like _tdbn.scale_shift."""
+    bn = bn_mod.bn
+    mean, var = F_.bn_stats(y)
+    with torch.no_grad():
+        if bn.track_running_stats:
+            n = float(y.T * y.N * y.H * y.W)
+            for _ in range(bn_mod.stat_updates):
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1.0, 1.0))
+        rstd = torch.rsqrt(var + bn.eps)
+        scale = (bn.weight * rstd).contiguous()
+        shift = (bn.bias - mean * scale).contiguous()
+    return scale, shift, mean, rstd
+
+
+def bn_train_bwd(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
+    """g_yn: [Tp,N,H,W,C] gradient w.r.t. the normalised output (already summed over T when y is a
+    T-broadcast tensor).  Returns g_y with the same shape."""
+    bn = bn_mod.bn
+    C = y.C
+    n = float(y.T * y.N * y.H * y.W)
+    tfac = float(y.T) / float(y.Tp)
+    sg, sgy = F_.colsum2(g_yn, y.data, C)
+    with torch.no_grad():
+        sgx = rstd * (sgy - mean * sg)
+        A = (bn.weight * rstd).contiguous()
+        B = (-A * rstd * sgx / n)
+        Cc = (-A * sg / n - B * mean)
+        B = (B * tfac).contiguous()
+        Cc = (Cc * tfac).contiguous()
+        zeros = torch.zeros_like(B)
+    _acc(grads, bn.weight, sgx)
+    _acc(grads, bn.bias, sg)
+    return F_.affine_add(Act(g_yn, g_yn.shape[0]), A, Cc, Act(y.data, y.Tp), B, zeros).data
+
+
+# ------------------------------------------------------------------------------------------------
+# LIF -> spike conv -> tdBN
+# ------------------------------------------------------------------------------------------------
+class _Saved:
+    __slots__ = ("x", "aff", "sp", "y", "mean", "rstd", "scale", "shift")
+
+
+def chain_fwd(lif, conv, bn, x: Act, aff):
+    sv = _Saved()
+    sv.x, sv.aff = x, aff
+    sv.sp = lif.spikes(x, aff)
+    sv.y = conv.conv_spikes(sv.sp)
+    sv.scale, sv.shift, sv.mean, sv.rstd = bn_train_fwd(bn, sv.y)
+    return sv
+
+
+def conv_spikes_bwd(conv, sp, g_y: torch.Tensor, grads):
+    """-> g_s [T,N,H,W,Ci]; accumulates dW."""
+    from .common import _cached
+    k, s, p = conv._geom()
+    dw = F_.spike_conv_wgrad(g_y, sp, k, s, p)
+    if conv.groups > 1:  # block-diagonal part of the dense gradient
+        cog, cig = conv.out_channels // conv.groups, conv.in_channels // conv.groups
+        dw = torch.cat([dw[g * cog:(g + 1) * cog, g * cig:(g + 1) * cig] for g in range(conv.groups)], 0)
+    _acc(grads, conv.weight, dw)
+    splits = F_.get_splits()
+
+    def build():
+        w = conv.weight
+        if conv.groups > 1:
+            w = F_.densify_grouped(w, conv.groups)
+        return F_.pack_dgrad_weight(w, splits)
+    wT = _cached(conv, "dgradw", (conv.weight,), build)
+    return F_.conv_dgrad(g_y, wT, splits, sp.H, sp.W, conv.in_channels, k, s, p)
+
+
+def chain_bwd(lif, conv, bn, sv: _Saved, g_yn: torch.Tensor, grads):
+    """g_yn: gradient w.r.t. the chain's normalised output -> gradient w.r.t. its (normalised) input."""
+    g_y = bn_train_bwd(bn, sv.y, sv.mean, sv.rstd, g_yn, grads)
+    g_s = conv_spikes_bwd(conv, sv.sp, g_y, grads)
+    g_x, gdw, gdb, gpw, gpb = F_.lif_ecs_bwd(g_s, sv.x, lif._weights(), lif.spread[1].weight, sv.aff, lif.ecs_tau,
+                                             lif.alpha, lif.beta)
+    _acc(grads, lif.spread[0].weight, gdw)
+    _acc(grads, lif.spread[0].bias, gdb)
+    _acc(grads, lif.spread[1].weight, gpw)
+    _acc(grads, lif.spread[1].bias, gpb)
+    return g_x
+
+
+def _to_nhwc(g: torch.Tensor) -> torch.Tensor:
+    """Incoming reference-shaped gradient [T,N,C,H,W] (any strides) -> contiguous NHWC data [T,N,H,W,C]."""
+    a = Act.from_ref(g)
+    return a.full().data if a.Tp != a.T else a.data
+
+
+def _add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return F_.affine_add(Act(a, a.shape[0]), None, None, Act(b, b.shape[0])).data
+
+
+class BasicBlockFn(torch.autograd.Function):
+    """BasicBlock_1 / BasicBlock_2 in training mode (models/common.py:1049-1079, 1182-1219)."""
+
+    @staticmethod
+    def forward(ctx, block, x_ref, *params):
+        a = Act.from_ref(x_ref)
+        l1, c1, b1, l2, c2, b2 = block.residual_function
+        s1 = chain_fwd(l1, c1, b1, a, None)
+        s2 = chain_fwd(l2, c2, b2, s1.y, (s1.scale, s1.shift))
+        ctx.block, ctx.a, ctx.s1, ctx.s2 = block, a, s1, s2
+        if len(block.shortcut) == 0:
+            ctx.s3 = None
+            out = F_.affine_add(s2.y, s2.scale, s2.shift, a, None, None)
+        else:
+            pool, l3, c3, b3 = block.shortcut
+            ctx.pool = pool.stride[1]
+            ctx.xp = F_.maxpool(a, ctx.pool)
+            s3 = chain_fwd(l3, c3, b3, ctx.xp, None)
+            ctx.s3 = s3
+            out = F_.affine_add(s2.y, s2.scale, s2.shift, s3.y, s3.scale, s3.shift)
+        return out.to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        block = ctx.block
+        g = _to_nhwc(g_ref)
+        grads: Dict[int, torch.Tensor] = {}
+        l1, c1, b1, l2, c2, b2 = block.residual_function
+        g_y1n = chain_bwd(l2, c2, b2, ctx.s2, g, grads)
+        g_x = chain_bwd(l1, c1, b1, ctx.s1, g_y1n, grads)
+        if ctx.s3 is None:
+            g_x = _add(g_x, g)
+        else:
+            pool, l3, c3, b3 = block.shortcut
+            g_p = chain_bwd(l3, c3, b3, ctx.s3, g, grads)
+            g_sc = F_.maxpool_bwd(ctx.a, g_p, ctx.pool) if ctx.pool > 1 else g_p
+            g_x = _add(g_x, g_sc)
+        return (None, g_x.permute(0, 1, 4, 2, 3)) + _grad_tuple(block, grads)
+
+
+class ConcatRes2Fn(torch.autograd.Function):
+    """Concat_res2 in training mode (models/common.py:1454-1488)."""
+
+    @staticmethod
+    def forward(ctx, block, x_ref, *params):
+        a = Act.from_ref(x_ref)
+        l1, c1, b1, l2, c2, b2 = block.residual_function
+        s1 = chain_fwd(l1, c1, b1, a, None)
+        s2 = chain_fwd(l2, c2, b2, s1.y, (s1.scale, s1.shift))
+        pool = block.pools.stride[1]
+        ctx.block, ctx.a, ctx.s1, ctx.s2, ctx.pool = block, a, s1, s2, pool
+        if len(block.shortcut) == 0:
+            ctx.s3, ctx.temp = None, a
+        else:
+            l3, c3, b3 = block.shortcut
+            ctx.s3 = chain_fwd(l3, c3, b3, a, None)
+            ctx.temp = F_.affine_add(ctx.s3.y, ctx.s3.scale, ctx.s3.shift)
+        sc = F_.concat_channels([ctx.temp, a], pool=pool)
+        out = F_.affine_add(s2.y, s2.scale, s2.shift, sc, None, None)
+        return out.to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        block = ctx.block
+        g = _to_nhwc(g_ref)
+        grads: Dict[int, torch.Tensor] = {}
+        l1, c1, b1, l2, c2, b2 = block.residual_function
+        g_y1n = chain_bwd(l2, c2, b2, ctx.s2, g, grads)
+        g_x = chain_bwd(l1, c1, b1, ctx.s1, g_y1n, grads)
+        ct = ctx.temp.C
+        # shortcut = max-pool(cat(temp, x)): the pool acts per channel, so each source gets its own slice back
+        g_temp = F_.maxpool_bwd(ctx.temp, g, ctx.pool, 0) if ctx.pool > 1 else F_.sumpool_slice(g, ct, 0, 1)
+        g_x2 = F_.maxpool_bwd(ctx.a, g, ctx.pool, ct) if ctx.pool > 1 else F_.sumpool_slice(g, ctx.a.C, ct, 1)
+        g_x = _add(g_x, g_x2)
+        if ctx.s3 is None:
+            g_x = _add(g_x, g_temp)
+        else:
+            l3, c3, b3 = block.shortcut
+            g_x = _add(g_x, chain_bwd(l3, c3, b3, ctx.s3, g_temp, grads))
+        return (None, g_x.permute(0, 1, 4, 2, 3)) + _grad_tuple(block, grads)
+
+
+class StemFn(torch.autograd.Function):
+    """Conv_1 in training mode: real-input conv + tdBN (models/common.py:409-425).  The image needs no
+    gradient.  For a T-broadcast input the output is ONE frame; the caller expands it, so autograd delivers
+    the sum over T."""
+
+    @staticmethod
+    def forward(ctx, mod, x_ref, *params):
+        a = Act.from_ref(x_ref)
+        y = mod.conv.conv_real(a)
+        scale, shift, mean, rstd = bn_train_fwd(mod.bn, y)
+        ctx.mod, ctx.a, ctx.y, ctx.mean, ctx.rstd = mod, a, y, mean, rstd
+        out = F_.affine_add(y, scale, shift)
+        return out.data.permute(0, 1, 4, 2, 3)        # [Tp,N,C,H,W]
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        mod = ctx.mod
+        g = Act.from_ref(g_ref).data                  # [Tp,N,H,W,C]
+        grads: Dict[int, torch.Tensor] = {}
+        g_y = bn_train_bwd(mod.bn, ctx.y, ctx.mean, ctx.rstd, g, grads)
+        k, s, p = mod.conv._geom()
+        _acc(grads, mod.conv.weight, F_.real_conv_wgrad(g_y, ctx.a, k, s, p))
+        return (None, None) + _grad_tuple(mod, grads)
+
+
+class SampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_ref, s):
+        ctx.s = s
+        return F_.upsample(Act.from_ref(x_ref), s).to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        g = _to_nhwc(g_ref)
+        return F_.sumpool_slice(g, g.shape[4], 0, ctx.s).permute(0, 1, 4, 2, 3), None
+
+
+class ConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        acts = [Act.from_ref(t) for t in xs]
+        ctx.cs = [a.C for a in acts]
+        return F_.concat_channels(acts).to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        g = _to_nhwc(g_ref)
+        outs, off = [], 0
+        for c in ctx.cs:
+            outs.append(F_.sumpool_slice(g, c, off, 1).permute(0, 1, 4, 2, 3))
+            off += c
+        return tuple(outs)
+
+
+def wants_grad(mod, *tensors) -> bool:
+    if not (mod.training and torch.is_grad_enabled()):
+        return False
+    return any(t.requires_grad for t in tensors if torch.is_tensor(t)) or any(p.requires_grad for p in mod.parameters())

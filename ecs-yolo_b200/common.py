@@ -10,8 +10,8 @@ libecsy.so through ``functional``; tensors crossing a module boundary are refere
 
 Known, deliberate differences from the reference: T is read from the tensor, not from a
 module-level global; ``mem_update.spread`` is created when the owning block is constructed (the
-channel count is known there) instead of on the first forward; no autograd graph is recorded yet
-(forward/inference and train-mode statistics only).
+channel count is known there) instead of on the first forward; the backward is a manual chain of C-ABI
+calls per block (``autograd.py``) instead of autograd through every time-loop op.
 """
 # NOTE: `Conv.conv` sees a REAL input (models/common.py:372), so it takes the im2col + tcgen05 path.
 from __future__ import annotations
@@ -260,6 +260,9 @@ class _BasicBlock(nn.Module):
         self._stride = stride
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import autograd as AG
+        if AG.wants_grad(self, x):
+            return AG.BasicBlockFn.apply(self, x, *self.parameters())
         a = Act.from_ref(x)
         if len(self.shortcut) == 0:
             return _residual_path(self.residual_function, a, a).to_ref()
@@ -302,6 +305,9 @@ class Concat_res2(nn.Module):
         self.pools = nn.MaxPool3d((1, stride, stride), stride=(1, stride, stride))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import autograd as AG
+        if AG.wants_grad(self, x):
+            return AG.ConcatRes2Fn.apply(self, x, *self.parameters())
         a = Act.from_ref(x)
         if len(self.shortcut) == 0:
             temp = a
@@ -323,6 +329,10 @@ class Conv_1(nn.Module):
         self.bn = batch_norm_2d(c2)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import autograd as AG
+        if AG.wants_grad(self, x):
+            out = AG.StemFn.apply(self, x, *self.parameters())
+            return out.expand(x.shape[0], -1, -1, -1, -1) if out.shape[0] != x.shape[0] else out
         a = Act.from_ref(x)
         if self.bn.bn.training:
             y = self.conv.conv_real(a)
@@ -408,6 +418,9 @@ class Sample(nn.Module):
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         if self.mode != 'nearest' or self.size is not None:
             raise NotImplementedError("Sample: only nearest up-sampling by an integer factor")
+        if torch.is_grad_enabled() and input.requires_grad:
+            from . import autograd as AG
+            return AG.SampleFn.apply(input, int(self.scale_factor))
         return F_.upsample(Act.from_ref(input), int(self.scale_factor)).to_ref()
 
 
@@ -420,6 +433,9 @@ class Concat(nn.Module):
 
     def forward(self, x):
         if self.d == 2 and all(t.dim() == 5 and t.is_cuda for t in x):
+            if torch.is_grad_enabled() and any(t.requires_grad for t in x):
+                from . import autograd as AG
+                return AG.ConcatFn.apply(*x)
             return F_.concat_channels([Act.from_ref(t) for t in x]).to_ref()
         return torch.cat(x, self.d)
 

@@ -616,6 +616,71 @@ __global__ void k_ddetect_decode(const float* __restrict__ box, const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward helpers of the resampling ops: max-pool (gradient to the first maximum of each window, as
+// nn.MaxPool3d), nearest up-sampling (sum over each s x s block) and channel slicing (Concat backward).
+// ------------------------------------------------------------------------------------------
+__global__ void k_maxpool_bwd(const float* __restrict__ x, int64_t x_imgs, const float* __restrict__ gp,
+                              float* __restrict__ gx, int64_t imgs, int Ho, int Wo, int C, int gC, int gcoff, int s) {
+  const int c4 = C >> 2;
+  const int64_t total = imgs * Ho * Wo * c4;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const int Hi = Ho * s, Wi = Wo * s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int q = static_cast<int>(i % c4);
+    int64_t p = i / c4;
+    const int wo = static_cast<int>(p % Wo); p /= Wo;
+    const int ho = static_cast<int>(p % Ho);
+    const int64_t img = p / Ho;
+    const float* src = x + ((img % x_imgs) * Hi * Wi) * (int64_t)C + q * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gp + (((img * Ho + ho) * Wo + wo) * (int64_t)gC + gcoff + q * 4));
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int arg[4] = {0, 0, 0, 0};
+    for (int dy = 0; dy < s; ++dy)
+      for (int dx = 0; dx < s; ++dx) {
+        const float4 u = *reinterpret_cast<const float4*>(src + ((int64_t)(ho * s + dy) * Wi + (wo * s + dx)) * C);
+        const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (uu[k] > best[k]) { best[k] = uu[k]; arg[k] = dy * s + dx; }
+      }
+    const float gg[4] = {g.x, g.y, g.z, g.w};
+    for (int dy = 0; dy < s; ++dy)
+      for (int dx = 0; dx < s; ++dx) {
+        float4 o;
+        o.x = arg[0] == dy * s + dx ? gg[0] : 0.f;
+        o.y = arg[1] == dy * s + dx ? gg[1] : 0.f;
+        o.z = arg[2] == dy * s + dx ? gg[2] : 0.f;
+        o.w = arg[3] == dy * s + dx ? gg[3] : 0.f;
+        *reinterpret_cast<float4*>(gx + (((img * Hi + ho * s + dy) * Wi + wo * s + dx) * (int64_t)C + q * 4)) = o;
+      }
+  }
+}
+
+// out[img][ho][wo][c] = sum over the s x s block of in[img][ho*s+dy][wo*s+dx][coff + c]  (s == 1: channel slice)
+__global__ void k_sumpool_slice(const float* __restrict__ in, float* __restrict__ out, int64_t imgs, int Ho, int Wo,
+                                int C, int inC, int coff, int s) {
+  const int c4 = C >> 2;
+  const int64_t total = imgs * Ho * Wo * c4;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const int Hi = Ho * s, Wi = Wo * s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int q = static_cast<int>(i % c4);
+    int64_t p = i / c4;
+    const int wo = static_cast<int>(p % Wo); p /= Wo;
+    const int ho = static_cast<int>(p % Ho);
+    const int64_t img = p / Ho;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dy = 0; dy < s; ++dy)
+      for (int dx = 0; dx < s; ++dx) {
+        const float4 u = *reinterpret_cast<const float4*>(
+            in + (((img * Hi + ho * s + dy) * Wi + wo * s + dx) * (int64_t)inC + coff + q * 4));
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -840,5 +905,27 @@ extern "C" int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float*
     k_silu_step<<<grid, kThreads, 0, st>>>(s, n4, C);
     ECSY_LAUNCH_CHECK();
   }
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_maxpool_bwd(const float* x, int64_t x_imgs, const float* g_pooled, float* gx, int64_t imgs, int Ho,
+                                int Wo, int C, int gC, int gcoff, int s, void* stream) {
+  ECSY_CHECK_ARG(x && g_pooled && gx && imgs > 0 && x_imgs > 0 && imgs % x_imgs == 0, "maxpool_bwd: bad arguments");
+  ECSY_CHECK_ARG(C % 4 == 0 && gC % 4 == 0 && gcoff % 4 == 0 && gcoff + C <= gC && s >= 1, "maxpool_bwd: channels");
+  const int64_t total = imgs * Ho * Wo * (C / 4);
+  k_maxpool_bwd<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+      x, x_imgs, g_pooled, gx, imgs, Ho, Wo, C, gC, gcoff, s);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_sumpool_slice(const float* in, float* out, int64_t imgs, int Ho, int Wo, int C, int inC, int coff,
+                                  int s, void* stream) {
+  ECSY_CHECK_ARG(in && out && imgs > 0 && s >= 1, "sumpool_slice: bad arguments");
+  ECSY_CHECK_ARG(C % 4 == 0 && inC % 4 == 0 && coff % 4 == 0 && coff + C <= inC, "sumpool_slice: channels");
+  const int64_t total = imgs * Ho * Wo * (C / 4);
+  k_sumpool_slice<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(in, out, imgs, Ho, Wo, C,
+                                                                                               inC, coff, s);
+  ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }

@@ -490,6 +490,26 @@ def concat_channels(xs, pool: int = 1) -> Act:
     return Act(out, T)
 
 
+def maxpool_bwd(x: Act, g_pooled: torch.Tensor, s: int, gcoff: int = 0) -> torch.Tensor:
+    """x: the pool input; g_pooled: [T,N,Ho,Wo,gC] (channels [gcoff, gcoff+x.C) are this input's) -> gx [T,N,H,W,C]."""
+    T, N, Ho, Wo, gC = g_pooled.shape
+    gx = torch.empty(T, N, Ho * s, Wo * s, x.C, device=g_pooled.device, dtype=torch.float32)
+    with _timed("resample_bwd", 1):
+        _cabi.check(_cabi.lib().ecsy_maxpool_bwd(_p(x.data), x.src_imgs, _p(g_pooled), _p(gx), T * N, Ho, Wo, x.C, gC,
+                                                 gcoff, s, _st()), "maxpool_bwd")
+    return gx
+
+
+def sumpool_slice(g: torch.Tensor, C: int, coff: int, s: int) -> torch.Tensor:
+    """[T,N,H,W,inC] -> [T,N,H/s,W/s,C]: block sums of channels [coff, coff+C) (Sample / Concat backward)."""
+    T, N, H, W, inC = g.shape
+    out = torch.empty(T, N, H // s, W // s, C, device=g.device, dtype=torch.float32)
+    with _timed("resample_bwd", 1):
+        _cabi.check(_cabi.lib().ecsy_sumpool_slice(_p(g), _p(out), T * N, H // s, W // s, C, inC, coff, s, _st()),
+                    "sumpool_slice")
+    return out
+
+
 def tsum(x: Act, w: Optional[torch.Tensor], div: float) -> torch.Tensor:
     """[T, N, H, W, C] -> [N, H, W, C]: (sum_t w[t] x[t]) / div."""
     x = x.full()

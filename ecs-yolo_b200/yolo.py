@@ -46,6 +46,8 @@ class Detect(nn.Module):
         conv + bias, so the features are reduced over T first (4x less head work), then one 1x1 conv
         with bias * sum(w) and the view/permute/decode kernel (models/yolo.py:85-146)."""
         x = list(x)
+        if self.training and torch.is_grad_enabled() and any(t.requires_grad for t in x):
+            return self._forward_train_autograd(x)
         z_rows = sum(self.na * xi.shape[3] * xi.shape[4] for xi in x)
         z = None
         if not self.training:
@@ -65,6 +67,21 @@ class Detect(nn.Module):
             x[i] = F_.detect_decode(y, self.na, self.no, self.anchors[i].contiguous(), stride_i, z, off)
             off += self.na * y.shape[1] * y.shape[2]
         return x if self.training else (z, x)
+
+
+    def _forward_train_autograd(self, x):
+        """Training with gradients: the head (< 0.1 % of the model's FLOPs, tensors of N*(ny*nx) rows) runs as
+        differentiable torch ops -- T-fusion, 1x1 conv + bias, view/permute (models/yolo.py:95-104)."""
+        import torch.nn.functional as tF
+        out = []
+        for i in range(self.nl):
+            xi = x[i]
+            wt = self.w[i].conv.weight.reshape(-1, 1, 1, 1, 1)
+            feat = (xi * wt).sum(0)
+            y = tF.conv2d(feat, self.m[i].weight, None) + self.m[i].bias.view(1, -1, 1, 1) * wt.sum()
+            bs, _, ny, nx = y.shape
+            out.append(y.view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous())
+        return out
 
 
 class Model(nn.Module):

@@ -98,6 +98,14 @@ int ecsy_affine_add(const float* a, int64_t a_imgs, const float* sa, const float
 int ecsy_resample(const float* in, int64_t in_imgs, const float* scale, const float* shift, float* out, int64_t imgs,
                   int Hi, int Wi, int C, int Ctot, int coff, int pool, int up, void* stream);
 
+/* ---- backward of the resampling ops: nn.MaxPool3d((1,s,s)) (gradient to the first maximum of each window; the
+ * pooled gradient may live in channels [gcoff, gcoff+C) of a wider tensor), and Sample / Concat
+ * (sum over each s x s block of channels [coff, coff+C) of `in`; s == 1 is a plain channel slice). */
+int ecsy_maxpool_bwd(const float* x, int64_t x_imgs, const float* g_pooled, float* gx, int64_t imgs, int Ho, int Wo,
+                     int C, int gC, int gcoff, int s, void* stream);
+int ecsy_sumpool_slice(const float* in, float* out, int64_t imgs, int Ho, int Wo, int C, int inC, int coff, int s,
+                       void* stream);
+
 /* ---- reduction over T: out = (sum_t w[t] * x[t]) / div.  Conv_7 (common.py:549-562, w = Conv3d weight) and
  * DDetect's mean over T (yolo_snn.py:115-116, w = NULL, div = T). */
 int ecsy_tsum(const float* x, const float* w, float div, float* out, int T, int64_t per_t, void* stream);
