@@ -107,6 +107,98 @@ def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads):
     return sample_imgs * steps / dt, dt / steps
 
 
+def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload):
+    """fwd + loss + bwd + SGD-nesterov step per batch (train.py:555-582 shape of a step; the loss here is a
+    synthetic quadratic on the raw head outputs -- the YOLO loss/assigner is outside the hot path)."""
+    model.train()
+    net = model
+    if dist is not None:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=64,
+                                                        gradient_as_bucket_view=True)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.937, nesterov=True)
+    with torch.no_grad():
+        probe = model(x[:1])
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    tgt = [torch.randn(args.batch, *o.shape[1:], device="cuda", generator=g) for o in probe]
+
+    def step(inp):
+        opt.zero_grad(set_to_none=True)
+        out = net(inp)
+        loss = sum(((o - t) ** 2).mean() for o, t in zip(out, tgt))
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, args.min_warmup)):
+        step(x)
+    barrier()
+    F.launches["n"] = 0
+    for k in F.flops:
+        F.flops[k] = 0.0
+    F.profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            step(x)
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    per_op = F.profile_end()
+    launches = F.launches["n"]
+    flops = dict(F.flops)
+    barrier()
+    t0 = time.perf_counter()
+    loss_host = 0.0
+    for _ in range(0 if args.no_e2e else args.steps):
+        xd = x_host.to("cuda", non_blocking=True)
+        loss_host = float(step(xd).detach().cpu())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    imgs = args.batch * world * args.steps
+    pk = peaks()
+    conv_ms = (per_op.get("spike_conv", 0.0) + per_op.get("conv_dgrad", 0.0) + per_op.get("conv_wgrad", 0.0)) / args.steps
+    conv_fl = (flops.get("spike_conv", 0.0) + flops.get("conv_bwd", 0.0)) / args.steps
+    conv_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    line = {
+        "metric": "images/s", "value": imgs / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload.replace("inference", "training (fwd + loss + bwd + SGD step)"),
+                   "model_cfg": f"cfg/{args.model}.yaml", "T": args.T, "global_batch": args.batch * world,
+                   "precision": args.precision, "accumulate": "fp32",
+                   "parallelism": f"DDP x{world} (NCCL all-reduce of fp32 gradients, 64 MB buckets)" if world > 1
+                                  else "single GPU",
+                   "loss": "synthetic quadratic on the raw head outputs (YOLO loss is outside the hot path)",
+                   "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": (imgs / (e2e_ms * 1e-3)) if e2e_ms > 0 else None, "unit": "images/s",
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clk.summary(),
+        "roofline": {"kernel": "tcgen05 conv kernels (spike conv fwd + dgrad + wgrad)", "bound": "tensor",
+                     "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": conv_tf / pk["tf_sust"],
+                     "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                     "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms},
+        "breakdown_ms_per_step": {k: v / args.steps for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
+        "last_loss": loss_host,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -122,6 +214,8 @@ def main():
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs under ncu may lower this")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--cpu-sample", type=int, default=1, help="images per CPU step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -169,6 +263,9 @@ def main():
     g = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.rand(args.batch, 3, args.img, args.img, generator=g).pin_memory()
     x = x_host.cuda()
+
+    if args.mode == "train":
+        return train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload)
 
     # momentum-1 calibration of every tdBN on the seed batch, then eval
     for m in model.modules():

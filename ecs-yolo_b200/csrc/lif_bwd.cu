@@ -103,11 +103,17 @@ __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __re
       }
     }
   }
-  if (ty < nty) {
+  // block reduction over the ty rows in shared memory, then one double atomic per (quantity, channel)
+  extern __shared__ float sred[];  // [nty][11][C]
 #pragma unroll
-    for (int a = 0; a < 11; ++a)
+  for (int a = 0; a < 11; ++a)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) atomicAdd(acc + (int64_t)a * C + tq * 4 + k, (double)s[a][k]);
+    for (int k = 0; k < 4; ++k) sred[(ty * 11 + a) * C + tq * 4 + k] = s[a][k];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 11 * C; idx += blockDim.x) {
+    double t = 0;
+    for (int y = 0; y < nty; ++y) t += sred[y * 11 * C + idx];
+    atomicAdd(acc + idx, t);
   }
 }
 
@@ -199,12 +205,17 @@ __global__ void k_colsum2(const float* __restrict__ g, const float* __restrict__
       cnt = 0;
     }
   }
-  if (ty < nty) {
+  extern __shared__ double dred[];  // [nty][2][C]
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      atomicAdd(acc + tq * 4 + k, sg[k] + fg[k]);
-      atomicAdd(acc + C + tq * 4 + k, sx[k] + fx[k]);
-    }
+  for (int k = 0; k < 4; ++k) {
+    dred[(ty * 2 + 0) * C + tq * 4 + k] = sg[k] + fg[k];
+    dred[(ty * 2 + 1) * C + tq * 4 + k] = sx[k] + fx[k];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    double t = 0;
+    for (int y = 0; y < nty; ++y) t += dred[y * 2 * C + idx];
+    atomicAdd(acc + idx, t);
   }
 }
 
@@ -273,8 +284,8 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
       if (rc) return rc;
       ECSY_CUDA(cudaMemsetAsync(acc, 0, 11 * (size_t)C * sizeof(double), st));
-      k_lif_bwd_reduce<<<grid_for(M, 64, ecsy_num_sms() * 4), rbd, 0, st>>>(ge, g1, spikes + t * words, acc, (int)N, H, W,
-                                                                        C);
+      k_lif_bwd_reduce<<<grid_for(M, 64, ecsy_num_sms() * 4), rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(
+          ge, g1, spikes + t * words, acc, (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
       k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(acc, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
@@ -301,7 +312,8 @@ extern "C" int ecsy_colsum2(const float* g, const float* x, int64_t rows, int64_
   ECSY_CUDA(cudaMemsetAsync(acc, 0, 2 * (size_t)C * sizeof(double), st));
   const int c4 = C / 4;
   const int bd = (256 / c4) * c4;
-  k_colsum2<<<grid_for(rows, 64, ecsy_num_sms() * 4), bd, 0, st>>>(g, x, rows, x_rows, C, acc);
+  k_colsum2<<<grid_for(rows, 64, ecsy_num_sms() * 4), bd, (size_t)(bd / c4) * 2 * C * sizeof(double), st>>>(g, x, rows,
+                                                                                                        x_rows, C, acc);
   ECSY_LAUNCH_CHECK();
   k_d2f<<<(C + 255) / 256, 256, 0, st>>>(acc, sum_g, C);
   ECSY_LAUNCH_CHECK();
