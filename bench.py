@@ -77,6 +77,16 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
 
 
+def measured_traffic(model, batch, T, precision):
+    """DRAM bytes per step of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None
+    when no capture exists for this exact configuration."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    ent = json.load(open(path)).get(f"{model}|{batch}|{T}|{precision}")
+    return ent["dram_bytes_per_step"] if ent else None
+
+
 def load_cfg(name):
     return yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", name + ".yaml")))
 
@@ -341,9 +351,12 @@ def main():
         "clocks": clk.summary(),
         "roofline": {"kernel": "k_umma_gemm<spikes,conv> (spike implicit-GEMM conv, tcgen05)", "bound": "tensor",
                      "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": conv_tf / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                     "frac": conv_tf / pk["tf_sust"],
+                     "traffic": measured_traffic(args.model, args.batch, args.T, args.precision),
+                     "traffic_note": "DRAM bytes per step summed over the kernel's launches (ncu, profiles/traffic.json)",
+                     "peak_source": pk["src"] + " sustained bf16",
                      "algorithmic_gflop_per_step": flops["spike_conv"] / args.steps / 1e9,
-                     "kernel_ms_per_step": conv_ms},
+                     "kernel_ms_per_step": conv_ms, "launches_per_step": 48},
         "breakdown_ms_per_step": {k: v / args.steps for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
         "dense_tflops_whole_step": (flops["spike_conv"] + flops["ecs_pw"] + flops["real_conv"]) / args.steps
                                    / (ms_total / args.steps * 1e-3) / 1e12,

@@ -9,7 +9,7 @@ The package directory carries the repo's hyphenated name, so it is imported thro
 """
 import os as _os
 
-from . import _cabi, functional, common, autograd, yolo, yolo_snn  # noqa: F401
+from . import _cabi, functional, common, autograd, yolo, yolo_snn, dist  # noqa: F401
 from .functional import set_precision  # noqa: F401
 
 __all__ = ["common", "yolo", "yolo_snn", "functional", "set_precision", "cfg_path", "build_library"]

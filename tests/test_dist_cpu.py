@@ -1,0 +1,68 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: batch sharding, max-over-ranks timing and the
+bucketed gradient all-reduce (equal to the single-process sum, missing gradients handled)."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+from util import ecsy
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    D = importlib.import_module("ecs-yolo_b200").dist
+    D.init("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    net[2].weight.requires_grad_(True)
+    lo, hi = D.shard_range(10, rank, world)
+    x = torch.arange(10 * 8, dtype=torch.float32).reshape(10, 8)[lo:hi] / 80.0
+    y = net[1](net[0](x)).sum()          # net[2] gets no gradient on any rank
+    y.backward()
+    ncoll = D.allreduce_grads(net.parameters(), bucket_bytes=256, average=False)
+    tmax = D.max_over_ranks([float(rank + 1), 5.0 - rank])
+    out[rank] = dict(g0=net[0].weight.grad.clone(), g2=net[2].weight.grad.clone(), ncoll=ncoll, tmax=tmax, lo=lo, hi=hi)
+    torch.distributed.destroy_process_group()
+
+
+def test_gloo_world2():
+    ecsy()
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert (r0["lo"], r0["hi"], r1["lo"], r1["hi"]) == (0, 5, 5, 10)
+    # single-process reference: full batch
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    x = torch.arange(10 * 8, dtype=torch.float32).reshape(10, 8) / 80.0
+    net[1](net[0](x)).sum().backward()
+    assert torch.allclose(r0["g0"], net[0].weight.grad, atol=1e-5) and torch.equal(r0["g0"], r1["g0"])
+    assert torch.equal(r0["g2"], torch.zeros(4, 4))           # missing gradients all-reduced as zeros
+    assert r0["ncoll"] == r1["ncoll"] and r0["ncoll"] >= 2   # several buckets, same count on every rank
+    assert r0["tmax"] == [2.0, 5.0] and r1["tmax"] == [2.0, 5.0]
+
+
+def test_shard_range_covers_everything():
+    D = ecsy().dist
+    for total in (1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
