@@ -2,6 +2,7 @@
 // the first LIF step, tdBN statistics, affine+add, max-pool, nearest upsample / concat, T-fusion
 // and the Stack-A / Stack-B head decodes.  All activations are NHWC fp32 ("[imgs][H][W][C]"),
 // spikes are one bit per channel packed along C ("[imgs][H][W][C/32]" uint32, bit c&31 of word c>>5).
+#include <cuda_fp16.h>
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
 #include "umma_gemm.h"
@@ -105,6 +106,27 @@ __global__ void k_lif_first(const float* __restrict__ x, const float* __restrict
 //   f_t     = beta*tanh(e_t)
 //   mem_t+1 = mem_t*decay*(1 - s_t) + x_{t+1} + f_t ;  s_{t+1} = mem_{t+1} > thresh
 // Every product / sum is rounded separately, in the reference's evaluation order.
+__device__ __forceinline__ float4 ld4h(const void* base, int64_t i) {
+  const uint2 r = reinterpret_cast<const uint2*>(base)[i];
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4h(void* base, int64_t i, float a, float b, float c, float d) {
+  __half2 h01 = __floats2half2_rn(a, b), h23 = __floats2half2_rn(c, d);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&h01);
+  pk.y = *reinterpret_cast<uint32_t*>(&h23);
+  reinterpret_cast<uint2*>(base)[i] = pk;
+}
+
+__device__ __forceinline__ float tanh_fast(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+template <bool HALF>
 __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4_round; i += stride) {
@@ -122,10 +144,10 @@ __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C)
         xv.z = ecsy::add_rn(ecsy::mul_rn(xv.z, s.z), b.z);
         xv.w = ecsy::add_rn(ecsy::mul_rn(xv.w, s.w), b.w);
       }
-      const float4 sv = ecsy::ldg_stream(reinterpret_cast<const float4*>(p.spread) + i);
+      const float4 sv = HALF ? ld4h(p.spread, i) : ecsy::ldg_stream(reinterpret_cast<const float4*>(p.spread) + i);
       const float4 mv = reinterpret_cast<const float4*>(p.mem_in)[i];
       float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!p.first) ev = reinterpret_cast<const float4*>(p.ecs)[i];
+      if (!p.first) ev = HALF ? ld4h(p.ecs, i) : reinterpret_cast<const float4*>(p.ecs)[i];
       const float4 pb = *reinterpret_cast<const float4*>(p.pw_b + c);
       const uint32_t pw = p.bits_t[i >> 3] >> (4 * sub);
       const float xin[4] = {xv.x, xv.y, xv.z, xv.w}, sp[4] = {sv.x, sv.y, sv.z, sv.w};
@@ -136,13 +158,17 @@ __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C)
       for (int k = 0; k < 4; ++k) {
         const float s_acc = ecsy::add_rn(sp[k], bb[k]);
         en[k] = ecsy::add_rn(ecsy::mul_rn(p.alpha, s_acc), ecsy::mul_rn(p.kappa, eo[k]));
-        const float fecs = ecsy::mul_rn(p.beta, tanhf(en[k]));
+        // fast mode (fp16 state): hardware tanh approximation (2^-11 relative), parity mode: tanhf
+        const float fecs = ecsy::mul_rn(p.beta, HALF ? tanh_fast(en[k]) : tanhf(en[k]));
         const float keep = ((pw >> k) & 1u) ? 0.f : 1.f;
         mn[k] = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(mo[k], p.decay), keep), xin[k]), fecs);
         nib |= (mn[k] > p.thresh ? 1u : 0u) << k;
       }
       if (p.mem_out != nullptr) reinterpret_cast<float4*>(p.mem_out)[i] = make_float4(mn[0], mn[1], mn[2], mn[3]);
-      if (p.store_ecs) reinterpret_cast<float4*>(p.ecs)[i] = make_float4(en[0], en[1], en[2], en[3]);
+      if (p.store_ecs) {
+        if (HALF) st4h(p.ecs, i, en[0], en[1], en[2], en[3]);
+        else reinterpret_cast<float4*>(p.ecs)[i] = make_float4(en[0], en[1], en[2], en[3]);
+      }
       if (p.ecs_save != nullptr) reinterpret_cast<float4*>(p.ecs_save)[i] = make_float4(en[0], en[1], en[2], en[3]);
     }
     uint32_t w = nib << (4 * sub);
@@ -734,7 +760,10 @@ int ecsy_launch_lif_first(const float* x, const float* scale, const float* shift
 int ecsy_launch_ecs_step(const EcsStep& p, int64_t pixels, int C, cudaStream_t st) {
   const int64_t n4 = pixels * C / 4;
   const int64_t n4_round = (n4 + 31) & ~int64_t(31);
-  k_ecs_step<<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(p, n4, n4_round, C);
+  if (p.half_state)
+    k_ecs_step<true><<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(p, n4, n4_round, C);
+  else
+    k_ecs_step<false><<<grid_for(n4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(p, n4, n4_round, C);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }

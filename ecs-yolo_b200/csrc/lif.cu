@@ -53,7 +53,9 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
   for (int t = 0; t + 1 < T; ++t) {
     rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, a_hi, a_lo, (int)N, H, W, C, st);
     if (rc) return rc;
-    rc = ecsy_umma_dense(a_hi, a_lo, M, C, pw_packed, splits, spread, C, nullptr, nullptr, nullptr, 0, st);
+    // fast mode (single bf16 weight plane): spread output and ECS trace are stored as fp16
+    const int half_state = splits == 1 ? 1 : 0;  // the recompute pass of the backward uses the same arithmetic
+    rc = ecsy_umma_dense(a_hi, a_lo, M, C, pw_packed, splits, spread, C, nullptr, nullptr, nullptr, 0, st, half_state);
     if (rc) return rc;
     EcsStep s{};
     s.spread = spread; s.pw_b = pw_b;
@@ -73,6 +75,7 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
     s.bits_t = spikes + t * words;
     s.bits_next = spikes + (t + 1) * words;
     s.first = (t == 0) ? 1 : 0;
+    s.half_state = half_state;
     s.thresh = thresh; s.decay = decay; s.alpha = alpha; s.beta = beta; s.kappa = kappa;
     rc = ecsy_launch_ecs_step(s, M, C, st);
     if (rc) return rc;

@@ -28,6 +28,7 @@
 #include <mutex>
 #include <tuple>
 
+#include <cuda_fp16.h>
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
 #include "umma_gemm.h"
@@ -59,6 +60,7 @@ struct EpiConv {
   const float* residual;  // [res_rows][ldc] or null
   int64_t res_rows;       // rows in residual (T-broadcast sources repeat)
   int ldc;                // Cout
+  int out_half;           // out points to __half (fp16 storage of the ECS spread in fast mode)
 };
 
 struct SpikeGeom {
@@ -355,7 +357,15 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
                 const float4 rr = *reinterpret_cast<const float4*>(res + 4 * q);
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
               }
-              *reinterpret_cast<float4*>(dst + 4 * q) = o;
+              if (e.out_half) {
+                __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(e.out) + pix * e.ldc + n0 + 4 * q) = pk;
+              } else {
+                *reinterpret_cast<float4*>(dst + 4 * q) = o;
+              }
             }
           }
         }
@@ -787,7 +797,7 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   CUtensorMap tb, dummy{};
   int rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)splits * Cout, (uint64_t)K, (uint32_t)BN, &tb);
   if (rc) return rc;
-  EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout};
+  EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout, 0};
   const int patch_bytes = sg.PP * Cw * 4;
   if (splits == 1) return launch_bn<kASpikes, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
   return launch_bn<kASpikes, 1, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
@@ -796,7 +806,7 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
 // Dense GEMM on a bf16 A matrix (hi [+ lo]) : out[M][Cout] = A * W^T (*scale + shift) (+ residual)
 int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
                     int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
-                    cudaStream_t st) {
+                    cudaStream_t st, int out_half) {
   ECSY_CHECK_ARG(K % 64 == 0 && M > 0, "dense gemm: K=%d must be a multiple of 64", K);
   const int BN = ecsy_pick_bn(Cout, splits);
   ECSY_CHECK_ARG(BN != 0, "dense gemm: Cout=%d must be a multiple of 64", Cout);
@@ -816,7 +826,7 @@ int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const 
   g.kb_total = K / 64;
   g.M = M;
   SpikeGeom sg{};
-  EpiConv e{out, scale, shift, residual, residual ? res_rows : M, Cout};
+  EpiConv e{out, scale, shift, residual, residual ? res_rows : M, Cout, out_half};
   if (splits == 1) return launch_bn<kATma, 1, 1, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
   return launch_bn<kATma, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
 }
@@ -855,7 +865,7 @@ int ecsy_umma_conv_bf16(const void* a_hi, const void* a_lo, const void* w_packed
   }
   rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)splits * Cout, (uint64_t)k * k * Cin, (uint32_t)BN, &tb);
   if (rc) return rc;
-  EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout};
+  EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout, 0};
   if (splits == 1) return launch_bn<kATma4, 1, 1, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
   return launch_bn<kATma4, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
 }

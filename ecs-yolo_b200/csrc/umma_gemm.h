@@ -11,24 +11,25 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
                          int Cout, int k, int stride, int pad, cudaStream_t st);
 int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
                     int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
-                    cudaStream_t st);
+                    cudaStream_t st, int out_half = 0);
 
 // elementwise.cu launchers used by lif.cu
 int ecsy_launch_lif_first(const float* x, const float* scale, const float* shift, float* mem, uint32_t* bits,
                           int64_t pixels, int C, float thresh, cudaStream_t st);
 struct EcsStep {
-  const float* spread;     // [M][C] pw(dw(s_t)) without bias (GEMM output)
+  const void* spread;      // [M][C] pw(dw(s_t)) without bias (GEMM output; fp32, or fp16 when `half_state`)
   const float* pw_b;       // [C]
   const float* x_next;     // [M][C] input current of step t+1
   const float* in_scale;   // optional folded tdBN on x
   const float* in_shift;
   const float* mem_in;     // membrane of step t
   float* mem_out;          // membrane of step t+1 (may alias mem_in; NULL = last step, not stored)
-  float* ecs;              // e_{t-1} in (unless first), e_t out (if store_ecs)
+  void* ecs;               // e_{t-1} in (unless first), e_t out (if store_ecs); fp32 or fp16 (`half_state`)
   float* ecs_save;         // optional copy of e_t kept for the backward pass
   const uint32_t* bits_t;  // spikes of step t
   uint32_t* bits_next;     // spikes of step t+1
   int first, store_ecs;
+  int half_state;          // fast mode: spread and the ECS trace are stored as fp16 (8 B/elem-step less traffic)
   float thresh, decay, alpha, beta, kappa;
 };
 int ecsy_launch_ecs_step(const EcsStep& s, int64_t pixels, int C, cudaStream_t st);
