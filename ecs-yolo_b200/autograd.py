@@ -32,6 +32,8 @@ def _grad_tuple(mod, grads: Dict[int, torch.Tensor]):
         g = grads.get(id(p))
         if g is not None and g.shape != p.shape:
             g = g.reshape(p.shape)
+        if g is not None and g.is_contiguous() and g.stride() != p.stride() and p.is_contiguous():
+            g = g.as_strided(p.shape, p.stride())   # size-1 dims: give DDP's bucket views the canonical strides
         out.append(g)
     return tuple(out)
 
