@@ -5,6 +5,7 @@
 //                   k_ecs_step             e_t = alpha*(S + b) + kappa*e_{t-1};  f_t = beta*tanh(e_t);
 //                                          mem_{t+1} = mem_t*decay*(1-s_t) + x_{t+1} + f_t; s_{t+1}   (streaming)
 // Spikes leave as bit-packed words; membrane / ECS state live in the caller-provided workspace.
+#include <stdlib.h>
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
 #include "umma_gemm.h"
@@ -51,12 +52,20 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
   int rc = ecsy_launch_lif_first(x, in_scale, in_shift, mem0, spikes, M, C, thresh, st);
   if (rc) return rc;
   for (int t = 0; t + 1 < T; ++t) {
-    rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, a_hi, a_lo, (int)N, H, W, C, st);
-    if (rc) return rc;
     // fast mode (single bf16 weight plane): spread output and ECS trace are stored as fp16
     const int half_state = splits == 1 ? 1 : 0;  // the recompute pass of the backward uses the same arithmetic
-    rc = ecsy_umma_dense(a_hi, a_lo, M, C, pw_packed, splits, spread, C, nullptr, nullptr, nullptr, 0, st, half_state);
-    if (rc) return rc;
+    static const bool fused_dw = getenv("ECSY_FUSED_DW") != nullptr && getenv("ECSY_FUSED_DW")[0] == '1';
+    if (fused_dw) {
+      // experimental: depth-wise spread computed by the GEMM's producer warps (no A round trip through HBM);
+      // measured slower than the two-kernel path at 1 CTA/SM (producer address math + 8 warps of ALU work)
+      rc = ecsy_umma_dw_gemm(spikes + t * words, dw_w, dw_b, pw_packed, splits, spread, half_state, (int)N, H, W, C, st);
+      if (rc) return rc;
+    } else {
+      rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, a_hi, a_lo, (int)N, H, W, C, st);
+      if (rc) return rc;
+      rc = ecsy_umma_dense(a_hi, a_lo, M, C, pw_packed, splits, spread, C, nullptr, nullptr, nullptr, 0, st, half_state);
+      if (rc) return rc;
+    }
     EcsStep s{};
     s.spread = spread; s.pw_b = pw_b;
     s.x_next = x + (t + 1) * x_tstride;

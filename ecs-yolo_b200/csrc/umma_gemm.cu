@@ -15,6 +15,10 @@
 //                       (hi [+ lo] planes): every (tap, 64-channel slab) K block is one 4-D TMA box
 //                       {64 ch, tw, th, tn} shifted by the tap, out-of-bounds = zero padding.  No im2col
 //                       buffer.  (Snn_Conv2d on real inputs, class Conv; conv input-gradients.)
+//   A_MODE = kADw     : A rows are pixels of ONE timestep and A[p][c] = b[c] + sum_tap s(p+tap, c) * w[tap][c], the
+//                       depth-wise half of the ECS spread (models/common.py:289-294), computed by the producer
+//                       warps from the spike bits (8 channels per thread, weights in registers) straight into the
+//                       swizzled operand tile -- the dw output never goes to HBM.  B = point-wise weights.
 //   B                 : packed weights [B_SPLIT*Cout][K] bf16 (hi plane, optional lo residual plane),
 //                       loaded by TMA.  With B_SPLIT=2 (and A_SPLIT=2 for real-valued A) the products
 //                       A_hi*B_hi + A_lo*B_hi + A_hi*B_lo reproduce fp32 weights to ~2^-17.
@@ -77,7 +81,9 @@ struct SpikeGeom {
 
 struct GemmArgs {
   int m_tiles, n_tiles, kb_total, stages;
-  int64_t M;       // valid rows (kATma) / unused (kASpikes)
+  int64_t M;       // valid rows (kATma, kADw) / unused (kASpikes)
+  const float* dw_w;   // kADw: depth-wise weights [9][C]
+  const float* dw_b;   // kADw: depth-wise bias [C]
   int wpg;             // expander warps per stage group (kExpWarps / stages)
 };
 
@@ -86,7 +92,7 @@ struct EpiSel;
 template <>
 struct EpiSel<0> { using type = EpiConv; };
 
-constexpr int kATma = 0, kASpikes = 1, kATma4 = 2;
+constexpr int kATma = 0, kASpikes = 1, kATma4 = 2, kADw = 3;
 constexpr int kEpiConv = 0;
 
 __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
@@ -95,7 +101,7 @@ __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
 }
 
 template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
-__global__ void __launch_bounds__(A_MODE == kASpikes ? kSpikeThreads : 192, 1)
+__global__ void __launch_bounds__((A_MODE == kASpikes || A_MODE == kADw) ? kSpikeThreads : 192, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
             const __grid_constant__ CUtensorMap tm_b, const GemmArgs g, const SpikeGeom sg,
             const typename EpiSel<EPI>::type ep) {
@@ -118,7 +124,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       if (A_SPLIT == 2) tma_prefetch_desc(&tm_a1);
     }
     for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&ctl->full_a[s], g.wpg);
+      mbar_init(&ctl->full_a[s], A_MODE == kADw ? kExpWarps : g.wpg);
       mbar_init(&ctl->full_b[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
@@ -152,7 +158,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
         mbar_wait(&ctl->empty[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* st = smem + (size_t)stage * kStageBytes;
-          constexpr uint32_t tx = (A_MODE != kASpikes ? A_SPLIT * kATileBytes : 0) + B_SPLIT * kBTileBytes;
+          constexpr uint32_t tx = ((A_MODE == kATma || A_MODE == kATma4) ? A_SPLIT * kATileBytes : 0) + B_SPLIT * kBTileBytes;
           mbar_arrive_expect_tx(&ctl->full_b[stage], tx);
           if (A_MODE == kATma) {
             tma_load_2d(st, &tm_a0, &ctl->full_b[stage], kb * 64, m_tile * 128);
@@ -189,7 +195,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       const uint32_t d_tmem = tmem_base + buf * BN;
       for (int kb = 0; kb < g.kb_total; ++kb) {
         mbar_wait(&ctl->full_b[stage], phase);
-        if (A_MODE == kASpikes) mbar_wait(&ctl->full_a[stage], phase);
+        if (A_MODE == kASpikes || A_MODE == kADw) mbar_wait(&ctl->full_a[stage], phase);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
@@ -213,6 +219,115 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
           if (kb == g.kb_total - 1) umma_commit(&ctl->tmem_full[buf]);
         }
         __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 6 && A_MODE == kADw) {
+    // =============================== depth-wise spread producers ===============================
+    if constexpr (A_MODE == kADw) {
+      const int et = threadIdx.x - 192;   // 0 .. 255
+      const int cg = et & 7;              // 8-channel group inside the 64-channel slab
+      const int rl = et >> 3;             // row lane: this thread owns rows rl, rl+32, rl+64, rl+96
+      const int H = sg.H, W = sg.W;
+      const int64_t HW = (int64_t)H * W;
+      const int c8 = sg.Cw * 4;           // bytes of spike bits per pixel
+      const int C = sg.Cw * 32;
+      const uint8_t* bytes = reinterpret_cast<const uint8_t*>(sg.bits);
+      float wreg[72], breg[8];
+      int cur_slab = -1;
+      const int nkb = g.kb_total;         // = C / 64
+      const uint32_t my_tiles = blockIdx.x < (uint32_t)total_tiles
+                                    ? (uint32_t)(total_tiles - 1 - (int)blockIdx.x) / gridDim.x + 1 : 0u;
+      const uint32_t n_items = my_tiles * (uint32_t)nkb;
+
+      // packed spike bytes of the 4 rows for the 9 taps of one (tile, slab): pk[tap] = row0 | row1<<8 | ...
+      auto load_bytes = [&](uint32_t item, uint32_t (&pk)[9]) {
+        const uint32_t ti = item / (uint32_t)nkb;
+        const int slab = (int)(item - ti * nkb);
+        const int tile = (int)blockIdx.x + (int)ti * (int)gridDim.x;
+        const int m_tile = tile / g.n_tiles;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) pk[t] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t m = (int64_t)m_tile * 128 + rl + 32 * i;
+          if (m < g.M) {
+            const int64_t n = m / HW;
+            const int rem = (int)(m - n * HW);
+            const int h = rem / W, w = rem - h * W;
+            const uint8_t* base = bytes + m * c8 + slab * 8 + cg;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int hh = h + ky - 1;
+              if (hh < 0 || hh >= H) continue;
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int ww = w + kx - 1;
+                if (ww < 0 || ww >= W) continue;
+                pk[ky * 3 + kx] |= (uint32_t)__ldg(base + ((int64_t)(ky - 1) * W + (kx - 1)) * c8) << (8 * i);
+              }
+            }
+          }
+        }
+      };
+
+      uint32_t stage = 0, phase = 0;
+      uint32_t cur[9];
+      if (n_items > 0) load_bytes(0, cur);
+      for (uint32_t item = 0; item < n_items; ++item) {
+        uint32_t nxt[9];
+        if (item + 1 < n_items) load_bytes(item + 1, nxt);
+        const int slab = (int)(item % (uint32_t)nkb);
+        if (slab != cur_slab) {
+          cur_slab = slab;
+          const int c0 = slab * 64 + cg * 8;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + t * C + c0));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.dw_w + t * C + c0 + 4));
+            wreg[t * 8 + 0] = w0.x; wreg[t * 8 + 1] = w0.y; wreg[t * 8 + 2] = w0.z; wreg[t * 8 + 3] = w0.w;
+            wreg[t * 8 + 4] = w1.x; wreg[t * 8 + 5] = w1.y; wreg[t * 8 + 6] = w1.z; wreg[t * 8 + 7] = w1.w;
+          }
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.dw_b + c0));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.dw_b + c0 + 4));
+          breg[0] = b0.x; breg[1] = b0.y; breg[2] = b0.z; breg[3] = b0.w;
+          breg[4] = b1.x; breg[5] = b1.y; breg[6] = b1.z; breg[7] = b1.w;
+        }
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        uint8_t* tile_hi = smem + (size_t)stage * kStageBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float acc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = breg[k];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t m = (cur[t] >> (8 * i)) & 0xFFu;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (m & (1u << k)) acc[k] += wreg[t * 8 + k];
+          }
+          const int r = rl + 32 * i;
+          const uint32_t off = (uint32_t)r * 128u + (((uint32_t)cg ^ ((uint32_t)r & 7u)) << 4);
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * q]), h1 = __float2bfloat16_rn(acc[2 * q + 1]);
+            hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            if (A_SPLIT == 2) {
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * q] - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * q + 1] - __bfloat162float(h1));
+              lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+          }
+          *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (A_SPLIT == 2) *reinterpret_cast<uint4*>(tile_hi + kATileBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->full_a[stage]);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) cur[t] = nxt[t];
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -715,7 +830,7 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, A_MODE == kASpikes ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
+  kern<<<grid, (A_MODE == kASpikes || A_MODE == kADw) ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }
@@ -917,4 +1032,26 @@ int ecsy_umma_spike_wgrad(const void* gy_hi, const void* gy_lo, const uint32_t* 
   }
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
+}
+
+// ECS spread of one timestep, fused: out[M][C] = dw3x3(spikes) * Wpw^T  (dw computed by the producer warps).
+int ecsy_umma_dw_gemm(const uint32_t* bits, const float* dw_w, const float* dw_b, const void* pw_packed, int splits,
+                      float* out, int out_half, int N, int H, int W, int C, cudaStream_t st) {
+  ECSY_CHECK_ARG(C % 64 == 0, "dw_gemm: C=%d must be a multiple of 64", C);
+  const int BN = ecsy_pick_bn(C, splits);
+  const int64_t M = (int64_t)N * H * W;
+  CUtensorMap tb, dummy{};
+  int rc = ecsy_tensor_map_bf16(pw_packed, (uint64_t)splits * C, (uint64_t)C, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  GemmArgs g{};
+  g.m_tiles = (int)((M + 127) / 128);
+  g.n_tiles = C / BN;
+  g.kb_total = C / 64;
+  g.M = M;
+  g.dw_w = dw_w; g.dw_b = dw_b;
+  SpikeGeom sg{};
+  sg.bits = bits; sg.imgs = N; sg.H = H; sg.W = W; sg.Cw = C / 32;
+  EpiConv e{out, nullptr, nullptr, nullptr, M, C, out_half};
+  if (splits == 1) return launch_bn<kADw, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, 0, st);
+  return launch_bn<kADw, 2, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, 0, st);
 }

@@ -44,3 +44,5 @@ int ecsy_umma_conv_bf16(const void* a_hi, const void* a_lo, const void* w_packed
 int ecsy_launch_f32_to_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st);
 int ecsy_umma_spike_wgrad(const void* gy_hi, const void* gy_lo, const uint32_t* bits, float* dw, int imgs, int H, int W,
                           int Cin, int Cout, int k, int stride, int pad, cudaStream_t st);
+int ecsy_umma_dw_gemm(const uint32_t* bits, const float* dw_w, const float* dw_b, const void* pw_packed, int splits,
+                      float* out, int out_half, int N, int H, int W, int C, cudaStream_t st);
