@@ -43,6 +43,7 @@ namespace {
 
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kEpiWarpFloats = 32 * 36 + 128;  // per epilogue warp: 32 x 36 float staging tile + 32 x 2 int64 row offsets
 constexpr int kExpWarps = 8;               // spike expander warps, grouped per pipeline stage
 constexpr int kSpikeThreads = 192 + kExpWarps * 32;
 
@@ -81,6 +82,7 @@ struct SpikeGeom {
 
 struct GemmArgs {
   int m_tiles, n_tiles, kb_total, stages;
+  uint32_t epi_off;  // byte offset of the epilogue staging buffers (4 warps x kEpiWarpFloats floats)
   int64_t M;       // valid rows (kATma, kADw) / unused (kASpikes)
   const float* dw_w;   // kADw: depth-wise weights [9][C]
   const float* dw_b;   // kADw: depth-wise bias [C]
@@ -447,43 +449,64 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       mbar_wait(&ctl->tmem_full[buf], bphase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * BN;
+      // Coalesced epilogue: TMEM gives each lane one ROW (32 columns); the affine is applied there, the tile
+      // slice is transposed through a padded per-warp staging buffer (pitch 36 floats: conflict-free 128-bit
+      // accesses both ways), and residual read / store are issued with 8 lanes per row (full 128-byte lines
+      // for fp32, 64-byte for fp16) instead of one lane per row (32 partially written sectors per request).
+      float* stg = reinterpret_cast<float*>(smem + g.epi_off) + warp * kEpiWarpFloats;
+      long long* rinfo = reinterpret_cast<long long*>(stg + 32 * 36);   // [32][2]: out offset (-1 = invalid), residual offset
+      const EpiConv& e = ep;
+      rinfo[lane * 2 + 0] = valid ? (long long)pix * e.ldc : -1LL;
+      rinfo[lane * 2 + 1] = (valid && e.residual != nullptr) ? (long long)(pix % e.res_rows) * e.ldc : 0LL;
+      __syncwarp();
+      const int sub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
         tmem_ld_wait();
         const int n0 = n_tile * BN + c0;
-        if constexpr (EPI == kEpiConv) {
-          const EpiConv& e = ep;
-          if (valid) {
-            float* dst = e.out + pix * e.ldc + n0;
-            const float* res = e.residual ? e.residual + (pix % e.res_rows) * e.ldc + n0 : nullptr;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-              if (e.scale != nullptr) {
-                const float4 s = *reinterpret_cast<const float4*>(e.scale + n0 + 4 * q);
-                const float4 b = *reinterpret_cast<const float4*>(e.shift + n0 + 4 * q);
-                o.x = fmaf(o.x, s.x, b.x); o.y = fmaf(o.y, s.y, b.y);
-                o.z = fmaf(o.z, s.z, b.z); o.w = fmaf(o.w, s.w, b.w);
-              }
-              if (res != nullptr) {
-                const float4 rr = *reinterpret_cast<const float4*>(res + 4 * q);
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-              }
-              if (e.out_half) {
-                __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h01);
-                pk.y = *reinterpret_cast<uint32_t*>(&h23);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(e.out) + pix * e.ldc + n0 + 4 * q) = pk;
-              } else {
-                *reinterpret_cast<float4*>(dst + 4 * q) = o;
-              }
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          if (e.scale != nullptr) {
+            const float4 s = *reinterpret_cast<const float4*>(e.scale + n0 + 4 * q);
+            const float4 b = *reinterpret_cast<const float4*>(e.shift + n0 + 4 * q);
+            o.x = fmaf(o.x, s.x, b.x); o.y = fmaf(o.y, s.y, b.y);
+            o.z = fmaf(o.z, s.z, b.z); o.w = fmaf(o.w, s.w, b.w);
+          }
+          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) = o;
+        }
+        __syncwarp();
+        // all residual loads of the slice first (independent, in flight together), then add + store
+        float4 r4[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + sub;
+          r4[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.residual != nullptr && rinfo[rr * 2] >= 0)
+            r4[itr] = *reinterpret_cast<const float4*>(e.residual + rinfo[rr * 2 + 1] + n0 + c4);
+        }
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + sub;                       // row of this warp's 32-row slice
+          const long long ooff = rinfo[rr * 2];
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
+          if (ooff >= 0) {
+            o.x += r4[itr].x; o.y += r4[itr].y; o.z += r4[itr].z; o.w += r4[itr].w;
+            if (e.out_half) {
+              __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h01);
+              pk.y = *reinterpret_cast<uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(e.out) + ooff + n0 + c4) = pk;
+            } else {
+              *reinterpret_cast<float4*>(e.out + ooff + n0 + c4) = o;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before_sync();
       mbar_arrive(&ctl->tmem_empty[buf]);
@@ -815,7 +838,8 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
     dyn_limit = lim;
   }
   (void)patch_bytes;
-  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 128;
+  constexpr int kEpiStage = 4 * kEpiWarpFloats * 4;
+  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 128 + kEpiStage;
   int stages = (dyn_limit - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (A_MODE == kASpikes) stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : (stages >= 2 ? 2 : 0));
@@ -826,7 +850,8 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   g.stages = stages;
   g.wpg = A_MODE == kASpikes ? kExpWarps / stages : 1;
   const uint32_t ctl_off = (uint32_t)stages * stage_bytes;
-  const int smem = 1024 + (int)ctl_off + (int)sizeof(SharedCtl) + 64;
+  g.epi_off = (ctl_off + (uint32_t)sizeof(SharedCtl) + 63u) & ~63u;
+  const int smem = 1024 + (int)g.epi_off + kEpiStage;
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
