@@ -38,6 +38,18 @@ def _grad_tuple(mod, grads: Dict[int, torch.Tensor]):
     return tuple(out)
 
 
+def _grad_tuple_params(params, grads: Dict[int, torch.Tensor]):
+    out = []
+    for p in params:
+        g = grads.get(id(p))
+        if g is not None and g.shape != p.shape:
+            g = g.reshape(p.shape)
+        if g is not None and g.is_contiguous() and g.stride() != p.stride() and p.is_contiguous():
+            g = g.as_strided(p.shape, p.stride())
+        out.append(g)
+    return tuple(out)
+
+
 def _acc(grads, p, g):
     grads[id(p)] = g if id(p) not in grads else grads[id(p)] + g
 
@@ -248,6 +260,62 @@ class StemFn(torch.autograd.Function):
         k, s, p = mod.conv._geom()
         _acc(grads, mod.conv.weight, F_.real_conv_wgrad(g_y, ctx.a, k, s, p))
         return (None, None) + _grad_tuple(mod, grads)
+
+
+class ConvSiluFn(torch.autograd.Function):
+    """class Conv in training mode: real-input conv -> tdBN -> SiLU neuron (models/common.py:362-375)."""
+
+    @staticmethod
+    def forward(ctx, mod, x_ref, *params):
+        a = Act.from_ref(x_ref).full()
+        y = mod.conv.conv_real(a)
+        scale, shift, mean, rstd = bn_train_fwd(mod.bn, y)
+        ctx.mod, ctx.a, ctx.y, ctx.mean, ctx.rstd, ctx.aff = mod, a, y, mean, rstd, (scale, shift)
+        return mod.act.analog(y, (scale, shift)).to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        from .common import _cached
+        mod = ctx.mod
+        g = _to_nhwc(g_ref)
+        grads: Dict[int, torch.Tensor] = {}
+        lif = mod.act
+        g_yn, gdw, gdb, gpw, gpb = F_.lif_silu_bwd(g, ctx.y, lif._weights(), lif.spread[1].weight, ctx.aff, lif.ecs_tau,
+                                                   lif.alpha, lif.beta)
+        _acc(grads, lif.spread[0].weight, gdw)
+        _acc(grads, lif.spread[0].bias, gdb)
+        _acc(grads, lif.spread[1].weight, gpw)
+        _acc(grads, lif.spread[1].bias, gpb)
+        g_y = bn_train_bwd(mod.bn, ctx.y, ctx.mean, ctx.rstd, g_yn, grads)
+        k, s, p = mod.conv._geom()
+        _acc(grads, mod.conv.weight, F_.real_conv_wgrad(g_y, ctx.a, k, s, p))
+        splits = F_.get_splits()
+        wT = _cached(mod.conv, "dgradw", (mod.conv.weight,), lambda: F_.pack_dgrad_weight(mod.conv.weight, splits))
+        g_x = F_.conv_dgrad(g_y, wT, splits, ctx.a.H, ctx.a.W, mod.conv.in_channels, k, s, p)
+        return (None, g_x.permute(0, 1, 4, 2, 3)) + _grad_tuple(mod, grads)
+
+
+class ConvBChainFn(torch.autograd.Function):
+    """Two chained Conv_B modules (LIF -> conv -> tdBN, twice) in training mode: the trunk of a DDetect branch
+    (models/yolo_snn.py:100-107).  Returns the normalised output of the second one."""
+
+    @staticmethod
+    def forward(ctx, cb0, cb1, x_ref, *params):
+        a = Act.from_ref(x_ref).full()
+        s1 = chain_fwd(cb0.act, cb0.conv, cb0.bn, a, None)
+        s2 = chain_fwd(cb1.act, cb1.conv, cb1.bn, s1.y, (s1.scale, s1.shift))
+        ctx.cb0, ctx.cb1, ctx.s1, ctx.s2 = cb0, cb1, s1, s2
+        return F_.affine_add(s2.y, s2.scale, s2.shift).to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        g = _to_nhwc(g_ref)
+        grads: Dict[int, torch.Tensor] = {}
+        cb0, cb1 = ctx.cb0, ctx.cb1
+        g_y1n = chain_bwd(cb1.act, cb1.conv, cb1.bn, ctx.s2, g, grads)
+        g_x = chain_bwd(cb0.act, cb0.conv, cb0.bn, ctx.s1, g_y1n, grads)
+        params = list(cb0.parameters()) + list(cb1.parameters())
+        return (None, None, g_x.permute(0, 1, 4, 2, 3)) + _grad_tuple_params(params, grads)
 
 
 class SampleFn(torch.autograd.Function):

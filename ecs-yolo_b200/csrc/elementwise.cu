@@ -281,7 +281,7 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v));
 
 __global__ void k_silu_first(const float* __restrict__ x, const float* __restrict__ scale,
                              const float* __restrict__ shift, float* __restrict__ out, float* __restrict__ mem,
-                             int64_t n4, int C) {
+                             float* __restrict__ mem_save, int64_t n4, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
@@ -295,6 +295,7 @@ __global__ void k_silu_first(const float* __restrict__ x, const float* __restric
       v.w = ecsy::add_rn(ecsy::mul_rn(v.w, s.w), b.w);
     }
     if (mem != nullptr) reinterpret_cast<float4*>(mem)[i] = v;
+    if (mem_save != nullptr) reinterpret_cast<float4*>(mem_save)[i] = v;
     reinterpret_cast<float4*>(out)[i] = make_float4(silu_f(v.x), silu_f(v.y), silu_f(v.z), silu_f(v.w));
   }
 }
@@ -310,6 +311,8 @@ struct SiluStep {
   float* ecs;
   const float* out_prev;  // silu(mem_t)
   float* out_next;        // silu(mem_{t+1})
+  float* mem_save;        // optional: raw membrane of step t+1 (backward recompute)
+  float* ecs_save;        // optional: e_t (backward recompute)
   int first, store_ecs;
   float decay, alpha, beta, kappa;
 };
@@ -348,6 +351,8 @@ __global__ void k_silu_step(const SiluStep p, int64_t n4, int C) {
     }
     if (p.mem_out != nullptr) reinterpret_cast<float4*>(p.mem_out)[i] = make_float4(mn[0], mn[1], mn[2], mn[3]);
     if (p.store_ecs) reinterpret_cast<float4*>(p.ecs)[i] = make_float4(en[0], en[1], en[2], en[3]);
+    if (p.mem_save != nullptr) reinterpret_cast<float4*>(p.mem_save)[i] = make_float4(mn[0], mn[1], mn[2], mn[3]);
+    if (p.ecs_save != nullptr) reinterpret_cast<float4*>(p.ecs_save)[i] = make_float4(en[0], en[1], en[2], en[3]);
     reinterpret_cast<float4*>(p.out_next)[i] = make_float4(on[0], on[1], on[2], on[3]);
   }
 }
@@ -768,6 +773,14 @@ int ecsy_launch_ecs_step(const EcsStep& p, int64_t pixels, int C, cudaStream_t s
   return ECSY_OK;
 }
 
+int ecsy_launch_dw_real(const float* s, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                        int N, int H, int W, int C, cudaStream_t st) {
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  k_dw_real<<<grid_for(total, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(s, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
 int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
                           __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st) {
   const int c8 = C / 8;
@@ -886,9 +899,9 @@ extern "C" size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, 
 
 extern "C" int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                                  const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b,
-                                 int splits, float* out, int inplace, int T, int64_t N, int H, int W, int C,
-                                 float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes,
-                                 void* stream) {
+                                 int splits, float* out, float* mem_save, float* ecs_save, int inplace, int T, int64_t N,
+                                 int H, int W, int C, float decay, float alpha, float beta, float kappa, void* ws,
+                                 size_t ws_bytes, void* stream) {
   cudaStream_t st = STREAM(stream);
   ECSY_CHECK_ARG(x && out && T >= 1 && N > 0 && H > 0 && W > 0, "lif_silu_fwd: bad arguments");
   ECSY_CHECK_ARG(C % 64 == 0, "lif_silu_fwd: C=%d must be a multiple of 64", C);
@@ -910,7 +923,7 @@ extern "C" int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float*
   __nv_bfloat16* a_lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
   const int64_t n4 = M * C / 4;
   const int grid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
-  k_silu_first<<<grid, kThreads, 0, st>>>(x, in_scale, in_shift, out, (T > 1 && !inplace) ? mem : nullptr, n4, C);
+  k_silu_first<<<grid, kThreads, 0, st>>>(x, in_scale, in_shift, out, (T > 1 && !inplace) ? mem : nullptr, mem_save, n4, C);
   ECSY_LAUNCH_CHECK();
   for (int t = 0; t + 1 < T; ++t) {
     const float* out_t = out + (size_t)t * mc;
@@ -929,6 +942,8 @@ extern "C" int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float*
     s.ecs = ecs; s.store_ecs = more ? 1 : 0;
     s.out_prev = out_t;
     s.out_next = out + (size_t)(t + 1) * mc;
+    s.mem_save = mem_save ? mem_save + (size_t)(t + 1) * mc : nullptr;
+    s.ecs_save = ecs_save ? ecs_save + (size_t)t * mc : nullptr;
     s.first = t == 0 ? 1 : 0;
     s.decay = decay; s.alpha = alpha; s.beta = beta; s.kappa = kappa;
     k_silu_step<<<grid, kThreads, 0, st>>>(s, n4, C);

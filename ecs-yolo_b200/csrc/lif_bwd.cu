@@ -183,6 +183,107 @@ __global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __re
   }
 }
 
+// ---- SiLU ("analog spike") neuron backward: mem_update(act=True) with the in-place SiLU of the reference
+// models (mem_old = silu(mem)):  m_t = d*o_{t-1}*(1 - stopgrad(o_{t-1})) + x_t + f_{t-1},  o_t = silu(m_t).
+//   go_t = gout_t + alpha*dw^T(G1) + gm*decay*(1 - o_t);  gm_t = go_t * silu'(m_t)
+__global__ void k_silu_bwd_reduce(const float* __restrict__ ge, const float* __restrict__ g1,
+                                  const float* __restrict__ o, double* __restrict__ acc, int N, int H, int W, int C) {
+  const int c4 = C >> 2;
+  const int tq = threadIdx.x % c4;
+  const int ty = threadIdx.x / c4, nty = blockDim.x / c4;
+  const int64_t pixels = (int64_t)N * H * W;
+  float s[11][4];
+#pragma unroll
+  for (int a = 0; a < 11; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[a][k] = 0.f;
+  const int64_t per_block = (pixels + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per_block;
+  const int64_t p1 = p0 + per_block < pixels ? p0 + per_block : pixels;
+  for (int64_t p = p0 + ty; p < p1; p += nty) {
+    const float4 a = reinterpret_cast<const float4*>(ge + p * C)[tq];
+    const float4 b = reinterpret_cast<const float4*>(g1 + p * C)[tq];
+    s[0][0] += a.x; s[0][1] += a.y; s[0][2] += a.z; s[0][3] += a.w;
+    s[1][0] += b.x; s[1][1] += b.y; s[1][2] += b.z; s[1][3] += b.w;
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ww = w + kx - 1;
+        if (ww < 0 || ww >= W) continue;
+        const float4 ov = reinterpret_cast<const float4*>(o + (p + (int64_t)(ky - 1) * W + (kx - 1)) * C)[tq];
+        const int t = 2 + ky * 3 + kx;
+        s[t][0] += b.x * ov.x; s[t][1] += b.y * ov.y; s[t][2] += b.z * ov.z; s[t][3] += b.w * ov.w;
+      }
+    }
+  }
+  extern __shared__ float sred[];
+#pragma unroll
+  for (int a = 0; a < 11; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sred[(ty * 11 + a) * C + tq * 4 + k] = s[a][k];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 11 * C; idx += blockDim.x) {
+    double t = 0;
+    for (int y = 0; y < nty; ++y) t += sred[y * 11 * C + idx];
+    atomicAdd(acc + idx, t);
+  }
+}
+
+__device__ __forceinline__ float silu_grad(float m) {
+  const float sg = 1.0f / (1.0f + expf(-m));
+  return sg * (1.0f + m * (1.0f - sg));
+}
+
+__global__ void k_silu_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1,
+                                const float* __restrict__ dw_w, const float* __restrict__ mem_t,
+                                const float* __restrict__ o_t, float* __restrict__ gm, int has_next,
+                                float* __restrict__ gx, int N, int H, int W, int C, float decay, float alpha) {
+  const int c4 = C >> 2;
+  const int64_t total = (int64_t)N * H * W * c4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int q = static_cast<int>(i % c4);
+    const int64_t p = i / c4;
+    float4 go = reinterpret_cast<const float4*>(gout)[i];
+    if (g1 != nullptr) {
+      const int w = static_cast<int>(p % W);
+      const int h = static_cast<int>((p / W) % H);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h - (ky - 1);
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ww = w - (kx - 1);
+          if (ww < 0 || ww >= W) continue;
+          const float4 g = reinterpret_cast<const float4*>(g1 + (p - (int64_t)(ky - 1) * W - (kx - 1)) * C)[q];
+          const float4 wt = *reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * C + q * 4);
+          acc.x = fmaf(g.x, wt.x, acc.x); acc.y = fmaf(g.y, wt.y, acc.y);
+          acc.z = fmaf(g.z, wt.z, acc.z); acc.w = fmaf(g.w, wt.w, acc.w);
+        }
+      }
+      go.x = fmaf(alpha, acc.x, go.x); go.y = fmaf(alpha, acc.y, go.y);
+      go.z = fmaf(alpha, acc.z, go.z); go.w = fmaf(alpha, acc.w, go.w);
+    }
+    if (has_next) {
+      const float4 gn = reinterpret_cast<const float4*>(gm)[i];
+      const float4 ov = reinterpret_cast<const float4*>(o_t)[i];
+      go.x += gn.x * decay * (1.0f - ov.x); go.y += gn.y * decay * (1.0f - ov.y);
+      go.z += gn.z * decay * (1.0f - ov.z); go.w += gn.w * decay * (1.0f - ov.w);
+    }
+    const float4 m = reinterpret_cast<const float4*>(mem_t)[i];
+    const float4 o = make_float4(go.x * silu_grad(m.x), go.y * silu_grad(m.y), go.z * silu_grad(m.z), go.w * silu_grad(m.w));
+    reinterpret_cast<float4*>(gm)[i] = o;
+    reinterpret_cast<float4*>(gx)[i] = o;
+  }
+}
+
 // per-channel sums over rows: sum_g[c] = sum g, sum_gx[c] = sum g*x  (tdBN / folded-affine backward)
 __global__ void k_colsum2(const float* __restrict__ g, const float* __restrict__ x, int64_t rows, int64_t x_rows,
                           int C, double* __restrict__ acc /*[2][C]*/) {
@@ -319,5 +420,70 @@ extern "C" int ecsy_colsum2(const float* g, const float* x, int64_t rows, int64_
   ECSY_LAUNCH_CHECK();
   k_d2f<<<(C + 255) / 256, 256, 0, st>>>(acc + C, sum_gx, C);
   ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+// Depth-wise 3x3 of a real tensor -> bf16 planes (elementwise.cu)
+int ecsy_launch_dw_real(const float* s, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                        int N, int H, int W, int C, cudaStream_t st);
+
+extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const float* mem, const float* ecs,
+                                 const float* dw_w, const float* dw_b, const void* pwT_packed, int splits, float* gx,
+                                 float* g_dw_w, float* g_dw_b, float* g_pw_w, float* g_pw_b, int T, int64_t N, int H,
+                                 int W, int C, float decay, float alpha, float beta, float kappa, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ECSY_CHECK_ARG(gout && out && mem && gx && T >= 1 && N > 0 && H > 0 && W > 0, "lif_silu_bwd: bad arguments");
+  ECSY_CHECK_ARG(C % 64 == 0 && C <= 1024, "lif_silu_bwd: C=%d must be a multiple of 64, <= 1024", C);
+  ECSY_CHECK_ARG(T == 1 || (ecs && dw_w && dw_b && pwT_packed && g_dw_w && g_dw_b && g_pw_w && g_pw_b),
+                 "lif_silu_bwd: spread tensors missing");
+  const int64_t M = N * H * W;
+  const size_t mc = static_cast<size_t>(M) * C;
+  const size_t need = ecsy_lif_ecs_bwd_ws_bytes(T, N, H, W, C, splits);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("lif_silu_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  float* gm = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  float* ge = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  float* g1 = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  __nv_bfloat16* ge_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
+  __nv_bfloat16* ge_lo = nullptr;
+  if (splits == 2) { ge_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2); }
+  __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
+  __nv_bfloat16* d_lo = nullptr;
+  if (splits == 2) { d_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2); }
+  double* acc = reinterpret_cast<double*>(p);
+  const int64_t n4 = M * C / 4;
+  const int egrid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
+  const int c4 = C / 4;
+  const int rbd = (256 / c4) * c4;
+  for (int t = T - 1; t >= 0; --t) {
+    const bool spread = t <= T - 2;
+    const bool has_next = t < T - 1;
+    const float* o_t = out + (size_t)t * mc;
+    if (spread) {
+      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gm, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta,
+                                                kappa);
+      ECSY_LAUNCH_CHECK();
+      int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
+      if (rc) return rc;
+      rc = ecsy_launch_dw_real(o_t, dw_w, dw_b, d_hi, d_lo, (int)N, H, W, C, st);
+      if (rc) return rc;
+      rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
+      if (rc) return rc;
+      ECSY_CUDA(cudaMemsetAsync(acc, 0, 11 * (size_t)C * sizeof(double), st));
+      k_silu_bwd_reduce<<<grid_for(M, 64, ecsy_num_sms() * 4), rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(
+          ge, g1, o_t, acc, (int)N, H, W, C);
+      ECSY_LAUNCH_CHECK();
+      k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(acc, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      ECSY_LAUNCH_CHECK();
+    }
+    k_silu_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
+                                                o_t, gm, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, decay,
+                                                alpha);
+    ECSY_LAUNCH_CHECK();
+  }
   return ECSY_OK;
 }

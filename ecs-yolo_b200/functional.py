@@ -365,11 +365,14 @@ def colsum2(g: torch.Tensor, x: torch.Tensor, C: int):
 
 
 def lif_silu(x: Act, w: Optional[LifW], affine=None, ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25,
-             inplace: bool = True) -> Act:
-    """mem_update(act=True).forward (models/common.py:252-283): real-valued silu(mem_t) outputs."""
+             inplace: bool = True, save: bool = False):
+    """mem_update(act=True).forward (models/common.py:252-283): real-valued silu(mem_t) outputs; with `save`
+    also the raw membranes [T,...] and ECS traces [T-1,...] (backward recompute)."""
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
     out = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32)
+    mem = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32) if save else None
+    ecs = torch.empty(max(T - 1, 1), N, H, W, C, device=dev, dtype=torch.float32) if save else None
     L = _cabi.lib()
     splits = w.splits if w is not None else 1
     nws = L.ecsy_lif_silu_ws_bytes(T, N, H, W, C, splits) if T > 1 else 0
@@ -382,9 +385,33 @@ def lif_silu(x: Act, w: Optional[LifW], affine=None, ecs_tau: float = 5.0, alpha
         _cabi.check(L.ecsy_lif_silu_fwd(_p(x.data), x.tstride, _p(sc), _p(sh),
                                         _p(w.dw_w) if w else None, _p(w.dw_b) if w else None,
                                         _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits, _p(out),
-                                        1 if inplace else 0, T, N, H, W, C, float(decay), float(alpha), float(beta),
-                                        float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(), _st()), "lif_silu_fwd")
-    return Act(out, T)
+                                        _p(mem), _p(ecs), 1 if inplace else 0, T, N, H, W, C, float(decay),
+                                        float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(),
+                                        _st()), "lif_silu_fwd")
+    return (Act(out, T), mem, ecs) if save else Act(out, T)
+
+
+def lif_silu_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, affine=None, ecs_tau: float = 5.0,
+                 alpha: float = 0.75, beta: float = 0.25):
+    """BPTT of the in-place SiLU neuron (class Conv inside a model).  Same returns as lif_ecs_bwd."""
+    T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
+    dev = x.data.device
+    out, mem, ecs = lif_silu(x, w, affine, ecs_tau, alpha, beta, inplace=True, save=True)
+    gout = gout.contiguous()
+    gx = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32)
+    g_dw_w = torch.zeros(9, C, device=dev, dtype=torch.float32)
+    g_dw_b = torch.zeros(C, device=dev, dtype=torch.float32)
+    g_pw_w = torch.zeros(C, C, device=dev, dtype=torch.float32)
+    g_pw_b = torch.zeros(C, device=dev, dtype=torch.float32)
+    pwT = pack_conv_weight(pw_weight.detach().reshape(C, C).t().contiguous().reshape(C, C, 1, 1), w.splits)
+    L = _cabi.lib()
+    ws = torch.empty(L.ecsy_lif_ecs_bwd_ws_bytes(T, N, H, W, C, w.splits), device=dev, dtype=torch.uint8)
+    with _timed("lif_silu_bwd", 1 + 7 * (T - 1)):
+        _cabi.check(L.ecsy_lif_silu_bwd(_p(gout), _p(out.data), _p(mem), _p(ecs), _p(w.dw_w), _p(w.dw_b), _p(pwT),
+                                        w.splits, _p(gx), _p(g_dw_w), _p(g_dw_b), _p(g_pw_w), _p(g_pw_b), T, N, H, W, C,
+                                        float(decay), float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _p(ws),
+                                        ws.numel(), _st()), "lif_silu_bwd")
+    return gx, g_dw_w.t().reshape(C, 1, 3, 3).contiguous(), g_dw_b, g_pw_w.reshape(C, C, 1, 1), g_pw_b
 
 
 def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[Act] = None) -> Act:

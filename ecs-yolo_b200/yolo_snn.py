@@ -58,8 +58,28 @@ class DDetect(nn.Module):
         out = conv.conv_real(Act(feat.unsqueeze(0), 1))
         return out.data[0]                              # [N,H,W,Cout]
 
+    def _forward_train_autograd(self, x):
+        """Training with gradients: the two Conv_B trunks of each branch run through the manual backward chains
+        (autograd.ConvBChainFn); the mean over T, the last 1x1 conv (+bias) and the concat -- N*H*W-row tensors,
+        < 0.1 % of the FLOPs -- are differentiable torch ops (models/yolo_snn.py:115-116)."""
+        import torch.nn.functional as tF
+        from . import autograd as AG
+        out = []
+        for i in range(self.nl):
+            parts = []
+            for seq in (self.cv2[i], self.cv3[i]):
+                params = list(seq[0].parameters()) + list(seq[1].parameters())
+                y2n = AG.ConvBChainFn.apply(seq[0], seq[1], x[i], *params)
+                feat = y2n.sum(dim=0) / y2n.shape[0]
+                parts.append(tF.conv2d(feat, seq[2].weight, seq[2].bias, groups=seq[2].groups))
+            out.append(torch.cat(parts, 1))
+        return out
+
     def forward(self, x):
         x = list(x)
+        if self.training and torch.is_grad_enabled() and (any(t.requires_grad for t in x) or
+                                                          any(p.requires_grad for p in self.parameters())):
+            return self._forward_train_autograd(x)
         a_total = sum(xi.shape[3] * xi.shape[4] for xi in x)
         N = x[0].shape[1]
         y = None

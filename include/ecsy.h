@@ -60,7 +60,13 @@ int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, c
 size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
 int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                       const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b, int splits,
-                      float* out, int inplace, int T, int64_t N, int H, int W, int C, float decay, float alpha,
+                      float* out, float* mem_save, float* ecs_save, int inplace, int T, int64_t N, int H, int W, int C,
+                      float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
+/* backward of the in-place SiLU neuron (out / mem / ecs from a re-run of ecsy_lif_silu_fwd with mem_save, ecs_save);
+ * same argument meaning as ecsy_lif_ecs_bwd, workspace size from ecsy_lif_ecs_bwd_ws_bytes. */
+int ecsy_lif_silu_bwd(const float* gout, const float* out, const float* mem, const float* ecs, const float* dw_w,
+                      const float* dw_b, const void* pwT_packed, int splits, float* gx, float* g_dw_w, float* g_dw_b,
+                      float* g_pw_w, float* g_pw_b, int T, int64_t N, int H, int W, int C, float decay, float alpha,
                       float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Snn_Conv2d.forward on spikes (models/common.py:609-624), tcgen05 implicit GEMM.

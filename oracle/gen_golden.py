@@ -166,7 +166,12 @@ def main():
             m.spread[0].weight.copy_(inp["dw_w"]); m.spread[0].bias.copy_(inp["dw_b"])
             m.spread[1].weight.copy_(inp["pw_w"]); m.spread[1].bias.copy_(inp["pw_b"])
             out = m(inp["x"].clone())
-        save(name, dict(spec=spec, chk=S.checksum(*[inp[k] for k in sorted(inp)]), out=out))
+        x = inp["x"].clone().requires_grad_(True)
+        og = m(x * 1.0)          # in-place SiLU must not hit a leaf
+        og.backward(inp["gout"])
+        g = {"gx": x.grad.clone(), "g_dw_w": m.spread[0].weight.grad.clone(), "g_dw_b": m.spread[0].bias.grad.clone(),
+             "g_pw_w": m.spread[1].weight.grad.clone(), "g_pw_b": m.spread[1].bias.grad.clone()}
+        save(name, dict(spec=spec, chk=S.checksum(*[inp[k] for k in sorted(inp)]), out=out, **g))
     for name, spec in S.CONVSILU_CASES.items():
         C, Y, SN = ref_shim.load(spec["T"])
         inp = S.convsilu_inputs(spec, O)
@@ -176,12 +181,20 @@ def main():
         with torch.no_grad():
             m(torch.zeros_like(inp["x"]))
         m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+        sd_before = {k: v.clone() for k, v in m.state_dict().items()}
+        x = inp["x"].clone().requires_grad_(True)
+        og = m(x)
+        gout = S.randn(S.gen(spec["seed"] + 13), *og.shape)
+        og.backward(gout)
+        grads = {"model.0." + k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        gx = x.grad.clone()
+        m.load_state_dict(sd_before)
         with torch.no_grad():
             out_train = m(inp["x"].clone())
             m.eval()
             out_eval = m(inp["x"].clone())
         save(name, dict(spec=spec, chk=S.sd_checksum(inp["sd"]) + S.checksum(inp["x"]), out_train=out_train,
-                        out_eval=out_eval))
+                        out_eval=out_eval, gx=gx, grads=grads))
     for name, spec in S.DDETECT_CASES.items():
         C, Y, SN = ref_shim.load(spec["T"])
         inp = S.ddetect_inputs(spec, O)
@@ -191,13 +204,22 @@ def main():
         with torch.no_grad():
             m([torch.zeros_like(f) for f in inp["feats"]])
         m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+        sd_before = {k: v.clone() for k, v in m.state_dict().items()}
+        fs = [f.clone().requires_grad_(True) for f in inp["feats"]]
+        og = m(list(fs))
+        gouts = [S.randn(S.gen(spec["seed"] + 13 + i), *o.shape) for i, o in enumerate(og)]
+        sum((o * g).sum() for o, g in zip(og, gouts)).backward()
+        grads = {"model.0." + k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        gfeats = [f.grad.clone() for f in fs]
+        m.load_state_dict(sd_before)
         with torch.no_grad():
             out_train = m([f.clone() for f in inp["feats"]])
             bn_after = {"model.0." + k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
             m.eval()
             y, xs = m([f.clone() for f in inp["feats"]])
         save(name, dict(spec=spec, chk=S.sd_checksum(inp["sd"]) + S.checksum(*inp["feats"]),
-                        out_train=[o.clone() for o in out_train], bn_after=bn_after, y_eval=y, xs_eval=[o.clone() for o in xs]))
+                        out_train=[o.clone() for o in out_train], bn_after=bn_after, y_eval=y, xs_eval=[o.clone() for o in xs],
+                        gfeats=gfeats, grads=grads))
     for name, spec in S.MODEL_B_CASES.items():
         C, Y, SN = ref_shim.load(spec["T"])
         path = os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")

@@ -71,5 +71,94 @@ def test_model_training_step():
             assert not missing, missing[:5]
             assert all(torch.isfinite(p.grad).all() for p in m.parameters())
         opt.step()
-        losses.append(float(loss))
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
+
+
+# ---------------------------------------------------------------- Stack B backward
+def test_silu_neuron_backward():
+    E = ecsy()
+    F = E.functional
+    name = "silu_c64_t4_inplace"
+    spec, gold = S.SILU_CASES[name], load_golden(name)
+    inp = S.lif_inputs(spec)
+    w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+    x = F.Act.from_ref(inp["x"].cuda())
+    gout = inp["gout"].cuda().permute(0, 1, 3, 4, 2).contiguous()
+    gx, g_dw_w, g_dw_b, g_pw_w, g_pw_b = F.lif_silu_bwd(gout, x, w, inp["pw_w"].cuda())
+    assert rel_l2(gx.permute(0, 1, 4, 2, 3).cpu(), gold["gx"]) < 2e-4
+    for got, k in [(g_dw_w, "g_dw_w"), (g_dw_b, "g_dw_b"), (g_pw_w, "g_pw_w"), (g_pw_b, "g_pw_b")]:
+        e = rel_l2(got.cpu(), gold[k])
+        assert e < 2e-4, f"{k}: {e:.3e}"
+
+
+@pytest.mark.parametrize("name", list(S.CONVSILU_CASES))
+def test_conv_silu_backward(name):
+    E = ecsy()
+    spec, gold = S.CONVSILU_CASES[name], load_golden(name)
+    inp = S.convsilu_inputs(spec, O)
+    m = E.common.Conv(spec["cin"], spec["cout"], spec["k"], spec["s"])
+    m.act.actFun.inplace = True
+    m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+    m = m.cuda().train()
+    x = inp["x"].cuda().requires_grad_(True)
+    out = m(x)
+    assert rel_l2(out.detach().cpu(), gold["out_train"]) < 5e-5
+    out.backward(S.randn(S.gen(spec["seed"] + 13), *out.shape).cuda())
+    assert rel_l2(x.grad.cpu(), gold["gx"]) < 5e-4
+    named = dict(m.named_parameters())
+    for k, g in gold["grads"].items():
+        e = rel_l2(named[k[len("model.0."):]].grad.cpu(), g)
+        assert e < 1e-3, f"{k}: {e:.3e}"
+
+
+@pytest.mark.parametrize("name", list(S.DDETECT_CASES))
+def test_ddetect_backward(name):
+    E = ecsy()
+    spec, gold = S.DDETECT_CASES[name], load_golden(name)
+    inp = S.ddetect_inputs(spec, O)
+    m = E.yolo_snn.DDetect(spec["nc"], spec["ch"])
+    m.stride = inp["stride"]
+    m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+    m = m.cuda().train()
+    fs = [f.cuda().requires_grad_(True) for f in inp["feats"]]
+    out = m(list(fs))
+    for a, b in zip(out, gold["out_train"]):
+        assert rel_l2(a.detach().cpu(), b) < 1e-3
+    gouts = [S.randn(S.gen(spec["seed"] + 13 + i), *o.shape).cuda() for i, o in enumerate(out)]
+    sum((o * g).sum() for o, g in zip(out, gouts)).backward()
+    for f, g in zip(fs, gold["gfeats"]):
+        assert rel_l2(f.grad.cpu(), g) < 1e-2
+    named = dict(m.named_parameters())
+    worst = ("", 0.0)
+    for k, g in gold["grads"].items():
+        p = named[k[len("model.0."):]]
+        assert p.grad is not None, k
+        e = rel_l2(p.grad.cpu(), g)
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < 2e-2, worst
+
+
+def test_model_b_training_step():
+    E = ecsy()
+    torch.manual_seed(0)
+    m = E.yolo_snn.DetectionModel(E.cfg_path("tiny_b")).cuda().train()
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    with torch.no_grad():
+        probe = m(x)
+    tgt = [torch.randn_like(o) for o in probe]
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9)
+    losses = []
+    for it in range(4):
+        opt.zero_grad(set_to_none=True)
+        out = m(x)
+        loss = sum(((o - t) ** 2).mean() for o, t in zip(out, tgt))
+        loss.backward()
+        if it == 0:
+            missing = [n for n, p in m.named_parameters() if p.grad is None and p.requires_grad]
+            assert not missing, missing[:5]
+            assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+        opt.step()
+        losses.append(loss.item())
     assert losses[-1] < losses[0], losses
