@@ -269,7 +269,8 @@ def main():
     E.common.time_window = args.T
 
     torch.manual_seed(0)
-    model = E.yolo.Model(E.cfg_path(args.model)).cuda()
+    is_b = any(row[2] == "DDetect" for row in load_cfg(args.model)["head"])
+    model = (E.yolo_snn.DetectionModel if is_b else E.yolo.Model)(E.cfg_path(args.model)).cuda()
     g = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.rand(args.batch, 3, args.img, args.img, generator=g).pin_memory()
     x = x_host.cuda()
