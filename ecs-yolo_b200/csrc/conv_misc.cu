@@ -36,6 +36,28 @@ __global__ void k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
+// Same for the tensor-memory ("TS") spike convolution: the spike expanders emit a spike as the single bit 0x4000
+// (= 2.0 in bf16) and pack channels (j, j+16) of every 32-channel half into one 32-bit word, so the weights are
+// stored pre-multiplied by 0.5 (exact) with K element e of a 64-channel slab holding channel
+// (e>>5)*32 + (e&1)*16 + ((e&31)>>1).
+__global__ void k_pack_weight_ts(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Co, int Ci, int kh,
+                                 int kw, int splits) {
+  const int K = kh * kw * Ci;
+  const int64_t total = (int64_t)Co * K;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int k = static_cast<int>(i % K);
+    const int co = static_cast<int>(i / K);
+    const int tap = k / Ci, pos = k - tap * Ci;
+    const int e = pos & 63;
+    const int ci = (pos & ~63) + ((e >> 5) << 5) + ((e & 1) << 4) + ((e & 31) >> 1);
+    const float v = 0.5f * w[((int64_t)co * Ci + ci) * (kh * kw) + tap];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (splits == 2) out[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
 // A[m][k] (bf16 hi [+ lo]) for a real-valued NHWC input; m = output pixel, k = (ky*kw+kx)*Ci + ci,
 // zero padded to Kpad.  Each thread writes 8 consecutive k (16 bytes per plane).  The k -> (dy, dx, ci)
 // decomposition is tabulated once per block in shared memory (no per-element divisions).
@@ -196,6 +218,32 @@ extern "C" int ecsy_pack_conv_weight(const float* w, void* out_bf16, int Co, int
       w, static_cast<__nv_bfloat16*>(out_bf16), Co, Ci, kh, kw, Kpad, splits);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
+}
+
+extern "C" int ecsy_pack_spike_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh, int kw, int splits,
+                                           void* stream) {
+  ECSY_CHECK_ARG(w && out_bf16 && Co > 0 && Ci > 0 && kh > 0 && kw > 0, "pack_spike_conv_weight: bad arguments");
+  ECSY_CHECK_ARG(Ci % 64 == 0 && (splits == 1 || splits == 2), "pack_spike_conv_weight: Ci %% 64 / splits");
+  k_pack_weight_ts<<<grid_for((int64_t)Co * kh * kw * Ci, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(out_bf16), Co, Ci, kh, kw, splits);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+
+extern "C" int ecsy_spike_conv_ts_supported(int Cin, int Cout) {
+  return (Cin % 64 == 0 && Cin >= 64 && ecsy_pick_bn_ts(Cout) != 0) ? 1 : 0;
+}
+
+extern "C" int ecsy_spike_conv_ts_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out,
+                                      const float* scale, const float* shift, const float* residual, int64_t res_imgs,
+                                      int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                      void* stream) {
+  ECSY_CHECK_ARG(spikes && w_ts && out && imgs > 0 && H > 0 && W > 0, "spike_conv_ts_fwd: bad arguments");
+  ECSY_CHECK_ARG((scale == nullptr) == (shift == nullptr), "spike_conv_ts_fwd: scale/shift pair");
+  ECSY_CHECK_ARG(!residual || (res_imgs > 0 && imgs % res_imgs == 0), "spike_conv_ts_fwd: residual image count");
+  ECSY_CHECK_ARG(imgs < (1 << 24), "spike_conv_ts_fwd: too many images");
+  return ecsy_umma_spike_conv(spikes, w_ts, splits, out, scale, shift, residual, res_imgs, (int)imgs, H, W, Cin,
+                              Cout, k, stride, pad, STREAM(stream), 1);
 }
 
 extern "C" int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed, int splits, float* out,

@@ -94,7 +94,7 @@ struct EpiSel;
 template <>
 struct EpiSel<0> { using type = EpiConv; };
 
-constexpr int kATma = 0, kASpikes = 1, kATma4 = 2, kADw = 3;
+constexpr int kATma = 0, kASpikes = 1, kATma4 = 2, kADw = 3, kASpikesT = 4;
 constexpr int kEpiConv = 0;
 
 __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
 }
 
 template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
-__global__ void __launch_bounds__((A_MODE == kASpikes || A_MODE == kADw) ? kSpikeThreads : 192, 1)
+__global__ void __launch_bounds__((A_MODE == kASpikes || A_MODE == kADw || A_MODE == kASpikesT) ? kSpikeThreads : 192, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
             const __grid_constant__ CUtensorMap tm_b, const GemmArgs g, const SpikeGeom sg,
             const typename EpiSel<EPI>::type ep) {
@@ -111,8 +111,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
   // 1024-byte alignment for the 128B-swizzled operand tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kBTileBytes = BN * 128;
-  constexpr int kStageBytes = A_SPLIT * kATileBytes + B_SPLIT * kBTileBytes;
-  constexpr int kTmemCols = 2 * BN;  // two accumulator buffers: 128, 256 or 512 columns
+  constexpr bool kTS = A_MODE == kASpikesT;   // A operand lives in tensor memory (no smem A tile)
+  constexpr int kASmemBytes = kTS ? 0 : A_SPLIT * kATileBytes;
+  constexpr int kStageBytes = kASmemBytes + B_SPLIT * kBTileBytes;
+  // two accumulator buffers (128, 256 or 512 columns); TS mode adds a ring of 32-column A stages behind them
+  constexpr int kTmemCols = kTS ? 512 : 2 * BN;
+  static_assert(!kTS || BN <= 128, "TS mode: accumulators + A ring must fit 512 TMEM columns");
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + (size_t)g.stages * kStageBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -126,7 +130,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       if (A_SPLIT == 2) tma_prefetch_desc(&tm_a1);
     }
     for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&ctl->full_a[s], A_MODE == kADw ? kExpWarps : g.wpg);
+      mbar_init(&ctl->full_a[s], A_MODE == kADw ? kExpWarps : (kTS ? 4 : g.wpg));
       mbar_init(&ctl->full_b[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
@@ -173,7 +177,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
           }
 #pragma unroll
           for (int bs = 0; bs < B_SPLIT; ++bs)
-            tma_load_2d(st + A_SPLIT * kATileBytes + bs * kBTileBytes, &tm_b, &ctl->full_b[stage], kb * 64,
+            tma_load_2d(st + kASmemBytes + bs * kBTileBytes, &tm_b, &ctl->full_b[stage], kb * 64,
                         bs * (g.n_tiles * BN) + n_tile * BN);
         }
         __syncwarp();
@@ -197,12 +201,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       const uint32_t d_tmem = tmem_base + buf * BN;
       for (int kb = 0; kb < g.kb_total; ++kb) {
         mbar_wait(&ctl->full_b[stage], phase);
-        if (A_MODE == kASpikes || A_MODE == kADw) mbar_wait(&ctl->full_a[stage], phase);
+        if (A_MODE == kASpikes || A_MODE == kADw || kTS) mbar_wait(&ctl->full_a[stage], phase);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
-          const uint32_t b_addr = a_addr + A_SPLIT * kATileBytes;
+          const uint32_t b_addr = a_addr + kASmemBytes;
           uint32_t acc = kb > 0 ? 1u : 0u;
+          if constexpr (kTS) {
+            const uint32_t a_tmem = tmem_base + 2 * BN + stage * 32;
+#pragma unroll
+            for (int bs = 0; bs < B_SPLIT; ++bs) {
+              const uint64_t db = umma_desc_sw128(b_addr + bs * kBTileBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_ts(d_tmem, a_tmem + k * 8, db + (uint64_t)(k * 2), idesc, acc);
+                acc = 1u;
+              }
+            }
+          } else {
 #pragma unroll
           for (int combo = 0; combo < A_SPLIT + B_SPLIT - 1; ++combo) {
             // combos: (A0,B0) [, (A1,B0)] [, (A0,B1)]  -- the lo*lo term is below fp32 resolution
@@ -216,6 +232,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
               umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
               acc = 1u;
             }
+          }
           }
           umma_commit(&ctl->empty[stage]);
           if (kb == g.kb_total - 1) umma_commit(&ctl->tmem_full[buf]);
@@ -333,6 +350,115 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp >= 6 && kTS) {
+    // =============================== spike expanders, A operand in tensor memory ===============================
+    // A thread owns ONE operand row (= output pixel) of the tile: TMEM lane = row, and a warp may only touch
+    // the lane quarter (warp id % 4).  Two warps share a quarter and alternate K blocks.  Per K block a thread
+    // reads the 64 spike bits of (pixel + tap, 64-channel slab) from the L2-resident bit tensor (kPf blocks
+    // ahead), turns them into 32 packed bf16 pairs with one shift + one mask each (a spike is the single bit
+    // 0x4000 = 2.0; the host packs the weights pre-multiplied by 0.5 and in the matching channel order:
+    // word j of a 32-channel half holds channels j and j+16) and stores them with one tcgen05.st -- the
+    // operand never touches shared memory, so the MMA reads only B from smem.
+    if constexpr (kTS) {
+      constexpr int kPf = 4;
+      const int q = warp & 3;
+      const uint32_t par = (uint32_t)(warp - 6) >> 2;
+      const int r = q * 32 + lane;
+      const int w_l = r & (sg.tw_b - 1);
+      const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
+      const int n_l = r >> (sg.tw_sh + sg.th_sh);
+      const uint32_t S = (uint32_t)g.stages;
+      const int kbt = g.kb_total;
+      const int tiles_hw = sg.tiles_h * sg.tiles_w;
+      const uint32_t my_tiles = blockIdx.x < (uint32_t)total_tiles
+                                    ? (uint32_t)(total_tiles - 1 - (int)blockIdx.x) / gridDim.x + 1 : 0u;
+      const uint32_t c_end = my_tiles * (uint32_t)kbt;
+      const uint32_t a_row = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN;
+      const int64_t wstride = (int64_t)sg.Cw;
+
+      // load cursor: K block `lc` of this CTA's sequence = (tile, ky, kx, slab)
+      uint32_t lc = par;
+      int l_tile = (int)blockIdx.x, l_kb = (int)par, l_ky = 0, l_kx = 0, l_slab = 0;
+      int l_hi0 = 0, l_wi0 = 0;
+      const uint32_t* l_img = nullptr;
+      bool l_ok = false;
+      auto set_tile = [&]() {
+        const int m_tile = l_tile / g.n_tiles;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        const int img = tn * sg.tn_b + n_l;
+        l_ok = img < sg.imgs;
+        l_hi0 = (th * sg.th_b + h_l) * sg.stride - sg.pad;
+        l_wi0 = (tw * sg.tw_b + w_l) * sg.stride - sg.pad;
+        l_img = sg.bits + (int64_t)(l_ok ? img : 0) * sg.H * sg.W * wstride;
+      };
+      auto set_kb = [&]() {   // decode l_kb (only after a tile change or at start)
+        const int tap = l_kb / sg.nslab;
+        l_slab = l_kb - tap * sg.nslab;
+        l_ky = tap / sg.kw;
+        l_kx = tap - l_ky * sg.kw;
+      };
+      auto advance2 = [&]() {  // move the cursor two K blocks forward
+        lc += 2;
+        l_kb += 2;
+        if (l_kb >= kbt) {
+          do { l_kb -= kbt; l_tile += (int)gridDim.x; } while (l_kb >= kbt);
+          set_tile();
+          set_kb();
+        } else {
+          l_slab += 2;
+          while (l_slab >= sg.nslab) {
+            l_slab -= sg.nslab;
+            if (++l_kx == sg.kw) { l_kx = 0; ++l_ky; }
+          }
+        }
+      };
+      auto load_cur = [&]() -> uint2 {
+        uint2 v = make_uint2(0u, 0u);
+        if (lc < c_end) {
+          const int hi = l_hi0 + l_ky, wi = l_wi0 + l_kx;
+          if (l_ok && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
+            v = __ldg(reinterpret_cast<const uint2*>(l_img + ((int64_t)hi * sg.W + wi) * wstride + l_slab * 2));
+        }
+        return v;
+      };
+
+      uint2 pf[kPf];
+      while (l_kb >= kbt) { l_kb -= kbt; l_tile += (int)gridDim.x; }
+      if (lc < c_end) { set_tile(); set_kb(); }
+#pragma unroll
+      for (int j = 0; j < kPf; ++j) {
+        pf[j] = load_cur();
+        if (lc < c_end) advance2();
+      }
+      uint32_t c = par;
+      while (c < c_end) {
+#pragma unroll
+        for (int j = 0; j < kPf; ++j) {
+          if (c < c_end) {
+            const uint2 cur = pf[j];
+            pf[j] = load_cur();
+            if (lc < c_end) advance2();
+            const uint32_t stage = c % S;
+            uint32_t v[32];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              v[jj] = (jj < 15 ? (cur.x << (14 - jj < 0 ? 0 : 14 - jj)) : (cur.x >> 1)) & 0x40004000u;
+              v[16 + jj] = (jj < 15 ? (cur.y << (14 - jj < 0 ? 0 : 14 - jj)) : (cur.y >> 1)) & 0x40004000u;
+            }
+            mbar_wait(&ctl->empty[stage], ((c / S) & 1) ^ 1);
+            tc_fence_after_sync();
+            tmem_st_32x32(a_row + stage * 32, v);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->full_a[stage]);
+            c += 2;
+          }
+        }
+      }
+    }
   } else if (warp >= 6) {
     // =============================== spike expanders ===============================
     // Stage group g (= pipeline stage g) owns every K block c with c % stages == g, so `stages` K blocks
@@ -431,7 +557,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       // output row of this thread
       int64_t pix;
       bool valid;
-      if (A_MODE == kASpikes || A_MODE == kATma4) {
+      if (A_MODE == kASpikes || A_MODE == kATma4 || kTS) {
         const int tiles_hw = sg.tiles_h * sg.tiles_w;
         const int tn = m_tile / tiles_hw;
         const int rem = m_tile - tn * tiles_hw;
@@ -827,7 +953,8 @@ constexpr int kSmemLimit = 227 * 1024;
 template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
 int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmArgs g, const SpikeGeom& sg,
                const typename EpiSel<EPI>::type& ep, int patch_bytes, cudaStream_t st) {
-  constexpr int stage_bytes = A_SPLIT * kATileBytes + B_SPLIT * BN * 128;
+  constexpr bool kTS = A_MODE == kASpikesT;
+  constexpr int stage_bytes = (kTS ? 0 : A_SPLIT * kATileBytes) + B_SPLIT * BN * 128;
   auto kern = k_umma_gemm<BN, A_MODE, A_SPLIT, B_SPLIT, EPI>;
   static int dyn_limit = 0;  // opt-in dynamic shared memory = 227 KB minus the kernel's static usage
   if (dyn_limit == 0) {
@@ -843,6 +970,11 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   int stages = (dyn_limit - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (A_MODE == kASpikes) stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : (stages >= 2 ? 2 : 0));
+  if (kTS) {  // the A ring lives in the TMEM columns behind the two accumulators (32 columns per stage)
+    const int tmem_stages = (512 - 2 * BN) / 32;
+    if (stages > tmem_stages) stages = tmem_stages;
+    stages &= ~1;
+  }
   if (stages < 2) {
     ecsy_set_error("umma gemm: shared memory budget allows only %d stage(s) (patch %d bytes)", stages, patch_bytes);
     return ECSY_ERR_UNSUPPORTED;
@@ -855,7 +987,7 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, (A_MODE == kASpikes || A_MODE == kADw) ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
+  kern<<<grid, (A_MODE == kASpikes || A_MODE == kADw || kTS) ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }
@@ -866,7 +998,9 @@ int launch_bn(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   switch (BN) {
     case 64: return launch_one<64, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
     case 128: return launch_one<128, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
-    case 256: return launch_one<256, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
+    case 256:
+      if constexpr (A_MODE != kASpikesT) return launch_one<256, A_MODE, A_SPLIT, B_SPLIT, EPI>(a0, a1, b, g, sg, ep, patch_bytes, st);
+      break;
   }
   ecsy_set_error("umma gemm: unsupported BN=%d", BN);
   return ECSY_ERR_UNSUPPORTED;
@@ -908,11 +1042,18 @@ int ecsy_pick_bn(int cout, int splits) {
 }
 
 // Spike convolution: out[imgs][Ho][Wo][Cout] = conv(spikes, W) (*scale + shift) (+ residual)
+int ecsy_pick_bn_ts(int cout) {
+  // TS mode: the A ring shares the 512 TMEM columns with the two accumulators -> at most 128 columns per tile
+  for (int bn = 128; bn >= 64; bn >>= 1)
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
 int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits, float* out, const float* scale,
                          const float* shift, const float* residual, int64_t res_imgs, int imgs, int H, int W, int Cin,
-                         int Cout, int k, int stride, int pad, cudaStream_t st) {
+                         int Cout, int k, int stride, int pad, cudaStream_t st, int ts) {
   ECSY_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "spike_conv: Cin=%d must be a multiple of 64", Cin);
-  const int BN = ecsy_pick_bn(Cout, splits);
+  const int BN = ts ? ecsy_pick_bn_ts(Cout) : ecsy_pick_bn(Cout, splits);
   ECSY_CHECK_ARG(BN != 0, "spike_conv: Cout=%d must be a multiple of 64", Cout);
   ECSY_CHECK_ARG(splits == 1 || splits == 2, "spike_conv: splits must be 1 or 2");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
@@ -939,6 +1080,10 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   if (rc) return rc;
   EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout, 0};
   const int patch_bytes = sg.PP * Cw * 4;
+  if (ts) {
+    if (splits == 1) return launch_bn<kASpikesT, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
+    return launch_bn<kASpikesT, 1, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
+  }
   if (splits == 1) return launch_bn<kASpikes, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
   return launch_bn<kASpikes, 1, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
 }

@@ -8,7 +8,8 @@ int ecsy_pick_bn(int cout, int splits);
 int ecsy_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out);
 int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits, float* out, const float* scale,
                          const float* shift, const float* residual, int64_t res_imgs, int imgs, int H, int W, int Cin,
-                         int Cout, int k, int stride, int pad, cudaStream_t st);
+                         int Cout, int k, int stride, int pad, cudaStream_t st, int ts = 0);
+int ecsy_pick_bn_ts(int cout);
 int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
                     int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
                     cudaStream_t st, int out_half = 0);

@@ -9,6 +9,7 @@ spikes are bit-packed int32 ``[T, N, H, W, C/32]``.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -21,7 +22,7 @@ thresh = 0.5
 lens = 0.5
 decay = 0.25
 
-_state = {"splits": 2}
+_state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "1") != "0"}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
@@ -72,6 +73,15 @@ def set_precision(mode: str) -> None:
 
 def get_splits() -> int:
     return _state["splits"]
+
+
+def set_conv_ts(on: bool) -> None:
+    """Spike convs stage their A operand in tensor memory (tcgen05.mma TS form) when on (default)."""
+    _state["conv_ts"] = bool(on)
+
+
+def conv_ts_enabled() -> bool:
+    return _state["conv_ts"]
 
 
 def _st() -> int:
@@ -196,6 +206,7 @@ class ConvW:
     groups: int
     splits: int
     dense_groups: bool = False   # `packed` holds the block-diagonal dense form of a grouped weight
+    packed_ts: Optional[torch.Tensor] = None   # spike-conv form for the tensor-memory path (ecsy_pack_spike_conv_weight)
 
 
 def densify_grouped(weight: torch.Tensor, groups: int) -> torch.Tensor:
@@ -209,21 +220,31 @@ def densify_grouped(weight: torch.Tensor, groups: int) -> torch.Tensor:
     return dense
 
 
+def pack_spike_conv_weight(w: torch.Tensor, splits: int) -> torch.Tensor:
+    """[Co, Ci, kh, kw] fp32 -> [splits, Co, kh*kw*Ci] bf16 in the operand order of the tensor-memory spike conv."""
+    _chk_cuda(w)
+    w = w.detach().float().contiguous()
+    Co, Ci, kh, kw = w.shape
+    out = torch.empty(splits, Co, kh * kw * Ci, device=w.device, dtype=torch.bfloat16)
+    _cabi.check(_cabi.lib().ecsy_pack_spike_conv_weight(_p(w), _p(out), Co, Ci, kh, kw, splits, _st()),
+                "pack_spike_conv_weight")
+    return out
+
+
 def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, umma: bool, simt: bool,
                 densify: bool = False) -> ConvW:
     splits = get_splits()
     Co, Cig, kh, kw = weight.shape
-    if densify and groups > 1:
-        packed = pack_conv_weight(densify_grouped(weight, groups), splits) if umma else None
-        sw = weight.detach().float().permute(2, 3, 1, 0).contiguous() if simt else None
-        b = bias.detach().float().contiguous() if bias is not None else None
-        cw = ConvW(packed, sw, b, Co, Cig * groups, kh, stride, pad, groups, splits)
-        cw.dense_groups = True
-        return cw
-    packed = pack_conv_weight(weight, splits) if umma else None
+    dense = densify_grouped(weight, groups) if (densify and groups > 1) else weight
+    packed = pack_conv_weight(dense, splits) if umma else None
     sw = weight.detach().float().permute(2, 3, 1, 0).contiguous() if simt else None
     b = bias.detach().float().contiguous() if bias is not None else None
-    return ConvW(packed, sw, b, Co, Cig * groups, kh, stride, pad, groups, splits)
+    cw = ConvW(packed, sw, b, Co, Cig * groups, kh, stride, pad, groups, splits)
+    cw.dense_groups = bool(densify and groups > 1)
+    if (packed is not None and conv_ts_enabled() and bias is None and (groups == 1 or densify)
+            and _cabi.lib().ecsy_spike_conv_ts_supported(Cig * groups, Co)):
+        cw.packed_ts = pack_spike_conv_weight(dense, splits)
+    return cw
 
 
 @dataclass
@@ -425,9 +446,11 @@ def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[A
     if residual is not None:
         assert (residual.N, residual.H, residual.W, residual.C) == (N, Ho, Wo, w.co), "residual shape"
     flops["spike_conv"] += 2.0 * T * N * Ho * Wo * w.co * s.C * w.k * w.k
+    ts = w.packed_ts is not None and conv_ts_enabled()
+    L = _cabi.lib()
     with _timed("spike_conv", 1):
-        _cabi.check(_cabi.lib().ecsy_spike_conv_fwd(
-            _p(s.bits), _p(w.packed), w.splits, _p(out), _p(scale), _p(shift),
+        _cabi.check((L.ecsy_spike_conv_ts_fwd if ts else L.ecsy_spike_conv_fwd)(
+            _p(s.bits), _p(w.packed_ts if ts else w.packed), w.splits, _p(out), _p(scale), _p(shift),
             _p(residual.data) if residual is not None else None, residual.src_imgs if residual is not None else 0,
             T * N, H, W, s.C, w.co, w.k, w.stride, w.pad, _st()), "spike_conv_fwd")
     return Act(out, T)

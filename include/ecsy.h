@@ -76,6 +76,16 @@ int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed, int splits
                         const float* shift, const float* residual, int64_t res_imgs, int64_t imgs, int H, int W,
                         int Cin, int Cout, int k, int stride, int pad, void* stream);
 
+/* Same operator with the spike operand staged in TENSOR MEMORY (tcgen05.mma with A in TMEM; Cin % 64 == 0,
+ * Cout % 64 == 0 -- ask ecsy_spike_conv_ts_supported).  w_ts: [splits][Cout][k*k*Cin] bf16 from
+ * ecsy_pack_spike_conv_weight (weights * 0.5 -- a spike is emitted as 2.0 -- in the expander's channel order). */
+int ecsy_pack_spike_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh, int kw, int splits,
+                                void* stream);
+int ecsy_spike_conv_ts_supported(int Cin, int Cout);
+int ecsy_spike_conv_ts_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out, const float* scale,
+                           const float* shift, const float* residual, int64_t res_imgs, int64_t imgs, int H, int W,
+                           int Cin, int Cout, int k, int stride, int pad, void* stream);
+
 /* ---- Snn_Conv2d.forward on REAL inputs: stem Conv_1 (common.py:409-425), Conv (common.py:362-375),
  * Detect.m (yolo.py:73), DDetect cv2/cv3[-1] (yolo_snn.py:100-107).  groups == 1 && Cout % 64 == 0 && no bias:
  * im2col + tcgen05 GEMM (needs w_packed + workspace); otherwise SIMT with w_simt = [kh][kw][Ci/g][Co] fp32.

@@ -29,12 +29,14 @@ def test_layout_and_bits_roundtrip():
     assert torch.equal(ab.to_ref().cpu(), xb.cpu())
 
 
+@pytest.mark.parametrize("ts", [True, False], ids=["tmemA", "smemA"])
 @pytest.mark.parametrize("mode,tol", [("parity", 2e-5), ("fast", 6e-3)])
 @pytest.mark.parametrize("name", [n for n, s in S.CONV_CASES.items() if s["spikes"]])
-def test_spike_conv(name, mode, tol):
+def test_spike_conv(name, mode, tol, ts):
     E = ecsy()
     F = E.functional
     F.set_precision(mode)
+    F.set_conv_ts(ts)
     try:
         spec, gold = S.CONV_CASES[name], load_golden(name)
         inp = S.conv_inputs(spec)
@@ -54,8 +56,45 @@ def test_spike_conv(name, mode, tol):
         resb = res[:1].cuda().expand(res.shape[0], -1, -1, -1, -1)
         out3 = F.spike_conv(sp, w, None, None, F.Act.from_ref(resb)).to_ref().cpu()
         assert rel_l2(out3, gold["out"] + res[:1]) < tol
+        assert (w.packed_ts is not None) == (ts and spec["ci"] % 64 == 0 and spec["co"] % 64 == 0)
     finally:
         F.set_precision("parity")
+        F.set_conv_ts(True)
+
+
+@pytest.mark.parametrize("mode", ["parity", "fast"])
+@pytest.mark.parametrize("ci,co,k,s,H,W,N,T", [
+    (64, 64, 1, 1, 9, 11, 3, 2),        # one K block per tile (both expander parities cross tiles every block)
+    (64, 64, 3, 1, 37, 41, 5, 4),       # odd K-block count, more tiles than SMs (persistent loop), ragged edges
+    (128, 256, 3, 2, 30, 30, 4, 2),     # stride 2, two N tiles of 128
+    (192, 128, 3, 1, 12, 20, 2, 3),     # three slabs per tap
+    (512, 512, 3, 1, 20, 20, 2, 4),     # deep K (72 blocks), four N tiles
+])
+def test_spike_conv_tmem_operand(ci, co, k, s, H, W, N, T, mode):
+    """The tensor-memory operand path against fp64 conv2d on the same bf16-rounded (fast) / fp32 (parity) weights,
+    and against the shared-memory operand path (same products, fp32 accumulation order may differ)."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision(mode)
+    try:
+        g = S.gen(ci + co + k)
+        x = (torch.rand(T, N, ci, H, W, generator=g) < 0.2).float()
+        w = torch.randn(co, ci, k, k, generator=g) * 0.05
+        sp = F.Spikes.from_act(F.Act.from_ref(x.cuda()))
+        F.set_conv_ts(True)
+        cw = F.make_conv_w(w.cuda(), None, s, k // 2, 1, True, False)
+        assert cw.packed_ts is not None
+        out_ts = F.spike_conv(sp, cw).to_ref().cpu()
+        F.set_conv_ts(False)
+        out_ss = F.spike_conv(sp, cw).to_ref().cpu()
+        wq = w if mode == "parity" else w.bfloat16().float()
+        ref = torch.nn.functional.conv2d(x.reshape(T * N, ci, H, W).double(), wq.double(), None, s, k // 2)
+        ref = ref.reshape(T, N, co, *ref.shape[-2:]).float()
+        assert rel_l2(out_ts, ref) < 2e-5
+        assert rel_l2(out_ts, out_ss) < 1e-5
+    finally:
+        F.set_precision("parity")
+        F.set_conv_ts(True)
 
 
 @pytest.mark.parametrize("name", [n for n, s in S.CONV_CASES.items() if not s["spikes"]])
