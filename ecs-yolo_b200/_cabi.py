@@ -39,6 +39,7 @@ SIGNATURES = {
     "ecsy_spike_conv_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_spike_conv_ts_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_spike_conv_ts_supported": (_i, [_i, _i]),
+    "ecsy_spike_conv_prefers_ts": (_i, [_i, _i, _i]),
     "ecsy_pack_spike_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ecsy_real_conv_ws_bytes": (_z, [_l, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "ecsy_real_conv_fwd": (_i, [_p, _l, _p, _p, _i, _p, _f, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i,

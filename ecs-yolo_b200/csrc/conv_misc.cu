@@ -234,6 +234,15 @@ extern "C" int ecsy_spike_conv_ts_supported(int Cin, int Cout) {
   return (Cin % 64 == 0 && Cin >= 64 && ecsy_pick_bn_ts(Cout) != 0) ? 1 : 0;
 }
 
+// Measured on B200 (profiles/r01_conv_microbench_*): with single-plane weights, wide layers (Cout % 256 == 0 and
+// Cin >= 256) run faster with 256-column tiles and the operand in shared memory (1.3-1.4 PFLOP/s) than with the
+// 128-column tiles the tensor-memory path is limited to (1.1 PFLOP/s); everything else prefers tensor memory.
+extern "C" int ecsy_spike_conv_prefers_ts(int Cin, int Cout, int splits) {
+  if (!ecsy_spike_conv_ts_supported(Cin, Cout)) return 0;
+  if (splits == 1 && Cout % 256 == 0 && Cin >= 256) return 0;
+  return 1;
+}
+
 extern "C" int ecsy_spike_conv_ts_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out,
                                       const float* scale, const float* shift, const float* residual, int64_t res_imgs,
                                       int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,

@@ -28,6 +28,7 @@
 // allocator, 6-13 spike expanders (kASpikes only).  smem ring of `stages` {A,B} slots guarded by
 // full/empty mbarriers; two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -649,6 +650,411 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------------
+// Production forward spike convolution: tensor-memory A operand + TMA-store epilogue.
+//
+// Same mainloop as k_umma_gemm<kASpikesT> (B by TMA, A expanded from spike bits straight into TMEM, two
+// accumulator buffers), but the epilogue is built for throughput: TWO epilogue groups of 4 warps (group g owns
+// accumulator buffer g, i.e. every other tile), each draining 32-column slices: tcgen05.ld (row per lane) ->
+// folded tdBN affine from shared memory -> (+ residual slice that TMA loaded into the staging buffer) ->
+// 128-byte-swizzled staging tile -> ONE cp.async.bulk.tensor store per slice.  No per-row address arithmetic,
+// no partially written sectors; image / row / column edges are clipped by the tensor map.
+// Warps: 0-3 epilogue group 0, 4-7 epilogue group 1, 8 TMA producer (weights), 9 MMA issuer + TMEM allocator,
+// 10-17 spike expanders (lane quarter = warp % 4, two warps per quarter alternate K blocks).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTsThreads = 576;
+constexpr int kTsSlice = 128 * 128;   // staging slice: 128 rows x 32 fp32
+constexpr int kTsMaxBuf = 3;
+
+constexpr int kTsMaxStages = 12;
+struct TsCtl {
+  uint64_t full_a[kTsMaxStages];
+  uint64_t full_b[kTsMaxStages];
+  uint64_t empty[kTsMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t res_full[2][kTsMaxBuf];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct TsArgs {
+  int m_tiles, n_tiles, kb_total, stages;
+  int resident;    // stages == kb_total: every weight K block stays in shared memory, loaded once per CTA (no
+                   // per-tile weight re-reads: 148 SMs hammering the same few hundred L2 lines was the limiter)
+  int nbuf;        // staging buffers per epilogue group: 3 = residual prefetched one slice ahead, else 2
+  int has_res;
+  int res_imgs;    // images in the residual tensor (T-broadcast sources repeat)
+  int cout;
+  const float* scale;
+  const float* shift;
+  uint32_t stg_off, aff_off, ctl_off;   // byte offsets inside the 1024-aligned dynamic shared memory
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int BN, int B_SPLIT>
+__global__ void __launch_bounds__(kTsThreads, 1)
+k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_out,
+                const __grid_constant__ CUtensorMap tm_res, const TsArgs g, const SpikeGeom sg) {
+  static_assert(BN == 64 || BN == 128, "accumulators + A ring must fit 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = B_SPLIT * kBTileBytes;
+  constexpr int kSlices = BN / 32;
+  TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + g.ctl_off);
+  float* s_scale = reinterpret_cast<float*>(smem + g.aff_off);
+  float* s_shift = s_scale + g.cout;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int tiles_hw = sg.tiles_h * sg.tiles_w;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
+    if (g.has_res) tma_prefetch_desc(&tm_res);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&ctl->full_a[s], 4);
+      mbar_init(&ctl->full_b[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->tmem_full[b], 1);
+      mbar_init(&ctl->tmem_empty[b], 128);
+      for (int k = 0; k < kTsMaxBuf; ++k) mbar_init(&ctl->res_full[b][k], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<512>(&ctl->tmem_base);
+  if (g.scale != nullptr)
+    for (int i = threadIdx.x; i < g.cout; i += kTsThreads) {
+      s_scale[i] = g.scale[i];
+      s_shift[i] = g.shift[i];
+    }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 8) {
+    // =============================== TMA producer: weight tiles ===============================
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % g.n_tiles;
+      if (g.resident && tile != (int)blockIdx.x) break;   // resident weights: loaded by the first tile only
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        if (!g.resident) mbar_wait(&ctl->empty[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* st = smem + (size_t)stage * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->full_b[stage], (uint32_t)kStageBytes);
+#pragma unroll
+          for (int bs = 0; bs < B_SPLIT; ++bs)
+            tma_load_2d(st + bs * kBTileBytes, &tm_b, &ctl->full_b[stage], kb * 64, bs * (g.n_tiles * BN) + n_tile * BN);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[buf], bphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        if (!g.resident || it == 0) mbar_wait(&ctl->full_b[stage], phase);
+        mbar_wait(&ctl->full_a[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t b_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint32_t a_tmem = tmem_base + 2 * BN + stage * 32;
+          uint32_t acc = kb > 0 ? 1u : 0u;
+#pragma unroll
+          for (int bs = 0; bs < B_SPLIT; ++bs) {
+            const uint64_t db = umma_desc_sw128(b_addr + bs * kBTileBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_ts(d_tmem, a_tmem + k * 8, db + (uint64_t)(k * 2), idesc, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&ctl->empty[stage]);
+          if (kb == g.kb_total - 1) umma_commit(&ctl->tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 10) {
+    // =============================== spike expanders (A operand -> tensor memory) ===============================
+    // See k_umma_gemm<kASpikesT>: one operand row (= output pixel) per thread, 64 spike bits per K block read
+    // kPf blocks ahead, one shift + one mask per packed bf16 pair (spike = 0x4000 = 2.0, weights carry the 0.5),
+    // one tcgen05.st per K block.
+    constexpr int kPf = 4;
+    const int q = warp & 3;
+    const uint32_t par = (uint32_t)(warp - 10) >> 2;
+    const int r = q * 32 + lane;
+    const int w_l = r & (sg.tw_b - 1);
+    const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
+    const int n_l = r >> (sg.tw_sh + sg.th_sh);
+    const uint32_t S = (uint32_t)g.stages;
+    const int kbt = g.kb_total;
+    const uint32_t my_tiles = blockIdx.x < (uint32_t)total_tiles
+                                  ? (uint32_t)(total_tiles - 1 - (int)blockIdx.x) / gridDim.x + 1 : 0u;
+    const uint32_t c_end = my_tiles * (uint32_t)kbt;
+    const uint32_t a_row = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN;
+    const int64_t wstride = (int64_t)sg.Cw;
+
+    // Load cursor: K block `lc` of this CTA's sequence = (tile, ky, kx, slab).  No divisions on the per-block path:
+    // the tile index advances by gridDim.x in the mixed radix (n_tile, tile_w, tile_h, tile_n) with carries.
+    uint32_t lc = par;
+    int l_kb = (int)par, l_ky = 0, l_kx = 0, l_slab = 0;
+    int d_n, d_w, d_h, d_t;              // digits of the cursor's tile
+    int s_n, s_w, s_h, s_t;              // digits of the tile step (gridDim.x)
+    {
+      int v = (int)blockIdx.x;
+      d_n = v % g.n_tiles; v /= g.n_tiles;
+      d_w = v % sg.tiles_w; v /= sg.tiles_w;
+      d_h = v % sg.tiles_h; d_t = v / sg.tiles_h;
+      v = (int)gridDim.x;
+      s_n = v % g.n_tiles; v /= g.n_tiles;
+      s_w = v % sg.tiles_w; v /= sg.tiles_w;
+      s_h = v % sg.tiles_h; s_t = v / sg.tiles_h;
+    }
+    int l_hi0 = 0, l_wi0 = 0;
+    const uint32_t* l_row0 = nullptr;    // &bits[img][hi0][wi0][0] of this thread's pixel (may point outside: guarded)
+    bool l_ok = false;
+    const int tapw = (int)wstride;       // words per pixel
+    const int roww = sg.W * tapw;        // words per image row
+    auto set_tile = [&]() {
+      const int img = d_t * sg.tn_b + n_l;
+      l_ok = img < sg.imgs;
+      l_hi0 = (d_h * sg.th_b + h_l) * sg.stride - sg.pad;
+      l_wi0 = (d_w * sg.tw_b + w_l) * sg.stride - sg.pad;
+      l_row0 = sg.bits + ((int64_t)(l_ok ? img : 0) * sg.H + l_hi0) * roww + (int64_t)l_wi0 * tapw;
+    };
+    auto next_tile = [&]() {
+      d_n += s_n;
+      int cy = d_n >= g.n_tiles ? 1 : 0;
+      d_n -= cy ? g.n_tiles : 0;
+      d_w += s_w + cy;
+      cy = d_w >= sg.tiles_w ? 1 : 0;
+      d_w -= cy ? sg.tiles_w : 0;
+      d_h += s_h + cy;
+      cy = d_h >= sg.tiles_h ? 1 : 0;
+      d_h -= cy ? sg.tiles_h : 0;
+      d_t += s_t + cy;
+    };
+    auto norm_kb = [&]() {   // (ky, kx, slab) of a small l_kb after a tile change
+      l_slab = l_kb; l_ky = 0; l_kx = 0;
+      while (l_slab >= sg.nslab) {
+        l_slab -= sg.nslab;
+        if (++l_kx == sg.kw) { l_kx = 0; ++l_ky; }
+      }
+    };
+    auto advance2 = [&]() {
+      lc += 2;
+      l_kb += 2;
+      if (l_kb >= kbt) {
+        do { l_kb -= kbt; next_tile(); } while (l_kb >= kbt);
+        set_tile();
+        norm_kb();
+      } else {
+        l_slab += 2;
+        while (l_slab >= sg.nslab) {
+          l_slab -= sg.nslab;
+          if (++l_kx == sg.kw) { l_kx = 0; ++l_ky; }
+        }
+      }
+    };
+    auto load_cur = [&]() -> uint2 {
+      uint2 v = make_uint2(0u, 0u);
+      if (lc < c_end) {
+        const int hi = l_hi0 + l_ky, wi = l_wi0 + l_kx;
+        if (l_ok && (unsigned)hi < (unsigned)sg.H && (unsigned)wi < (unsigned)sg.W)
+          v = __ldg(reinterpret_cast<const uint2*>(l_row0 + (l_ky * roww + l_kx * tapw + l_slab * 2)));
+      }
+      return v;
+    };
+
+    uint2 pf[kPf];
+    while (l_kb >= kbt) { l_kb -= kbt; next_tile(); }
+    set_tile();
+    norm_kb();
+#pragma unroll
+    for (int j = 0; j < kPf; ++j) {
+      pf[j] = load_cur();
+      if (lc < c_end) advance2();
+    }
+    uint32_t c = par;
+    uint32_t stage = par % S, sphase = ((par / S) & 1) ^ 1;   // stage / wait parity of block c, advanced incrementally
+    while (c < c_end) {
+#pragma unroll
+      for (int j = 0; j < kPf; ++j) {
+        if (c < c_end) {
+          const uint2 cur = pf[j];
+          pf[j] = load_cur();
+          if (lc < c_end) advance2();
+          uint32_t v[32];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            v[jj] = (jj < 15 ? (cur.x << (14 - jj < 0 ? 0 : 14 - jj)) : (cur.x >> 1)) & 0x40004000u;
+            v[16 + jj] = (jj < 15 ? (cur.y << (14 - jj < 0 ? 0 : 14 - jj)) : (cur.y >> 1)) & 0x40004000u;
+          }
+          mbar_wait(&ctl->empty[stage], sphase);
+          tc_fence_after_sync();
+          tmem_st_32x32(a_row + stage * 32, v);
+          tmem_st_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->full_a[stage]);
+          c += 2;
+          stage += 2;
+          if (stage >= S) { stage -= S; sphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue groups (warps 0-3: buffer 0, warps 4-7: buffer 1) ===============================
+    const uint32_t ge = (uint32_t)warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = (q == 0 && lane == 0);
+    const uint32_t nbuf = (uint32_t)g.nbuf;
+    const bool prefetch = g.has_res && nbuf == 3;
+    uint8_t* stg = smem + g.stg_off + (size_t)ge * nbuf * kTsSlice;
+    const uint32_t my_row = smem_u32(stg) + (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)row & 7u;
+    const uint32_t aff = smem_u32(s_scale);
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ge * BN;
+
+    auto coords = [&](int tile, int& n_base, int& w0, int& h0, int& img0) {
+      const int m_tile = tile / g.n_tiles;
+      n_base = (tile - m_tile * g.n_tiles) * BN;
+      const int tn = m_tile / tiles_hw;
+      const int rem = m_tile - tn * tiles_hw;
+      const int th = rem / sg.tiles_w;
+      img0 = tn * sg.tn_b;
+      h0 = th * sg.th_b;
+      w0 = (rem - th * sg.tiles_w) * sg.tw_b;
+    };
+    // leader only: make staging buffer (s % nbuf) reusable (its last TMA store has finished reading it) and start
+    // the residual load of slice s into it
+    auto prepare = [&](uint32_t s, int c0, int w0, int h0, int img0) {
+      bulk_wait_group_read<1>();
+      if (g.has_res) {
+        const uint32_t b = s % nbuf;
+        mbar_arrive_expect_tx(&ctl->res_full[ge][b], (uint32_t)kTsSlice);
+        tma_load_4d(stg + (size_t)b * kTsSlice, &tm_res, &ctl->res_full[ge][b], c0, w0, h0, img0 % g.res_imgs);
+      }
+    };
+
+    uint32_t sl = 0;   // slices this group has processed
+    const int first = (int)blockIdx.x + (int)ge * (int)gridDim.x;
+    const int tstep = 2 * (int)gridDim.x;
+    if (prefetch && leader && first < total_tiles) {
+      int nb, w0, h0, i0;
+      coords(first, nb, w0, h0, i0);
+      prepare(0, nb, w0, h0, i0);
+    }
+    uint32_t git = 0;   // tiles this group has processed: accumulator phase
+    for (int tile = first; tile < total_tiles; tile += tstep, ++git) {
+      int n_base, w0, h0, img0;
+      coords(tile, n_base, w0, h0, img0);
+#pragma unroll 1
+      for (int j = 0; j < kSlices; ++j, ++sl) {
+        const uint32_t b = sl % nbuf;
+        const uint32_t buf_addr = my_row + b * (uint32_t)kTsSlice;
+        if (leader) {
+          if (!prefetch) {
+            prepare(sl, n_base + j * 32, w0, h0, img0);
+          } else if (j + 1 < kSlices) {
+            prepare(sl + 1, n_base + (j + 1) * 32, w0, h0, img0);
+          } else if (tile + tstep < total_tiles) {
+            int nb2, w2, h2, i2;
+            coords(tile + tstep, nb2, w2, h2, i2);
+            prepare(sl + 1, nb2, w2, h2, i2);
+          }
+        }
+        if (j == 0) {
+          mbar_wait(&ctl->tmem_full[ge], git & 1);
+          tc_fence_after_sync();
+        }
+        named_bar_sync(1 + (int)ge, 128);   // the staging buffer of this slice is free
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + j * 32, v);
+        tmem_ld_wait();
+        if (j == kSlices - 1) {   // accumulator buffer drained: the MMA warp may start the group's next tile
+          tc_fence_before_sync();
+          mbar_arrive(&ctl->tmem_empty[ge]);
+        }
+        float4 o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          o[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                             __uint_as_float(v[4 * k + 3]));
+        if (g.scale != nullptr) {
+          const uint32_t a0 = aff + (uint32_t)(n_base + j * 32) * 4u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 sc = lds128(a0 + k * 16), sh = lds128(a0 + (uint32_t)g.cout * 4u + k * 16);
+            o[k].x = fmaf(o[k].x, sc.x, sh.x); o[k].y = fmaf(o[k].y, sc.y, sh.y);
+            o[k].z = fmaf(o[k].z, sc.z, sh.z); o[k].w = fmaf(o[k].w, sc.w, sh.w);
+          }
+        }
+        if (g.has_res) {
+          mbar_wait(&ctl->res_full[ge][b], (sl / nbuf) & 1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 rv = lds128(buf_addr + (((uint32_t)k ^ sw) << 4));
+            o[k].x += rv.x; o[k].y += rv.y; o[k].z += rv.z; o[k].w += rv.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sts128(buf_addr + (((uint32_t)k ^ sw) << 4), o[k]);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + (int)ge, 128);
+        if (leader) {
+          tma_store_4d(&tm_out, stg + (size_t)b * kTsSlice, n_base + j * 32, w0, h0, img0);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (leader) bulk_wait_group_all();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Weight gradient of the spike convolution:  dW[co][(tap, ci)] += sum_pixels gy[p][co] * s[p*stride + tap - pad][ci]
 // The contraction runs over PIXELS, i.e. over the rows of both operands, so both are fed to the tensor
 // core as MN-major tiles: A = gy tile [128 pixels x 128 co] (bf16 hi [+ lo], 4-D TMA boxes in the tile's
@@ -946,6 +1352,31 @@ int ecsy_tensor_map_bf16_nhwc(const void* ptr, int imgs, int H, int W, int C, in
   return ECSY_OK;
 }
 
+// 4-D fp32 NHWC [imgs][H][W][C] tensor map with a {32 floats, tw, th, tn} box (128-byte rows), 128-byte swizzle:
+// the staging slices of the TMA-store epilogue.
+static int ecsy_tensor_map_f32_nhwc(const void* ptr, int imgs, int H, int W, int C, int tn, int th, int tw,
+                                    CUtensorMap* out) {
+  ECSY_CHECK_ARG(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && C % 32 == 0, "f32 nhwc tensor map: alignment");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    ecsy_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECSY_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)imgs};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ecsy_set_error("cuTensorMapEncodeTiled(f32 4d) failed with %d (imgs=%d H=%d W=%d C=%d box=%d,%d,%d)", (int)r, imgs, H,
+                   W, C, tn, th, tw);
+    return ECSY_ERR_CUDA;
+  }
+  return ECSY_OK;
+}
+
 namespace {
 
 constexpr int kSmemLimit = 227 * 1024;
@@ -1042,6 +1473,51 @@ int ecsy_pick_bn(int cout, int splits) {
 }
 
 // Spike convolution: out[imgs][Ho][Wo][Cout] = conv(spikes, W) (*scale + shift) (+ residual)
+namespace {
+template <int BN, int B_SPLIT>
+int launch_ts(const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres, TsArgs g, const SpikeGeom& sg,
+              cudaStream_t st) {
+  auto kern = k_spike_conv_ts<BN, B_SPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr = true;
+  }
+  constexpr int stage_bytes = B_SPLIT * BN * 128;
+  const int aff_bytes = (2 * g.cout * 4 + 127) & ~127;
+  const int fixed = 1024 + aff_bytes + (int)sizeof(TsCtl) + 128;
+  g.nbuf = g.has_res ? 3 : 2;
+  int stages = (kSmemLimit - fixed - 2 * g.nbuf * kTsSlice) / stage_bytes;
+  if (stages < 4 && g.nbuf == 3) {   // split-weight mode: the wider weight ring matters more than the residual prefetch
+    g.nbuf = 2;
+    stages = (kSmemLimit - fixed - 2 * g.nbuf * kTsSlice) / stage_bytes;
+  }
+  const int tmem_stages = (512 - 2 * BN) / 32;
+  // all weight K blocks resident (n_tiles == 1: one weight panel for every tile of the CTA)?
+  static const bool allow_res = getenv("ECSY_TS_RESIDENT") == nullptr || getenv("ECSY_TS_RESIDENT")[0] != '0';
+  g.resident = (allow_res && g.n_tiles == 1 && g.kb_total >= 4 && g.kb_total <= stages && g.kb_total <= tmem_stages &&
+                g.kb_total <= kTsMaxStages) ? 1 : 0;
+  if (g.resident) stages = g.kb_total;
+  if (stages > tmem_stages) stages = tmem_stages;
+  if (stages > 8) stages = g.resident ? stages : 8;
+  if (stages < 2) {
+    ecsy_set_error("spike_conv_ts: shared memory budget allows only %d stage(s)", stages);
+    return ECSY_ERR_UNSUPPORTED;
+  }
+  g.stages = stages;
+  g.stg_off = (uint32_t)stages * stage_bytes;                       // multiples of 8 KB: 1024-aligned
+  g.aff_off = g.stg_off + 2u * (uint32_t)g.nbuf * kTsSlice;
+  g.ctl_off = g.aff_off + (uint32_t)aff_bytes;
+  const int smem = 1024 + (int)g.ctl_off + (int)sizeof(TsCtl) + 64;
+  int grid = g.m_tiles * g.n_tiles;
+  const int sms = ecsy_num_sms();
+  if (grid > sms) grid = sms;
+  kern<<<grid, kTsThreads, smem, st>>>(tb, tout, tres, g, sg);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+}  // namespace
+
 int ecsy_pick_bn_ts(int cout) {
   // TS mode: the A ring shares the 512 TMEM columns with the two accumulators -> at most 128 columns per tile
   for (int bn = 128; bn >= 64; bn >>= 1)
@@ -1081,6 +1557,24 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout, 0};
   const int patch_bytes = sg.PP * Cw * 4;
   if (ts) {
+    // TMA-store epilogue unless a T-broadcast residual would straddle the wrap inside one tile box
+    const int64_t rimgs = residual ? res_imgs : imgs;
+    const bool tma_epi = ts != 2 && (residual == nullptr || rimgs == imgs || rimgs % sg.tn_b == 0);
+    if (tma_epi) {
+      CUtensorMap tout, tres{};
+      rc = ecsy_tensor_map_f32_nhwc(out, imgs, Ho, Wo, Cout, sg.tn_b, sg.th_b, sg.tw_b, &tout);
+      if (rc) return rc;
+      if (residual) {
+        rc = ecsy_tensor_map_f32_nhwc(residual, (int)rimgs, Ho, Wo, Cout, sg.tn_b, sg.th_b, sg.tw_b, &tres);
+        if (rc) return rc;
+      }
+      TsArgs ta{};
+      ta.m_tiles = g.m_tiles; ta.n_tiles = g.n_tiles; ta.kb_total = g.kb_total;
+      ta.has_res = residual ? 1 : 0; ta.res_imgs = (int)rimgs; ta.cout = Cout;
+      ta.scale = scale; ta.shift = shift;
+      if (BN == 64) return splits == 1 ? launch_ts<64, 1>(tb, tout, tres, ta, sg, st) : launch_ts<64, 2>(tb, tout, tres, ta, sg, st);
+      return splits == 1 ? launch_ts<128, 1>(tb, tout, tres, ta, sg, st) : launch_ts<128, 2>(tb, tout, tres, ta, sg, st);
+    }
     if (splits == 1) return launch_bn<kASpikesT, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
     return launch_bn<kASpikesT, 1, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
   }

@@ -22,7 +22,8 @@ thresh = 0.5
 lens = 0.5
 decay = 0.25
 
-_state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "1") != "0"}
+# conv_ts: "auto" (measured dispatch rule), "all" (wherever supported) or "off"
+_state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto")}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
@@ -75,13 +76,29 @@ def get_splits() -> int:
     return _state["splits"]
 
 
-def set_conv_ts(on: bool) -> None:
-    """Spike convs stage their A operand in tensor memory (tcgen05.mma TS form) when on (default)."""
-    _state["conv_ts"] = bool(on)
+def set_conv_ts(mode) -> None:
+    """Where spike convs stage their A operand: "auto" = tensor memory (tcgen05.mma TS form) except on the wide
+    layers where 256-column tiles with a shared-memory operand measured faster; "all" / True = tensor memory
+    wherever supported; "off" / False = shared memory."""
+    if mode is True:
+        mode = "all"
+    elif mode is False:
+        mode = "off"
+    if mode not in ("auto", "all", "off"):
+        raise ValueError(mode)
+    _state["conv_ts"] = mode
 
 
 def conv_ts_enabled() -> bool:
-    return _state["conv_ts"]
+    return _state["conv_ts"] != "off"
+
+
+def _use_ts(ci: int, co: int, splits: int) -> bool:
+    m = _state["conv_ts"]
+    if m == "off":
+        return False
+    L = _cabi.lib()
+    return bool(L.ecsy_spike_conv_ts_supported(ci, co) if m == "all" else L.ecsy_spike_conv_prefers_ts(ci, co, splits))
 
 
 def _st() -> int:
@@ -241,7 +258,7 @@ def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, 
     b = bias.detach().float().contiguous() if bias is not None else None
     cw = ConvW(packed, sw, b, Co, Cig * groups, kh, stride, pad, groups, splits)
     cw.dense_groups = bool(densify and groups > 1)
-    if (packed is not None and conv_ts_enabled() and bias is None and (groups == 1 or densify)
+    if (packed is not None and bias is None and (groups == 1 or densify)
             and _cabi.lib().ecsy_spike_conv_ts_supported(Cig * groups, Co)):
         cw.packed_ts = pack_spike_conv_weight(dense, splits)
     return cw
@@ -446,7 +463,7 @@ def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[A
     if residual is not None:
         assert (residual.N, residual.H, residual.W, residual.C) == (N, Ho, Wo, w.co), "residual shape"
     flops["spike_conv"] += 2.0 * T * N * Ho * Wo * w.co * s.C * w.k * w.k
-    ts = w.packed_ts is not None and conv_ts_enabled()
+    ts = w.packed_ts is not None and _use_ts(s.C, w.co, w.splits)
     L = _cabi.lib()
     with _timed("spike_conv", 1):
         _cabi.check((L.ecsy_spike_conv_ts_fwd if ts else L.ecsy_spike_conv_fwd)(

@@ -82,6 +82,7 @@ int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed, int splits
 int ecsy_pack_spike_conv_weight(const float* w, void* out_bf16, int Co, int Ci, int kh, int kw, int splits,
                                 void* stream);
 int ecsy_spike_conv_ts_supported(int Cin, int Cout);
+int ecsy_spike_conv_prefers_ts(int Cin, int Cout, int splits);   /* measured dispatch rule (wide layers keep smem A) */
 int ecsy_spike_conv_ts_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out, const float* scale,
                            const float* shift, const float* residual, int64_t res_imgs, int64_t imgs, int H, int W,
                            int Cin, int Cout, int k, int stride, int pad, void* stream);

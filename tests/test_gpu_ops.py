@@ -56,10 +56,10 @@ def test_spike_conv(name, mode, tol, ts):
         resb = res[:1].cuda().expand(res.shape[0], -1, -1, -1, -1)
         out3 = F.spike_conv(sp, w, None, None, F.Act.from_ref(resb)).to_ref().cpu()
         assert rel_l2(out3, gold["out"] + res[:1]) < tol
-        assert (w.packed_ts is not None) == (ts and spec["ci"] % 64 == 0 and spec["co"] % 64 == 0)
+        assert (w.packed_ts is not None) == (spec["ci"] % 64 == 0 and spec["co"] % 64 == 0)
     finally:
         F.set_precision("parity")
-        F.set_conv_ts(True)
+        F.set_conv_ts("auto")
 
 
 @pytest.mark.parametrize("mode", ["parity", "fast"])
@@ -92,9 +92,19 @@ def test_spike_conv_tmem_operand(ci, co, k, s, H, W, N, T, mode):
         ref = ref.reshape(T, N, co, *ref.shape[-2:]).float()
         assert rel_l2(out_ts, ref) < 2e-5
         assert rel_l2(out_ts, out_ss) < 1e-5
+        # folded tdBN affine + full / T-broadcast residual through the TMA-store epilogue
+        F.set_conv_ts(True)
+        sc = torch.rand(co, generator=g) + 0.5
+        sh = torch.rand(co, generator=g) - 0.5
+        res = torch.randn(*ref.shape, generator=g)
+        out2 = F.spike_conv(sp, cw, sc.cuda(), sh.cuda(), F.Act.from_ref(res.cuda())).to_ref().cpu()
+        assert rel_l2(out2, ref * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1) + res) < 2e-5
+        resb = res[:1].cuda().expand(T, -1, -1, -1, -1)
+        out3 = F.spike_conv(sp, cw, None, None, F.Act.from_ref(resb)).to_ref().cpu()
+        assert rel_l2(out3, ref + res[:1]) < 2e-5
     finally:
         F.set_precision("parity")
-        F.set_conv_ts(True)
+        F.set_conv_ts("auto")
 
 
 @pytest.mark.parametrize("name", [n for n, s in S.CONV_CASES.items() if not s["spikes"]])

@@ -12,10 +12,10 @@ ap.add_argument("--mode", default="fast")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--only", type=int, default=-1)
 ap.add_argument("--N", type=int, default=64)
-ap.add_argument("--ts", type=int, default=1, help="1: spike operand in tensor memory, 0: in shared memory")
+ap.add_argument("--ts", default="auto", help="auto | all (spike operand in tensor memory) | off (shared memory)")
 args = ap.parse_args()
 F.set_precision(args.mode)
-F.set_conv_ts(bool(args.ts))
+F.set_conv_ts(args.ts)
 T, N = 4, args.N
 # (cin, cout, k, stride, H)
 SHAPES = [(64, 64, 3, 1, 160), (128, 128, 3, 1, 80), (256, 256, 3, 1, 40), (512, 512, 3, 1, 20),
