@@ -23,7 +23,8 @@ lens = 0.5
 decay = 0.25
 
 # conv_ts: "auto" (measured dispatch rule), "all" (wherever supported) or "off"
-_state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto")}
+_state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
+          "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1"}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
@@ -87,6 +88,12 @@ def set_conv_ts(mode) -> None:
     if mode not in ("auto", "all", "off"):
         raise ValueError(mode)
     _state["conv_ts"] = mode
+
+
+def set_lif_fused(on: bool) -> None:
+    """Fast mode, C == 64: run the ECS-LIF forward as ONE kernel with all T steps on chip.  Parity-green but
+    measured slower than the per-timestep pipeline so far (csrc/lif_fused.cu header), hence off by default."""
+    _state["lif_fused"] = bool(on)
 
 
 def conv_ts_enabled() -> bool:
@@ -271,13 +278,21 @@ class LifW:
     pw: torch.Tensor     # [splits, C, C] bf16
     pw_b: torch.Tensor   # [C]
     splits: int
+    w_eff: Optional[torch.Tensor] = None    # fused kernel: folded 3x3 spread weight (ecsy_pack_spike_conv_weight form)
+    bconst: Optional[torch.Tensor] = None   # fused kernel: pw @ dw_b + pw_b
 
 
 def make_lif_w(dw_w, dw_b, pw_w, pw_b) -> LifW:
     splits = get_splits()
     C = dw_w.shape[0]
-    return LifW(dw_w.detach().float().reshape(C, 9).t().contiguous(), dw_b.detach().float().contiguous(),
-                pack_conv_weight(pw_w, splits), pw_b.detach().float().contiguous(), splits)
+    w = LifW(dw_w.detach().float().reshape(C, 9).t().contiguous(), dw_b.detach().float().contiguous(),
+             pack_conv_weight(pw_w, splits), pw_b.detach().float().contiguous(), splits)
+    if splits == 1 and C == 64:
+        pw2 = pw_w.detach().float().reshape(C, C)
+        w_eff = pw2.reshape(C, C, 1, 1) * dw_w.detach().float().reshape(1, C, 3, 3)
+        w.w_eff = pack_spike_conv_weight(w_eff, 1)
+        w.bconst = (pw2 @ dw_b.detach().float() + pw_b.detach().float()).contiguous()
+    return w
 
 
 # ------------------------------------------------------------------------------------------------
@@ -290,6 +305,16 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
     bits = torch.empty(T, N, H, W, C // 32, device=dev, dtype=torch.int32)
+    if (not save_mem and w is not None and w.w_eff is not None and _state["lif_fused"]
+            and _cabi.lib().ecsy_lif_ecs_fused_supported(T, C)):
+        sc, sh = affine if affine is not None else (None, None)
+        flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
+        with _timed("lif_ecs", 1):
+            _cabi.check(_cabi.lib().ecsy_lif_ecs_fused_fwd(
+                _p(x.data), x.tstride, _p(sc), _p(sh), _p(w.w_eff), _p(w.bconst), _p(bits), T, N, H, W, C,
+                float(thresh), float(decay), float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _st()),
+                "lif_ecs_fused_fwd")
+        return Spikes(bits, C)
     mem = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
     ecs = torch.empty(max(T - 1, 1), N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
     L = _cabi.lib()

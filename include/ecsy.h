@@ -57,6 +57,15 @@ int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, c
 /* ---- mem_update(act=True).forward: the SiLU "analog spike" neuron of class Conv (models/common.py:362-375,
  * 252-283).  out: [T][N][H][W][C] fp32 = silu(mem_t).  inplace != 0 reproduces the reference models, where
  * initialize_weights() makes nn.SiLU in-place so that mem_old holds silu(mem) (utils/torch_utils.py:165-166). */
+/* Fused forward of the same neuron for C == 64 (fast / single-plane mode): every timestep of a 22x22 pixel tile runs
+ * inside one CTA, membrane and ECS trace stay in tensor memory, only x is read and only spike bits are written.
+ * w_eff_ts: ecsy_pack_spike_conv_weight of W_eff[co][ci][ky][kx] = pw[co][ci] * dw[ci][ky][kx] (splits = 1);
+ * bconst[co] = sum_ci pw[co][ci] * dw_b[ci] + pw_b[co].  No workspace. */
+int ecsy_lif_ecs_fused_supported(int T, int C);
+int ecsy_lif_ecs_fused_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
+                           const void* w_eff_ts, const float* bconst, uint32_t* spikes, int T, int64_t N, int H, int W,
+                           int C, float thresh, float decay, float alpha, float beta, float kappa, void* stream);
+
 size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
 int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                       const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b, int splits,

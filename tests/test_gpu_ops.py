@@ -241,6 +241,47 @@ def test_lif_affine_and_broadcast():
     assert agree(gotb, wantb) > 0.999
 
 
+@pytest.mark.parametrize("T,N,H,W", [(4, 3, 37, 45), (2, 2, 23, 20), (5, 1, 30, 16), (8, 1, 12, 12), (4, 1, 160, 160)])
+def test_lif_ecs_fused(T, N, H, W):
+    """Fused all-T-on-chip ECS-LIF (C = 64, fast mode): several tiles per image, ragged edges, every halo width;
+    against the CPU oracle and against the per-timestep pipeline; with folded tdBN and a T-broadcast input."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision("fast")
+    try:
+        inp = S.lif_inputs(dict(T=T, N=N, C=64, H=H, W=W, seed=900 + T + H))
+        w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+        assert w.w_eff is not None
+        x = inp["x"]
+        a = F.Act.from_ref(x.cuda())
+        F.set_lif_fused(True)
+        n0 = F.launches["n"]
+        got = F.lif_ecs(a, w).to_act().to_ref().cpu()
+        assert F.launches["n"] - n0 == 1, "the fused kernel must be the path that ran"
+        F.set_lif_fused(False)
+        unf = F.lif_ecs(a, w).to_act().to_ref().cpu()
+        want = O.ecs_lif(x, inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
+        assert agree(got, want) >= 0.995, agree(got, want)
+        assert agree(got, unf) >= 0.995, agree(got, unf)
+        assert agree(got[0], want[0]) == 1.0          # step 0 has no ECS term: exact
+        assert abs(float(got.mean()) - float(want.mean())) < 3e-3
+        if H <= 64:
+            F.set_lif_fused(True)
+            sc = torch.rand(64, generator=S.gen(3)) + 0.5
+            sh = torch.rand(64, generator=S.gen(4)) * 0.2
+            got2 = F.lif_ecs(a, w, (sc.cuda(), sh.cuda())).to_act().to_ref().cpu()
+            want2 = O.ecs_lif(x * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1), inp["dw_w"], inp["dw_b"],
+                              inp["pw_w"], inp["pw_b"])
+            assert agree(got2, want2) >= 0.995
+            xb = x[:1].expand(T, -1, -1, -1, -1)
+            gotb = F.lif_ecs(F.Act.from_ref(xb.cuda()), w).to_act().to_ref().cpu()
+            wantb = O.ecs_lif(xb.contiguous(), inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
+            assert agree(gotb, wantb) >= 0.995
+    finally:
+        F.set_precision("parity")
+        F.set_lif_fused(False)
+
+
 @pytest.mark.parametrize("ci,co,k,H,W,N,T", [(64, 128, 3, 10, 12, 2, 2), (128, 64, 1, 7, 9, 1, 3), (192, 256, 3, 20, 20, 3, 1)])
 @pytest.mark.parametrize("mode,tol", [("parity", 2e-5), ("fast", 8e-3)])
 def test_real_conv_implicit(ci, co, k, H, W, N, T, mode, tol):
