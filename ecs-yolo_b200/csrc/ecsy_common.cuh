@@ -232,6 +232,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Index arithmetic of the grid-stride streaming kernels: a 64-bit div/mod by a run-time divisor costs ~100
+// instructions; every tensor of the hot path has fewer than 2^32 float4 items, so the kernels test once (warp
+// uniform) and divide in 32 bits.
+__device__ __forceinline__ uint32_t mod_u(int64_t i, uint32_t d, bool small) {
+  return small ? static_cast<uint32_t>(i) % d : static_cast<uint32_t>(i % d);
+}
+__device__ __forceinline__ int64_t div_u(int64_t i, uint32_t d, bool small) {
+  return small ? static_cast<int64_t>(static_cast<uint32_t>(i) / d) : i / d;
+}
+
 // streaming 128-bit global accesses
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;

@@ -75,12 +75,13 @@ __global__ void k_lif_first(const float* __restrict__ x, const float* __restrict
   // always active together; the shuffles below only exchange data inside such 8-lane groups.
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4_round = (n4 + 31) & ~int64_t(31);
+  const bool small = n4_round < (int64_t(1) << 32);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4_round; i += stride) {
     const bool ok = i < n4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) v = ecsy::ldg_stream(reinterpret_cast<const float4*>(x) + i);
     if (scale != nullptr) {
-      int c = static_cast<int>((i * 4) % C);
+      int c = static_cast<int>(ecsy::mod_u(i, (uint32_t)(C >> 2), small) * 4u);
       float4 s = *reinterpret_cast<const float4*>(scale + c);
       float4 b = *reinterpret_cast<const float4*>(shift + c);
       v.x = ecsy::add_rn(ecsy::mul_rn(v.x, s.x), b.x);
@@ -129,12 +130,13 @@ __device__ __forceinline__ float tanh_fast(float v) {
 template <bool HALF>
 __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = n4_round < (int64_t(1) << 32);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4_round; i += stride) {
     const bool ok = i < n4;
     uint32_t nib = 0;
     const int sub = threadIdx.x & 7;
     if (ok) {
-      const int c = static_cast<int>((i * 4) % C);
+      const int c = static_cast<int>(ecsy::mod_u(i, (uint32_t)(C >> 2), small) * 4u);
       float4 xv = ecsy::ldg_stream(reinterpret_cast<const float4*>(p.x_next) + i);
       if (p.in_scale != nullptr) {
         const float4 s = *reinterpret_cast<const float4*>(p.in_scale + c);
@@ -489,16 +491,17 @@ __global__ void k_affine_add(const float* __restrict__ a, int64_t a_mod, const f
                              float* __restrict__ out, int64_t imgs, int64_t hwc4, int C) {
   const int64_t total = imgs * hwc4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = total < (int64_t(1) << 32) && hwc4 < (int64_t(1) << 32);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t img = i / hwc4, rem = i - img * hwc4;
-    const int c = static_cast<int>((rem * 4) % C);
-    float4 v = reinterpret_cast<const float4*>(a)[(img % a_mod) * hwc4 + rem];
+    const int64_t img = ecsy::div_u(i, (uint32_t)hwc4, small), rem = i - img * hwc4;
+    const int c = static_cast<int>(ecsy::mod_u(rem, (uint32_t)(C >> 2), small) * 4u);
+    float4 v = reinterpret_cast<const float4*>(a)[ecsy::mod_u(img, (uint32_t)a_mod, small) * hwc4 + rem];
     if (sa != nullptr) {
       float4 s = *reinterpret_cast<const float4*>(sa + c), t = *reinterpret_cast<const float4*>(ba + c);
       v.x = v.x * s.x + t.x; v.y = v.y * s.y + t.y; v.z = v.z * s.z + t.z; v.w = v.w * s.w + t.w;
     }
     if (b != nullptr) {
-      float4 u = reinterpret_cast<const float4*>(b)[(img % b_mod) * hwc4 + rem];
+      float4 u = reinterpret_cast<const float4*>(b)[ecsy::mod_u(img, (uint32_t)b_mod, small) * hwc4 + rem];
       if (sb != nullptr) {
         float4 s = *reinterpret_cast<const float4*>(sb + c), t = *reinterpret_cast<const float4*>(bb + c);
         u.x = u.x * s.x + t.x; u.y = u.y * s.y + t.y; u.z = u.z * s.z + t.z; u.w = u.w * s.w + t.w;
@@ -520,14 +523,15 @@ __global__ void k_resample(const float* __restrict__ in, int64_t in_mod, const f
   const int c4 = C >> 2;
   const int64_t total = imgs * Ho * Wo * c4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = total < (int64_t(1) << 32);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int q = static_cast<int>(i % c4);
-    int64_t p = i / c4;
-    const int wo = static_cast<int>(p % Wo);
-    p /= Wo;
-    const int ho = static_cast<int>(p % Ho);
-    const int64_t img = p / Ho;
-    const float* src = in + ((img % in_mod) * Hi * Wi) * (int64_t)C + q * 4;
+    const int q = static_cast<int>(ecsy::mod_u(i, (uint32_t)c4, small));
+    int64_t p = ecsy::div_u(i, (uint32_t)c4, small);
+    const int wo = static_cast<int>(ecsy::mod_u(p, (uint32_t)Wo, small));
+    p = ecsy::div_u(p, (uint32_t)Wo, small);
+    const int ho = static_cast<int>(ecsy::mod_u(p, (uint32_t)Ho, small));
+    const int64_t img = ecsy::div_u(p, (uint32_t)Ho, small);
+    const float* src = in + ((int64_t)ecsy::mod_u(img, (uint32_t)in_mod, small) * Hi * Wi) * (int64_t)C + q * 4;
     float4 v;
     if (pool > 1) {
       v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);

@@ -78,13 +78,19 @@ __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __re
   const int64_t p0 = blockIdx.x * per_block;
   const int64_t p1 = p0 + per_block < pixels ? p0 + per_block : pixels;
   const int Cw = C >> 5;
+  // (h, w) of the thread's pixel advance incrementally (64-bit div/mod per pixel was most of this kernel's time)
+  int w = 0, h = 0;
+  if (p0 + ty < p1) {
+    const int64_t pp = p0 + ty;
+    w = static_cast<int>(pp % W);
+    h = static_cast<int>((pp / W) % H);
+  }
+  const int dw_ = nty % W, dh_ = (nty / W) % H;
   for (int64_t p = p0 + ty; p < p1; p += nty) {
     const float4 a = reinterpret_cast<const float4*>(ge + p * C)[tq];
     const float4 b = reinterpret_cast<const float4*>(g1 + p * C)[tq];
     s[0][0] += a.x; s[0][1] += a.y; s[0][2] += a.z; s[0][3] += a.w;
     s[1][0] += b.x; s[1][1] += b.y; s[1][2] += b.z; s[1][3] += b.w;
-    const int w = static_cast<int>(p % W);
-    const int h = static_cast<int>((p / W) % H);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int hh = h + ky - 1;
@@ -102,6 +108,10 @@ __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __re
         if (nib & 8u) s[t][3] += b.w;
       }
     }
+    w += dw_;
+    h += dh_;
+    if (w >= W) { w -= W; ++h; }
+    if (h >= H) h -= H;
   }
   // block reduction over the ty rows in shared memory, then one double atomic per (quantity, channel)
   extern __shared__ float sred[];  // [nty][11][C]
@@ -138,14 +148,15 @@ __global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __re
   const int c4 = C >> 2;
   const int64_t total = (int64_t)N * H * W * c4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = total < (int64_t(1) << 32);
   const float inv = 1.0f / (2.0f * lens);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int q = static_cast<int>(i % c4);
-    const int64_t p = i / c4;
+    const int q = static_cast<int>(ecsy::mod_u(i, (uint32_t)c4, small));
+    const int64_t p = ecsy::div_u(i, (uint32_t)c4, small);
     float4 gs = reinterpret_cast<const float4*>(gout)[i];
     if (g1 != nullptr) {
-      const int w = static_cast<int>(p % W);
-      const int h = static_cast<int>((p / W) % H);
+      const int w = static_cast<int>(ecsy::mod_u(p, (uint32_t)W, small));
+      const int h = static_cast<int>(ecsy::mod_u(ecsy::div_u(p, (uint32_t)W, small), (uint32_t)H, small));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -205,8 +216,9 @@ __global__ void k_silu_bwd_reduce(const float* __restrict__ ge, const float* __r
     const float4 b = reinterpret_cast<const float4*>(g1 + p * C)[tq];
     s[0][0] += a.x; s[0][1] += a.y; s[0][2] += a.z; s[0][3] += a.w;
     s[1][0] += b.x; s[1][1] += b.y; s[1][2] += b.z; s[1][3] += b.w;
-    const int w = static_cast<int>(p % W);
-    const int h = static_cast<int>((p / W) % H);
+    const bool small = pixels < (int64_t(1) << 32);
+    const int w = static_cast<int>(ecsy::mod_u(p, (uint32_t)W, small));
+    const int h = static_cast<int>(ecsy::mod_u(ecsy::div_u(p, (uint32_t)W, small), (uint32_t)H, small));
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int hh = h + ky - 1;
@@ -246,13 +258,14 @@ __global__ void k_silu_bwd_post(const float* __restrict__ gout, const float* __r
   const int c4 = C >> 2;
   const int64_t total = (int64_t)N * H * W * c4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = total < (int64_t(1) << 32);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int q = static_cast<int>(i % c4);
-    const int64_t p = i / c4;
+    const int q = static_cast<int>(ecsy::mod_u(i, (uint32_t)c4, small));
+    const int64_t p = ecsy::div_u(i, (uint32_t)c4, small);
     float4 go = reinterpret_cast<const float4*>(gout)[i];
     if (g1 != nullptr) {
-      const int w = static_cast<int>(p % W);
-      const int h = static_cast<int>((p / W) % H);
+      const int w = static_cast<int>(ecsy::mod_u(p, (uint32_t)W, small));
+      const int h = static_cast<int>(ecsy::mod_u(ecsy::div_u(p, (uint32_t)W, small), (uint32_t)H, small));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -295,9 +308,14 @@ __global__ void k_colsum2(const float* __restrict__ g, const float* __restrict__
   double sg[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
   float fg[4] = {0, 0, 0, 0}, fx[4] = {0, 0, 0, 0};
   int cnt = 0;
+  // row of x (a T-broadcast x repeats every x_rows rows) tracked incrementally: no 64-bit modulo per row
+  int64_t xr = r0 + ty < r1 ? (r0 + ty) % x_rows : 0;
+  const int64_t xstep = nty % x_rows;
   for (int64_t r = r0 + ty; r < r1; r += nty) {
     const float4 a = reinterpret_cast<const float4*>(g + r * C)[tq];
-    const float4 b = reinterpret_cast<const float4*>(x + (r % x_rows) * C)[tq];
+    const float4 b = reinterpret_cast<const float4*>(x + xr * C)[tq];
+    xr += xstep;
+    if (xr >= x_rows) xr -= x_rows;
     fg[0] += a.x; fg[1] += a.y; fg[2] += a.z; fg[3] += a.w;
     fx[0] += a.x * b.x; fx[1] += a.y * b.y; fx[2] += a.z * b.z; fx[3] += a.w * b.w;
     if (++cnt == 32) {
