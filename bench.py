@@ -91,19 +91,31 @@ def load_cfg(name):
     return yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", name + ".yaml")))
 
 
-def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads):
+def event_frames(n, T, img, gen):
+    """Gen1-style event frames (g1-resnet/utils/give_g1_data.py:550-565): ternary {0, 127, 255}/255 frames
+    on a grey background, ~3 % event pixels, three identical channels -> [T, n, 3, img, img] for _forward_once."""
+    u = torch.rand(n, T, 1, img, img, generator=gen)
+    f = torch.full_like(u, 127.0 / 255.0)
+    f[u < 0.015] = 0.0
+    f[u > 0.985] = 1.0
+    return f.expand(-1, -1, 3, -1, -1).permute(1, 0, 2, 3, 4).contiguous()
+
+
+def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, events=False):
     """Times the oracle port of the reference's CPU path (torch fp32, all host threads) on a bounded
     sample of the same workload: `sample_imgs` images per step."""
     import ecs_oracle as O
     torch.set_num_threads(threads)
     cfg = load_cfg(model_name)
+    if events:
+        cfg["nc"] = 2
     sd = O.init_state_dict(cfg, T, seed=0)
     stride = O.detect_strides(cfg)
     for k in sd:
         if k.endswith("anchors"):
             sd[k] = sd[k] / stride.view(-1, 1, 1)
     g = torch.Generator().manual_seed(0)
-    x = torch.rand(sample_imgs, 3, img, img, generator=g)
+    x = event_frames(sample_imgs, T, img, g) if events else torch.rand(sample_imgs, 3, img, img, generator=g)
     with torch.no_grad():
         O.BN_MOMENTUM = 1.0
         O.forward(cfg, sd, x, T, True, stride=stride)   # calibration pass (train-mode tdBN) == warm-up 0
@@ -127,7 +139,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
                                                         gradient_as_bucket_view=True)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.937, nesterov=True)
     with torch.no_grad():
-        probe = model(x[:1])
+        probe = model(x[:, :1] if args.events else x[:1])
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     tgt = [torch.randn(args.batch, *o.shape[1:], device="cuda", generator=g) for o in probe]
 
@@ -224,6 +236,9 @@ def main():
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs under ncu may lower this")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--cpu-sample", type=int, default=1, help="images per CPU step")
+    ap.add_argument("--events", action="store_true",
+                    help="BASELINE config 4: Gen1-style event frames [T,N,3,H,W] straight into _forward_once, nc=2 "
+                         "(use with --T 5)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()
@@ -233,12 +248,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
     workload = f"EMS-{args.model} SNN-YOLO T={args.T} inference, batch {args.batch}/GPU, synthetic {args.img}x{args.img}"
+    if args.events:
+        workload += " Gen1-style event frames (ternary, nc=2)"
 
     if args.impl == "reference":
         if rank != 0:
             return
         steps = max(args.steps, 1)
-        ips, spstep = cpu_reference(args.model, args.T, args.img, args.cpu_sample, steps, max(args.warmup, 1), threads)
+        ips, spstep = cpu_reference(args.model, args.T, args.img, args.cpu_sample, steps, max(args.warmup, 1), threads,
+                                    args.events)
         line = {"impl": "reference", "metric": "images/s", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -270,9 +288,13 @@ def main():
 
     torch.manual_seed(0)
     is_b = any(row[2] == "DDetect" for row in load_cfg(args.model)["head"])
-    model = (E.yolo_snn.DetectionModel if is_b else E.yolo.Model)(E.cfg_path(args.model)).cuda()
+    model = (E.yolo_snn.DetectionModel if is_b else E.yolo.Model)(E.cfg_path(args.model),
+                                                                  nc=2 if args.events else None).cuda()
     g = torch.Generator().manual_seed(1000 + rank)
-    x_host = torch.rand(args.batch, 3, args.img, args.img, generator=g).pin_memory()
+    if args.events:
+        x_host = event_frames(args.batch, args.T, args.img, g).pin_memory()
+    else:
+        x_host = torch.rand(args.batch, 3, args.img, args.img, generator=g).pin_memory()
     x = x_host.cuda()
 
     if args.mode == "train":
@@ -369,7 +391,8 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": z_host.numel() * 4},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "k_umma_gemm<spikes,conv> (spike implicit-GEMM conv, tcgen05)", "bound": "tensor",
+        "roofline": {"kernel": "k_spike_conv_ts + k_umma_gemm<spikes> (spike implicit-GEMM convs, tcgen05; operand in "
+                               "tensor memory / shared memory)", "bound": "tensor",
                      "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                      "frac": conv_tf / pk["tf_sust"],
                      "traffic": measured_traffic(args.model, args.batch, args.T, args.precision),
@@ -382,7 +405,7 @@ def main():
                                    / (ms_total / args.steps * 1e-3) / 1e12,
     }
     if world == 1 and not args.no_cpu_baseline:
-        ips, _ = cpu_reference(args.model, args.T, args.img, args.cpu_sample, 2, 1, threads)
+        ips, _ = cpu_reference(args.model, args.T, args.img, args.cpu_sample, 2, 1, threads, args.events)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_sample} image(s)/step x 2 steps of the same workload, oracle "
                                           "port (torch fp32 CPU) of the reference forward"}

@@ -11,8 +11,10 @@ import os as _os
 
 from . import _cabi, functional, common, autograd, yolo, yolo_snn, dist  # noqa: F401
 from .functional import set_precision  # noqa: F401
+from .convert import convert  # noqa: F401
+from . import ops  # noqa: F401  (registers torch.ops.ecsy.*)
 
-__all__ = ["common", "yolo", "yolo_snn", "functional", "set_precision", "cfg_path", "build_library"]
+__all__ = ["common", "yolo", "yolo_snn", "functional", "ops", "set_precision", "convert", "cfg_path", "build_library"]
 
 
 def cfg_path(name: str) -> str:

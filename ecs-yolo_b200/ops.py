@@ -1,0 +1,142 @@
+"""PyTorch custom operators (``torch.library``) over the C ABI: ``torch.ops.ecsy.*``.
+
+The drop-in modules (``common.py``) call ``functional`` directly and chain whole blocks in hand-written
+``autograd.Function``s; these operators expose the same kernels as first-class PyTorch ops -- schema, fake
+(meta) implementations for shape inference / export, and an autograd formula for the differentiable unit of the
+path -- so that code outside this package (a converted reference model, ``torch.export``, a custom head) can call the
+B200 kernels without touching ctypes.  Tensors use the internal layout: real activations fp32 NHWC
+``[Tp, N, H, W, C]`` (Tp == T, or 1 for a T-broadcast tensor), spikes bit-packed int32 ``[T, N, H, W, C/32]``.
+CUDA only: there is no CPU kernel behind any of them (the fake implementations only compute shapes).
+
+    bits = torch.ops.ecsy.lif_ecs(x, T, dw_w, dw_b, pw_w, pw_b, scale, shift, 5.0, 0.75, 0.25)
+    y    = torch.ops.ecsy.spike_conv(bits, Cin, weight, scale, shift, residual, stride, pad)
+    y    = torch.ops.ecsy.lif_spike_conv(x, T, dw_w, dw_b, pw_w, pw_b, weight, stride, pad, 5.0, 0.75, 0.25)  # autograd
+    mean, var = torch.ops.ecsy.tdbn_stats(y)
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import functional as F_
+from .functional import Act, Spikes
+
+_wcache: dict = {}
+
+
+def _cached(kind: str, tensors, builder):
+    key = (kind, F_.get_splits(), F_._state["conv_ts"]) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    v = _wcache.get(key)
+    if v is None:
+        if len(_wcache) > 512:
+            _wcache.clear()
+        with torch.no_grad():
+            v = builder()
+        _wcache[key] = v
+    return v
+
+
+def _lif_w(dw_w, dw_b, pw_w, pw_b):
+    return _cached("lif", (dw_w, dw_b, pw_w, pw_b), lambda: F_.make_lif_w(dw_w, dw_b, pw_w, pw_b))
+
+
+def _conv_w(weight, stride, pad):
+    return _cached(f"conv{stride}.{pad}", (weight,), lambda: F_.make_conv_w(weight, None, stride, pad, 1, True, False))
+
+
+def _conv_out(h: int, w: int, k: int, stride: int, pad: int) -> Tuple[int, int]:
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+# ---------------------------------------------------------------------------------------------- lif_ecs
+@torch.library.custom_op("ecsy::lif_ecs", mutates_args=())
+def lif_ecs(x: Tensor, T: int, dw_w: Tensor, dw_b: Tensor, pw_w: Tensor, pw_b: Tensor, scale: Optional[Tensor],
+            shift: Optional[Tensor], ecs_tau: float, alpha: float, beta: float) -> Tensor:
+    """mem_update.forward (models/common.py:252-283) -> bit-packed spikes."""
+    aff = (scale, shift) if scale is not None else None
+    return F_.lif_ecs(Act(x.contiguous(), T), _lif_w(dw_w, dw_b, pw_w, pw_b), aff, ecs_tau, alpha, beta).bits
+
+
+@lif_ecs.register_fake
+def _(x, T, dw_w, dw_b, pw_w, pw_b, scale, shift, ecs_tau, alpha, beta):
+    _, N, H, W, C = x.shape
+    torch._check(C % 64 == 0, lambda: "ecsy::lif_ecs: C must be a multiple of 64")
+    return x.new_empty((T, N, H, W, C // 32), dtype=torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------- spike_conv
+@torch.library.custom_op("ecsy::spike_conv", mutates_args=())
+def spike_conv(bits: Tensor, cin: int, weight: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
+               residual: Optional[Tensor], stride: int, pad: int) -> Tensor:
+    """Snn_Conv2d on spikes (models/common.py:609-624) with folded tdBN affine and shortcut add."""
+    T = bits.shape[0]
+    res = Act(residual.contiguous(), T) if residual is not None else None
+    return F_.spike_conv(Spikes(bits.contiguous(), cin), _conv_w(weight, stride, pad), scale, shift, res).data
+
+
+@spike_conv.register_fake
+def _(bits, cin, weight, scale, shift, residual, stride, pad):
+    T, N, H, W, _ = bits.shape
+    Ho, Wo = _conv_out(H, W, weight.shape[2], stride, pad)
+    return weight.new_empty((T, N, Ho, Wo, weight.shape[0]), dtype=torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------- tdbn_stats
+@torch.library.custom_op("ecsy::tdbn_stats", mutates_args=())
+def tdbn_stats(y: Tensor) -> Tuple[Tensor, Tensor]:
+    """Per-channel mean / biased variance over (T, N, H, W) (models/common.py:668-700)."""
+    return F_.bn_stats(Act(y.contiguous(), y.shape[0]))
+
+
+@tdbn_stats.register_fake
+def _(y):
+    C = y.shape[-1]
+    return y.new_empty((C,)), y.new_empty((C,))
+
+
+# ---------------------------------------------------------------------------------------------- lif -> conv (autograd)
+@torch.library.custom_op("ecsy::lif_spike_conv", mutates_args=())
+def lif_spike_conv(x: Tensor, T: int, dw_w: Tensor, dw_b: Tensor, pw_w: Tensor, pw_b: Tensor, weight: Tensor, stride: int,
+                   pad: int, ecs_tau: float, alpha: float, beta: float) -> Tuple[Tensor, Tensor]:
+    """The differentiable unit of the path: ECS-LIF -> Snn_Conv2d (raw output, no tdBN).  Returns (y, bits); bits
+    (1 bit per element) is what the backward keeps instead of the membranes, which it recomputes."""
+    sp = F_.lif_ecs(Act(x.contiguous(), T), _lif_w(dw_w, dw_b, pw_w, pw_b), None, ecs_tau, alpha, beta)
+    y = F_.spike_conv(sp, _conv_w(weight, stride, pad))
+    return y.data, sp.bits
+
+
+@lif_spike_conv.register_fake
+def _(x, T, dw_w, dw_b, pw_w, pw_b, weight, stride, pad, ecs_tau, alpha, beta):
+    _, N, H, W, C = x.shape
+    Ho, Wo = _conv_out(H, W, weight.shape[2], stride, pad)
+    return (x.new_empty((T, N, Ho, Wo, weight.shape[0])), x.new_empty((T, N, H, W, C // 32), dtype=torch.int32))
+
+
+def _lsc_setup(ctx, inputs, output):
+    x, T, dw_w, dw_b, pw_w, pw_b, weight, stride, pad, ecs_tau, alpha, beta = inputs
+    ctx.save_for_backward(x, dw_w, dw_b, pw_w, pw_b, weight, output[1])
+    ctx.cfg = (T, stride, pad, ecs_tau, alpha, beta)
+
+
+def _lsc_backward(ctx, g_y, _g_bits):
+    """Surrogate-gradient BPTT through the neuron (forward recomputed), dgrad / wgrad of the conv on tcgen05."""
+    x, dw_w, dw_b, pw_w, pw_b, weight, bits = ctx.saved_tensors
+    T, stride, pad, ecs_tau, alpha, beta = ctx.cfg
+    with torch.no_grad():
+        C, k = x.shape[-1], weight.shape[2]
+        sp = Spikes(bits, C)
+        g_y = g_y.contiguous()
+        g_w = F_.spike_conv_wgrad(g_y, sp, k, stride, pad)
+        splits = F_.get_splits()
+        wT = _cached("dgrad", (weight,), lambda: F_.pack_dgrad_weight(weight, splits))
+        g_s = F_.conv_dgrad(g_y, wT, splits, sp.H, sp.W, C, k, stride, pad)
+        g_x, g_dw, g_db, g_pw, g_pb = F_.lif_ecs_bwd(g_s, Act(x.contiguous(), T), _lif_w(dw_w, dw_b, pw_w, pw_b), pw_w,
+                                                     None, ecs_tau, alpha, beta)
+        if x.shape[0] != T:   # T-broadcast input: the gradient of the single stored frame is the sum over T
+            g_x = g_x.sum(0, keepdim=True)
+    return g_x, None, g_dw, g_db, g_pw, g_pb, g_w, None, None, None, None, None
+
+
+lif_spike_conv.register_autograd(_lsc_backward, setup_context=_lsc_setup)

@@ -173,6 +173,43 @@ def test_model_tiny(name):
     assert rel_l2(zt.cpu(), gold["z_eval"]) < 1e-5
 
 
+def test_model_event_frames():
+    """BASELINE config 4 path: [T, N, 3, H, W] event frames (T = 5, a different frame every step) straight into
+    _forward_once, against the CPU oracle on the same weights (train-mode tdBN: firing-rate-level agreement, and
+    the stem -- the only layer that sees the frames directly -- to 1e-4)."""
+    E = ecsy()
+    T, N, H = 5, 2, 64
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", "tiny.yaml")))
+    g = S.gen(77)
+    u = torch.rand(N, T, 1, H, H, generator=g)
+    f = torch.full_like(u, 127.0 / 255.0)
+    f[u < 0.05] = 0.0
+    f[u > 0.95] = 1.0
+    x = f.expand(-1, -1, 3, -1, -1).permute(1, 0, 2, 3, 4).contiguous()      # [T, N, 3, H, W]
+    sd = O.init_state_dict(cfg, T, seed=3)
+    stride = O.detect_strides(cfg)
+    rec = {}
+    with torch.no_grad():
+        want = O.forward(cfg, {k: v.clone() for k, v in sd.items()}, x, T, True, stride=stride, rec=rec)
+    E.common.time_window = T
+    try:
+        m = E.yolo.Model(E.cfg_path("tiny"))
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        feats = {}
+        h = m.model[0].register_forward_hook(lambda mod, i, o: feats.__setitem__("stem", o.detach().cpu()))
+        with torch.no_grad():
+            out = m(x.cuda())
+        h.remove()
+    finally:
+        E.common.time_window = 4
+    assert feats["stem"].shape[0] == T and rel_l2(feats["stem"], rec["layer0"]) < 1e-4
+    assert len(out) == len(want)
+    for a_, b_ in zip(out, want):
+        assert a_.shape == b_.shape
+        assert rel_l2(a_.cpu(), b_) < 8e-2
+
+
 # ---------------------------------------------------------------- Stack B
 @pytest.mark.parametrize("name", list(S.SILU_CASES))
 def test_silu_neuron(name):
