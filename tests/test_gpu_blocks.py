@@ -183,8 +183,8 @@ def test_model_event_frames():
     g = S.gen(77)
     u = torch.rand(N, T, 1, H, H, generator=g)
     f = torch.full_like(u, 127.0 / 255.0)
-    f[u < 0.05] = 0.0
-    f[u > 0.95] = 1.0
+    f[u < 0.3] = 0.0     # dense events: a nearly constant frame makes train-mode tdBN amplify rounding noise
+    f[u > 0.7] = 1.0
     x = f.expand(-1, -1, 3, -1, -1).permute(1, 0, 2, 3, 4).contiguous()      # [T, N, 3, H, W]
     sd = O.init_state_dict(cfg, T, seed=3)
     stride = O.detect_strides(cfg)
