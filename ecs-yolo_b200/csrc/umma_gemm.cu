@@ -1055,6 +1055,171 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dense GEMM with fp16 output and the TMA-store epilogue: the point-wise half of the ECS spread in fast mode,
+//     S[M][C] (fp16) = A[M][C] (bf16, the depth-wise output) * Wpw[C][C]^T
+// K = C is only 1..16 K blocks, so a tile is dominated by its 32 KB of HBM traffic and its epilogue, not by the MMAs:
+// same two-epilogue-group / staging / cp.async.bulk.tensor-store structure as k_spike_conv_ts (64-column fp16
+// slices = 128-byte rows), A and B by TMA, SS-mode MMA.  Warps: 0-3 epilogue group 0, 4-7 group 1, 8 TMA, 9 MMA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDtThreads = 320;
+
+struct DtCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct DtArgs {
+  int m_tiles, n_tiles, kb_total, stages;
+  uint32_t stg_off, ctl_off;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kDtThreads, 1)
+k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+              const __grid_constant__ CUtensorMap tm_out, const DtArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  constexpr int kTmemCols = 2 * BN;
+  constexpr int kSlices = BN / 64;
+  DtCtl* ctl = reinterpret_cast<DtCtl*>(smem + g.ctl_off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->tmem_full[b], 1);
+      mbar_init(&ctl->tmem_empty[b], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<kTmemCols>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 8) {
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* st = smem + (size_t)stage * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kStageBytes);
+          tma_load_2d(st, &tm_a, &ctl->full[stage], kb * 64, m_tile * 128);
+          tma_load_2d(st + kATileBytes, &tm_b, &ctl->full[stage], kb * 64, n_tile * BN);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[buf], bphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        mbar_wait(&ctl->full[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&ctl->empty[stage]);
+          if (kb == g.kb_total - 1) umma_commit(&ctl->tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---- epilogue groups: TMEM -> fp16 -> swizzled staging rows (64 halves = 128 bytes) -> one TMA store per slice ----
+    const uint32_t ge = (uint32_t)warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = (q == 0 && lane == 0);
+    uint8_t* stg = smem + g.stg_off + (size_t)ge * 2 * kATileBytes;
+    const uint32_t my_row = smem_u32(stg) + (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)row & 7u;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ge * BN;
+    uint32_t sl = 0, git = 0;
+    for (int tile = (int)blockIdx.x + (int)ge * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, ++git) {
+      const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+#pragma unroll 1
+      for (int j = 0; j < kSlices; ++j, ++sl) {
+        const uint32_t b = sl & 1u;
+        if (leader) bulk_wait_group_read<1>();   // the store that last used this staging buffer has read it
+        if (j == 0) {
+          mbar_wait(&ctl->tmem_full[ge], git & 1);
+          tc_fence_after_sync();
+        }
+        named_bar_sync(1 + (int)ge, 128);
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(t_row + j * 64, v0);
+        tmem_ld_32x32(t_row + j * 64 + 32, v1);
+        tmem_ld_wait();
+        if (j == kSlices - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&ctl->tmem_empty[ge]);
+        }
+        const uint32_t dst = my_row + b * (uint32_t)kATileBytes;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {   // chunk c = 8 halves
+          const uint32_t* src = c < 4 ? &v0[8 * c] : &v1[8 * (c - 4)];
+          uint32_t w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const __half2 h = __floats2half2_rn(__uint_as_float(src[2 * u]), __uint_as_float(src[2 * u + 1]));
+            w[u] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)c ^ sw) << 4)), "r"(w[0]),
+                       "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + (int)ge, 128);
+        if (leader) {
+          tma_store_2d(&tm_out, stg + (size_t)b * kATileBytes, n_tile * BN + j * 64, m_tile * 128);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (leader) bulk_wait_group_all();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Weight gradient of the spike convolution:  dW[co][(tap, ci)] += sum_pixels gy[p][co] * s[p*stride + tap - pad][ci]
 // The contraction runs over PIXELS, i.e. over the rows of both operands, so both are fed to the tensor
 // core as MN-major tiles: A = gy tile [128 pixels x 128 co] (bf16 hi [+ lo], 4-D TMA boxes in the tile's
@@ -1582,6 +1747,59 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   return launch_bn<kASpikes, 1, 2, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, patch_bytes, st);
 }
 
+// 2-D fp16 row-major [rows][cols] tensor map with a {64, 128} box (128-byte rows), 128-byte swizzle.
+static int ecsy_tensor_map_f16_2d(const void* ptr, uint64_t rows, uint64_t cols, CUtensorMap* out) {
+  ECSY_CHECK_ARG(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cols % 64 == 0, "f16 tensor map: alignment");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    ecsy_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECSY_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ecsy_set_error("cuTensorMapEncodeTiled(f16 2d) failed with %d (rows=%llu cols=%llu)", (int)r, (unsigned long long)rows,
+                   (unsigned long long)cols);
+    return ECSY_ERR_CUDA;
+  }
+  return ECSY_OK;
+}
+
+namespace {
+template <int BN>
+int launch_dense_tma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, DtArgs g, cudaStream_t st) {
+  auto kern = k_dense_tma_h<BN>;
+  static bool attr = false;
+  if (!attr) {
+    ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr = true;
+  }
+  constexpr int stage_bytes = kATileBytes + BN * 128;
+  const int fixed = 1024 + (int)sizeof(DtCtl) + 128 + 4 * kATileBytes;
+  int stages = (kSmemLimit - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    ecsy_set_error("dense_tma: shared memory budget allows only %d stage(s)", stages);
+    return ECSY_ERR_UNSUPPORTED;
+  }
+  g.stages = stages;
+  g.stg_off = (uint32_t)stages * stage_bytes;     // stage sizes are multiples of 8 KB: 1024-aligned
+  g.ctl_off = g.stg_off + 4u * kATileBytes;
+  const int smem = 1024 + (int)g.ctl_off + (int)sizeof(DtCtl) + 64;
+  int grid = g.m_tiles * g.n_tiles;
+  const int sms = ecsy_num_sms();
+  if (grid > sms) grid = sms;
+  kern<<<grid, kDtThreads, smem, st>>>(ta, tb, to, g);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+}  // namespace
+
 // Dense GEMM on a bf16 A matrix (hi [+ lo]) : out[M][Cout] = A * W^T (*scale + shift) (+ residual)
 int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,
                     int Cout, const float* scale, const float* shift, const float* residual, int64_t res_rows,
@@ -1599,6 +1817,22 @@ int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const 
   }
   rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)splits * Cout, (uint64_t)K, (uint32_t)BN, &tb);
   if (rc) return rc;
+  static const bool dense_tma = getenv("ECSY_DENSE_TMA") == nullptr || getenv("ECSY_DENSE_TMA")[0] != '0';
+  if (dense_tma && splits == 1 && out_half && !scale && !residual && M >= 128) {
+    // fast-mode ECS spread: fp16 output through the two-group TMA-store epilogue
+    CUtensorMap to;
+    rc = ecsy_tensor_map_f16_2d(out, (uint64_t)M, (uint64_t)Cout, &to);
+    if (rc) return rc;
+    DtArgs d{};
+    d.m_tiles = (int)((M + 127) / 128);
+    d.n_tiles = Cout / BN;
+    d.kb_total = K / 64;
+    switch (BN) {
+      case 64: return launch_dense_tma<64>(ta0, tb, to, d, st);
+      case 128: return launch_dense_tma<128>(ta0, tb, to, d, st);
+      case 256: return launch_dense_tma<256>(ta0, tb, to, d, st);
+    }
+  }
   GemmArgs g{};
   g.m_tiles = (int)((M + 127) / 128);
   g.n_tiles = Cout / BN;

@@ -1,7 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_gpu_ops.py -m gpu -q --no-header -p no:cacheprovider -k "lif" 2>&1 | tail -30
-echo "== ecs bench fused"
+timeout -k 10 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_blocks.py -m gpu -q --no-header -p no:cacheprovider -x 2>&1 | tail -6
+echo "== ecs bench"
 timeout -k 10 300 python tools/ecs_bench.py 2>&1 | tail -6
-echo "== ecs bench unfused"
-ECSY_LIF_FUSED=0 timeout -k 10 300 python tools/ecs_bench.py 2>&1 | tail -6
+echo "== ecs bench old dense epilogue"
+ECSY_DENSE_TMA=0 timeout -k 10 300 python tools/ecs_bench.py 2>&1 | tail -6
+echo "== bench"
+timeout -k 10 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_infer.json 2> gpurun_out/bench_infer.err
+echo "rc=$?"; tail -2 gpurun_out/bench_infer.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/bench_infer.json"))
+print(round(d["value"], 1), "img/s", round(d["ms_per_step"], 2), "ms", d["roofline"]["achieved"], {k: round(v, 2) for k, v in d.get("breakdown_ms_per_step", {}).items()})
+PY
