@@ -8,3 +8,5 @@ run r10_infer --model resnet10 --steps 3 --warmup 3
 run r18_T1 --model resnet18 --T 1 --steps 3 --warmup 3
 run r18_T8 --model resnet18 --T 8 --batch 32 --steps 3 --warmup 3
 run r34_parity --model resnet34 --precision parity --steps 3 --warmup 3
+run r34_gen1_T5 --model resnet34 --T 5 --events --batch 32 --steps 3 --warmup 3
+run r34_train --model resnet34 --mode train --batch 32 --steps 3 --warmup 2 --min-warmup 2
