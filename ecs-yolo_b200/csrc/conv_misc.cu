@@ -1,5 +1,6 @@
 // Weight packing, im2col for real-valued inputs, the generic SIMT convolution (odd shapes:
 // grouped convs, Cout not a multiple of 64) and the C-ABI convolution entry points.
+#include <stdlib.h>
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
 #include "umma_gemm.h"
@@ -267,9 +268,15 @@ extern "C" int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed,
                               Cout, k, stride, pad, STREAM(stream));
 }
 
+static bool use_gather_conv(int Cin, int Cout, int k, int groups, int splits) {
+  static const bool gather = getenv("ECSY_CONV_GATHER") == nullptr || getenv("ECSY_CONV_GATHER")[0] != '0';
+  return gather && splits == 1 && groups == 1 && Cout % 64 == 0 && Cin < 64 && k * k * Cin <= 1024;
+}
+
 extern "C" size_t ecsy_real_conv_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                                           int groups, int splits) {
   if (groups != 1 || Cout % 64 != 0) return 0;
+  if (use_gather_conv(Cin, Cout, k, groups, splits)) return 0;   // operand tiles gathered on the fly
   if (Cin % 64 == 0 && stride == 1)  // implicit GEMM over bf16 planes of the input, no im2col buffer
     return static_cast<size_t>(imgs) * H * W * Cin * 2 * splits + 1024;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
@@ -303,6 +310,10 @@ extern "C" int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_
     return ecsy_umma_conv_bf16(a_hi, a_lo, w_packed, splits, out, scale, shift, nullptr, 0, (int)imgs, H, W, Cin, Cout, k,
                                pad, STREAM(stream));
   }
+  if (use_gather_conv(Cin, Cout, k, groups, splits) && w_packed != nullptr && bias == nullptr)
+    // the stem: operand tiles gathered on the fly, no im2col matrix in HBM
+    return ecsy_umma_conv_gather(x, x_imgs, w_packed, out, scale, shift, (int)imgs, H, W, Cin, Cout, k, stride, pad,
+                                 STREAM(stream));
   if (groups == 1 && Cout % 64 == 0 && w_packed != nullptr && bias == nullptr) {
     const int Kpad = (k * k * Cin + 63) / 64 * 64;
     const int64_t M = imgs * Ho * Wo;

@@ -88,6 +88,11 @@ struct GemmArgs {
   const float* dw_w;   // kADw: depth-wise weights [9][C]
   const float* dw_b;   // kADw: depth-wise bias [C]
   int wpg;             // expander warps per stage group (kExpWarps / stages)
+  // kAGather: im2col on the fly from a real-valued fp32 NHWC tensor (small Cin: the stem)
+  const float* gx;     // [gx_imgs][H][W][gcin]
+  int64_t gx_imgs;     // images in gx (T-broadcast sources repeat)
+  int gcin, gK;        // input channels, K = kh*kw*gcin (kb_total*64 >= gK, zero padded)
+  uint32_t ktab_off;   // byte offset of the k -> (offset, ky, kx) table in shared memory
 };
 
 template <int EPI>
@@ -95,7 +100,7 @@ struct EpiSel;
 template <>
 struct EpiSel<0> { using type = EpiConv; };
 
-constexpr int kATma = 0, kASpikes = 1, kATma4 = 2, kADw = 3, kASpikesT = 4;
+constexpr int kATma = 0, kASpikes = 1, kATma4 = 2, kADw = 3, kASpikesT = 4, kAGather = 5;
 constexpr int kEpiConv = 0;
 
 __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
@@ -104,7 +109,7 @@ __device__ __forceinline__ uint32_t bits2_to_bf16x2(uint32_t x) {
 }
 
 template <int BN, int A_MODE, int A_SPLIT, int B_SPLIT, int EPI>
-__global__ void __launch_bounds__((A_MODE == kASpikes || A_MODE == kADw || A_MODE == kASpikesT) ? kSpikeThreads : 192, 1)
+__global__ void __launch_bounds__((A_MODE == kASpikes || A_MODE == kADw || A_MODE == kASpikesT || A_MODE == kAGather) ? kSpikeThreads : 192, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
             const __grid_constant__ CUtensorMap tm_b, const GemmArgs g, const SpikeGeom sg,
             const typename EpiSel<EPI>::type ep) {
@@ -131,7 +136,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       if (A_SPLIT == 2) tma_prefetch_desc(&tm_a1);
     }
     for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&ctl->full_a[s], A_MODE == kADw ? kExpWarps : (kTS ? 4 : g.wpg));
+      mbar_init(&ctl->full_a[s], (A_MODE == kADw || A_MODE == kAGather) ? kExpWarps : (kTS ? 4 : g.wpg));
       mbar_init(&ctl->full_b[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
@@ -142,6 +147,18 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
     mbar_fence_init();
   }
   if (warp == 5) tmem_alloc<kTmemCols>(&ctl->tmem_base);
+  if (A_MODE == kAGather) {   // k -> {float offset inside the receptive field, (ky << 16) | kx}; ky = 0xFFFF: zero padding of K
+    int2* ktab = reinterpret_cast<int2*>(smem + g.ktab_off);
+    for (int k = threadIdx.x; k < g.kb_total * 64; k += blockDim.x) {
+      int2 e = make_int2(0, (int)0xFFFF0000u);
+      if (k < g.gK) {
+        const int tap = k / g.gcin, ci = k - tap * g.gcin;
+        const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
+        e = make_int2((ky * sg.W + kx) * g.gcin + ci, (ky << 16) | kx);
+      }
+      ktab[k] = e;
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -202,7 +219,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       const uint32_t d_tmem = tmem_base + buf * BN;
       for (int kb = 0; kb < g.kb_total; ++kb) {
         mbar_wait(&ctl->full_b[stage], phase);
-        if (A_MODE == kASpikes || A_MODE == kADw || kTS) mbar_wait(&ctl->full_a[stage], phase);
+        if (A_MODE == kASpikes || A_MODE == kADw || A_MODE == kAGather || kTS) mbar_wait(&ctl->full_a[stage], phase);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
@@ -240,6 +257,59 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
         }
         __syncwarp();
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 6 && A_MODE == kAGather) {
+    // =============================== im2col-on-the-fly producers (real input, small Cin) ===============================
+    // 256 threads build every [128 rows x 64 k] operand tile: thread = (row, half of the K block); the receptive
+    // field of an output pixel is read straight from the fp32 NHWC tensor (L1/L2 resident: neighbouring pixels
+    // overlap), converted to bf16 and written in the 128-byte-swizzled layout -- no im2col matrix in HBM.
+    if constexpr (A_MODE == kAGather) {
+      const int et = threadIdx.x - 192;
+      const int row = et & 127, part = et >> 7;
+      const int w_l = row & (sg.tw_b - 1);
+      const int h_l = (row >> sg.tw_sh) & (sg.th_b - 1);
+      const int n_l = row >> (sg.tw_sh + sg.th_sh);
+      const int2* ktab = reinterpret_cast<const int2*>(smem + g.ktab_off);
+      const int tiles_hw = sg.tiles_h * sg.tiles_w;
+      const uint32_t sw = (uint32_t)row & 7u;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / g.n_tiles;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        const int img = tn * sg.tn_b + n_l, ho = th * sg.th_b + h_l, wo = tw * sg.tw_b + w_l;
+        const bool valid = img < sg.imgs && ho < sg.Ho && wo < sg.Wo;
+        const int hi0 = ho * sg.stride - sg.pad, wi0 = wo * sg.stride - sg.pad;
+        const float* px = g.gx + (((int64_t)(valid ? img % g.gx_imgs : 0) * sg.H + hi0) * sg.W + wi0) * g.gcin;
+        for (int kb = 0; kb < g.kb_total; ++kb) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          const uint32_t dst = smem_u32(smem + (size_t)stage * kStageBytes) + (uint32_t)row * 128u;
+          const int2* kt = ktab + kb * 64 + part * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float v[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int2 e = kt[c * 8 + u * 2 + h];
+                const int hi = hi0 + (int)((uint32_t)e.y >> 16), wi = wi0 + (e.y & 0xFFFF);
+                v[h] = (valid && (unsigned)hi < (unsigned)sg.H && (unsigned)wi < (unsigned)sg.W) ? __ldg(px + e.x) : 0.f;
+              }
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[0], v[1]);
+              w4[u] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t)(part * 4 + c)) ^ sw) << 4)),
+                         "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->full_a[stage]);
+          if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp >= 6 && A_MODE == kADw) {
@@ -558,7 +628,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       // output row of this thread
       int64_t pix;
       bool valid;
-      if (A_MODE == kASpikes || A_MODE == kATma4 || kTS) {
+      if (A_MODE == kASpikes || A_MODE == kATma4 || A_MODE == kAGather || kTS) {
         const int tiles_hw = sg.tiles_h * sg.tiles_w;
         const int tn = m_tile / tiles_hw;
         const int rem = m_tile - tn * tiles_hw;
@@ -1562,7 +1632,7 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   }
   (void)patch_bytes;
   constexpr int kEpiStage = 4 * kEpiWarpFloats * 4;
-  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 128 + kEpiStage;
+  const int fixed = 1024 /*align slack*/ + (int)sizeof(SharedCtl) + 128 + kEpiStage + (A_MODE == kAGather ? g.kb_total * 64 * 8 : 0);
   int stages = (dyn_limit - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (A_MODE == kASpikes) stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : (stages >= 2 ? 2 : 0));
@@ -1579,11 +1649,12 @@ int launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   g.wpg = A_MODE == kASpikes ? kExpWarps / stages : 1;
   const uint32_t ctl_off = (uint32_t)stages * stage_bytes;
   g.epi_off = (ctl_off + (uint32_t)sizeof(SharedCtl) + 63u) & ~63u;
-  const int smem = 1024 + (int)g.epi_off + kEpiStage;
+  g.ktab_off = g.epi_off + (uint32_t)kEpiStage;
+  const int smem = 1024 + (int)g.epi_off + kEpiStage + (A_MODE == kAGather ? g.kb_total * 64 * 8 : 0);
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, (A_MODE == kASpikes || A_MODE == kADw || kTS) ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
+  kern<<<grid, (A_MODE == kASpikes || A_MODE == kADw || A_MODE == kAGather || kTS) ? kSpikeThreads : 192, smem, st>>>(a0, a1, b, g, sg, ep);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }
@@ -1881,6 +1952,39 @@ int ecsy_umma_conv_bf16(const void* a_hi, const void* a_lo, const void* w_packed
   EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout, 0};
   if (splits == 1) return launch_bn<kATma4, 1, 1, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
   return launch_bn<kATma4, 2, 2, kEpiConv>(BN, ta0, ta1, tb, g, sg, e, 0, st);
+}
+
+// Convolution over a real-valued fp32 NHWC tensor with a small channel count (the stem: 3 -> 64, 7x7, stride 2):
+// implicit GEMM whose A tiles are gathered on the fly (no im2col matrix).  Single weight plane only.
+int ecsy_umma_conv_gather(const float* x, int64_t x_imgs, const void* w_packed, float* out, const float* scale,
+                          const float* shift, int imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                          cudaStream_t st) {
+  const int BN = ecsy_pick_bn(Cout, 1);
+  ECSY_CHECK_ARG(BN != 0, "conv_gather: Cout=%d must be a multiple of 64", Cout);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  ECSY_CHECK_ARG(Ho > 0 && Wo > 0 && k < 256, "conv_gather: geometry");
+  const int K = k * k * Cin, Kpad = (K + 63) / 64 * 64;
+  ECSY_CHECK_ARG(Kpad <= 1024, "conv_gather: K=%d too large", K);
+  SpikeGeom sg{};
+  if (!pick_tile_box(sg, imgs, Ho, Wo, 1, k, stride)) {
+    ecsy_set_error("conv_gather: no tile shape found");
+    return ECSY_ERR_ARG;
+  }
+  sg.bits = nullptr; sg.imgs = imgs; sg.H = H; sg.W = W; sg.Cw = 0; sg.Ho = Ho; sg.Wo = Wo;
+  sg.kh = k; sg.kw = k; sg.stride = stride; sg.pad = pad;
+  sg.tn_sh = ilog2(sg.tn_b); sg.th_sh = ilog2(sg.th_b); sg.tw_sh = ilog2(sg.tw_b);
+  sg.tiles_h = (Ho + sg.th_b - 1) / sg.th_b; sg.tiles_w = (Wo + sg.tw_b - 1) / sg.tw_b;
+  sg.nslab = 1;
+  GemmArgs g{};
+  g.m_tiles = ((imgs + sg.tn_b - 1) / sg.tn_b) * sg.tiles_h * sg.tiles_w;
+  g.n_tiles = Cout / BN;
+  g.kb_total = Kpad / 64;
+  g.gx = x; g.gx_imgs = x_imgs; g.gcin = Cin; g.gK = K;
+  CUtensorMap tb, dummy{};
+  int rc = ecsy_tensor_map_bf16(w_packed, (uint64_t)Cout, (uint64_t)Kpad, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  EpiConv e{out, scale, shift, nullptr, (int64_t)imgs * Ho * Wo, Cout, 0};
+  return launch_bn<kAGather, 1, 1, kEpiConv>(BN, dummy, dummy, tb, g, sg, e, 0, st);
 }
 
 // dW[Cout][k*k*Cin] (fp32, accumulated) for a spike convolution; gy as bf16 planes [imgs][Ho][Wo][Cout].

@@ -42,6 +42,9 @@ int ecsy_umma_xty(const void* p_hi, const void* p_lo, const void* q_hi, const vo
 int ecsy_umma_conv_bf16(const void* a_hi, const void* a_lo, const void* w_packed, int splits, float* out,
                         const float* scale, const float* shift, const float* residual, int64_t res_imgs, int imgs, int H,
                         int W, int Cin, int Cout, int k, int pad, cudaStream_t st);
+int ecsy_umma_conv_gather(const float* x, int64_t x_imgs, const void* w_packed, float* out, const float* scale,
+                          const float* shift, int imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                          cudaStream_t st);
 int ecsy_launch_f32_to_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st);
 int ecsy_umma_spike_wgrad(const void* gy_hi, const void* gy_lo, const uint32_t* bits, float* dw, int imgs, int H, int W,
                           int Cin, int Cout, int k, int stride, int pad, cudaStream_t st);

