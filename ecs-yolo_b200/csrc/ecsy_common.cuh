@@ -251,6 +251,12 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
+__device__ __forceinline__ float ldg_stream_f(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
 // Round-to-nearest ops that ptxas may not contract into FMAs: the LIF update reproduces the
 // reference's separately rounded element-wise products and sums (models/common.py:306-309).
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }

@@ -19,6 +19,9 @@ def test_layout_and_bits_roundtrip():
     assert torch.equal(a.data.cpu(), x.permute(0, 1, 3, 4, 2).contiguous())
     back = F.nhwc_to_nchw(a.data.reshape(6, 5, 7, 64)).cpu().reshape(3, 2, 64, 5, 7)
     assert torch.equal(back, x)
+    for c in (1, 2, 3, 4):   # few-channel inputs (RGB / event frames) take the per-pixel kernel
+        xs = torch.rand(1, 3, c, 9, 11, generator=g)
+        assert torch.equal(Act.from_ref(xs.cuda()).data.cpu(), xs.permute(0, 1, 3, 4, 2).contiguous())
     sp = Spikes.from_act(a)
     ref = (x > 0.5).float()
     assert torch.equal(sp.to_act().to_ref().cpu(), ref)
