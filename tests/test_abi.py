@@ -60,3 +60,19 @@ def test_state_dict_keys_match_reference_layout():
         got = m.state_dict()
         assert set(got) == set(want)
         assert all(got[k].shape == want[k].shape for k in got)
+
+
+def test_dispatch_rules_are_pure_host_functions():
+    """The measured dispatch rules are part of the C ABI and need no device: tensor-memory operand for every layer it
+    supports except the wide ones (Cout % 256 == 0 and Cin >= 256 with single-plane weights), fused LIF only for C = 64."""
+    L = ecsy()._cabi.lib()
+    assert L.ecsy_spike_conv_ts_supported(64, 64) == 1 and L.ecsy_spike_conv_ts_supported(64, 192) == 1
+    assert L.ecsy_spike_conv_ts_supported(32, 64) == 0 and L.ecsy_spike_conv_ts_supported(64, 96) == 0
+    assert L.ecsy_spike_conv_prefers_ts(64, 64, 1) == 1 and L.ecsy_spike_conv_prefers_ts(128, 256, 1) == 1
+    assert L.ecsy_spike_conv_prefers_ts(512, 512, 1) == 0 and L.ecsy_spike_conv_prefers_ts(384, 256, 1) == 0
+    assert L.ecsy_spike_conv_prefers_ts(512, 512, 2) == 1      # split weights: 128-column tiles either way
+    assert L.ecsy_lif_ecs_fused_supported(4, 64) == 1 and L.ecsy_lif_ecs_fused_supported(1, 64) == 0
+    assert L.ecsy_lif_ecs_fused_supported(4, 128) == 0 and L.ecsy_lif_ecs_fused_supported(9, 64) == 0
+    # the stem's operand tiles are gathered on the fly in fast mode: no im2col workspace
+    assert L.ecsy_real_conv_ws_bytes(64, 640, 640, 3, 64, 7, 2, 3, 1, 1) == 0
+    assert L.ecsy_real_conv_ws_bytes(64, 640, 640, 3, 64, 7, 2, 3, 1, 2) > 0
