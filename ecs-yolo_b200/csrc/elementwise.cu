@@ -506,26 +506,35 @@ __global__ void k_affine_add(const float* __restrict__ a, int64_t a_mod, const f
                              const float* __restrict__ ba, const float* __restrict__ b, int64_t b_mod,
                              const float* __restrict__ sb, const float* __restrict__ bb,
                              float* __restrict__ out, int64_t imgs, int64_t hwc4, int C) {
-  const int64_t total = imgs * hwc4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const bool small = total < (int64_t(1) << 32) && hwc4 < (int64_t(1) << 32);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t img = ecsy::div_u(i, (uint32_t)hwc4, small), rem = i - img * hwc4;
-    const int c = static_cast<int>(ecsy::mod_u(rem, (uint32_t)(C >> 2), small) * 4u);
-    float4 v = reinterpret_cast<const float4*>(a)[ecsy::mod_u(img, (uint32_t)a_mod, small) * hwc4 + rem];
-    if (sa != nullptr) {
-      float4 s = *reinterpret_cast<const float4*>(sa + c), t = *reinterpret_cast<const float4*>(ba + c);
-      v.x = v.x * s.x + t.x; v.y = v.y * s.y + t.y; v.z = v.z * s.z + t.z; v.w = v.w * s.w + t.w;
-    }
-    if (b != nullptr) {
-      float4 u = reinterpret_cast<const float4*>(b)[ecsy::mod_u(img, (uint32_t)b_mod, small) * hwc4 + rem];
-      if (sb != nullptr) {
-        float4 s = *reinterpret_cast<const float4*>(sb + c), t = *reinterpret_cast<const float4*>(bb + c);
-        u.x = u.x * s.x + t.x; u.y = u.y * s.y + t.y; u.z = u.z * s.z + t.z; u.w = u.w * s.w + t.w;
+  // blockIdx.y walks the images, blockIdx.x / the grid-stride loop one image's float4 items: the channel index
+  // advances incrementally and no per-item division is left (the kernel was ALU-bound on index arithmetic).
+  const int stride = (int)(gridDim.x * blockDim.x);
+  const int i0 = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int c0 = (int)(((int64_t)i0 * 4) % C);
+  const int cstep = (int)(((int64_t)stride * 4) % C);
+  for (int64_t img = blockIdx.y; img < imgs; img += gridDim.y) {
+    const float4* pa = reinterpret_cast<const float4*>(a) + (img % a_mod) * hwc4;
+    const float4* pb = b != nullptr ? reinterpret_cast<const float4*>(b) + (img % b_mod) * hwc4 : nullptr;
+    float4* po = reinterpret_cast<float4*>(out) + img * hwc4;
+    int c = c0;
+    for (int64_t i = i0; i < hwc4; i += stride) {
+      float4 v = pa[i];
+      if (sa != nullptr) {
+        float4 s = *reinterpret_cast<const float4*>(sa + c), t = *reinterpret_cast<const float4*>(ba + c);
+        v.x = v.x * s.x + t.x; v.y = v.y * s.y + t.y; v.z = v.z * s.z + t.z; v.w = v.w * s.w + t.w;
       }
-      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      if (pb != nullptr) {
+        float4 u = pb[i];
+        if (sb != nullptr) {
+          float4 s = *reinterpret_cast<const float4*>(sb + c), t = *reinterpret_cast<const float4*>(bb + c);
+          u.x = u.x * s.x + t.x; u.y = u.y * s.y + t.y; u.z = u.z * s.z + t.z; u.w = u.w * s.w + t.w;
+        }
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      po[i] = v;
+      c += cstep;
+      if (c >= C) c -= C;
     }
-    reinterpret_cast<float4*>(out)[i] = v;
   }
 }
 
@@ -870,8 +879,13 @@ extern "C" int ecsy_affine_add(const float* a, int64_t a_imgs, const float* sa, 
                  "affine_add: source image counts must divide imgs");
   ECSY_CHECK_ARG((sa == nullptr) == (ba == nullptr) && (sb == nullptr) == (bb == nullptr), "affine_add: scale/shift pairs");
   const int64_t hwc4 = hw * C / 4;
-  k_affine_add<<<grid_for(imgs * hwc4, kThreads, ecsy_num_sms() * 8), kThreads, 0, STREAM(stream)>>>(
-      a, a_imgs, sa, ba, b, b ? b_imgs : 1, sb, bb, out, imgs, hwc4, C);
+  const int64_t want = (int64_t)ecsy_num_sms() * 8;                      // blocks in flight
+  const int64_t per_img = (hwc4 + kThreads - 1) / kThreads;
+  int64_t gx = (want + imgs - 1) / imgs;
+  if (gx > per_img) gx = per_img;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)(imgs < 65535 ? imgs : 65535));
+  k_affine_add<<<grid, kThreads, 0, STREAM(stream)>>>(a, a_imgs, sa, ba, b, b ? b_imgs : 1, sb, bb, out, imgs, hwc4, C);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }

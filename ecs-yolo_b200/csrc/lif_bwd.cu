@@ -61,9 +61,9 @@ __global__ void k_lif_bwd_pre(const float* __restrict__ gm_next, const float* __
 }
 
 // Per-channel pixel sums for the spread parameter gradients: acc[0][c] = sum ge, acc[1][c] = sum G1,
-// acc[2+tap][c] = sum_p G1[p][c] * s_t[p + off(tap)][c].  Double atomics into a [11][C] scratch.
+// acc[2+tap][c] = sum_p G1[p][c] * s_t[p + off(tap)][c].  Per-block partial sums [grid][11][C], reduced in double by the final kernel.
 __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __restrict__ g1,
-                                 const uint32_t* __restrict__ bits, double* __restrict__ acc, int N, int H, int W,
+                                 const uint32_t* __restrict__ bits, float* __restrict__ part, int N, int H, int W,
                                  int C) {
   const int c4 = C >> 2;
   const int tq = threadIdx.x % c4;         // channel quad (blockDim is a multiple of c4)
@@ -123,17 +123,20 @@ __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __re
   for (int idx = threadIdx.x; idx < 11 * C; idx += blockDim.x) {
     double t = 0;
     for (int y = 0; y < nty; ++y) t += sred[y * 11 * C + idx];
-    atomicAdd(acc + idx, t);
+    part[(size_t)blockIdx.x * 11 * C + idx] = static_cast<float>(t);   // per-block partial: no atomics (592 blocks x 11C
+                                                                        // double atomics on 11C addresses serialised in L2)
   }
 }
 
 // outputs += alpha * acc ; layouts: g_pw_b [C], g_dw_b [C], g_dw_w [9][C]
-__global__ void k_lif_bwd_reduce_final(const double* __restrict__ acc, float* __restrict__ g_pw_b,
+__global__ void k_lif_bwd_reduce_final(const float* __restrict__ part, int nblocks, float* __restrict__ g_pw_b,
                                        float* __restrict__ g_dw_b, float* __restrict__ g_dw_w, int C, float alpha) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 11 * C) return;
+  double t = 0;
+  for (int b = 0; b < nblocks; ++b) t += part[(size_t)b * 11 * C + i];   // coalesced across i, deterministic order
   const int a = i / C, c = i - a * C;
-  const float v = alpha * static_cast<float>(acc[i]);
+  const float v = alpha * static_cast<float>(t);
   if (a == 0) g_pw_b[c] += v;
   else if (a == 1) g_dw_b[c] += v;
   else g_dw_w[(a - 2) * C + c] += v;
@@ -198,7 +201,7 @@ __global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __re
 // models (mem_old = silu(mem)):  m_t = d*o_{t-1}*(1 - stopgrad(o_{t-1})) + x_t + f_{t-1},  o_t = silu(m_t).
 //   go_t = gout_t + alpha*dw^T(G1) + gm*decay*(1 - o_t);  gm_t = go_t * silu'(m_t)
 __global__ void k_silu_bwd_reduce(const float* __restrict__ ge, const float* __restrict__ g1,
-                                  const float* __restrict__ o, double* __restrict__ acc, int N, int H, int W, int C) {
+                                  const float* __restrict__ o, float* __restrict__ part, int N, int H, int W, int C) {
   const int c4 = C >> 2;
   const int tq = threadIdx.x % c4;
   const int ty = threadIdx.x / c4, nty = blockDim.x / c4;
@@ -242,7 +245,8 @@ __global__ void k_silu_bwd_reduce(const float* __restrict__ ge, const float* __r
   for (int idx = threadIdx.x; idx < 11 * C; idx += blockDim.x) {
     double t = 0;
     for (int y = 0; y < nty; ++y) t += sred[y * 11 * C + idx];
-    atomicAdd(acc + idx, t);
+    part[(size_t)blockIdx.x * 11 * C + idx] = static_cast<float>(t);   // per-block partial: no atomics (592 blocks x 11C
+                                                                        // double atomics on 11C addresses serialised in L2)
   }
 }
 
@@ -351,7 +355,8 @@ extern "C" size_t ecsy_lif_ecs_bwd_ws_bytes(int T, int64_t N, int H, int W, int 
   const size_t mc = static_cast<size_t>(N) * H * W * C;
   (void)T;
   // gm, ge, G1 (fp32) + ge planes + dw planes (bf16) + reduction scratch
-  return 512 + 3 * al256(mc * 4) + 2 * static_cast<size_t>(splits) * al256(mc * 2) + al256(11 * (size_t)C * 8);
+  return 512 + 3 * al256(mc * 4) + 2 * static_cast<size_t>(splits) * al256(mc * 2) +
+         al256((size_t)ecsy_num_sms() * 4 * 11 * C * 4);   // per-block partial sums of the parameter gradients
 }
 
 extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const float* mem, const float* ecs,
@@ -382,7 +387,7 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
   __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
   __nv_bfloat16* d_lo = nullptr;
   if (splits == 2) { d_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2); }
-  double* acc = reinterpret_cast<double*>(p);
+  float* part = reinterpret_cast<float*>(p);
   const int64_t words = M * (C / 32);
   const int64_t n4 = M * C / 4;
   const int egrid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
@@ -402,11 +407,11 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       if (rc) return rc;
       rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
       if (rc) return rc;
-      ECSY_CUDA(cudaMemsetAsync(acc, 0, 11 * (size_t)C * sizeof(double), st));
-      k_lif_bwd_reduce<<<grid_for(M, 64, ecsy_num_sms() * 4), rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(
-          ge, g1, spikes + t * words, acc, (int)N, H, W, C);
+      const int rgrid = grid_for(M, 64, ecsy_num_sms() * 4);
+      k_lif_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, spikes + t * words, part,
+                                                                                       (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
-      k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(acc, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(part, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
     k_lif_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
@@ -472,7 +477,7 @@ extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const floa
   __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
   __nv_bfloat16* d_lo = nullptr;
   if (splits == 2) { d_lo = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2); }
-  double* acc = reinterpret_cast<double*>(p);
+  float* part = reinterpret_cast<float*>(p);
   const int64_t n4 = M * C / 4;
   const int egrid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
   const int c4 = C / 4;
@@ -491,11 +496,10 @@ extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const floa
       if (rc) return rc;
       rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
       if (rc) return rc;
-      ECSY_CUDA(cudaMemsetAsync(acc, 0, 11 * (size_t)C * sizeof(double), st));
-      k_silu_bwd_reduce<<<grid_for(M, 64, ecsy_num_sms() * 4), rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(
-          ge, g1, o_t, acc, (int)N, H, W, C);
+      const int rgrid = grid_for(M, 64, ecsy_num_sms() * 4);
+      k_silu_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, o_t, part, (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
-      k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(acc, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 255) / 256, 256, 0, st>>>(part, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
     k_silu_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
