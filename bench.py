@@ -162,7 +162,6 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
     F.launches["n"] = 0
     for k in F.flops:
         F.flops[k] = 0.0
-    F.profile_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         ev0.record()
@@ -171,9 +170,14 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         ev1.record()
         barrier()
     ms_total = ev0.elapsed_time(ev1)
-    per_op = F.profile_end()
     launches = F.launches["n"]
     flops = dict(F.flops)
+    # per-operator breakdown from ONE extra step outside the timed region (two CUDA events per operator cost host
+    # time, and the training step is close to launch-bound)
+    F.profile_begin()
+    step(x)
+    barrier()
+    per_op = {k: v * args.steps for k, v in F.profile_end().items()}
     barrier()
     t0 = time.perf_counter()
     loss_host = 0.0
@@ -216,9 +220,31 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         "breakdown_ms_per_step": {k: v / args.steps for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
         "last_loss": loss_host,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, torch warnings) goes to stderr; the ONE JSON line is
+    written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -242,6 +268,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()
+    protect_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -265,7 +292,7 @@ def main():
                                  "sample": f"{args.cpu_sample} image(s)/step of the same workload, oracle port "
                                            "(torch fp32 CPU) of the reference forward"},
                 "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -322,7 +349,6 @@ def main():
         F.launches["n"] = 0
         for k in F.flops:
             F.flops[k] = 0.0
-        F.profile_begin()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
             ev0.record()
@@ -331,9 +357,14 @@ def main():
             ev1.record()
             barrier()
         ms_total = ev0.elapsed_time(ev1)
-        per_op = F.profile_end()
         launches = F.launches["n"]
         flops = dict(F.flops)
+        # per-operator CUDA-event breakdown (and the dominant kernel's duration for `roofline`) from ONE extra step
+        # outside the timed region, scaled to `steps`
+        F.profile_begin()
+        model(x)
+        barrier()
+        per_op = {k: v * args.steps for k, v in F.profile_end().items()}
 
         # end to end through the public API: every step uploads ITS batch from pinned host memory and downloads
         # its decoded detections; the upload of batch i+1 runs on a copy stream while batch i computes.
@@ -409,7 +440,7 @@ def main():
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_sample} image(s)/step x 2 steps of the same workload, oracle "
                                           "port (torch fp32 CPU) of the reference forward"}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
