@@ -40,6 +40,7 @@ SIGNATURES = {
                                _f, _f, _f, _f, _p, _z, _p]),
     "ecsy_spike_conv_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_spike_conv_ts_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ecsy_spike_conv_pair_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_spike_conv_ts_supported": (_i, [_i, _i]),
     "ecsy_spike_conv_prefers_ts": (_i, [_i, _i, _i]),
     "ecsy_pack_spike_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),

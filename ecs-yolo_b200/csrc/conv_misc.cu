@@ -256,6 +256,20 @@ extern "C" int ecsy_spike_conv_ts_fwd(const uint32_t* spikes, const void* w_ts, 
                               Cout, k, stride, pad, STREAM(stream), 1);
 }
 
+// Shared-memory-operand kernel (256-column tiles) on weights in the tensor-memory layout: same {0, 2.0} pair expansion
+// (2 ALU ops per word instead of 4.5), used for the wide layers where ecsy_spike_conv_prefers_ts says no.
+extern "C" int ecsy_spike_conv_pair_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out,
+                                        const float* scale, const float* shift, const float* residual, int64_t res_imgs,
+                                        int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                        void* stream) {
+  ECSY_CHECK_ARG(spikes && w_ts && out && imgs > 0 && H > 0 && W > 0, "spike_conv_pair_fwd: bad arguments");
+  ECSY_CHECK_ARG((scale == nullptr) == (shift == nullptr), "spike_conv_pair_fwd: scale/shift pair");
+  ECSY_CHECK_ARG(!residual || (res_imgs > 0 && imgs % res_imgs == 0), "spike_conv_pair_fwd: residual image count");
+  ECSY_CHECK_ARG(imgs < (1 << 24), "spike_conv_pair_fwd: too many images");
+  return ecsy_umma_spike_conv(spikes, w_ts, splits, out, scale, shift, residual, res_imgs, (int)imgs, H, W, Cin,
+                              Cout, k, stride, pad, STREAM(stream), 3);
+}
+
 extern "C" int ecsy_spike_conv_fwd(const uint32_t* spikes, const void* w_packed, int splits, float* out,
                                    const float* scale, const float* shift, const float* residual, int64_t res_imgs,
                                    int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,

@@ -93,6 +93,7 @@ struct GemmArgs {
   int64_t gx_imgs;     // images in gx (T-broadcast sources repeat)
   int gcin, gK;        // input channels, K = kh*kw*gcin (kb_total*64 >= gK, zero padded)
   uint32_t ktab_off;   // byte offset of the k -> (offset, ky, kx) table in shared memory
+  int pair_expand;     // kASpikes: weights in the ecsy_pack_spike_conv_weight layout, spikes emitted as {0, 2.0} pairs
 };
 
 template <int EPI>
@@ -562,51 +563,80 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
                                     ? (uint32_t)(total_tiles - 1 - (int)blockIdx.x) / gridDim.x + 1 : 0u;
       const uint32_t c_end = my_tiles * kbt;
 
-      auto load_rows = [&](uint32_t c, uint2 (&wd)[4]) {
-        const uint32_t ti = c / kbt;
-        const int kb = (int)(c - ti * kbt);
-        const int tile = (int)blockIdx.x + (int)ti * (int)gridDim.x;
-        const int m_tile = tile / g.n_tiles;
+      // load cursor of this stage group: K block c = (tile, kb) advances by S blocks; the tile is decoded only when it
+      // changes (3 divisions per tile instead of 5 per block)
+      int l_kb = grp, l_tile = (int)blockIdx.x, l_img0 = 0, l_h0 = 0, l_w0 = 0;
+      auto decode_tile = [&]() {
+        const int m_tile = l_tile / g.n_tiles;
         const int tn = m_tile / tiles_hw;
         const int rem = m_tile - tn * tiles_hw;
         const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
-        const int tap = kb / sg.nslab, slab = kb - tap * sg.nslab;
+        l_img0 = tn * sg.tn_b;
+        l_h0 = th * sg.th_b * sg.stride - sg.pad;
+        l_w0 = tw * sg.tw_b * sg.stride - sg.pad;
+      };
+      while (l_kb >= (int)kbt) { l_kb -= (int)kbt; l_tile += (int)gridDim.x; }
+      decode_tile();
+      auto load_rows = [&](uint2 (&wd)[4]) {   // rows of the cursor's block, then advance the cursor by S blocks
+        const int tap = l_kb / sg.nslab, slab = l_kb - tap * sg.nslab;
         const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
-        const int img0 = tn * sg.tn_b;
-        const int hi0 = th * sg.th_b * sg.stride - sg.pad + ky;
-        const int wi0 = tw * sg.tw_b * sg.stride - sg.pad + kx;
+        const int hi0 = l_h0 + ky, wi0 = l_w0 + kx;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           wd[i] = make_uint2(0u, 0u);
           if (i < nrow) {
-            const int img = img0 + n_l[i], hi = hi0 + h_l[i] * sg.stride, wi = wi0 + w_l[i] * sg.stride;
+            const int img = l_img0 + n_l[i], hi = hi0 + h_l[i] * sg.stride, wi = wi0 + w_l[i] * sg.stride;
             if (img < sg.imgs && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
               wd[i] = __ldg(reinterpret_cast<const uint2*>(
                   sg.bits + (((int64_t)img * sg.H + hi) * sg.W + wi) * sg.Cw + slab * 2));
           }
         }
+        l_kb += (int)S;
+        if (l_kb >= (int)kbt) {
+          do { l_kb -= (int)kbt; l_tile += (int)gridDim.x; } while (l_kb >= (int)kbt);
+          decode_tile();
+        }
       };
 
       uint32_t c = (uint32_t)grp;
+      uint32_t wphase = 1;   // parity of the wait on empty[grp] for block c (first use of a fresh barrier passes)
       uint2 cur[4];
-      if (c < c_end) load_rows(c, cur);
+      if (c < c_end) load_rows(cur);
       while (c < c_end) {
         uint2 nxt[4];
-        if (c + S < c_end) load_rows(c + S, nxt);
-        mbar_wait(&ctl->empty[grp], ((c / S) & 1) ^ 1);
+        if (c + S < c_end) load_rows(nxt);
+        mbar_wait(&ctl->empty[grp], wphase);
+        wphase ^= 1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < nrow) {
             uint8_t* row = tile_a + row_off[i];
+            if (g.pair_expand) {
+              // one shift + one mask per packed pair: word jj of a 32-channel half = channels (jj, jj + 16), spike = 2.0
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t byte = ((j < 4 ? cur[i].x : cur[i].y) >> (8 * (j & 3))) & 0xFFu;
-              uint4 o;
-              o.x = bits2_to_bf16x2(byte);
-              o.y = bits2_to_bf16x2(byte >> 2);
-              o.z = bits2_to_bf16x2(byte >> 4);
-              o.w = bits2_to_bf16x2(byte >> 6);
-              *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = o;
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t x = j < 4 ? cur[i].x : cur[i].y;
+                uint4 o;
+                uint32_t w4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int jj = (j & 3) * 4 + u;
+                  w4[u] = (jj < 15 ? (x << (14 - jj < 0 ? 0 : 14 - jj)) : (x >> 1)) & 0x40004000u;
+                }
+                o.x = w4[0]; o.y = w4[1]; o.z = w4[2]; o.w = w4[3];
+                *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t byte = ((j < 4 ? cur[i].x : cur[i].y) >> (8 * (j & 3))) & 0xFFu;
+                uint4 o;
+                o.x = bits2_to_bf16x2(byte);
+                o.y = bits2_to_bf16x2(byte >> 2);
+                o.z = bits2_to_bf16x2(byte >> 4);
+                o.w = bits2_to_bf16x2(byte >> 6);
+                *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = o;
+              }
             }
           }
         }
@@ -1765,7 +1795,10 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
                          const float* shift, const float* residual, int64_t res_imgs, int imgs, int H, int W, int Cin,
                          int Cout, int k, int stride, int pad, cudaStream_t st, int ts) {
   ECSY_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "spike_conv: Cin=%d must be a multiple of 64", Cin);
-  const int BN = ts ? ecsy_pick_bn_ts(Cout) : ecsy_pick_bn(Cout, splits);
+  // ts: 0 = smem operand, natural weight layout; 1 = tensor-memory operand kernel; 2 = tensor-memory operand with the
+  // legacy epilogue; 3 = smem operand (wide tiles) with weights in the tensor-memory layout (pair expansion)
+  const bool tsk = ts == 1 || ts == 2;
+  const int BN = tsk ? ecsy_pick_bn_ts(Cout) : ecsy_pick_bn(Cout, splits);
   ECSY_CHECK_ARG(BN != 0, "spike_conv: Cout=%d must be a multiple of 64", Cout);
   ECSY_CHECK_ARG(splits == 1 || splits == 2, "spike_conv: splits must be 1 or 2");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
@@ -1792,7 +1825,8 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   if (rc) return rc;
   EpiConv e{out, scale, shift, residual, (residual ? res_imgs : (int64_t)imgs) * Ho * Wo, Cout, 0};
   const int patch_bytes = sg.PP * Cw * 4;
-  if (ts) {
+  g.pair_expand = ts == 3 ? 1 : 0;
+  if (tsk) {
     // TMA-store epilogue unless a T-broadcast residual would straddle the wrap inside one tile box
     const int64_t rimgs = residual ? res_imgs : imgs;
     const bool tma_epi = ts != 2 && (residual == nullptr || rimgs == imgs || rimgs % sg.tn_b == 0);

@@ -489,10 +489,12 @@ def spike_conv(s: Spikes, w: ConvW, scale=None, shift=None, residual: Optional[A
         assert (residual.N, residual.H, residual.W, residual.C) == (N, Ho, Wo, w.co), "residual shape"
     flops["spike_conv"] += 2.0 * T * N * Ho * Wo * w.co * s.C * w.k * w.k
     ts = w.packed_ts is not None and _use_ts(s.C, w.co, w.splits)
+    pair = (not ts) and w.packed_ts is not None and _state["conv_ts"] != "off"   # smem operand, tensor-memory weight layout
     L = _cabi.lib()
+    fn = L.ecsy_spike_conv_ts_fwd if ts else (L.ecsy_spike_conv_pair_fwd if pair else L.ecsy_spike_conv_fwd)
     with _timed("spike_conv", 1):
-        _cabi.check((L.ecsy_spike_conv_ts_fwd if ts else L.ecsy_spike_conv_fwd)(
-            _p(s.bits), _p(w.packed_ts if ts else w.packed), w.splits, _p(out), _p(scale), _p(shift),
+        _cabi.check(fn(
+            _p(s.bits), _p(w.packed_ts if (ts or pair) else w.packed), w.splits, _p(out), _p(scale), _p(shift),
             _p(residual.data) if residual is not None else None, residual.src_imgs if residual is not None else 0,
             T * N, H, W, s.C, w.co, w.k, w.stride, w.pad, _st()), "spike_conv_fwd")
     return Act(out, T)

@@ -92,6 +92,10 @@ int ecsy_pack_spike_conv_weight(const float* w, void* out_bf16, int Co, int Ci, 
                                 void* stream);
 int ecsy_spike_conv_ts_supported(int Cin, int Cout);
 int ecsy_spike_conv_prefers_ts(int Cin, int Cout, int splits);   /* measured dispatch rule (wide layers keep smem A) */
+/* shared-memory-operand kernel (wide 256-column tiles) on the same w_ts weights: the layers prefers_ts rejects */
+int ecsy_spike_conv_pair_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out, const float* scale,
+                             const float* shift, const float* residual, int64_t res_imgs, int64_t imgs, int H, int W,
+                             int Cin, int Cout, int k, int stride, int pad, void* stream);
 int ecsy_spike_conv_ts_fwd(const uint32_t* spikes, const void* w_ts, int splits, float* out, const float* scale,
                            const float* shift, const float* residual, int64_t res_imgs, int64_t imgs, int H, int W,
                            int Cin, int Cout, int k, int stride, int pad, void* stream);

@@ -72,6 +72,8 @@ def test_spike_conv(name, mode, tol, ts):
     (128, 256, 3, 2, 30, 30, 4, 2),     # stride 2, two N tiles of 128
     (192, 128, 3, 1, 12, 20, 2, 3),     # three slabs per tap
     (512, 512, 3, 1, 20, 20, 2, 4),     # deep K (72 blocks), four N tiles
+    (256, 256, 3, 1, 23, 17, 3, 2),     # wide + ragged: the pair-expansion smem-operand kernel in "auto" mode
+    (384, 256, 1, 1, 9, 9, 2, 2),
 ])
 def test_spike_conv_tmem_operand(ci, co, k, s, H, W, N, T, mode):
     """The tensor-memory operand path against fp64 conv2d on the same bf16-rounded (fast) / fp32 (parity) weights,
@@ -95,6 +97,11 @@ def test_spike_conv_tmem_operand(ci, co, k, s, H, W, N, T, mode):
         ref = ref.reshape(T, N, co, *ref.shape[-2:]).float()
         assert rel_l2(out_ts, ref) < 2e-5
         assert rel_l2(out_ts, out_ss) < 1e-5
+        # "auto": wide layers (Cout % 256 == 0, Cin >= 256, single plane) take the smem-operand kernel on the SAME
+        # tensor-memory-layout weights (pair expansion); everything else the tensor-memory kernel
+        F.set_conv_ts("auto")
+        out_auto = F.spike_conv(sp, cw).to_ref().cpu()
+        assert rel_l2(out_auto, ref) < 2e-5
         # folded tdBN affine + full / T-broadcast residual through the TMA-store epilogue
         F.set_conv_ts(True)
         sc = torch.rand(co, generator=g) + 0.5
