@@ -761,7 +761,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
 // Warps: 0-3 epilogue group 0, 4-7 epilogue group 1, 8 TMA producer (weights), 9 MMA issuer + TMEM allocator,
 // 10-17 spike expanders (lane quarter = warp % 4, two warps per quarter alternate K blocks).
 // ---------------------------------------------------------------------------------------------
-constexpr int kTsThreads = 576;
+constexpr int kTsThreads = 576;     // V = 1: 8 expander warps, one K block per barrier round
+constexpr int kTsThreads2 = 832;    // V = 2: 16 expander warps, two K blocks per barrier round
 constexpr int kTsSlice = 128 * 128;   // staging slice: 128 rows x 32 fp32
 constexpr int kTsMaxBuf = 3;
 
@@ -810,11 +811,17 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int BN, int B_SPLIT>
-__global__ void __launch_bounds__(kTsThreads, 1)
+// V = 2 ("rounds"): the single MMA-issuer warp needs ~430 cycles of its own instructions per barrier round and an
+// expander warp ~1000 cycles per K block (single-warp issue latency), against a 128 / 256-cycle MMA per K block at
+// N = 64 / 128.  So a barrier round covers TWO K blocks (one wait / commit per 8 MMAs, A ring stages of 64 TMEM
+// columns, weight stages of two tiles) and four expander warps share a lane quarter (warp e expands the K blocks
+// kb = e mod 4 of every tile; a tile with an odd block count gets a phantom block that only synchronises).
+template <int BN, int B_SPLIT, int V>
+__global__ void __launch_bounds__(V == 2 ? kTsThreads2 : kTsThreads, 1)
 k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ CUtensorMap tm_res, const TsArgs g, const SpikeGeom sg) {
   static_assert(BN == 64 || BN == 128, "accumulators + A ring must fit 512 TMEM columns");
+  constexpr int kNT = V == 2 ? kTsThreads2 : kTsThreads;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kBTileBytes = BN * 128;
@@ -833,8 +840,8 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_out);
     if (g.has_res) tma_prefetch_desc(&tm_res);
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&ctl->full_a[s], 4);
+    for (int s = 0; s < kTsMaxStages; ++s) {
+      mbar_init(&ctl->full_a[s], V == 2 ? 8 : 4);
       mbar_init(&ctl->full_b[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
@@ -847,7 +854,7 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
   }
   if (warp == 9) tmem_alloc<512>(&ctl->tmem_base);
   if (g.scale != nullptr)
-    for (int i = threadIdx.x; i < g.cout; i += kTsThreads) {
+    for (int i = threadIdx.x; i < g.cout; i += kNT) {
       s_scale[i] = g.scale[i];
       s_shift[i] = g.shift[i];
     }
@@ -856,7 +863,40 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp == 8) {
+  if (warp == 8 && V == 2) {
+    // =============================== TMA producer (rounds of two K blocks) ===============================
+    const int kbt = g.kb_total, R = (kbt + 1) >> 1;
+    if (g.resident) {   // every weight K block has its own slot and barrier, loaded once
+      if (lane == 0 && (int)blockIdx.x < total_tiles)
+        for (int kb = 0; kb < kbt; ++kb) {
+          uint8_t* st = smem + (size_t)kb * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->full_b[kb], (uint32_t)kStageBytes);
+#pragma unroll
+          for (int bs = 0; bs < B_SPLIT; ++bs)
+            tma_load_2d(st + bs * kBTileBytes, &tm_b, &ctl->full_b[kb], kb * 64, bs * (g.n_tiles * BN));
+        }
+    } else {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % g.n_tiles;
+        for (int r = 0; r < R; ++r) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          if (lane == 0) {
+            const int nb = (2 * r + 1 < kbt) ? 2 : 1;
+            uint8_t* st = smem + (size_t)stage * (2 * kStageBytes);
+            mbar_arrive_expect_tx(&ctl->full_b[stage], (uint32_t)(nb * kStageBytes));
+            for (int h = 0; h < nb; ++h)
+#pragma unroll
+              for (int bs = 0; bs < B_SPLIT; ++bs)
+                tma_load_2d(st + h * kStageBytes + bs * kBTileBytes, &tm_b, &ctl->full_b[stage], (2 * r + h) * 64,
+                            bs * (g.n_tiles * BN) + n_tile * BN);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 8) {
     // =============================== TMA producer: weight tiles ===============================
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -870,6 +910,51 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
 #pragma unroll
           for (int bs = 0; bs < B_SPLIT; ++bs)
             tma_load_2d(st + bs * kBTileBytes, &tm_b, &ctl->full_b[stage], kb * 64, bs * (g.n_tiles * BN) + n_tile * BN);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9 && V == 2) {
+    // =============================== MMA issuer (rounds of two K blocks) ===============================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    const int kbt = g.kb_total, R = (kbt + 1) >> 1;
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[buf], bphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int r = 0; r < R; ++r) {
+        const int nb = (2 * r + 1 < kbt) ? 2 : 1;
+        if (g.resident) {
+          if (it == 0) {
+            mbar_wait(&ctl->full_b[2 * r], 0);
+            if (nb == 2) mbar_wait(&ctl->full_b[2 * r + 1], 0);
+          }
+        } else {
+          mbar_wait(&ctl->full_b[stage], phase);
+        }
+        mbar_wait(&ctl->full_a[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t b_addr = smem_u32(smem) + (g.resident ? (uint32_t)(2 * r) * (uint32_t)kStageBytes
+                                                               : stage * (uint32_t)(2 * kStageBytes));
+          const uint32_t a_tmem = tmem_base + 2 * BN + stage * 64;
+          uint32_t acc = r > 0 ? 1u : 0u;
+          for (int h = 0; h < nb; ++h) {
+#pragma unroll
+            for (int bs = 0; bs < B_SPLIT; ++bs) {
+              const uint64_t db = umma_desc_sw128(b_addr + h * kStageBytes + bs * kBTileBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_ts(d_tmem, a_tmem + h * 32 + k * 8, db + (uint64_t)(k * 2), idesc, acc);
+                acc = 1u;
+              }
+            }
+          }
+          umma_commit(&ctl->empty[stage]);
+          if (r == R - 1) umma_commit(&ctl->tmem_full[buf]);
         }
         __syncwarp();
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
@@ -906,6 +991,127 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
         }
         __syncwarp();
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 10 && V == 2) {
+    // =============================== spike expanders, four warps per lane quarter ===============================
+    constexpr int kPf = 4;
+    const int q = warp & 3;
+    const int e = (warp - 10) >> 2;                 // this warp expands the (padded) K blocks kb = e mod 4 of every tile
+    const int r = q * 32 + lane;
+    const int w_l = r & (sg.tw_b - 1);
+    const int h_l = (r >> sg.tw_sh) & (sg.th_b - 1);
+    const int n_l = r >> (sg.tw_sh + sg.th_sh);
+    const uint32_t S = (uint32_t)g.stages;
+    const int kbt = g.kb_total, R = (kbt + 1) >> 1, KP = 2 * R;
+    const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t a_row = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN;
+    const int tapw = sg.Cw, roww = sg.W * sg.Cw;
+    if (e < KP && my_tiles > 0) {
+      // ---- load cursor (tile digits in the mixed radix (n_tile, tile_w, tile_h, tile_n); no divisions per block) ----
+      int l_ti = 0, l_kb = e, l_ky = 0, l_kx = 0, l_slab = e;
+      int d_n, d_w, d_h, d_t, s_n, s_w, s_h, s_t;
+      {
+        int v = (int)blockIdx.x;
+        d_n = v % g.n_tiles; v /= g.n_tiles;
+        d_w = v % sg.tiles_w; v /= sg.tiles_w;
+        d_h = v % sg.tiles_h; d_t = v / sg.tiles_h;
+        v = (int)gridDim.x;
+        s_n = v % g.n_tiles; v /= g.n_tiles;
+        s_w = v % sg.tiles_w; v /= sg.tiles_w;
+        s_h = v % sg.tiles_h; s_t = v / sg.tiles_h;
+      }
+      int l_hi0 = 0, l_wi0 = 0;
+      const uint32_t* l_row0 = nullptr;
+      bool l_ok = false;
+      auto set_tile = [&]() {
+        const int img = d_t * sg.tn_b + n_l;
+        l_ok = img < sg.imgs;
+        l_hi0 = (d_h * sg.th_b + h_l) * sg.stride - sg.pad;
+        l_wi0 = (d_w * sg.tw_b + w_l) * sg.stride - sg.pad;
+        l_row0 = sg.bits + ((int64_t)(l_ok ? img : 0) * sg.H + l_hi0) * roww + (int64_t)l_wi0 * tapw;
+      };
+      auto norm_slab = [&]() {
+        while (l_slab >= sg.nslab) {
+          l_slab -= sg.nslab;
+          if (++l_kx == sg.kw) { l_kx = 0; ++l_ky; }
+        }
+      };
+      auto l_advance = [&]() {
+        l_kb += 4;
+        if (l_kb >= KP) {
+          l_kb = e; ++l_ti;
+          d_n += s_n;
+          int cy = d_n >= g.n_tiles ? 1 : 0;
+          d_n -= cy ? g.n_tiles : 0;
+          d_w += s_w + cy;
+          cy = d_w >= sg.tiles_w ? 1 : 0;
+          d_w -= cy ? sg.tiles_w : 0;
+          d_h += s_h + cy;
+          cy = d_h >= sg.tiles_h ? 1 : 0;
+          d_h -= cy ? sg.tiles_h : 0;
+          d_t += s_t + cy;
+          set_tile();
+          l_slab = e; l_ky = 0; l_kx = 0;
+        } else {
+          l_slab += 4;
+        }
+        norm_slab();
+      };
+      auto load_cur = [&]() -> uint2 {
+        uint2 v = make_uint2(0u, 0u);
+        if (l_ti < my_tiles && l_kb < kbt) {
+          const int hi = l_hi0 + l_ky, wi = l_wi0 + l_kx;
+          if (l_ok && (unsigned)hi < (unsigned)sg.H && (unsigned)wi < (unsigned)sg.W)
+            v = __ldg(reinterpret_cast<const uint2*>(l_row0 + (l_ky * roww + l_kx * tapw + l_slab * 2)));
+        }
+        return v;
+      };
+      set_tile();
+      norm_slab();
+      uint2 pf[kPf];
+#pragma unroll
+      for (int j = 0; j < kPf; ++j) {
+        pf[j] = load_cur();
+        l_advance();
+      }
+      // ---- consume cursor: (tile, kb) -> round -> A stage / wait parity, advanced incrementally ----
+      int c_ti = 0, c_kb = e;
+      uint32_t stage = (uint32_t)(e >> 1) % S, sphase = (((uint32_t)(e >> 1) / S) & 1u) ^ 1u;
+      while (c_ti < my_tiles) {
+#pragma unroll
+        for (int j = 0; j < kPf; ++j) {
+          if (c_ti < my_tiles) {
+            const uint2 cur = pf[j];
+            pf[j] = load_cur();
+            l_advance();
+            const bool phantom = c_kb >= kbt;
+            mbar_wait(&ctl->empty[stage], sphase);
+            if (!phantom) {
+              tc_fence_after_sync();
+              const uint32_t dst = a_row + stage * 64 + (uint32_t)(c_kb & 1) * 32u;
+#pragma unroll
+              for (int hw = 0; hw < 2; ++hw) {   // 16 columns at a time: 832 threads leave 72 registers per thread
+                const uint32_t x = hw == 0 ? cur.x : cur.y;
+                uint32_t v[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj)
+                  v[jj] = (jj < 15 ? (x << (14 - jj < 0 ? 0 : 14 - jj)) : (x >> 1)) & 0x40004000u;
+                tmem_st_32x16(dst + hw * 16, v);
+              }
+              tmem_st_wait();
+              tc_fence_before_sync();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->full_a[stage]);
+            const int r_old = c_kb >> 1;
+            c_kb += 4;
+            uint32_t dr = 2;
+            if (c_kb >= KP) { c_kb = e; ++c_ti; dr = (uint32_t)(R - r_old + (e >> 1)); }
+            stage += dr;
+            while (stage >= S) { stage -= S; sphase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp >= 10) {
@@ -1740,47 +1946,65 @@ int ecsy_pick_bn(int cout, int splits) {
 
 // Spike convolution: out[imgs][Ho][Wo][Cout] = conv(spikes, W) (*scale + shift) (+ residual)
 namespace {
-template <int BN, int B_SPLIT>
-int launch_ts(const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres, TsArgs g, const SpikeGeom& sg,
-              cudaStream_t st) {
-  auto kern = k_spike_conv_ts<BN, B_SPLIT>;
+template <int BN, int B_SPLIT, int V>
+int launch_ts_v(const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres, TsArgs g, const SpikeGeom& sg,
+                cudaStream_t st) {
+  auto kern = k_spike_conv_ts<BN, B_SPLIT, V>;
   static bool attr = false;
   if (!attr) {
     ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr = true;
   }
-  constexpr int stage_bytes = B_SPLIT * BN * 128;
+  constexpr int block_bytes = B_SPLIT * BN * 128;            // one weight K block
+  constexpr int stage_bytes = V == 2 ? 2 * block_bytes : block_bytes;
+  constexpr int tmem_stages = (512 - 2 * BN) / (V == 2 ? 64 : 32);
   const int aff_bytes = (2 * g.cout * 4 + 127) & ~127;
   const int fixed = 1024 + aff_bytes + (int)sizeof(TsCtl) + 128;
-  g.nbuf = g.has_res ? 3 : 2;
-  int stages = (kSmemLimit - fixed - 2 * g.nbuf * kTsSlice) / stage_bytes;
-  if (stages < 4 && g.nbuf == 3) {   // split-weight mode: the wider weight ring matters more than the residual prefetch
-    g.nbuf = 2;
-    stages = (kSmemLimit - fixed - 2 * g.nbuf * kTsSlice) / stage_bytes;
-  }
-  const int tmem_stages = (512 - 2 * BN) / 32;
-  // all weight K blocks resident (n_tiles == 1: one weight panel for every tile of the CTA)?
   static const bool allow_res = getenv("ECSY_TS_RESIDENT") == nullptr || getenv("ECSY_TS_RESIDENT")[0] != '0';
-  g.resident = (allow_res && g.n_tiles == 1 && g.kb_total >= 4 && g.kb_total <= stages && g.kb_total <= tmem_stages &&
-                g.kb_total <= kTsMaxStages) ? 1 : 0;
-  if (g.resident) stages = g.kb_total;
-  if (stages > tmem_stages) stages = tmem_stages;
-  if (stages > 8) stages = g.resident ? stages : 8;
+  g.nbuf = g.has_res ? 3 : 2;
+  // all weight K blocks resident (n_tiles == 1: one weight panel for every tile of the CTA)?
+  int b_bytes = 0, stages = 0;
+  auto plan = [&]() {
+    const int avail = kSmemLimit - fixed - 2 * g.nbuf * kTsSlice;
+    g.resident = (allow_res && g.n_tiles == 1 && g.kb_total >= 4 && g.kb_total <= kTsMaxStages &&
+                  g.kb_total * block_bytes <= avail && (V == 2 || g.kb_total <= tmem_stages)) ? 1 : 0;
+    if (g.resident) {
+      b_bytes = g.kb_total * block_bytes;
+      stages = V == 2 ? tmem_stages : g.kb_total;
+    } else {
+      stages = avail / stage_bytes;
+      if (stages > tmem_stages) stages = tmem_stages;
+      if (stages > 8) stages = 8;
+      b_bytes = stages * stage_bytes;
+    }
+  };
+  plan();
+  if (!g.resident && stages < (V == 2 ? 3 : 4) && g.nbuf == 3) {   // the weight ring matters more than the residual prefetch
+    g.nbuf = 2;
+    plan();
+  }
   if (stages < 2) {
     ecsy_set_error("spike_conv_ts: shared memory budget allows only %d stage(s)", stages);
     return ECSY_ERR_UNSUPPORTED;
   }
   g.stages = stages;
-  g.stg_off = (uint32_t)stages * stage_bytes;                       // multiples of 8 KB: 1024-aligned
+  g.stg_off = (uint32_t)b_bytes;                                    // multiples of 8 KB: 1024-aligned
   g.aff_off = g.stg_off + 2u * (uint32_t)g.nbuf * kTsSlice;
   g.ctl_off = g.aff_off + (uint32_t)aff_bytes;
   const int smem = 1024 + (int)g.ctl_off + (int)sizeof(TsCtl) + 64;
   int grid = g.m_tiles * g.n_tiles;
   const int sms = ecsy_num_sms();
   if (grid > sms) grid = sms;
-  kern<<<grid, kTsThreads, smem, st>>>(tb, tout, tres, g, sg);
+  kern<<<grid, V == 2 ? kTsThreads2 : kTsThreads, smem, st>>>(tb, tout, tres, g, sg);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
+}
+
+template <int BN, int B_SPLIT>
+int launch_ts(const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres, const TsArgs& g, const SpikeGeom& sg,
+              cudaStream_t st) {
+  static const bool v2 = getenv("ECSY_TS_V2") == nullptr || getenv("ECSY_TS_V2")[0] != '0';
+  return v2 ? launch_ts_v<BN, B_SPLIT, 2>(tb, tout, tres, g, sg, st) : launch_ts_v<BN, B_SPLIT, 1>(tb, tout, tres, g, sg, st);
 }
 }  // namespace
 

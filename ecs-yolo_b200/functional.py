@@ -85,7 +85,7 @@ def set_conv_ts(mode) -> None:
         mode = "all"
     elif mode is False:
         mode = "off"
-    if mode not in ("auto", "all", "off"):
+    if mode not in ("auto", "all", "off", "pair"):
         raise ValueError(mode)
     _state["conv_ts"] = mode
 
@@ -102,7 +102,7 @@ def conv_ts_enabled() -> bool:
 
 def _use_ts(ci: int, co: int, splits: int) -> bool:
     m = _state["conv_ts"]
-    if m == "off":
+    if m in ("off", "pair"):     # "pair": shared-memory operand kernel on tensor-memory-layout weights everywhere
         return False
     L = _cabi.lib()
     return bool(L.ecsy_spike_conv_ts_supported(ci, co) if m == "all" else L.ecsy_spike_conv_prefers_ts(ci, co, splits))
