@@ -48,7 +48,10 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
   __nv_bfloat16* a_lo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
   const int64_t words = M * (C / 32);
 
-  float* mem0 = mem_save ? mem_save : (T > 1 ? mem : nullptr);
+  // mem_0 == x_0 when no affine is pending on the input current (inference: tdBN is folded into the producing conv), so
+  // step 0 only thresholds and the first ECS step reads its membrane straight from x_0: no 4 B/elem copy.
+  const bool alias0 = in_scale == nullptr && mem_save == nullptr;
+  float* mem0 = mem_save ? mem_save : ((T > 1 && !alias0) ? mem : nullptr);
   int rc = ecsy_launch_lif_first(x, in_scale, in_shift, mem0, spikes, M, C, thresh, st);
   if (rc) return rc;
   for (int t = 0; t + 1 < T; ++t) {
@@ -75,7 +78,7 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
       s.mem_in = mem_save + (size_t)t * mc;
       s.mem_out = mem_save + (size_t)(t + 1) * mc;
     } else {
-      s.mem_in = mem;
+      s.mem_in = (t == 0 && alias0) ? x : mem;
       s.mem_out = more ? mem : nullptr;
     }
     s.ecs = ecs;
