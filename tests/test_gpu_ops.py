@@ -74,6 +74,7 @@ def test_spike_conv(name, mode, tol, ts):
     (512, 512, 3, 1, 20, 20, 2, 4),     # deep K (72 blocks), four N tiles
     (256, 256, 3, 1, 23, 17, 3, 2),     # wide + ragged: the pair-expansion smem-operand kernel in "auto" mode
     (384, 256, 1, 1, 9, 9, 2, 2),
+    (64, 192, 3, 1, 14, 18, 2, 2),      # three N tiles of 64: weight ring (not resident), tile-major order
 ])
 def test_spike_conv_tmem_operand(ci, co, k, s, H, W, N, T, mode):
     """The tensor-memory operand path against fp64 conv2d on the same bf16-rounded (fast) / fp32 (parity) weights,
@@ -347,3 +348,49 @@ def test_real_conv_implicit(ci, co, k, H, W, N, T, mode, tol):
         assert err < tol, err
     finally:
         F.set_precision("parity")
+
+
+def test_full_size_cross_checks():
+    """BASELINE-size tensors (resnet34 stage-1 shapes at batch 64, T = 4: 1.7 GB activations), checked through
+    independence instead of a CPU oracle: the tensor-memory and the shared-memory operand conv kernels must agree, and the
+    fused all-T-on-chip LIF kernel must agree with the per-timestep pipeline; plus linearity of the conv in its weights."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision("fast")
+    try:
+        T, N, C, H = 4, 64, 64, 160
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.randn(T, N, H, H, C, device="cuda", generator=g) * 0.5 + 0.1
+        inp = S.lif_inputs(dict(T=1, N=1, C=C, H=2, W=2, seed=5))
+        w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+        a = F.Act(x, T)
+        F.set_lif_fused(False)
+        sp = F.lif_ecs(a, w)
+        F.set_lif_fused(True)
+        spf = F.lif_ecs(a, w)
+        F.set_lif_fused(False)
+        assert torch.equal(sp.bits[0], spf.bits[0])                       # step 0 is exact
+        words = int((sp.bits != spf.bits).sum())                           # 32-spike words with any difference
+        assert words / sp.bits.numel() < 2e-2, words / sp.bits.numel()     # (fp16 vs fp32 trace, bf16 folded weights)
+        rate = float(sp.to_act().data[:, :4].mean())
+        assert 0.05 < rate < 0.6
+        del x, a, spf
+        w1 = torch.randn(C, C, 3, 3, device="cuda", generator=g) * 0.05
+        w2 = torch.randn(C, C, 3, 3, device="cuda", generator=g) * 0.05
+        F.set_conv_ts("all")
+        y_ts = F.spike_conv(sp, F.make_conv_w(w1, None, 1, 1, 1, True, False)).data
+        F.set_conv_ts("off")
+        y_ss = F.spike_conv(sp, F.make_conv_w(w1, None, 1, 1, 1, True, False)).data
+        assert rel_l2(y_ts[:, :8], y_ss[:, :8]) < 1e-5 and float((y_ts - y_ss).abs().max()) < 1e-3
+        del y_ss
+        F.set_conv_ts("auto")
+        y2 = F.spike_conv(sp, F.make_conv_w(w2, None, 1, 1, 1, True, False)).data
+        # linearity in the (bf16-rounded) weights: conv(s, q(w1) + q(w2)) == conv(s, w1) + conv(s, w2)
+        w12 = w1.bfloat16().float() + w2.bfloat16().float()
+        F.set_precision("parity")
+        y12 = F.spike_conv(sp, F.make_conv_w(w12, None, 1, 1, 1, True, False)).data
+        assert rel_l2(y12[:, :8], (y_ts + y2)[:, :8]) < 2e-5
+    finally:
+        F.set_precision("parity")
+        F.set_conv_ts("auto")
+        F.set_lif_fused(False)
