@@ -1007,7 +1007,88 @@ k_spike_conv_ts(const __grid_constant__ CUtensorMap tm_b, const __grid_constant_
     const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t a_row = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN;
     const int tapw = sg.Cw, roww = sg.W * sg.Cw;
-    if (e < KP && my_tiles > 0) {
+    static const bool kFastTap = true;
+    if (kFastTap && sg.nslab == 1 && KP <= 12 && g.n_tiles == 1) {
+      // ---- one 64-channel slab (Cin = 64): K block = filter tap.  Tile-level code: this warp's taps kb = e, e+4, e+8 are
+      // fixed for the whole kernel, a tile costs one pixel decode + up to three guarded 8-byte loads (requested one
+      // tile ahead) -- no per-block cursor arithmetic (the kernel is bound by exactly that skeleton).
+      if (e < KP && my_tiles > 0) {
+        int tky[3], tkx[3], toff[3];
+        bool town[3], treal[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int kb = e + 4 * i;
+          town[i] = kb < KP;
+          treal[i] = kb < kbt;
+          tky[i] = kb / sg.kw;
+          tkx[i] = kb - tky[i] * sg.kw;
+          toff[i] = (tky[i] * sg.W + tkx[i]) * tapw;
+        }
+        int d_w, d_h, d_t, s_w, s_h, s_t;
+        {
+          int v = (int)blockIdx.x;
+          d_w = v % sg.tiles_w; v /= sg.tiles_w;
+          d_h = v % sg.tiles_h; d_t = v / sg.tiles_h;
+          v = (int)gridDim.x;
+          s_w = v % sg.tiles_w; v /= sg.tiles_w;
+          s_h = v % sg.tiles_h; s_t = v / sg.tiles_h;
+        }
+        auto load_tile = [&](uint2 (&wd)[3]) {   // this thread's pixel of the tile at the cursor, then advance the cursor
+          const int img = d_t * sg.tn_b + n_l;
+          const int hi0 = (d_h * sg.th_b + h_l) * sg.stride - sg.pad;
+          const int wi0 = (d_w * sg.tw_b + w_l) * sg.stride - sg.pad;
+          const bool ok = img < sg.imgs;
+          const uint32_t* base = sg.bits + ((int64_t)(ok ? img : 0) * sg.H + hi0) * roww + (int64_t)wi0 * tapw;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            wd[i] = make_uint2(0u, 0u);
+            if (treal[i] && ok && (unsigned)(hi0 + tky[i]) < (unsigned)sg.H && (unsigned)(wi0 + tkx[i]) < (unsigned)sg.W)
+              wd[i] = __ldg(reinterpret_cast<const uint2*>(base + toff[i]));
+          }
+          d_w += s_w;
+          int cy = d_w >= sg.tiles_w ? 1 : 0;
+          d_w -= cy ? sg.tiles_w : 0;
+          d_h += s_h + cy;
+          cy = d_h >= sg.tiles_h ? 1 : 0;
+          d_h -= cy ? sg.tiles_h : 0;
+          d_t += s_t + cy;
+        };
+        uint2 nxt[3];
+        load_tile(nxt);
+        uint32_t stage = (uint32_t)(e >> 1) % S, sphase = (((uint32_t)(e >> 1) / S) & 1u) ^ 1u;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          uint2 cur[3] = {nxt[0], nxt[1], nxt[2]};
+          if (ti + 1 < my_tiles) load_tile(nxt);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            if (town[i]) {
+              const int kb = e + 4 * i;
+              mbar_wait(&ctl->empty[stage], sphase);
+              if (treal[i]) {
+                tc_fence_after_sync();
+                const uint32_t dst = a_row + stage * 64 + (uint32_t)(kb & 1) * 32u;
+#pragma unroll
+                for (int hw = 0; hw < 2; ++hw) {
+                  const uint32_t x = hw == 0 ? cur[i].x : cur[i].y;
+                  uint32_t v[16];
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj)
+                    v[jj] = (jj < 15 ? (x << (14 - jj < 0 ? 0 : 14 - jj)) : (x >> 1)) & 0x40004000u;
+                  tmem_st_32x16(dst + hw * 16, v);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ctl->full_a[stage]);
+              const bool last = (i == 2) || !(e + 4 * (i + 1) < KP);     // last own block of this tile
+              stage += last ? (uint32_t)(R - (kb >> 1) + (e >> 1)) : 2u;
+              while (stage >= S) { stage -= S; sphase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (e < KP && my_tiles > 0) {
       // ---- load cursor (tile digits in the mixed radix (n_tile, tile_w, tile_h, tile_n); no divisions per block) ----
       int l_ti = 0, l_kb = e, l_ky = 0, l_kx = 0, l_slab = e;
       int d_n, d_w, d_h, d_t, s_n, s_w, s_h, s_t;
