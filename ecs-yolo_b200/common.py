@@ -79,8 +79,9 @@ class mem_update(nn.Module):
 
     def _weights(self) -> F_.LifW:
         dw, pw = self.spread[0], self.spread[1]
+        Cp = F_.pad64(dw.weight.shape[0])   # narrow layers (res*-ee.yaml front: 3 / 32 channels) run zero-padded
         return _cached(self, "lif", (dw.weight, dw.bias, pw.weight, pw.bias),
-                       lambda: F_.make_lif_w(dw.weight, dw.bias, pw.weight, pw.bias))
+                       lambda: F_.make_lif_w(dw.weight, dw.bias, pw.weight, pw.bias, Cp))
 
     def analog(self, x: Act, affine=None) -> Act:
         """act=True: real-valued silu(mem) outputs (class Conv)."""
@@ -126,9 +127,32 @@ class Snn_Conv2d(nn.Conv2d):
         return _cached(self, "conv", (self.weight, self.bias),
                        lambda: F_.make_conv_w(self.weight, self.bias, s, p, self.groups, umma, True, densify=True))
 
+    def _w_padded(self, cip: int, cop: int) -> F_.ConvW:
+        """Weight zero-padded to [cop, cip, k, k]: narrow layers on the 64-channel tensor-core granule."""
+        k, s, p = self._geom()
+
+        def build():
+            w = torch.nn.functional.pad(self.weight.detach().float(),
+                                        (0, 0, 0, 0, 0, cip - self.in_channels, 0, cop - self.out_channels))
+            return F_.make_conv_w(w, None, s, p, 1, True, False)
+        return _cached(self, "conv_pad", (self.weight,), build)
+
     def conv_spikes(self, sp: Spikes, scale=None, shift=None, residual: Optional[Act] = None) -> Act:
-        if self.umma_ok() and self.in_channels % 64 == 0:
+        if sp.Cr != self.in_channels:
+            raise RuntimeError(f"Snn_Conv2d: {sp.Cr} spike channels for a {self.in_channels}-channel conv")
+        if self.umma_ok() and sp.C == self.in_channels:
             return F_.spike_conv(sp, self._w(), scale, shift, residual)
+        if self.bias is None and self.groups == 1:
+            # narrow input and / or output (res*-ee.yaml: 3 -> 32 -> 32 -> 64): same tcgen05 kernel on padded weights
+            co, cop = self.out_channels, F_.pad64(self.out_channels)
+            w = self._w_padded(sp.C, cop)
+            if cop == co:
+                return F_.spike_conv(sp, w, scale, shift, residual)
+            if scale is not None:
+                scale, shift = F_.pad_channels(scale, cop), F_.pad_channels(shift, cop)
+            y = F_.spike_conv(sp, w, scale, shift, None)
+            y = Act(y.data[..., :co].contiguous(), y.T)
+            return F_.affine_add(y, None, None, residual) if residual is not None else y
         y = F_.real_conv(sp.to_act(), self._w(), scale, shift)
         return F_.affine_add(y, None, None, residual) if residual is not None else y
 
@@ -292,8 +316,11 @@ class Concat_res2(nn.Module):
 
     def __init__(self, in_channels, out_channels, k_size=3, stride=1, ECS=False):
         super().__init__()
+        self._build(in_channels, out_channels, out_channels, k_size, stride)
+
+    def _build(self, in_channels, hid, out_channels, k_size, stride):
         pad = 1 if k_size == 3 else 0
-        self.residual_function = _make_residual(in_channels, out_channels, out_channels, k_size, stride, pad)
+        self.residual_function = _make_residual(in_channels, hid, out_channels, k_size, stride, pad)
         self.shortcut = nn.Sequential()
         if in_channels < out_channels:
             self.shortcut = nn.Sequential(
@@ -318,6 +345,54 @@ class Concat_res2(nn.Module):
                 temp = F_.affine_add(temp, aff[0], aff[1])
         sc = F_.concat_channels([temp, a], pool=self.pools.stride[1])
         return _residual_path(self.residual_function, a, sc).to_ref()
+
+
+class BasicBlock_ms(nn.Module):
+    """models/common.py:1658-1687 (res*-ee.yaml, the original EMS-YOLO block): hidden width e*out; the shortcut is
+    max-pool -> 1x1 conv on the REAL input -> tdBN, with no neuron in front of the conv."""
+
+    def __init__(self, in_channels, out_channels, k_size=3, stride=1, e=0.5):
+        super().__init__()
+        pad = 1 if k_size == 3 else 0
+        self.residual_function = _make_residual(in_channels, int(out_channels * e), out_channels, k_size, stride, pad)
+        self.shortcut = nn.Sequential()
+        if stride != 1 or in_channels != out_channels:
+            self.shortcut = nn.Sequential(
+                nn.MaxPool3d((1, stride, stride), stride=(1, stride, stride)),
+                Snn_Conv2d(in_channels, out_channels, kernel_size=1, stride=1, bias=False),
+                batch_norm_2d(out_channels),
+            )
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import autograd as AG
+        if AG.wants_grad(self, x):
+            raise NotImplementedError("BasicBlock_ms: forward only (no BPTT chain for the res*-ee.yaml blocks yet); "
+                                      "call under torch.no_grad()")
+        a = Act.from_ref(x)
+        if len(self.shortcut) == 0:
+            return _residual_path(self.residual_function, a, a).to_ref()
+        pool, conv, bn = self.shortcut
+        z = F_.maxpool(a, pool.stride[1])
+        if bn.bn.training:
+            z = conv.conv_real(z)
+            return _residual_path(self.residual_function, a, z, bn.scale_shift(z)).to_ref()
+        sc, sh = bn.scale_shift(None)
+        return _residual_path(self.residual_function, a, conv.conv_real(z, sc, sh)).to_ref()
+
+
+class ConcatBlock_ms(Concat_res2):
+    """models/common.py:1690-1725: Concat_res2's topology with hidden width e*out (res*-ee.yaml)."""
+
+    def __init__(self, in_channels, out_channels, k_size=3, stride=1, e=0.5):
+        nn.Module.__init__(self)
+        self._build(in_channels, int(out_channels * e), out_channels, k_size, stride)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import autograd as AG
+        if AG.wants_grad(self, x):
+            raise NotImplementedError("ConcatBlock_ms: forward only (no BPTT chain for the res*-ee.yaml blocks yet); "
+                                      "call under torch.no_grad()")
+        return super().forward(x)
 
 
 class Conv_1(nn.Module):
@@ -370,7 +445,11 @@ class Conv_2(Conv_B):
     """models/common.py:428-440 (same chain, explicit stride argument)."""
 
     def __init__(self, c1, c2, k, s, p=None, g=1):
-        super().__init__(c1, c2, k, s, p, g)
+        nn.Module.__init__(self)   # registration order of the reference (conv, bn, act) = state_dict key order
+        self.conv = Snn_Conv2d(c1, c2, k, s, autopad(k, p), groups=g, bias=False)
+        self.bn = batch_norm_2d(c2)
+        self.act = mem_update(act=False)
+        self.act._init_spread(c1)
 
 
 class Conv(nn.Module):

@@ -175,11 +175,14 @@ class Act:
 
 
 class Spikes:
-    """Bit-packed spike train [T, N, H, W, C/32] (int32 words)."""
-    __slots__ = ("bits", "C")
+    """Bit-packed spike train [T, N, H, W, C/32] (int32 words).  ``Cr`` <= C is the number of channels that
+    carry data: layers narrower than the kernels' 64-channel granule (the 3- and 32-channel front of
+    res*-ee.yaml) run zero-padded to C, and the padded channels never fire."""
+    __slots__ = ("bits", "C", "Cr")
 
-    def __init__(self, bits: torch.Tensor, C: int):
+    def __init__(self, bits: torch.Tensor, C: int, Cr: Optional[int] = None):
         self.bits, self.C = bits, C
+        self.Cr = C if Cr is None else Cr
 
     T = property(lambda s: s.bits.shape[0])
     N = property(lambda s: s.bits.shape[1])
@@ -190,6 +193,8 @@ class Spikes:
         T, N, H, W, _ = self.bits.shape
         out = torch.empty(T, N, H, W, self.C, device=self.bits.device, dtype=torch.float32)
         _cabi.check(_cabi.lib().ecsy_spikes_unpack(_p(self.bits), _p(out), T * N * H * W, self.C, _st()), "spikes_unpack")
+        if self.Cr != self.C:
+            out = out[..., :self.Cr].contiguous()
         return Act(out, T)
 
     @staticmethod
@@ -282,9 +287,26 @@ class LifW:
     bconst: Optional[torch.Tensor] = None   # fused kernel: pw @ dw_b + pw_b
 
 
-def make_lif_w(dw_w, dw_b, pw_w, pw_b) -> LifW:
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def pad_channels(t: torch.Tensor, Cp: int) -> torch.Tensor:
+    """Zero-pad the last (channel) axis of an NHWC tensor / a [C] vector to Cp entries."""
+    return t if t.shape[-1] == Cp else torch.nn.functional.pad(t, (0, Cp - t.shape[-1]))
+
+
+def make_lif_w(dw_w, dw_b, pw_w, pw_b, Cp: Optional[int] = None) -> LifW:
+    """Cp > C: spread weights zero-padded to Cp channels (the extra channels see zero current, a zero trace
+    and never fire), for layers narrower than the 64-channel granule."""
     splits = get_splits()
     C = dw_w.shape[0]
+    if Cp is not None and Cp != C:
+        dw_w = torch.nn.functional.pad(dw_w.detach().float(), (0, 0, 0, 0, 0, 0, 0, Cp - C))
+        dw_b = pad_channels(dw_b.detach().float(), Cp)
+        pw_w = torch.nn.functional.pad(pw_w.detach().float(), (0, 0, 0, 0, 0, Cp - C, 0, Cp - C))
+        pw_b = pad_channels(pw_b.detach().float(), Cp)
+        C = Cp
     w = LifW(dw_w.detach().float().reshape(C, 9).t().contiguous(), dw_b.detach().float().contiguous(),
              pack_conv_weight(pw_w, splits), pw_b.detach().float().contiguous(), splits)
     if splits == 1 and C == 64:
@@ -301,7 +323,18 @@ def make_lif_w(dw_w, dw_b, pw_w, pw_b) -> LifW:
 def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
             ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25, save_mem: bool = False):
     """mem_update.forward (models/common.py:252-283) -> bit-packed spikes; with save_mem also the membranes
-    m_t [T,...] and ECS traces e_t [T-1,...] (the backward's recompute pass)."""
+    m_t [T,...] and ECS traces e_t [T-1,...] (the backward's recompute pass).  C % 64 != 0: the input current
+    is zero-padded to the next multiple of 64 (``w`` must come from make_lif_w(..., Cp)); the result carries Cr = C."""
+    Cr = x.C
+    if Cr % 64:
+        if save_mem:
+            raise NotImplementedError("lif_ecs: the BPTT recompute pass needs C % 64 == 0")
+        Cp = pad64(Cr)
+        if w is not None and w.dw_b.numel() != Cp:
+            raise RuntimeError("lif_ecs: spread weights must be padded to %d channels" % Cp)
+        x = Act(pad_channels(x.data, Cp), x.T)
+        if affine is not None:
+            affine = (pad_channels(affine[0], Cp), pad_channels(affine[1], Cp))
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
     bits = torch.empty(T, N, H, W, C // 32, device=dev, dtype=torch.int32)
@@ -314,7 +347,7 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
                 _p(x.data), x.tstride, _p(sc), _p(sh), _p(w.w_eff), _p(w.bconst), _p(bits), T, N, H, W, C,
                 float(thresh), float(decay), float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _st()),
                 "lif_ecs_fused_fwd")
-        return Spikes(bits, C)
+        return Spikes(bits, C, Cr)
     mem = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
     ecs = torch.empty(max(T - 1, 1), N, H, W, C, device=dev, dtype=torch.float32) if save_mem else None
     L = _cabi.lib()
@@ -331,7 +364,7 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
                                    _p(w.pw) if w else None, _p(w.pw_b) if w else None, splits,
                                    _p(bits), _p(mem), _p(ecs), T, N, H, W, C, float(thresh), float(decay), float(alpha),
                                    float(beta), float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(), _st()), "lif_ecs_fwd")
-    sp = Spikes(bits, C)
+    sp = Spikes(bits, C, Cr)
     return (sp, mem, ecs) if save_mem else sp
 
 

@@ -153,7 +153,8 @@ class Model(nn.Module):
         return self
 
 
-_CHANNEL_MODULES = ("Conv", "Conv_1", "Conv_2", "Conv_B", "BasicBlock_1", "BasicBlock_2", "Concat_res2")
+_CHANNEL_MODULES = ("Conv", "Conv_1", "Conv_2", "Conv_B", "BasicBlock_1", "BasicBlock_2", "Concat_res2",
+                    "BasicBlock_ms", "ConcatBlock_ms")
 
 
 def parse_model(d, ch, use_cupy=False, heads=None):

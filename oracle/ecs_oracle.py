@@ -195,15 +195,37 @@ def concat_res2(sd, p, x, cin, cout, k=3, stride=1, training=False, rec=None):
     return _residual(sd, p, x, stride, pad, training, rec) + out
 
 
+def basic_block_ms(sd, p, x, cin, cout, k=3, stride=1, training=False, rec=None):
+    """BasicBlock_ms (common.py:1658-1687, res*-ee.yaml): hidden width 0.5*cout (implicit in the weight
+    shapes); the shortcut has NO neuron: max-pool -> 1x1 conv on the real input -> tdBN."""
+    pad = 1 if k == 3 else 0
+    out = _residual(sd, p, x, stride, pad, training, rec)
+    if stride != 1 or cin != cout:
+        q = p + "shortcut."
+        z = snn_conv2d(maxpool_hw(x, stride), sd[q + "1.weight"], None, 1, 0)
+        sc = tdbn(z, sd, q + "2.bn.", training)
+    else:
+        sc = x
+    return out + sc
+
+
+def concat_block_ms(sd, p, x, cin, cout, k=3, stride=1, training=False, rec=None):
+    """ConcatBlock_ms (common.py:1690-1725): Concat_res2's data flow; only the hidden width (0.5*cout,
+    implicit in the weight shapes) differs."""
+    return concat_res2(sd, p, x, cin, cout, k, stride, training, rec)
+
+
 def conv_1(sd, p, x, k, s, training=False):
     """Conv_1 (common.py:409-425): conv on the REAL input then tdBN, no neuron."""
     y = snn_conv2d(x, sd[p + "conv.weight"], None, s, k // 2)
     return tdbn(y, sd, p + "bn.bn.", training)
 
 
-def conv_b(sd, p, x, k, s=1, g=1, training=False):
+def conv_b(sd, p, x, k, s=1, g=1, training=False, rec=None):
     """Conv_B / Conv_2 (common.py:393-406, 428-440): LIF -> conv -> tdBN."""
     sp = lif_from_sd(sd, p + "act.", x)
+    if rec is not None:
+        rec[p + "act"] = sp
     y = snn_conv2d(sp, sd[p + "conv.weight"], None, s, k // 2, g)
     return tdbn(y, sd, p + "bn.bn.", training)
 
@@ -360,10 +382,15 @@ def _run_layer(sd, L, p, x, training, T_dedupe, rec):
         k = a[2] if len(a) > 2 else 3
         s = a[3] if len(a) > 3 else 1
         return concat_res2(sd, p, x, a[0], a[1], k, s, training, rec)
+    if t in ("BasicBlock_ms", "ConcatBlock_ms"):
+        k = a[2] if len(a) > 2 else 3
+        s = a[3] if len(a) > 3 else 1
+        fn = basic_block_ms if t == "BasicBlock_ms" else concat_block_ms
+        return fn(sd, p, x, a[0], a[1], k, s, training, rec)
     if t == "Conv":
         return conv_silu(sd, p, x, a[2], a[3], 1, training)
     if t in ("Conv_B", "Conv_2"):
-        return conv_b(sd, p, x, a[2], a[3] if len(a) > 3 else 1, 1, training)
+        return conv_b(sd, p, x, a[2], a[3] if len(a) > 3 else 1, 1, training, rec)
     if t == "Sample":
         return sample_nearest(x, a[1])
     if t == "Concat":
@@ -474,6 +501,20 @@ def init_state_dict(cfg: dict, T: int, ch: int = 3, seed: int = 0) -> Dict[str, 
                     lif(p + "shortcut.0.", a[0])
                     conv(p + "shortcut.1.", a[1] - a[0], a[0], 1, False)
                     bn(p + "shortcut.2.bn.", a[1] - a[0], THRESH)
+            elif t == "BasicBlock_ms":
+                k = a[2] if len(a) > 2 else 3
+                s = a[3] if len(a) > 3 else 1
+                residual(p, a[0], int(a[1] * 0.5), a[1], k)
+                if s != 1 or a[0] != a[1]:
+                    conv(p + "shortcut.1.", a[1], a[0], 1, False)
+                    bn(p + "shortcut.2.bn.", a[1], THRESH)
+            elif t == "ConcatBlock_ms":
+                k = a[2] if len(a) > 2 else 3
+                residual(p, a[0], int(a[1] * 0.5), a[1], k)
+                if a[0] < a[1]:
+                    lif(p + "shortcut.0.", a[0])
+                    conv(p + "shortcut.1.", a[1] - a[0], a[0], 1, False)
+                    bn(p + "shortcut.2.bn.", a[1] - a[0], THRESH)
             elif t == "Conv":
                 conv(p + "conv.", a[1], a[0], a[2], False)
                 bn(p + "bn.bn.", a[1], THRESH)
@@ -515,7 +556,7 @@ def detect_strides(cfg: dict, ch: int = 3, s: int = 256) -> torch.Tensor:
         t, a = L["type"], L["args"]
         if t == "Conv_1" or t == "Conv" or t in ("Conv_B", "Conv_2"):
             r = base * a[3] if len(a) > 3 else base
-        elif t == "BasicBlock_2" or t == "Concat_res2":
+        elif t in ("BasicBlock_2", "Concat_res2", "BasicBlock_ms", "ConcatBlock_ms"):
             r = base * (a[3] if len(a) > 3 else 1)
         elif t == "BasicBlock_1":
             r = base * (a[2] if len(a) > 2 else 1)

@@ -21,6 +21,9 @@ import seeded as S  # noqa: E402
 import ecs_oracle as O  # noqa: E402  (key/shape bookkeeping only)
 
 
+ONLY = set(sys.argv[1:])   # optional: regenerate just the named fixtures
+
+
 def save(name, obj):
     path = os.path.join(S.GOLDEN_DIR, name + ".pt")
     torch.save(obj, path)
@@ -40,6 +43,8 @@ def main():
     torch.set_num_threads(4)
     # ---------------- LIF (forward + surrogate-gradient BPTT) ----------------
     for name, spec in S.LIF_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, _ = ref_shim.load(spec["T"])
         inp = S.lif_inputs(spec)
         m = ref_lif(C, inp, spec["T"])
@@ -54,6 +59,8 @@ def main():
                         spikes=S.pack_spikes(out.detach()), rate=float(out.mean()), **g))
     # ---------------- Snn_Conv2d ----------------
     for name, spec in S.CONV_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, _ = ref_shim.load(spec["T"])
         inp = S.conv_inputs(spec)
         m = C.Snn_Conv2d(spec["ci"], spec["co"], spec["k"], spec["s"], spec["p"], bias=inp["b"] is not None)
@@ -65,6 +72,8 @@ def main():
         save(name, dict(spec=spec, chk=S.checksum(inp["x"], inp["w"]), out=out))
     # ---------------- tdBN ----------------
     for name, spec in S.BN_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, _ = ref_shim.load(spec["T"])
         res = {}
         for cls, tag in [(C.batch_norm_2d, "bn1"), (C.batch_norm_2d1, "bn2")]:
@@ -81,7 +90,9 @@ def main():
         inp = S.bn_inputs(spec)
         save(name, dict(spec=spec, chk=S.checksum(inp["x"]), **res))
     # ---------------- blocks ----------------
-    for name, spec in S.BLOCK_CASES.items():
+    for name, spec in {**S.BLOCK_CASES, **S.MS_BLOCK_CASES}.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, _ = ref_shim.load(spec["T"])
         inp = S.block_inputs(spec, O)
         cls = getattr(C, spec["kind"])
@@ -123,6 +134,8 @@ def main():
             h.remove()
     # ---------------- whole model (Stack A) ----------------
     for name, spec in S.MODEL_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, _ = ref_shim.load(spec["T"])
         path = os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")
         cfg = yaml.safe_load(open(path))
@@ -157,6 +170,8 @@ def main():
 
     # ---------------- Stack B: SiLU neuron, Conv, DDetect, whole model ----------------
     for name, spec in S.SILU_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, SN = ref_shim.load(spec["T"])
         inp = S.lif_inputs(spec)
         m = C.mem_update(act=True)
@@ -173,6 +188,8 @@ def main():
              "g_pw_w": m.spread[1].weight.grad.clone(), "g_pw_b": m.spread[1].bias.grad.clone()}
         save(name, dict(spec=spec, chk=S.checksum(*[inp[k] for k in sorted(inp)]), out=out, **g))
     for name, spec in S.CONVSILU_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, SN = ref_shim.load(spec["T"])
         inp = S.convsilu_inputs(spec, O)
         m = C.Conv(spec["cin"], spec["cout"], spec["k"], spec["s"])
@@ -196,6 +213,8 @@ def main():
         save(name, dict(spec=spec, chk=S.sd_checksum(inp["sd"]) + S.checksum(inp["x"]), out_train=out_train,
                         out_eval=out_eval, gx=gx, grads=grads))
     for name, spec in S.DDETECT_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, SN = ref_shim.load(spec["T"])
         inp = S.ddetect_inputs(spec, O)
         m = SN.DDetect(spec["nc"], spec["ch"])
@@ -221,6 +240,8 @@ def main():
                         out_train=[o.clone() for o in out_train], bn_after=bn_after, y_eval=y, xs_eval=[o.clone() for o in xs],
                         gfeats=gfeats, grads=grads))
     for name, spec in S.MODEL_B_CASES.items():
+        if ONLY and name not in ONLY:
+            continue
         C, Y, SN = ref_shim.load(spec["T"])
         path = os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")
         cfg = yaml.safe_load(open(path))

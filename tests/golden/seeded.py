@@ -121,8 +121,19 @@ BLOCK_CASES = {
     "cr2_64_128_s2": dict(kind="Concat_res2", cin=64, cout=128, k=3, s=2, T=4, N=2, H=12, W=12, seed=404),
     "bb1_128_64_s1": dict(kind="BasicBlock_1", cin=128, cout=64, k=3, s=1, T=4, N=1, H=6, W=6, seed=405),
 }
+# res*-ee.yaml blocks (the original EMS-YOLO topology): narrow 3 / 32-channel front, hidden width 0.5*cout,
+# neuron-free shortcut conv
+MS_BLOCK_CASES = {
+    "conv2_3_32_s2": dict(kind="Conv_2", cin=3, cout=32, k=3, s=2, T=4, N=2, H=16, W=16, seed=411),
+    "cb_ms_32_64_s2": dict(kind="ConcatBlock_ms", cin=32, cout=64, k=3, s=2, T=4, N=2, H=12, W=12, seed=412),
+    "cb_ms_128_256_s1": dict(kind="ConcatBlock_ms", cin=128, cout=256, k=3, s=1, T=4, N=1, H=8, W=8, seed=413),
+    "bb_ms_64_128_s2": dict(kind="BasicBlock_ms", cin=64, cout=128, k=3, s=2, T=4, N=2, H=12, W=12, seed=414),
+    "bb_ms_128_128_s1": dict(kind="BasicBlock_ms", cin=128, cout=128, k=3, s=1, T=4, N=2, H=8, W=8, seed=415),
+    "bb_ms_256_128_k1": dict(kind="BasicBlock_ms", cin=256, cout=128, k=1, s=1, T=4, N=2, H=6, W=6, seed=416),
+}
 MODEL_CASES = {
     "tiny_64": dict(cfg="tiny", T=4, N=2, H=64, W=64, seed=501),
+    "tiny_ee_64": dict(cfg="tiny_ee", T=4, N=2, H=64, W=64, seed=502),
 }
 # Stack B
 SILU_CASES = {

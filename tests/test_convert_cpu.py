@@ -12,7 +12,8 @@ REF = "/root/reference"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
 
 
-@pytest.mark.parametrize("stack,cfg", [("A", "resnet10.yaml"), ("B", "resnet18.yaml")])
+@pytest.mark.parametrize("stack,cfg", [("A", "resnet10.yaml"), ("B", "resnet18.yaml"), ("A", "res10-ee.yaml"),
+                                       ("A", "res18-ee.yaml")])
 def test_convert_reference_model(stack, cfg):
     import ref_shim
     C, Y, S = ref_shim.load(4)
