@@ -3,6 +3,7 @@
 // and the Stack-A / Stack-B head decodes.  All activations are NHWC fp32 ("[imgs][H][W][C]"),
 // spikes are one bit per channel packed along C ("[imgs][H][W][C/32]" uint32, bit c&31 of word c>>5).
 #include <cuda_fp16.h>
+#include <algorithm>
 #include "ecsy_common.cuh"
 #include "../../include/ecsy.h"
 #include "umma_gemm.h"
@@ -286,6 +287,112 @@ k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*
       const int64_t o = ((img * H + h) * W + x) * (int64_t)c8 + cg;
       reinterpret_cast<uint4*>(a_hi)[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// Version 2: the bits of a tile (3 rows x (PX + 2) pixels x C/8 bytes) are staged in shared memory with
+// coalesced 8-byte loads, so the per-pixel byte reads of the sliding window become LDS.U8 (v1 read them with
+// one-byte global loads one pixel ahead and was latency bound: 32 % issue utilisation, 0.8 TB/s).  A block owns
+// `segs` runs of R consecutive pixels of one image row for all C/8 channel groups (blockDim = segs * C/8);
+// same accumulation order as v1, bit-identical output.
+template <int R, bool LO>
+__global__ void __launch_bounds__(256, 2)
+k_spread_dw2(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*[9][C]*/,
+             const float* __restrict__ dw_b, __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo,
+             int N, int H, int W, int C, int segs, int tiles_per_row) {
+  extern __shared__ __align__(16) uint8_t dw_sm[];   // [3][PX + 2][c8]
+  const int c8 = C >> 3;
+  const int PX = segs * R;
+  const int rowbytes = (PX + 2) * c8;
+  const int chunks_row = rowbytes >> 3;              // c8 % 8 == 0
+  const int cg = threadIdx.x % c8, seg = threadIdx.x / c8;
+  const uint8_t* gbytes = reinterpret_cast<const uint8_t*>(bits);
+  float w[72], bias[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = *reinterpret_cast<const float4*>(dw_w + t * C + cg * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(dw_w + t * C + cg * 8 + 4);
+    w[t * 8 + 0] = w0.x; w[t * 8 + 1] = w0.y; w[t * 8 + 2] = w0.z; w[t * 8 + 3] = w0.w;
+    w[t * 8 + 4] = w1.x; w[t * 8 + 5] = w1.y; w[t * 8 + 6] = w1.z; w[t * 8 + 7] = w1.w;
+  }
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(dw_b + cg * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(dw_b + cg * 8 + 4);
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
+  const int64_t tiles = (int64_t)N * H * tiles_per_row;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tx = static_cast<int>(tile % tiles_per_row);
+    const int64_t r = tile / tiles_per_row;
+    const int h = static_cast<int>(r % H);
+    const int64_t img = r / H;
+    const int x0 = tx * PX;
+    __syncthreads();   // the previous tile's window reads are done
+    const int q = c8 >> 3;                           // 8-byte chunks per pixel
+    const int qshift = (q & (q - 1)) == 0 ? __ffs(q) - 1 : -1;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      const bool rok = hh >= 0 && hh < H;
+      const uint8_t* grow = gbytes + ((img * H + (rok ? hh : h)) * W + (x0 - 1)) * (int64_t)c8;
+      for (int j = threadIdx.x; j < chunks_row; j += blockDim.x) {
+        const int px = qshift >= 0 ? (j >> qshift) : j / q;   // staged pixel 0 .. PX+1  <->  image column x0 - 1 + px
+        const int xx = x0 - 1 + px;
+        uint2 v = make_uint2(0u, 0u);
+        if (rok && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const uint2*>(grow) + j);
+        reinterpret_cast<uint2*>(dw_sm + ky * rowbytes)[j] = v;
+      }
+    }
+    __syncthreads();
+    const int p0 = seg * R;
+    const uint8_t* sp = dw_sm + p0 * c8 + cg;        // staged pixel p0 = image column x0 + p0 - 1
+    uint32_t win[3][3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      win[ky][0] = 0;
+      win[ky][1] = sp[ky * rowbytes];
+      win[ky][2] = sp[ky * rowbytes + c8];
+    }
+    int64_t o = ((img * H + h) * W + x0 + p0) * (int64_t)c8 + cg;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      sp += c8;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[ky][0] = win[ky][1];
+        win[ky][1] = win[ky][2];
+        win[ky][2] = sp[ky * rowbytes + c8];
+      }
+      if (x0 + p0 + j < W) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = bias[k];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint32_t m = win[ky][kx];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (m & (1u << k)) acc[k] += w[(ky * 3 + kx) * 8 + k];
+          }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 hp = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);   // one packed cvt
+          hi[q] = *reinterpret_cast<const uint32_t*>(&hp);
+          if (LO) {
+            const float2 hf = __bfloat1622float2(hp);
+            const __nv_bfloat162 lp = __floats2bfloat162_rn(acc[2 * q] - hf.x, acc[2 * q + 1] - hf.y);
+            lo[q] = *reinterpret_cast<const uint32_t*>(&lp);
+          }
+        }
+        reinterpret_cast<uint4*>(a_hi)[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (LO) reinterpret_cast<uint4*>(a_lo)[o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      o += c8;
     }
   }
 }
@@ -823,12 +930,54 @@ int ecsy_launch_dw_real(const float* s, const float* dw_w, const float* dw_b, __
   return ECSY_OK;
 }
 
-int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
-                          __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st) {
+template <int R>
+static void launch_dw2(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
+                       __nv_bfloat16* a_lo, int N, int H, int W, int C, int segs, cudaStream_t st) {
+  const int c8 = C / 8, PX = segs * R;
+  const int tiles_per_row = (W + PX - 1) / PX;
+  const int64_t tiles = (int64_t)N * H * tiles_per_row;
+  const size_t smem = (size_t)3 * (PX + 2) * c8;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)ecsy_num_sms() * 8);
+  if (a_lo)
+    k_spread_dw2<R, true><<<grid, segs * c8, smem, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, tiles_per_row);
+  else
+    k_spread_dw2<R, false><<<grid, segs * c8, smem, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, tiles_per_row);
+}
+
+// version: 0 = default (2 unless ECSY_DW_V=1), 1 = global byte loads, 2 = shared-memory staged tiles
+int ecsy_launch_spread_dw_v(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
+                            __nv_bfloat16* a_lo, int N, int H, int W, int C, int version, cudaStream_t st) {
   const int c8 = C / 8;
-  if (c8 < 1 || c8 > 256) {
+  if (c8 < 1 || c8 > 256 || C % 64 != 0) {
     ecsy_set_error("spread_dw: C=%d out of range", C);
     return ECSY_ERR_ARG;
+  }
+  if (version == 0) {
+    static const int env_v = (getenv("ECSY_DW_V") != nullptr && getenv("ECSY_DW_V")[0] == '1') ? 1 : 2;
+    version = env_v;
+  }
+  if (version == 2) {
+    // runs of R pixels per thread; pick the R whose tiles waste the fewest columns (640-pixel inputs: W = 20 * 2^n -> R = 5)
+    int segs = 256 / c8 > 0 ? 256 / c8 : 1;
+    static const int kR[4] = {5, 4, 8, 6};
+    int bestR = 5;
+    int64_t best = -1;
+    for (int i = 0; i < 4; ++i) {
+      const int R = kR[i];
+      const int sg = std::max(1, std::min(segs, (W + R - 1) / R));
+      const int PX = sg * R;
+      const int64_t padded = (int64_t)((W + PX - 1) / PX) * PX;
+      if (best < 0 || padded < best) { best = padded; bestR = R; }
+    }
+    segs = std::max(1, std::min(segs, (W + bestR - 1) / bestR));
+    switch (bestR) {
+      case 4: launch_dw2<4>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, st); break;
+      case 5: launch_dw2<5>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, st); break;
+      case 6: launch_dw2<6>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, st); break;
+      default: launch_dw2<8>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, st); break;
+    }
+    ECSY_LAUNCH_CHECK();
+    return ECSY_OK;
   }
   // block size: a multiple of c8 (every thread keeps one channel group for all of its work items)
   int lcm = c8;
@@ -839,6 +988,22 @@ int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* 
   k_spread_dw<<<grid_for(items, bd, ecsy_num_sms() * 4), bd, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
+}
+
+int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
+                          __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st) {
+  return ecsy_launch_spread_dw_v(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, 0, st);
+}
+
+// Depth-wise half of the ECS spread on its own (models/common.py:289-294, spread[0]): bits [N,H,W,C/32] ->
+// bf16 rows a_hi (+ a_lo residual plane or NULL) [N*H*W, C].  `version` selects the kernel (0 = default).
+extern "C" int ecsy_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, void* a_hi, void* a_lo,
+                              int64_t N, int H, int W, int C, int version, void* stream) {
+  ECSY_CHECK_ARG(bits && dw_w && dw_b && a_hi && N > 0 && N < (1LL << 31) && H > 0 && W > 0, "spread_dw: bad arguments");
+  ECSY_CHECK_ARG(version >= 0 && version <= 2, "spread_dw: version");
+  return ecsy_launch_spread_dw_v(bits, dw_w, dw_b, reinterpret_cast<__nv_bfloat16*>(a_hi),
+                                 reinterpret_cast<__nv_bfloat16*>(a_lo), (int)N, H, W, C, version,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t ecsy_tdbn_stats_ws_bytes(int64_t rows, int C) {

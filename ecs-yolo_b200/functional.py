@@ -368,6 +368,18 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     return (sp, mem, ecs) if save_mem else sp
 
 
+def spread_dw(sp: Spikes, t: int, w: LifW, lo: bool = False, version: int = 0):
+    """Depth-wise half of mem_update.spread (models/common.py:289-294) on the spikes of step t -> bf16 rows
+    [N*H*W, C] (hi plane, and the residual plane when `lo`): the A operand of the point-wise spread GEMM."""
+    N, H, W, C = sp.N, sp.H, sp.W, sp.C
+    a_hi = torch.empty(N * H * W, C, device=sp.bits.device, dtype=torch.bfloat16)
+    a_lo = torch.empty_like(a_hi) if lo else None
+    with _timed("spread_dw", 1):
+        _cabi.check(_cabi.lib().ecsy_spread_dw(_p(sp.bits[t]), _p(w.dw_w), _p(w.dw_b), _p(a_hi), _p(a_lo), N, H, W, C,
+                                               int(version), _st()), "spread_dw")
+    return (a_hi, a_lo) if lo else a_hi
+
+
 def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, affine=None, ecs_tau: float = 5.0,
                 alpha: float = 0.75, beta: float = 0.25):
     """Surrogate-gradient BPTT of lif_ecs.  gout: [T,N,H,W,C] dL/dspikes.  Re-runs the forward to recompute the

@@ -54,6 +54,13 @@ int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* in_scale, c
                      float thresh,
                      float decay, float alpha, float beta, float kappa, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- the depth-wise half of mem_update.spread on its own (models/common.py:289-294, spread[0] = Conv2d(C, C, 3,
+ * padding 1, groups C) applied to the spikes of one step): bits [N][H][W][C/32] -> bf16 rows [N*H*W][C] a_hi
+ * (+ residual plane a_lo = bf16(v - a_hi), or NULL), the A operand of the point-wise spread GEMM.  `version`: 0 = the
+ * kernel ecsy_lif_ecs_fwd uses, 1 = per-pixel global byte loads, 2 = shared-memory staged tiles (bit-identical). */
+int ecsy_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, void* a_hi, void* a_lo, int64_t N,
+                   int H, int W, int C, int version, void* stream);
+
 /* ---- mem_update(act=True).forward: the SiLU "analog spike" neuron of class Conv (models/common.py:362-375,
  * 252-283).  out: [T][N][H][W][C] fp32 = silu(mem_t).  inplace != 0 reproduces the reference models, where
  * initialize_weights() makes nn.SiLU in-place so that mem_old holds silu(mem) (utils/torch_utils.py:165-166). */

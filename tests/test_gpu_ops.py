@@ -394,3 +394,30 @@ def test_full_size_cross_checks():
         F.set_precision("parity")
         F.set_conv_ts("auto")
         F.set_lif_fused(False)
+
+
+@pytest.mark.parametrize("C,N,H,W", [(64, 2, 20, 20), (64, 1, 13, 163), (128, 2, 9, 80), (192, 1, 7, 11), (384, 1, 6, 40),
+                                      (512, 2, 5, 20), (1024, 1, 4, 21), (64, 1, 3, 2)])
+def test_spread_dw_versions(C, N, H, W):
+    """Depth-wise half of the ECS spread (models/common.py:289-294): the shared-memory staged kernel (version 2, the
+    default) is bit-identical to the per-pixel global-load kernel (version 1) on both bf16 planes, and both match
+    F.conv2d(groups=C) of the oracle within one bf16 rounding."""
+    import torch.nn.functional as TF
+    F = ecsy().functional
+    g = S.gen(900 + C + W)
+    s = (torch.rand(1, N, C, H, W, generator=g) < 0.2).float()
+    dw_w = S.uniform(g, C, 1, 3, 3, lo=-1 / 3, hi=1 / 3)
+    dw_b = S.uniform(g, C, lo=-1 / 3, hi=1 / 3)
+    pw_w = S.uniform(g, C, C, 1, 1, lo=-0.1, hi=0.1)
+    w = F.make_lif_w(dw_w.cuda(), dw_b.cuda(), pw_w.cuda(), torch.zeros(C).cuda())
+    sp = F.Spikes.from_act(F.Act.from_ref(s.cuda()))
+    h1, l1 = F.spread_dw(sp, 0, w, lo=True, version=1)
+    h2, l2 = F.spread_dw(sp, 0, w, lo=True, version=2)
+    h0 = F.spread_dw(sp, 0, w, lo=False, version=0)
+    torch.cuda.synchronize()
+    assert torch.equal(h1.view(torch.int16), h2.view(torch.int16)) and torch.equal(l1.view(torch.int16), l2.view(torch.int16))
+    assert torch.equal(h0.view(torch.int16), h2.view(torch.int16))
+    want = TF.conv2d(s[0], dw_w, dw_b, 1, 1, 1, C).permute(0, 2, 3, 1).reshape(-1, C)
+    got = (h2.float() + l2.float()).cpu()
+    assert float((got - want).abs().max()) < 4e-5      # hi + lo planes carry ~16 mantissa bits
+    assert float((h2.float().cpu() - want).abs().max()) < 2 ** -8 * float(want.abs().max())
