@@ -944,7 +944,7 @@ static void launch_dw2(const uint32_t* bits, const float* dw_w, const float* dw_
     k_spread_dw2<R, false><<<grid, segs * c8, smem, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C, segs, tiles_per_row);
 }
 
-// version: 0 = default (2 unless ECSY_DW_V=1), 1 = global byte loads, 2 = shared-memory staged tiles
+// version: 0 = measured default (ECSY_DW_V=1|2 overrides), 1 = global byte loads, 2 = shared-memory staged tiles
 int ecsy_launch_spread_dw_v(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
                             __nv_bfloat16* a_lo, int N, int H, int W, int C, int version, cudaStream_t st) {
   const int c8 = C / 8;
@@ -953,8 +953,10 @@ int ecsy_launch_spread_dw_v(const uint32_t* bits, const float* dw_w, const float
     return ECSY_ERR_ARG;
   }
   if (version == 0) {
-    static const int env_v = (getenv("ECSY_DW_V") != nullptr && getenv("ECSY_DW_V")[0] == '1') ? 1 : 2;
-    version = env_v;
+    // measured (profiles/r01_dw_microbench.txt): both versions are issue bound on the bit tests + predicated adds; the
+    // staged tiles win from 256 channels up (fewer, longer byte rows per pixel), the direct loads below that
+    static const char* env = getenv("ECSY_DW_V");
+    version = (env != nullptr && (env[0] == '1' || env[0] == '2')) ? env[0] - '0' : (c8 >= 32 ? 2 : 1);
   }
   if (version == 2) {
     // runs of R pixels per thread; pick the R whose tiles waste the fewest columns (640-pixel inputs: W = 20 * 2^n -> R = 5)
