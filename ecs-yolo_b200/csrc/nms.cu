@@ -1,0 +1,277 @@
+// Batched non-maximum suppression for the decoded Detect output (reference:
+// utils/general.py:649-741 `non_max_suppression`, which loops over images in Python and calls torchvision.ops.nms).
+//
+//   k_nms_candidates : one thread per prediction row [x, y, w, h, obj, cls_0..cls_{nc-1}]: rows with obj > conf_thres,
+//                      conf = obj * cls (general.py:691), best class (first maximum) or, with multi_label, every class
+//                      above the threshold (general.py:697-702), optional class filter (:705-706).  A candidate is
+//                      a 64-bit key (~score bits << 32 | row * nc + class): ascending key order = descending score,
+//                      ties by prediction order -- the order of the stable sort inside torchvision's nms.
+//   k_nms_select     : one CTA per image: bitonic sort of the keys (shared memory up to 8192 candidates, in place in
+//                      the L2-resident workspace above that), truncation to max_nms (general.py:716-717), then the
+//                      greedy scan in chunks of 256 candidates: every thread tests one candidate against the boxes
+//                      kept so far, the chunk's own 256 x 256 suppression bit matrix resolves the order dependence
+//                      inside the chunk, and the scan stops at max_det kept boxes (general.py:723-724: the first
+//                      max_det survivors of a greedy scan do not depend on anything after them).
+// Arithmetic follows the reference to the bit: xywh -> xyxy as x -+ w/2 (general.py:603-609), class offset
+// cls * 4096 added to the corners (general.py:720-721), IoU = inter / (area_a + area_b - inter) with separately
+// rounded products (torchvision/csrc/ops/cpu/nms_kernel.cpp), suppressed when IoU > iou_thres.
+#include "ecsy_common.cuh"
+#include "../../include/ecsy.h"
+
+namespace {
+
+constexpr int kChunk = 256;         // candidates resolved per round of the greedy scan
+constexpr int kSelThreads = 256;
+constexpr int kSortSmemKeys = 8192; // 64 KB of keys sorted in shared memory
+constexpr float kMaxWh = 4096.f;    // general.py:667
+
+struct NmsArgs {
+  const float* pred;     // [N][R][5 + nc]
+  const uint8_t* cls_ok; // optional [nc]: 1 = keep this class (general.py:705)
+  unsigned long long* keys;  // [N][cap]
+  int* counts;           // [N]
+  float* out;            // [N][max_det][6]
+  int* out_count;        // [N]
+  int N, R, nc, cap, max_det, max_nms, agnostic, multi_label;
+  float conf_thres;
+  double iou_thres;
+};
+
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t idx) {
+  return ((unsigned long long)(~__float_as_uint(score)) << 32) | idx;   // score > 0: raw bits are monotonic
+}
+
+__global__ void k_nms_candidates(const NmsArgs a) {
+  const int img = blockIdx.y;
+  const int no = 5 + a.nc;
+  unsigned long long* keys = a.keys + (size_t)img * a.cap;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.R; r += gridDim.x * blockDim.x) {
+    const float* p = a.pred + ((size_t)img * a.R + r) * no;
+    const float obj = p[4];
+    if (!(obj > a.conf_thres)) continue;
+    if (a.multi_label) {
+      for (int j = 0; j < a.nc; ++j) {
+        const float conf = __fmul_rn(p[5 + j], obj);
+        if (conf > a.conf_thres && (a.cls_ok == nullptr || a.cls_ok[j])) {
+          const int slot = atomicAdd(a.counts + img, 1);
+          keys[slot] = make_key(conf, (uint32_t)r * (uint32_t)a.nc + (uint32_t)j);
+        }
+      }
+    } else {
+      float best = __fmul_rn(p[5], obj);
+      int bj = 0;
+      for (int j = 1; j < a.nc; ++j) {
+        const float conf = __fmul_rn(p[5 + j], obj);
+        if (conf > best) { best = conf; bj = j; }
+      }
+      if (best > a.conf_thres && (a.cls_ok == nullptr || a.cls_ok[bj])) {
+        const int slot = atomicAdd(a.counts + img, 1);
+        keys[slot] = make_key(best, (uint32_t)r * (uint32_t)a.nc + (uint32_t)bj);
+      }
+    }
+  }
+}
+
+// in-place bitonic sort (ascending) of P = 2^k keys by one CTA; `k` may live in shared or global memory
+__device__ void bitonic_sort(unsigned long long* k, int P) {
+  int lp = 0;
+  while ((1 << lp) < P) ++lp;
+  for (int lsize = 1; lsize <= lp; ++lsize) {
+    const int size = 1 << lsize;
+    for (int ls = lsize - 1; ls >= 0; --ls) {
+      const int stride = 1 << ls;
+      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+        const int lo = ((i >> ls) << (ls + 1)) | (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long x = k[lo], y = k[hi];
+        if ((x > y) == up) { k[lo] = y; k[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct Cand {
+  float x1, y1, x2, y2;   // class-offset corners (what torchvision's nms sees)
+  float area;
+};
+
+__device__ __forceinline__ bool iou_gt(const Cand& a, const Cand& b, double thr) {
+  const float xx1 = fmaxf(a.x1, b.x1), yy1 = fmaxf(a.y1, b.y1);
+  const float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
+  return (double)ovr > thr;
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) {
+  extern __shared__ __align__(16) uint8_t nms_sm[];
+  __shared__ Cand s_chunk[kChunk];
+  __shared__ uint32_t s_sup[kChunk][kChunk / 32];   // s_sup[i]: candidates of the chunk that i suppresses
+  __shared__ uint32_t s_alive[kChunk / 32];
+  __shared__ int s_newk[kChunk];
+  __shared__ int s_nnew, s_kept;
+  const int img = blockIdx.x;
+  const int no = 5 + a.nc;
+  unsigned long long* gkeys = a.keys + (size_t)img * a.cap;
+  int n = a.counts[img];
+  // kept boxes live in dynamic shared memory: [max_det] Cand
+  Cand* s_keep = reinterpret_cast<Cand*>(nms_sm);
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(nms_sm + (((size_t)a.max_det * sizeof(Cand) + 15) & ~size_t(15)));
+
+  if (threadIdx.x == 0) s_kept = 0;
+  if (n == 0) {
+    if (threadIdx.x == 0) a.out_count[img] = 0;
+    return;
+  }
+  int P = 1;
+  while (P < n) P <<= 1;
+  unsigned long long* keys = gkeys;
+  if (P <= kSortSmemKeys) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < n ? gkeys[i] : ~0ull;
+    keys = s_keys;
+  } else {
+    for (int i = n + threadIdx.x; i < P; i += blockDim.x) gkeys[i] = ~0ull;   // cap is a power of two >= P
+  }
+  __syncthreads();
+  bitonic_sort(keys, P);
+  if (n > a.max_nms) n = a.max_nms;
+
+  const float* pred = a.pred + (size_t)img * a.R * no;
+  float* out = a.out + (size_t)img * a.max_det * 6;
+  for (int base = 0; base < n; base += kChunk) {
+    const int t = threadIdx.x;
+    const int c = base + t;
+    const bool valid = c < n;
+    Cand me{0.f, 0.f, 0.f, 0.f, 0.f};
+    float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f, conf = 0.f;
+    int cls = 0;
+    if (valid) {
+      const unsigned long long key = keys[c];
+      const uint32_t idx = (uint32_t)(key & 0xffffffffull);
+      const int r = idx / a.nc;
+      cls = idx - r * a.nc;
+      const float* p = pred + (size_t)r * no;
+      const float hw = __fmul_rn(p[2], 0.5f), hh = __fmul_rn(p[3], 0.5f);   // w / 2 is exact either way
+      bx1 = __fsub_rn(p[0], hw); by1 = __fsub_rn(p[1], hh);
+      bx2 = __fadd_rn(p[0], hw); by2 = __fadd_rn(p[1], hh);
+      conf = __fmul_rn(p[5 + cls], p[4]);
+      const float off = a.agnostic ? 0.f : __fmul_rn((float)cls, kMaxWh);
+      me.x1 = __fadd_rn(bx1, off); me.y1 = __fadd_rn(by1, off);
+      me.x2 = __fadd_rn(bx2, off); me.y2 = __fadd_rn(by2, off);
+      me.area = __fmul_rn(__fsub_rn(me.x2, me.x1), __fsub_rn(me.y2, me.y1));
+    }
+    s_chunk[t] = me;
+    // (a) against the boxes kept by earlier chunks
+    bool alive = valid;
+    const int kept0 = s_kept;
+    for (int k = 0; alive && k < kept0; ++k)
+      if (iou_gt(s_keep[k], me, a.iou_thres)) alive = false;
+    const uint32_t ball = __ballot_sync(0xffffffffu, alive);
+    if ((t & 31) == 0) s_alive[t >> 5] = ball;
+    __syncthreads();
+    // (b) the chunk's own suppression matrix: row t = later candidates of the chunk that t would suppress
+    {
+      // a candidate that is already dead never suppresses anything in the greedy scan: its row stays empty
+      uint32_t word = 0;
+      for (int u = 0; u < kChunk; ++u) {
+        const bool s = alive && u > t && (base + u) < n && iou_gt(me, s_chunk[u], a.iou_thres);
+        word |= (s ? 1u : 0u) << (u & 31);
+        if ((u & 31) == 31) { s_sup[t][u >> 5] = word; word = 0; }
+      }
+    }
+    __syncthreads();
+    // (c) sequential resolution by one thread: 256 steps over 8-word masks
+    if (t == 0) {
+      uint32_t al[kChunk / 32];
+#pragma unroll
+      for (int w = 0; w < kChunk / 32; ++w) al[w] = s_alive[w];
+      int nn = 0, kept = s_kept;
+      for (int i = 0; i < kChunk && kept + nn < a.max_det; ++i) {
+        uint32_t bit = 0;
+#pragma unroll
+        for (int w = 0; w < kChunk / 32; ++w)
+          if ((i >> 5) == w) bit = (al[w] >> (i & 31)) & 1u;
+        if (!bit) continue;
+        s_newk[nn++] = i;
+#pragma unroll
+        for (int w = 0; w < kChunk / 32; ++w) al[w] &= ~s_sup[i][w];
+      }
+      s_nnew = nn;
+    }
+    __syncthreads();
+    // (d) append the survivors (in score order) to the kept list and the output
+    const int nn = s_nnew, kept = s_kept;
+    for (int j = 0; j < nn; ++j) {
+      if (s_newk[j] == t) {
+        s_keep[kept + j] = me;
+        float* o = out + (size_t)(kept + j) * 6;
+        o[0] = bx1; o[1] = by1; o[2] = bx2; o[3] = by2; o[4] = conf; o[5] = (float)cls;
+      }
+    }
+    __syncthreads();
+    if (t == 0) s_kept = kept + nn;
+    __syncthreads();
+    if (s_kept >= a.max_det) break;
+  }
+  if (threadIdx.x == 0) a.out_count[img] = s_kept;
+}
+
+inline size_t al256n(size_t v) { return (v + 255) & ~size_t(255); }
+
+int cap_for(int R, int nc, int multi_label) {
+  const long long m = (long long)R * (multi_label ? nc : 1);
+  long long cap = 1;
+  while (cap < m) cap <<= 1;
+  return (int)cap;
+}
+
+}  // namespace
+
+extern "C" size_t ecsy_nms_ws_bytes(int64_t N, int R, int nc, int multi_label) {
+  if (N <= 0 || R <= 0 || nc <= 0) return 0;
+  return 512 + al256n((size_t)N * sizeof(int)) + (size_t)N * cap_for(R, nc, multi_label) * sizeof(unsigned long long);
+}
+
+extern "C" int ecsy_nms(const float* pred, int64_t N, int R, int nc, float conf_thres, double iou_thres, int agnostic,
+                        int multi_label, const uint8_t* cls_ok, int max_det, int max_nms, float* out, int* out_count,
+                        void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ECSY_CHECK_ARG(pred && out && out_count && N > 0 && N < 65536 && R > 0 && nc > 0, "nms: bad arguments");
+  ECSY_CHECK_ARG(conf_thres >= 0.f && conf_thres <= 1.f && iou_thres >= 0.0 && iou_thres <= 1.0,
+                 "nms: thresholds must lie in [0, 1] (utils/general.py:661-662)");
+  ECSY_CHECK_ARG(max_det > 0 && max_det <= 4096 && max_nms > 0, "nms: max_det in [1, 4096], max_nms > 0");
+  ECSY_CHECK_ARG((long long)R * nc < (1LL << 31), "nms: too many (row, class) pairs");
+  if (nc == 1) multi_label = 0;   // general.py:669
+  const size_t need = ecsy_nms_ws_bytes(N, R, nc, multi_label);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("nms: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  NmsArgs a{};
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  a.counts = reinterpret_cast<int*>(p); p += al256n((size_t)N * sizeof(int));
+  a.keys = reinterpret_cast<unsigned long long*>(p);
+  a.pred = pred; a.cls_ok = cls_ok; a.out = out; a.out_count = out_count;
+  a.N = (int)N; a.R = R; a.nc = nc; a.cap = cap_for(R, nc, multi_label);
+  a.max_det = max_det; a.max_nms = max_nms; a.agnostic = agnostic; a.multi_label = multi_label;
+  a.conf_thres = conf_thres;
+  a.iou_thres = iou_thres;   // a double, like the argument of torchvision.ops.nms
+  ECSY_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)N * sizeof(int), st));
+  dim3 grid((unsigned)((R + 255) / 256), (unsigned)N);
+  if (grid.x > 64) grid.x = 64;
+  k_nms_candidates<<<grid, 256, 0, st>>>(a);
+  ECSY_LAUNCH_CHECK();
+  const size_t keep_bytes = (((size_t)max_det * sizeof(Cand) + 15) & ~size_t(15));
+  const size_t smem = keep_bytes + (size_t)kSortSmemKeys * sizeof(unsigned long long);
+  static bool attr = false;
+  if (!attr) {
+    ECSY_CUDA(cudaFuncSetAttribute(k_nms_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  k_nms_select<<<(unsigned)N, kSelThreads, smem, st>>>(a);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}

@@ -158,6 +158,18 @@ int ecsy_detect_decode(const float* y, float* raw, float* z, const float* anchor
 int ecsy_ddetect_decode(const float* box, const float* cls, float* xs, float* y, float stride_px, int N, int H, int W,
                         int nc, int64_t a_total, int64_t a_off, void* stream);
 
+/* ---- non_max_suppression (utils/general.py:649-741) on the decoded Detect output, all images in one call.
+ * pred: [N][R][5+nc] rows (cx, cy, w, h, obj, cls...).  Candidates: obj > conf_thres, conf = obj*cls > conf_thres for
+ * the best class, or for every class with multi_label; cls_ok (optional [nc] bytes) is the `classes` filter; at most
+ * max_nms candidates by confidence enter the greedy scan (torchvision.ops.nms on class-offset boxes, IoU > iou_thres
+ * suppresses; iou_thres is a double like torchvision's argument); the first max_det survivors are written as
+ * out[n][i] = (x1, y1, x2, y2, conf, cls), i < out_count[n], in descending confidence (ties: prediction order).
+ * `labels` (autolabelling, general.py:681-688) and merge-NMS (dead code in the reference) are not supported. */
+size_t ecsy_nms_ws_bytes(int64_t N, int R, int nc, int multi_label);
+int ecsy_nms(const float* pred, int64_t N, int R, int nc, float conf_thres, double iou_thres, int agnostic, int multi_label,
+             const uint8_t* cls_ok, int max_det, int max_nms, float* out, int* out_count, void* ws, size_t ws_bytes,
+             void* stream);
+
 /* ---- backward of mem_update.forward: surrogate-gradient BPTT (ActFun.backward, models/common.py:66-79; autograd
  * through :263-281).  gout: dL/dspikes [T][N][H][W][C]; spikes / mem / ecs: from a re-run of ecsy_lif_ecs_fwd with
  * mem_save + ecs_save; pwT_packed: ecsy_pack_conv_weight of spread[1].weight TRANSPOSED ([ci][co]).

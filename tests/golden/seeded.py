@@ -232,3 +232,82 @@ def ddetect_inputs(spec, oracle):
     feats = [randn(g, spec["T"], spec["N"], spec["ch"][0], spec["H"], spec["W"], scale=0.6, shift=0.1),
              randn(g, spec["T"], spec["N"], spec["ch"][1], spec["H"] // 2, spec["W"] // 2, scale=0.6, shift=0.1)]
     return dict(sd=sd, feats=feats, stride=torch.tensor([8.0, 16.0]))
+
+
+# ---------------------------------------------------------------------------------------------
+# post-decode NMS, optimizer + EMA step
+# ---------------------------------------------------------------------------------------------
+NMS_CASES = {
+    "nms_basic": dict(N=3, R=600, nc=3, conf=0.25, iou=0.45, seed=701),
+    "nms_multi": dict(N=2, R=500, nc=4, conf=0.001, iou=0.6, multi_label=True, seed=702),
+    "nms_agnostic_classes": dict(N=2, R=400, nc=5, conf=0.2, iou=0.5, agnostic=True, classes=[0, 2, 3], seed=703),
+    "nms_maxdet": dict(N=2, R=800, nc=2, conf=0.05, iou=0.3, max_det=20, seed=704),
+    "nms_empty": dict(N=3, R=200, nc=3, conf=0.6, iou=0.45, seed=705, empty_image=1),
+    "nms_nc1": dict(N=2, R=300, nc=1, conf=0.1, iou=0.45, multi_label=True, seed=706),
+    "nms_big": dict(N=1, R=6000, nc=13, conf=0.001, iou=0.6, multi_label=True, seed=707),   # > max_nms candidates
+}
+
+
+def nms_inputs(spec) -> torch.Tensor:
+    """Detect-shaped decoded predictions [N, R, 5 + nc]: jittered boxes around a few objects per image (so that
+    suppression actually happens) plus background boxes; objectness / class scores in (0, 1)."""
+    g = gen(spec["seed"])
+    N, R, nc = spec["N"], spec["R"], spec["nc"]
+    n_obj = 6
+    centers = torch.rand(N, n_obj, 2, generator=g) * 520 + 60
+    sizes = torch.rand(N, n_obj, 2, generator=g) * 150 + 30
+    which = torch.randint(0, n_obj + 2, (N, R), generator=g)          # the last two ids = background
+    pred = torch.zeros(N, R, 5 + nc)
+    bg = which >= n_obj
+    idx = which.clamp(max=n_obj - 1)
+    c = torch.gather(centers, 1, idx.unsqueeze(-1).expand(-1, -1, 2))
+    s = torch.gather(sizes, 1, idx.unsqueeze(-1).expand(-1, -1, 2))
+    jitter = torch.randn(N, R, 2, generator=g) * 6
+    scale = 1 + torch.randn(N, R, 2, generator=g) * 0.08
+    pred[..., 0:2] = torch.where(bg.unsqueeze(-1), torch.rand(N, R, 2, generator=g) * 640, c + jitter)
+    pred[..., 2:4] = torch.where(bg.unsqueeze(-1), torch.rand(N, R, 2, generator=g) * 100 + 8, s * scale)
+    obj = torch.rand(N, R, generator=g)
+    pred[..., 4] = torch.where(bg, obj * 0.3, obj)
+    pred[..., 5:] = torch.rand(N, R, nc, generator=g)
+    if spec.get("empty_image") is not None:
+        pred[spec["empty_image"], :, 4] = 0.0
+    return pred
+
+
+OPT_CASE = dict(lr=0.01, momentum=0.937, weight_decay=0.0005, steps=3, seed=801)
+
+
+class _OptNet(torch.nn.Module):
+    """The three parameter kinds train.py:259-270 sorts into groups: BatchNorm3d weights (g0, no decay), other
+    weights (g1, decay), biases (g2); plus BN buffers, which only the EMA touches."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(4, 8, 3, bias=True)
+        self.bn = torch.nn.BatchNorm3d(8)
+        self.head = torch.nn.Conv2d(8, 5, 1, bias=True)
+        self.big = torch.nn.Conv2d(16, 33, 3, bias=False)     # 4752 elements: more than one chunk, odd tail
+
+
+def opt_inputs(spec):
+    torch.manual_seed(spec["seed"])
+    m = _OptNet()
+    g = gen(spec["seed"] + 1)
+    with torch.no_grad():
+        m.bn.weight.copy_(uniform(g, 8, lo=0.3, hi=0.7))
+        m.bn.running_var.copy_(uniform(g, 8, lo=0.5, hi=1.5))
+    grads = [[randn(g, *p.shape, scale=0.1) for p in m.parameters()] for _ in range(spec["steps"])]
+    return m, grads
+
+
+def opt_groups(model):
+    """train.py:259-270"""
+    g0, g1, g2 = [], [], []
+    for v in model.modules():
+        if hasattr(v, 'bias') and isinstance(v.bias, torch.nn.Parameter):
+            g2.append(v.bias)
+        if isinstance(v, torch.nn.BatchNorm3d):
+            g0.append(v.weight)
+        elif hasattr(v, 'weight') and isinstance(v.weight, torch.nn.Parameter):
+            g1.append(v.weight)
+    return g0, g1, g2

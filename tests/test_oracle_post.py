@@ -1,0 +1,52 @@
+"""The section-8f oracles (oracle/post_oracle.py) against fixtures made by the UNMODIFIED reference functions
+(oracle/gen_golden_post.py): utils.general.non_max_suppression, torch.optim.SGD + utils.torch_utils.ModelEMA."""
+import copy
+import os
+
+import pytest
+import torch
+
+import post_oracle as P
+import seeded as S
+
+
+def _load(name):
+    return torch.load(os.path.join(S.GOLDEN_DIR, name + ".pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", list(S.NMS_CASES))
+def test_nms_oracle(name):
+    gold = _load("post_nms")[name]
+    spec = S.NMS_CASES[name]
+    pred = S.nms_inputs(spec)
+    assert abs(S.checksum(pred) - gold["chk"]) <= 1e-6 * abs(gold["chk"])
+    out = P.non_max_suppression(pred.clone(), spec["conf"], spec["iou"], spec.get("classes"), spec.get("agnostic", False),
+                                spec.get("multi_label", False), spec.get("max_det", 300))
+    assert len(out) == len(gold["out"])
+    for a, b in zip(out, gold["out"]):
+        assert a.shape == b.shape
+        assert torch.equal(a, b)          # bit-exact: same candidates, same order, same arithmetic
+
+
+def test_sgd_ema_oracle():
+    gold = _load("post_opt")
+    spec = S.OPT_CASE
+    model, grads = S.opt_inputs(spec)
+    groups = S.opt_groups(model)
+    gid = {id(p): j for j, g in enumerate(groups) for p in g}
+    params = dict(model.named_parameters())
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ema = copy.deepcopy(state)
+    bufs = {k: None for k in params}
+    for step, gs in enumerate(grads):
+        state["bn.running_mean"] += 0.01 * (step + 1)
+        for (k, p), g in zip(params.items(), gs):
+            j = gid[id(p)]
+            lr = spec["lr"] * (1.0 + 0.1 * step) * (1.5 if j == 2 else 1.0)
+            wd = spec["weight_decay"] if j == 1 else 0.0
+            state[k], bufs[k] = P.sgd_nesterov_step(state[k], g, bufs[k], lr, spec["momentum"], wd)
+        P.ema_update(ema, state, P.ema_decay(step + 1))
+        want = gold["states"][step]
+        for k in state:
+            assert torch.allclose(state[k].float(), want["model"][k].float(), rtol=1e-6, atol=1e-8), (step, k)
+            assert torch.allclose(ema[k].float(), want["ema"][k].float(), rtol=1e-6, atol=1e-8), (step, k)
