@@ -59,6 +59,9 @@ SIGNATURES = {
     "ecsy_xty_bf16": (_i, [_p, _p, _p, _p, _l, _i, _i, _f, _p, _p]),
     "ecsy_nms_ws_bytes": (_z, [_l, _i, _i, _i]),
     "ecsy_nms": (_i, [_p, _l, _i, _i, _f, C.c_double, _i, _i, _p, _i, _i, _p, _p, _p, _z, _p]),
+    "ecsy_optim_chunk": (_i, []),
+    "ecsy_sgd_ema_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _l, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
+                               _f, _i, _i, _i, _f, _f, _p]),
     "ecsy_ddetect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _l, _l, _p]),
 }
 

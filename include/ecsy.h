@@ -170,6 +170,20 @@ int ecsy_nms(const float* pred, int64_t N, int R, int nc, float conf_thres, doub
              const uint8_t* cls_ok, int max_det, int max_nms, float* out, int* out_count, void* ws, size_t ws_bytes,
              void* stream);
 
+/* ---- optimizer.step() + ModelEMA.update() of the training loop (train.py:282-287, 576-582; utils/torch_utils.py:
+ * 306-316) as one multi-tensor launch.  Device tables (caller-owned, built once per model): per tensor the address of the
+ * fp32 value, of its gradient (0 = none: a buffer, or no grad this step), of its zero-initialised momentum buffer (0 =
+ * none) and of its EMA copy (0 = none), its element count and parameter group; per chunk of ecsy_optim_chunk() elements
+ * the tensor index and element offset.  lr / weight_decay: HOST arrays [n_groups] (n_groups <= 8).
+ * SGD (dampening 0): d = g + wd*p; buf = first_step ? d : momentum*buf + d; d = nesterov ? d + momentum*buf : buf;
+ * p -= lr*d.  EMA (do_ema): e = e*ema_d + ema_one_minus_d*p on the UPDATED p, for every tensor with an EMA address. */
+int ecsy_optim_chunk(void);
+int ecsy_sgd_ema_step(const uint64_t* val, const uint64_t* grad, const uint64_t* mom, const uint64_t* ema,
+                      const int64_t* numel, const int32_t* group, int n_tensors, const int32_t* chunk_tensor,
+                      const int64_t* chunk_off, int64_t n_chunks, const float* lr, const float* weight_decay, int n_groups,
+                      float momentum, int nesterov, int first_step, int do_ema, float ema_d, float ema_one_minus_d,
+                      void* stream);
+
 /* ---- backward of mem_update.forward: surrogate-gradient BPTT (ActFun.backward, models/common.py:66-79; autograd
  * through :263-281).  gout: dL/dspikes [T][N][H][W][C]; spikes / mem / ecs: from a re-run of ecsy_lif_ecs_fwd with
  * mem_save + ecs_save; pwT_packed: ecsy_pack_conv_weight of spread[1].weight TRANSPOSED ([ci][co]).

@@ -73,3 +73,65 @@ def test_nms_rejects_bad_arguments():
     with pytest.raises(RuntimeError):
         E.general.non_max_suppression(torch.zeros(1, 4, 8))          # CPU tensor: no fallback
     assert E.general.non_max_suppression(torch.zeros(2, 4, 8).cuda())[1].shape == (0, 6)
+
+
+def test_sgd_ema_golden():
+    """Three optimizer steps (warm-up learning rates per group, weight decay on g1 only, BN buffers moving) + EMA
+    updates against torch.optim.SGD + utils.torch_utils.ModelEMA run by the reference (fixture): fp32 tolerance 1e-6
+    (the reference's CPU kernels fuse a + alpha*b differently), EMA of buffers included."""
+    E = ecsy()
+    gold = _load("post_opt")
+    spec = S.OPT_CASE
+    model, grads = S.opt_inputs(spec)
+    model = model.cuda()
+    opt = E.optim.SGDNesterovEMA(model, lr=spec["lr"], momentum=spec["momentum"], weight_decay=spec["weight_decay"])
+    g0, g1, g2 = S.opt_groups(model)
+    assert [len(g["params"]) for g in opt.param_groups] == [len(g0), len(g1), len(g2)]
+    for step, gs in enumerate(grads):
+        for p, g in zip(model.parameters(), gs):
+            p.grad = g.cuda()
+        for j, pg in enumerate(opt.param_groups):
+            pg["lr"] = spec["lr"] * (1.0 + 0.1 * step) * (1.5 if j == 2 else 1.0)
+        with torch.no_grad():
+            model.bn.running_mean.add_(0.01 * (step + 1))
+        opt.step()
+        opt.zero_grad()
+        want = gold["states"][step]
+        assert opt.ema.updates == want["updates"]
+        sd, esd = model.state_dict(), opt.ema.ema.state_dict()
+        for k in sd:
+            assert torch.allclose(sd[k].cpu().float(), want["model"][k].float(), rtol=1e-6, atol=1e-8), (step, k)
+            assert torch.allclose(esd[k].cpu().float(), want["ema"][k].float(), rtol=1e-6, atol=1e-8), (step, k)
+
+
+def test_sgd_ema_vs_torch_cuda_on_model():
+    """On a real model (tiny Stack-A plan, 235 tensors): identical to torch.optim.SGD(nesterov) on the GPU to 1e-6, a
+    parameter without a gradient is left alone, and the whole step is one kernel launch."""
+    E = ecsy()
+    F = E.functional
+    torch.manual_seed(3)
+    m1 = E.yolo.Model(E.cfg_path("tiny")).cuda()
+    m2 = copy.deepcopy(m1)
+    opt = E.optim.SGDNesterovEMA(m1, lr=0.02, momentum=0.9, weight_decay=1e-3)
+    h0, h1, h2 = E.optim.param_groups_of(m2)
+    ref = torch.optim.SGD(h0, lr=0.02, momentum=0.9, nesterov=True)
+    ref.add_param_group({"params": h1, "weight_decay": 1e-3})
+    ref.add_param_group({"params": h2})
+    g = S.gen(5)
+    skip = next(iter(m1.parameters()))
+    for step in range(2):
+        for p1, p2 in zip(m1.parameters(), m2.parameters()):
+            gr = (torch.randn(p1.shape, generator=g) * 0.05).cuda()
+            if p1 is skip:
+                p1.grad, p2.grad = None, None
+            else:
+                p1.grad, p2.grad = gr.clone(), gr.clone()
+        n0 = F.launches["n"]
+        opt.step()
+        assert F.launches["n"] - n0 == 1
+        ref.step()
+    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+        if a.dtype.is_floating_point:
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), k
+    d1, d2 = opt.ema.decay(1), opt.ema.decay(2)
+    assert opt.ema.updates == 2 and 0 < d1 < d2 < 1
