@@ -137,7 +137,11 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
     if dist is not None:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=64,
                                                         gradient_as_bucket_view=True)
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.937, nesterov=True)
+    if args.optim == "fused":
+        # the reference's three parameter groups + ModelEMA in one multi-tensor launch per step
+        opt = E.optim.SGDNesterovEMA(model, lr=1e-3, momentum=0.937, weight_decay=5e-4)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.937, nesterov=True)
     with torch.no_grad():
         probe = model(x[:, :1] if args.events else x[:1])
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
@@ -203,7 +207,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         "metric": "images/s", "value": imgs / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload.replace("inference", "training (fwd + loss + bwd + SGD step)"),
+        "config": {"workload": workload.replace("inference", "training (fwd + loss + bwd + SGD step" + (" + EMA, fused)" if args.optim == "fused" else ")")),
                    "model_cfg": f"cfg/{args.model}.yaml", "T": args.T, "global_batch": args.batch * world,
                    "precision": args.precision, "accumulate": "fp32",
                    "parallelism": f"DDP x{world} (NCCL all-reduce of fp32 gradients, 64 MB buckets)" if world > 1
@@ -265,6 +269,8 @@ def main():
     ap.add_argument("--events", action="store_true",
                     help="BASELINE config 4: Gen1-style event frames [T,N,3,H,W] straight into _forward_once, nc=2 "
                          "(use with --T 5)")
+    ap.add_argument("--optim", default="fused", choices=["fused", "torch"],
+                    help="training: fused SGD-Nesterov + EMA kernel (default) or torch.optim.SGD without EMA")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()

@@ -62,6 +62,8 @@ SIGNATURES = {
     "ecsy_optim_chunk": (_i, []),
     "ecsy_sgd_ema_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _l, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
                                _f, _i, _i, _i, _f, _f, _p]),
+    "ecsy_event_frames_ws_bytes": (_z, [_l, _i, _i, _i]),
+    "ecsy_event_frames": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "ecsy_ddetect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _l, _l, _p]),
 }
 

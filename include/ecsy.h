@@ -184,6 +184,18 @@ int ecsy_sgd_ema_step(const uint64_t* val, const uint64_t* grad, const uint64_t*
                       float momentum, int nesterov, int first_step, int do_ema, float ema_d, float ema_one_minus_d,
                       void* stream);
 
+/* ---- Gen1 event-camera input: event bins -> network input (g1-resnet/utils/give_g1_data.py:550-565 create_data,
+ * g1-resnet/utils/datasets_g1T.py:518-533 cv2.resize per frame, g1-resnet/train_g1.py:298 "/ 255").
+ * Events in sensor order: ex / ey pixel, ep polarity (0 / 1), eframe = sample * T + time bin.  The last event of a pixel
+ * wins (255 * p over grey 127); frames [H][W] (Gen1: 240 x 304) are resized to [Ho][Wo] with OpenCV's fixed-point
+ * bilinear kernel, bit-exactly, and written as float32 / 255 to out [T][N][Ho][Wo][3] (the model's NHWC input; the
+ * three channels are identical, as in the reference).  oob_count: events outside the sensor / frame range (the
+ * reference asserts on them; they are skipped here and counted). */
+size_t ecsy_event_frames_ws_bytes(int64_t N, int T, int H, int W);
+int ecsy_event_frames(const int32_t* ex, const int32_t* ey, const int32_t* ep, const int32_t* eframe, int64_t n_events,
+                      int64_t N, int T, int H, int W, int Ho, int Wo, float* out, int* oob_count, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* ---- backward of mem_update.forward: surrogate-gradient BPTT (ActFun.backward, models/common.py:66-79; autograd
  * through :263-281).  gout: dL/dspikes [T][N][H][W][C]; spikes / mem / ecs: from a re-run of ecsy_lif_ecs_fwd with
  * mem_save + ecs_save; pwT_packed: ecsy_pack_conv_weight of spread[1].weight TRANSPOSED ([ci][co]).

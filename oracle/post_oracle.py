@@ -122,3 +122,69 @@ def ema_update(ema: Dict[str, torch.Tensor], model: Dict[str, torch.Tensor], d: 
         if v.dtype.is_floating_point:
             v *= d
             v += (1 - d) * model[k].detach()
+
+
+# --------------------------------------------------------------------------------------
+# Gen1 event -> frame input path (g1-resnet/utils/give_g1_data.py:550-565 `create_data`; the loader's per-frame
+# cv2.resize, g1-resnet/utils/datasets_g1T.py:518-533; `imgs.float() / 255`, g1-resnet/train_g1.py:298).
+# cv2 (OpenCV 4.x, a third-party dependency that is not vendored in /root/reference) resizes uint8 images with
+# INTER_LINEAR in 11-bit fixed point: restated here from its published algorithm (imgproc/src/resize.cpp:
+# resizeGeneric_ / HResizeLinear / VResizeLinear<uchar>) and pinned bit-exactly on cv2 outputs.
+# --------------------------------------------------------------------------------------
+EV_W, EV_H = 304, 240
+
+
+def events_to_frames(samples, T: int) -> torch.Tensor:
+    """samples[n][t] = dict(x, y, p) in sensor order -> uint8 [N, T, 240, 304]: grey 127, an event paints 255*p, the
+    LAST event of a pixel wins (numpy fancy assignment in event order).  The 3 channels are identical."""
+    out = torch.full((len(samples), T, EV_H, EV_W), 127, dtype=torch.uint8)
+    for n, bins in enumerate(samples):
+        for t in range(T):
+            b = bins[t]
+            for x, y, p in zip(b["x"].tolist(), b["y"].tolist(), b["p"].tolist()):
+                out[n, t, y, x] = 255 * p
+    return out
+
+
+def _linear_coeffs(ssize: int, dsize: int, reset: bool):
+    import numpy as np
+    scale = 1.0 / (float(dsize) / float(ssize))           # resize.cpp: scale_x = 1. / inv_scale_x
+    idx = np.zeros(dsize, np.int64)
+    a = np.zeros((dsize, 2), np.int64)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if reset:                                          # x only: border columns take the edge pixel with weight 1
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= ssize - 1:
+                f, s = np.float32(0), ssize - 1
+        idx[d] = s
+        a[d, 0] = int(np.rint(np.float32(np.float32(1.0) - f) * np.float32(2048)))
+        a[d, 1] = int(np.rint(f * np.float32(2048)))
+    return idx, a
+
+
+def resize_linear_u8(img: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
+    """cv2.resize(img, (dw, dh)) (INTER_LINEAR) for a uint8 [H, W] image, bit-exact."""
+    import numpy as np
+    src = img.numpy().astype(np.int64)
+    sh, sw = src.shape
+    xi, xa = _linear_coeffs(sw, dw, True)
+    yi, ya = _linear_coeffs(sh, dh, False)                 # y: rows are clamped, the weights are not reset
+    x1 = np.minimum(xi + 1, sw - 1)
+    H = src[:, xi] * xa[:, 0][None, :] + src[:, x1] * xa[:, 1][None, :]
+    S0, S1 = H[np.clip(yi, 0, sh - 1)], H[np.clip(yi + 1, 0, sh - 1)]
+    b0, b1 = ya[:, 0][:, None], ya[:, 1][:, None]
+    out = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2
+    return torch.from_numpy(out.astype(np.uint8))
+
+
+def event_frames(samples, T: int, out_hw: int) -> torch.Tensor:
+    """The network input of the Gen1 detector: float32 [T, N, 3, S, S] = resized frames / 255."""
+    fr = events_to_frames(samples, T)
+    N = fr.shape[0]
+    res = torch.stack([torch.stack([resize_linear_u8(fr[n, t], out_hw, out_hw) for t in range(T)]) for n in range(N)])
+    x = res.float() / 255                                  # [N, T, S, S]
+    return x.permute(1, 0, 2, 3).unsqueeze(2).expand(-1, -1, 3, -1, -1).contiguous()

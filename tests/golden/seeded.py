@@ -311,3 +311,47 @@ def opt_groups(model):
         elif hasattr(v, 'weight') and isinstance(v.weight, torch.nn.Parameter):
             g1.append(v.weight)
     return g0, g1, g2
+
+
+# Gen1 event-camera input (g1-resnet): T bins of (x, y, p) events of a 304 x 240 sensor per sample
+EVENT_CASES = {
+    "ev_t5_320": dict(N=3, T=5, n_events=40000, out=320, seed=901),
+    "ev_t5_640": dict(N=2, T=5, n_events=15000, out=640, seed=902),
+    "ev_t4_sparse": dict(N=2, T=4, n_events=300, out=320, seed=903, empty_bin=(1, 2)),
+}
+EV_W, EV_H = 304, 240
+
+
+def event_inputs(spec):
+    """-> list over samples of list over T bins of dict(x, y, p) int64 arrays, in sensor (time) order.  Events
+    cluster around a few moving blobs so that many pixels receive several events (last write wins)."""
+    g = gen(spec["seed"])
+    samples = []
+    for n in range(spec["N"]):
+        bins = []
+        for t in range(spec["T"]):
+            k = int(torch.randint(spec["n_events"] // 2, spec["n_events"], (1,), generator=g))
+            if spec.get("empty_bin") == (n, t):
+                k = 0
+            c = torch.rand(4, 2, generator=g) * torch.tensor([EV_W - 40.0, EV_H - 40.0]) + 20
+            which = torch.randint(0, 5, (k,), generator=g)
+            pos = torch.where((which < 4).unsqueeze(-1), c[which.clamp(max=3)] + torch.randn(k, 2, generator=g) * 9,
+                              torch.rand(k, 2, generator=g) * torch.tensor([float(EV_W), float(EV_H)]))
+            x = pos[:, 0].round().long().clamp(0, EV_W - 1)
+            y = pos[:, 1].round().long().clamp(0, EV_H - 1)
+            p = torch.randint(0, 2, (k,), generator=g)
+            bins.append(dict(x=x, y=y, p=p))
+        samples.append(bins)
+    return samples
+
+
+def zpack(t: torch.Tensor) -> dict:
+    """uint8 tensor -> zlib-compressed bytes (event frames are mostly grey: ~50x smaller fixtures)."""
+    import zlib
+    assert t.dtype == torch.uint8
+    return dict(z=zlib.compress(t.contiguous().numpy().tobytes(), 9), shape=tuple(t.shape))
+
+
+def zunpack(d: dict) -> torch.Tensor:
+    import zlib
+    return torch.frombuffer(bytearray(zlib.decompress(d["z"])), dtype=torch.uint8).reshape(*d["shape"]).clone()

@@ -135,3 +135,59 @@ def test_sgd_ema_vs_torch_cuda_on_model():
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), k
     d1, d2 = opt.ema.decay(1), opt.ema.decay(2)
     assert opt.ema.updates == 2 and 0 < d1 < d2 < 1
+
+
+def _flat_events(samples, T):
+    xs, ys, ps, fs = [], [], [], []
+    for n, bins in enumerate(samples):
+        for t in range(T):
+            b = bins[t]
+            xs.append(b["x"]); ys.append(b["y"]); ps.append(b["p"])
+            fs.append(torch.full_like(b["x"], n * T + t))
+    cat = lambda v: torch.cat(v).to(torch.int32).cuda()
+    return cat(xs), cat(ys), cat(ps), cat(fs)
+
+
+@pytest.mark.parametrize("name", list(S.EVENT_CASES))
+def test_event_frames_golden(name):
+    """Bit-exact against the reference's create_data + cv2.resize + /255 (fixture), incl. an empty bin, pixels hit by
+    many events (the last one wins) and both network sizes."""
+    E = ecsy()
+    gold = _load("post_events")[name]
+    spec = S.EVENT_CASES[name]
+    samples = S.event_inputs(spec)
+    x, y, p, f = _flat_events(samples, spec["T"])
+    out = E.events.event_frames(x, y, p, f, spec["N"], spec["T"], (spec["out"], spec["out"]), check=True)
+    assert out.shape == (spec["T"], spec["N"], 3, spec["out"], spec["out"])
+    want = (S.zunpack(gold["resized_ch0"]).float() / 255).permute(1, 0, 2, 3)      # [T, N, S, S]
+    got = out.cpu()
+    for c in range(3):
+        assert torch.equal(got[:, :, c], want), (name, c)
+    # identity size = the painted frames themselves
+    same = E.events.event_frames(x, y, p, f, spec["N"], spec["T"], (240, 304)).cpu()
+    painted = S.zunpack(gold["painted_ch0"]).float() / 255                            # [N, T, 240, 304]
+    assert torch.equal(same[:, :, 0], painted.permute(1, 0, 2, 3))
+
+
+def test_event_frames_feed_the_model_and_flag_bad_events():
+    E = ecsy()
+    spec = S.EVENT_CASES["ev_t4_sparse"]
+    samples = S.event_inputs(spec)
+    x, y, p, f = _flat_events(samples, spec["T"])
+    frames = E.events.event_frames(x, y, p, f, spec["N"], spec["T"], (64, 64))
+    a = E.functional.Act.from_ref(frames)
+    assert a.data.data_ptr() == frames.data_ptr()            # NHWC memory: no layout conversion in front of the stem
+    E.common.time_window = spec["T"]
+    try:
+        m = E.yolo.Model(E.cfg_path("tiny"), nc=2).cuda().train()
+        with torch.no_grad():
+            out = m._forward_once(frames)
+    finally:
+        E.common.time_window = 4
+    assert all(torch.isfinite(o).all() for o in out)
+    xb = x.clone(); xb[5] = 304
+    with pytest.raises(AssertionError):
+        E.events.event_frames(xb, y, p, f, spec["N"], spec["T"], (64, 64), check=True)
+    empty = torch.zeros(0, dtype=torch.int32).cuda()
+    grey = E.events.event_frames(empty, empty, empty, empty, 1, 2, (32, 32))
+    assert torch.equal(grey.cpu(), torch.full((2, 1, 3, 32, 32), 127.0) / 255)

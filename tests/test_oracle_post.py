@@ -50,3 +50,21 @@ def test_sgd_ema_oracle():
         for k in state:
             assert torch.allclose(state[k].float(), want["model"][k].float(), rtol=1e-6, atol=1e-8), (step, k)
             assert torch.allclose(ema[k].float(), want["ema"][k].float(), rtol=1e-6, atol=1e-8), (step, k)
+
+
+@pytest.mark.parametrize("name", list(S.EVENT_CASES))
+def test_event_frames_oracle(name):
+    """create_data (last event of a pixel wins) and the cv2.resize restatement, bit-exact on the reference's frames."""
+    gold = _load("post_events")[name]
+    spec = S.EVENT_CASES[name]
+    samples = S.event_inputs(spec)
+    assert gold["same_channels"] and gold["resized_same"]
+    painted = P.events_to_frames(samples, spec["T"])
+    assert torch.equal(painted, S.zunpack(gold["painted_ch0"]))
+    want = S.zunpack(gold["resized_ch0"])                       # [N, T, S, S]
+    for n in range(spec["N"]):
+        for t in range(0, spec["T"], 2):
+            assert torch.equal(P.resize_linear_u8(painted[n, t], spec["out"], spec["out"]), want[n, t]), (n, t)
+    x = P.event_frames(samples[:1], spec["T"], spec["out"])
+    assert x.shape == (spec["T"], 1, 3, spec["out"], spec["out"])
+    assert torch.equal(x[:, 0, 1], want[0].float() / 255)
