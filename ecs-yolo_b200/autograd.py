@@ -100,13 +100,21 @@ def bn_train_bwd(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
 # LIF -> spike conv -> tdBN
 # ------------------------------------------------------------------------------------------------
 class _Saved:
-    __slots__ = ("x", "aff", "sp", "y", "mean", "rstd", "scale", "shift")
+    __slots__ = ("x", "aff", "sp", "y", "mean", "rstd", "scale", "shift", "state")
 
 
 def chain_fwd(lif, conv, bn, x: Act, aff):
     sv = _Saved()
     sv.x, sv.aff = x, aff
-    sv.sp = lif.spikes(x, aff)
+    if F_.lif_store_ok(x):
+        # keep membranes + traces for the backward (memory for time on a 180 GB part): no forward recompute there
+        if lif.spread is None:
+            lif._init_spread(x.C, x.data.device)
+        sv.sp, mem, ecs = F_.lif_ecs(x, lif._weights(), aff, lif.ecs_tau, lif.alpha, lif.beta, save_mem=True)
+        sv.state = (sv.sp, mem, ecs)
+    else:
+        sv.sp = lif.spikes(x, aff)
+        sv.state = None
     sv.y = conv.conv_spikes(sv.sp)
     sv.scale, sv.shift, sv.mean, sv.rstd = bn_train_fwd(bn, sv.y)
     return sv
@@ -137,7 +145,8 @@ def chain_bwd(lif, conv, bn, sv: _Saved, g_yn: torch.Tensor, grads):
     g_y = bn_train_bwd(bn, sv.y, sv.mean, sv.rstd, g_yn, grads)
     g_s = conv_spikes_bwd(conv, sv.sp, g_y, grads)
     g_x, gdw, gdb, gpw, gpb = F_.lif_ecs_bwd(g_s, sv.x, lif._weights(), lif.spread[1].weight, sv.aff, lif.ecs_tau,
-                                             lif.alpha, lif.beta)
+                                             lif.alpha, lif.beta, saved=sv.state)
+    sv.state = None
     _acc(grads, lif.spread[0].weight, gdw)
     _acc(grads, lif.spread[0].bias, gdb)
     _acc(grads, lif.spread[1].weight, gpw)

@@ -24,7 +24,8 @@ decay = 0.25
 
 # conv_ts: "auto" (measured dispatch rule), "all" (wherever supported) or "off"
 _state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
-          "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1"}
+          "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1",
+          "lif_store": os.environ.get("ECSY_LIF_STORE", "1") == "1"}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
@@ -94,6 +95,22 @@ def set_lif_fused(on: bool) -> None:
     """Fast mode, C == 64: run the ECS-LIF forward as ONE kernel with all T steps on chip.  Parity-green but
     measured slower than the per-timestep pipeline so far (csrc/lif_fused.cu header), hence off by default."""
     _state["lif_fused"] = bool(on)
+
+
+def set_lif_store(on: bool) -> None:
+    """Training: keep the membranes / ECS traces the forward pass computes for the BPTT backward (8 B per element-step,
+    ~35 GB for resnet34 at batch 32 -- sized for the B200's 180 GB) instead of recomputing the forward inside the
+    backward.  Falls back to recomputation per layer when free device memory is short."""
+    _state["lif_store"] = bool(on)
+
+
+def lif_store_ok(x: "Act") -> bool:
+    if not _state["lif_store"] or x.C % 64:
+        return False
+    need = (2 * x.T - 1) * x.N * x.H * x.W * x.C * 4
+    free, _ = torch.cuda.mem_get_info(x.data.device)
+    # the caching allocator may hold reusable blocks on top of `free`; keep a wide margin for the backward's workspaces
+    return free + torch.cuda.memory_reserved(x.data.device) - torch.cuda.memory_allocated(x.data.device) > 3 * need + (8 << 30)
 
 
 def conv_ts_enabled() -> bool:
@@ -381,13 +398,14 @@ def spread_dw(sp: Spikes, t: int, w: LifW, lo: bool = False, version: int = 0):
 
 
 def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, affine=None, ecs_tau: float = 5.0,
-                alpha: float = 0.75, beta: float = 0.25):
+                alpha: float = 0.75, beta: float = 0.25, saved=None):
     """Surrogate-gradient BPTT of lif_ecs.  gout: [T,N,H,W,C] dL/dspikes.  Re-runs the forward to recompute the
     membranes / ECS traces, then the reverse scan.  Returns (g_in [T,N,H,W,C] wrt the affine-applied input
     current, g_dw_w [C,1,3,3], g_dw_b [C], g_pw_w [C,C,1,1], g_pw_b [C])."""
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
-    sp, mem, ecs = lif_ecs(x, w, affine, ecs_tau, alpha, beta, save_mem=True)
+    # `saved` = (spikes, membranes, traces) kept by a forward run with save_mem (set_lif_store); otherwise recompute
+    sp, mem, ecs = saved if saved is not None else lif_ecs(x, w, affine, ecs_tau, alpha, beta, save_mem=True)
     gout = gout.contiguous()
     gx = torch.empty(T, N, H, W, C, device=dev, dtype=torch.float32)
     g_dw_w = torch.zeros(9, C, device=dev, dtype=torch.float32)

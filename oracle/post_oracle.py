@@ -62,12 +62,14 @@ def greedy_nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thres: float) -> t
 
 def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
                         classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
-                        max_det: int = 300) -> List[torch.Tensor]:
-    """utils/general.py:649-741 without the autolabelling / merge-NMS / time-limit branches."""
+                        max_det: int = 300, use_torchvision: bool = False) -> List[torch.Tensor]:
+    """utils/general.py:649-741 without the autolabelling / merge-NMS / time-limit branches.  ``use_torchvision``
+    calls torchvision.ops.nms for the inner step exactly like the reference (the timing leg of tools/post_bench.py;
+    works on CUDA tensors too); the default is the pure-torch restatement of it."""
     nc = prediction.shape[2] - 5
     xc = prediction[..., 4] > conf_thres
     multi_label &= nc > 1
-    output = [torch.zeros((0, 6))] * prediction.shape[0]
+    output = [torch.zeros((0, 6), device=prediction.device)] * prediction.shape[0]
     for xi, x in enumerate(prediction):
         x = x[xc[xi]].clone()
         if not x.shape[0]:
@@ -81,7 +83,7 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
             conf, j = x[:, 5:].max(1, keepdim=True)
             x = torch.cat((box, conf, j.float()), 1)[conf.view(-1) > conf_thres]
         if classes is not None:
-            x = x[(x[:, 5:6] == torch.tensor(classes)).any(1)]
+            x = x[(x[:, 5:6] == torch.tensor(classes, device=x.device)).any(1)]
         n = x.shape[0]
         if not n:
             continue
@@ -89,7 +91,11 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
             x = x[x[:, 4].argsort(descending=True)[:MAX_NMS]]
         c = x[:, 5:6] * (0 if agnostic else MAX_WH)
         boxes, scores = x[:, :4] + c, x[:, 4]
-        i = greedy_nms(boxes, scores, iou_thres)
+        if use_torchvision:
+            import torchvision
+            i = torchvision.ops.nms(boxes, scores, iou_thres)
+        else:
+            i = greedy_nms(boxes, scores, iou_thres)
         if i.shape[0] > max_det:
             i = i[:max_det]
         output[xi] = x[i]

@@ -162,3 +162,33 @@ def test_model_b_training_step():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+def test_stored_lif_state_equals_recompute():
+    """set_lif_store(True) keeps the forward's membranes / traces for the BPTT backward; the gradients must be
+    the recompute path's (same kernels, same arithmetic on the same state), in both precision modes."""
+    E = ecsy()
+    F = E.functional
+    spec = S.BLOCK_CASES["bb2_64_128_s2"]
+    inp = S.block_inputs(spec, O)
+    for mode in ("parity", "fast"):
+        F.set_precision(mode)
+        try:
+            res = []
+            for store in (True, False):
+                F.set_lif_store(store)
+                m = _build_block(E, spec)
+                m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+                m = m.cuda().train()
+                x = inp["x"].cuda().requires_grad_(True)
+                out = m(x)
+                out.backward(S.randn(S.gen(5), *out.shape).cuda())
+                res.append((out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+            assert torch.equal(res[0][0], res[1][0])            # the forward is deterministic
+            # the backward reductions use floating-point atomics (run-to-run order), so gradients agree to rounding
+            assert rel_l2(res[0][1], res[1][1]) < 1e-5
+            for a, b in zip(res[0][2], res[1][2]):
+                assert rel_l2(a, b) < 1e-5
+        finally:
+            F.set_precision("parity")
+            F.set_lif_store(True)
