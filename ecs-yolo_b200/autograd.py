@@ -124,6 +124,21 @@ def conv_spikes_bwd(conv, sp, g_y: torch.Tensor, grads):
     """-> g_s [T,N,H,W,Ci]; accumulates dW."""
     from .common import _cached
     k, s, p = conv._geom()
+    co, ci = conv.out_channels, conv.in_channels
+    if (sp.C != ci or co % 64) and conv.groups == 1:
+        # narrow layer (res*-ee.yaml front) on the padded 64-channel granule: zero-padded output gradient and weights,
+        # the real block of the weight gradient; the input gradient keeps the padded width of the spike tensor
+        cop = F_.pad64(co)
+        g_yp = F_.pad_channels(g_y, cop)
+        _acc(grads, conv.weight, F_.spike_conv_wgrad(g_yp, sp, k, s, p)[:co, :ci].contiguous())
+        splits = F_.get_splits()
+
+        def build_p():
+            w = torch.nn.functional.pad(conv.weight.detach().float(), (0, 0, 0, 0, 0, sp.C - ci, 0, cop - co))
+            return F_.pack_dgrad_weight(w, splits)
+        wT = _cached(conv, "dgradw_pad", (conv.weight,), build_p)
+        g_s = F_.conv_dgrad(g_yp, wT, splits, sp.H, sp.W, sp.C, k, s, p)
+        return g_s[..., :ci].contiguous() if sp.C != ci else g_s
     dw = F_.spike_conv_wgrad(g_y, sp, k, s, p)
     if conv.groups > 1:  # block-diagonal part of the dense gradient
         cog, cig = conv.out_channels // conv.groups, conv.in_channels // conv.groups
@@ -202,6 +217,73 @@ class BasicBlockFn(torch.autograd.Function):
             g_sc = F_.maxpool_bwd(ctx.a, g_p, ctx.pool) if ctx.pool > 1 else g_p
             g_x = _add(g_x, g_sc)
         return (None, g_x.permute(0, 1, 4, 2, 3)) + _grad_tuple(block, grads)
+
+
+class BasicBlockMsFn(torch.autograd.Function):
+    """BasicBlock_ms in training mode (models/common.py:1658-1687): the shortcut is max-pool -> 1x1 conv on the REAL
+    input -> tdBN, no neuron."""
+
+    @staticmethod
+    def forward(ctx, block, x_ref, *params):
+        a = Act.from_ref(x_ref)
+        l1, c1, b1, l2, c2, b2 = block.residual_function
+        s1 = chain_fwd(l1, c1, b1, a, None)
+        s2 = chain_fwd(l2, c2, b2, s1.y, (s1.scale, s1.shift))
+        ctx.block, ctx.a, ctx.s1, ctx.s2 = block, a, s1, s2
+        if len(block.shortcut) == 0:
+            ctx.z = None
+            out = F_.affine_add(s2.y, s2.scale, s2.shift, a, None, None)
+        else:
+            pool, conv, bn = block.shortcut
+            ctx.pool = pool.stride[1]
+            ctx.xp = F_.maxpool(a, ctx.pool).full()
+            ctx.z = conv.conv_real(ctx.xp)
+            sc, sh, ctx.mean, ctx.rstd = bn_train_fwd(bn, ctx.z)
+            out = F_.affine_add(s2.y, s2.scale, s2.shift, ctx.z, sc, sh)
+        return out.to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        from .common import _cached
+        block = ctx.block
+        g = _to_nhwc(g_ref)
+        grads: Dict[int, torch.Tensor] = {}
+        l1, c1, b1, l2, c2, b2 = block.residual_function
+        g_y1n = chain_bwd(l2, c2, b2, ctx.s2, g, grads)
+        g_x = chain_bwd(l1, c1, b1, ctx.s1, g_y1n, grads)
+        if ctx.z is None:
+            g_x = _add(g_x, g)
+        else:
+            pool, conv, bn = block.shortcut
+            g_z = bn_train_bwd(bn, ctx.z, ctx.mean, ctx.rstd, g, grads)
+            k, s, p = conv._geom()
+            _acc(grads, conv.weight, F_.real_conv_wgrad(g_z, ctx.xp, k, s, p))
+            splits = F_.get_splits()
+            wT = _cached(conv, "dgradw", (conv.weight,), lambda: F_.pack_dgrad_weight(conv.weight, splits))
+            g_xp = F_.conv_dgrad(g_z, wT, splits, ctx.xp.H, ctx.xp.W, conv.in_channels, k, s, p)
+            g_sc = F_.maxpool_bwd(ctx.a, g_xp, ctx.pool) if ctx.pool > 1 else g_xp
+            g_x = _add(g_x, g_sc)
+        return (None, g_x.permute(0, 1, 4, 2, 3)) + _grad_tuple(block, grads)
+
+
+class ConvBFn(torch.autograd.Function):
+    """One Conv_B / Conv_2 (LIF -> conv -> tdBN) in training mode (models/common.py:393-406, 428-440)."""
+
+    @staticmethod
+    def forward(ctx, mod, x_ref, *params):
+        a = Act.from_ref(x_ref)
+        ctx.mod, ctx.need_gx = mod, x_ref.requires_grad
+        ctx.s1 = chain_fwd(mod.act, mod.conv, mod.bn, a, None)
+        return F_.affine_add(ctx.s1.y, ctx.s1.scale, ctx.s1.shift).to_ref()
+
+    @staticmethod
+    def backward(ctx, g_ref):
+        g = _to_nhwc(g_ref)
+        grads: Dict[int, torch.Tensor] = {}
+        mod = ctx.mod
+        g_x = chain_bwd(mod.act, mod.conv, mod.bn, ctx.s1, g, grads)
+        gx_ref = g_x.permute(0, 1, 4, 2, 3) if ctx.need_gx else None
+        return (None, gx_ref) + _grad_tuple(mod, grads)
 
 
 class ConcatRes2Fn(torch.autograd.Function):

@@ -366,8 +366,7 @@ class BasicBlock_ms(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         from . import autograd as AG
         if AG.wants_grad(self, x):
-            raise NotImplementedError("BasicBlock_ms: forward only (no BPTT chain for the res*-ee.yaml blocks yet); "
-                                      "call under torch.no_grad()")
+            return AG.BasicBlockMsFn.apply(self, x, *self.parameters())
         a = Act.from_ref(x)
         if len(self.shortcut) == 0:
             return _residual_path(self.residual_function, a, a).to_ref()
@@ -387,12 +386,6 @@ class ConcatBlock_ms(Concat_res2):
         nn.Module.__init__(self)
         self._build(in_channels, int(out_channels * e), out_channels, k_size, stride)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        from . import autograd as AG
-        if AG.wants_grad(self, x):
-            raise NotImplementedError("ConcatBlock_ms: forward only (no BPTT chain for the res*-ee.yaml blocks yet); "
-                                      "call under torch.no_grad()")
-        return super().forward(x)
 
 
 class Conv_1(nn.Module):
@@ -438,6 +431,9 @@ class Conv_B(nn.Module):
         return y if aff is None else F_.affine_add(y, aff[0], aff[1])
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import autograd as AG
+        if AG.wants_grad(self, x):
+            return AG.ConvBFn.apply(self, x, *self.parameters())
         return self.run(Act.from_ref(x)).to_ref()
 
 

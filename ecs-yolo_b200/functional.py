@@ -344,9 +344,7 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     is zero-padded to the next multiple of 64 (``w`` must come from make_lif_w(..., Cp)); the result carries Cr = C."""
     Cr = x.C
     if Cr % 64:
-        if save_mem:
-            raise NotImplementedError("lif_ecs: the BPTT recompute pass needs C % 64 == 0")
-        Cp = pad64(Cr)
+        Cp = pad64(Cr)     # with save_mem the membranes / traces come back padded too (lif_ecs_bwd slices its results)
         if w is not None and w.dw_b.numel() != Cp:
             raise RuntimeError("lif_ecs: spread weights must be padded to %d channels" % Cp)
         x = Act(pad_channels(x.data, Cp), x.T)
@@ -402,6 +400,18 @@ def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, af
     """Surrogate-gradient BPTT of lif_ecs.  gout: [T,N,H,W,C] dL/dspikes.  Re-runs the forward to recompute the
     membranes / ECS traces, then the reverse scan.  Returns (g_in [T,N,H,W,C] wrt the affine-applied input
     current, g_dw_w [C,1,3,3], g_dw_b [C], g_pw_w [C,C,1,1], g_pw_b [C])."""
+    Cr = x.C
+    if Cr % 64:
+        # narrow layer (res*-ee.yaml front): run zero-padded to the 64-channel granule, slice the results
+        Cp = pad64(Cr)
+        x = Act(pad_channels(x.data, Cp), x.T)
+        if affine is not None:
+            affine = (pad_channels(affine[0], Cp), pad_channels(affine[1], Cp))
+        gout = pad_channels(gout, Cp)
+        pw_weight = torch.nn.functional.pad(pw_weight.detach().float(), (0, 0, 0, 0, 0, Cp - Cr, 0, Cp - Cr))
+        gx, gdw, gdb, gpw, gpb = lif_ecs_bwd(gout, x, w, pw_weight, affine, ecs_tau, alpha, beta, saved)
+        return (gx[..., :Cr].contiguous(), gdw[:Cr].contiguous(), gdb[:Cr].contiguous(),
+                gpw[:Cr, :Cr].contiguous(), gpb[:Cr].contiguous())
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
     # `saved` = (spikes, membranes, traces) kept by a forward run with save_mem (set_lif_store); otherwise recompute

@@ -20,10 +20,13 @@ def _build_block(E, spec):
     return cls(spec["cin"], spec["cout"], spec["k"], spec["s"])
 
 
-@pytest.mark.parametrize("name", list(S.BLOCK_CASES))
+ALL_BLOCKS = {**S.BLOCK_CASES, **S.MS_BLOCK_CASES}   # MS_*: res*-ee.yaml blocks incl. the zero-padded 3 / 32-channel front
+
+
+@pytest.mark.parametrize("name", list(ALL_BLOCKS))
 def test_block_backward(name):
     E = ecsy()
-    spec, gold = S.BLOCK_CASES[name], load_golden(name)
+    spec, gold = ALL_BLOCKS[name], load_golden(name)
     inp = S.block_inputs(spec, O)
     m = _build_block(E, spec)
     m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
@@ -192,3 +195,27 @@ def test_stored_lif_state_equals_recompute():
         finally:
             F.set_precision("parity")
             F.set_lif_store(True)
+
+
+def test_model_ee_training_step():
+    """res*-ee.yaml topology (Conv_2 on the image, ConcatBlock_ms, BasicBlock_ms): forward + backward + fused optimizer
+    step; every parameter gets a finite gradient and the loss goes down on a fixed batch."""
+    E = ecsy()
+    torch.manual_seed(0)
+    m = E.yolo.Model(E.cfg_path("tiny_ee")).cuda().train()
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    opt = E.optim.SGDNesterovEMA(m, lr=0.002, momentum=0.9, weight_decay=0.0)
+    with torch.no_grad():
+        tgt = [torch.randn_like(o) for o in m(x)]
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        out = m(x)
+        loss = sum(((o - t) ** 2).mean() for o, t in zip(out, tgt))
+        loss.backward()
+        if not losses:
+            missing = [k for k, p in m.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+            assert not missing, missing[:5]
+        opt.step()
+        losses.append(loss.item())
+    assert min(losses[1:]) < losses[0], losses
