@@ -102,15 +102,26 @@ def set_lif_store(on: bool) -> None:
     ~35 GB for resnet34 at batch 32 -- sized for the B200's 180 GB) instead of recomputing the forward inside the
     backward.  Falls back to recomputation per layer when free device memory is short."""
     _state["lif_store"] = bool(on)
+    _store_decisions.clear()
+
+
+_store_decisions = {}
 
 
 def lif_store_ok(x: "Act") -> bool:
     if not _state["lif_store"] or x.C % 64:
         return False
-    need = (2 * x.T - 1) * x.N * x.H * x.W * x.C * 4
-    free, _ = torch.cuda.mem_get_info(x.data.device)
-    # the caching allocator may hold reusable blocks on top of `free`; keep a wide margin for the backward's workspaces
-    return free + torch.cuda.memory_reserved(x.data.device) - torch.cuda.memory_allocated(x.data.device) > 3 * need + (8 << 30)
+    # decided once per (device, layer shape), in forward order of the first training step: cudaMemGetInfo is a slow,
+    # driver-serialised call (measured: ~3 ms each with two ranks on one box -- 170 ms per step when asked per layer)
+    key = (x.data.device.index, x.T, x.N, x.H, x.W, x.C)
+    ok = _store_decisions.get(key)
+    if ok is None:
+        need = (2 * x.T - 1) * x.N * x.H * x.W * x.C * 4
+        free, _ = torch.cuda.mem_get_info(x.data.device)
+        # the caching allocator may hold reusable blocks on top of `free`; keep a wide margin for the backward's workspaces
+        spare = free + torch.cuda.memory_reserved(x.data.device) - torch.cuda.memory_allocated(x.data.device)
+        ok = _store_decisions[key] = bool(spare > 3 * need + (8 << 30))
+    return ok
 
 
 def conv_ts_enabled() -> bool:
