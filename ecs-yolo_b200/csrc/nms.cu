@@ -6,8 +6,8 @@
 //                      above the threshold (general.py:697-702), optional class filter (:705-706).  A candidate is
 //                      a 64-bit key (~score bits << 32 | row * nc + class): ascending key order = descending score,
 //                      ties by prediction order -- the order of the stable sort inside torchvision's nms.
-//   k_nms_select     : one CTA per image: bitonic sort of the keys (shared memory up to 8192 candidates, in place in
-//                      the L2-resident workspace above that), truncation to max_nms (general.py:716-717), then the
+//   k_nms_select     : one CTA per image: bitonic sort of the keys (shared memory up to 8192 candidates; above that the
+//                      large strides run over the L2-resident workspace and the small ones chunk-wise in shared memory), truncation to max_nms (general.py:716-717), then the
 //                      greedy scan in chunks of 256 candidates: every thread tests one candidate against the boxes
 //                      kept so far, the chunk's own 256 x 256 suppression bit matrix resolves the order dependence
 //                      inside the chunk, and the scan stops at max_det kept boxes (general.py:723-724: the first
@@ -72,21 +72,59 @@ __global__ void k_nms_candidates(const NmsArgs a) {
   }
 }
 
-// in-place bitonic sort (ascending) of P = 2^k keys by one CTA; `k` may live in shared or global memory
-__device__ void bitonic_sort(unsigned long long* k, int P) {
-  int lp = 0;
+// Strides 2^ls_start .. 1 of bitonic stage `size = 1 << lsize` on the CH keys of `s` (shared memory) whose first key has
+// global index `base`: the direction of a compare-exchange depends on the GLOBAL index of its lower element.
+__device__ void bitonic_chunk(unsigned long long* s, int base, int CH, int lsize, int ls_start) {
+  const int size = 1 << lsize;
+  for (int ls = ls_start; ls >= 0; --ls) {
+    const int stride = 1 << ls;
+    for (int i = threadIdx.x; i < (CH >> 1); i += blockDim.x) {
+      const int lo = ((i >> ls) << (ls + 1)) | (i & (stride - 1));
+      const int hi = lo + stride;
+      const bool up = ((base + lo) & size) == 0;
+      const unsigned long long x = s[lo], y = s[hi];
+      if ((x > y) == up) { s[lo] = y; s[hi] = x; }
+    }
+    __syncthreads();
+  }
+}
+
+// Ascending bitonic sort of P = 2^lp keys by one CTA.  P <= CH: entirely in shared memory (`s` holds the keys).
+// P > CH: the keys stay in `g` (global, L2 resident); every stage runs its strides >= CH as passes over global memory
+// and finishes its strides < CH chunk by chunk in shared memory (10 global passes instead of 153 at P = 131072).
+__device__ void bitonic_sort_hybrid(unsigned long long* g, unsigned long long* s, int P, int CH) {
+  int lp = 0, lch = 0;
   while ((1 << lp) < P) ++lp;
-  for (int lsize = 1; lsize <= lp; ++lsize) {
+  while ((1 << lch) < CH) ++lch;
+  if (P <= CH) {
+    for (int lsize = 1; lsize <= lp; ++lsize) bitonic_chunk(s, 0, P, lsize, lsize - 1);
+    return;
+  }
+  for (int base = 0; base < P; base += CH) {
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[base + i];
+    __syncthreads();
+    for (int lsize = 1; lsize <= lch; ++lsize) bitonic_chunk(s, base, CH, lsize, lsize - 1);
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) g[base + i] = s[i];
+    __syncthreads();
+  }
+  for (int lsize = lch + 1; lsize <= lp; ++lsize) {
     const int size = 1 << lsize;
-    for (int ls = lsize - 1; ls >= 0; --ls) {
+    for (int ls = lsize - 1; ls >= lch; --ls) {
       const int stride = 1 << ls;
       for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
         const int lo = ((i >> ls) << (ls + 1)) | (i & (stride - 1));
         const int hi = lo + stride;
         const bool up = (lo & size) == 0;
-        const unsigned long long x = k[lo], y = k[hi];
-        if ((x > y) == up) { k[lo] = y; k[hi] = x; }
+        const unsigned long long x = g[lo], y = g[hi];
+        if ((x > y) == up) { g[lo] = y; g[hi] = x; }
       }
+      __syncthreads();
+    }
+    for (int base = 0; base < P; base += CH) {
+      for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[base + i];
+      __syncthreads();
+      bitonic_chunk(s, base, CH, lsize, lch - 1);
+      for (int i = threadIdx.x; i < CH; i += blockDim.x) g[base + i] = s[i];
       __syncthreads();
     }
   }
@@ -136,7 +174,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
     for (int i = n + threadIdx.x; i < P; i += blockDim.x) gkeys[i] = ~0ull;   // cap is a power of two >= P
   }
   __syncthreads();
-  bitonic_sort(keys, P);
+  bitonic_sort_hybrid(gkeys, s_keys, P, kSortSmemKeys);
   if (n > a.max_nms) n = a.max_nms;
 
   const float* pred = a.pred + (size_t)img * a.R * no;
