@@ -200,7 +200,8 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         return
     imgs = args.batch * world * args.steps
     pk = peaks()
-    conv_ms = (per_op.get("spike_conv", 0.0) + per_op.get("conv_dgrad", 0.0) + per_op.get("conv_wgrad", 0.0)) / args.steps
+    conv_ms = (per_op.get("spike_conv", 0.0) + per_op.get("conv_dgrad", 0.0) + per_op.get("conv_wgrad", 0.0)
+               + per_op.get("conv_bwd", 0.0)) / args.steps
     conv_fl = (flops.get("spike_conv", 0.0) + flops.get("conv_bwd", 0.0)) / args.steps
     conv_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     line = {

@@ -64,6 +64,8 @@ SIGNATURES = {
                                _f, _i, _i, _i, _f, _f, _p]),
     "ecsy_event_frames_ws_bytes": (_z, [_l, _i, _i, _i]),
     "ecsy_event_frames": (_i, [_p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
+    "ecsy_spike_conv_bwd_ws_bytes": (_z, [_l, _i, _i, _i, _i, _i, _i, _i]),
+    "ecsy_spike_conv_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "ecsy_ddetect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _l, _l, _p]),
 }
 

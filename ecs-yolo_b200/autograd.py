@@ -75,9 +75,9 @@ def bn_train_fwd(bn_mod, y: Act):
     return scale, shift, mean, rstd
 
 
-def bn_train_bwd(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
-    """g_yn: [Tp,N,H,W,C] gradient w.r.t. the normalised output (already summed over T when y is a
-    T-broadcast tensor).  Returns g_y with the same shape."""
+def bn_train_bwd_coeffs(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
+    """Batch sums of the tdBN backward -> per-channel (A, B, C) with g_y = A*g_yn + B*y + C; accumulates the
+    gradients of the tdBN weight / bias."""
     bn = bn_mod.bn
     C = y.C
     n = float(y.T * y.N * y.H * y.W)
@@ -90,9 +90,16 @@ def bn_train_bwd(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
         Cc = (-A * sg / n - B * mean)
         B = (B * tfac).contiguous()
         Cc = (Cc * tfac).contiguous()
-        zeros = torch.zeros_like(B)
     _acc(grads, bn.weight, sgx)
     _acc(grads, bn.bias, sg)
+    return A, B, Cc
+
+
+def bn_train_bwd(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
+    """g_yn: [Tp,N,H,W,C] gradient w.r.t. the normalised output (already summed over T when y is a
+    T-broadcast tensor).  Returns g_y with the same shape."""
+    A, B, Cc = bn_train_bwd_coeffs(bn_mod, y, mean, rstd, g_yn, grads)
+    zeros = torch.zeros_like(B)
     return F_.affine_add(Act(g_yn, g_yn.shape[0]), A, Cc, Act(y.data, y.Tp), B, zeros).data
 
 
@@ -157,8 +164,18 @@ def conv_spikes_bwd(conv, sp, g_y: torch.Tensor, grads):
 
 def chain_bwd(lif, conv, bn, sv: _Saved, g_yn: torch.Tensor, grads):
     """g_yn: gradient w.r.t. the chain's normalised output -> gradient w.r.t. its (normalised) input."""
-    g_y = bn_train_bwd(bn, sv.y, sv.mean, sv.rstd, g_yn, grads)
-    g_s = conv_spikes_bwd(conv, sv.sp, g_y, grads)
+    if conv.groups == 1 and conv.out_channels % 64 == 0 and sv.sp.C == conv.in_channels and sv.y.Tp == sv.y.T:
+        # one call: the output gradient (tdBN backward folded in) is formed once as bf16 planes for wgrad and dgrad
+        from .common import _cached
+        coef = bn_train_bwd_coeffs(bn, sv.y, sv.mean, sv.rstd, g_yn, grads)
+        k, s_, p_ = conv._geom()
+        splits = F_.get_splits()
+        wT = _cached(conv, "dgradw", (conv.weight,), lambda: F_.pack_dgrad_weight(conv.weight, splits))
+        g_s, dw = F_.spike_conv_bwd(g_yn, sv.y.data, coef, sv.sp, wT, k, s_, p_, conv.in_channels)
+        _acc(grads, conv.weight, dw)
+    else:
+        g_y = bn_train_bwd(bn, sv.y, sv.mean, sv.rstd, g_yn, grads)
+        g_s = conv_spikes_bwd(conv, sv.sp, g_y, grads)
     g_x, gdw, gdb, gpw, gpb = F_.lif_ecs_bwd(g_s, sv.x, lif._weights(), lif.spread[1].weight, sv.aff, lif.ecs_tau,
                                              lif.alpha, lif.beta, saved=sv.state)
     sv.state = None

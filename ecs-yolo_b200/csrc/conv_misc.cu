@@ -419,6 +419,112 @@ extern "C" int ecsy_spike_conv_wgrad(const float* gy, const uint32_t* spikes, fl
   return ecsy_umma_spike_wgrad(hi, lo, spikes, dw, (int)imgs, H, W, Cin, Cout, k, stride, pad, STREAM(stream));
 }
 
+// Output gradient of a conv in tensor-core form, produced ONCE for both the weight- and the input-gradient pass:
+// v = A[c]*g + B[c]*y + Cv[c] (the tdBN backward folded in: g is the gradient w.r.t. the normalised output, y the raw
+// conv output; A == NULL: v = g), written as bf16 hi (+ lo) planes [imgs][Hu][Wu][C], zero-inserted when the conv was
+// strided (s > 1 or Hu != Ho).  Replaces affine_add (fp32 g_y round trip) + two separate fp32 -> bf16 passes.
+__global__ void k_gy_to_bf16(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ A,
+                             const float* __restrict__ B, const float* __restrict__ Cv, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, int64_t imgs, int Ho, int Wo, int C, int Hu, int Wu, int s) {
+  const int c4 = C >> 2;
+  const int64_t total = imgs * Hu * Wu * c4;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const bool small = total < (int64_t(1) << 32);
+  const bool plain = s == 1 && Hu == Ho && Wu == Wo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int q = static_cast<int>(ecsy::mod_u(i, (uint32_t)c4, small));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t src = i;
+    bool have = true;
+    if (!plain) {
+      int64_t p = ecsy::div_u(i, (uint32_t)c4, small);
+      const int wu = static_cast<int>(ecsy::mod_u(p, (uint32_t)Wu, small));
+      p = ecsy::div_u(p, (uint32_t)Wu, small);
+      const int hu = static_cast<int>(ecsy::mod_u(p, (uint32_t)Hu, small));
+      const int64_t img = ecsy::div_u(p, (uint32_t)Hu, small);
+      have = hu % s == 0 && wu % s == 0 && hu / s < Ho && wu / s < Wo;
+      src = ((img * Ho + hu / s) * Wo + wu / s) * (int64_t)c4 + q;
+    }
+    if (have) {
+      v = reinterpret_cast<const float4*>(g)[src];
+      if (A != nullptr) {
+        const float4 yv = reinterpret_cast<const float4*>(y)[src];
+        const float4 a = *reinterpret_cast<const float4*>(A + q * 4);
+        const float4 b = *reinterpret_cast<const float4*>(B + q * 4);
+        const float4 c = *reinterpret_cast<const float4*>(Cv + q * 4);
+        v.x = fmaf(a.x, v.x, fmaf(b.x, yv.x, c.x)); v.y = fmaf(a.y, v.y, fmaf(b.y, yv.y, c.y));
+        v.z = fmaf(a.z, v.z, fmaf(b.z, yv.z, c.z)); v.w = fmaf(a.w, v.w, fmaf(b.w, yv.w, c.w));
+      }
+    }
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (lo != nullptr) {
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      reinterpret_cast<uint2*>(lo)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+  }
+}
+
+static bool dgrad_plain(int H, int W, int k, int stride, int pad) {
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  return stride == 1 && H - k + 1 + 2 * pad == Ho && W - k + 1 + 2 * pad == Wo;
+}
+
+extern "C" size_t ecsy_spike_conv_bwd_ws_bytes(int64_t imgs, int H, int W, int Cout, int k, int stride, int pad,
+                                               int splits) {
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int Hu = H - k + 1 + 2 * pad, Wu = W - k + 1 + 2 * pad;
+  size_t b = 1024 + static_cast<size_t>(splits) * al256c(static_cast<size_t>(imgs) * Ho * Wo * Cout * 2);
+  if (!dgrad_plain(H, W, k, stride, pad)) b += static_cast<size_t>(splits) * al256c(static_cast<size_t>(imgs) * Hu * Wu * Cout * 2);
+  return b;
+}
+
+// Backward of Snn_Conv2d on spikes followed by tdBN (training), one call: the output gradient is formed once as bf16
+// planes (tdBN backward folded in, see k_gy_to_bf16) and feeds both the weight gradient (accumulated into dw
+// [Cout][k*k*Cin]) and the input gradient gx [imgs][H][W][Cin].
+extern "C" int ecsy_spike_conv_bwd(const float* g, const float* y, const float* A, const float* B, const float* Cv,
+                                   const uint32_t* spikes, const void* wT_packed, int splits, float* gx, float* dw,
+                                   int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  ECSY_CHECK_ARG(g && spikes && wT_packed && gx && dw && imgs > 0, "spike_conv_bwd: bad arguments");
+  ECSY_CHECK_ARG((A == nullptr) == (B == nullptr) && (A == nullptr) == (Cv == nullptr) && (A == nullptr || y != nullptr),
+                 "spike_conv_bwd: the tdBN-backward coefficients A, B, C and y come together");
+  ECSY_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0, "spike_conv_bwd: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+  ECSY_CHECK_ARG(splits == 1 || splits == 2, "spike_conv_bwd: splits");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int Hu = H - k + 1 + 2 * pad, Wu = W - k + 1 + 2 * pad;
+  ECSY_CHECK_ARG(Ho > 0 && Wo > 0 && Hu >= (Ho - 1) * stride + 1 && Wu >= (Wo - 1) * stride + 1, "spike_conv_bwd: geometry");
+  const size_t need = ecsy_spike_conv_bwd_ws_bytes(imgs, H, W, Cout, k, stride, pad, splits);
+  if (ws == nullptr || ws_bytes < need) {
+    ecsy_set_error("spike_conv_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  cudaStream_t st = STREAM(stream);
+  const size_t n = static_cast<size_t>(imgs) * Ho * Wo * Cout;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base); base += al256c(n * 2);
+  __nv_bfloat16* lo = nullptr;
+  if (splits == 2) { lo = reinterpret_cast<__nv_bfloat16*>(base); base += al256c(n * 2); }
+  k_gy_to_bf16<<<grid_for((int64_t)n / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(g, y, A, B, Cv, hi, lo, imgs, Ho,
+                                                                                         Wo, Cout, Ho, Wo, 1);
+  ECSY_LAUNCH_CHECK();
+  int rc = ecsy_umma_spike_wgrad(hi, lo, spikes, dw, (int)imgs, H, W, Cin, Cout, k, stride, pad, st);
+  if (rc) return rc;
+  __nv_bfloat16 *dhi = hi, *dlo = lo;
+  if (!dgrad_plain(H, W, k, stride, pad)) {
+    const size_t nu = static_cast<size_t>(imgs) * Hu * Wu * Cout;
+    dhi = reinterpret_cast<__nv_bfloat16*>(base); base += al256c(nu * 2);
+    dlo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(base) : nullptr;
+    k_gy_to_bf16<<<grid_for((int64_t)nu / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(g, y, A, B, Cv, dhi, dlo, imgs,
+                                                                                            Ho, Wo, Cout, Hu, Wu, stride);
+    ECSY_LAUNCH_CHECK();
+  }
+  return ecsy_umma_conv_bf16(dhi, dlo, wT_packed, splits, gx, nullptr, nullptr, nullptr, 0, (int)imgs, Hu, Wu, Cout, Cin, k,
+                             k - 1 - pad, st);
+}
+
 extern "C" size_t ecsy_real_conv_wgrad_ws_bytes(int64_t imgs, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                                                 int splits) {
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;

@@ -481,6 +481,29 @@ def spike_conv_wgrad(gy: torch.Tensor, s: Spikes, k: int, stride: int, pad: int)
     return dw.reshape(Co, k, k, Ci).permute(0, 3, 1, 2).contiguous()
 
 
+def spike_conv_bwd(g: torch.Tensor, y: Optional[torch.Tensor], coef, s: Spikes, wT_packed: torch.Tensor, k: int, stride: int,
+                   pad: int, Cin: int):
+    """Backward of Snn_Conv2d (+ tdBN) on spikes in one call.  g: [T,N,Ho,Wo,Co] gradient w.r.t. the normalised
+    output with coef = (A, B, C) per-channel vectors and y the raw conv output (g_y = A*g + B*y + C), or the plain
+    output gradient with coef = None.  -> (g_s [T,N,H,W,Cin], dW [Co, Cin, k, k])."""
+    T, N, Ho, Wo, Co = g.shape
+    g = g.contiguous()
+    H, W = s.H, s.W
+    dev = g.device
+    splits = get_splits()
+    gx = torch.empty(T, N, H, W, Cin, device=dev, dtype=torch.float32)
+    dw = torch.zeros(Co, k * k * Cin, device=dev, dtype=torch.float32)
+    L = _cabi.lib()
+    ws = torch.empty(L.ecsy_spike_conv_bwd_ws_bytes(T * N, H, W, Co, k, stride, pad, splits), device=dev, dtype=torch.uint8)
+    A, B, Cv = coef if coef is not None else (None, None, None)
+    # same accounting as conv_dgrad + spike_conv_wgrad (the dgrad of a strided conv runs over the zero-inserted gradient)
+    flops["conv_bwd"] = flops.get("conv_bwd", 0.0) + 2.0 * T * N * (H * W + Ho * Wo) * Cin * Co * k * k
+    with _timed("conv_bwd", 3 if stride == 1 else 4):
+        _cabi.check(L.ecsy_spike_conv_bwd(_p(g), _p(y), _p(A), _p(B), _p(Cv), _p(s.bits), _p(wT_packed), splits, _p(gx), _p(dw),
+                                          T * N, H, W, Cin, Co, k, stride, pad, _p(ws), ws.numel(), _st()), "spike_conv_bwd")
+    return gx, dw.reshape(Co, k, k, Cin).permute(0, 3, 1, 2).contiguous()
+
+
 def real_conv_wgrad(gy: torch.Tensor, x: Act, k: int, stride: int, pad: int) -> torch.Tensor:
     """gy: [Tp,N,Ho,Wo,Co] fp32 (already summed over T for a T-broadcast input), x: the conv's real input."""
     Tp, N, Ho, Wo, Co = gy.shape

@@ -158,6 +158,16 @@ int ecsy_detect_decode(const float* y, float* raw, float* z, const float* anchor
 int ecsy_ddetect_decode(const float* box, const float* cls, float* xs, float* y, float stride_px, int N, int H, int W,
                         int nc, int64_t a_total, int64_t a_off, void* stream);
 
+/* ---- backward of `Snn_Conv2d -> batch_norm_2d` on spikes in training, one call (autograd of F.conv2d,
+ * models/common.py:623, and of nn.BatchNorm3d, :674-679).  g: gradient w.r.t. the NORMALISED output [imgs][Ho][Wo][Cout],
+ * y: the raw conv output, A / B / Cv [Cout]: g_y = A*g + B*y + Cv (the tdBN backward given the batch sums from
+ * ecsy_colsum2; all NULL: g is already g_y).  g_y is formed once as bf16 planes and feeds the weight gradient (dw
+ * [Cout][k*k*Cin], ACCUMULATED) and the input gradient (gx [imgs][H][W][Cin]); wT_packed as for ecsy_conv_dgrad. */
+size_t ecsy_spike_conv_bwd_ws_bytes(int64_t imgs, int H, int W, int Cout, int k, int stride, int pad, int splits);
+int ecsy_spike_conv_bwd(const float* g, const float* y, const float* A, const float* B, const float* Cv,
+                        const uint32_t* spikes, const void* wT_packed, int splits, float* gx, float* dw, int64_t imgs, int H,
+                        int W, int Cin, int Cout, int k, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- non_max_suppression (utils/general.py:649-741) on the decoded Detect output, all images in one call.
  * pred: [N][R][5+nc] rows (cx, cy, w, h, obj, cls...).  Candidates: obj > conf_thres, conf = obj*cls > conf_thres for
  * the best class, or for every class with multi_label; cls_ok (optional [nc] bytes) is the `classes` filter; at most
