@@ -145,7 +145,7 @@ __global__ void k_lif_bwd_reduce_final(const float* __restrict__ part, int nbloc
 // gs = gout + alpha*dw^T(G1); gm = gs*sigma'(m_t) + gm_next*decay*(1-s_t); writes gm carry and gx[t].
 __global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*null at t=T-1*/,
                                const float* __restrict__ dw_w, const float* __restrict__ mem_t,
-                               const uint32_t* __restrict__ bits_t, float* __restrict__ gm /*in: next, out: t*/,
+                               const uint32_t* __restrict__ bits_t, const float* __restrict__ gm /*dL/dm_{t+1} = gx[t+1]*/,
                                int has_next, float* __restrict__ gx, int N, int H, int W, int C, float thresh,
                                float lens, float decay, float alpha) {
   const int c4 = C >> 2;
@@ -192,8 +192,7 @@ __global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __re
       o.z += (nib & 4u) ? 0.f : gn.z * decay;
       o.w += (nib & 8u) ? 0.f : gn.w * decay;
     }
-    reinterpret_cast<float4*>(gm)[i] = o;
-    reinterpret_cast<float4*>(gx)[i] = o;
+    reinterpret_cast<float4*>(gx)[i] = o;   // gx[t] IS the carry dL/dm_t of the next (earlier) step: no separate copy
   }
 }
 
@@ -378,7 +377,7 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
     return ECSY_ERR_WS;
   }
   uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
-  float* gm = reinterpret_cast<float*>(p); p += al256(mc * 4);
+  p += al256(mc * 4);   // (the membrane-gradient carry lived here; gx[t+1] is the carry now -- layout kept for the SiLU path)
   float* ge = reinterpret_cast<float*>(p); p += al256(mc * 4);
   float* g1 = reinterpret_cast<float*>(p); p += al256(mc * 4);
   __nv_bfloat16* ge_hi = reinterpret_cast<__nv_bfloat16*>(p); p += al256(mc * 2);
@@ -398,8 +397,8 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
     const bool spread = t <= T - 2;
     const bool has_next = t < T - 1;
     if (spread) {
-      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gm, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta,
-                                                kappa);
+      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi,
+                                                ge_lo, n4, beta, kappa);
       ECSY_LAUNCH_CHECK();
       int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
       if (rc) return rc;
@@ -415,8 +414,9 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       ECSY_LAUNCH_CHECK();
     }
     k_lif_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
-                                               spikes + t * words, gm, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H,
-                                               W, C, thresh, lens, decay, alpha);
+                                               spikes + t * words, has_next ? gx + (size_t)(t + 1) * mc : nullptr,
+                                               has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, thresh, lens, decay,
+                                               alpha);
     ECSY_LAUNCH_CHECK();
   }
   return ECSY_OK;
@@ -487,8 +487,8 @@ extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const floa
     const bool has_next = t < T - 1;
     const float* o_t = out + (size_t)t * mc;
     if (spread) {
-      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gm, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta,
-                                                kappa);
+      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi,
+                                                ge_lo, n4, beta, kappa);
       ECSY_LAUNCH_CHECK();
       int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
       if (rc) return rc;
