@@ -130,8 +130,10 @@ def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, event
 
 
 def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload):
-    """fwd + loss + bwd + SGD-nesterov step per batch (train.py:555-582 shape of a step; the loss here is a
-    synthetic quadratic on the raw head outputs -- the YOLO loss/assigner is outside the hot path)."""
+    """fwd + loss + bwd + SGD-nesterov step per batch (train.py:555-582 shape of a step).  Stack-A models (Detect head)
+    train against the reference's ComputeLoss (utils/loss.py:130-234: SIoU + BCE, build_targets) on COCO-shaped synthetic
+    targets, computed on the device by ecsy_yolo_loss; the DDetect models (Stack B, whose TAL loss is
+    not built) and `--loss quadratic` use a synthetic quadratic on the raw head outputs, and the JSON line says which."""
     model.train()
     net = model
     if dist is not None:
@@ -145,12 +147,38 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
     with torch.no_grad():
         probe = model(x[:, :1] if args.events else x[:1])
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
-    tgt = [torch.randn(args.batch, *o.shape[1:], device="cuda", generator=g) for o in probe]
+    det = model.model[-1]
+    use_yolo_loss = args.loss == "yolo" and type(det).__name__ == "Detect"
+    if use_yolo_loss:
+        # hyp.scratch.yaml gains with train.py:427-433's scaling to nl levels / nc classes / the image size
+        nl, nc = det.nl, det.nc
+        model.hyp = dict(box=0.05 * 3 / nl, cls=0.5 * nc / 80 * 3 / nl, obj=1.0 * (args.img / 640) ** 2 * 3 / nl,
+                         cls_pw=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)
+        compute_loss = E.loss.ComputeLoss(model)
+        # COCO-shaped labels: 5-8 boxes per image, class ~ U{0..nc-1}, centre ~ U(.2,.8), size ~ U(.05,.35)
+        gc = torch.Generator().manual_seed(1 + rank)
+        per = torch.randint(5, 9, (args.batch,), generator=gc)
+        img = torch.repeat_interleave(torch.arange(args.batch), per).float()
+        n_t = int(img.numel())
+        tgt_host = torch.cat([img[:, None], torch.randint(0, nc, (n_t, 1), generator=gc).float(),
+                              torch.rand(n_t, 2, generator=gc) * 0.6 + 0.2,
+                              torch.rand(n_t, 2, generator=gc) * 0.3 + 0.05], 1).pin_memory()
+        tgt = tgt_host.cuda()
+        loss_name = (f"ComputeLoss (utils/loss.py:130-234: SIoU box + BCE obj / cls, build_targets) on the device "
+                     f"(ecsy_yolo_loss), {n_t} synthetic COCO-shaped boxes per batch")
+    else:
+        tgt = [torch.randn(args.batch, *o.shape[1:], device="cuda", generator=g) for o in probe]
+        tgt_host = None
+        loss_name = "synthetic quadratic on the raw head outputs" + (
+            "" if type(det).__name__ == "Detect" else " (the DDetect models' TAL loss is not built)")
 
-    def step(inp):
+    def step(inp, targets=None):
         opt.zero_grad(set_to_none=True)
         out = net(inp)
-        loss = sum(((o - t) ** 2).mean() for o, t in zip(out, tgt))
+        if use_yolo_loss:
+            loss, _items = compute_loss(out, tgt if targets is None else targets)
+        else:
+            loss = sum(((o - t) ** 2).mean() for o, t in zip(out, tgt))
         loss.backward()
         opt.step()
         return loss
@@ -187,7 +215,8 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
     loss_host = 0.0
     for _ in range(0 if args.no_e2e else args.steps):
         xd = x_host.to("cuda", non_blocking=True)
-        loss_host = float(step(xd).detach().cpu())
+        td = tgt_host.to("cuda", non_blocking=True) if tgt_host is not None else None
+        loss_host = float(step(xd, td).detach().cpu())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
@@ -213,10 +242,11 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
                    "precision": args.precision, "accumulate": "fp32",
                    "parallelism": f"DDP x{world} (NCCL all-reduce of fp32 gradients, 64 MB buckets)" if world > 1
                                   else "single GPU",
-                   "loss": "synthetic quadratic on the raw head outputs (YOLO loss is outside the hot path)",
+                   "loss": loss_name,
                    "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": (imgs / (e2e_ms * 1e-3)) if e2e_ms > 0 else None, "unit": "images/s",
-                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": x_host.numel() * 4 + (tgt_host.numel() * 4 if tgt_host is not None else 0),
+                "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clk.summary(),
         "roofline": {"kernel": "tcgen05 conv kernels (spike conv fwd + dgrad + wgrad)", "bound": "tensor",
                      "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": conv_tf / pk["tf_sust"],
@@ -272,6 +302,8 @@ def main():
                          "(use with --T 5)")
     ap.add_argument("--optim", default="fused", choices=["fused", "torch"],
                     help="training: fused SGD-Nesterov + EMA kernel (default) or torch.optim.SGD without EMA")
+    ap.add_argument("--loss", default="yolo", choices=["yolo", "quadratic"],
+                    help="training: the reference's ComputeLoss on the device (Detect models) or a synthetic quadratic")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()

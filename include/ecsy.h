@@ -244,6 +244,22 @@ int ecsy_colsum2(const float* g, const float* x, int64_t rows, int64_t x_rows, i
 int ecsy_xty_bf16(const void* p_hi, const void* p_lo, const void* q_hi, const void* q_lo, int64_t rows, int Ca, int Cb,
                   float alpha, float* out, void* stream);
 
+/* ---- Stack-A training loss, forward + gradient in one call: replaces ComputeLoss.__call__ and
+ * build_targets (utils/loss.py:162-290; SIoU box term utils/metrics.py:227-307; BCEWithLogits with pos_weight for the
+ * objectness / class terms, label smoothing cp / cn, per-level balance) on the path data/hyps/hyp.scratch.yaml selects
+ * (fl_gamma = 0, slide_ratio = 0).  p / gp: HOST arrays of nl DEVICE pointers to the raw Detect outputs
+ * [N][na][ny_l][nx_l][5 + nc] and their gradients (gp or gp[l] may be null: forward only; otherwise gp[l] is
+ * OVERWRITTEN with d loss / d p[l] for an upstream gradient of 1).  targets: device [nt][6] = (image, class, cx, cy,
+ * w, h) normalised; anchors: device [nl][na][2] in grid units (Detect.anchors, models/yolo.py:230); ny / nx / balance:
+ * host arrays [nl].  out: device [4 + nl] = loss (already times the batch size, :231), lbox, lobj, lcls (the
+ * reference's loss_items), then the objectness BCE mean of every level (what autobalance reads, :224).
+ * Duplicate (image, anchor, cell) matches resolve to the last one in the reference's row order (:205). */
+size_t ecsy_yolo_loss_ws_bytes(int nl, int64_t N, int na, int64_t nt, const int* ny, const int* nx);
+int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets, int64_t nt, const float* anchors,
+                   int nl, int64_t N, int na, int nc, const int* ny, const int* nx, const float* balance, float box,
+                   float obj, float cls, float cls_pw, float obj_pw, float cp, float cn, float anchor_t, float gr,
+                   float* out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

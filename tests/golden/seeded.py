@@ -355,3 +355,53 @@ def zpack(t: torch.Tensor) -> dict:
 def zunpack(d: dict) -> torch.Tensor:
     import zlib
     return torch.frombuffer(bytearray(zlib.decompress(d["z"])), dtype=torch.uint8).reshape(*d["shape"]).clone()
+
+
+# ---------------------------------------------------------------------------------------------
+# Stack-A training loss (utils/loss.py ComputeLoss, SIoU box term)
+# ---------------------------------------------------------------------------------------------
+_ANCH2 = [[[1.25, 1.625], [2.0, 3.75], [4.125, 2.875]], [[1.875, 3.8125], [3.875, 2.8125], [3.6875, 7.4375]]]
+_ANCH3 = _ANCH2 + [[[3.625, 2.8125], [4.875, 6.1875], [11.65625, 10.1875]]]
+_HYP = dict(box=0.05, obj=1.0, cls=0.5, cls_pw=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0,
+            label_smoothing=0.0)
+LOSS_CASES = {
+    "loss_basic": dict(N=4, nc=13, grids=[(12, 16), (6, 8)], anchors=_ANCH2, nt=24, seed=801, hyp=_HYP),
+    "loss_empty": dict(N=2, nc=13, grids=[(8, 8), (4, 4)], anchors=_ANCH2, nt=0, seed=802, hyp=_HYP),
+    "loss_dups": dict(N=2, nc=4, grids=[(8, 8), (4, 4)], anchors=_ANCH2, nt=40, seed=803, hyp=_HYP, cluster=True),
+    "loss_nc1": dict(N=3, nc=1, grids=[(10, 10), (5, 5)], anchors=_ANCH2, nt=15, seed=804, hyp=_HYP),
+    "loss_nl3_smooth": dict(N=2, nc=6, grids=[(16, 16), (8, 8), (4, 4)], anchors=_ANCH3, nt=30, seed=805,
+                            hyp=dict(_HYP, box=0.0375, obj=0.7, cls=0.3, cls_pw=1.5, obj_pw=0.8, anchor_t=3.0,
+                                     label_smoothing=0.1)),
+    "loss_border": dict(N=2, nc=3, grids=[(8, 12), (4, 6)], anchors=_ANCH2, nt=32, seed=806, hyp=_HYP, border=True),
+    "loss_unmatched": dict(N=2, nc=3, grids=[(8, 8), (4, 4)], anchors=_ANCH2, nt=6, seed=807, hyp=_HYP, tiny_boxes=True),
+}
+
+
+def loss_inputs(spec):
+    """Raw Detect training outputs p[i] [N, na, ny, nx, 5 + nc] (models/yolo.py:141-145 layout), anchors in grid units
+    (models/yolo.py:230) and targets [nt, 6] = (image, class, cx, cy, w, h) normalised (utils/datasets.py:615-630)."""
+    g = gen(spec["seed"])
+    N, nc = spec["N"], spec["nc"]
+    anchors = torch.tensor(spec["anchors"], dtype=torch.float32)
+    na = anchors.shape[1]
+    p = [randn(g, N, na, ny, nx, 5 + nc, scale=1.5) for ny, nx in spec["grids"]]
+    nt = spec["nt"]
+    img = torch.randint(0, N, (nt,), generator=g).float()
+    cls = torch.randint(0, nc, (nt,), generator=g).float()
+    if spec.get("cluster"):          # a few centres shared by many boxes: duplicate (image, anchor, cell) indices
+        centres = torch.rand(4, 2, generator=g) * 0.6 + 0.2
+        cxy = centres[torch.randint(0, 4, (nt,), generator=g)] + (torch.rand(nt, 2, generator=g) - 0.5) * 0.02
+        img = (img % 2)
+    elif spec.get("border"):         # centres in the outermost cells and just beyond the half-cell offsets
+        cxy = torch.rand(nt, 2, generator=g)
+        edge = torch.rand(nt, 2, generator=g)
+        cxy = torch.where(edge < 0.35, cxy * 0.06, torch.where(edge > 0.65, 1.0 - cxy * 0.06, cxy))
+    else:
+        cxy = torch.rand(nt, 2, generator=g) * 0.9 + 0.05
+    if spec.get("tiny_boxes"):       # no anchor within anchor_t: every level ends up without a match
+        wh = torch.rand(nt, 2, generator=g) * 0.004 + 0.001
+    else:
+        wh = torch.exp(torch.rand(nt, 2, generator=g) * 3.2 - 3.6)          # 0.027 .. 0.67, log-uniform
+    targets = torch.cat([img[:, None], cls[:, None], cxy, wh], 1).reshape(nt, 6)
+    gout = float(torch.rand(1, generator=g)) + 0.5                          # upstream gradient of the scalar loss
+    return dict(p=p, anchors=anchors, targets=targets, gout=gout)

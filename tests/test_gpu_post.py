@@ -191,3 +191,83 @@ def test_event_frames_feed_the_model_and_flag_bad_events():
     empty = torch.zeros(0, dtype=torch.int32).cuda()
     grey = E.events.event_frames(empty, empty, empty, empty, 1, 2, (32, 32))
     assert torch.equal(grey.cpu(), torch.full((2, 1, 3, 32, 32), 127.0) / 255)
+
+
+# ---- Stack-A training loss ------------------------------------------------------------------
+class _LossHolder(torch.nn.Module):
+    """What ComputeLoss.__init__ reads off a model (utils/loss.py:131-160)."""
+
+    def __init__(self, anchors, nc, hyp):
+        super().__init__()
+        import types
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.hyp = dict(hyp)
+        nl = anchors.shape[0]
+        self.model = [types.SimpleNamespace(na=anchors.shape[1], nc=nc, nl=nl, anchors=anchors.cuda(),
+                                            stride=torch.tensor([16.0, 32.0, 64.0][:nl]))]
+
+
+@pytest.mark.parametrize("name", list(S.LOSS_CASES))
+def test_compute_loss_golden(name):
+    """ecs.loss.ComputeLoss (ecsy_yolo_loss through autograd) against utils.loss.ComputeLoss of the unmodified
+    reference: loss and loss_items within 1e-5 relative, gradients w.r.t. the raw head outputs within 1e-4 relative
+    (fp32 transcendental differences; cells hit by several matches accumulate with float atomics)."""
+    E = ecsy()
+    gold = _load("post_loss")[name]
+    spec = S.LOSS_CASES[name]
+    inp = S.loss_inputs(spec)
+    crit = E.loss.ComputeLoss(_LossHolder(inp["anchors"], spec["nc"], spec["hyp"]))
+    p = [x.cuda().requires_grad_(True) for x in inp["p"]]
+    loss, items = crit(p, inp["targets"].cuda())
+    assert loss.shape == (1,) and items.shape == (3,) and not items.requires_grad
+    assert torch.allclose(loss.detach().cpu(), gold["loss"], rtol=1e-5, atol=1e-6), (float(loss), float(gold["loss"]))
+    assert torch.allclose(items.cpu(), gold["items"], rtol=1e-5, atol=1e-6)
+    (loss * inp["gout"]).sum().backward()
+    for x, g in zip(p, gold["grads"]):
+        err = (x.grad.cpu() - g).abs().max() / g.abs().max().clamp_min(1e-12)
+        assert float(err) < 1e-4, (name, float(err))
+        assert torch.allclose(x.grad.cpu(), g, rtol=1e-3, atol=1e-7 * float(g.abs().max()) + 1e-10)
+
+
+def test_compute_loss_full_size_vs_oracle():
+    """BASELINE training shape (batch 32, 40x40 + 20x20 levels, nc = 13, ~6.5 boxes per image): against the CPU oracle,
+    bit-reproducible loss across runs, forward-only call, an empty target list, and an out-of-range image index."""
+    import loss_oracle as LO
+    E = ecsy()
+    spec = dict(N=32, nc=13, grids=[(40, 40), (20, 20)], anchors=S._ANCH2, nt=208, seed=811, hyp=S._HYP)
+    inp = S.loss_inputs(spec)
+    hyp = dict(S._HYP, box=0.05 * 3 / 2, cls=0.5 * 13 / 80 * 3 / 2, obj=1.0 * 3 / 2)     # train.py:427-433 scaling, nl = 2
+    p_ref = [x.clone().requires_grad_(True) for x in inp["p"]]
+    want, items, counts, objs = LO.compute_loss(p_ref, inp["targets"], inp["anchors"], hyp)
+    want.sum().backward()
+    assert min(counts) > 0
+    kw = dict(balance=LO.BALANCE_DEFAULT, box=hyp["box"], obj=hyp["obj"], cls=hyp["cls"], anchor_t=hyp["anchor_t"])
+    pc = [x.cuda() for x in inp["p"]]
+    out, grads = E.loss.yolo_loss(pc, inp["targets"].cuda(), inp["anchors"].cuda(), **kw)
+    o = out.cpu()
+    assert torch.allclose(o[0:1], want.detach(), rtol=1e-5)
+    assert torch.allclose(o[1:4], items, rtol=1e-5)
+    assert torch.allclose(o[4:6], torch.tensor(objs), rtol=1e-5)
+    for g, x in zip(grads, p_ref):
+        err = (g.cpu() - x.grad).abs().max() / x.grad.abs().max()
+        assert float(err) < 1e-4, float(err)
+    out2, none = E.loss.yolo_loss(pc, inp["targets"].cuda(), inp["anchors"].cuda(), need_grad=False, **kw)
+    assert none == [] and torch.equal(out2, out)                        # fixed-order reductions: same bits
+    # no targets: objectness against an all-zero target only
+    out0, g0 = E.loss.yolo_loss(pc, torch.zeros(0, 6).cuda(), inp["anchors"].cuda(), **kw)
+    w0, it0, c0, _ = LO.compute_loss(inp["p"], torch.zeros(0, 6), inp["anchors"], hyp)
+    assert c0 == [0, 0] and torch.allclose(out0[0:1].cpu(), w0, rtol=1e-5) and float(out0[1]) == 0.0 == float(out0[3])
+    assert float(g0[0][..., :4].abs().max()) == 0.0 and float(g0[0][..., 5:].abs().max()) == 0.0
+    # a target whose image index is outside the batch is ignored instead of read out of bounds
+    bad = torch.cat([inp["targets"], torch.tensor([[99.0, 1.0, 0.5, 0.5, 0.2, 0.2]])]).cuda()
+    out3, _ = E.loss.yolo_loss(pc, bad, inp["anchors"].cuda(), need_grad=False, **kw)
+    assert torch.allclose(out3, out, rtol=1e-6)
+
+
+def test_compute_loss_rejects_unsupported_variants():
+    E = ecsy()
+    with pytest.raises(NotImplementedError):
+        E.loss.ComputeLoss(_LossHolder(torch.tensor(S._ANCH2), 3, dict(S._HYP, fl_gamma=1.5)))
+    with pytest.raises(ValueError):
+        E.loss.yolo_loss([torch.zeros(1, 3, 4, 4, 8).cuda()], torch.zeros(2, 5).cuda(), torch.ones(1, 3, 2).cuda(),
+                         balance=[4.0], box=0.05, obj=1.0, cls=0.5)

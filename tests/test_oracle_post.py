@@ -68,3 +68,22 @@ def test_event_frames_oracle(name):
     x = P.event_frames(samples[:1], spec["T"], spec["out"])
     assert x.shape == (spec["T"], 1, 3, spec["out"], spec["out"])
     assert torch.equal(x[:, 0, 1], want[0].float() / 255)
+
+
+@pytest.mark.parametrize("name", list(S.LOSS_CASES))
+def test_compute_loss_oracle(name):
+    """oracle/loss_oracle.py against utils.loss.ComputeLoss of the unmodified reference: loss, loss_items, match counts and
+    the gradient w.r.t. every level's raw head output."""
+    import loss_oracle as LO
+    gold = _load("post_loss")[name]
+    spec = S.LOSS_CASES[name]
+    inp = S.loss_inputs(spec)
+    assert abs(S.checksum(*inp["p"], inp["targets"]) - gold["chk"]) <= 1e-6 * abs(gold["chk"])
+    p = [x.clone().requires_grad_(True) for x in inp["p"]]
+    loss, items, counts, _ = LO.compute_loss(p, inp["targets"], inp["anchors"], spec["hyp"])
+    assert counts == gold["n"]
+    assert torch.allclose(loss, gold["loss"], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(items, gold["items"], rtol=1e-6, atol=1e-7)
+    (loss * inp["gout"]).sum().backward()
+    for x, g in zip(p, gold["grads"]):
+        assert torch.allclose(x.grad, g, rtol=1e-5, atol=1e-9)
