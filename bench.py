@@ -131,9 +131,10 @@ def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, event
 
 def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload):
     """fwd + loss + bwd + SGD-nesterov step per batch (train.py:555-582 shape of a step).  Stack-A models (Detect head)
-    train against the reference's ComputeLoss (utils/loss.py:130-234: SIoU + BCE, build_targets) on COCO-shaped synthetic
-    targets, computed on the device by ecsy_yolo_loss; the DDetect models (Stack B, whose TAL loss is
-    not built) and `--loss quadratic` use a synthetic quadratic on the raw head outputs, and the JSON line says which."""
+    train against the reference's ComputeLoss (utils/loss.py:130-234: SIoU + BCE, build_targets), DDetect models (Stack B)
+    against utils/loss_tal.py:105-215 (TaskAlignedAssigner + box + DFL + BCE), both on COCO-shaped synthetic targets and
+    computed on the device (ecsy_yolo_loss / ecsy_tal_loss); `--loss quadratic` is a synthetic quadratic
+    on the raw head outputs.  The JSON line says which."""
     model.train()
     net = model
     if dist is not None:
@@ -148,13 +149,14 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         probe = model(x[:, :1] if args.events else x[:1])
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     det = model.model[-1]
-    use_yolo_loss = args.loss == "yolo" and type(det).__name__ == "Detect"
+    use_yolo_loss = args.loss == "yolo" and type(det).__name__ in ("Detect", "DDetect")
     if use_yolo_loss:
         # hyp.scratch.yaml gains with train.py:427-433's scaling to nl levels / nc classes / the image size
         nl, nc = det.nl, det.nc
         model.hyp = dict(box=0.05 * 3 / nl, cls=0.5 * nc / 80 * 3 / nl, obj=1.0 * (args.img / 640) ** 2 * 3 / nl,
                          cls_pw=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)
-        compute_loss = E.loss.ComputeLoss(model)
+        stack_a = type(det).__name__ == "Detect"
+        compute_loss = E.loss.ComputeLoss(model) if stack_a else E.loss_tal.ComputeLoss(model)
         # COCO-shaped labels: 5-8 boxes per image, class ~ U{0..nc-1}, centre ~ U(.2,.8), size ~ U(.05,.35)
         gc = torch.Generator().manual_seed(1 + rank)
         per = torch.randint(5, 9, (args.batch,), generator=gc)
@@ -164,13 +166,14 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
                               torch.rand(n_t, 2, generator=gc) * 0.6 + 0.2,
                               torch.rand(n_t, 2, generator=gc) * 0.3 + 0.05], 1).pin_memory()
         tgt = tgt_host.cuda()
-        loss_name = (f"ComputeLoss (utils/loss.py:130-234: SIoU box + BCE obj / cls, build_targets) on the device "
-                     f"(ecsy_yolo_loss), {n_t} synthetic COCO-shaped boxes per batch")
+        loss_name = ((f"ComputeLoss (utils/loss.py:130-234: SIoU box + BCE obj / cls, build_targets) on the device "
+                      f"(ecsy_yolo_loss)") if stack_a else
+                     (f"ComputeLoss (utils/loss_tal.py:105-215: TaskAlignedAssigner + box + DFL + BCE) on the device "
+                      f"(ecsy_tal_loss)")) + f", {n_t} synthetic COCO-shaped boxes per batch"
     else:
         tgt = [torch.randn(args.batch, *o.shape[1:], device="cuda", generator=g) for o in probe]
         tgt_host = None
-        loss_name = "synthetic quadratic on the raw head outputs" + (
-            "" if type(det).__name__ == "Detect" else " (the DDetect models' TAL loss is not built)")
+        loss_name = "synthetic quadratic on the raw head outputs"
 
     def step(inp, targets=None):
         opt.zero_grad(set_to_none=True)

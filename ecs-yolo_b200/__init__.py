@@ -5,16 +5,16 @@
 
 The package directory carries the repo's hyphenated name, so it is imported through importlib (or the
 ``ecs_yolo_b200`` alias module at the repo root).  Sub-modules: ``common`` (drop-in layers), ``yolo``
-(Stack A model / Detect), ``general`` (batched NMS), ``loss`` (Stack-A ComputeLoss), ``functional`` (tensor-level ops over the C ABI), ``_cabi`` (ctypes binding).
+(Stack A model / Detect), ``general`` (batched NMS), ``loss`` / ``loss_tal`` (ComputeLoss of Stack A / Stack B), ``functional`` (tensor-level ops over the C ABI), ``_cabi`` (ctypes binding).
 """
 import os as _os
 
-from . import _cabi, functional, common, autograd, yolo, yolo_snn, dist, general, optim, events, loss  # noqa: F401
+from . import _cabi, functional, common, autograd, yolo, yolo_snn, dist, general, optim, events, loss, loss_tal  # noqa: F401
 from .functional import set_precision  # noqa: F401
 from .convert import convert  # noqa: F401
 from . import ops  # noqa: F401  (registers torch.ops.ecsy.*)
 
-__all__ = ["common", "yolo", "yolo_snn", "functional", "general", "optim", "events", "loss", "ops", "set_precision", "convert", "cfg_path", "build_library"]
+__all__ = ["common", "yolo", "yolo_snn", "functional", "general", "optim", "events", "loss", "loss_tal", "ops", "set_precision", "convert", "cfg_path", "build_library"]
 
 
 def cfg_path(name: str) -> str:

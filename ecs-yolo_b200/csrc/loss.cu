@@ -16,13 +16,14 @@
 // k_loss_obj per level (objectness BCE over every cell, its gradient) -> k_loss_final.  Reductions run in double in a
 // fixed order (bit-reproducible loss); only gradients of cells hit by several candidates are accumulated with float
 // atomics.  All streaming is a few MB: the point of the kernel is removing the host round trips, not bandwidth.
-#include "ecsy_common.cuh"
+#include "loss_common.cuh"
 #include "../../include/ecsy.h"
 
 namespace {
 
+using namespace ecsy_loss;
+
 constexpr int kMaxLevels = 5;      // P3-P7, the length of the reference's balance list (utils/loss.py:156)
-constexpr int kThreads = 256;
 constexpr float kEps = 1e-7f;      // utils/metrics.py:228
 
 struct LossArgs {
@@ -46,62 +47,6 @@ struct LossArgs {
   double* lvl;       // [nl][2]  n, sum(1 - iou)
   float* out;        // [4 + nl]  loss, lbox, lobj, lcls, objectness BCE mean per level
 };
-
-// ---- forward-mode dual numbers over the four box coordinates: value + d/d(px, py, pw, ph) -------------------
-struct D4 {
-  float v, d[4];
-};
-__device__ __forceinline__ D4 cst(float c) { return D4{c, {0.f, 0.f, 0.f, 0.f}}; }
-__device__ __forceinline__ D4 var(float c, int i) {
-  D4 r = cst(c);
-  r.d[i] = 1.f;
-  return r;
-}
-__device__ __forceinline__ D4 operator+(D4 a, D4 b) {
-  return D4{a.v + b.v, {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2], a.d[3] + b.d[3]}};
-}
-__device__ __forceinline__ D4 operator-(D4 a, D4 b) {
-  return D4{a.v - b.v, {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2], a.d[3] - b.d[3]}};
-}
-__device__ __forceinline__ D4 operator+(D4 a, float c) { a.v += c; return a; }
-__device__ __forceinline__ D4 operator-(D4 a, float c) { a.v -= c; return a; }
-__device__ __forceinline__ D4 rsub(float c, D4 a) { return D4{c - a.v, {-a.d[0], -a.d[1], -a.d[2], -a.d[3]}}; }
-__device__ __forceinline__ D4 scale(D4 a, float c, float dc) {   // value c * a.v given, derivative factor dc
-  return D4{c, {a.d[0] * dc, a.d[1] * dc, a.d[2] * dc, a.d[3] * dc}};
-}
-__device__ __forceinline__ D4 operator*(D4 a, float c) { return scale(a, a.v * c, c); }
-__device__ __forceinline__ D4 operator*(D4 a, D4 b) {
-  return D4{a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2],
-                        a.d[3] * b.v + a.v * b.d[3]}};
-}
-__device__ __forceinline__ D4 operator/(D4 a, D4 b) {
-  const float q = a.v / b.v, ib = 1.f / b.v;
-  return D4{q, {(a.d[0] - q * b.d[0]) * ib, (a.d[1] - q * b.d[1]) * ib, (a.d[2] - q * b.d[2]) * ib,
-                (a.d[3] - q * b.d[3]) * ib}};
-}
-// autograd conventions: ties of the binary min / max share the gradient, clamp(0) passes it at x >= 0, |x|' = sign(x)
-__device__ __forceinline__ D4 mix(D4 a, D4 b) {
-  return D4{a.v, {0.5f * (a.d[0] + b.d[0]), 0.5f * (a.d[1] + b.d[1]), 0.5f * (a.d[2] + b.d[2]), 0.5f * (a.d[3] + b.d[3])}};
-}
-__device__ __forceinline__ D4 dmax(D4 a, D4 b) { return a.v > b.v ? a : (a.v < b.v ? b : mix(a, b)); }
-__device__ __forceinline__ D4 dmin(D4 a, D4 b) { return a.v < b.v ? a : (a.v > b.v ? b : mix(a, b)); }
-__device__ __forceinline__ D4 clamp0(D4 a) { return a.v >= 0.f ? a : cst(0.f); }
-__device__ __forceinline__ D4 dabs(D4 a) {
-  const float s = a.v > 0.f ? 1.f : (a.v < 0.f ? -1.f : 0.f);
-  return scale(a, fabsf(a.v), s);
-}
-__device__ __forceinline__ D4 dexp(D4 a) {
-  const float e = expf(a.v);
-  return scale(a, e, e);
-}
-__device__ __forceinline__ D4 dsqrt(D4 a) {
-  const float r = sqrtf(a.v);
-  return scale(a, r, 0.5f / r);
-}
-__device__ __forceinline__ D4 dpow4(D4 a) {
-  const float a2 = a.v * a.v;
-  return scale(a, a2 * a2, 4.f * a2 * a.v);
-}
 
 // bbox_iou(pbox.T, tbox, x1y1x2y2=False, SIoU=True): utils/metrics.py:236-257, 286-307 (alpha = 1, not Focal)
 __device__ D4 siou(D4 px, D4 py, D4 pw, D4 ph, float tx, float ty, float tw, float th) {
@@ -128,16 +73,6 @@ __device__ D4 siou(D4 px, D4 py, D4 pw, D4 ph, float tx, float ty, float tw, flo
   const D4 ow = dabs(w1 - w2) / dmax(w1, cst(w2)), oh = dabs(h1 - h2) / dmax(h1, cst(h2));
   const D4 shape = dpow4(rsub(1.f, dexp(ow * -1.f))) + dpow4(rsub(1.f, dexp(oh * -1.f)));
   return iou - ((dist + shape) * 0.5f + kEps);
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-// F.binary_cross_entropy_with_logits(x, t, pos_weight = pw), element-wise: (1 - t) x - (1 + (pw - 1) t) logsigmoid(x)
-__device__ __forceinline__ float bce(float x, float t, float pw, float& dx) {
-  const float lw = (pw - 1.f) * t + 1.f;
-  const float ls = fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
-  dx = (1.f - t) - lw * (1.f - sigmoidf_(x));
-  return (1.f - t) * x - lw * ls;
 }
 
 // ---- pass 1 over the candidates: build_targets (:236-288) + box regression (:177-199) --------------------------
@@ -187,18 +122,6 @@ __global__ void __launch_bounds__(kThreads) k_loss_match(const LossArgs a) {
   d.w = r.d[3] * 4.f * ph2 * s3 * (1.f - s3) * ah;
   reinterpret_cast<float4*>(a.c_diou)[idx] = d;
   atomicMax(a.stamp + a.cell_base[l] + cell, (int)row + 1);
-}
-
-template <typename T>
-__device__ __forceinline__ T block_sum(T v, T* sh) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  T r = 0;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < kThreads / 32; ++w) r += sh[w];
-  __syncthreads();
-  return r;   // valid in thread 0
 }
 
 // ---- per level: n and sum(1 - iou) over the matches, fixed summation order --------------------------------------

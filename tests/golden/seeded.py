@@ -405,3 +405,41 @@ def loss_inputs(spec):
     targets = torch.cat([img[:, None], cls[:, None], cxy, wh], 1).reshape(nt, 6)
     gout = float(torch.rand(1, generator=g)) + 0.5                          # upstream gradient of the scalar loss
     return dict(p=p, anchors=anchors, targets=targets, gout=gout)
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY section 8f rank 1, Stack B: TAL loss (utils/loss_tal.py ComputeLoss + utils/tal/assigner.py)
+# ---------------------------------------------------------------------------------------------
+TAL_CASES = {
+    "tal_basic": dict(N=3, nc=5, grids=[(8, 8), (4, 4)], strides=[16.0, 32.0], nt=12, seed=901, wh=(0.3, 0.7)),
+    "tal_empty": dict(N=2, nc=5, grids=[(8, 8), (4, 4)], strides=[16.0, 32.0], nt=0, seed=902, wh=(0.3, 0.7)),
+    "tal_dense": dict(N=2, nc=3, grids=[(10, 10), (5, 5)], strides=[16.0, 32.0], nt=30, seed=903, wh=(0.35, 0.8)),
+    "tal_rect_nc1": dict(N=2, nc=1, grids=[(6, 10), (3, 5)], strides=[16.0, 32.0], nt=9, seed=904, wh=(0.4, 0.8)),
+    "tal_small_boxes": dict(N=2, nc=4, grids=[(16, 16), (8, 8)], strides=[16.0, 32.0], nt=14, seed=905, wh=(0.04, 0.5)),
+    "tal_nl3_uneven": dict(N=4, nc=6, grids=[(16, 16), (8, 8), (4, 4)], strides=[8.0, 16.0, 32.0], nt=20, seed=906,
+                           wh=(0.3, 0.9), skip_image=2, smooth=0.0, cls_pw=1.3),
+}
+
+
+def tal_inputs(spec):
+    """Raw DDetect training outputs feats[i] [N, 64 + nc, ny, nx] (models/yolo_snn.py:117-119) and targets [nt, 6] =
+    (image, class, cx, cy, w, h) normalised.  The box logits are scaled so that the decoded boxes are a few cells wide
+    (positive CIoU with the synthetic boxes, i.e. a non-trivial assignment)."""
+    g = gen(spec["seed"])
+    N, nc = spec["N"], spec["nc"]
+    feats = []
+    for ny, nx in spec["grids"]:
+        f = randn(g, N, 64 + nc, ny, nx, scale=1.0)
+        f[:, :64] = f[:, :64] * 1.5 - torch.arange(16.0).repeat(4).view(1, 64, 1, 1) * 0.45   # mass on the low bins
+        feats.append(f)
+    nt = spec["nt"]
+    img = torch.randint(0, N, (nt,), generator=g).float()
+    if "skip_image" in spec and nt:
+        img = torch.where(img == spec["skip_image"], torch.zeros_like(img), img)     # one image without labels
+    cls = torch.randint(0, nc, (nt,), generator=g).float()
+    lo, hi = spec["wh"]
+    wh = torch.rand(nt, 2, generator=g) * (hi - lo) + lo
+    cxy = torch.rand(nt, 2, generator=g) * (1 - wh) + wh / 2                          # boxes inside the image
+    targets = torch.cat([img[:, None], cls[:, None], cxy, wh], 1).reshape(nt, 6)
+    gout = float(torch.rand(1, generator=g)) + 0.5
+    return dict(feats=feats, targets=targets, strides=torch.tensor(spec["strides"]), gout=gout)

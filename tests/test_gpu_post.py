@@ -271,3 +271,62 @@ def test_compute_loss_rejects_unsupported_variants():
     with pytest.raises(ValueError):
         E.loss.yolo_loss([torch.zeros(1, 3, 4, 4, 8).cuda()], torch.zeros(2, 5).cuda(), torch.ones(1, 3, 2).cuda(),
                          balance=[4.0], box=0.05, obj=1.0, cls=0.5)
+
+
+# ---- Stack-B training loss: TAL -------------------------------------------------------------
+class _TalHolder(torch.nn.Module):
+    def __init__(self, spec, strides):
+        super().__init__()
+        import types
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.hyp = dict(cls_pw=spec.get("cls_pw", 1.0), fl_gamma=0.0, label_smoothing=spec.get("smooth", 0.0))
+        self.model = [types.SimpleNamespace(nl=len(strides), nc=spec["nc"], no=64 + spec["nc"], reg_max=16, stride=strides)]
+
+
+@pytest.mark.parametrize("name", list(S.TAL_CASES))
+def test_tal_loss_golden(name):
+    """ecs.loss_tal.ComputeLoss (ecsy_tal_loss through autograd) against utils.loss_tal.ComputeLoss of the unmodified
+    reference: same number of foreground anchors, loss / loss_items within 1e-5 relative, gradients within 1e-4."""
+    E = ecsy()
+    gold = _load("post_tal")[name]
+    spec = S.TAL_CASES[name]
+    inp = S.tal_inputs(spec)
+    crit = E.loss_tal.ComputeLoss(_TalHolder(spec, inp["strides"]))
+    feats = [x.cuda().requires_grad_(True) for x in inp["feats"]]
+    loss, items = crit(feats, inp["targets"].cuda())
+    out, _ = E.loss_tal.tal_loss([x.detach() for x in feats], inp["targets"].cuda(), spec["strides"],
+                                 spec.get("cls_pw", 1.0), need_grad=False)
+    assert int(out[4]) == gold["fg"], (int(out[4]), gold["fg"])
+    assert abs(float(out[5]) - gold["score_sum"]) <= 1e-5 * max(gold["score_sum"], 1.0)
+    assert loss.dim() == 0 and items.shape == (3,) and not items.requires_grad
+    assert torch.allclose(loss.detach().cpu(), gold["loss"], rtol=1e-5), (float(loss), float(gold["loss"]))
+    assert torch.allclose(items.cpu(), gold["items"], rtol=1e-5, atol=1e-6)
+    (loss * inp["gout"]).backward()
+    for x, g in zip(feats, gold["grads"]):
+        err = (x.grad.cpu() - g).abs().max() / g.abs().max().clamp_min(1e-12)
+        assert float(err) < 1e-4, (name, float(err))
+
+
+def test_tal_loss_full_size_vs_oracle():
+    """BASELINE training shape of resnet18.yaml (batch 16, 40x40 + 20x20 levels, nc = 80, ~6.5 boxes per image) against
+    the CPU oracle; bit-reproducible across runs; a label outside the batch is ignored."""
+    import tal_oracle as TO
+    E = ecsy()
+    spec = dict(N=16, nc=80, grids=[(40, 40), (20, 20)], strides=[16.0, 32.0], nt=104, seed=911, wh=(0.05, 0.35))
+    inp = S.tal_inputs(spec)
+    ref = [x.clone().requires_grad_(True) for x in inp["feats"]]
+    want, items, n_fg = TO.compute_loss(ref, inp["targets"], spec["strides"])
+    want.backward()
+    fc = [x.cuda() for x in inp["feats"]]
+    out, grads = E.loss_tal.tal_loss(fc, inp["targets"].cuda(), spec["strides"])
+    assert int(out[4]) == n_fg and n_fg > 100
+    assert torch.allclose(out[0].cpu(), want.detach(), rtol=1e-5), (float(out[0]), float(want))
+    assert torch.allclose(out[1:4].cpu(), items, rtol=1e-5)
+    for g, x in zip(grads, ref):
+        err = (g.cpu() - x.grad).abs().max() / x.grad.abs().max()
+        assert float(err) < 1e-4, float(err)
+    out2, _ = E.loss_tal.tal_loss(fc, inp["targets"].cuda(), spec["strides"], need_grad=False)
+    assert torch.equal(out2, out)
+    bad = torch.cat([inp["targets"][:50], torch.tensor([[99.0, 1.0, 0.5, 0.5, 0.2, 0.2]]), inp["targets"][50:]]).cuda()
+    out3, _ = E.loss_tal.tal_loss(fc, bad, spec["strides"], need_grad=False)
+    assert torch.equal(out3, out)

@@ -87,3 +87,22 @@ def test_compute_loss_oracle(name):
     (loss * inp["gout"]).sum().backward()
     for x, g in zip(p, gold["grads"]):
         assert torch.allclose(x.grad, g, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(S.TAL_CASES))
+def test_tal_loss_oracle(name):
+    """oracle/tal_oracle.py against utils.loss_tal.ComputeLoss (TaskAlignedAssigner + SIoU + DFL + BCE) of the unmodified
+    reference: loss, loss_items, number of foreground anchors, gradient w.r.t. every level's raw head output."""
+    import tal_oracle as TO
+    gold = _load("post_tal")[name]
+    spec = S.TAL_CASES[name]
+    inp = S.tal_inputs(spec)
+    assert abs(S.checksum(*inp["feats"], inp["targets"]) - gold["chk"]) <= 1e-6 * abs(gold["chk"])
+    feats = [x.clone().requires_grad_(True) for x in inp["feats"]]
+    loss, items, n_fg = TO.compute_loss(feats, inp["targets"], spec["strides"], spec.get("cls_pw", 1.0))
+    assert n_fg == gold["fg"]
+    assert torch.allclose(loss, gold["loss"], rtol=2e-6, atol=1e-6), (float(loss), float(gold["loss"]))
+    assert torch.allclose(items, gold["items"], rtol=2e-6, atol=1e-6)
+    (loss * inp["gout"]).sum().backward()
+    for x, g in zip(feats, gold["grads"]):
+        assert torch.allclose(x.grad, g, rtol=1e-4, atol=1e-7 * float(g.abs().max()))
