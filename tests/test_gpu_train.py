@@ -219,3 +219,58 @@ def test_model_ee_training_step():
         opt.step()
         losses.append(loss.item())
     assert min(losses[1:]) < losses[0], losses
+
+
+def _coco_like_targets(n_img, nc, seed):
+    g = torch.Generator().manual_seed(seed)
+    per = torch.randint(2, 5, (n_img,), generator=g)
+    img = torch.repeat_interleave(torch.arange(n_img), per).float()
+    n = int(img.numel())
+    return torch.cat([img[:, None], torch.randint(0, nc, (n, 1), generator=g).float(),
+                      torch.rand(n, 2, generator=g) * 0.6 + 0.2, torch.rand(n, 2, generator=g) * 0.4 + 0.2], 1).cuda()
+
+
+def test_model_trains_against_compute_loss():
+    """Stack-A model end to end with the reference's training loss on the device (ecs.loss.ComputeLoss, utils/loss.py
+    semantics): finite gradients everywhere and a decreasing loss on a fixed batch."""
+    E = ecsy()
+    torch.manual_seed(0)
+    m = E.yolo.Model(E.cfg_path("tiny")).cuda().train()
+    det = m.model[-1]
+    m.hyp = dict(box=0.05 * 3 / det.nl, cls=0.5 * det.nc / 80 * 3 / det.nl, obj=1.0 * 3 / det.nl, cls_pw=1.0, obj_pw=1.0,
+                 anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)
+    crit = E.loss.ComputeLoss(m)
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    tg = _coco_like_targets(2, det.nc, 5)
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9)
+    losses = []
+    for it in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss, items = crit(m(x), tg)
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+        opt.step()
+        losses.append(float(loss))
+        assert abs(float(items.sum()) * 2 - losses[-1]) < 1e-4 * losses[-1]     # loss = sum(items) * batch size
+    assert min(losses[-2:]) < losses[0], losses
+
+
+def test_model_b_trains_against_tal_loss():
+    """Stack-B model end to end with utils/loss_tal.py semantics on the device (ecs.loss_tal.ComputeLoss)."""
+    E = ecsy()
+    torch.manual_seed(0)
+    m = E.yolo_snn.DetectionModel(E.cfg_path("tiny_b")).cuda().train()
+    m.hyp = dict(cls_pw=1.0, fl_gamma=0.0, label_smoothing=0.0)
+    crit = E.loss_tal.ComputeLoss(m)
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    tg = _coco_like_targets(2, m.model[-1].nc, 6)
+    opt = torch.optim.SGD(m.parameters(), lr=0.002, momentum=0.9)
+    losses = []
+    for it in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss, items = crit(m(x), tg)
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+        opt.step()
+        losses.append(float(loss))
+    assert min(losses[-2:]) < losses[0], losses
