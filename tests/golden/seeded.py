@@ -443,3 +443,18 @@ def tal_inputs(spec):
     targets = torch.cat([img[:, None], cls[:, None], cxy, wh], 1).reshape(nt, 6)
     gout = float(torch.rand(1, generator=g)) + 0.5
     return dict(feats=feats, targets=targets, strides=torch.tensor(spec["strides"]), gout=gout)
+
+
+# ---------------------------------------------------------------------------------------------
+# pickled reference checkpoints (models/experimental.py:87-127)
+# ---------------------------------------------------------------------------------------------
+CKPT_PLANS = {
+    "micro_a": dict(nc=3, depth_multiple=1.0, width_multiple=1.0, anchors=[[10, 14, 23, 27, 37, 58], [81, 82, 135, 169, 344, 319]],
+                    backbone=[[-1, 1, "Conv_1", [64, 7, 2]], [-1, 1, "BasicBlock_2", [64, 3, 2]],
+                              [-1, 1, "BasicBlock_2", [64, 3, 2]]],
+                    head=[[[1, 2], 1, "Detect", ["nc", "anchors"]]]),
+    "micro_b": dict(nc=3, depth_multiple=1.0, width_multiple=1.0, anchors=2,
+                    backbone=[[-1, 1, "Conv_1", [64, 7, 2]], [-1, 1, "BasicBlock_2", [64, 3, 2]],
+                              [-1, 1, "BasicBlock_2", [64, 3, 2]]],
+                    head=[[[1, 2], 1, "DDetect", ["nc"]]]),
+}
