@@ -15,7 +15,7 @@ CUDA only: there is no CPU kernel behind any of them (the fake implementations o
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -140,3 +140,39 @@ def _lsc_backward(ctx, g_y, _g_bits):
 
 
 lif_spike_conv.register_autograd(_lsc_backward, setup_context=_lsc_setup)
+
+
+# ---------------------------------------------------------------------------------------------- training losses
+# Forward AND gradient in one call: the gradient w.r.t. every level is an explicit output (for an
+# upstream gradient of 1) -- `loss.ComputeLoss` / `loss_tal.ComputeLoss` wrap these in an autograd.Function that scales it.
+@torch.library.custom_op("ecsy::yolo_loss", mutates_args=())
+def yolo_loss(p: List[Tensor], targets: Tensor, anchors: Tensor, balance: List[float], box: float, obj: float, cls: float,
+              cls_pw: float, obj_pw: float, cp: float, cn: float, anchor_t: float, gr: float) -> Tuple[Tensor, List[Tensor]]:
+    """utils/loss.py:162-290 (`ComputeLoss.__call__` + `build_targets`, SIoU + BCE) -> (out [4 + nl], d loss / d p)."""
+    from .loss import yolo_loss as _impl
+    out, grads = _impl(p, targets, anchors, balance, box, obj, cls, cls_pw, obj_pw, cp, cn, anchor_t, gr, True)
+    return out, grads
+
+
+@yolo_loss.register_fake
+def _(p, targets, anchors, balance, box, obj, cls, cls_pw, obj_pw, cp, cn, anchor_t, gr):
+    torch._check(all(x.dim() == 5 for x in p), lambda: "ecsy::yolo_loss: levels are [N, na, ny, nx, 5 + nc]")
+    torch._check(targets.dim() == 2 and targets.shape[1] == 6, lambda: "ecsy::yolo_loss: targets are [nt, 6]")
+    return p[0].new_empty((4 + len(p),), dtype=torch.float32), [torch.empty_like(x, dtype=torch.float32) for x in p]
+
+
+@torch.library.custom_op("ecsy::tal_loss", mutates_args=())
+def tal_loss(feats: List[Tensor], targets: Tensor, strides: List[float], cls_pw: float, gain_box: float, gain_cls: float,
+             gain_dfl: float) -> Tuple[Tensor, List[Tensor]]:
+    """utils/loss_tal.py:162-215 (TaskAlignedAssigner + box + DFL + BCE) -> (out [6], d loss / d feats)."""
+    from .loss_tal import tal_loss as _impl
+    out, grads = _impl(feats, targets, strides, cls_pw, (gain_box, gain_cls, gain_dfl), True)
+    return out, grads
+
+
+@tal_loss.register_fake
+def _(feats, targets, strides, cls_pw, gain_box, gain_cls, gain_dfl):
+    torch._check(all(x.dim() == 4 and x.shape[1] > 64 for x in feats),
+                 lambda: "ecsy::tal_loss: levels are [N, 64 + nc, ny, nx]")
+    torch._check(len(strides) == len(feats), lambda: "ecsy::tal_loss: one stride per level")
+    return feats[0].new_empty((6,), dtype=torch.float32), [torch.empty_like(x, dtype=torch.float32) for x in feats]

@@ -64,3 +64,25 @@ def test_lif_spike_conv_autograd():
     assert rel_l2(wc.grad.cpu(), wl.grad) < 5e-3
     for t, k in zip(p, ("dw_w", "dw_b", "pw_w", "pw_b")):
         assert rel_l2(t.grad.cpu(), leaves[k].grad) < 5e-3, k
+
+
+def test_loss_ops_match_direct_calls():
+    """torch.ops.ecsy.yolo_loss / tal_loss return exactly what loss.yolo_loss / loss_tal.tal_loss return (same C-ABI call)."""
+    E = ecsy()
+    ns = torch.ops.ecsy
+    spec = S.LOSS_CASES["loss_basic"]
+    li = S.loss_inputs(spec)
+    h = spec["hyp"]
+    p = [x.cuda() for x in li["p"]]
+    tg, an = li["targets"].cuda(), li["anchors"].cuda()
+    out, grads = ns.yolo_loss(p, tg, an, [4.0, 1.0], h["box"], h["obj"], h["cls"], 1.0, 1.0, 1.0, 0.0, h["anchor_t"], 1.0)
+    out2, grads2 = E.loss.yolo_loss(p, tg, an, [4.0, 1.0], h["box"], h["obj"], h["cls"], anchor_t=h["anchor_t"])
+    assert torch.equal(out, out2)
+    # cells hit by several matches accumulate with float atomics: equal up to summation order
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-8) for a, b in zip(grads, grads2))
+    ts = S.TAL_CASES["tal_basic"]
+    ti = S.tal_inputs(ts)
+    f = [x.cuda() for x in ti["feats"]]
+    out, grads = ns.tal_loss(f, ti["targets"].cuda(), ts["strides"], 1.0, 7.5, 0.5, 1.5)
+    out2, grads2 = E.loss_tal.tal_loss(f, ti["targets"].cuda(), ts["strides"])
+    assert torch.equal(out, out2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))

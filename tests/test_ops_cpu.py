@@ -28,9 +28,25 @@ def test_custom_ops_registered_and_fake_shapes():
     assert y2.shape == (T, N, H, W, Co) and b2.shape == bits.shape
 
 
+def test_loss_ops_fake_shapes():
+    ecsy()
+    ns = torch.ops.ecsy
+    m = "meta"
+    p = [torch.empty(4, 3, 40, 40, 18, device=m), torch.empty(4, 3, 20, 20, 18, device=m)]
+    out, grads = ns.yolo_loss(p, torch.empty(9, 6, device=m), torch.empty(2, 3, 2, device=m), [4.0, 1.0], 0.05, 1.0, 0.5,
+                              1.0, 1.0, 1.0, 0.0, 4.0, 1.0)
+    assert out.shape == (6,) and [g.shape for g in grads] == [x.shape for x in p]
+    f = [torch.empty(4, 144, 40, 40, device=m), torch.empty(4, 144, 20, 20, device=m)]
+    out, grads = ns.tal_loss(f, torch.empty(9, 6, device=m), [16.0, 32.0], 1.0, 7.5, 0.5, 1.5)
+    assert out.shape == (6,) and [g.shape for g in grads] == [x.shape for x in f]
+
+
 def test_custom_ops_have_no_cpu_kernel():
     ecsy()
     import pytest
     x = torch.zeros(1, 1, 2, 2, 64)
     with pytest.raises(RuntimeError):
         torch.ops.ecsy.tdbn_stats(x)
+    with pytest.raises(RuntimeError):
+        torch.ops.ecsy.yolo_loss([torch.zeros(1, 3, 4, 4, 8)], torch.zeros(1, 6), torch.ones(1, 3, 2), [4.0], 0.05, 1.0, 0.5,
+                                 1.0, 1.0, 1.0, 0.0, 4.0, 1.0)
