@@ -306,7 +306,8 @@ def main():
     ap.add_argument("--optim", default="fused", choices=["fused", "torch"],
                     help="training: fused SGD-Nesterov + EMA kernel (default) or torch.optim.SGD without EMA")
     ap.add_argument("--loss", default="yolo", choices=["yolo", "quadratic"],
-                    help="training: the reference's ComputeLoss on the device (Detect models) or a synthetic quadratic")
+                    help="training: the reference's ComputeLoss on the device (utils/loss.py for Detect models, utils/loss_tal.py for "
+                         "DDetect models) or a synthetic quadratic on the raw head outputs")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()
