@@ -458,3 +458,20 @@ CKPT_PLANS = {
                               [-1, 1, "BasicBlock_2", [64, 3, 2]]],
                     head=[[[1, 2], 1, "DDetect", ["nc"]]]),
 }
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole model + training loss (north_star: "head outputs and loss agree within 1e-3 relative")
+# ---------------------------------------------------------------------------------------------
+MODEL_LOSS_HYP = dict(box=0.05 * 3 / 2, cls=0.5 * 3 / 80 * 3 / 2, obj=1.0 * (64 / 640) ** 2 * 3 / 2, cls_pw=1.0, obj_pw=1.0,
+                      anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)     # train.py:427-433 scaling
+
+
+def model_targets(spec, nc=3):
+    """[nt, 6] labels for the whole-model loss cases: 3 boxes per image, sized to match the tiny plans' anchors."""
+    g = gen(spec["seed"] + 31)
+    N = spec["N"]
+    img = torch.arange(N).repeat_interleave(3).float()
+    n = img.numel()
+    return torch.cat([img[:, None], torch.randint(0, nc, (n, 1), generator=g).float(),
+                      torch.rand(n, 2, generator=g) * 0.5 + 0.25, torch.rand(n, 2, generator=g) * 0.4 + 0.25], 1)

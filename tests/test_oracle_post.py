@@ -106,3 +106,24 @@ def test_tal_loss_oracle(name):
     (loss * inp["gout"]).sum().backward()
     for x, g in zip(feats, gold["grads"]):
         assert torch.allclose(x.grad, g, rtol=1e-4, atol=1e-7 * float(g.abs().max()))
+
+
+@pytest.mark.parametrize("name", ["tiny_64", "tiny_ee_64"])
+def test_model_plus_loss_oracle(name):
+    """The two oracles chained -- ecs_oracle.forward (train mode) -> loss_oracle.compute_loss -- against the unmodified
+    reference's model + utils.loss.ComputeLoss on the same weights, image and labels (oracle/gen_golden_model_loss.py)."""
+    import yaml
+    import ecs_oracle as O
+    import loss_oracle as LO
+    from util import ROOT
+    spec = S.MODEL_CASES[name]
+    gold = _load("model_loss")[name]
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")))
+    inp = S.model_inputs(spec, O, cfg)
+    with torch.no_grad():
+        out = O.forward(cfg, inp["sd"], inp["x"], spec["T"], True, stride=inp["stride"])
+    anchors = [v for k, v in inp["sd"].items() if k.endswith("anchors")][0]
+    loss, items, counts, _ = LO.compute_loss(out, S.model_targets(spec, cfg["nc"]), anchors, S.MODEL_LOSS_HYP)
+    assert min(counts) > 0
+    assert torch.allclose(loss.reshape(-1), gold["loss"], rtol=1e-5), (float(loss), float(gold["loss"]))
+    assert torch.allclose(items, gold["items"], rtol=1e-5, atol=1e-7)
