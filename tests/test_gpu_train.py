@@ -330,3 +330,7 @@ def test_model_loss_matches_reference_other_plans(name):
     print(name, float(loss), float(gold["loss"]), items.tolist(), gold["items"].tolist())
     assert torch.allclose(loss, gold["loss"], rtol=1e-3), (float(loss), float(gold["loss"]))
     assert torch.allclose(items, gold["items"], rtol=1e-3, atol=1e-6)
+    params = dict(m.named_parameters())
+    errs = {k: rel_l2(params[k].grad.cpu(), g) for k, g in gold["head_grads"].items()}
+    print(name, "head grad errs", {k: round(v, 6) for k, v in errs.items()})
+    assert max(errs.values()) < 2e-2, errs
