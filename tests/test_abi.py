@@ -47,6 +47,10 @@ def test_no_cpu_fallback():
     E = ecsy()
     with pytest.raises(RuntimeError):
         E.functional.Act.from_ref(torch.zeros(1, 1, 64, 2, 2))
+    with pytest.raises(RuntimeError):      # the training losses have no CPU path either
+        E.loss.yolo_loss([torch.zeros(1, 3, 4, 4, 8)], torch.zeros(1, 6), torch.ones(1, 3, 2), [4.0], 0.05, 1.0, 0.5)
+    with pytest.raises(RuntimeError):
+        E.loss_tal.tal_loss([torch.zeros(1, 67, 4, 4)], torch.zeros(1, 6), [16.0])
 
 
 def test_state_dict_keys_match_reference_layout():
