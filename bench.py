@@ -101,9 +101,10 @@ def event_frames(n, T, img, gen):
     return f.expand(-1, -1, 3, -1, -1).permute(1, 0, 2, 3, 4).contiguous()
 
 
-def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, events=False):
+def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, events=False, device="cpu", autocast=False):
     """Times the oracle port of the reference's CPU path (torch fp32, all host threads) on a bounded
-    sample of the same workload: `sample_imgs` images per step."""
+    sample of the same workload: `sample_imgs` images per step.  device="cuda" (`--impl reference --ref-device cuda`)
+    runs the same stock-PyTorch eager code on the GPU instead: the same-box GPU comparison of SURVEY 8(d)."""
     import ecs_oracle as O
     torch.set_num_threads(threads)
     cfg = load_cfg(model_name)
@@ -116,15 +117,26 @@ def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, event
             sd[k] = sd[k] / stride.view(-1, 1, 1)
     g = torch.Generator().manual_seed(0)
     x = event_frames(sample_imgs, T, img, g) if events else torch.rand(sample_imgs, 3, img, img, generator=g)
-    with torch.no_grad():
+    on_gpu = device != "cpu"
+    if on_gpu:
+        sd = {k: v.to(device) for k, v in sd.items()}
+        x, stride = x.to(device), stride.to(device)
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
+    amp = torch.autocast("cuda", dtype=torch.float16, enabled=bool(autocast and on_gpu))   # the reference's AMP (train.py:546)
+    with torch.no_grad(), amp:
         O.BN_MOMENTUM = 1.0
         O.forward(cfg, sd, x, T, True, stride=stride)   # calibration pass (train-mode tdBN) == warm-up 0
         O.BN_MOMENTUM = 0.1
         for _ in range(max(warmup - 1, 0)):
             O.forward(cfg, sd, x, T, False, stride=stride)
+        sync()
         t0 = time.perf_counter()
         for _ in range(steps):
             O.forward(cfg, sd, x, T, False, stride=stride)
+        sync()
         dt = time.perf_counter() - t0
     return sample_imgs * steps / dt, dt / steps
 
@@ -300,6 +312,10 @@ def main():
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs under ncu may lower this")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--cpu-sample", type=int, default=1, help="images per CPU step")
+    ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda only: run the eager port under fp16 autocast")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the reference arm proper (host cores); cuda = the same stock-PyTorch "
+                         "eager code on the GPU (extra same-box comparison, SURVEY 8d)")
     ap.add_argument("--events", action="store_true",
                     help="BASELINE config 4: Gen1-style event frames [T,N,3,H,W] straight into _forward_once, nc=2 "
                          "(use with --T 5)")
@@ -326,7 +342,7 @@ def main():
             return
         steps = max(args.steps, 1)
         ips, spstep = cpu_reference(args.model, args.T, args.img, args.cpu_sample, steps, max(args.warmup, 1), threads,
-                                    args.events)
+                                    args.events, args.ref_device, args.ref_autocast)
         line = {"impl": "reference", "metric": "images/s", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -335,6 +351,11 @@ def main():
                                  "sample": f"{args.cpu_sample} image(s)/step of the same workload, oracle port "
                                            "(torch fp32 CPU) of the reference forward"},
                 "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if args.ref_device != "cpu":      # not the reference arm proper: the same eager code on the GPU, labelled as such
+            line["config"]["device"] = ("cuda: stock PyTorch eager (oracle port, " +
+                                        ("fp16 autocast" if args.ref_autocast else "fp32, cuDNN TF32 convolutions") +
+                                        "), same-box GPU comparison")
+            line["cpu_baseline"] = None
         emit(line)
         return
 

@@ -112,7 +112,7 @@ def snn_conv2d(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = Non
     k = w.shape[-1]
     ho = (x.shape[3] - (k - 1) + 2 * padding - 1) // stride + 1
     wo = (x.shape[4] - (k - 1) + 2 * padding - 1) // stride + 1
-    out = torch.zeros(T, N, w.shape[0], ho, wo, dtype=x.dtype)
+    out = torch.zeros(T, N, w.shape[0], ho, wo, dtype=x.dtype, device=x.device)
     for t in range(T):
         out[t] = F.conv2d(x[t], w, b, stride, padding, 1, groups)
     return out
@@ -241,7 +241,8 @@ def conv_silu(sd, p, x, k, s, g=1, training=False, silu_inplace=True):
 # a6  Sample / Concat  (models/common.py:844-868, 1758-1765)
 # --------------------------------------------------------------------------------------
 def sample_nearest(x: torch.Tensor, scale: int) -> torch.Tensor:
-    out = torch.zeros(x.shape[0], x.shape[1], x.shape[2], x.shape[3] * scale, x.shape[4] * scale, dtype=x.dtype)
+    out = torch.zeros(x.shape[0], x.shape[1], x.shape[2], x.shape[3] * scale, x.shape[4] * scale, dtype=x.dtype,
+                      device=x.device)
     for t in range(x.shape[0]):
         out[t] = F.interpolate(x[t], scale_factor=float(scale), mode="nearest")
     return out
@@ -265,7 +266,7 @@ def detect_a(sd, p, feats: Sequence[torch.Tensor], nc: int, anchors: torch.Tenso
         y = y.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
         xs.append(y)
         if not training:
-            yv, xv = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing="ij")
+            yv, xv = torch.meshgrid([torch.arange(ny, device=y.device), torch.arange(nx, device=y.device)], indexing="ij")
             grid = torch.stack((xv, yv), 2).expand((1, na, ny, nx, 2)).float()
             ag = (anchors[i].clone() * stride[i]).view((1, na, 1, 1, 2)).expand((1, na, ny, nx, 2)).float()
             o = y.sigmoid()
@@ -312,17 +313,17 @@ def ddetect(sd, p, feats: Sequence[torch.Tensor], nc: int, stride: torch.Tensor,
     pts, strs = [], []
     for i, s in enumerate(stride):
         _, _, h, w = xs[i].shape
-        sx = torch.arange(end=w, dtype=torch.float32) + 0.5
-        sy = torch.arange(end=h, dtype=torch.float32) + 0.5
+        sx = torch.arange(end=w, dtype=torch.float32, device=xs[i].device) + 0.5
+        sy = torch.arange(end=h, dtype=torch.float32, device=xs[i].device) + 0.5
         sy, sx = torch.meshgrid(sy, sx, indexing="ij")
         pts.append(torch.stack((sx, sy), -1).view(-1, 2))
-        strs.append(torch.full((h * w, 1), float(s), dtype=torch.float32))
+        strs.append(torch.full((h * w, 1), float(s), dtype=torch.float32, device=xs[i].device))
     anchors = torch.cat(pts).transpose(0, 1)
     strides = torch.cat(strs).transpose(0, 1)
     bs = xs[0].shape[0]
     box, cls = torch.cat([xi.view(bs, no, -1) for xi in xs], 2).split((reg_max * 4, nc), 1)
     b, _, a = box.shape
-    proj = torch.arange(reg_max, dtype=torch.float32).view(1, reg_max, 1, 1)
+    proj = torch.arange(reg_max, dtype=torch.float32, device=box.device).view(1, reg_max, 1, 1)
     dist = F.conv2d(box.view(b, 4, reg_max, a).transpose(2, 1).softmax(1), proj).view(b, 4, a)
     lt, rb = torch.split(dist, 2, 1)
     x1y1 = anchors.unsqueeze(0) - lt
@@ -406,7 +407,7 @@ def forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, T: int, tra
     Detect ([nl,na,2]), i.e. the module's ``anchors`` buffer; ``stride``: the head strides."""
     layers, save = plan_model(cfg, x.shape[-3])
     if x.dim() == 4:
-        inp = torch.zeros(T, *x.shape, dtype=x.dtype)
+        inp = torch.zeros(T, *x.shape, dtype=x.dtype, device=x.device)
         for t in range(T):
             inp[t] = x
         x = inp
