@@ -64,7 +64,7 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
                         classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
                         max_det: int = 300, use_torchvision: bool = False) -> List[torch.Tensor]:
     """utils/general.py:649-741 without the autolabelling / merge-NMS / time-limit branches.  ``use_torchvision``
-    calls torchvision.ops.nms for the inner step exactly like the reference (the timing leg of tools/post_bench.py;
+    calls torchvision.ops.nms for the inner step exactly like the reference (the timing leg of tests/diag/post_bench.py;
     works on CUDA tensors too); the default is the pure-torch restatement of it."""
     nc = prediction.shape[2] - 5
     xc = prediction[..., 4] > conf_thres

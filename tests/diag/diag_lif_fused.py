@@ -1,6 +1,6 @@
 """Diagnose the fused ECS-LIF kernel with structured spread weights (which taps / channel mixes are right?)."""
 import importlib, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import torch
 import ecs_oracle as O

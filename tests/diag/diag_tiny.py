@@ -1,6 +1,6 @@
 """Per-layer divergence of the tiny model, CUDA path vs CPU oracle (end-to-end, not teacher-forced)."""
 import importlib, os, sys, yaml, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import ecs_oracle as O, seeded as S

@@ -2,7 +2,7 @@
 GPU legs: CUDA events after warm-up.  CPU legs: the oracle port with torchvision.ops.nms / torch.optim.SGD + a
 ModelEMA-style loop -- the reference's own algorithm and libraries -- on this box's host cores."""
 import importlib, json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")):
     sys.path.insert(0, p)
 import torch

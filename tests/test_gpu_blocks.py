@@ -297,7 +297,7 @@ def test_model_b_tiny(name):
         E.common.mem_update.spikes, E.common.mem_update.analog = orig_s, orig_a
     # End to end this miniature is chaotic: ~5 near-threshold flips out of 655k spikes in the first block
     # already move its (small) output by 4e-2 rel-L2 and the error saturates three blocks later (measured,
-    # tools/diag_model.py tiny_b).  The reference behaves the same PyTorch-vs-PyTorch,
+    # tests/diag/diag_model.py tiny_b).  The reference behaves the same PyTorch-vs-PyTorch,
     # so the whole-model check is statistical; exactness is established teacher-forced per block above.
     for n_, r in rates.items():
         assert abs(r - gold["rates_train"][n_]) < 1e-2, (n_, r, gold["rates_train"][n_])

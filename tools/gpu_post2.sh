@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -k 10 500 python tools/post_bench.py 2>&1 | tail -12
+timeout -k 10 500 python tests/diag/post_bench.py 2>&1 | tail -12
 echo "== train bench fused vs torch (batch 32)"
 timeout -k 10 400 python bench.py --mode train --batch 32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/train_fused.json 2> gpurun_out/train_fused.err; echo rc=$?; tail -2 gpurun_out/train_fused.err
 timeout -k 10 400 python bench.py --mode train --batch 32 --steps 3 --warmup 3 --no-cpu-baseline --optim torch --no-e2e > gpurun_out/train_torch.json 2> gpurun_out/train_torch.err; echo rc=$?
