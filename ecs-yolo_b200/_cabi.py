@@ -68,7 +68,7 @@ SIGNATURES = {
     "ecsy_spike_conv_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "ecsy_yolo_loss_ws_bytes": (_z, [_i, _l, _i, _l, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ecsy_yolo_loss": (_i, [C.POINTER(_p), C.POINTER(_p), _p, _l, _p, _i, _l, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int),
-                            C.POINTER(C.c_float), _f, _f, _f, _f, _f, _f, _f, _f, _f, _p, _p, _z, _p]),
+                            C.POINTER(C.c_float), _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _p, _p, _p, _z, _p]),
     "ecsy_tal_loss_ws_bytes": (_z, [_i, _l, _l, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ecsy_tal_loss": (_i, [C.POINTER(_p), C.POINTER(_p), _p, _l, _i, _l, _i, C.POINTER(C.c_int), C.POINTER(C.c_int),
                            C.POINTER(C.c_float), _f, _f, _f, _f, _p, _p, _z, _p]),

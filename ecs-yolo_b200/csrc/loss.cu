@@ -38,6 +38,9 @@ struct LossArgs {
   int nl, na, nc, no;
   int64_t N, nt, per_level;            // per_level = 5 * na * nt candidates
   float box, obj, cls, cls_pw, obj_pw, cp, cn, anchor_t, gr;
+  float fl_gamma;      // > 0: FocalLoss around the BCE terms (utils/loss.py:80-106, alpha 0.25)
+  float* slide_state;  // non-null: SlideLoss (utils/loss.py:38-76); caller-owned [4] = ema_cls, ema_obj, has_cls, has_obj
+  float* thr;          // [nl][2] the SlideLoss ema in force for the class / objectness term of level l
   int* stamp;        // [cells]      row + 1 of the last candidate writing the cell, 0 = background
   float* c_iou;      // [nl * per_level]   SIoU of the candidate (valid ones)
   float* c_diou;     // [nl * per_level][4]  d SIoU / d raw (x, y, w, h) logits
@@ -73,6 +76,62 @@ __device__ D4 siou(D4 px, D4 py, D4 pw, D4 ph, float tx, float ty, float tw, flo
   const D4 ow = dabs(w1 - w2) / dmax(w1, cst(w2)), oh = dabs(h1 - h2) / dmax(h1, cst(h2));
   const D4 shape = dpow4(rsub(1.f, dexp(ow * -1.f))) + dpow4(rsub(1.f, dexp(oh * -1.f)));
   return iou - ((dist + shape) * 0.5f + kEps);
+}
+
+// ---- the wrapped criteria (utils/loss.py:145-152) ----------------------------------------------------------------
+// SlideLoss.forward's modulating weight (:61-69): 1 up to ema - 0.1, exp(1 - ema) below ema, exp(1 - true) from ema on.
+__device__ __forceinline__ float slide_weight(float t, float ema) {
+  if (t >= ema) return expf(-(t - 1.f));
+  if (t > ema - 0.1f) return (float)exp(1.0 - (double)ema);
+  return 1.f;
+}
+
+// element loss and its derivative: plain BCE, BCE * slide weight (a constant w.r.t. the logit), or the focal form
+// bce * (t*0.25 + (1-t)*0.75) * (1 - p_t)^gamma with p_t = t*p + (1-t)*(1-p)
+__device__ __forceinline__ float criterion(const LossArgs& a, float x, float t, float pw, float ema, float& dx) {
+  float l = bce(x, t, pw, dx);
+  if (a.slide_state != nullptr) {
+    const float w = slide_weight(t, ema);
+    dx *= w;
+    return l * w;
+  }
+  if (a.fl_gamma > 0.f) {
+    const float p = sigmoidf_(x);
+    const float base = 1.f - (t * p + (1.f - t) * (1.f - p));
+    const float af = t * 0.25f + (1.f - t) * 0.75f;
+    const float mod = powf(base, a.fl_gamma);
+    const float dmod = -a.fl_gamma * powf(base, a.fl_gamma - 1.f) * (2.f * t - 1.f) * p * (1.f - p);
+    dx = af * (dx * mod + l * dmod);
+    return l * af * mod;
+  }
+  return l;
+}
+
+// SlideLoss keeps an exponential average of `auto_iou` per wrapped criterion, updated on EVERY call in level order
+// (:50-59; the new value carries alpha = 0.999): class term only at levels with matches, objectness term always
+// (auto_iou defaults to 0.5 at a level without matches, :219-222).  One thread: nl sequential updates.
+__global__ void k_loss_slide_ema(const LossArgs a) {
+  float ema_c = a.slide_state[0], ema_o = a.slide_state[1];
+  bool has_c = a.slide_state[2] != 0.f, has_o = a.slide_state[3] != 0.f;
+  for (int l = 0; l < a.nl; ++l) {
+    const double n = a.nt > 0 ? a.lvl[2 * l] : 0.0;
+    float au = 0.5f;
+    if (n > 0.0) {
+      au = fmaxf((float)(1.0 - a.lvl[2 * l + 1] / n), 0.2f);      // iou.mean(), floored at 0.2 (:48-49)
+      if (a.nc > 1) {
+        ema_c = has_c ? 0.999f * au + 0.001f * ema_c : au;
+        has_c = true;
+      }
+    }
+    ema_o = has_o ? 0.999f * au + 0.001f * ema_o : au;
+    has_o = true;
+    a.thr[2 * l] = ema_c;
+    a.thr[2 * l + 1] = ema_o;
+  }
+  a.slide_state[0] = ema_c;
+  a.slide_state[1] = ema_o;
+  a.slide_state[2] = has_c ? 1.f : 0.f;
+  a.slide_state[3] = has_o ? 1.f : 0.f;
 }
 
 // ---- pass 1 over the candidates: build_targets (:236-288) + box regression (:177-199) --------------------------
@@ -168,10 +227,11 @@ __global__ void __launch_bounds__(kThreads) k_loss_cand_grad(const LossArgs a) {
     const int c = (int)a.targets[j * 6 + 1];
     const float* ps = a.p[l] + (int64_t)cell * a.no + 5;
     const float w = a.cls * bs / (n * (float)a.nc);
+    const float ema = a.slide_state ? a.thr[2 * l] : 0.f;
     float sum = 0.f;
     for (int q = 0; q < a.nc; ++q) {
       float dx;
-      sum += bce(ps[q], q == c ? a.cp : a.cn, a.cls_pw, dx);
+      sum += criterion(a, ps[q], q == c ? a.cp : a.cn, a.cls_pw, ema, dx);
       if (g) atomicAdd(g + 5 + q, w * dx);
     }
     a.c_cls[idx] = sum;
@@ -187,12 +247,13 @@ __global__ void __launch_bounds__(kThreads) k_loss_obj(const LossArgs a, int l) 
   const int* stamp = a.stamp + a.cell_base[l];
   const float* iou = a.c_iou + (int64_t)l * a.per_level;
   const float w = a.obj * (float)a.N * a.balance[l] / (float)cells;
+  const float ema = a.slide_state ? a.thr[2 * l + 1] : 0.f;
   double s = 0.0;
   for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < cells; c += (int64_t)gridDim.x * kThreads) {
     const int st = stamp[c];
     const float t = st > 0 ? (1.f - a.gr) + a.gr * fmaxf(iou[st - 1], 0.f) : 0.f;   // iou.detach().clamp(0) (:201-205)
     float dx;
-    s += (double)bce(p[c * a.no + 4], t, a.obj_pw, dx);
+    s += (double)criterion(a, p[c * a.no + 4], t, a.obj_pw, ema, dx);
     if (gp) gp[c * a.no + 4] = w * dx;
   }
   s = block_sum(s, sh);
@@ -236,7 +297,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_final(const LossArgs a) {
 }
 
 struct WsLayout {
-  size_t stamp, c_iou, c_diou, c_cell, c_cls, obj_part, lvl, total;
+  size_t stamp, c_iou, c_diou, c_cell, c_cls, obj_part, lvl, thr, total;
 };
 
 inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
@@ -251,6 +312,7 @@ WsLayout ws_layout(int nl, int64_t cells_total, int64_t cands, int obj_blocks) {
   w.c_cls = o;    o = align_up(o + (size_t)cands * 4);
   w.obj_part = o; o = align_up(o + (size_t)obj_blocks * 8);
   w.lvl = o;      o = align_up(o + (size_t)nl * 16);
+  w.thr = o;      o = align_up(o + (size_t)nl * 8);
   w.total = o;
   return w;
 }
@@ -278,19 +340,21 @@ extern "C" size_t ecsy_yolo_loss_ws_bytes(int nl, int64_t N, int na, int64_t nt,
 extern "C" int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets, int64_t nt,
                               const float* anchors, int nl, int64_t N, int na, int nc, const int* ny, const int* nx,
                               const float* balance, float box, float obj, float cls, float cls_pw, float obj_pw,
-                              float cp, float cn, float anchor_t, float gr, float* out, void* ws, size_t ws_bytes,
-                              void* stream) {
+                              float cp, float cn, float anchor_t, float gr, float fl_gamma, float* slide_state,
+                              float* out, void* ws, size_t ws_bytes, void* stream) {
   ECSY_CHECK_ARG(nl >= 1 && nl <= kMaxLevels, "yolo_loss: 1..%d detection levels, got %d", kMaxLevels, nl);
   ECSY_CHECK_ARG(p && ny && nx && balance && anchors && out, "yolo_loss: null argument");
   ECSY_CHECK_ARG(N >= 1 && na >= 1 && nc >= 1 && nt >= 0, "yolo_loss: bad sizes N=%lld na=%d nc=%d nt=%lld", (long long)N,
                  na, nc, (long long)nt);
   ECSY_CHECK_ARG(nt == 0 || targets, "yolo_loss: null targets");
+  ECSY_CHECK_ARG(!(fl_gamma > 0.f && slide_state), "yolo_loss: FocalLoss and SlideLoss cannot be combined (nor can the "
+                 "reference: FocalLoss.forward takes no auto_iou)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LossArgs a{};
   a.nl = nl; a.na = na; a.nc = nc; a.no = nc + 5; a.N = N; a.nt = nt; a.per_level = 5LL * na * nt;
   a.targets = targets; a.anchors = anchors;
   a.box = box; a.obj = obj; a.cls = cls; a.cls_pw = cls_pw; a.obj_pw = obj_pw; a.cp = cp; a.cn = cn;
-  a.anchor_t = anchor_t; a.gr = gr; a.out = out;
+  a.anchor_t = anchor_t; a.gr = gr; a.out = out; a.fl_gamma = fl_gamma; a.slide_state = slide_state;
   a.cell_base[0] = 0;
   a.obj_block_base[0] = 0;
   for (int l = 0; l < nl; ++l) {
@@ -317,6 +381,7 @@ extern "C" int ecsy_yolo_loss(const float* const* p, float* const* gp, const flo
   a.c_cls = reinterpret_cast<float*>(base + w.c_cls);
   a.obj_part = reinterpret_cast<double*>(base + w.obj_part);
   a.lvl = reinterpret_cast<double*>(base + w.lvl);
+  a.thr = reinterpret_cast<float*>(base + w.thr);
   ECSY_CUDA(cudaMemsetAsync(a.stamp, 0, (size_t)a.cell_base[nl] * 4, st));
   for (int l = 0; l < nl; ++l)
     if (a.gp[l]) ECSY_CUDA(cudaMemsetAsync(a.gp[l], 0, (size_t)(a.cell_base[l + 1] - a.cell_base[l]) * a.no * 4, st));
@@ -326,6 +391,13 @@ extern "C" int ecsy_yolo_loss(const float* const* p, float* const* gp, const flo
     ECSY_LAUNCH_CHECK();
     k_loss_level_sums<<<nl, kThreads, 0, st>>>(a);
     ECSY_LAUNCH_CHECK();
+  }
+  if (slide_state != nullptr) {
+    k_loss_slide_ema<<<1, 1, 0, st>>>(a);
+    ECSY_LAUNCH_CHECK();
+  }
+  if (nt > 0) {
+    const unsigned grid = (unsigned)((cands + kThreads - 1) / kThreads);
     k_loss_cand_grad<<<grid, kThreads, 0, st>>>(a);
     ECSY_LAUNCH_CHECK();
   }

@@ -8,12 +8,13 @@ round trips to the host, no per-level index lists, ~10 launches instead of ~150.
 
 Covers the path the shipped hyper-parameter files select (data/hyps/hyp.scratch*.yaml: fl_gamma = 0, slide_ratio = 0):
 SIoU box term, BCE-with-logits objectness / class terms with pos_weight, label smoothing, per-level balance,
-autobalance.  FocalLoss / SlideLoss wrappers raise NotImplementedError instead of silently computing something else.
+autobalance -- and the two wrappers the reference can put around the BCE terms: FocalLoss (fl_gamma > 0) and the
+stateful SlideLoss (slide_ratio > 0; its two EMAs live in a device tensor owned by this object).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -31,10 +32,12 @@ def smooth_BCE(eps=0.1):
 
 def yolo_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torch.Tensor, balance: Sequence[float],
               box: float, obj: float, cls: float, cls_pw: float = 1.0, obj_pw: float = 1.0, cp: float = 1.0,
-              cn: float = 0.0, anchor_t: float = 4.0, gr: float = 1.0, need_grad: bool = True
-              ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+              cn: float = 0.0, anchor_t: float = 4.0, gr: float = 1.0, need_grad: bool = True, fl_gamma: float = 0.0,
+              slide_state: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """-> (out [4 + nl] = (loss, lbox, lobj, lcls, objectness BCE mean per level), grads per level or []).
-    Tensor-level entry over `ecsy_yolo_loss`; the gradients are for an upstream gradient of 1."""
+    Tensor-level entry over `ecsy_yolo_loss`; the gradients are for an upstream gradient of 1.
+    fl_gamma > 0: FocalLoss around the BCE terms; slide_state: a zero-initialised fp32 CUDA tensor [4] that persists
+    across calls (the two SlideLoss EMAs + has-value flags) -- passing it selects SlideLoss and updates it in place."""
     p = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in p]
     _chk_cuda(*p, targets, anchors)
     nl = len(p)
@@ -48,6 +51,12 @@ def yolo_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torch.T
     if targets.dim() != 2 or targets.shape[1] != 6:
         raise ValueError(f"targets must be [nt, 6] = (image, class, x, y, w, h), got {tuple(targets.shape)}")
     dev = p[0].device
+    if slide_state is not None:
+        _chk_cuda(slide_state)
+        if slide_state.dtype != torch.float32 or slide_state.numel() != 4 or not slide_state.is_contiguous():
+            raise ValueError("slide_state must be a contiguous fp32 tensor of 4 elements")
+        if fl_gamma > 0:
+            raise TypeError("SlideLoss and FocalLoss cannot be combined (FocalLoss.forward takes no auto_iou in the reference)")
     tg = targets.detach().to(device=dev, dtype=torch.float32).contiguous()
     an = anchors.detach().to(device=dev, dtype=torch.float32).contiguous()
     nt = tg.shape[0]
@@ -60,11 +69,12 @@ def yolo_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torch.T
     bal = (C.c_float * nl)(*[float(b) for b in balance[:nl]])
     L = _cabi.lib()
     ws = torch.empty(max(L.ecsy_yolo_loss_ws_bytes(nl, N, na, nt, ny, nx), 256), device=dev, dtype=torch.uint8)
-    with _timed("loss", (4 if nt else 1) + nl):
+    with _timed("loss", (4 if nt else 1) + nl + (1 if slide_state is not None else 0)):
         _cabi.check(L.ecsy_yolo_loss(pp, gp, tg.data_ptr() if nt else None, nt, an.data_ptr(), nl, N, na, no - 5, ny, nx,
                                      bal, float(box), float(obj), float(cls), float(cls_pw), float(obj_pw), float(cp),
-                                     float(cn), float(anchor_t), float(gr), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                     _st()), "yolo_loss")
+                                     float(cn), float(anchor_t), float(gr), float(fl_gamma),
+                                     slide_state.data_ptr() if slide_state is not None else None, out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _st()), "yolo_loss")
     return out, grads
 
 
@@ -94,9 +104,12 @@ class ComputeLoss:
     def __init__(self, model, autobalance=False):
         self.sort_obj_iou = False
         h = model.hyp
-        if h.get('fl_gamma', 0.0) > 0 or h.get('slide_ratio', 0.0) > 0:
-            raise NotImplementedError("FocalLoss (fl_gamma > 0) / SlideLoss (slide_ratio > 0) are not implemented on the "
-                                      "device path; the shipped hyp files use plain BCE")
+        self.slide_ratio = h.get('slide_ratio', 0.0)                              # utils/loss.py:144-147
+        self.fl_gamma = h.get('fl_gamma', 0.0)                                    # utils/loss.py:149-152
+        if self.slide_ratio > 0 and self.fl_gamma > 0:
+            raise TypeError("slide_ratio > 0 together with fl_gamma > 0: the reference's FocalLoss.forward takes no auto_iou "
+                            "(utils/loss.py:212 would raise); use one of the two wrappers")
+        self._slide_state = None          # the two SlideLoss EMAs live on the device, created at the first call
         self.cp, self.cn = smooth_BCE(eps=h.get('label_smoothing', 0.0))          # utils/loss.py:142
         m = model.module if hasattr(model, 'module') and hasattr(model.module, 'model') else model   # de-parallel (:155)
         det = m.model[-1]
@@ -109,7 +122,12 @@ class ComputeLoss:
     def __call__(self, p, targets):
         h = self.hyp
         cfg = dict(balance=list(self.balance), box=h['box'], obj=h['obj'], cls=h['cls'], cls_pw=h['cls_pw'],
-                   obj_pw=h['obj_pw'], cp=self.cp, cn=self.cn, anchor_t=h['anchor_t'], gr=self.gr)
+                   obj_pw=h['obj_pw'], cp=self.cp, cn=self.cn, anchor_t=h['anchor_t'], gr=self.gr,
+                   fl_gamma=self.fl_gamma if self.fl_gamma > 0 else 0.0)
+        if self.slide_ratio > 0:
+            if self._slide_state is None or self._slide_state.device != p[0].device:
+                self._slide_state = torch.zeros(4, device=p[0].device, dtype=torch.float32)
+            cfg["slide_state"] = self._slide_state
         loss, out = _YoloLossFn.apply(cfg, targets, self.anchors, *p)
         if self.autobalance:                                                      # utils/loss.py:224-228 (host read)
             obji = out[4:4 + self.nl].tolist()

@@ -253,12 +253,16 @@ int ecsy_xty_bf16(const void* p_hi, const void* p_lo, const void* q_hi, const vo
  * w, h) normalised; anchors: device [nl][na][2] in grid units (Detect.anchors, models/yolo.py:230); ny / nx / balance:
  * host arrays [nl].  out: device [4 + nl] = loss (already times the batch size, :231), lbox, lobj, lcls (the
  * reference's loss_items), then the objectness BCE mean of every level (what autobalance reads, :224).
- * Duplicate (image, anchor, cell) matches resolve to the last one in the reference's row order (:205). */
+ * Duplicate (image, anchor, cell) matches resolve to the last one in the reference's row order (:205).
+ * fl_gamma > 0: the BCE terms are wrapped in FocalLoss (:80-106, alpha 0.25).  slide_state != null: they are wrapped in
+ * SlideLoss (:38-76); slide_state is a caller-owned, zero-initialised DEVICE array [4] = (ema of the class criterion,
+ * ema of the objectness criterion, has-value flags) that the call reads and updates, like the `ema` attributes of the
+ * reference's two SlideLoss objects.  The two wrappers exclude each other (in the reference too). */
 size_t ecsy_yolo_loss_ws_bytes(int nl, int64_t N, int na, int64_t nt, const int* ny, const int* nx);
 int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets, int64_t nt, const float* anchors,
                    int nl, int64_t N, int na, int nc, const int* ny, const int* nx, const float* balance, float box,
                    float obj, float cls, float cls_pw, float obj_pw, float cp, float cn, float anchor_t, float gr,
-                   float* out, void* ws, size_t ws_bytes, void* stream);
+                   float fl_gamma, float* slide_state, float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Stack-B training loss, forward + gradient in one call: replaces ComputeLoss.__call__ of
  * utils/loss_tal.py:162-215 with TaskAlignedAssigner (utils/tal/assigner.py:51-179; topk 10, alpha 0.5, beta 6, CIoU

@@ -37,6 +37,9 @@ def main():
         det = types.SimpleNamespace(na=anchors.shape[1], nc=spec["nc"], nl=anchors.shape[0], anchors=anchors,
                                     stride=torch.tensor([16.0, 32.0, 64.0][:anchors.shape[0]]))
         crit = ComputeLoss(_Holder(det, dict(spec["hyp"])))
+        for extra in range(spec.get("calls", 1) - 1):          # stateful criteria (SlideLoss EMA): earlier calls first
+            pre = S.loss_inputs(dict(spec, seed=spec["seed"] + 50 + extra))
+            crit([x.clone().requires_grad_(True) for x in pre["p"]], pre["targets"].clone())
         p = [x.clone().requires_grad_(True) for x in inp["p"]]
         loss, items = crit(p, inp["targets"].clone())
         (loss * inp["gout"]).sum().backward()

@@ -85,13 +85,47 @@ def siou(pb: torch.Tensor, tb: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
     return iou - torch.pow(0.5 * (dist + shape) + eps, 1)
 
 
-def compute_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torch.Tensor, hyp: dict, gr: float = 1.0):
+def _slide_weight(true: torch.Tensor, ema: float) -> torch.Tensor:
+    """SlideLoss.forward's modulating weight (utils/loss.py:61-69): 1 below ema - 0.1, exp(1 - ema) up to ema,
+    exp(1 - true) from ema on."""
+    w = torch.ones_like(true)
+    w = torch.where((true > ema - 0.1) & (true < ema), torch.full_like(true, math.exp(1.0 - ema)), w)
+    return torch.where(true >= ema, torch.exp(-(true - 1.0)), w)
+
+
+def _elem_loss(x, t, pw, kind, *, focal_gamma=0.0, slide=None, which=None, auto_iou=0.5):
+    """The wrapped criterion of utils/loss.py:138-152 with reduction 'mean': BCEWithLogits, optionally inside SlideLoss
+    (:38-76, stateful: `slide[which]` is its `ema`, updated on every call with the new value weighted by alpha = 0.999
+    as the reference does) or FocalLoss (:80-106, alpha 0.25)."""
+    loss = F.binary_cross_entropy_with_logits(x, t, pos_weight=pw, reduction="none")
+    if slide is not None:
+        a = max(float(auto_iou), 0.2)
+        ema = slide.get(which)
+        ema = a if ema is None else float(torch.tensor(0.999, dtype=torch.float32) * torch.tensor(a, dtype=torch.float32)
+                                            + torch.tensor(1 - 0.999) * torch.tensor(ema, dtype=torch.float32))
+        slide[which] = ema
+        loss = loss * _slide_weight(t, ema)
+    elif focal_gamma > 0:
+        prob = torch.sigmoid(x)
+        p_t = t * prob + (1 - t) * (1 - prob)
+        loss = loss * (t * 0.25 + (1 - t) * 0.75) * (1.0 - p_t) ** focal_gamma
+    return loss.mean()
+
+
+def compute_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torch.Tensor, hyp: dict, gr: float = 1.0,
+                 slide_state: dict = None):
     """-> (loss [1], loss_items [3] = (lbox, lobj, lcls) detached, per-level match counts, per-level objectness BCE).
-    p[i]: [N, na, ny, nx, 5 + nc] raw outputs, anchors [nl, na, 2] in grid units, targets [nt, 6]."""
+    p[i]: [N, na, ny, nx, 5 + nc] raw outputs, anchors [nl, na, 2] in grid units, targets [nt, 6].
+    slide_state: the two SlideLoss EMAs ({'cls': .., 'obj': ..}, empty before the first call) when hyp['slide_ratio'] > 0."""
     nl, nc = len(p), p[0].shape[-1] - 5
     cp, cn = smooth_bce(hyp.get("label_smoothing", 0.0))
-    if hyp.get("fl_gamma", 0.0) > 0 or hyp.get("slide_ratio", 0.0) > 0:
-        raise NotImplementedError("focal / slide loss variants are not on the shipped configuration's path")
+    use_slide = hyp.get("slide_ratio", 0.0) > 0
+    gamma = hyp.get("fl_gamma", 0.0)
+    if use_slide and gamma > 0:
+        raise TypeError("the reference cannot combine SlideLoss and FocalLoss (FocalLoss.forward takes no auto_iou)")
+    if use_slide and slide_state is None:
+        raise ValueError("slide_ratio > 0 needs the caller's persistent slide_state dict")
+    crit = dict(focal_gamma=gamma, slide=slide_state if use_slide else None)
     balance = BALANCE.get(nl, BALANCE_DEFAULT)
     cls_pw, obj_pw = torch.tensor([hyp["cls_pw"]]), torch.tensor([hyp["obj_pw"]])
     lbox, lobj, lcls = torch.zeros(1), torch.zeros(1), torch.zeros(1)
@@ -110,6 +144,7 @@ def compute_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torc
             pwh = (ps[:, 2:4].sigmoid() * 2) ** 2 * anchors[i][a]
             iou = siou(torch.cat((pxy, pwh), 1), cand["tbox"][sel])
             lbox = lbox + (1.0 - iou).mean()
+            auto_iou = float(iou.detach().mean())
             score = iou.detach().clamp(0)
             flat = ((b * na + a) * ny + gj) * nx + gi
             last = torch.full((tobj.numel(),), -1, dtype=torch.long).scatter_reduce(
@@ -119,8 +154,8 @@ def compute_loss(p: Sequence[torch.Tensor], targets: torch.Tensor, anchors: torc
             if nc > 1:
                 t = torch.full_like(ps[:, 5:], cn)
                 t[torch.arange(n), cand["c"][sel]] = cp
-                lcls = lcls + F.binary_cross_entropy_with_logits(ps[:, 5:], t, pos_weight=cls_pw)
-        obji = F.binary_cross_entropy_with_logits(pi[..., 4], tobj, pos_weight=obj_pw)
+                lcls = lcls + _elem_loss(ps[:, 5:], t, cls_pw, "cls", which="cls", auto_iou=auto_iou, **crit)
+        obji = _elem_loss(pi[..., 4], tobj, obj_pw, "obj", which="obj", auto_iou=auto_iou if n else 0.5, **crit)
         objs.append(float(obji.detach()))
         lobj = lobj + obji * balance[i]
     lbox = lbox * hyp["box"]

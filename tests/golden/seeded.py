@@ -373,6 +373,12 @@ LOSS_CASES = {
                             hyp=dict(_HYP, box=0.0375, obj=0.7, cls=0.3, cls_pw=1.5, obj_pw=0.8, anchor_t=3.0,
                                      label_smoothing=0.1)),
     "loss_border": dict(N=2, nc=3, grids=[(8, 12), (4, 6)], anchors=_ANCH2, nt=32, seed=806, hyp=_HYP, border=True),
+    # the wrapped criteria (utils/loss.py:38-106): FocalLoss, and the stateful SlideLoss over two consecutive calls
+    "loss_focal": dict(N=3, nc=5, grids=[(10, 10), (5, 5)], anchors=_ANCH2, nt=18, seed=808, hyp=dict(_HYP, fl_gamma=1.5)),
+    "loss_slide": dict(N=3, nc=5, grids=[(10, 10), (5, 5)], anchors=_ANCH2, nt=18, seed=809, hyp=dict(_HYP, slide_ratio=1.0),
+                       calls=2),
+    "loss_slide_mixed": dict(N=2, nc=4, grids=[(8, 8), (4, 4)], anchors=[_ANCH2[0], [[30.0, 30.0], [40.0, 40.0], [50.0, 50.0]]],
+                             nt=14, seed=810, hyp=dict(_HYP, slide_ratio=1.0), calls=3),   # level 1 never matches: auto_iou 0.5
     "loss_unmatched": dict(N=2, nc=3, grids=[(8, 8), (4, 4)], anchors=_ANCH2, nt=6, seed=807, hyp=_HYP, tiny_boxes=True),
 }
 

@@ -217,6 +217,9 @@ def test_compute_loss_golden(name):
     spec = S.LOSS_CASES[name]
     inp = S.loss_inputs(spec)
     crit = E.loss.ComputeLoss(_LossHolder(inp["anchors"], spec["nc"], spec["hyp"]))
+    for extra in range(spec.get("calls", 1) - 1):              # SlideLoss keeps an EMA across calls (utils/loss.py:50-59)
+        pre = S.loss_inputs(dict(spec, seed=spec["seed"] + 50 + extra))
+        crit([x.cuda() for x in pre["p"]], pre["targets"].cuda())
     p = [x.cuda().requires_grad_(True) for x in inp["p"]]
     loss, items = crit(p, inp["targets"].cuda())
     assert loss.shape == (1,) and items.shape == (3,) and not items.requires_grad
@@ -266,8 +269,8 @@ def test_compute_loss_full_size_vs_oracle():
 
 def test_compute_loss_rejects_unsupported_variants():
     E = ecsy()
-    with pytest.raises(NotImplementedError):
-        E.loss.ComputeLoss(_LossHolder(torch.tensor(S._ANCH2), 3, dict(S._HYP, fl_gamma=1.5)))
+    with pytest.raises(TypeError):      # the reference cannot combine the two wrappers either
+        E.loss.ComputeLoss(_LossHolder(torch.tensor(S._ANCH2), 3, dict(S._HYP, fl_gamma=1.5, slide_ratio=1.0)))
     with pytest.raises(ValueError):
         E.loss.yolo_loss([torch.zeros(1, 3, 4, 4, 8).cuda()], torch.zeros(2, 5).cuda(), torch.ones(1, 3, 2).cuda(),
                          balance=[4.0], box=0.05, obj=1.0, cls=0.5)

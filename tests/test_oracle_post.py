@@ -79,8 +79,12 @@ def test_compute_loss_oracle(name):
     spec = S.LOSS_CASES[name]
     inp = S.loss_inputs(spec)
     assert abs(S.checksum(*inp["p"], inp["targets"]) - gold["chk"]) <= 1e-6 * abs(gold["chk"])
+    state = {}
+    for extra in range(spec.get("calls", 1) - 1):              # SlideLoss keeps an EMA across calls
+        pre = S.loss_inputs(dict(spec, seed=spec["seed"] + 50 + extra))
+        LO.compute_loss(pre["p"], pre["targets"], pre["anchors"], spec["hyp"], slide_state=state)
     p = [x.clone().requires_grad_(True) for x in inp["p"]]
-    loss, items, counts, _ = LO.compute_loss(p, inp["targets"], inp["anchors"], spec["hyp"])
+    loss, items, counts, _ = LO.compute_loss(p, inp["targets"], inp["anchors"], spec["hyp"], slide_state=state)
     assert counts == gold["n"]
     assert torch.allclose(loss, gold["loss"], rtol=1e-6, atol=1e-7)
     assert torch.allclose(items, gold["items"], rtol=1e-6, atol=1e-7)
