@@ -95,15 +95,7 @@ __device__ __forceinline__ float criterion(const LossArgs& a, float x, float t, 
     dx *= w;
     return l * w;
   }
-  if (a.fl_gamma > 0.f) {
-    const float p = sigmoidf_(x);
-    const float base = 1.f - (t * p + (1.f - t) * (1.f - p));
-    const float af = t * 0.25f + (1.f - t) * 0.75f;
-    const float mod = powf(base, a.fl_gamma);
-    const float dmod = -a.fl_gamma * powf(base, a.fl_gamma - 1.f) * (2.f * t - 1.f) * p * (1.f - p);
-    dx = af * (dx * mod + l * dmod);
-    return l * af * mod;
-  }
+  if (a.fl_gamma > 0.f) return focal_wrap(x, t, a.fl_gamma, l, dx);
   return l;
 }
 

@@ -73,6 +73,18 @@ __device__ __forceinline__ float bce(float x, float t, float pw, float& dx) {
   return (1.f - t) * x - lw * ls;
 }
 
+// FocalLoss around an element BCE (utils/loss.py:80-106, utils/loss_tal.py:32-60; alpha 0.25):
+// bce * (t*0.25 + (1-t)*0.75) * (1 - p_t)^gamma with p_t = t*p + (1-t)*(1-p); l / dx: the BCE value and derivative.
+__device__ __forceinline__ float focal_wrap(float x, float t, float gamma, float l, float& dx) {
+  const float p = sigmoidf_(x);
+  const float base = 1.f - (t * p + (1.f - t) * (1.f - p));
+  const float af = t * 0.25f + (1.f - t) * 0.75f;
+  const float mod = powf(base, gamma);
+  const float dmod = -gamma * powf(base, gamma - 1.f) * (2.f * t - 1.f) * p * (1.f - p);
+  dx = af * (dx * mod + l * dmod);
+  return l * af * mod;
+}
+
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* sh) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

@@ -38,7 +38,7 @@ struct TalArgs {
   const float* targets;
   int nl, nc, no, A;
   int64_t N, nt;
-  float img_w, img_h, cls_pw, gain_box, gain_cls, gain_dfl;
+  float img_w, img_h, cls_pw, gain_box, gain_cls, gain_dfl, fl_gamma;
   // workspace
   float* pbox;       // [N][A][4] xyxy, grid units
   int* img_off;      // [N + 1]
@@ -326,7 +326,10 @@ __global__ void __launch_bounds__(kThreads) k_tal_loss(const TalArgs a) {
     float acc = 0.f;
     for (int c = 0; c < a.nc; ++c) {
       float dx;
-      acc += bce(p[(4 * kReg + c) * cs], c == label ? norm : 0.f, a.cls_pw, dx);
+      const float xv = p[(4 * kReg + c) * cs], tv = c == label ? norm : 0.f;
+      float l = bce(xv, tv, a.cls_pw, dx);
+      if (a.fl_gamma > 0.f) l = focal_wrap(xv, tv, a.fl_gamma, l, dx);       // FocalLoss(BCEcls, g), utils/loss_tal.py:116-119
+      acc += l;
       if (g) g[(4 * kReg + c) * cs] = a.gain_cls * inv * dx;
     }
     s_cls = (double)acc;
@@ -439,8 +442,8 @@ extern "C" size_t ecsy_tal_loss_ws_bytes(int nl, int64_t N, int64_t nt, const in
 
 extern "C" int ecsy_tal_loss(const float* const* feats, float* const* gfeats, const float* targets, int64_t nt, int nl,
                              int64_t N, int nc, const int* ny, const int* nx, const float* strides, float cls_pw,
-                             float gain_box, float gain_cls, float gain_dfl, float* out, void* ws, size_t ws_bytes,
-                             void* stream) {
+                             float gain_box, float gain_cls, float gain_dfl, float fl_gamma, float* out, void* ws,
+                             size_t ws_bytes, void* stream) {
   ECSY_CHECK_ARG(nl >= 1 && nl <= kMaxLevels, "tal_loss: 1..%d detection levels, got %d", kMaxLevels, nl);
   ECSY_CHECK_ARG(feats && ny && nx && strides && out, "tal_loss: null argument");
   ECSY_CHECK_ARG(N >= 1 && nc >= 1 && nt >= 0 && (nt == 0 || targets), "tal_loss: bad sizes N=%lld nc=%d nt=%lld",
@@ -448,7 +451,7 @@ extern "C" int ecsy_tal_loss(const float* const* feats, float* const* gfeats, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   TalArgs a{};
   a.nl = nl; a.nc = nc; a.no = nc + 4 * kReg; a.N = N; a.nt = nt; a.targets = targets; a.out = out;
-  a.cls_pw = cls_pw; a.gain_box = gain_box; a.gain_cls = gain_cls; a.gain_dfl = gain_dfl;
+  a.cls_pw = cls_pw; a.gain_box = gain_box; a.gain_cls = gain_cls; a.gain_dfl = gain_dfl; a.fl_gamma = fl_gamma;
   a.a_base[0] = 0;
   for (int l = 0; l < nl; ++l) {
     ECSY_CHECK_ARG(feats[l] && ny[l] >= 1 && nx[l] >= 1 && strides[l] > 0.f, "tal_loss: level %d: bad grid / stride", l);

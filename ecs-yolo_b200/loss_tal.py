@@ -6,7 +6,7 @@ C-ABI call (`ecsy_tal_loss`): no per-image Python loop, no padded [batch, max la
     loss, loss_items = compute_loss(pred, targets)          # pred: list of [N, 64 + nc, ny, nx]; targets [nt, 6] (GPU)
     loss.backward()
 
-fl_gamma > 0 (FocalLoss) and use_dfl=False raise NotImplementedError.  The assigner's hyper-parameters are read from
+fl_gamma > 0 wraps the class BCE in FocalLoss like the reference; use_dfl=False raises NotImplementedError.  The assigner's hyper-parameters are read from
 the YOLOM / YOLOA / YOLOB environment variables like the reference (:134-137), but only its defaults (10, 0.5, 6.0) are
 built into the kernel.
 """
@@ -26,7 +26,8 @@ GAINS = (7.5, 0.5, 1.5)      # box, cls, dfl (utils/loss_tal.py:210-212)
 
 
 def tal_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides: Sequence[float], cls_pw: float = 1.0,
-             gains: Sequence[float] = GAINS, need_grad: bool = True) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+             gains: Sequence[float] = GAINS, need_grad: bool = True, fl_gamma: float = 0.0
+             ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """-> (out [6] = (loss, box, cls, dfl, foreground anchors, target_scores.sum()), gradients per level or [])."""
     feats = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in feats]
     _chk_cuda(*feats, targets)
@@ -54,7 +55,8 @@ def tal_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides: Sequ
     ws = torch.empty(max(L.ecsy_tal_loss_ws_bytes(nl, N, nt, ny, nx), 256), device=dev, dtype=torch.uint8)
     with _timed("loss", 9 if nt else 7):
         _cabi.check(L.ecsy_tal_loss(fp, gp, tg.data_ptr() if nt else None, nt, nl, N, no - 4 * REG_MAX, ny, nx, st,
-                                    float(cls_pw), float(gains[0]), float(gains[1]), float(gains[2]), out.data_ptr(),
+                                    float(cls_pw), float(gains[0]), float(gains[1]), float(gains[2]), float(fl_gamma),
+                                    out.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _st()), "tal_loss")
     return out, grads
 
@@ -81,8 +83,7 @@ class ComputeLoss:
 
     def __init__(self, model, use_dfl=True):
         h = model.hyp
-        if h.get("fl_gamma", 0.0) > 0:
-            raise NotImplementedError("FocalLoss (fl_gamma > 0) is not implemented on the device path")
+        self.fl_gamma = float(h.get("fl_gamma", 0.0))        # > 0: FocalLoss around the class BCE (:116-119)
         if not use_dfl:
             raise NotImplementedError("use_dfl=False is not implemented on the device path")
         if (int(os.getenv('YOLOM', 10)), float(os.getenv('YOLOA', 0.5)), float(os.getenv('YOLOB', 6.0))) != (10, 0.5, 6.0):
@@ -99,6 +100,6 @@ class ComputeLoss:
 
     def __call__(self, p, targets, img=None, epoch=0):
         feats = p[1] if isinstance(p, tuple) else p
-        cfg = dict(strides=self._strides, cls_pw=self.hyp["cls_pw"])
+        cfg = dict(strides=self._strides, cls_pw=self.hyp["cls_pw"], fl_gamma=max(self.fl_gamma, 0.0))
         loss, out = _TalLossFn.apply(cfg, targets, *feats)
         return loss, out[1:4]

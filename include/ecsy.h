@@ -267,7 +267,8 @@ int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets
 /* ---- Stack-B training loss, forward + gradient in one call: replaces ComputeLoss.__call__ of
  * utils/loss_tal.py:162-215 with TaskAlignedAssigner (utils/tal/assigner.py:51-179; topk 10, alpha 0.5, beta 6, CIoU
  * overlaps), BCE class term with pos_weight, the box term as the reference evaluates it (GIoU: utils/metrics2.py:282
- * keeps the requested SIoU branch unreachable) and the distribution focal loss, reg_max = 16, fl_gamma = 0.
+ * keeps the requested SIoU branch unreachable) and the distribution focal loss, reg_max = 16; fl_gamma > 0 wraps the
+ * class BCE in FocalLoss (utils/loss_tal.py:32-60, 116-119).
  * feats / gfeats: HOST arrays of nl DEVICE pointers to the raw DDetect training outputs [N][64 + nc][ny_l][nx_l]
  * (models/yolo_snn.py:117-119) and their gradients (gfeats or gfeats[l] may be null: forward only; otherwise
  * OVERWRITTEN, upstream gradient 1).  targets: device [nt][6] = (image, class, cx, cy, w, h) normalised; ny / nx /
@@ -277,7 +278,7 @@ int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets
 size_t ecsy_tal_loss_ws_bytes(int nl, int64_t N, int64_t nt, const int* ny, const int* nx);
 int ecsy_tal_loss(const float* const* feats, float* const* gfeats, const float* targets, int64_t nt, int nl, int64_t N,
                   int nc, const int* ny, const int* nx, const float* strides, float cls_pw, float gain_box,
-                  float gain_cls, float gain_dfl, float* out, void* ws, size_t ws_bytes, void* stream);
+                  float gain_cls, float gain_dfl, float fl_gamma, float* out, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def main():
         inp = S.tal_inputs(spec)
         nl = len(spec["grids"])
         det = types.SimpleNamespace(nl=nl, nc=spec["nc"], no=64 + spec["nc"], reg_max=16, stride=inp["strides"])
-        hyp = dict(cls_pw=spec.get("cls_pw", 1.0), fl_gamma=0.0, label_smoothing=spec.get("smooth", 0.0))
+        hyp = dict(cls_pw=spec.get("cls_pw", 1.0), fl_gamma=spec.get("fl_gamma", 0.0), label_smoothing=spec.get("smooth", 0.0))
         crit = ComputeLoss(_Holder(det, hyp))
         fg = {}
         orig = crit.assigner.forward

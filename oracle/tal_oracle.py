@@ -94,7 +94,7 @@ def assign_image(scores, boxes_px, pts_px, labels, gts):
     return gt_idx, fg, norm
 
 
-def compute_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides, cls_pw: float = 1.0):
+def compute_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides, cls_pw: float = 1.0, fl_gamma: float = 0.0):
     """-> (loss [1]-shaped scalar tensor, loss_items [3] = (box, cls, dfl) detached, number of foreground anchors)."""
     N, no = feats[0].shape[:2]
     nc = no - 4 * REG_MAX
@@ -121,8 +121,12 @@ def compute_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides, 
                 t_score[b, torch.arange(A), mine[gt_idx, 1].long()] = norm * fg
             fg_all[b] = fg
     tss = max(t_score.sum(), 1)                                                         # (:192)
-    lcls = F.binary_cross_entropy_with_logits(cls_logits, t_score, pos_weight=torch.tensor([cls_pw]),
-                                              reduction="none").sum() / tss
+    bce = F.binary_cross_entropy_with_logits(cls_logits, t_score, pos_weight=torch.tensor([cls_pw]), reduction="none")
+    if fl_gamma > 0:                                                                    # FocalLoss, utils/loss_tal.py:32-60
+        prob = cls_logits.sigmoid()
+        p_t = t_score * prob + (1 - t_score) * (1 - prob)
+        bce = bce * (t_score * 0.25 + (1 - t_score) * 0.75) * (1.0 - p_t) ** fl_gamma
+    lcls = bce.sum() / tss
     lbox, ldfl = torch.zeros(()), torch.zeros(())
     if fg_all.any():
         w = t_score.sum(-1)[fg_all]

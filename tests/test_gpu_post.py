@@ -282,7 +282,8 @@ class _TalHolder(torch.nn.Module):
         super().__init__()
         import types
         self.w = torch.nn.Parameter(torch.zeros(1))
-        self.hyp = dict(cls_pw=spec.get("cls_pw", 1.0), fl_gamma=0.0, label_smoothing=spec.get("smooth", 0.0))
+        self.hyp = dict(cls_pw=spec.get("cls_pw", 1.0), fl_gamma=spec.get("fl_gamma", 0.0),
+                        label_smoothing=spec.get("smooth", 0.0))
         self.model = [types.SimpleNamespace(nl=len(strides), nc=spec["nc"], no=64 + spec["nc"], reg_max=16, stride=strides)]
 
 
@@ -298,7 +299,7 @@ def test_tal_loss_golden(name):
     feats = [x.cuda().requires_grad_(True) for x in inp["feats"]]
     loss, items = crit(feats, inp["targets"].cuda())
     out, _ = E.loss_tal.tal_loss([x.detach() for x in feats], inp["targets"].cuda(), spec["strides"],
-                                 spec.get("cls_pw", 1.0), need_grad=False)
+                                 spec.get("cls_pw", 1.0), need_grad=False, fl_gamma=spec.get("fl_gamma", 0.0))
     assert int(out[4]) == gold["fg"], (int(out[4]), gold["fg"])
     assert abs(float(out[5]) - gold["score_sum"]) <= 1e-5 * max(gold["score_sum"], 1.0)
     assert loss.dim() == 0 and items.shape == (3,) and not items.requires_grad
