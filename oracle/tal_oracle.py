@@ -1,11 +1,12 @@
 """CPU oracle for the Stack-B training loss -- TEST INFRASTRUCTURE ONLY.
 
-A plain-torch restatement of `ComputeLoss.__call__` of utils/loss_tal.py:105-215 (fl_gamma = 0, DFL on): anchor points
+A plain-torch restatement of `ComputeLoss.__call__` of utils/loss_tal.py:105-215 (DFL on): anchor points
 (utils/tal/anchor_generator.py:8-21), DFL box decode (:154-160), `TaskAlignedAssigner` (utils/tal/assigner.py:51-179,
-topk 10, alpha 0.5, beta 6; CIoU overlaps from utils/metrics2.py:254-289), BCE class term, the box term -- requested
-as SIoU, evaluated as GIoU by utils/metrics2.py:279-311, see box_term_iou -- and distribution focal loss (utils/loss_tal.py:63-103).  It is written per image over the
-image's OWN label list (the reference pads every image to the longest list; padded rows never become positive) because
-that is the formulation the CUDA kernels use.
+topk 10, alpha 0.5, beta 6; CIoU overlaps from utils/metrics2.py:254-289), BCE class term (optionally inside FocalLoss,
+:32-60), the box term -- requested as SIoU, evaluated as GIoU by utils/metrics2.py:279-311, see box_term_iou -- and
+the distribution focal loss (:63-103).  It is written per image over the image's OWN label list (the reference pads
+every image to the longest list; padded rows never become positive) because that is the formulation the CUDA kernels
+use.
 Where the reference leaves a choice open -- `torch.topk` among equal (zero) metrics, `argmax` among equal overlaps -- the
 lowest index wins here.  Pinned by tests/test_oracle_post.py against fixtures made by the UNMODIFIED reference
 (oracle/gen_golden_tal.py -> tests/golden/post_tal.pt).  Only tests/, smoke() and bench.py's CPU legs may import this.
