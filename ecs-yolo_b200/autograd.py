@@ -375,6 +375,11 @@ class ConvSiluFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mod, x_ref, *params):
+        if not bool(getattr(mod.act.actFun, "inplace", False)):
+            # ecsy_lif_silu_bwd differentiates the in-place recurrence (mem <- silu(mem) feeds the next step, what
+            # Model.__init__ sets up, models/yolo.py:237-239); the out-of-place variant has a different gradient
+            raise NotImplementedError("Conv (mem_update(act=True)): the BPTT backward is implemented for SiLU(inplace=True) "
+                                      "only, the setting every reference model runs with")
         a = Act.from_ref(x_ref).full()
         y = mod.conv.conv_real(a)
         scale, shift, mean, rstd = bn_train_fwd(mod.bn, y)
@@ -456,6 +461,13 @@ class ConcatFn(torch.autograd.Function):
 
 
 def wants_grad(mod, *tensors) -> bool:
-    if not (mod.training and torch.is_grad_enabled()):
+    if not torch.is_grad_enabled():
+        return False
+    if not mod.training:
+        # the backward chains are built for training-mode tdBN (batch statistics); an eval-mode forward whose INPUT asks
+        # for a gradient would silently come back without a grad_fn -- fail where the cause is
+        if any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+            raise RuntimeError(f"{type(mod).__name__}: autograd through an eval-mode (running-statistics) forward is not "
+                               "implemented; call .train(), or run under torch.no_grad() / detach the input")
         return False
     return any(t.requires_grad for t in tensors if torch.is_tensor(t)) or any(p.requires_grad for p in mod.parameters())

@@ -31,7 +31,7 @@ _caches: "weakref.WeakKeyDictionary[nn.Module, dict]" = weakref.WeakKeyDictionar
 
 
 def _cached(mod: nn.Module, key: str, tensors, builder):
-    ver = tuple((t.data_ptr(), t._version) for t in tensors if t is not None) + (F_.get_splits(),)
+    ver = tuple((t.data_ptr(), t._version) for t in tensors if t is not None) + (F_.get_splits(), F_.weights_epoch())
     c = _caches.setdefault(mod, {})
     ent = c.get(key)
     if ent is not None and ent[0] == ver:
@@ -479,6 +479,8 @@ class Conv_7(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         a = Act.from_ref(x)
+        if self.conv.weight.numel() != a.T:   # the reference's Conv3d raises a shape error here (models/common.py:549-562)
+            raise RuntimeError(f"Conv_7: built for time_window={self.conv.weight.numel()} but the input has T={a.T} steps")
         out = F_.tsum(a, self.conv.weight.detach().reshape(-1).contiguous(), 1.0)
         return out.permute(0, 3, 1, 2)
 

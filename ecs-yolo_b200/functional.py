@@ -66,6 +66,16 @@ class _timed:
         return False
 
 
+def bump_weights_epoch() -> None:
+    """Called by anything that rewrites parameters behind torch's back (the fused optimizer writes through raw pointers):
+    part of every derived-weight cache key (common._cached, ops._cached)."""
+    _state["weights_epoch"] = _state.get("weights_epoch", 0) + 1
+
+
+def weights_epoch() -> int:
+    return _state.get("weights_epoch", 0)
+
+
 def set_precision(mode: str) -> None:
     """'parity': weights as bf16 hi+lo pairs (2 MMAs, ~fp32 weights; spikes are exact in bf16);
     'fast': single bf16 plane."""

@@ -27,7 +27,7 @@ _wcache: dict = {}
 
 
 def _cached(kind: str, tensors, builder):
-    key = (kind, F_.get_splits(), F_._state["conv_ts"]) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    key = (kind, F_.get_splits(), F_._state["conv_ts"], F_.weights_epoch()) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
     v = _wcache.get(key)
     if v is None:
         if len(_wcache) > 512:

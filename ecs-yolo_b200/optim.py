@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
+from . import functional as F_
 from .functional import _p, _st, _timed
 
 
@@ -96,8 +97,14 @@ class SGDNesterovEMA:
             ema=i64(emas), numel=i64([v.numel() for v in vals]),
             group=torch.tensor(groups, dtype=torch.int32, device=dev),
             chunk_tensor=torch.tensor(ct, dtype=torch.int32, device=dev), chunk_off=i64(co), n_chunks=len(ct))
-        self._grad_host = torch.zeros(len(vals), dtype=torch.int64).pin_memory()
-        self._grad_dev = torch.zeros(len(vals), dtype=torch.int64, device=dev)
+        # two pinned staging buffers + upload events: the host may run a step ahead of the GPU, so the table the
+        # in-flight H2D copy of step n reads must not be rewritten by step n+1 (the buffer of step n-1 is reused only
+        # after ITS copy has executed)
+        self._grad_host = [torch.zeros(len(vals), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._grad_dev = [torch.zeros(len(vals), dtype=torch.int64, device=dev) for _ in range(2)]
+        self._grad_evt = [None, None]
+        self._flip = 0
+        self._ema_vals = [esd[k] for k in sd if k in esd and esd[k].dtype.is_floating_point]
 
     def zero_grad(self, set_to_none: bool = True):
         for g in self.param_groups:
@@ -121,8 +128,15 @@ class SGDNesterovEMA:
             if g is not None and (g.dtype != torch.float32 or not g.is_contiguous() or g.device != v.device):
                 raise RuntimeError("SGDNesterovEMA: gradients must be contiguous fp32 tensors on the parameter's device")
             ptrs.append(g.data_ptr() if g is not None else 0)
-        self._grad_host.copy_(torch.tensor(ptrs, dtype=torch.int64))
-        self._grad_dev.copy_(self._grad_host, non_blocking=True)
+        b = self._flip
+        self._flip ^= 1
+        if self._grad_evt[b] is not None:
+            self._grad_evt[b].synchronize()
+        self._grad_host[b].copy_(torch.tensor(ptrs, dtype=torch.int64))
+        self._grad_dev[b].copy_(self._grad_host[b], non_blocking=True)
+        self._grad_evt[b] = torch.cuda.Event()
+        self._grad_evt[b].record()
+        grad_dev = self._grad_dev[b]
         d = 0.0
         do_ema = bool(update_ema and self.ema is not None)
         if do_ema:
@@ -134,7 +148,14 @@ class SGDNesterovEMA:
         wds = (C.c_float * n_g)(*[float(g["weight_decay"]) for g in self.param_groups])
         with _timed("sgd_ema", 1):
             _cabi.check(_cabi.lib().ecsy_sgd_ema_step(
-                _p(t["val"]), _p(self._grad_dev), _p(t["mom"]), _p(t["ema"]), _p(t["numel"]), _p(t["group"]),
+                _p(t["val"]), _p(grad_dev), _p(t["mom"]), _p(t["ema"]), _p(t["numel"]), _p(t["group"]),
                 len(self._vals), _p(t["chunk_tensor"]), _p(t["chunk_off"]), t["n_chunks"], lrs, wds, n_g,
                 float(self.momentum), 1 if self.nesterov else 0, 0, 1 if do_ema else 0, float(d), float(1 - d), _st()),
                 "sgd_ema_step")
+        # The kernel writes parameters / EMA tensors through raw pointers: tell torch (version counters) and the
+        # derived-weight caches (packed bf16 conv / spread weights, folded tdBN affines keyed on data_ptr + _version)
+        # that every one of them changed.
+        torch._C._increment_version(self._vals)
+        if do_ema and self._ema_vals:
+            torch._C._increment_version(self._ema_vals)
+        F_.bump_weights_epoch()

@@ -56,6 +56,8 @@ class Detect(nn.Module):
         for i in range(self.nl):
             a = Act.from_ref(x[i])
             wt = self.w[i].conv.weight
+            if wt.numel() != a.T:   # the reference's Conv3d(T -> 1) raises a shape error (models/common.py:549-562)
+                raise RuntimeError(f"Detect: built for time_window={wt.numel()} but the input has T={a.T} steps")
             tw = _cached(self.w[i], "tw", (wt,), lambda: wt.detach().reshape(-1).float().contiguous())
             feat = F_.tsum(a, tw, 1.0)                                   # [N,H,W,C]
             conv = self.m[i]
@@ -76,6 +78,9 @@ class Detect(nn.Module):
         out = []
         for i in range(self.nl):
             xi = x[i]
+            if self.w[i].conv.weight.numel() != xi.shape[0]:
+                raise RuntimeError(f"Detect: built for time_window={self.w[i].conv.weight.numel()} but the input has "
+                                   f"T={xi.shape[0]} steps")
             wt = self.w[i].conv.weight.reshape(-1, 1, 1, 1, 1)
             feat = (xi * wt).sum(0)
             y = tF.conv2d(feat, self.m[i].weight, None) + self.m[i].bias.view(1, -1, 1, 1) * wt.sum()

@@ -280,14 +280,14 @@ def detect_a(sd, p, feats: Sequence[torch.Tensor], nc: int, anchors: torch.Tenso
 # a9  DDetect (Stack B)  (models/yolo_snn.py:83-139) + DFL (common.py:312-323) + anchors
 #     (utils/tal/anchor_generator.py:8-32)
 # --------------------------------------------------------------------------------------
-def _ddetect_branch(sd, p, x, groups_mid: int, groups_last: int, training: bool):
-    y = conv_b(sd, p + "0.", x, 3, 1, 1, training)
-    y = conv_b(sd, p + "1.", y, 3, 1, groups_mid, training)
+def _ddetect_branch(sd, p, x, groups_mid: int, groups_last: int, training: bool, rec=None):
+    y = conv_b(sd, p + "0.", x, 3, 1, 1, training, rec)
+    y = conv_b(sd, p + "1.", y, 3, 1, groups_mid, training, rec)
     return snn_conv2d(y, sd[p + "2.weight"], sd[p + "2.bias"], 1, 0, groups_last)
 
 
 def ddetect(sd, p, feats: Sequence[torch.Tensor], nc: int, stride: torch.Tensor, training: bool,
-            double_eval: bool = True):
+            double_eval: bool = True, rec=None):
     """Mean over T of the box (cv2) and class (cv3) branches.  The reference evaluates every
     branch twice per forward (yolo_snn.py:115-116), which in training mode applies the tdBN
     momentum update twice; ``double_eval`` reproduces that."""
@@ -295,13 +295,13 @@ def ddetect(sd, p, feats: Sequence[torch.Tensor], nc: int, stride: torch.Tensor,
     no = nc + 4 * reg_max
     xs = []
     for i, f in enumerate(feats):
-        a = _ddetect_branch(sd, f"{p}cv2.{i}.", f, 4, 4, training)
+        a = _ddetect_branch(sd, f"{p}cv2.{i}.", f, 4, 4, training, rec)
         if double_eval:
             a2 = _ddetect_branch(sd, f"{p}cv2.{i}.", f, 4, 4, training)
             a = a.sum(dim=0) / a2.size()[0]
         else:
             a = a.sum(dim=0) / a.size()[0]
-        b = _ddetect_branch(sd, f"{p}cv3.{i}.", f, 1, 1, training)
+        b = _ddetect_branch(sd, f"{p}cv3.{i}.", f, 1, 1, training, rec)
         if double_eval:
             b2 = _ddetect_branch(sd, f"{p}cv3.{i}.", f, 1, 1, training)
             b = b.sum(dim=0) / b2.size()[0]
@@ -421,7 +421,7 @@ def forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, T: int, tra
             x = detect_a(sd, p, list(x), L["args"][0], anchors if anchors is not None else sd[p + "anchors"],
                          stride, training)
         elif L["type"] == "DDetect":
-            x = ddetect(sd, p, list(x), L["args"][0], stride, training, ddetect_double_eval)
+            x = ddetect(sd, p, list(x), L["args"][0], stride, training, ddetect_double_eval, rec)
         elif L["n"] > 1:
             for j in range(L["n"]):
                 x = _run_layer(sd, L, f"{p}{j}.", x, training, False, rec)

@@ -8,7 +8,7 @@ import yaml
 
 import ecs_oracle as O
 import seeded as S
-from util import ROOT, agree, ecsy, load_golden, rel_l2
+from util import ROOT, agree, ecsy, forced_spikes, load_golden, quantize_weights_bf16, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -21,6 +21,31 @@ def _build_block(E, spec):
 
 
 ALL_BLOCKS = {**S.BLOCK_CASES, **S.MS_BLOCK_CASES}   # MS_*: the res*-ee.yaml blocks, incl. the 3 / 32-channel front
+
+
+def _oracle_block(inp, spec, sd, training, rec=None):
+    return O.forward(inp["cfg"], sd, inp["x"], spec["T"], training, rec=rec)
+
+
+class _oracle_forced:
+    """ecs_oracle neurons return recorded spikes (evaluation of the oracle on bf16-rounded weights with the spikes of
+    its fp32 run: the reference a fast-precision block is compared with when its own neurons are teacher-forced)."""
+
+    def __init__(self, rec):
+        self.rec = rec
+
+    def __enter__(self):
+        self.orig = orig = O.lif_from_sd
+        rec = self.rec
+
+        def forced(sd, prefix, x, act=False, silu_inplace=False, record=None):
+            key = prefix[:-1]
+            return rec[key] if (not act and key in rec) else orig(sd, prefix, x, act=act, silu_inplace=silu_inplace, record=record)
+        O.lif_from_sd = forced
+
+    def __exit__(self, *exc):
+        O.lif_from_sd = self.orig
+        return False
 
 
 @pytest.mark.parametrize("name", list(ALL_BLOCKS))
@@ -52,36 +77,59 @@ def test_block_forward(name):
 
 
 @pytest.mark.parametrize("name", list(ALL_BLOCKS))
-def test_block_spikes(name):
-    """Per-LIF spike agreement inside the block (>= 99.9 % of positions)."""
+def test_block_forward_fast(name):
+    """The benchmark precision (one bf16 weight plane, fp16 ECS trace, tanh.approx) at the north-star tolerances, block by
+    block.  Every neuron is teacher-forced (util.forced_spikes): its spikes must equal the fp32 oracle's at >= 99.9 % of
+    the positions, and the real-valued block output must be within 1e-3 rel-L2 of the oracle evaluated on the same
+    bf16-rounded conv / point-wise spread weights and the same spikes (exact products, fp32 accumulation), train and eval
+    mode, including the running statistics.  The distance to the fp32-weight reference output is printed and bounded by
+    the bf16 rounding of the weights.  Blocks whose shortcut convolves a REAL tensor (BasicBlock_ms) also round that
+    operand to bf16: 6e-3."""
     E = ecsy()
+    F = E.functional
     spec, gold = ALL_BLOCKS[name], load_golden(name)
     inp = S.block_inputs(spec, O)
-    m = _build_block(E, spec)
-    m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
-    m = m.cuda().train()
+    real_operand = spec["kind"] == "BasicBlock_ms" and (spec["s"] != 1 or spec["cin"] != spec["cout"])
+    tol = 6e-3 if real_operand else 1e-3
     with torch.no_grad():
-        m(inp["x"].cuda())  # the fixture's eval pass follows one train pass (running-stat update)
-    m.eval()
-    got = {}
-    orig = E.common.mem_update.spikes
-
-    def rec(self, x, affine=None):
-        sp = orig(self, x, affine)
-        got[id(self)] = sp.to_act().to_ref().cpu()
-        return sp
-    E.common.mem_update.spikes = rec
+        sd32 = {k: v.clone() for k, v in inp["sd"].items()}
+        rec_t, rec_e = {}, {}
+        _oracle_block(inp, spec, sd32, True, rec_t)
+        _oracle_block(inp, spec, sd32, False, rec_e)
+        sdq = quantize_weights_bf16(inp["sd"])
+        with _oracle_forced(rec_t):
+            want_t = _oracle_block(inp, spec, sdq, True)
+        with _oracle_forced(rec_e):
+            want_e = _oracle_block(inp, spec, sdq, False)
+    spk = lambda r: {k: v for k, v in r.items() if not k.startswith("layer")}
+    F.set_precision("fast")
     try:
+        m = _build_block(E, spec)
+        m.load_state_dict({k[len("model.0."):]: v for k, v in inp["sd"].items()})
+        m = m.cuda().train()
+        x = inp["x"].cuda()
         with torch.no_grad():
-            m(inp["x"].cuda())
+            with forced_spikes(E, m, spk(rec_t), "model.0.") as ft:
+                out_t = m(x).cpu()
+            m.eval()
+            with forced_spikes(E, m, spk(rec_e), "model.0.") as fe:
+                out_e = m(x).cpu()
+        e_t, e_e = rel_l2(out_t, want_t), rel_l2(out_e, want_e)
+        d_t, d_e = rel_l2(out_t, gold["out_train"]), rel_l2(out_e, gold["out_eval"])
+        agree_min = min(list(ft.agree.values()) + list(fe.agree.values()))
+        print(f"\n{name} [fast]: train {e_t:.2e} eval {e_e:.2e} (vs fp32-weight reference {d_t:.2e} / {d_e:.2e}), "
+              f"min spike agreement {agree_min:.6f}")
+        assert e_t < tol and e_e < tol, f"{name}: train {e_t:.3e} eval {e_e:.3e}"
+        assert d_t < 1e-2 and d_e < 1e-2, f"{name}: vs the fp32-weight reference train {d_t:.3e} eval {d_e:.3e}"
+        assert len(ft.agree) == len(spk(rec_t)) and len(fe.agree) == len(spk(rec_e))
+        assert agree_min >= 0.999, {**ft.agree, **fe.agree}
+        sd = m.state_dict()
+        for k, v in sdq.items():       # the oracle's train pass updated sdq's running statistics in place
+            if "running_" in k:
+                kk = k[len("model.0."):]
+                assert torch.allclose(sd[kk].cpu().float(), v.float(), rtol=2e-3, atol=1e-5), k
     finally:
-        E.common.mem_update.spikes = orig
-    names = {id(mod): n for n, mod in m.named_modules() if isinstance(mod, E.common.mem_update)}
-    assert len(got) == len(gold["spikes_eval"])
-    for i, s in got.items():
-        ref = S.unpack_spikes(gold["spikes_eval"][names[i]], s.shape)
-        frac = agree(s, ref)
-        assert frac >= 0.999, f"{name}/{names[i]}: {frac:.6f}"
+        F.set_precision("parity")
 
 
 def test_detect_head():

@@ -202,7 +202,7 @@ def test_resample_concat_tsum():
     assert torch.allclose(out, a * sa.view(1, 1, -1, 1, 1) + ba.view(1, 1, -1, 1, 1) + a, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode,min_agree", [("parity", 0.9995), ("fast", 0.995)])
+@pytest.mark.parametrize("mode,min_agree", [("parity", 0.9995), ("fast", 0.999)])
 @pytest.mark.parametrize("name", list(S.LIF_CASES))
 def test_lif_ecs(name, mode, min_agree):
     """Spikes must agree with the reference at >= 99.9 % of positions (north star); parity mode is
@@ -306,8 +306,8 @@ def test_lif_ecs_fused(T, N, H, W):
         F.set_lif_fused(False)
         unf = F.lif_ecs(a, w).to_act().to_ref().cpu()
         want = O.ecs_lif(x, inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
-        assert agree(got, want) >= 0.995, agree(got, want)
-        assert agree(got, unf) >= 0.995, agree(got, unf)
+        assert agree(got, want) >= 0.999, agree(got, want)
+        assert agree(got, unf) >= 0.999, agree(got, unf)
         assert agree(got[0], want[0]) == 1.0          # step 0 has no ECS term: exact
         assert abs(float(got.mean()) - float(want.mean())) < 3e-3
         if H <= 64:
@@ -317,11 +317,11 @@ def test_lif_ecs_fused(T, N, H, W):
             got2 = F.lif_ecs(a, w, (sc.cuda(), sh.cuda())).to_act().to_ref().cpu()
             want2 = O.ecs_lif(x * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1), inp["dw_w"], inp["dw_b"],
                               inp["pw_w"], inp["pw_b"])
-            assert agree(got2, want2) >= 0.995
+            assert agree(got2, want2) >= 0.999
             xb = x[:1].expand(T, -1, -1, -1, -1)
             gotb = F.lif_ecs(F.Act.from_ref(xb.cuda()), w).to_act().to_ref().cpu()
             wantb = O.ecs_lif(xb.contiguous(), inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
-            assert agree(gotb, wantb) >= 0.995
+            assert agree(gotb, wantb) >= 0.999
     finally:
         F.set_precision("parity")
         F.set_lif_fused(False)

@@ -23,9 +23,22 @@ def _build_block(E, spec):
 ALL_BLOCKS = {**S.BLOCK_CASES, **S.MS_BLOCK_CASES}   # MS_*: res*-ee.yaml blocks incl. the zero-padded 3 / 32-channel front
 
 
+@pytest.mark.parametrize("mode,tol_out,tol_gx,tol_p", [("parity", 1e-3, 5e-3, 1e-2), ("fast", 3e-2, 5e-2, 5e-2)])
 @pytest.mark.parametrize("name", list(ALL_BLOCKS))
-def test_block_backward(name):
+def test_block_backward(name, mode, tol_out, tol_gx, tol_p):
+    """Block forward + BPTT against the reference's autograd, in both precisions.  Not teacher-forced inside the block:
+    in fast precision (one bf16 plane for weights and gradient operands) a flipped near-threshold spike also moves
+    the surrogate window of the elements it feeds, hence the wider fast-mode bounds; test_block_forward_fast holds
+    the same blocks' forward to the north-star tolerances with teacher-forced neurons."""
     E = ecsy()
+    E.set_precision(mode)
+    try:
+        _block_backward(E, name, tol_out, tol_gx, tol_p)
+    finally:
+        E.set_precision("parity")
+
+
+def _block_backward(E, name, tol_out, tol_gx, tol_p):
     spec, gold = ALL_BLOCKS[name], load_golden(name)
     inp = S.block_inputs(spec, O)
     m = _build_block(E, spec)
@@ -33,12 +46,13 @@ def test_block_backward(name):
     m = m.cuda().train()
     x = inp["x"].cuda().requires_grad_(True)
     out = m(x)
-    assert rel_l2(out.detach().cpu(), gold["out_train"]) < 1e-3
+    e_out = rel_l2(out.detach().cpu(), gold["out_train"])
+    assert e_out < tol_out, e_out
     gout = S.randn(S.gen(spec["seed"] + 13), *out.shape).cuda()
     out.backward(gout)
     # teacher-forced bound: a near-threshold flip moves the surrogate window of a few elements
     e = rel_l2(x.grad.cpu(), gold["gx"])
-    assert e < 5e-3, f"{name}: gx {e:.3e}"
+    assert e < tol_gx, f"{name}: gx {e:.3e}"
     named = dict(m.named_parameters())
     worst = ("", 0.0)
     for k, g in gold["grads"].items():
@@ -51,7 +65,8 @@ def test_block_backward(name):
         e = rel_l2(got, want)
         if e > worst[1]:
             worst = (k, e)
-    assert worst[1] < 1e-2, f"{name}: worst parameter gradient {worst[0]} rel-L2 {worst[1]:.3e}"
+    print(f"\n{name}: out {e_out:.2e} gx {e:.2e} worst parameter gradient {worst[0]} {worst[1]:.2e}")
+    assert worst[1] < tol_p, f"{name}: worst parameter gradient {worst[0]} rel-L2 {worst[1]:.3e}"
 
 
 def test_model_training_step():
@@ -285,8 +300,16 @@ def test_model_b_trains_against_tal_loss():
 
 
 # ---------------------------------------------------------------- whole model + the reference's loss
-def _model_loss_case(name):
+def _model_loss_case(name, mode="parity"):
     E = ecsy()
+    E.set_precision(mode)
+    try:
+        return _model_loss_case_impl(E, name)
+    finally:
+        E.set_precision("parity")
+
+
+def _model_loss_case_impl(E, name):
     stack_b = name in S.MODEL_B_CASES
     spec = (S.MODEL_B_CASES if stack_b else S.MODEL_CASES)[name]
     gold = torch.load(os.path.join(S.GOLDEN_DIR, "model_loss.pt"), weights_only=False)[name]
@@ -336,3 +359,102 @@ def test_model_loss_matches_reference_other_plans(name):
     errs = {k: rel_l2(params[k].grad.cpu(), g) for k, g in gold["head_grads"].items()}
     print(name, "head grad errs", {k: round(v, 6) for k, v in errs.items()})
     assert max(errs.values()) < 2e-2, errs
+
+
+def test_fused_optimizer_refreshes_derived_weights():
+    """The fused optimizer writes parameters through raw pointers; every derived-weight cache (packed bf16 conv / spread
+    weights, dgrad weights, folded tdBN affines, keyed on data_ptr + _version) must see the update.  Two copies of one model
+    train for four steps on the same batch -- one with SGDNesterovEMA (EMA off), one with torch.optim.SGD configured like
+    the reference's three parameter groups (train.py:259-287) -- and their OUTPUTS, not only their state_dicts, must agree
+    after every step.  With stale caches the fused copy would keep producing its step-0 features."""
+    E = ecsy()
+    torch.manual_seed(0)
+    ma = E.yolo.Model(E.cfg_path("tiny")).cuda().train()
+    mb = E.yolo.Model(E.cfg_path("tiny")).cuda().train()
+    mb.load_state_dict(ma.state_dict())
+    det = ma.model[-1]
+    hyp = dict(box=0.05 * 3 / det.nl, cls=0.5 * det.nc / 80 * 3 / det.nl, obj=1.0 * 3 / det.nl, cls_pw=1.0, obj_pw=1.0,
+               anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)
+    ma.hyp = mb.hyp = hyp
+    ca, cb = E.loss.ComputeLoss(ma), E.loss.ComputeLoss(mb)
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    tg = _coco_like_targets(2, det.nc, 5)
+    lr, mom, wd = 0.05, 0.9, 5e-4
+    oa = E.optim.SGDNesterovEMA(ma, lr=lr, momentum=mom, weight_decay=wd, ema=False)
+    g0, g1, g2 = E.optim.param_groups_of(mb)
+    ob = torch.optim.SGD([dict(params=g0, weight_decay=0.0), dict(params=g1, weight_decay=wd),
+                          dict(params=g2, weight_decay=0.0)], lr=lr, momentum=mom, nesterov=True)
+    with torch.no_grad():
+        first = [o.clone() for o in ma(x)]
+    for it in range(4):
+        for m, crit, opt in ((ma, ca, oa), (mb, cb, ob)):
+            opt.zero_grad(set_to_none=True)
+            loss, _ = crit(m(x), tg)
+            loss.backward()
+            opt.step()
+        with torch.no_grad():
+            ya, yb = ma(x), mb(x)
+        for a, b in zip(ya, yb):
+            # identical arithmetic up to the order of float atomics in the weight gradients
+            assert rel_l2(a, b) < 2e-3, (it, rel_l2(a, b))
+    moved = max(rel_l2(a, f) for a, f in zip(ya, first))
+    assert moved > 1e-2, f"the outputs did not move ({moved:.2e}): the forward still runs on the initial weights"
+
+
+def test_fused_optimizer_ema_model_evaluates_current_average():
+    """opt.ema.ema (the ModelEMA copy) is updated by the same launch; its packed weights and folded tdBN affines must be
+    rebuilt too.  After enough steps at a short EMA horizon its eval output has to differ from its initial eval output
+    and equal the output of a fresh model loaded with the EMA state_dict (no caches at all)."""
+    E = ecsy()
+    torch.manual_seed(0)
+    m = E.yolo.Model(E.cfg_path("tiny")).cuda().train()
+    det = m.model[-1]
+    m.hyp = dict(box=0.05 * 3 / det.nl, cls=0.5 * det.nc / 80 * 3 / det.nl, obj=1.0 * 3 / det.nl, cls_pw=1.0, obj_pw=1.0,
+                 anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)
+    crit = E.loss.ComputeLoss(m)
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    tg = _coco_like_targets(2, det.nc, 5)
+    opt = E.optim.SGDNesterovEMA(m, lr=0.05, momentum=0.9, weight_decay=5e-4, ema=True, ema_decay=0.5)
+    opt.ema.decay = lambda n: 0.5
+    with torch.no_grad():
+        z0 = opt.ema.ema(x)[0].clone()
+    for it in range(4):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = crit(m(x), tg)
+        loss.backward()
+        opt.step()
+    with torch.no_grad():
+        z1 = opt.ema.ema(x)[0]
+    fresh = E.yolo.Model(E.cfg_path("tiny")).cuda().eval()
+    fresh.load_state_dict(opt.ema.ema.state_dict())
+    with torch.no_grad():
+        z2 = fresh(x)[0]
+    assert rel_l2(z1, z2) < 1e-5, rel_l2(z1, z2)
+    assert rel_l2(z1, z0) > 1e-3, "the EMA model still evaluates its initial weights"
+
+
+def test_time_window_mismatch_raises():
+    """Conv_7 / Detect built for T = 4 must reject a T = 5 input like the reference's Conv3d(T -> 1) does
+    (models/common.py:549-562) instead of reading past the weight buffer."""
+    E = ecsy()
+    c7 = E.common.Conv_7(1, 1).cuda()
+    with pytest.raises(RuntimeError):
+        c7(torch.rand(5, 1, 64, 4, 4, device="cuda"))
+    det = E.yolo.Detect(3, [[10, 14, 23, 27, 37, 58]], (64,)).cuda().eval()
+    det.stride = torch.tensor([8.])
+    with pytest.raises(RuntimeError):
+        det([torch.rand(5, 1, 64, 4, 4, device="cuda")])
+
+
+@pytest.mark.parametrize("name", ["tiny_64", "tiny_ee_64", "tiny_b_64"])
+def test_model_loss_fast_precision(name):
+    """The same whole-model + loss cases in the BENCHMARK precision (one bf16 weight plane, fp16 ECS trace), end to end
+    and NOT teacher-forced: what moves the loss here is the bf16 rounding of the conv weights and the near-threshold
+    spikes it flips (tests/test_gpu_baseline_cfgs.py holds every layer of the real plans to 1e-3 / 99.9 % teacher-forced
+    in this precision).  Measured on B200 and printed; gate: 2 % of the reference loss."""
+    m, gold, loss, items = _model_loss_case(name, "fast")
+    rel = abs(float(loss.reshape(-1)[0]) - float(gold["loss"].reshape(-1)[0])) / abs(float(gold["loss"].reshape(-1)[0]))
+    print(f"\n{name} [fast] loss {float(loss.reshape(-1)[0]):.6f} vs reference {float(gold['loss'].reshape(-1)[0]):.6f} (rel {rel:.2e})")
+    assert rel < 2e-2, rel
+    params = dict(m.named_parameters())
+    assert all(torch.isfinite(p.grad).all() for p in params.values() if p.grad is not None)
