@@ -139,10 +139,13 @@ __device__ __forceinline__ void st4h(void* base, int64_t i, float a, float b, fl
   reinterpret_cast<uint2*>(base)[i] = pk;
 }
 
+// Fast-precision tanh: 1 - 2 / (exp(2v) + 1) with ex2.approx / rcp.approx -- ABSOLUTE error ~1e-7 (what the membrane
+// sees: f = beta * tanh(e)), against 2^-11 ~ 5e-4 for the hardware tanh.approx it replaces, which alone moved the
+// membrane by 1.2e-4 and cost ~0.03 % of the spikes (tests/test_gpu_baseline_cfgs.py).  Two MUFU ops instead of one in a
+// kernel that waits on HBM.  Saturates correctly: exp -> inf gives 1, exp -> 0 gives -1.
 __device__ __forceinline__ float tanh_fast(float v) {
-  float r;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
-  return r;
+  const float y = __expf(2.f * v);
+  return 1.f - __fdividef(2.f, y + 1.f);
 }
 
 template <bool HALF>

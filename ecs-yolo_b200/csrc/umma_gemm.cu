@@ -2064,7 +2064,7 @@ int launch_ts_v(const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMa
     g.nbuf = 2;
     plan();
   }
-  if (stages < 2) {
+  if (stages < (V == 2 ? 3 : 2)) {   // V == 2: an expander hops up to 3 rounds at a tile boundary; the ring must be at least that deep
     ecsy_set_error("spike_conv_ts: shared memory budget allows only %d stage(s)", stages);
     return ECSY_ERR_UNSUPPORTED;
   }
@@ -2103,7 +2103,12 @@ int ecsy_umma_spike_conv(const uint32_t* bits, const void* w_packed, int splits,
   // ts: 0 = smem operand, natural weight layout; 1 = tensor-memory operand kernel; 2 = tensor-memory operand with the
   // legacy epilogue; 3 = smem operand (wide tiles) with weights in the tensor-memory layout (pair expansion)
   const bool tsk = ts == 1 || ts == 2;
-  const int BN = tsk ? ecsy_pick_bn_ts(Cout) : ecsy_pick_bn(Cout, splits);
+  int BN = tsk ? ecsy_pick_bn_ts(Cout) : ecsy_pick_bn(Cout, splits);
+  // Two weight planes (parity precision) on a 128-column tile leave room for only TWO ring stages of two K blocks each.
+  // The expanders hop up to three rounds when they cross a tile boundary (their parity of K blocks), i.e. over a whole
+  // period of a two-stage ring, and an mbarrier parity wait cannot tell phase p from phase p + 2: measured as a hang on
+  // resnet10's 64 -> 128 stride-2 conv at batch 2 (tests/test_gpu_baseline_cfgs.py).  64-column tiles keep >= 4 stages.
+  if (tsk && splits == 2 && BN == 128) BN = 64;
   ECSY_CHECK_ARG(BN != 0, "spike_conv: Cout=%d must be a multiple of 64", Cout);
   ECSY_CHECK_ARG(splits == 1 || splits == 2, "spike_conv: splits must be 1 or 2");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;

@@ -25,6 +25,7 @@ decay = 0.25
 # conv_ts: "auto" (measured dispatch rule), "all" (wherever supported) or "off"
 _state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
           "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1",
+          "lif_wave": os.environ.get("ECSY_LIF_WAVE", "1") == "1",
           "lif_store": os.environ.get("ECSY_LIF_STORE", "1") == "1"}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
@@ -105,6 +106,12 @@ def set_lif_fused(on: bool) -> None:
     """Fast mode, C == 64: run the ECS-LIF forward as ONE kernel with all T steps on chip.  Parity-green but
     measured slower than the per-timestep pipeline so far (csrc/lif_fused.cu header), hence off by default."""
     _state["lif_fused"] = bool(on)
+
+
+def set_lif_wave(on: bool) -> None:
+    """Fast precision, C == 64, 2 <= T <= 4 (default ON): the ECS-LIF forward runs as ONE wavefront kernel with membrane and
+    ECS trace of all T steps in tensor memory (csrc/lif_wave.cu) instead of the per-timestep pipeline."""
+    _state["lif_wave"] = bool(on)
 
 
 def set_lif_store(on: bool) -> None:
@@ -322,7 +329,8 @@ class LifW:
     pw_b: torch.Tensor   # [C]
     splits: int
     w_eff: Optional[torch.Tensor] = None    # fused kernel: folded 3x3 spread weight (ecsy_pack_spike_conv_weight form)
-    bconst: Optional[torch.Tensor] = None   # fused kernel: pw @ dw_b + pw_b
+    bconst: Optional[torch.Tensor] = None   # fused kernels: pw @ dw_b + pw_b
+    w_wave: Optional[torch.Tensor] = None   # wavefront kernel: [9][64][64] bf16 folded spread weight (pack_lif_wave_weight)
 
 
 def pad64(c: int) -> int:
@@ -332,6 +340,16 @@ def pad64(c: int) -> int:
 def pad_channels(t: torch.Tensor, Cp: int) -> torch.Tensor:
     """Zero-pad the last (channel) axis of an NHWC tensor / a [C] vector to Cp entries."""
     return t if t.shape[-1] == Cp else torch.nn.functional.pad(t, (0, Cp - t.shape[-1]))
+
+
+def pack_lif_wave_weight(w_eff: torch.Tensor) -> torch.Tensor:
+    """[64 co, 64 ci, 3, 3] fp32 folded spread weight -> [9 taps][64 co][64 kk] bf16 for ecsy_lif_ecs_wave_fwd.  kk is the
+    position of channel c in the operand row a thread of the kernel writes: it holds channels 8k + 2q + e (k = 0..7, e =
+    0, 1) of a pixel for its q = lane % 4 and stores them at kk = 16q + 2k + e (csrc/lif_wave.cu)."""
+    kk = torch.arange(64, device=w_eff.device)
+    c_of_kk = 8 * ((kk % 16) // 2) + 2 * (kk // 16) + (kk % 2)
+    w = w_eff.detach().float()[:, c_of_kk]                       # [co, kk, ky, kx]
+    return w.permute(2, 3, 0, 1).reshape(9, 64, 64).contiguous().to(torch.bfloat16)
 
 
 def make_lif_w(dw_w, dw_b, pw_w, pw_b, Cp: Optional[int] = None) -> LifW:
@@ -352,6 +370,7 @@ def make_lif_w(dw_w, dw_b, pw_w, pw_b, Cp: Optional[int] = None) -> LifW:
         w_eff = pw2.reshape(C, C, 1, 1) * dw_w.detach().float().reshape(1, C, 3, 3)
         w.w_eff = pack_spike_conv_weight(w_eff, 1)
         w.bconst = (pw2 @ dw_b.detach().float() + pw_b.detach().float()).contiguous()
+        w.w_wave = pack_lif_wave_weight(w_eff)
     return w
 
 
@@ -374,6 +393,16 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
     bits = torch.empty(T, N, H, W, C // 32, device=dev, dtype=torch.int32)
+    if (not save_mem and w is not None and w.w_wave is not None and _state["lif_wave"] and not _state["lif_fused"]
+            and _cabi.lib().ecsy_lif_ecs_wave_supported(T, C, H, W)):
+        sc, sh = affine if affine is not None else (None, None)
+        flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
+        with _timed("lif_ecs", 1):
+            _cabi.check(_cabi.lib().ecsy_lif_ecs_wave_fwd(
+                _p(x.data), x.tstride, _p(sc), _p(sh), _p(w.w_wave), _p(w.bconst), _p(bits), T, N, H, W, C,
+                float(thresh), float(decay), float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _st()),
+                "lif_ecs_wave_fwd")
+        return Spikes(bits, C, Cr)
     if (not save_mem and w is not None and w.w_eff is not None and _state["lif_fused"]
             and _cabi.lib().ecsy_lif_ecs_fused_supported(T, C)):
         sc, sh = affine if affine is not None else (None, None)

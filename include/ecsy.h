@@ -73,6 +73,18 @@ int ecsy_lif_ecs_fused_fwd(const float* x, int64_t x_tstride, const float* in_sc
                            const void* w_eff_ts, const float* bconst, uint32_t* spikes, int T, int64_t N, int H, int W,
                            int C, float thresh, float decay, float alpha, float beta, float kappa, void* stream);
 
+/* Wavefront forward of the same neuron for C == 64, 2 <= T <= 4 (fast / single-plane precision): the DEFAULT inference
+ * path for 64-channel layers.  The time loop runs as a wavefront down vertical bands of the image inside one persistent
+ * kernel (csrc/lif_wave.cu): membrane and ECS trace of all T steps stay in tensor memory, x is read once, only spike
+ * bits are written (reference loop: models/common.py:252-283, state `mem` / `ecs` carried across `for i in
+ * range(time_window)`).  w_eff: [9][64][64] bf16, tap-major, W_eff[tap][co][kk] = pw[co][c(kk)] * dw[c(kk)][tap] with
+ * the channel permutation c(kk) = 8 * ((kk % 16) / 2) + 2 * (kk / 16) + kk % 2 (functional.pack_lif_wave_weight);
+ * bconst as above.  No workspace. */
+int ecsy_lif_ecs_wave_supported(int T, int C, int H, int W);
+int ecsy_lif_ecs_wave_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
+                          const void* w_eff, const float* bconst, uint32_t* spikes, int T, int64_t N, int H, int W,
+                          int C, float thresh, float decay, float alpha, float beta, float kappa, void* stream);
+
 size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
 int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                       const float* dw_w, const float* dw_b, const void* pw_packed, const float* pw_b, int splits,

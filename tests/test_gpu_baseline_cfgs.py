@@ -108,7 +108,7 @@ def test_baseline_plan_teacher_forced(name, N, img, mode):
 
     def layer_input(L):
         f = L["f"]
-        prev = lambda j: xin if j == -1 and L["i"] == 0 else rec[f"layer{L['i'] - 1 if j == -1 else j}"]
+        prev = lambda j: xin if (j < 0 and L["i"] + j < 0) else rec[f"layer{L['i'] + j if j < 0 else j}"]
         return prev(f) if isinstance(f, int) else [prev(j) for j in f]
 
     # ---- our model

@@ -327,6 +327,54 @@ def test_lif_ecs_fused(T, N, H, W):
         F.set_lif_fused(False)
 
 
+@pytest.mark.parametrize("T,N,H,W", [(4, 3, 37, 45), (2, 2, 23, 20), (3, 1, 30, 16), (4, 2, 9, 61), (4, 1, 160, 160),
+                                     (4, 5, 48, 80), (4, 2, 64, 200), (3, 7, 5, 7)])
+def test_lif_ecs_wave(T, N, H, W):
+    """Wavefront ECS-LIF (C = 64, fast precision, csrc/lif_wave.cu; the default inference path): one band / several bands
+    per image (W = 61 is the widest single 64-column band, 80 -> 4 bands of 32, 160 -> 3 of 64, 200 -> 4 of 64), odd heights,
+    more images than CTAs' segments (warm-up / cool-down blocks across band and image boundaries), T = 2..4; against the
+    CPU oracle (>= 99.9 % of the spikes, step 0 exact) and the per-timestep pipeline; with a pending tdBN affine and a
+    T-broadcast input."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision("fast")
+    try:
+        inp = S.lif_inputs(dict(T=T, N=N, C=64, H=H, W=W, seed=700 + T + H + W))
+        w = F.make_lif_w(inp["dw_w"].cuda(), inp["dw_b"].cuda(), inp["pw_w"].cuda(), inp["pw_b"].cuda())
+        assert w.w_wave is not None and E._cabi.lib().ecsy_lif_ecs_wave_supported(T, 64, H, W)
+        x = inp["x"]
+        a = F.Act.from_ref(x.cuda())
+        F.set_lif_wave(True)
+        n0 = F.launches["n"]
+        got = F.lif_ecs(a, w).to_act().to_ref().cpu()
+        assert F.launches["n"] - n0 == 1, "the wavefront kernel must be the path that ran"
+        F.set_lif_wave(False)
+        unf = F.lif_ecs(a, w).to_act().to_ref().cpu()
+        F.set_lif_wave(True)
+        want = O.ecs_lif(x, inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
+        per_t = [agree(got[t], want[t]) for t in range(T)]
+        print(f"\nwave T={T} N={N} {H}x{W}: agreement vs oracle {agree(got, want):.6f} per step {[round(v, 6) for v in per_t]}, "
+              f"vs pipeline {agree(got, unf):.6f} (pipeline vs oracle {agree(unf, want):.6f})")
+        assert agree(got[0], want[0]) == 1.0          # step 0 has no ECS term: exact
+        assert agree(got, want) >= 0.999, agree(got, want)
+        assert agree(got, unf) >= 0.999, agree(got, unf)
+        assert abs(float(got.mean()) - float(want.mean())) < 3e-3
+        if H <= 64:
+            sc = torch.rand(64, generator=S.gen(3)) + 0.5
+            sh = torch.rand(64, generator=S.gen(4)) * 0.2
+            got2 = F.lif_ecs(a, w, (sc.cuda(), sh.cuda())).to_act().to_ref().cpu()
+            want2 = O.ecs_lif(x * sc.view(1, 1, -1, 1, 1) + sh.view(1, 1, -1, 1, 1), inp["dw_w"], inp["dw_b"],
+                              inp["pw_w"], inp["pw_b"])
+            assert agree(got2, want2) >= 0.999
+            xb = x[:1].expand(T, -1, -1, -1, -1)
+            gotb = F.lif_ecs(F.Act.from_ref(xb.cuda()), w).to_act().to_ref().cpu()
+            wantb = O.ecs_lif(xb.contiguous(), inp["dw_w"], inp["dw_b"], inp["pw_w"], inp["pw_b"])
+            assert agree(gotb, wantb) >= 0.999
+    finally:
+        F.set_precision("parity")
+        F.set_lif_wave(True)
+
+
 @pytest.mark.parametrize("ci,co,k,H,W,N,T", [(64, 128, 3, 10, 12, 2, 2), (128, 64, 1, 7, 9, 1, 3), (192, 256, 3, 20, 20, 3, 1)])
 @pytest.mark.parametrize("mode,tol", [("parity", 2e-5), ("fast", 8e-3)])
 def test_real_conv_implicit(ci, co, k, H, W, N, T, mode, tol):
@@ -348,6 +396,34 @@ def test_real_conv_implicit(ci, co, k, H, W, N, T, mode, tol):
         assert err < tol, err
     finally:
         F.set_precision("parity")
+
+
+@pytest.mark.parametrize("ci,co,s,H,N", [(64, 128, 2, 160, 8), (128, 128, 1, 80, 8), (64, 64, 1, 96, 6)])
+def test_spike_conv_parity_many_tiles_per_cta(ci, co, s, H, N):
+    """Parity precision (two weight planes) with MORE tiles than CTAs, so every persistent CTA crosses tile boundaries
+    while the tensor core (twice the MMAs per K block) is the slow side and the operand ring runs full: the configuration
+    that hung when a 128-column tile left only a two-stage ring (resnet10.yaml's 64 -> 128 stride-2 conv at batch 2).
+    Tensor-memory operand kernel against the shared-memory operand kernel (independent pipeline) and fp64 conv2d on a sample."""
+    E = ecsy()
+    F = E.functional
+    F.set_precision("parity")
+    try:
+        g = S.gen(ci + co + H)
+        x = (torch.rand(1, N, ci, H, H, generator=g) < 0.2).float()
+        w = torch.randn(co, ci, 3, 3, generator=g) * 0.05
+        sp = F.Spikes.from_act(F.Act.from_ref(x.cuda()))
+        F.set_conv_ts(True)
+        cw = F.make_conv_w(w.cuda(), None, s, 1, 1, True, False)
+        out_ts = F.spike_conv(sp, cw).to_ref()
+        F.set_conv_ts(False)
+        out_ss = F.spike_conv(sp, cw).to_ref()
+        torch.cuda.synchronize()
+        assert rel_l2(out_ts, out_ss) < 1e-5
+        ref = torch.nn.functional.conv2d(x[0, :1].double(), w.double(), None, s, 1).float()
+        assert rel_l2(out_ts[0, :1].cpu(), ref) < 2e-5
+    finally:
+        F.set_precision("parity")
+        F.set_conv_ts("auto")
 
 
 def test_full_size_cross_checks():
