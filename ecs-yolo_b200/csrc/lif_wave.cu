@@ -53,10 +53,12 @@ namespace {
 
 constexpr int kWvC = 64;
 constexpr int kWvMaxT = 4;
-constexpr int kWvESlots = 5;
-constexpr int kWvMSlots = 3;
-constexpr int kWvMCol0 = kWvESlots * 64;        // membrane slots start at column 320
+constexpr int kWvESlots = 8;                    // all 512 tensor-memory columns hold spread accumulators
+constexpr int kWvMSlots = 6;                    // membrane slots: CTA-private global scratch (stays in L2)
+constexpr int kWvMSlotFloats = 128 * 64;         // one block of membranes, stored in the writing thread's own order
 constexpr int kWvWBytes = 9 * 64 * 128;         // nine [64 co x 64 kk] bf16 tap tiles
+constexpr int kWvThreads = 608;                 // 16 level warps + 3 issuer warps (a CTA is allocated in units of 4 warps: 96 registers)
+constexpr int kWvIssuerWarp = 16;
 constexpr int kWvFullDepth = 8;                 // `full` barriers per level: a level may run up to kWvESlots blocks ahead of the next
 
 struct WvCtl {
@@ -64,7 +66,8 @@ struct WvCtl {
   uint64_t ring_free[kWvMaxT];              // every MMA that reads the ring rows level t is about to overwrite has completed
   uint64_t full[kWvMaxT][kWvFullDepth];     // every MMA into E(block j) for level t has completed (barrier j % 8)
   uint64_t e_free[kWvESlots];               // the last level has read E of the block that held this slot
-  uint64_t m_free[kWvMSlots];
+  uint64_t m_free[kWvMSlots];               // the last level has read the membranes of the block that held this slot
+  uint64_t m_ready[kWvMSlots];              // a level has written its membranes of the block in this slot (T-2 phases per use)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -77,6 +80,7 @@ struct WvArgs {
   const uint16_t* w_eff;     // [9][64][64] bf16, K-permuted (see ecsy_lif_wave_pack)
   const float* bconst;       // [64] pw * b_dw + b_pw
   uint32_t* spikes;          // [T][N][H][W][2]
+  float* mscr;               // [gridDim.x][kWvMSlots][128 * 64] membrane scratch
   int T, N, H, W;
   int R, Wb, logWb;          // block = R image rows x Wb region columns
   int nb, hb;                // bands per image, blocks per band (+1 gap entry in the stream)
@@ -97,6 +101,34 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Blocking wait without a clock read in the loop (CS2R shares the XU pipe with the MUFU ops of the working warps): the
+// hardware suspends the warp up to the hint and wakes it on the arrival; a pipeline bug traps instead of hanging the box.
+__device__ __forceinline__ void wv_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int it = 0; it < (1 << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("ecsy: lif_wave barrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, addr, parity);
+  __trap();
+}
+__device__ __forceinline__ uint4 ld_cg_u4(const float* p) {     // L2-coherent (another warp group of this CTA wrote it)
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_cg_u4(float* p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 16 lanes x 32 columns: thread i <-> rows i/4 (+8), columns 8k + 2(i%4) + {0,1}; v[4k + 2r + e].
 __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -107,6 +139,21 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 16 columns: v[4k + 2r + e], k = 0, 1.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
@@ -115,9 +162,17 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
-__device__ __forceinline__ float wv_tanh(float v) {   // absolute error ~1e-7 (see elementwise.cu: tanh_fast)
-  const float y = __expf(2.f * v);
-  return 1.f - __fdividef(2.f, y + 1.f);
+// beta * tanh(alpha E) = beta - 2 beta / (2^(2 log2(e) alpha E) + 1): ex2.approx + rcp.approx, absolute error ~1e-7 (see
+// elementwise.cu: tanh_fast); 2^t -> inf gives beta, 2^t -> 0 gives -beta.
+__device__ __forceinline__ float exp2f_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 __device__ __forceinline__ float2 ldg_stream2(const float* p) {
   float2 r;
@@ -136,243 +191,310 @@ __device__ __forceinline__ float2 lds64f(uint32_t addr) {
 // Ring geometry (rows of 128 bytes): [8 pad][guard-top: Wb][slot A: 128][slot B: 128][guard-bottom: Wb][8 pad]
 __host__ __device__ constexpr int wv_ring_rows(int Wb) { return 8 + Wb + 256 + Wb + 8; }
 
-struct BlockGeom {   // one stream entry
-  bool gap;
-  int n, row0, rx0, ox0, ox1;
-};
-
-__device__ __forceinline__ BlockGeom wv_locate(const WvArgs& g, int64_t p) {
-  BlockGeom b;
-  const int per = g.hb + 1;
-  b.gap = p < 0 || p >= g.S;
-  int64_t band = b.gap ? 0 : p / per;
-  const int r = b.gap ? 0 : (int)(p - band * per);
-  if (r == g.hb) b.gap = true;
-  b.n = (int)(band / g.nb);
-  const int bi = (int)(band - (int64_t)b.n * g.nb);
-  b.row0 = r * g.R;
-  b.ox0 = (int)(((int64_t)g.W * bi) / g.nb);
-  b.ox1 = (int)(((int64_t)g.W * (bi + 1)) / g.nb);
-  b.rx0 = b.ox0 - (bi == 0 ? 1 : g.T - 1);
-  return b;
-}
+#ifdef WV_PROF
+#define WV_DECL long long prof_full = 0, prof_ring = 0, prof_work = 0, prof_pre = 0
+#define WV_T(v) const long long v = clock64()
+#define WV_ACC(a, d) a += (d)
+#define WV_REPORT                                                                                                        \
+  if (blockIdx.x == 1 && (threadIdx.x & 127) == 0)                                                                       \
+    printf("wave prof: level %d blocks %d  per block: pre %lld  wait_full %lld  wait_ring %lld  work %lld\n", lvl, nblk, \
+           prof_pre / nblk, prof_full / nblk, prof_ring / nblk, prof_work / nblk)
+#else
+#define WV_DECL
+#define WV_T(v)
+#define WV_ACC(a, d)
+#define WV_REPORT
+#endif
 
 struct LevelCtx {
   WvCtl* ctl;
   uint32_t tmem_base, rings_u32, c_bconst, c_scale, c_shift;
   int ring_bytes, P, lvl;
-  int64_t p_begin, seg0, seg1;
+  int p_begin, seg0, seg1;
 };
 
 // =============================== one level: timestep `lvl` of every block ===============================
 // KIND 0: level 0 (m_0 = x_0, no tensor memory); 1: level 1 (m_0 re-read from x_0); 2: levels >= 2 (membrane from
-// tensor memory).  LAST: level T-1 (nothing handed on: no ring rows, no tensor-memory stores).
-template <int KIND, bool LAST>
+// tensor memory).  LAST: level T-1 (nothing handed on: no ring rows, no tensor-memory stores).  AFF: a tdBN affine is
+// pending on the input current.
+//
+// A level runs on ONE warp per scheduler partition, so its block time is set by instruction count and dependency
+// latency, not by memory: the loop below is written for few instructions per element (folded constants, one FSET per
+// spike, spike rows and HBM words assembled with byte permutes) and no spills (with ~225 KB of shared memory in use the
+// L1 is ~1 KB: a spilled register is an L2 round trip).
+template <int KIND, bool LAST, bool AFF>
 __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
   WvCtl* ctl = cx.ctl;
   const uint32_t tmem_base = cx.tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = g.T, lvl = cx.lvl, P = cx.P;
-  const int64_t p_begin = cx.p_begin, seg0 = cx.seg0, seg1 = cx.seg1;
-  const bool affine = g.in_scale != nullptr;
+  const int lvl = cx.lvl, P = cx.P;
+  const int p_begin = cx.p_begin, seg0 = cx.seg0, seg1 = cx.seg1;
   const int SA = 8 + g.Wb, SB = SA + 128, GT = 8, GB = SB + 128;
-  constexpr bool last = LAST;
-  {
-    const int q = warp & 3;                   // tensor-memory lane quarter (hardware: warp id % 4)
-    const int q4 = lane & 3;
-    const uint32_t ring = cx.rings_u32 + (uint32_t)lvl * (uint32_t)cx.ring_bytes;          // written by levels < T-1
-    const uint32_t c_bconst = cx.c_bconst + (uint32_t)q4 * 8u;
-    const uint32_t c_scale = cx.c_scale + (uint32_t)q4 * 8u;
-    const uint32_t c_shift = cx.c_shift + (uint32_t)q4 * 8u;
-    const int64_t bits_tstride = (int64_t)g.N * g.H * g.W * 2;
-    const float* xt = g.x + (int64_t)lvl * g.x_tstride;
-    const int nblk = P - lvl;                 // level lvl processes local blocks 0 .. P-1-lvl
+  const int q = warp & 3;                   // tensor-memory lane quarter (hardware: warp id % 4)
+  const int q4 = lane & 3;
+  const uint32_t ring = cx.rings_u32 + (uint32_t)lvl * (uint32_t)cx.ring_bytes;          // written by levels < T-1
+  const uint32_t c_bconst = cx.c_bconst + (uint32_t)q4 * 8u;
+  const uint32_t c_scale = cx.c_scale + (uint32_t)q4 * 8u;
+  const uint32_t c_shift = cx.c_shift + (uint32_t)q4 * 8u;
+  const int64_t bits_tstride = (int64_t)g.N * g.H * g.W * 2;
+  const float* xt = g.x + (int64_t)lvl * g.x_tstride + 2 * q4;
+  const float* x0p = g.x + 2 * q4;
+  const int nblk = P - lvl;                 // level lvl processes local blocks 0 .. P-1-lvl
+  // this thread's four pixels i = 2h + rs: block row a_i = 32q + 16h + 8rs + lane/4 -> (ry_i, rx_i) inside the block
+  const int a0 = 32 * q + (lane >> 2);
+  const float c1 = 2.f * 1.4426950408889634f * g.alpha;      // tanh(alpha E) = 1 - 2 / (2^(c1 E) + 1)
+  const float nb2 = -2.f * g.beta;
 
-    for (int j = 0; j < nblk; ++j) {
-      const int64_t p = p_begin + j;
-      const BlockGeom bg = wv_locate(g, p);
-      const bool seg_out = p >= seg0 && p < seg1;
-
-      // ---- this thread's four pixels: (half h, row-select rs) -> block row a = 32q + 16h + 8rs + lane/4 ----
-      int pix[4];
-      uint32_t flags = 0;       // bit i: inside the image, bit 4+i: result is written to HBM
+  // ---- stream position -> band geometry, kept incrementally (three divisions only when a new band starts) ----
+  int r_in_band, band_pix0, rx0, ox0, ox1;      // block index in the band; pixel index of (row 0, region column 0); columns
+  bool band_valid;
+  auto set_band = [&](int p) {
+    const uint32_t per = (uint32_t)(g.hb + 1);
+    band_valid = p >= 0 && p < (int)g.S;
+    const uint32_t up = band_valid ? (uint32_t)p : 0u;
+    const uint32_t band = up / per;
+    r_in_band = (int)(up - band * per);
+    const int n = (int)(band / (uint32_t)g.nb);
+    const int bi = (int)(band - (uint32_t)n * (uint32_t)g.nb);
+    ox0 = (int)(((uint32_t)g.W * (uint32_t)bi) / (uint32_t)g.nb);
+    ox1 = (int)(((uint32_t)g.W * (uint32_t)(bi + 1)) / (uint32_t)g.nb);
+    rx0 = ox0 - (bi == 0 ? 1 : g.T - 1);
+    band_pix0 = n * g.H * g.W + rx0;
+  };
+  set_band(p_begin);
+  // pixel index + flags (bit i: inside the image, bit 4+i: written to HBM) of the four pixels in the CURRENT block
+  auto locate = [&](int p, int (&pix)[4]) -> uint32_t {
+    const bool gap = !band_valid || r_in_band == g.hb;
+    const bool seg_out = p >= seg0 && p < seg1;
+    const int row0 = r_in_band * g.R;
+    uint32_t flags = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int a = 32 * q + 16 * (i >> 1) + 8 * (i & 1) + (lane >> 2);
-        const int ry = a >> g.logWb, rx = a & (g.Wb - 1);
-        const int y = bg.row0 + ry, xx = bg.rx0 + rx;
-        const bool inside = !bg.gap && y < g.H && xx >= 0 && xx < g.W;
-        pix[i] = inside ? (bg.n * g.H + y) * g.W + xx : 0;
-        flags |= (inside ? 1u : 0u) << i;
-        flags |= ((inside && seg_out && xx >= bg.ox0 && xx < bg.ox1) ? 1u : 0u) << (4 + i);
-      }
-
-      float xa[2][16];          // input current of the chunk being computed / the next chunk (software pipeline)
-      float x0a[2][16];         // level 1 only: x_0 = m_0
-      auto load_chunk = [&](int u, float (&xv)[16], float (&x0v)[16]) {
-        const int h = u >> 1, gq = u & 1;
+    for (int i = 0; i < 4; ++i) {
+      const int a = a0 + 16 * (i >> 1) + 8 * (i & 1);
+      const int ry = a >> g.logWb, rx = a & (g.Wb - 1);
+      const int y = row0 + ry, xx = rx0 + rx;
+      const bool inside = !gap && y < g.H && xx >= 0 && xx < g.W;
+      pix[i] = inside ? band_pix0 + y * g.W + rx : 0;
+      flags |= (inside ? 1u : 0u) << i;
+      flags |= ((inside && seg_out && xx >= ox0 && xx < ox1) ? 1u : 0u) << (4 + i);
+    }
+    return flags;
+  };
+  // 8 values of one chunk u = (h, gq, kh): pixels (h, rs = 0, 1), channels 16 (u & 3) + 8 k + 2 q4 + e (k, e = 0, 1).  A
+  // pixel outside the image reads a huge negative current: it never fires (zero padding of the spread), its state stays
+  // finite.  The chunk loop is NOT unrolled (four levels x eight unrolled chunks were 140 KB of hot code on one SM: a
+  // quarter of all warp stalls were instruction-cache misses); buffers rotate through registers instead.
+  auto load_x = [&](int u, const int (&pix)[4], uint32_t flags, float (&xv)[8], const float* base) {
+    const bool hi = u >= 4;
+    const int cb = 16 * (u & 3);
 #pragma unroll
-        for (int rs = 0; rs < 2; ++rs) {
-          const int pi = 2 * h + rs;
-          const bool ok = (flags >> pi) & 1u;
-          const float* src = xt + (int64_t)pix[pi] * 64 + 32 * gq + 2 * q4;
+    for (int rs = 0; rs < 2; ++rs) {
+      const int pp = hi ? pix[2 + rs] : pix[rs];
+      const bool ok = (flags >> ((hi ? 2 : 0) + rs)) & 1u;
+      const float* src = base + (int64_t)pp * 64 + cb;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float2 v = ok ? ldg_stream2(src + 8 * k) : make_float2(0.f, 0.f);
-            xv[4 * k + 2 * rs] = v.x;
-            xv[4 * k + 2 * rs + 1] = v.y;
-            if (KIND == 1) {
-              float2 v0 = ok ? ldg_stream2(src - g.x_tstride + 8 * k) : make_float2(0.f, 0.f);
-              x0v[4 * k + 2 * rs] = v0.x;
-              x0v[4 * k + 2 * rs + 1] = v0.y;
-            }
-          }
-        }
-      };
-      load_chunk(0, xa[0], x0a[0]);
-
-      // ---- wait for this block's spread accumulator, the ring rows and the tensor-memory slots we are about to write ----
-      if (KIND > 0) {
-        mbar_wait(&ctl->full[lvl][j & (kWvFullDepth - 1)], (uint32_t)(j / kWvFullDepth) & 1u);
-        if (KIND == 1 && !LAST && j >= kWvMSlots) mbar_wait(&ctl->m_free[j % kWvMSlots], (uint32_t)(j / kWvMSlots - 1) & 1u);
-        tc_fence_after_sync();
-      }
-      if (!last && j >= 1) mbar_wait(&ctl->ring_free[lvl], (uint32_t)(j - 1) & 1u);
-
-      const uint32_t e_col = (uint32_t)(j % kWvESlots) * 64u;
-      const uint32_t m_col = (uint32_t)kWvMCol0 + (uint32_t)(j % kWvMSlots) * 64u;
-      const uint32_t slot_row = (uint32_t)((j & 1) ? SB : SA);
-      uint32_t wlo[4] = {0u, 0u, 0u, 0u}, whi[4] = {0u, 0u, 0u, 0u};   // HBM spike words (channels 0-31 / 32-63) per pixel
-
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int h = u >> 1, gq = u & 1;
-        if (u + 1 < 4) load_chunk(u + 1, xa[(u + 1) & 1], x0a[(u + 1) & 1]);
-        float (&xv)[16] = xa[u & 1];
-        float (&x0v)[16] = x0a[u & 1];
-        const uint32_t t_addr = tmem_base + ((uint32_t)(32 * q + 16 * h) << 16);
-        uint32_t ev[16], mv[16];
-        if (KIND > 0) {
-          tmem_ld_16x256b_x4(t_addr + e_col + 32u * gq, ev);
-          if (KIND > 1) tmem_ld_16x256b_x4(t_addr + m_col + 32u * gq, mv);
-          tmem_ld_wait();
-        }
-        uint32_t sbits = 0;      // bit 4k + 2rs + e of this chunk
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = 32 * gq + 8 * k;     // + 2*q4 + e
-          float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f), bc = make_float2(0.f, 0.f);
-          if (affine) { sc = lds64f(c_scale + c * 4); sh = lds64f(c_shift + c * 4); }
-          if (KIND > 0) bc = lds64f(c_bconst + c * 4);
-#pragma unroll
-          for (int rs = 0; rs < 2; ++rs) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int idx = 4 * k + 2 * rs + e;
-              float xin = xv[idx];
-              if (affine) xin = add_rn(mul_rn(xin, e ? sc.y : sc.x), e ? sh.y : sh.x);
-              float m;
-              if (KIND == 0) {
-                m = xin;
-              } else {
-                float mo;
-                if (KIND == 1) {
-                  mo = x0v[idx];
-                  if (affine) mo = add_rn(mul_rn(mo, e ? sc.y : sc.x), e ? sh.y : sh.x);
-                } else {
-                  mo = __uint_as_float(mv[idx]);
-                }
-                const float E = add_rn(__uint_as_float(ev[idx]), e ? bc.y : bc.x);
-                const float f = mul_rn(g.beta, wv_tanh(mul_rn(g.alpha, E)));
-                const float keep = mo > g.thresh ? 0.f : 1.f;
-                m = add_rn(add_rn(mul_rn(mul_rn(mo, g.decay), keep), xin), f);
-                ev[idx] = __float_as_uint(mul_rn(g.kappa, E));
-              }
-              mv[idx] = __float_as_uint(m);
-              sbits |= (m > g.thresh ? 1u : 0u) << idx;
-            }
-          }
-        }
-        if (!last) {
-          if (KIND > 0) {
-            tmem_st_16x256b_x4(t_addr + e_col + 32u * gq, ev);
-            tmem_st_16x256b_x4(t_addr + m_col + 32u * gq, mv);
-          }
-        }
-        // per pixel: zero outside the image (zero padding of the spread), bf16 row chunk, HBM word
-#pragma unroll
-        for (int rs = 0; rs < 2; ++rs) {
-          const int pi = 2 * h + rs;
-          const bool inside = (flags >> pi) & 1u;
-          uint32_t w4[4];
-          uint32_t word = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t b0 = inside ? (sbits >> (4 * k + 2 * rs)) & 1u : 0u;
-            const uint32_t b1 = inside ? (sbits >> (4 * k + 2 * rs + 1)) & 1u : 0u;
-            w4[k] = b0 * 0x3F80u + b1 * 0x3F800000u;
-            word |= (b0 | (b1 << 1)) << (8 * k);
-          }
-          word <<= 2 * q4;
-          if (gq == 0) wlo[pi] = word; else whi[pi] = word;
-          if (!last) {
-            const int a = 32 * q + 16 * h + 8 * rs + (lane >> 2);
-            const uint32_t chunk = (uint32_t)(2 * q4 + gq);
-            const uint32_t row = slot_row + (uint32_t)a;
-            sts128(ring + row * 128u + ((chunk ^ (row & 7u)) << 4), w4[0], w4[1], w4[2], w4[3]);
-            const int ry = a >> g.logWb, rx = a & (g.Wb - 1);
-            // mirrors: first image row of a block in slot A -> guard-bottom, last image row of a block in slot B -> guard-top
-            if (!(j & 1) && ry == 0) {
-              const uint32_t mr = (uint32_t)(GB + rx);
-              sts128(ring + mr * 128u + ((chunk ^ (mr & 7u)) << 4), w4[0], w4[1], w4[2], w4[3]);
-            }
-            if ((j & 1) && ry == g.R - 1) {
-              const uint32_t mr = (uint32_t)(GT + rx);
-              sts128(ring + mr * 128u + ((chunk ^ (mr & 7u)) << 4), w4[0], w4[1], w4[2], w4[3]);
-            }
-          }
-        }
-      }
-      // ---- HBM spikes: combine the four threads of a pixel, lane q4 writes pixel q4 ----
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        wlo[i] |= __shfl_xor_sync(0xffffffffu, wlo[i], 1);
-        wlo[i] |= __shfl_xor_sync(0xffffffffu, wlo[i], 2);
-        whi[i] |= __shfl_xor_sync(0xffffffffu, whi[i], 1);
-        whi[i] |= __shfl_xor_sync(0xffffffffu, whi[i], 2);
-      }
-      {
-        uint32_t lo = wlo[0], hi = whi[0];
-        int pp = pix[0];
-        bool ok = (flags >> 4) & 1u;
-#pragma unroll
-        for (int i = 1; i < 4; ++i)
-          if (q4 == i) { lo = wlo[i]; hi = whi[i]; pp = pix[i]; ok = (flags >> (4 + i)) & 1u; }
-        if (ok) {
-          uint2 v = make_uint2(lo, hi);
-          *reinterpret_cast<uint2*>(g.spikes + (int64_t)lvl * bits_tstride + (int64_t)pp * 2) = v;
-        }
-      }
-      // ---- hand over ----
-      if (!last) {
-        if (KIND > 0) tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->ready[lvl]);
-      } else {
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&ctl->e_free[j % kWvESlots]);
-          if (T > 2) mbar_arrive(&ctl->m_free[j % kWvMSlots]);
-        }
+      for (int k = 0; k < 2; ++k) {
+        const float2 v = ok ? ldg_stream2(src + 8 * k) : make_float2(-1e30f, -1e30f);
+        xv[4 * k + 2 * rs] = v.x;
+        xv[4 * k + 2 * rs + 1] = v.y;
       }
     }
+  };
+
+  WV_DECL;
+  for (int j = 0; j < nblk; ++j) {
+    WV_T(tpb);
+    const int p = p_begin + j;
+    int pix[4];
+    const uint32_t flags = locate(p, pix);
+    // L2 prefetch of the NEXT block's input tile (same band: R rows further down): one 256-byte pixel row per thread
+    if (r_in_band + 1 < g.hb) {
+      int pp = pix[0];
+      bool ok = flags & 1u;
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+        if (q4 == i) { pp = pix[i]; ok = (flags >> i) & 1u; }
+      if (ok) {
+        const float* nx = xt + ((int64_t)pp + (int64_t)g.R * g.W) * 64 - 2 * q4;
+        prefetch_l2(nx);
+        prefetch_l2(nx + 32);
+      }
+    }
+    float xc[8], xn[8], xn2[8];   // input current: chunk being computed / next / next-but-one (software pipeline, depth 2)
+    float x0c[8], x0n[8];         // level 1 only: x_0 = m_0 (an L2 hit: level 0 read it a block earlier; depth 1)
+    uint32_t mc[8], mn[8];        // levels >= 2: m_{t-1} from the scratch (L2; depth 1)
+    load_x(0, pix, flags, xc, xt);                    // in flight during the waits
+    load_x(1, pix, flags, xn, xt);
+    if (KIND == 1) load_x(0, pix, flags, x0c, x0p);
+
+    // ---- wait for this block's spread accumulator, the ring rows and the tensor-memory slots we are about to write ----
+    WV_T(tp0);
+    if (KIND > 0) {
+      wv_wait(&ctl->full[lvl][j & (kWvFullDepth - 1)], (uint32_t)(j / kWvFullDepth) & 1u);
+      WV_T(tp1);
+      WV_ACC(prof_full, tp1 - tp0);
+      if (KIND == 1 && !LAST && j >= kWvMSlots) wv_wait(&ctl->m_free[j % kWvMSlots], (uint32_t)(j / kWvMSlots - 1) & 1u);
+      // membranes of this block written by level lvl-1: phase (use * (T-2) + lvl - 2) of the slot's barrier
+      if (KIND > 1) wv_wait(&ctl->m_ready[j % kWvMSlots], (uint32_t)((j / kWvMSlots) * (g.T - 2) + lvl - 2) & 1u);
+      tc_fence_after_sync();
+    }
+    WV_T(tp2);
+    if (!LAST && j >= 1) wv_wait(&ctl->ring_free[lvl], (uint32_t)(j - 1) & 1u);
+    WV_T(tp3);
+    WV_ACC(prof_ring, tp3 - tp2);
+    WV_ACC(prof_pre, tp0 - tpb);
+
+    const uint32_t e_col = (uint32_t)(j % kWvESlots) * 64u;
+    // membrane scratch of this block: [chunk u][thread of the level][8 values] -> two coalesced 16-byte accesses per chunk
+    float* mslot = g.mscr + ((size_t)blockIdx.x * kWvMSlots + (size_t)(j % kWvMSlots)) * kWvMSlotFloats + (threadIdx.x & 127) * 8;
+    const uint32_t slot_row = (uint32_t)((j & 1) ? SB : SA);
+    uint32_t wlo[2] = {0u, 0u}, whi[2] = {0u, 0u};     // HBM spike words (channels 0-31 / 32-63) of the half's two pixels
+    auto load_m = [&](int u, uint32_t (&m)[8]) {
+      const uint4 m0 = ld_cg_u4(mslot + u * 1024), m1 = ld_cg_u4(mslot + u * 1024 + 4);
+      m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+    };
+    if (KIND > 1) load_m(0, mc);
+
+#pragma unroll 1
+    for (int u = 0; u < 8; ++u) {
+      const int h = u >> 2, gq = (u >> 1) & 1, kh = u & 1, cb = 16 * (u & 3);     // cb: first channel of the chunk (+ 2 q4 + e)
+      // next chunk's loads first, then this chunk's tensor-memory load: all in flight while the previous results retire
+      if (u + 2 < 8) load_x(u + 2, pix, flags, xn2, xt);
+      if (u + 1 < 8) {
+        if (KIND == 1) load_x(u + 1, pix, flags, x0n, x0p);
+        if (KIND > 1) load_m(u + 1, mn);
+      }
+      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * q + 16 * h) << 16) + (uint32_t)cb;
+      uint32_t ev[8];
+      if (KIND > 0) tmem_ld_16x256b_x2(t_addr + e_col, ev);
+      float2 scv[2], shv[2];
+      if (AFF) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { scv[k] = lds64f(c_scale + (cb + 8 * k) * 4); shv[k] = lds64f(c_shift + (cb + 8 * k) * 4); }
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx)
+          xc[idx] = add_rn(mul_rn(xc[idx], (idx & 1) ? scv[idx >> 2].y : scv[idx >> 2].x), (idx & 1) ? shv[idx >> 2].y : shv[idx >> 2].x);
+      }
+      uint32_t mv[8];       // m_t
+      float2 bcv[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      if (KIND > 0) {
+        bcv[0] = lds64f(c_bconst + cb * 4);
+        bcv[1] = lds64f(c_bconst + (cb + 8) * 4);
+        tmem_ld_wait();
+      }
+      uint32_t w2[2][2];      // {0,1} bf16 pairs of the chunk's two pixels (4 channels = 8 bytes each) for the ring
+      uint32_t word[2] = {0u, 0u};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          uint32_t sp[2];      // all-ones where the neuron fires
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int idx = 4 * k + 2 * rs + e;
+            float m;
+            if (KIND == 0) {
+              m = xc[idx];
+            } else {
+              float mo;
+              if (KIND == 1) {
+                mo = x0c[idx];
+                if (AFF) mo = add_rn(mul_rn(mo, e ? scv[k].y : scv[k].x), e ? shv[k].y : shv[k].x);
+              } else {
+                mo = __uint_as_float(mc[idx]);
+              }
+              const float pre = add_rn(mo > g.thresh ? 0.f : mul_rn(mo, g.decay), xc[idx]);
+              const float E = add_rn(__uint_as_float(ev[idx]), e ? bcv[k].y : bcv[k].x);
+              const float y = exp2f_approx(mul_rn(E, c1));
+              const float f = __fmaf_rn(rcp_approx(add_rn(y, 1.f)), nb2, g.beta);      // beta * tanh(alpha * E)
+              m = add_rn(pre, f);
+              ev[idx] = __float_as_uint(mul_rn(g.kappa, E));
+            }
+            mv[idx] = __float_as_uint(m);
+            sp[e] = m > g.thresh ? 0xffffffffu : 0u;
+          }
+          w2[rs][k] = __byte_perm(sp[0], sp[1], 0x5410) & 0x3F803F80u;          // low half: channel e = 0, high half: e = 1
+          word[rs] |= ((sp[0] & 1u) | (sp[1] & 2u)) << (8 * k);
+        }
+      }
+      if (!LAST && KIND > 0) {
+        tmem_st_16x256b_x2(t_addr + e_col, ev);
+        st_cg_u4(mslot + u * 1024, make_uint4(mv[0], mv[1], mv[2], mv[3]));
+        st_cg_u4(mslot + u * 1024 + 4, make_uint4(mv[4], mv[5], mv[6], mv[7]));
+      }
+      const uint32_t wshift = (uint32_t)(16 * kh + 2 * q4);
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        if (gq == 0) wlo[rs] |= word[rs] << wshift; else whi[rs] |= word[rs] << wshift;
+        if (!LAST) {
+          const int a = a0 + 16 * h + 8 * rs;
+          const uint32_t chunk = (uint32_t)(2 * q4 + gq);
+          const uint32_t row = slot_row + (uint32_t)a;
+          sts64(ring + row * 128u + ((chunk ^ (row & 7u)) << 4) + 8u * kh, w2[rs][0], w2[rs][1]);
+          const int ry = a >> g.logWb, rx = a & (g.Wb - 1);
+          // mirrors: first image row of a block in slot A -> guard-bottom, last image row of a block in slot B -> guard-top
+          if (!(j & 1) && ry == 0) {
+            const uint32_t mr = (uint32_t)(GB + rx);
+            sts64(ring + mr * 128u + ((chunk ^ (mr & 7u)) << 4) + 8u * kh, w2[rs][0], w2[rs][1]);
+          }
+          if ((j & 1) && ry == g.R - 1) {
+            const uint32_t mr = (uint32_t)(GT + rx);
+            sts64(ring + mr * 128u + ((chunk ^ (mr & 7u)) << 4) + 8u * kh, w2[rs][0], w2[rs][1]);
+          }
+        }
+      }
+      if ((u & 3) == 3) {
+        // ---- HBM spikes of this half: combine the four threads of a pixel; lane q4 = 0 / 1 writes pixel rs = 0 / 1 ----
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          wlo[rs] |= __shfl_xor_sync(0xffffffffu, wlo[rs], 1);
+          wlo[rs] |= __shfl_xor_sync(0xffffffffu, wlo[rs], 2);
+          whi[rs] |= __shfl_xor_sync(0xffffffffu, whi[rs], 1);
+          whi[rs] |= __shfl_xor_sync(0xffffffffu, whi[rs], 2);
+        }
+        const int rsel = q4 & 1;
+        const int pA = h ? pix[2] : pix[0], pB = h ? pix[3] : pix[1];
+        if (q4 < 2 && ((flags >> (4 + 2 * h + rsel)) & 1u))
+          *reinterpret_cast<uint2*>(g.spikes + (int64_t)lvl * bits_tstride + (int64_t)(rsel ? pB : pA) * 2) =
+              make_uint2(rsel ? wlo[1] : wlo[0], rsel ? whi[1] : whi[0]);
+        wlo[0] = wlo[1] = whi[0] = whi[1] = 0u;
+      }
+      // rotate the software pipeline
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xc[i] = xn[i];
+        xn[i] = xn2[i];
+        if (KIND == 1) x0c[i] = x0n[i];
+        if (KIND > 1) mc[i] = mn[i];
+      }
+    }
+    WV_T(tp4);
+    WV_ACC(prof_work, tp4 - tp3);
+    // ---- hand over ----
+    if (!LAST) {
+      if (KIND > 0) tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (KIND > 0) mbar_arrive(&ctl->m_ready[j % kWvMSlots]);     // release: this warp's membrane stores are visible
+        mbar_arrive(&ctl->ready[lvl]);
+      }
+    } else {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ctl->e_free[j % kWvESlots]);
+        if (g.T > 2) mbar_arrive(&ctl->m_free[j % kWvMSlots]);
+      }
+    }
+    // ---- next stream entry ----
+    if (band_valid && r_in_band < g.hb) ++r_in_band; else set_band(p + 1);
   }
+  WV_REPORT;
 }
 
-__global__ void __launch_bounds__(32 * (4 * kWvMaxT + 1), 1)
+__global__ void __launch_bounds__(kWvThreads, 1)
 k_lif_ecs_wave64(const WvArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -416,7 +538,7 @@ k_lif_ecs_wave64(const WvArgs g) {
       for (int k = 0; k < kWvFullDepth; ++k) mbar_init(&ctl->full[t][k], 1);
     }
     for (int k = 0; k < kWvESlots; ++k) mbar_init(&ctl->e_free[k], 4);
-    for (int k = 0; k < kWvMSlots; ++k) mbar_init(&ctl->m_free[k], 4);
+    for (int k = 0; k < kWvMSlots; ++k) { mbar_init(&ctl->m_free[k], 4); mbar_init(&ctl->m_ready[k], 4); }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&ctl->tmem_base);
@@ -428,68 +550,56 @@ k_lif_ecs_wave64(const WvArgs g) {
   const uint32_t rings_u32 = smem_u32(rings);
   const int SA = 8 + g.Wb, SB = SA + 128;
 
-  if (warp == 4 * T) {
-    // =============================== MMA issuer (event driven) ===============================
+  if (warp >= kWvIssuerWarp) {
+    if (warp - kWvIssuerWarp + 1 < T) {
+    // =============================== MMA issuers: one warp per producing level ===============================
+    // Issuer t sleeps on ready[t] (hardware-suspended wait, no polling: a polling issuer took most of its scheduler
+    // partition's issue slots from the four level warps that share it) and, when level t has finished block j, issues
+    //   taps ky = +1 of block j-1 for level t+1 (they needed the first image row of block j)  -> full[t+1] of block j-1
+    //   taps ky = -1, 0 of block j for level t+1                                              -> ring_free[t]
+    // One thread issues every MMA into a given accumulator; accumulation rounds of different levels on the same E slot are
+    // separated by the level that reads and rewrites it in between (ready / full handshakes).
+    const int t = warp - kWvIssuerWarp;
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
     const uint64_t db0 = umma_desc_sw128(smem_u32(w_smem));
-    int nj[kWvMaxT] = {0, 0, 0, 0};
-    int remaining = 0;
-    for (int t = 0; t + 1 < T; ++t) remaining += (P - t > 0 ? P - t : 0);
-    long long t_last = clock64();
-    while (remaining > 0) {
-      bool progress = false;
-      for (int t = 0; t + 1 < T; ++t) {
-        const int j = nj[t];
-        if (j > P - 1 - t) continue;
-        if (!mbar_test(&ctl->ready[t], (uint32_t)j & 1u)) continue;
-        const bool has_p1 = j <= P - 2 - t;              // level t+1 processes blocks 0 .. P-2-t
-        if (t == 0 && has_p1 && j >= kWvESlots &&
-            !mbar_test(&ctl->e_free[j % kWvESlots], (uint32_t)(j / kWvESlots - 1) & 1u))
-          continue;
-        tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t ring = rings_u32 + (uint32_t)t * (uint32_t)ring_bytes;
-          if (j >= 1) {
-            // taps ky = +1 of block j-1 (level t+1): rows of block j-1 and the first image row of block j
-            const int jb = j - 1;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(jb % kWvESlots) * 64u;
-            const uint32_t base_row = (uint32_t)((jb & 1) ? SB : SA);
+    const uint32_t ring = rings_u32 + (uint32_t)t * (uint32_t)ring_bytes;
+    for (int j = 0; j <= P - 1 - t; ++j) {
+      wv_wait(&ctl->ready[t], (uint32_t)j & 1u);
+      const bool has_p1 = j <= P - 2 - t;              // level t+1 processes blocks 0 .. P-2-t
+      // the accumulator slot of block j is recycled from block j - kWvESlots: the last level must have read it
+      if (t == 0 && has_p1 && j >= kWvESlots) wv_wait(&ctl->e_free[j % kWvESlots], (uint32_t)(j / kWvESlots - 1) & 1u);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        if (j >= 1) {
+          const int jb = j - 1;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(jb % kWvESlots) * 64u;
+          const uint32_t base_row = (uint32_t)((jb & 1) ? SB : SA);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint64_t da = umma_desc_sw128(ring + (base_row + (uint32_t)g.Wb + (uint32_t)kx - 1u) * 128u);
-              const uint64_t db = db0 + (uint64_t)((6 + kx) * 512);
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint64_t da = umma_desc_sw128(ring + (base_row + (uint32_t)g.Wb + (uint32_t)kx - 1u) * 128u);
+            const uint64_t db = db0 + (uint64_t)((6 + kx) * 512);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
-            }
-            umma_commit(&ctl->full[t + 1][jb & (kWvFullDepth - 1)]);
+            for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
           }
-          if (has_p1) {
-            // taps ky = -1, 0 of block j (level t+1): last image row of block j-1 (or the mirrored guard) and block j
-            const uint32_t d_tmem = tmem_base + (uint32_t)(j % kWvESlots) * 64u;
-            const uint32_t base_row = (uint32_t)((j & 1) ? SB : SA);
-#pragma unroll
-            for (int tap = 0; tap < 6; ++tap) {
-              const int ky = tap / 3 - 1, kx = tap % 3 - 1;
-              const uint64_t da = umma_desc_sw128(ring + (uint32_t)((int)base_row + ky * g.Wb + kx) * 128u);
-              const uint64_t db = db0 + (uint64_t)(tap * 512);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (t > 0 || tap > 0 || kk > 0) ? 1u : 0u);
-            }
-          }
-          umma_commit(&ctl->ring_free[t]);
+          umma_commit(&ctl->full[t + 1][jb & (kWvFullDepth - 1)]);
         }
-        __syncwarp();
-        ++nj[t];
-        --remaining;
-        progress = true;
+        if (has_p1) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(j % kWvESlots) * 64u;
+          const uint32_t base_row = (uint32_t)((j & 1) ? SB : SA);
+#pragma unroll
+          for (int tap = 0; tap < 6; ++tap) {
+            const int ky = tap / 3 - 1, kx = tap % 3 - 1;
+            const uint64_t da = umma_desc_sw128(ring + (uint32_t)((int)base_row + ky * g.Wb + kx) * 128u);
+            const uint64_t db = db0 + (uint64_t)(tap * 512);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (t > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&ctl->ring_free[t]);
       }
-      if (progress) {
-        t_last = clock64();
-      } else if (clock64() - t_last > 4000000000LL) {
-        if (lane == 0) printf("ecsy: lif_wave issuer stalled, block %d (nj %d %d %d, P %d)\n", blockIdx.x, nj[0], nj[1], nj[2], P);
-        __trap();
-      }
+      __syncwarp();
+    }
     }
   } else if (warp < 4 * T) {
     const int lvl = warp >> 2;
@@ -497,10 +607,16 @@ k_lif_ecs_wave64(const WvArgs g) {
     LevelCtx c;
     c.ctl = ctl; c.tmem_base = tmem_base; c.rings_u32 = rings_u32; c.ring_bytes = ring_bytes;
     c.c_bconst = smem_u32(s_bconst); c.c_scale = smem_u32(s_scale); c.c_shift = smem_u32(s_shift);
-    c.p_begin = p_begin; c.seg0 = seg0; c.seg1 = seg1; c.P = P; c.lvl = lvl;
-    if (lvl == 0) wv_level<0, false>(g, c);
-    else if (lvl == 1) { if (last) wv_level<1, true>(g, c); else wv_level<1, false>(g, c); }
-    else { if (last) wv_level<2, true>(g, c); else wv_level<2, false>(g, c); }
+    c.p_begin = (int)p_begin; c.seg0 = (int)seg0; c.seg1 = (int)seg1; c.P = P; c.lvl = lvl;
+    if (affine) {
+      if (lvl == 0) wv_level<0, false, true>(g, c);
+      else if (lvl == 1) { if (last) wv_level<1, true, true>(g, c); else wv_level<1, false, true>(g, c); }
+      else { if (last) wv_level<2, true, true>(g, c); else wv_level<2, false, true>(g, c); }
+    } else {
+      if (lvl == 0) wv_level<0, false, false>(g, c);
+      else if (lvl == 1) { if (last) wv_level<1, true, false>(g, c); else wv_level<1, false, false>(g, c); }
+      else { if (last) wv_level<2, true, false>(g, c); else wv_level<2, false, false>(g, c); }
+    }
   }
 
   tc_fence_before_sync();
@@ -541,10 +657,22 @@ extern "C" int ecsy_lif_ecs_wave_supported(int T, int C, int H, int W) {
   return (C == kWvC && T >= 2 && T <= kWvMaxT && H >= 1 && wv_plan(T, W, &R, &Wb, &nb)) ? 1 : 0;
 }
 
+static int64_t wv_grid(int64_t S) {
+  // every CTA should own at least ~8 blocks of useful work next to its warm-up / cool-down blocks
+  int64_t grid = ecsy_num_sms();
+  if (S / 8 < grid) grid = S / 8 > 0 ? S / 8 : 1;
+  return grid;
+}
+
+extern "C" size_t ecsy_lif_ecs_wave_ws_bytes(int T, int64_t N, int H, int W, int C) {
+  (void)T; (void)N; (void)H; (void)W; (void)C;
+  return (size_t)ecsy_num_sms() * kWvMSlots * kWvMSlotFloats * sizeof(float) + 256;
+}
+
 extern "C" int ecsy_lif_ecs_wave_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                                      const void* w_eff, const float* bconst, uint32_t* spikes, int T, int64_t N, int H,
                                      int W, int C, float thresh, float decay, float alpha, float beta, float kappa,
-                                     void* stream) {
+                                     void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ECSY_CHECK_ARG(x && spikes && w_eff && bconst && N > 0 && H > 0 && W > 0, "lif_ecs_wave_fwd: bad arguments");
   ECSY_CHECK_ARG(ecsy_lif_ecs_wave_supported(T, C, H, W), "lif_ecs_wave_fwd: unsupported T=%d / C=%d / W=%d (C == 64, 2 <= T <= 4)",
@@ -569,10 +697,14 @@ extern "C" int ecsy_lif_ecs_wave_fwd(const float* x, int64_t x_tstride, const fl
     ECSY_CUDA(cudaFuncSetAttribute(k_lif_ecs_wave64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  // every CTA should own at least ~8 blocks of useful work next to its warm-up / cool-down blocks
-  int64_t grid = ecsy_num_sms();
-  if (g.S / 8 < grid) grid = g.S / 8 > 0 ? g.S / 8 : 1;
-  k_lif_ecs_wave64<<<(int)grid, 32 * (4 * T + 1), smem, st>>>(g);
+  const int64_t grid = wv_grid(g.S);
+  const size_t need = ecsy_lif_ecs_wave_ws_bytes(T, N, H, W, C);
+  if (T > 2 && (ws == nullptr || ws_bytes < need)) {
+    ecsy_set_error("lif_ecs_wave_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return ECSY_ERR_WS;
+  }
+  g.mscr = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  k_lif_ecs_wave64<<<(int)grid, kWvThreads, smem, st>>>(g);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }

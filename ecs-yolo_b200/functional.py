@@ -377,6 +377,19 @@ def make_lif_w(dw_w, dw_b, pw_w, pw_b, Cp: Optional[int] = None) -> LifW:
 # ------------------------------------------------------------------------------------------------
 # operators
 # ------------------------------------------------------------------------------------------------
+_wave_ws_cache = {}
+
+
+def _wave_ws(dev, nbytes: int) -> torch.Tensor:
+    """Membrane scratch of the wavefront LIF kernel: one buffer per (device, stream), reused by every layer (the kernels of
+    a stream run one after the other), so it stays resident in the L2."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    t = _wave_ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = _wave_ws_cache[key] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    return t
+
+
 def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
             ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25, save_mem: bool = False):
     """mem_update.forward (models/common.py:252-283) -> bit-packed spikes; with save_mem also the membranes
@@ -397,11 +410,12 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
             and _cabi.lib().ecsy_lif_ecs_wave_supported(T, C, H, W)):
         sc, sh = affine if affine is not None else (None, None)
         flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
+        ws = _wave_ws(dev, _cabi.lib().ecsy_lif_ecs_wave_ws_bytes(T, N, H, W, C))
         with _timed("lif_ecs", 1):
             _cabi.check(_cabi.lib().ecsy_lif_ecs_wave_fwd(
                 _p(x.data), x.tstride, _p(sc), _p(sh), _p(w.w_wave), _p(w.bconst), _p(bits), T, N, H, W, C,
-                float(thresh), float(decay), float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _st()),
-                "lif_ecs_wave_fwd")
+                float(thresh), float(decay), float(alpha), float(beta), float(1.0 - 1.0 / ecs_tau), _p(ws), ws.numel(),
+                _st()), "lif_ecs_wave_fwd")
         return Spikes(bits, C, Cr)
     if (not save_mem and w is not None and w.w_eff is not None and _state["lif_fused"]
             and _cabi.lib().ecsy_lif_ecs_fused_supported(T, C)):

@@ -79,11 +79,14 @@ int ecsy_lif_ecs_fused_fwd(const float* x, int64_t x_tstride, const float* in_sc
  * bits are written (reference loop: models/common.py:252-283, state `mem` / `ecs` carried across `for i in
  * range(time_window)`).  w_eff: [9][64][64] bf16, tap-major, W_eff[tap][co][kk] = pw[co][c(kk)] * dw[c(kk)][tap] with
  * the channel permutation c(kk) = 8 * ((kk % 16) / 2) + 2 * (kk / 16) + kk % 2 (functional.pack_lif_wave_weight);
- * bconst as above.  No workspace. */
+ * bconst as above.  ws: ecsy_lif_ecs_wave_ws_bytes() of CTA-private membrane scratch (28 MB, written and re-read within
+ * microseconds: it lives in the L2). */
 int ecsy_lif_ecs_wave_supported(int T, int C, int H, int W);
+size_t ecsy_lif_ecs_wave_ws_bytes(int T, int64_t N, int H, int W, int C);
 int ecsy_lif_ecs_wave_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                           const void* w_eff, const float* bconst, uint32_t* spikes, int T, int64_t N, int H, int W,
-                          int C, float thresh, float decay, float alpha, float beta, float kappa, void* stream);
+                          int C, float thresh, float decay, float alpha, float beta, float kappa, void* ws,
+                          size_t ws_bytes, void* stream);
 
 size_t ecsy_lif_silu_ws_bytes(int T, int64_t N, int H, int W, int C, int splits);
 int ecsy_lif_silu_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
