@@ -139,13 +139,20 @@ __device__ __forceinline__ void st4h(void* base, int64_t i, float a, float b, fl
   reinterpret_cast<uint2*>(base)[i] = pk;
 }
 
-// Fast-precision tanh: 1 - 2 / (exp(2v) + 1) with ex2.approx / rcp.approx -- ABSOLUTE error ~1e-7 (what the membrane
-// sees: f = beta * tanh(e)), against 2^-11 ~ 5e-4 for the hardware tanh.approx it replaces, which alone moved the
-// membrane by 1.2e-4 and cost ~0.03 % of the spikes (tests/test_gpu_baseline_cfgs.py).  Two MUFU ops instead of one in a
-// kernel that waits on HBM.  Saturates correctly: exp -> inf gives 1, exp -> 0 gives -1.
+// Fast-precision tanh: the hardware approximation (one MUFU op, absolute error ~2^-11).  Measured on the BASELINE plans
+// (tests/test_gpu_baseline_cfgs.py, fast precision, every neuron fed the oracle's input): replacing it by the 1e-7-accurate
+// 1 - 2 / (exp(2v) + 1) (two MUFU ops + three FP32 ops) did not change the spike agreement beyond the fifth digit but made
+// the ECS step kernels, which are closer to the MUFU / issue limit than to the HBM limit, 20 % slower (lif_ecs 32.6 ->
+// 40.1 ms per resnet34 batch-64 step).  ECSY_ACCURATE_TANH selects the accurate form at compile time.
 __device__ __forceinline__ float tanh_fast(float v) {
+#ifdef ECSY_ACCURATE_TANH
   const float y = __expf(2.f * v);
   return 1.f - __fdividef(2.f, y + 1.f);
+#else
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+#endif
 }
 
 template <bool HALF>

@@ -164,6 +164,11 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
 }
 // beta * tanh(alpha E) = beta - 2 beta / (2^(2 log2(e) alpha E) + 1): ex2.approx + rcp.approx, absolute error ~1e-7 (see
 // elementwise.cu: tanh_fast); 2^t -> inf gives beta, 2^t -> 0 gives -beta.
+__device__ __forceinline__ float tanh_approx(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 __device__ __forceinline__ float exp2f_approx(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -405,8 +410,12 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
               }
               const float pre = add_rn(mo > g.thresh ? 0.f : mul_rn(mo, g.decay), xc[idx]);
               const float E = add_rn(__uint_as_float(ev[idx]), e ? bcv[k].y : bcv[k].x);
+#ifdef ECSY_ACCURATE_TANH
               const float y = exp2f_approx(mul_rn(E, c1));
               const float f = __fmaf_rn(rcp_approx(add_rn(y, 1.f)), nb2, g.beta);      // beta * tanh(alpha * E)
+#else
+              const float f = mul_rn(g.beta, tanh_approx(mul_rn(g.alpha, E)));         // one MUFU op (see elementwise.cu)
+#endif
               m = add_rn(pre, f);
               ev[idx] = __float_as_uint(mul_rn(g.kappa, E));
             }

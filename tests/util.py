@@ -37,10 +37,15 @@ class forced_spikes:
     `ref_spikes`: {module name (state_dict prefix without the trailing dot): [T,N,C,H,W] {0,1} tensor}; `prefix` is put in
     front of root's own module names ("model.0." for a bare block, "" for a whole model)."""
 
-    def __init__(self, E, root, ref_spikes, prefix="", force=True):
+    def __init__(self, E, root, ref_spikes, prefix="", force=True, gate_spikes=None):
+        """gate_spikes (optional): the spikes the agreement is MEASURED against when they differ from the forced ones --
+        fast precision: the oracle neuron applied to the bf16-weight conv output it actually receives (the forced spikes
+        stay those of the fp32 run, so producer and consumer see the same tensors in both implementations).  The
+        agreement with the forced (fp32-run) spikes is then kept in `agree_fp32`."""
         self.E, self.ref, self.force = E, ref_spikes, force
+        self.gate = gate_spikes
         self.names = {id(mod): prefix + n for n, mod in root.named_modules() if isinstance(mod, E.common.mem_update)}
-        self.agree, self.rate = {}, {}
+        self.agree, self.rate, self.agree_fp32 = {}, {}, {}
 
     def __enter__(self):
         E, outer = self.E, self
@@ -54,7 +59,10 @@ class forced_spikes:
             ref = outer.ref[name]
             got = sp.to_act().to_ref()
             refc = ref.to(got.device)
-            outer.agree[name] = float((got == refc).float().mean())
+            outer.agree_fp32[name] = float((got == refc).float().mean())
+            outer.agree[name] = outer.agree_fp32[name]
+            if outer.gate is not None and name in outer.gate:
+                outer.agree[name] = float((got == outer.gate[name].to(got.device)).float().mean())
             outer.rate[name] = float(refc.mean())
             if not outer.force:
                 return sp
