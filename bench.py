@@ -78,13 +78,29 @@ class ClockSampler:
 
 
 def measured_traffic(model, batch, T, precision):
-    """DRAM bytes per step of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None
-    when no capture exists for this exact configuration."""
+    """{"lif": {...}, "conv": {...}}: DRAM bytes per step of the two dominant operators from the committed ncu capture
+    (profiles/traffic.json, raw CSV beside it), or None when no capture exists for this exact configuration."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
-    ent = json.load(open(path)).get(f"{model}|{batch}|{T}|{precision}")
-    return ent["dram_bytes_per_step"] if ent else None
+    return json.load(open(path)).get(f"{model}|{batch}|{T}|{precision}")
+
+
+def parity_record(args, parity_ips):
+    """What the benchmarked precision was VALIDATED at: the teacher-forced per-layer figures of the BASELINE plans measured
+    on a B200 by tests/test_gpu_baseline_cfgs.py (committed summary: profiles/parity_summary.json), and the throughput of
+    the same step in `parity` precision (bf16 hi + lo weight planes, fp32 state)."""
+    rec = {"precision": args.precision,
+           "gates": "tests/test_gpu_baseline_cfgs.py (resnet10 / resnet34 / resnet18 plans at 640x640, every layer "
+                    "teacher-forced on the oracle's input, both precisions): spikes >= 99.9 % per neuron, real tensors, head "
+                    "and loss <= 1e-3"}
+    path = os.path.join(ROOT, "profiles", "parity_summary.json")
+    if os.path.exists(path):
+        summ = json.load(open(path))
+        rec["measured"] = summ.get(f"{args.model}|{args.precision}") or summ
+    if parity_ips is not None:
+        rec["parity_precision_images_per_s"] = parity_ips
+    return rec
 
 
 def load_cfg(name):
@@ -141,8 +157,9 @@ def cpu_reference(model_name, T, img, sample_imgs, steps, warmup, threads, event
     return sample_imgs * steps / dt, dt / steps
 
 
-def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload):
-    """fwd + loss + bwd + SGD-nesterov step per batch (train.py:555-582 shape of a step).  Stack-A models (Detect head)
+def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload, emit_line=True):
+    """fwd + loss + bwd + SGD-nesterov step per batch (train.py:555-582 shape of a step).  Returns the JSON record (rank 0;
+    None elsewhere) and, with emit_line, prints it as the bench line (`--mode train`).  Stack-A models (Detect head)
     train against the reference's ComputeLoss (utils/loss.py:130-234: SIoU + BCE, build_targets), DDetect models (Stack B)
     against utils/loss_tal.py:105-215 (TaskAlignedAssigner + box + DFL + BCE), both on COCO-shaped synthetic targets and
     computed on the device (ecsy_yolo_loss / ecsy_tal_loss); `--loss quadratic` is a synthetic quadratic
@@ -207,6 +224,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         step(x)
     barrier()
     F.launches["n"] = 0
+    F.launches_by_op.clear()
     for k in F.flops:
         F.flops[k] = 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -218,6 +236,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = F.launches["n"]
+    launch_by_op = dict(F.launches_by_op)
     flops = dict(F.flops)
     # per-operator breakdown from ONE extra step outside the timed region (two CUDA events per operator cost host
     # time, and the training step is close to launch-bound)
@@ -226,6 +245,37 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
     barrier()
     per_op = {k: v * args.steps for k, v in F.profile_end().items()}
     barrier()
+    # the exchange step (train.py:419 DDP, :559-567): the same steps WITHOUT the gradient all-reduce (no_sync) -> what of the
+    # communication is not hidden behind the backward kernels
+    comm = None
+    if dist is not None:
+        n_sync = min(args.steps, 5)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        for _ in range(n_sync):
+            step(x)
+        e1.record()
+        with net.no_sync():
+            for _ in range(n_sync):
+                step(x)
+        e2.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1) / n_sync, e1.elapsed_time(e2) / n_sync], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        gbytes = sum(p.numel() * 4 for p in model.parameters() if p.requires_grad)
+        try:
+            bucket_sizes = [int(v) for v in str(net._get_ddp_logging_data().get("bucket_sizes", "")).split(",") if v.strip()]
+        except Exception:
+            bucket_sizes = []
+        comm = {"collective": "NCCL all-reduce (sum) of the fp32 gradients through DistributedDataParallel, overlapped with "
+                              "the backward kernels (train.py:419, :559-567)",
+                "allreduce_bytes_per_step": gbytes, "bucket_cap_mb": 64, "buckets": len(bucket_sizes) or None,
+                "largest_bucket_bytes": max(bucket_sizes) if bucket_sizes else None,
+                "ms_per_step_with_allreduce": float(tt[0]), "ms_per_step_no_sync": float(tt[1]),
+                "exposed_comm_ms_per_step": float(tt[0] - tt[1]),
+                "exposed_note": "step time with the all-reduce minus the same step under no_sync(); what stays exposed is the "
+                                "last bucket(s): the gradients of the first layers are ready only when the backward ends"}
+        opt.zero_grad(set_to_none=True)
     t0 = time.perf_counter()
     loss_host = 0.0
     for _ in range(0 if args.no_e2e else args.steps):
@@ -239,9 +289,9 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
-        if dist is not None:
+        if dist is not None and emit_line:
             dist.destroy_process_group()
-        return
+        return None
     imgs = args.batch * world * args.steps
     pk = peaks()
     conv_ms = (per_op.get("spike_conv", 0.0) + per_op.get("conv_dgrad", 0.0) + per_op.get("conv_wgrad", 0.0)
@@ -270,9 +320,28 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         "breakdown_ms_per_step": {k: v / args.steps for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
         "last_loss": loss_host,
     }
-    emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    line["config"]["lif_state"] = ("membranes + ECS traces of the forward kept for the backward (set_lif_store, 8 B per "
+                                   "element-step; falls back to recomputation per layer when memory is short)"
+                                   if F._state["lif_store"] else "membranes recomputed in the backward")
+    line["config"]["optimizer"] = ("fused SGD-Nesterov + EMA, one multi-tensor launch (ecsy_sgd_ema_step)" if args.optim == "fused"
+                                   else "torch.optim.SGD (nesterov)")
+    # the LIF backward against its algorithmic traffic (gout 4 + membrane 4 + gx 4 bytes per element-step)
+    lif_elems = flops.get("lif_elems", 0.0) / args.steps
+    lb_ms = per_op.get("lif_ecs_bwd", 0.0) / args.steps
+    if lb_ms > 0 and lif_elems > 0:
+        gbs = lif_elems * 12.0 / (lb_ms * 1e-3) / 1e9
+        line["roofline_lif_bwd"] = {"kernel": "ecsy_lif_ecs_bwd (reverse scan + spread dgrad / wgrad)", "bound": "hbm",
+                                    "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                    "traffic": None, "kernel_ms_per_step": lb_ms,
+                                    "algorithmic_bytes_per_step": lif_elems * 12.0}
+    if comm is not None:
+        line["allreduce"] = comm
+    line["launches_by_op_per_step"] = {k: v / args.steps for k, v in sorted(launch_by_op.items(), key=lambda kv: -kv[1])}
+    if emit_line:
+        emit(line)
+        if dist is not None:
+            dist.destroy_process_group()
+    return line
 
 
 _REAL_STDOUT = None
@@ -311,7 +380,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs under ncu may lower this")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
-    ap.add_argument("--cpu-sample", type=int, default=1, help="images per CPU step")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU step")
     ap.add_argument("--ref-autocast", action="store_true", help="--ref-device cuda only: run the eager port under fp16 autocast")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu = the reference arm proper (host cores); cuda = the same stock-PyTorch "
@@ -324,6 +393,10 @@ def main():
     ap.add_argument("--loss", default="yolo", choices=["yolo", "quadratic"],
                     help="training: the reference's ComputeLoss on the device (utils/loss.py for Detect models, utils/loss_tal.py for "
                          "DDetect models) or a synthetic quadratic on the raw head outputs")
+    ap.add_argument("--no-train", action="store_true", help="infer mode: skip the `train` sub-record")
+    ap.add_argument("--no-parity-leg", action="store_true", help="skip the parity-precision timing of the same step")
+    ap.add_argument("--train-model", default="resnet18", help="model of the `train` sub-record (BASELINE configs[2])")
+    ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train: forward + loss + backward + SGD step (DDP gradient all-reduce when --gpus > 1)")
     args = ap.parse_args()
@@ -411,6 +484,7 @@ def main():
             z, _ = model(x)
         barrier()
         F.launches["n"] = 0
+        F.launches_by_op.clear()
         for k in F.flops:
             F.flops[k] = 0.0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -422,6 +496,7 @@ def main():
             barrier()
         ms_total = ev0.elapsed_time(ev1)
         launches = F.launches["n"]
+        launch_by_op = dict(F.launches_by_op)
         flops = dict(F.flops)
         # per-operator CUDA-event breakdown (and the dominant kernel's duration for `roofline`) from ONE extra step
         # outside the timed region, scaled to `steps`
@@ -467,10 +542,51 @@ def main():
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    # the same step in `parity` precision (bf16 hi + lo weight planes, fp32 ECS state, tanhf): the precision whose
+    # real-valued outputs match the fp32 reference to 1e-5; two timed steps
+    parity_ips = None
+    if args.precision != "parity" and not args.no_parity_leg:
+        E.set_precision("parity")
+        with torch.no_grad():
+            model(x)
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(2):
+                model(x)
+            p1.record()
+            barrier()
+        parity_ips = args.batch * world * 2 / (p0.elapsed_time(p1) * 1e-3)
+        E.set_precision(args.precision)
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, parity_ips or 0.0], device="cuda", dtype=torch.float64)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[:2], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[2:], op=dist.ReduceOp.MIN)
     ms_total, e2e_ms = float(t[0]), float(t[1])
+    parity_ips = float(t[2]) if parity_ips is not None else None
+
+    # "fwd + train" half of the metric (BASELINE configs[2]): surrogate-gradient BPTT training of the train model with the
+    # reference's loss on the device, fused optimizer, DDP gradient all-reduce when launched on several GPUs
+    train_rec = None
+    if not args.no_train:
+        del model, x, bufs, z, zz
+        torch.cuda.empty_cache()
+        targs = argparse.Namespace(**vars(args))
+        targs.model, targs.batch, targs.mode = args.train_model, args.train_batch, "train"
+        targs.steps, targs.warmup, targs.no_e2e = min(args.steps, 10), 3, False
+        torch.manual_seed(0)
+        is_bt = any(row[2] == "DDetect" for row in load_cfg(targs.model)["head"])
+        tmodel = (E.yolo_snn.DetectionModel if is_bt else E.yolo.Model)(E.cfg_path(targs.model)).cuda()
+        gt = torch.Generator().manual_seed(2000 + rank)
+        xt_host = torch.rand(targs.batch, 3, args.img, args.img, generator=gt).pin_memory()
+        twork = f"EMS-{targs.model} SNN-YOLO T={args.T} inference, batch {targs.batch}/GPU, synthetic {args.img}x{args.img}"
+        train_rec = train_bench(targs, E, F, tmodel, xt_host.cuda(), xt_host, rank, world, local, dist, twork, emit_line=False)
+        if train_rec is not None:
+            train_rec["images_per_s"] = train_rec.pop("value")
+            for k in ("metric", "unit", "higher_is_better", "scaling", "vs_baseline", "data", "clocks"):
+                train_rec.pop(k, None)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -480,6 +596,13 @@ def main():
     pk = peaks()
     conv_ms = per_op.get("spike_conv", 0.0) / args.steps
     conv_tf = flops["spike_conv"] / args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # ECS-LIF: the dominant operator of the step.  Algorithmic bytes: every input element once (4 B; a
+    # T-broadcast input is ONE frame) + 1 bit of spike per element-step.
+    lif_ms = per_op.get("lif_ecs", 0.0) / args.steps
+    lif_bytes = (flops["lif_fwd_in_elems"] * 4.0 + flops["lif_fwd_elems"] / 8.0) / args.steps
+    lif_bytes_full = flops["lif_fwd_elems"] * 4.125 / args.steps       # counting the T-broadcast frame T times
+    lif_gbs = lif_bytes_full / (lif_ms * 1e-3) / 1e9 if lif_ms > 0 else 0.0
+    tr = measured_traffic(args.model, args.batch, args.T, args.precision) or {}
     line = {
         "metric": "images/s", "value": imgs / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_total / args.steps,
@@ -493,24 +616,41 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": z_host.numel() * 4},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "k_spike_conv_ts + k_umma_gemm<spikes> (spike implicit-GEMM convs, tcgen05; operand in "
-                               "tensor memory / shared memory)", "bound": "tensor",
-                     "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": conv_tf / pk["tf_sust"],
-                     "traffic": measured_traffic(args.model, args.batch, args.T, args.precision),
-                     "traffic_note": "DRAM bytes per step summed over the kernel's launches (ncu, profiles/traffic.json)",
-                     "peak_source": pk["src"] + " sustained bf16",
-                     "algorithmic_gflop_per_step": flops["spike_conv"] / args.steps / 1e9,
-                     "kernel_ms_per_step": conv_ms, "launches_per_step": 48},
+        # the DOMINANT operator of the step: the ECS-LIF (wavefront kernel on the 64-channel layers, per-timestep pipeline
+        # elsewhere), HBM-bound by design; the convolutions' tensor-pipe roofline follows in `roofline_conv`
+        "roofline": {"kernel": "ecsy_lif_ecs_*: k_lif_ecs_wave64 (C = 64: all T steps on chip) + k_lif_first / k_spread_dw / "
+                               "k_dense_tma_h / k_ecs_step (other widths, per timestep)", "bound": "hbm",
+                     "achieved": lif_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": lif_gbs / pk["hbm"],
+                     "traffic": tr.get("lif", {}).get("dram_bytes_per_step"),
+                     "traffic_note": "DRAM bytes per step summed over the operator's launches (ncu, profiles/traffic.json)",
+                     "peak_source": pk["src"] + " HBM copy bandwidth",
+                     "algorithmic_bytes_per_step": lif_bytes_full,
+                     "algorithmic_bytes_note": "BASELINE.md section 2 / SURVEY 8d: elements x (4 B of input current + 1/8 B of "
+                                               "spike), 137.4 M elements per image for resnet34; the kernels read the "
+                                               "T-broadcast stem output as ONE frame, which makes the bytes they must move "
+                                               f"{lif_bytes:.4g}",
+                     "kernel_ms_per_step": lif_ms, "launches_per_step": launch_by_op.get("lif_ecs", 0) / args.steps},
+        "roofline_conv": {"kernel": "k_spike_conv_ts + k_umma_gemm<spikes> (spike implicit-GEMM convs, tcgen05; operand in "
+                                    "tensor memory / shared memory)", "bound": "tensor",
+                          "achieved": conv_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                          "frac": conv_tf / pk["tf_sust"],
+                          "traffic": tr.get("conv", {}).get("dram_bytes_per_step"),
+                          "peak_source": pk["src"] + " sustained bf16",
+                          "algorithmic_gflop_per_step": flops["spike_conv"] / args.steps / 1e9,
+                          "kernel_ms_per_step": conv_ms, "launches_per_step": launch_by_op.get("spike_conv", 0) / args.steps},
         "breakdown_ms_per_step": {k: v / args.steps for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
+        "launches_by_op_per_step": {k: v / args.steps for k, v in sorted(launch_by_op.items(), key=lambda kv: -kv[1])},
         "dense_tflops_whole_step": (flops["spike_conv"] + flops["ecs_pw"] + flops["real_conv"]) / args.steps
                                    / (ms_total / args.steps * 1e-3) / 1e12,
     }
+    line["parity"] = parity_record(args, parity_ips)
+    if train_rec is not None:
+        line["train"] = train_rec
     if world == 1 and not args.no_cpu_baseline:
-        ips, _ = cpu_reference(args.model, args.T, args.img, args.cpu_sample, 2, 1, threads, args.events)
+        ips, _ = cpu_reference(args.model, args.T, args.img, args.cpu_sample, 3, 1, threads, args.events)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": f"{args.cpu_sample} image(s)/step x 2 steps of the same workload, oracle "
-                                          "port (torch fp32 CPU) of the reference forward"}
+                                "sample": f"{args.cpu_sample} image(s)/step x 3 steps (+ 1 calibration step) of the same "
+                                          "workload, oracle port (torch fp32 CPU) of the reference forward"}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

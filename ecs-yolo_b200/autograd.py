@@ -120,7 +120,10 @@ def chain_fwd(lif, conv, bn, x: Act, aff):
         sv.sp, mem, ecs = F_.lif_ecs(x, lif._weights(), aff, lif.ecs_tau, lif.alpha, lif.beta, save_mem=True)
         sv.state = (sv.sp, mem, ecs)
     else:
-        sv.sp = lif.spikes(x, aff)
+        # the backward recomputes membranes / traces with the per-timestep pipeline: the forward must produce ITS spikes
+        if lif.spread is None:
+            lif._init_spread(x.C, x.data.device)
+        sv.sp = F_.lif_ecs(x, lif._weights(), aff, lif.ecs_tau, lif.alpha, lif.beta, allow_wave=False)
         sv.state = None
     sv.y = conv.conv_spikes(sv.sp)
     sv.scale, sv.shift, sv.mean, sv.rstd = bn_train_fwd(bn, sv.y)

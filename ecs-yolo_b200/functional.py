@@ -30,8 +30,10 @@ _state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
+launches_by_op = {}
 _prof = {"on": False, "events": []}
-flops = {"spike_conv": 0.0, "ecs_pw": 0.0, "real_conv": 0.0}
+flops = {"spike_conv": 0.0, "ecs_pw": 0.0, "real_conv": 0.0, "lif_fwd_elems": 0.0, "lif_fwd_in_elems": 0.0, "lif_elems": 0.0,
+         "tdbn_elems": 0.0}
 
 
 def profile_begin():
@@ -54,6 +56,7 @@ class _timed:
 
     def __enter__(self):
         launches["n"] += self.n
+        launches_by_op[self.name] = launches_by_op.get(self.name, 0) + self.n
         if _prof["on"]:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
@@ -391,7 +394,7 @@ def _wave_ws(dev, nbytes: int) -> torch.Tensor:
 
 
 def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-            ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25, save_mem: bool = False):
+            ecs_tau: float = 5.0, alpha: float = 0.75, beta: float = 0.25, save_mem: bool = False, allow_wave: bool = True):
     """mem_update.forward (models/common.py:252-283) -> bit-packed spikes; with save_mem also the membranes
     m_t [T,...] and ECS traces e_t [T-1,...] (the backward's recompute pass).  C % 64 != 0: the input current
     is zero-padded to the next multiple of 64 (``w`` must come from make_lif_w(..., Cp)); the result carries Cr = C."""
@@ -405,9 +408,15 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
             affine = (pad_channels(affine[0], Cp), pad_channels(affine[1], Cp))
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
+    # algorithmic traffic of the neuron: every element-step of input current once (a T-broadcast input: one frame), 1 bit out
+    flops["lif_fwd_elems"] += float(T) * N * H * W * Cr
+    flops["lif_fwd_in_elems"] += float(x.Tp) * N * H * W * Cr
     bits = torch.empty(T, N, H, W, C // 32, device=dev, dtype=torch.int32)
-    if (not save_mem and w is not None and w.w_wave is not None and _state["lif_wave"] and not _state["lif_fused"]
-            and _cabi.lib().ecsy_lif_ecs_wave_supported(T, C, H, W)):
+    # The wavefront kernel is the inference path.  The BPTT chains (autograd.chain_fwd) keep, or their backward recomputes,
+    # membranes and traces with the per-timestep pipeline, and both passes must see the SAME spikes (the folded-spread
+    # arithmetic of the wavefront kernel differs from the pipeline's in the last bits): they pass allow_wave=False.
+    if (not save_mem and allow_wave and w is not None and w.w_wave is not None and _state["lif_wave"]
+            and not _state["lif_fused"] and _cabi.lib().ecsy_lif_ecs_wave_supported(T, C, H, W)):
         sc, sh = affine if affine is not None else (None, None)
         flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
         ws = _wave_ws(dev, _cabi.lib().ecsy_lif_ecs_wave_ws_bytes(T, N, H, W, C))
@@ -478,6 +487,7 @@ def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, af
                 gpw[:Cr, :Cr].contiguous(), gpb[:Cr].contiguous())
     T, N, H, W, C = x.T, x.N, x.H, x.W, x.C
     dev = x.data.device
+    flops["lif_elems"] += float(T) * N * H * W * C
     # `saved` = (spikes, membranes, traces) kept by a forward run with save_mem (set_lif_store); otherwise recompute
     sp, mem, ecs = saved if saved is not None else lif_ecs(x, w, affine, ecs_tau, alpha, beta, save_mem=True)
     gout = gout.contiguous()
@@ -687,6 +697,7 @@ def bn_stats(y: Act) -> Tuple[torch.Tensor, torch.Tensor]:
     rows = y.Tp * y.N * y.H * y.W
     C = y.C
     dev = y.data.device
+    flops["tdbn_elems"] += float(rows) * C
     mean = torch.empty(C, device=dev, dtype=torch.float32)
     var = torch.empty(C, device=dev, dtype=torch.float32)
     L = _cabi.lib()

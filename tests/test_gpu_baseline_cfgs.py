@@ -199,5 +199,18 @@ def test_baseline_plan_teacher_forced(name, N, img, mode):
         for r in rows:
             print("   layer %2d %-14s rel-L2 %.2e  vs-fp32 %.2e  min-spike-agree %.6f  (vs the fp32-weight run's spikes %.6f)" % r)
         assert e_loss < 1e-3, f"{name} {mode}: loss {float(loss.reshape(-1)[0])} vs {float(want_loss.reshape(-1)[0])}"
+        if os.environ.get("ECSY_WRITE_PARITY_SUMMARY"):
+            # committed beside the bench numbers (profiles/parity_summary.json, read by bench.py's `parity` record)
+            import json
+            path = os.path.join(ROOT, os.environ["ECSY_WRITE_PARITY_SUMMARY"])
+            summ = json.load(open(path)) if os.path.exists(path) else {}
+            summ[f"{name}|{mode}"] = {
+                "plan": f"cfg/{name}.yaml, T={T}, batch {N}, {img}x{img}, train-mode tdBN, every layer fed the oracle's input",
+                "min_spike_agreement": worst["spike"][1], "min_spike_agreement_neuron": worst["spike"][0],
+                "min_spike_agreement_vs_fp32_weight_run": min(r[5] for r in rows),
+                "worst_layer_rel_l2": worst["real"][1], "worst_layer_rel_l2_vs_fp32_weight_oracle": worst["fp32"][1],
+                "head_rel_l2": e_head, "loss_rel": e_loss,
+                "reference": "fp32 oracle" if mode == "parity" else "oracle on the same bf16-rounded conv / spread weights"}
+            json.dump(summ, open(path, "w"), indent=1)
     finally:
         E.set_precision("parity")

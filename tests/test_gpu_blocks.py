@@ -31,16 +31,20 @@ class _oracle_forced:
     """ecs_oracle neurons return recorded spikes (evaluation of the oracle on bf16-rounded weights with the spikes of
     its fp32 run: the reference a fast-precision block is compared with when its own neurons are teacher-forced)."""
 
-    def __init__(self, rec):
-        self.rec = rec
+    def __init__(self, rec, own=None):
+        self.rec, self.own = rec, own       # own: what each neuron computes from the input it gets in THIS evaluation
 
     def __enter__(self):
         self.orig = orig = O.lif_from_sd
-        rec = self.rec
+        rec, own = self.rec, self.own
 
         def forced(sd, prefix, x, act=False, silu_inplace=False, record=None):
             key = prefix[:-1]
-            return rec[key] if (not act and key in rec) else orig(sd, prefix, x, act=act, silu_inplace=silu_inplace, record=record)
+            if not act and key in rec:
+                if own is not None:
+                    own[key] = orig(sd, prefix, x, act=act, silu_inplace=silu_inplace, record=record)
+                return rec[key]
+            return orig(sd, prefix, x, act=act, silu_inplace=silu_inplace, record=record)
         O.lif_from_sd = forced
 
     def __exit__(self, *exc):
@@ -79,8 +83,8 @@ def test_block_forward(name):
 @pytest.mark.parametrize("name", list(ALL_BLOCKS))
 def test_block_forward_fast(name):
     """The benchmark precision (one bf16 weight plane, fp16 ECS trace, tanh.approx) at the north-star tolerances, block by
-    block.  Every neuron is teacher-forced (util.forced_spikes): its spikes must equal the fp32 oracle's at >= 99.9 % of
-    the positions, and the real-valued block output must be within 1e-3 rel-L2 of the oracle evaluated on the same
+    block.  Every neuron is teacher-forced (util.forced_spikes): its spikes must equal, at >= 99.9 % of the positions, those
+    of the fp32 oracle neuron applied to the same input (the bf16-weight conv output), and the real-valued block output must be within 1e-3 rel-L2 of the oracle evaluated on the same
     bf16-rounded conv / point-wise spread weights and the same spikes (exact products, fp32 accumulation), train and eval
     mode, including the running statistics.  The distance to the fp32-weight reference output is printed and bounded by
     the bf16 rounding of the weights.  Blocks whose shortcut convolves a REAL tensor (BasicBlock_ms) also round that
@@ -97,9 +101,10 @@ def test_block_forward_fast(name):
         _oracle_block(inp, spec, sd32, True, rec_t)
         _oracle_block(inp, spec, sd32, False, rec_e)
         sdq = quantize_weights_bf16(inp["sd"])
-        with _oracle_forced(rec_t):
+        own_t, own_e = {}, {}
+        with _oracle_forced(rec_t, own_t):
             want_t = _oracle_block(inp, spec, sdq, True)
-        with _oracle_forced(rec_e):
+        with _oracle_forced(rec_e, own_e):
             want_e = _oracle_block(inp, spec, sdq, False)
     spk = lambda r: {k: v for k, v in r.items() if not k.startswith("layer")}
     F.set_precision("fast")
@@ -109,16 +114,17 @@ def test_block_forward_fast(name):
         m = m.cuda().train()
         x = inp["x"].cuda()
         with torch.no_grad():
-            with forced_spikes(E, m, spk(rec_t), "model.0.") as ft:
+            with forced_spikes(E, m, spk(rec_t), "model.0.", gate_spikes=own_t) as ft:
                 out_t = m(x).cpu()
             m.eval()
-            with forced_spikes(E, m, spk(rec_e), "model.0.") as fe:
+            with forced_spikes(E, m, spk(rec_e), "model.0.", gate_spikes=own_e) as fe:
                 out_e = m(x).cpu()
         e_t, e_e = rel_l2(out_t, want_t), rel_l2(out_e, want_e)
         d_t, d_e = rel_l2(out_t, gold["out_train"]), rel_l2(out_e, gold["out_eval"])
         agree_min = min(list(ft.agree.values()) + list(fe.agree.values()))
+        agree_fp32 = min(list(ft.agree_fp32.values()) + list(fe.agree_fp32.values()))
         print(f"\n{name} [fast]: train {e_t:.2e} eval {e_e:.2e} (vs fp32-weight reference {d_t:.2e} / {d_e:.2e}), "
-              f"min spike agreement {agree_min:.6f}")
+              f"min spike agreement {agree_min:.6f} (vs the fp32-weight run's spikes {agree_fp32:.6f})")
         assert e_t < tol and e_e < tol, f"{name}: train {e_t:.3e} eval {e_e:.3e}"
         assert d_t < 1e-2 and d_e < 1e-2, f"{name}: vs the fp32-weight reference train {d_t:.3e} eval {d_e:.3e}"
         assert len(ft.agree) == len(spk(rec_t)) and len(fe.agree) == len(spk(rec_e))
