@@ -201,6 +201,76 @@ __global__ void k_simt_conv(const float* __restrict__ x, int64_t x_imgs, const f
   }
 }
 
+// Few-input-channel direct convolution in plain fp32 (the parity-precision stem: Conv_1 on the 3-channel image,
+// models/common.py:409-425; 123 GFLOP at batch 64 -- k_simt_conv, one thread per output element, ran it at 1.9 TFLOP/s =
+// 66 of the parity step's 150 ms).  A thread owns one output pixel and 32 output channels: its 32 accumulators live in
+// registers, the weights [kh*kw*Ci][Co] sit in shared memory and are read as warp-wide broadcasts (every lane of a warp
+// works on the same channels), the input value of a tap is one cached global load per thread.  Same accumulation order
+// as k_simt_conv (ky, kx, ci; fmaf), so the two kernels agree bit for bit.
+__global__ void __launch_bounds__(256)
+k_stem_conv_f32(const float* __restrict__ x, int64_t x_imgs, const float* __restrict__ w, const float* __restrict__ scale,
+                const float* __restrict__ shift, float* __restrict__ out, int64_t imgs, int H, int W, int Ci, int Ho, int Wo,
+                int Co, int kh, int kw, int stride, int pad) {
+  extern __shared__ float s_w[];                   // [kh*kw*Ci][Co]
+  const int K = kh * kw * Ci;
+  for (int i = threadIdx.x; i < K * Co / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(w)[i];
+  __syncthreads();
+  const int cgroups = Co / 32;                     // channel groups of 32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t pixels = imgs * Ho * Wo;
+  const int64_t units = ((pixels + 31) / 32) * cgroups;          // (32 consecutive pixels) x (32 channels) per warp
+  for (int64_t u = (int64_t)blockIdx.x * nwarps + warp; u < units; u += (int64_t)gridDim.x * nwarps) {
+    const int cg = static_cast<int>(u % cgroups);
+    const int64_t m = (u / cgroups) * 32 + lane;
+    const bool ok = m < pixels;
+    const int64_t mm = ok ? m : pixels - 1;
+    const int wo = static_cast<int>(mm % Wo);
+    const int ho = static_cast<int>((mm / Wo) % Ho);
+    const int64_t img = mm / ((int64_t)Wo * Ho);
+    const float* src = x + (img % x_imgs) * (int64_t)H * W * Ci;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int hi = ho * stride - pad + ky;
+      const bool hok = hi >= 0 && hi < H;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int wi = wo * stride - pad + kx;
+        const bool inb = hok && wi >= 0 && wi < W;
+        const float* xp = src + ((int64_t)(inb ? hi : 0) * W + (inb ? wi : 0)) * Ci;
+        const float* wp = s_w + (size_t)((ky * kw + kx) * Ci) * Co + cg * 32;
+        for (int ci = 0; ci < Ci; ++ci) {
+          // a tap outside the image is SKIPPED by k_simt_conv; adding fmaf(0, w, acc) == acc keeps the bits identical
+          const float xv = inb ? __ldg(xp + ci) : 0.f;
+          const float4* w4 = reinterpret_cast<const float4*>(wp + (size_t)ci * Co);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 wv = w4[c4];
+            acc[4 * c4 + 0] = fmaf(xv, wv.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(xv, wv.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(xv, wv.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(xv, wv.w, acc[4 * c4 + 3]);
+          }
+        }
+      }
+    }
+    if (ok) {
+      float* op = out + m * Co + cg * 32;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 v = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        if (scale != nullptr) {
+          const float4 sc = *reinterpret_cast<const float4*>(scale + cg * 32 + 4 * c4);
+          const float4 sh = *reinterpret_cast<const float4*>(shift + cg * 32 + 4 * c4);
+          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        }
+        reinterpret_cast<float4*>(op)[c4] = v;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
@@ -347,6 +417,22 @@ extern "C" int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_
   }
   ECSY_CHECK_ARG(w_simt != nullptr, "real_conv_fwd: this shape needs the SIMT weight layout");
   ECSY_CHECK_ARG(groups >= 1 && Cin % groups == 0 && Cout % groups == 0, "real_conv_fwd: groups");
+  if (groups == 1 && bias == nullptr && Cin <= 8 && Cout % 32 == 0 && (size_t)k * k * Cin * Cout * 4 <= 96 * 1024) {
+    // few input channels, many outputs (the stem in parity precision): register-tiled fp32 kernel
+    const size_t smem = (size_t)k * k * Cin * Cout * 4;
+    static size_t attr = 0;
+    if (smem > attr) {
+      ECSY_CUDA(cudaFuncSetAttribute(k_stem_conv_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    const int64_t units = ((imgs * Ho * Wo + 31) / 32) * (Cout / 32);
+    int64_t grid = (units + 7) / 8;
+    if (grid > (int64_t)ecsy_num_sms() * 4) grid = (int64_t)ecsy_num_sms() * 4;
+    k_stem_conv_f32<<<(int)grid, 256, smem, STREAM(stream)>>>(x, x_imgs, w_simt, scale, shift, out, imgs, H, W, Cin, Ho, Wo,
+                                                              Cout, k, k, stride, pad);
+    ECSY_LAUNCH_CHECK();
+    return ECSY_OK;
+  }
   const int64_t total = imgs * Ho * Wo * Cout;
   k_simt_conv<<<grid_for(total, kThreads, ecsy_num_sms() * 16), kThreads, 0, STREAM(stream)>>>(
       x, x_imgs, w_simt, bias, bias_mul, scale, shift, out, imgs, H, W, Cin, Ho, Wo, Cout, k, k, stride, pad, groups);

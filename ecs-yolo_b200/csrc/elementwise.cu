@@ -155,6 +155,13 @@ __device__ __forceinline__ float tanh_fast(float v) {
 #endif
 }
 
+// Parity-precision tanh: 1 - 2 / (exp(2v) + 1) with ex2.approx / rcp.approx -- ABSOLUTE error ~1e-7, which is what the
+// membrane sees (f = beta * tanh(e)); five instructions against ~25 for tanhf.  Saturates correctly (exp -> inf: 1, -> 0: -1).
+__device__ __forceinline__ float tanh_acc(float v) {
+  const float y = __expf(2.f * v);
+  return 1.f - __fdividef(2.f, y + 1.f);
+}
+
 template <bool HALF>
 __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -188,8 +195,8 @@ __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C)
       for (int k = 0; k < 4; ++k) {
         const float s_acc = ecsy::add_rn(sp[k], bb[k]);
         en[k] = ecsy::add_rn(ecsy::mul_rn(p.alpha, s_acc), ecsy::mul_rn(p.kappa, eo[k]));
-        // fast mode (fp16 state): hardware tanh approximation (2^-11 relative), parity mode: tanhf
-        const float fecs = ecsy::mul_rn(p.beta, HALF ? tanh_fast(en[k]) : tanhf(en[k]));
+        // fast mode (fp16 state): hardware tanh approximation (2^-11), parity mode: ex2 / rcp form (1e-7 absolute)
+        const float fecs = ecsy::mul_rn(p.beta, HALF ? tanh_fast(en[k]) : tanh_acc(en[k]));
         const float keep = ((pw >> k) & 1u) ? 0.f : 1.f;
         mn[k] = ecsy::add_rn(ecsy::add_rn(ecsy::mul_rn(ecsy::mul_rn(mo[k], p.decay), keep), xin[k]), fecs);
         nib |= (mn[k] > p.thresh ? 1u : 0u) << k;
