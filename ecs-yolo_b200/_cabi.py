@@ -25,6 +25,7 @@ SIGNATURES = {
     "ecsy_lif_ecs_fused_supported": (_i, [_i, _i]),
     "ecsy_lif_ecs_fused_fwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _f, _f, _f, _f, _f, _p]),
     "ecsy_lif_ecs_wave_supported": (_i, [_i, _i, _i, _i]),
+    "ecsy_lif_ecs_wave_prefers": (_i, [_i, _i, _i, _i]),
     "ecsy_lif_ecs_wave_ws_bytes": (_z, [_i, _l, _i, _i, _i]),
     "ecsy_lif_ecs_wave_fwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _f, _f, _f, _f, _f, _p, _z, _p]),
     "ecsy_lif_ecs_bwd_ws_bytes": (_z, [_i, _l, _i, _i, _i, _i]),

@@ -678,6 +678,16 @@ extern "C" size_t ecsy_lif_ecs_wave_ws_bytes(int T, int64_t N, int H, int W, int
   return (size_t)ecsy_num_sms() * kWvMSlots * kWvMSlotFloats * sizeof(float) + 256;
 }
 
+// Measured on B200 (tools/wave_bench.py, batch 64, T = 4, fast precision): against the per-timestep pipeline the wavefront
+// kernel takes 1.36 vs 1.47 ms at 64 ch @ 160 x 160, 4.8 vs 5.6 ms on the T-broadcast 320 x 320 layer, but 0.51 vs 0.42 ms at
+// 80 x 80, where the bands are 32 columns wide (four rows per block: a larger share of halo and mirror work).
+extern "C" int ecsy_lif_ecs_wave_prefers(int T, int C, int H, int W) {
+  int R, Wb, nb;
+  if (!ecsy_lif_ecs_wave_supported(T, C, H, W)) return 0;
+  wv_plan(T, W, &R, &Wb, &nb);
+  return Wb == 64 ? 1 : 0;
+}
+
 extern "C" int ecsy_lif_ecs_wave_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                                      const void* w_eff, const float* bconst, uint32_t* spikes, int T, int64_t N, int H,
                                      int W, int C, float thresh, float decay, float alpha, float beta, float kappa,

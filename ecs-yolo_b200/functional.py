@@ -25,7 +25,7 @@ decay = 0.25
 # conv_ts: "auto" (measured dispatch rule), "all" (wherever supported) or "off"
 _state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
           "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1",
-          "lif_wave": os.environ.get("ECSY_LIF_WAVE", "1") == "1",
+          "lif_wave": {"1": "auto", "0": "off"}.get(os.environ.get("ECSY_LIF_WAVE", "auto"), os.environ.get("ECSY_LIF_WAVE", "auto")),
           "lif_store": os.environ.get("ECSY_LIF_STORE", "1") == "1"}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
@@ -111,10 +111,14 @@ def set_lif_fused(on: bool) -> None:
     _state["lif_fused"] = bool(on)
 
 
-def set_lif_wave(on: bool) -> None:
-    """Fast precision, C == 64, 2 <= T <= 4 (default ON): the ECS-LIF forward runs as ONE wavefront kernel with membrane and
-    ECS trace of all T steps in tensor memory (csrc/lif_wave.cu) instead of the per-timestep pipeline."""
-    _state["lif_wave"] = bool(on)
+def set_lif_wave(mode) -> None:
+    """Fast precision, C == 64, 2 <= T <= 4: the ECS-LIF forward as ONE wavefront kernel with the state of all T steps on
+    chip (csrc/lif_wave.cu) instead of the per-timestep pipeline.  "auto" (default): where it measured faster
+    (ecsy_lif_ecs_wave_prefers); "all" / True: wherever supported; "off" / False: never."""
+    mode = {True: "all", False: "off"}.get(mode, mode)
+    if mode not in ("auto", "all", "off"):
+        raise ValueError(mode)
+    _state["lif_wave"] = mode
 
 
 def set_lif_store(on: bool) -> None:
@@ -415,8 +419,10 @@ def lif_ecs(x: Act, w: Optional[LifW], affine: Optional[Tuple[torch.Tensor, torc
     # The wavefront kernel is the inference path.  The BPTT chains (autograd.chain_fwd) keep, or their backward recomputes,
     # membranes and traces with the per-timestep pipeline, and both passes must see the SAME spikes (the folded-spread
     # arithmetic of the wavefront kernel differs from the pipeline's in the last bits): they pass allow_wave=False.
-    if (not save_mem and allow_wave and w is not None and w.w_wave is not None and _state["lif_wave"]
-            and not _state["lif_fused"] and _cabi.lib().ecsy_lif_ecs_wave_supported(T, C, H, W)):
+    if (not save_mem and allow_wave and w is not None and w.w_wave is not None and _state["lif_wave"] != "off"
+            and not _state["lif_fused"]
+            and (_cabi.lib().ecsy_lif_ecs_wave_supported(T, C, H, W) if _state["lif_wave"] == "all"
+                 else _cabi.lib().ecsy_lif_ecs_wave_prefers(T, C, H, W))):
         sc, sh = affine if affine is not None else (None, None)
         flops["ecs_pw"] += 2.0 * (T - 1) * N * H * W * C * C
         ws = _wave_ws(dev, _cabi.lib().ecsy_lif_ecs_wave_ws_bytes(T, N, H, W, C))

@@ -82,6 +82,7 @@ int ecsy_lif_ecs_fused_fwd(const float* x, int64_t x_tstride, const float* in_sc
  * bconst as above.  ws: ecsy_lif_ecs_wave_ws_bytes() of CTA-private membrane scratch (28 MB, written and re-read within
  * microseconds: it lives in the L2). */
 int ecsy_lif_ecs_wave_supported(int T, int C, int H, int W);
+int ecsy_lif_ecs_wave_prefers(int T, int C, int H, int W);   /* measured dispatch rule (csrc/lif_wave.cu) */
 size_t ecsy_lif_ecs_wave_ws_bytes(int T, int64_t N, int H, int W, int C);
 int ecsy_lif_ecs_wave_fwd(const float* x, int64_t x_tstride, const float* in_scale, const float* in_shift,
                           const void* w_eff, const float* bconst, uint32_t* spikes, int T, int64_t N, int H, int W,

@@ -372,7 +372,7 @@ def test_lif_ecs_wave(T, N, H, W):
             assert agree(gotb, wantb) >= 0.999
     finally:
         F.set_precision("parity")
-        F.set_lif_wave(True)
+        F.set_lif_wave("auto")
 
 
 @pytest.mark.parametrize("ci,co,k,H,W,N,T", [(64, 128, 3, 10, 12, 2, 2), (128, 64, 1, 7, 9, 1, 3), (192, 256, 3, 20, 20, 3, 1)])

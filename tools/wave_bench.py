@@ -23,7 +23,7 @@ for tag in args.shapes.split(","):
     pw = torch.randn(C, C, 1, 1, device="cuda") / C ** 0.5
     w = F.make_lif_w(dw, torch.zeros(C, device="cuda"), pw, torch.zeros(C, device="cuda"))
     res = {}
-    for name, on in (("pipeline", False), ("wave", True)):
+    for name, on in (("pipeline", "off"), ("wave", "all")):
         F.set_lif_wave(on)
         for _ in range(2):
             sp = F.lif_ecs(a, w)
