@@ -197,13 +197,13 @@ __device__ __forceinline__ float2 lds64f(uint32_t addr) {
 __host__ __device__ constexpr int wv_ring_rows(int Wb) { return 8 + Wb + 256 + Wb + 8; }
 
 #ifdef WV_PROF
-#define WV_DECL long long prof_full = 0, prof_ring = 0, prof_work = 0, prof_pre = 0
+#define WV_DECL long long prof_full = 0, prof_ring = 0, prof_work = 0, prof_pre = 0, pc_issue = 0, pc_tmem = 0, pc_math = 0, pc_store = 0, pc_rot = 0
 #define WV_T(v) const long long v = clock64()
 #define WV_ACC(a, d) a += (d)
 #define WV_REPORT                                                                                                        \
   if (blockIdx.x == 1 && (threadIdx.x & 127) == 0)                                                                       \
-    printf("wave prof: level %d blocks %d  per block: pre %lld  wait_full %lld  wait_ring %lld  work %lld\n", lvl, nblk, \
-           prof_pre / nblk, prof_full / nblk, prof_ring / nblk, prof_work / nblk)
+    printf("wave prof: level %d blocks %d  per block: pre %lld  wait_full %lld  wait_ring %lld  work %lld | per chunk: issue %lld tmem %lld math %lld store %lld rotate %lld\n", lvl, nblk, \
+           prof_pre / nblk, prof_full / nblk, prof_ring / nblk, prof_work / nblk, pc_issue / (8 * nblk), pc_tmem / (8 * nblk), pc_math / (8 * nblk), pc_store / (8 * nblk), pc_rot / (8 * nblk))
 #else
 #define WV_DECL
 #define WV_T(v)
@@ -289,20 +289,38 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
   // pixel outside the image reads a huge negative current: it never fires (zero padding of the spread), its state stays
   // finite.  The chunk loop is NOT unrolled (four levels x eight unrolled chunks were 140 KB of hot code on one SM: a
   // quarter of all warp stalls were instruction-cache misses); buffers rotate through registers instead.
-  auto load_x = [&](int u, const int (&pix)[4], uint32_t flags, float (&xv)[8], const float* base) {
+  // The kernel is bound by the load / store unit's WAVEFRONTS (one per 128-byte line an instruction touches, ~2 cycles
+  // each; measured with in-kernel clocks: a level spent 900-1400 cycles per chunk just ISSUING its loads).  In the fragment
+  // layout a thread owns channel pairs, so a warp's 8-byte loads touch 8 lines for 256 bytes.  Here a thread loads 16 bytes
+  // (four channels of ONE of the chunk's two channel groups) and swaps one pair with its neighbour lane: 8 lines for 512
+  // bytes, half the wavefronts.  Lane q4: group kq = q4 & 1, channels 4 (q4 >> 1) .. + 3 of it; it needs the pairs 2 q4,
+  // 2 q4 + 1 of BOTH groups: even lanes keep (x, y) as their group-0 pair and get the group-1 pair from the odd neighbour,
+  // odd lanes keep (z, w) as their group-1 pair and get the group-0 pair from the even neighbour.
+  // load_x only REQUESTS the data (raw[4 rs + i] = element i of the lane's 16-byte slice of pixel rs); the pair swap
+  // happens in unpack_x when the chunk is consumed -- a shuffle right after the load would wait for it.
+  auto load_x = [&](int u, const int (&pix)[4], uint32_t flags, float (&raw)[8], const float* base) {
     const bool hi = u >= 4;
     const int cb = 16 * (u & 3);
 #pragma unroll
     for (int rs = 0; rs < 2; ++rs) {
       const int pp = hi ? pix[2 + rs] : pix[rs];
       const bool ok = (flags >> ((hi ? 2 : 0) + rs)) & 1u;
-      const float* src = base + (int64_t)pp * 64 + cb;
+      // `base` carries + 2 q4; the 16-byte slice of this lane starts at 8 (q4 & 1) + 4 (q4 >> 1)
+      const float* src = base - 2 * q4 + (int64_t)pp * 64 + cb + 8 * (q4 & 1) + 4 * (q4 >> 1);
+      const float4 v = ok ? ldg_stream(reinterpret_cast<const float4*>(src)) : make_float4(-1e30f, -1e30f, -1e30f, -1e30f);
+      raw[4 * rs] = v.x; raw[4 * rs + 1] = v.y; raw[4 * rs + 2] = v.z; raw[4 * rs + 3] = v.w;
+    }
+  };
+  auto unpack_x = [&](const float (&raw)[8], float (&xv)[8]) {
+    const int kq = q4 & 1;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float2 v = ok ? ldg_stream2(src + 8 * k) : make_float2(-1e30f, -1e30f);
-        xv[4 * k + 2 * rs] = v.x;
-        xv[4 * k + 2 * rs + 1] = v.y;
-      }
+    for (int rs = 0; rs < 2; ++rs) {
+      const float r0 = __shfl_xor_sync(0xffffffffu, kq ? raw[4 * rs] : raw[4 * rs + 2], 1);
+      const float r1 = __shfl_xor_sync(0xffffffffu, kq ? raw[4 * rs + 1] : raw[4 * rs + 3], 1);
+      xv[2 * rs] = kq ? r0 : raw[4 * rs];               // group k = 0: channels cb + 2 q4 + {0, 1}
+      xv[2 * rs + 1] = kq ? r1 : raw[4 * rs + 1];
+      xv[4 + 2 * rs] = kq ? raw[4 * rs + 2] : r0;       // group k = 1: channels cb + 8 + 2 q4 + {0, 1}
+      xv[4 + 2 * rs + 1] = kq ? raw[4 * rs + 3] : r1;
     }
   };
 
@@ -363,6 +381,7 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
 #pragma unroll 1
     for (int u = 0; u < 8; ++u) {
       const int h = u >> 2, gq = (u >> 1) & 1, kh = u & 1, cb = 16 * (u & 3);     // cb: first channel of the chunk (+ 2 q4 + e)
+      WV_T(c0);
       // next chunk's loads first, then this chunk's tensor-memory load: all in flight while the previous results retire
       if (u + 2 < 8) load_x(u + 2, pix, flags, xn2, xt);
       if (u + 1 < 8) {
@@ -372,6 +391,18 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
       const uint32_t t_addr = tmem_base + ((uint32_t)(32 * q + 16 * h) << 16) + (uint32_t)cb;
       uint32_t ev[8];
       if (KIND > 0) tmem_ld_16x256b_x2(t_addr + e_col, ev);
+      // the chunk's input current arrives as raw 16-byte slices: swap pairs with the neighbour lane now (see load_x)
+      {
+        float t8[8];
+        unpack_x(xc, t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xc[i] = t8[i];
+        if (KIND == 1) {
+          unpack_x(x0c, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x0c[i] = t8[i];
+        }
+      }
       float2 scv[2], shv[2];
       if (AFF) {
 #pragma unroll
@@ -385,8 +416,13 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
       if (KIND > 0) {
         bcv[0] = lds64f(c_bconst + cb * 4);
         bcv[1] = lds64f(c_bconst + (cb + 8) * 4);
+        WV_T(c1);
         tmem_ld_wait();
+        WV_T(c2);
+        WV_ACC(pc_issue, c1 - c0);
+        WV_ACC(pc_tmem, c2 - c1);
       }
+      WV_T(c2b);
       uint32_t w2[2][2];      // {0,1} bf16 pairs of the chunk's two pixels (4 channels = 8 bytes each) for the ring
       uint32_t word[2] = {0u, 0u};
 #pragma unroll
@@ -426,6 +462,8 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
           word[rs] |= ((sp[0] & 1u) | (sp[1] & 2u)) << (8 * k);
         }
       }
+      WV_T(c3);
+      WV_ACC(pc_math, c3 - c2b);
       if (!LAST && KIND > 0) {
         tmem_st_16x256b_x2(t_addr + e_col, ev);
         st_cg_u4(mslot + u * 1024, make_uint4(mv[0], mv[1], mv[2], mv[3]));
@@ -468,6 +506,8 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
               make_uint2(rsel ? wlo[1] : wlo[0], rsel ? whi[1] : whi[0]);
         wlo[0] = wlo[1] = whi[0] = whi[1] = 0u;
       }
+      WV_T(c4);
+      WV_ACC(pc_store, c4 - c3);
       // rotate the software pipeline
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -476,6 +516,8 @@ __device__ __forceinline__ void wv_level(const WvArgs& g, const LevelCtx& cx) {
         if (KIND == 1) x0c[i] = x0n[i];
         if (KIND > 1) mc[i] = mn[i];
       }
+      WV_T(c5);
+      WV_ACC(pc_rot, c5 - c4);
     }
     WV_T(tp4);
     WV_ACC(prof_work, tp4 - tp3);
