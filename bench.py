@@ -167,7 +167,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
     model.train()
     net = model
     if dist is not None:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=64,
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=25,
                                                         gradient_as_bucket_view=True)
     if args.optim == "fused":
         # the reference's three parameter groups + ModelEMA in one multi-tensor launch per step
@@ -269,7 +269,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
             bucket_sizes = []
         comm = {"collective": "NCCL all-reduce (sum) of the fp32 gradients through DistributedDataParallel, overlapped with "
                               "the backward kernels (train.py:419, :559-567)",
-                "allreduce_bytes_per_step": gbytes, "bucket_cap_mb": 64, "buckets": len(bucket_sizes) or None,
+                "allreduce_bytes_per_step": gbytes, "bucket_cap_mb": 25, "buckets": len(bucket_sizes) or None,
                 "largest_bucket_bytes": max(bucket_sizes) if bucket_sizes else None,
                 "ms_per_step_with_allreduce": float(tt[0]), "ms_per_step_no_sync": float(tt[1]),
                 "exposed_comm_ms_per_step": float(tt[0] - tt[1]),
@@ -305,7 +305,7 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         "config": {"workload": workload.replace("inference", "training (fwd + loss + bwd + SGD step" + (" + EMA, fused)" if args.optim == "fused" else ")")),
                    "model_cfg": f"cfg/{args.model}.yaml", "T": args.T, "global_batch": args.batch * world,
                    "precision": args.precision, "accumulate": "fp32",
-                   "parallelism": f"DDP x{world} (NCCL all-reduce of fp32 gradients, 64 MB buckets)" if world > 1
+                   "parallelism": f"DDP x{world} (NCCL all-reduce of fp32 gradients, 25 MB buckets)" if world > 1
                                   else "single GPU",
                    "loss": loss_name,
                    "l2": "activations per step (GBs) exceed the 126 MB L2; no explicit flush"},

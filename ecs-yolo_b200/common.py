@@ -95,6 +95,14 @@ class mem_update(nn.Module):
             raise RuntimeError("mem_update(act=True) produces real values: use analog()")
         if self.spread is None:
             self._init_spread(x.C, x.data.device)
+        if F_._state["dispatch"] == "ops" and x.C % 64 == 0 and not self.training and not torch.is_grad_enabled():
+            # the inference path goes through the PyTorch custom operator (ops.py) over the C ABI
+            from . import ops  # noqa: F401  (registers torch.ops.ecsy.*)
+            w = self._weights()
+            sc, sh = affine if affine is not None else (None, None)
+            bits = torch.ops.ecsy.lif_ecs_w(x.data, x.T, w.dw_w, w.dw_b, w.pw, w.pw_b, w.w_eff, w.bconst, w.w_wave, w.splits,
+                                            sc, sh, float(self.ecs_tau), float(self.alpha), float(self.beta))
+            return Spikes(bits, x.C)
         return F_.lif_ecs(x, self._weights(), affine, self.ecs_tau, self.alpha, self.beta)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -141,6 +149,12 @@ class Snn_Conv2d(nn.Conv2d):
         if sp.Cr != self.in_channels:
             raise RuntimeError(f"Snn_Conv2d: {sp.Cr} spike channels for a {self.in_channels}-channel conv")
         if self.umma_ok() and sp.C == self.in_channels:
+            if F_._state["dispatch"] == "ops" and self.groups == 1 and self.bias is None and not self.training and not torch.is_grad_enabled():
+                from . import ops  # noqa: F401
+                w = self._w()
+                out = torch.ops.ecsy.spike_conv_w(sp.bits, sp.C, w.packed, w.packed_ts, w.splits, w.co, w.k, w.stride, w.pad,
+                                                  scale, shift, residual.data if residual is not None else None)
+                return Act(out, sp.T)
             return F_.spike_conv(sp, self._w(), scale, shift, residual)
         if self.bias is None and self.groups == 1:
             # narrow input and / or output (res*-ee.yaml: 3 -> 32 -> 32 -> 64): same tcgen05 kernel on padded weights

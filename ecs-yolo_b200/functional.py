@@ -26,7 +26,8 @@ decay = 0.25
 _state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
           "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1",
           "lif_wave": {"1": "auto", "0": "off"}.get(os.environ.get("ECSY_LIF_WAVE", "auto"), os.environ.get("ECSY_LIF_WAVE", "auto")),
-          "lif_store": os.environ.get("ECSY_LIF_STORE", "1") == "1"}
+          "lif_store": os.environ.get("ECSY_LIF_STORE", "1") == "1",
+          "dispatch": os.environ.get("ECSY_DISPATCH", "ops")}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
@@ -109,6 +110,15 @@ def set_lif_fused(on: bool) -> None:
     """Fast mode, C == 64: run the ECS-LIF forward as ONE kernel with all T steps on chip.  Parity-green but
     measured slower than the per-timestep pipeline so far (csrc/lif_fused.cu header), hence off by default."""
     _state["lif_fused"] = bool(on)
+
+
+def set_dispatch(mode: str) -> None:
+    """How the drop-in modules reach the kernels on the inference path: "ops" (default) = through the PyTorch custom
+    operators torch.ops.ecsy.lif_ecs / torch.ops.ecsy.spike_conv (ops.py: torch.library ops with fake implementations, so
+    the modules can be traced / exported), which call this module's C-ABI wrappers; "direct" = the wrappers themselves."""
+    if mode not in ("ops", "direct"):
+        raise ValueError(mode)
+    _state["dispatch"] = mode
 
 
 def set_lif_wave(mode) -> None:

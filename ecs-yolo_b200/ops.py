@@ -27,14 +27,20 @@ _wcache: dict = {}
 
 
 def _cached(kind: str, tensors, builder):
+    """Derived-weight cache of the raw-parameter operators.  The key holds data_ptr / _version / shape; because the caching
+    allocator hands the address of a freed parameter to the next model, an entry is only valid while the tensors it was
+    built from are still alive (weak references) -- a stale hit would silently run another model's weights."""
+    import weakref
     key = (kind, F_.get_splits(), F_._state["conv_ts"], F_.weights_epoch()) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
-    v = _wcache.get(key)
-    if v is None:
-        if len(_wcache) > 512:
-            _wcache.clear()
-        with torch.no_grad():
-            v = builder()
-        _wcache[key] = v
+    ent = _wcache.get(key)
+    if ent is not None and all(r() is not None and r().data_ptr() == t.data_ptr() for r, t in zip(ent[0], tensors)):
+        return ent[1]
+    if len(_wcache) > 512:
+        _wcache.clear()
+    with torch.no_grad():
+        v = builder()
+    # the operator may see a fresh alias of the caller's tensor: keep the storage's owner alive-ness via the base object
+    _wcache[key] = ([weakref.ref(t._base if t._base is not None else t) for t in tensors], v)
     return v
 
 
@@ -64,6 +70,43 @@ def _(x, T, dw_w, dw_b, pw_w, pw_b, scale, shift, ecs_tau, alpha, beta):
     _, N, H, W, C = x.shape
     torch._check(C % 64 == 0, lambda: "ecsy::lif_ecs: C must be a multiple of 64")
     return x.new_empty((T, N, H, W, C // 32), dtype=torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------- module-facing operators
+# The drop-in modules keep their derived weights in a per-module cache (common._cached) and hand them over explicitly: no
+# hidden state in the operator.
+@torch.library.custom_op("ecsy::lif_ecs_w", mutates_args=())
+def lif_ecs_w(x: Tensor, T: int, dw_w9: Tensor, dw_b: Tensor, pw_packed: Tensor, pw_b: Tensor, w_eff: Optional[Tensor],
+              bconst: Optional[Tensor], w_wave: Optional[Tensor], splits: int, scale: Optional[Tensor], shift: Optional[Tensor],
+              ecs_tau: float, alpha: float, beta: float) -> Tensor:
+    """mem_update.forward (models/common.py:252-283) on prepacked spread weights (functional.make_lif_w) -> spike bits."""
+    w = F_.LifW(dw_w9, dw_b, pw_packed, pw_b, splits, w_eff, bconst, w_wave)
+    aff = (scale, shift) if scale is not None else None
+    return F_.lif_ecs(Act(x, T), w, aff, ecs_tau, alpha, beta).bits
+
+
+@lif_ecs_w.register_fake
+def _(x, T, dw_w9, dw_b, pw_packed, pw_b, w_eff, bconst, w_wave, splits, scale, shift, ecs_tau, alpha, beta):
+    _, N, H, W, C = x.shape
+    torch._check(C % 64 == 0, lambda: "ecsy::lif_ecs_w: C must be a multiple of 64")
+    return x.new_empty((T, N, H, W, C // 32), dtype=torch.int32)
+
+
+@torch.library.custom_op("ecsy::spike_conv_w", mutates_args=())
+def spike_conv_w(bits: Tensor, cin: int, packed: Tensor, packed_ts: Optional[Tensor], splits: int, cout: int, k: int, stride: int,
+                 pad: int, scale: Optional[Tensor], shift: Optional[Tensor], residual: Optional[Tensor]) -> Tensor:
+    """Snn_Conv2d on spikes (models/common.py:609-624) on prepacked weights (functional.make_conv_w), folded tdBN, shortcut."""
+    T = bits.shape[0]
+    w = F_.ConvW(packed, None, None, cout, cin, k, stride, pad, 1, splits, False, packed_ts)
+    res = Act(residual, T) if residual is not None else None
+    return F_.spike_conv(Spikes(bits, cin), w, scale, shift, res).data
+
+
+@spike_conv_w.register_fake
+def _(bits, cin, packed, packed_ts, splits, cout, k, stride, pad, scale, shift, residual):
+    T, N, H, W, _ = bits.shape
+    Ho, Wo = _conv_out(H, W, k, stride, pad)
+    return bits.new_empty((T, N, Ho, Wo, cout), dtype=torch.float32)
 
 
 # ---------------------------------------------------------------------------------------------- spike_conv
