@@ -414,7 +414,7 @@ class Conv_1(nn.Module):
         from . import autograd as AG
         if AG.wants_grad(self, x):
             out = AG.StemFn.apply(self, x, *self.parameters())
-            return out.expand(x.shape[0], -1, -1, -1, -1) if out.shape[0] != x.shape[0] else out
+            return AG.ExpandT.apply(out, x.shape[0]) if out.shape[0] != x.shape[0] else out
         a = Act.from_ref(x)
         if self.bn.bn.training:
             y = self.conv.conv_real(a)

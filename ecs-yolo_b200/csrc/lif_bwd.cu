@@ -17,6 +17,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kPartBlocksPerSm = 6;   // grid of the streaming backward kernels that leave per-block gradient partials
 
 inline int grid_for(int64_t work, int per_block, int max_blocks) {
   int64_t g = (work + per_block - 1) / per_block;
@@ -31,11 +32,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 // ge_t = gm_next*beta*(1-tanh^2(e_t)) + kappa*ge_next  -> fp32 carry (in place) + bf16 hi/lo GEMM operand
+// With `part` (spiking neuron): also the per-block partial of sum_p ge_t[p][c] (row 0 of part[block][11][C], the point-wise
+// bias gradient) -- blockDim is a multiple of C/4, so a thread keeps one channel quad for its whole grid-stride loop.
 __global__ void k_lif_bwd_pre(const float* __restrict__ gm_next, const float* __restrict__ ecs_t,
                               float* __restrict__ ge /*in: ge_next (if has_next), out: ge_t*/, int has_next,
                               __nv_bfloat16* __restrict__ ge_hi, __nv_bfloat16* __restrict__ ge_lo, int64_t n4,
-                              float beta, float kappa) {
+                              float beta, float kappa, float* __restrict__ part, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 g = reinterpret_cast<const float4*>(gm_next)[i];
     const float4 e = reinterpret_cast<const float4*>(ecs_t)[i];
@@ -48,6 +52,7 @@ __global__ void k_lif_bwd_pre(const float* __restrict__ gm_next, const float* __
     th = tanhf(e.z); o.z = g.z * beta * (1.0f - th * th) + kappa * n.z;
     th = tanhf(e.w); o.w = g.w * beta * (1.0f - th * th) + kappa * n.w;
     reinterpret_cast<float4*>(ge)[i] = o;
+    sum[0] += o.x; sum[1] += o.y; sum[2] += o.z; sum[3] += o.w;
     const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y);
     const __nv_bfloat16 h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
     reinterpret_cast<uint2*>(ge_hi)[i] =
@@ -57,6 +62,18 @@ __global__ void k_lif_bwd_pre(const float* __restrict__ gm_next, const float* __
       reinterpret_cast<uint2*>(ge_lo)[i] =
           make_uint2(pack_bf16x2(o.x - __bfloat162float(h0), o.y - __bfloat162float(h1)),
                      pack_bf16x2(o.z - __bfloat162float(h2), o.w - __bfloat162float(h3)));
+  }
+  if (part == nullptr) return;
+  extern __shared__ float sred[];  // [nty][C]
+  const int c4 = C >> 2;
+  const int tq = threadIdx.x % c4, ty = threadIdx.x / c4, nty = blockDim.x / c4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sred[ty * C + tq * 4 + k] = sum[k];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
+    double t = 0;
+    for (int y = 0; y < nty; ++y) t += sred[y * C + idx];
+    part[(size_t)blockIdx.x * 11 * C + idx] = static_cast<float>(t);
   }
 }
 
@@ -154,56 +171,120 @@ k_lif_bwd_reduce_final(const float* __restrict__ part, int nblocks, float* __res
 }
 
 // gs = gout + alpha*dw^T(G1); gm = gs*sigma'(m_t) + gm_next*decay*(1-s_t); writes gm carry and gx[t].
-__global__ void k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*null at t=T-1*/,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*null at t=T-1*/,
                                const float* __restrict__ dw_w, const float* __restrict__ mem_t,
                                const uint32_t* __restrict__ bits_t, const float* __restrict__ gm /*dL/dm_{t+1} = gx[t+1]*/,
                                int has_next, float* __restrict__ gx, int N, int H, int W, int C, float thresh,
-                               float lens, float decay, float alpha) {
+                               float lens, float decay, float alpha, float* __restrict__ part) {
+  // blockDim is a multiple of C/4: a thread keeps ONE channel quad and walks pixels p = block*nty + ty + k*grid*nty with
+  // (h, w) tracked incrementally -- no division, no 64-bit multiply per element (the index arithmetic of the first version
+  // was ~580 instructions per float4 and the kernel was issue bound at a third of the HBM rate).
   const int c4 = C >> 2;
-  const int64_t total = (int64_t)N * H * W * c4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const bool small = total < (int64_t(1) << 32);
+  const int tq = threadIdx.x % c4, ty = threadIdx.x / c4, nty = blockDim.x / c4;
+  const int64_t pixels = (int64_t)N * H * W;
+  const int64_t pstep = (int64_t)gridDim.x * nty;
   const float inv = 1.0f / (2.0f * lens);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int q = static_cast<int>(ecsy::mod_u(i, (uint32_t)c4, small));
-    const int64_t p = ecsy::div_u(i, (uint32_t)c4, small);
-    float4 gs = reinterpret_cast<const float4*>(gout)[i];
+  // spread parameter gradients (with `part`): the depth-wise dgrad below already gathers G1 at the nine neighbours
+  // p - off(tap) of pixel p, and
+  //   dWdw[tap][c] = sum_p' G1[p'][c] * s_t[p' + off(tap)][c] = sum_p s_t[p][c] * G1[p - off(tap)][c]
+  // is the same nine values gated by the spike of the centre pixel: rows 2..10 of part[block][11][C]; row 1 = sum_p G1[p][c].
+  float aw[9][4], ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 9; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) aw[a][k] = 0.f;
+  int64_t p = (int64_t)blockIdx.x * nty + ty;
+  int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
+  const int dw_ = static_cast<int>(pstep % W), dh_ = static_cast<int>((pstep / W) % H);
+  const int64_t estep = pstep * C;
+  const int WC = W * C;
+  int64_t e = p * C + tq * 4;
+  const int Cw = C >> 5, sh = 4 * (tq & 7);
+  const uint32_t* bp = bits_t + p * Cw + (tq >> 3);
+  const int64_t bstep = pstep * Cw;
+  const float* wq = dw_w + tq * 4;
+  const float* g1p = g1 != nullptr ? g1 + e : nullptr;
+  for (; p < pixels; p += pstep, e += estep, bp += bstep, g1p += estep) {
+    // every load of the iteration is issued before the first use (clamped addresses + masks instead of branches around
+    // the border taps)
+    float4 gs = *reinterpret_cast<const float4*>(gout + e);
+    const float4 m = *reinterpret_cast<const float4*>(mem_t + e);
+    float4 gn = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t nib = 0;
+    if (has_next) {
+      gn = *reinterpret_cast<const float4*>(gm + e);
+      nib = (*bp >> sh) & 0xFu;
+    }
     if (g1 != nullptr) {
-      const int w = static_cast<int>(ecsy::mod_u(p, (uint32_t)W, small));
-      const int h = static_cast<int>(ecsy::mod_u(ecsy::div_u(p, (uint32_t)W, small), (uint32_t)H, small));
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g[9];
+      uint32_t okm = 0;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        const int hh = h - (ky - 1);   // s[q] feeds out[q - off(tap)]
-        if (hh < 0 || hh >= H) continue;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int ww = w - (kx - 1);
-          if (ww < 0 || ww >= W) continue;
-          const float4 g = reinterpret_cast<const float4*>(g1 + (p - (int64_t)(ky - 1) * W - (kx - 1)) * C)[q];
-          const float4 wt = *reinterpret_cast<const float4*>(dw_w + (ky * 3 + kx) * C + q * 4);
-          acc.x = fmaf(g.x, wt.x, acc.x); acc.y = fmaf(g.y, wt.y, acc.y);
-          acc.z = fmaf(g.z, wt.z, acc.z); acc.w = fmaf(g.w, wt.w, acc.w);
+          const int hh = h - (ky - 1), ww = w - (kx - 1);   // s[q] feeds out[q - off(tap)]
+          const bool ok = (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+          const int off = ok ? (1 - ky) * WC + (1 - kx) * C : 0;   // 32-bit offset from the running pointer
+          g[ky * 3 + kx] = *reinterpret_cast<const float4*>(g1p + off);
+          okm |= (ok ? 1u : 0u) << (ky * 3 + kx);
+        }
+      }
+      if (okm != 0x1FFu) {   // image border (rare): the taps outside contribute nothing
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+          if (!((okm >> tp) & 1u)) g[tp] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float s0 = (nib & 1u) ? 1.f : 0.f, s1 = (nib & 2u) ? 1.f : 0.f;
+      const float s2 = (nib & 4u) ? 1.f : 0.f, s3 = (nib & 8u) ? 1.f : 0.f;
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        const float4 wt = __ldg(reinterpret_cast<const float4*>(wq + tp * C));
+        acc.x = fmaf(g[tp].x, wt.x, acc.x); acc.y = fmaf(g[tp].y, wt.y, acc.y);
+        acc.z = fmaf(g[tp].z, wt.z, acc.z); acc.w = fmaf(g[tp].w, wt.w, acc.w);
+        if (part != nullptr) {
+          // g * 1 or g * 0 (+-0 leaves the sum unchanged): same values as a predicated add
+          aw[tp][0] = fmaf(g[tp].x, s0, aw[tp][0]); aw[tp][1] = fmaf(g[tp].y, s1, aw[tp][1]);
+          aw[tp][2] = fmaf(g[tp].z, s2, aw[tp][2]); aw[tp][3] = fmaf(g[tp].w, s3, aw[tp][3]);
+          if (tp == 4) { ab[0] += g[tp].x; ab[1] += g[tp].y; ab[2] += g[tp].z; ab[3] += g[tp].w; }
         }
       }
       gs.x = fmaf(alpha, acc.x, gs.x); gs.y = fmaf(alpha, acc.y, gs.y);
       gs.z = fmaf(alpha, acc.z, gs.z); gs.w = fmaf(alpha, acc.w, gs.w);
     }
-    const float4 m = reinterpret_cast<const float4*>(mem_t)[i];
     float4 o;
     o.x = fabsf(m.x - thresh) < lens ? gs.x * inv : 0.f;
     o.y = fabsf(m.y - thresh) < lens ? gs.y * inv : 0.f;
     o.z = fabsf(m.z - thresh) < lens ? gs.z * inv : 0.f;
     o.w = fabsf(m.w - thresh) < lens ? gs.w * inv : 0.f;
     if (has_next) {
-      const float4 gn = reinterpret_cast<const float4*>(gm)[i];
-      const uint32_t nib = (bits_t[p * (C >> 5) + (q >> 3)] >> (4 * (q & 7))) & 0xFu;
       o.x += (nib & 1u) ? 0.f : gn.x * decay;
       o.y += (nib & 2u) ? 0.f : gn.y * decay;
       o.z += (nib & 4u) ? 0.f : gn.z * decay;
       o.w += (nib & 8u) ? 0.f : gn.w * decay;
     }
-    reinterpret_cast<float4*>(gx)[i] = o;   // gx[t] IS the carry dL/dm_t of the next (earlier) step: no separate copy
+    *reinterpret_cast<float4*>(gx + e) = o;   // gx[t] IS the carry dL/dm_t of the next (earlier) step: no separate copy
+    w += dw_;
+    h += dh_;
+    if (w >= W) { w -= W; ++h; }
+    if (h >= H) h -= H;
+  }
+  if (part == nullptr) return;
+  // block reduction over the threads of a channel quad in shared memory (double), one per-block partial per (row, channel)
+  extern __shared__ float sred[];  // [nty][10][C]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sred[(ty * 10 + 0) * C + tq * 4 + k] = ab[k];
+#pragma unroll
+  for (int a = 0; a < 9; ++a)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sred[(ty * 10 + 1 + a) * C + tq * 4 + k] = aw[a][k];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 10 * C; idx += blockDim.x) {
+    double t = 0;
+    for (int y = 0; y < nty; ++y) t += sred[y * 10 * C + idx];
+    part[(size_t)blockIdx.x * 11 * C + C + idx] = static_cast<float>(t);
   }
 }
 
@@ -366,7 +447,7 @@ extern "C" size_t ecsy_lif_ecs_bwd_ws_bytes(int T, int64_t N, int H, int W, int 
   (void)T;
   // gm, ge, G1 (fp32) + ge planes + dw planes (bf16) + reduction scratch
   return 512 + 3 * al256(mc * 4) + 2 * static_cast<size_t>(splits) * al256(mc * 2) +
-         al256((size_t)ecsy_num_sms() * 4 * 11 * C * 4);   // per-block partial sums of the parameter gradients
+         al256((size_t)ecsy_num_sms() * 8 * 11 * C * 4);   // per-block partial sums of the parameter gradients
 }
 
 extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const float* mem, const float* ecs,
@@ -400,16 +481,19 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
   float* part = reinterpret_cast<float*>(p);
   const int64_t words = M * (C / 32);
   const int64_t n4 = M * C / 4;
-  const int egrid = grid_for(n4, kThreads, ecsy_num_sms() * 8);
   const int c4 = C / 4;
-  const int rbd = (256 / c4) * c4;  // reduce kernels: block size a multiple of c4 (C <= 1024 -> c4 <= 256)
+  const int rbd = (256 / c4) * c4;  // block size a multiple of c4 (C <= 1024 -> c4 <= 256): one channel quad per thread
+  // the parameter-gradient sums ride in the streaming kernels (pre: sum ge; post: sum G1 and the spike-gated taps): both
+  // run on the same grid and leave part[block][11][C]; the old separate pass (k_lif_bwd_reduce: 16 of 142 ms of a
+  // resnet18 step, profiles/r02_launch_summary_train_r18_b32.txt) re-read ge, G1 and nine spike words per element
+  const int egrid = grid_for(n4, rbd, ecsy_num_sms() * kPartBlocksPerSm);
 
   for (int t = T - 1; t >= 0; --t) {
     const bool spread = t <= T - 2;
     const bool has_next = t < T - 1;
     if (spread) {
-      k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi,
-                                                ge_lo, n4, beta, kappa);
+      k_lif_bwd_pre<<<egrid, rbd, (size_t)(rbd / c4) * C * sizeof(float), st>>>(
+          gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta, kappa, part, C);
       ECSY_LAUNCH_CHECK();
       int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
       if (rc) return rc;
@@ -417,6 +501,10 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       if (rc) return rc;
       rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
       if (rc) return rc;
+    }
+    static const int variant = getenv("ECSY_LIF_BWD_V") ? atoi(getenv("ECSY_LIF_BWD_V")) : 2;
+    const bool fused = variant != 0;
+    if (spread && !fused) {
       const int rgrid = grid_for(M, 64, ecsy_num_sms() * 4);
       k_lif_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, spikes + t * words, part,
                                                                                        (int)N, H, W, C);
@@ -424,11 +512,20 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
-    k_lif_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
-                                               spikes + t * words, has_next ? gx + (size_t)(t + 1) * mc : nullptr,
-                                               has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, thresh, lens, decay,
-                                               alpha);
+    const size_t psm = (spread && fused) ? (size_t)(rbd / c4) * 10 * C * sizeof(float) : 0;
+    float* pp = (spread && fused) ? part : nullptr;
+#define ECSY_POST_ARGS gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc, spikes + t * words, \
+        has_next ? gx + (size_t)(t + 1) * mc : nullptr, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, thresh, lens, \
+        decay, alpha, pp
+    if (variant == 3) k_lif_bwd_post<3><<<egrid, rbd, psm, st>>>(ECSY_POST_ARGS);
+    else if (variant == 4) k_lif_bwd_post<4><<<egrid, rbd, psm, st>>>(ECSY_POST_ARGS);
+    else k_lif_bwd_post<2><<<egrid, rbd, psm, st>>>(ECSY_POST_ARGS);
+#undef ECSY_POST_ARGS
     ECSY_LAUNCH_CHECK();
+    if (spread && fused) {
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, egrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      ECSY_LAUNCH_CHECK();
+    }
   }
   return ECSY_OK;
 }
@@ -499,7 +596,7 @@ extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const floa
     const float* o_t = out + (size_t)t * mc;
     if (spread) {
       k_lif_bwd_pre<<<egrid, kThreads, 0, st>>>(gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi,
-                                                ge_lo, n4, beta, kappa);
+                                                ge_lo, n4, beta, kappa, nullptr, C);
       ECSY_LAUNCH_CHECK();
       int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
       if (rc) return rc;

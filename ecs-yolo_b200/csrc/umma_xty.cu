@@ -128,11 +128,14 @@ k_umma_xty(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CU
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
         tmem_ld_wait();
         if (ra < g.Ca) {
+          // Cb is a multiple of 64 and nb divides it: the 32 columns are in range; 16-byte vector reductions (a quarter
+          // of the L2 atomic operations -- the small layers of this kernel were bound by them)
+          float* dst = g.out + (int64_t)ra * g.Cb + b0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cb = b0 + c0 + j;
-            if (cb < g.Cb) atomicAdd(g.out + (int64_t)ra * g.Cb + cb, g.alpha * __uint_as_float(v[j]));
-          }
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                         "f"(g.alpha * __uint_as_float(v[j])), "f"(g.alpha * __uint_as_float(v[j + 1])),
+                         "f"(g.alpha * __uint_as_float(v[j + 2])), "f"(g.alpha * __uint_as_float(v[j + 3])) : "memory");
         }
       }
     }
@@ -172,8 +175,9 @@ int ecsy_umma_xty(const void* p_hi, const void* p_lo, const void* q_hi, const vo
   const int ya = (Ca + 127) / 128, zb = Cb / nb;
   const int64_t tiles = (rows + kRows - 1) / kRows;
   int64_t rs = (2 * (int64_t)ecsy_num_sms()) / (ya * zb);
+  // every CTA ends with 128 x nb reductions into the output: give it at least 16 row tiles of contraction to amortise them
+  if (rs > tiles / 16) rs = tiles / 16;
   if (rs < 1) rs = 1;
-  if (rs > tiles) rs = tiles;
   g.row_splits = (int)rs;
   const int stage_bytes = split * (2 + nb / 64) * kBlk;
   int stages = (220 * 1024) / stage_bytes;

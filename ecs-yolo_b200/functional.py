@@ -515,7 +515,7 @@ def lif_ecs_bwd(gout: torch.Tensor, x: Act, w: LifW, pw_weight: torch.Tensor, af
     pwT = pack_conv_weight(pw_weight.detach().reshape(C, C).t().contiguous().reshape(C, C, 1, 1), w.splits)
     L = _cabi.lib()
     ws = torch.empty(L.ecsy_lif_ecs_bwd_ws_bytes(T, N, H, W, C, w.splits), device=dev, dtype=torch.uint8)
-    with _timed("lif_ecs_bwd", 1 + 7 * (T - 1)):
+    with _timed("lif_ecs_bwd", 1 + 6 * (T - 1)):
         _cabi.check(L.ecsy_lif_ecs_bwd(_p(gout), _p(sp.bits), _p(mem), _p(ecs), _p(w.dw_w), _p(w.dw_b), _p(pwT), w.splits,
                                        _p(gx), _p(g_dw_w), _p(g_dw_b), _p(g_pw_w), _p(g_pw_b), T, N, H, W, C,
                                        float(thresh), float(lens), float(decay), float(alpha), float(beta),
