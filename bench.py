@@ -395,6 +395,7 @@ def main():
                          "DDetect models) or a synthetic quadratic on the raw head outputs")
     ap.add_argument("--no-train", action="store_true", help="infer mode: skip the `train` sub-record")
     ap.add_argument("--no-parity-leg", action="store_true", help="skip the parity-precision timing of the same step")
+    ap.add_argument("--no-small-batch", action="store_true", help="skip the batch-1 eager / CUDA-graph record")
     ap.add_argument("--train-model", default="resnet18", help="model of the `train` sub-record (BASELINE configs[2])")
     ap.add_argument("--train-batch", type=int, default=32, help="images per GPU per training step")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
@@ -559,6 +560,43 @@ def main():
         parity_ips = args.batch * world * 2 / (p0.elapsed_time(p1) * 1e-3)
         E.set_precision(args.precision)
 
+    # small-batch serving: one image per call, eager launches vs CUDA-graph replay of the same launch sequence
+    small_rec = None
+    if not args.no_small_batch and rank == 0:
+        x1 = (x[:, :1] if x.dim() == 5 else x[:1]).contiguous()
+        x1_host = (x_host[:, :1] if x_host.dim() == 5 else x_host[:1]).contiguous().pin_memory()
+
+        def per_call_ms(fn, n=30):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        with torch.no_grad():
+            eager_ms = per_call_ms(lambda: model(x1))
+            gf = E.graph.GraphedForward(model, x1)
+            graph_ms = per_call_ms(lambda: gf(x1))
+            z1_host = torch.empty(gf.static_out[0].shape, dtype=torch.float32).pin_memory()
+
+            def e2e_call():
+                gf(x1_host)                                    # H2D copy of the image into the graph's input buffer + replay
+                z1_host.copy_(gf.static_out[0], non_blocking=True)
+                torch.cuda.current_stream().synchronize()      # the caller needs the detections before the next request
+            e2e1_ms = per_call_ms(e2e_call)
+        small_rec = {"workload": f"EMS-{args.model} T={args.T} inference, batch 1, {args.img}x{args.img}, {args.precision}",
+                     "eager_ms_per_image": eager_ms, "graph_ms_per_image": graph_ms, "graph_e2e_ms_per_image": e2e1_ms,
+                     "images_per_s_eager": 1e3 / eager_ms, "images_per_s_graph": 1e3 / graph_ms,
+                     "images_per_s_graph_e2e": 1e3 / e2e1_ms, "launches_per_replay": gf.launches_per_replay,
+                     "note": "ecs-yolo_b200/graph.py GraphedForward: the eval forward captured once, replayed per request; "
+                             "outputs bit-identical to eager (tests/test_gpu_graph.py); e2e = pinned-host image in, "
+                             "decoded predictions out, synchronised per request"}
+        del gf
+
     t = torch.tensor([ms_total, e2e_s * 1e3, parity_ips or 0.0], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t[:2], op=dist.ReduceOp.MAX)
@@ -644,6 +682,8 @@ def main():
                                    / (ms_total / args.steps * 1e-3) / 1e12,
     }
     line["parity"] = parity_record(args, parity_ips)
+    if small_rec is not None:
+        line["small_batch"] = small_rec
     if train_rec is not None:
         line["train"] = train_rec
     if world == 1 and not args.no_cpu_baseline:

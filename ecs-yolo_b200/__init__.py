@@ -9,12 +9,12 @@ The package directory carries the repo's hyphenated name, so it is imported thro
 """
 import os as _os
 
-from . import _cabi, functional, common, autograd, yolo, yolo_snn, dist, general, optim, events, loss, loss_tal, experimental  # noqa: F401
+from . import _cabi, functional, common, autograd, yolo, yolo_snn, dist, general, optim, events, loss, loss_tal, experimental, graph  # noqa: F401
 from .functional import set_precision  # noqa: F401
 from .convert import convert  # noqa: F401
 from . import ops  # noqa: F401  (registers torch.ops.ecsy.*)
 
-__all__ = ["common", "yolo", "yolo_snn", "functional", "general", "optim", "events", "loss", "loss_tal", "experimental", "ops", "set_precision", "convert", "cfg_path", "build_library"]
+__all__ = ["common", "yolo", "yolo_snn", "functional", "general", "optim", "events", "loss", "loss_tal", "experimental", "graph", "ops", "set_precision", "convert", "cfg_path", "build_library"]
 
 
 def cfg_path(name: str) -> str:
