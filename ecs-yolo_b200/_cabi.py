@@ -75,7 +75,7 @@ SIGNATURES = {
                             C.POINTER(C.c_float), _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _p, _p, _p, _z, _p]),
     "ecsy_tal_loss_ws_bytes": (_z, [_i, _l, _l, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ecsy_tal_loss": (_i, [C.POINTER(_p), C.POINTER(_p), _p, _l, _i, _l, _i, C.POINTER(C.c_int), C.POINTER(C.c_int),
-                           C.POINTER(C.c_float), _f, _f, _f, _f, _f, _p, _p, _z, _p]),
+                           C.POINTER(C.c_float), _f, _f, _f, _f, _f, _i, _f, _f, _p, _p, _z, _p]),
     "ecsy_ddetect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _l, _l, _p]),
 }
 
@@ -94,7 +94,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.ecsy_abi_version() != 1:
+        if L.ecsy_abi_version() != 2:
             raise RuntimeError("libecsy.so ABI version mismatch")
         _lib = L
     return _lib

@@ -26,7 +26,6 @@ using namespace ecsy_loss;
 
 constexpr int kMaxLevels = 5;
 constexpr int kReg = 16;         // DDetect.reg_max (models/yolo_snn.py:95)
-constexpr int kTopK = 10;        // utils/loss_tal.py:134
 constexpr float kAssignEps = 1e-9f;
 constexpr float kIouEps = 1e-7f;
 
@@ -39,6 +38,8 @@ struct TalArgs {
   int nl, nc, no, A;
   int64_t N, nt;
   float img_w, img_h, cls_pw, gain_box, gain_cls, gain_dfl, fl_gamma;
+  int topk;            // TaskAlignedAssigner hyper-parameters (utils/loss_tal.py:134-137: YOLOM / YOLOA / YOLOB)
+  float alpha, beta;
   // workspace
   float* pbox;       // [N][A][4] xyxy, grid units
   int* img_off;      // [N + 1]
@@ -147,6 +148,16 @@ __device__ float ciou(float4 g, float4 p) {
   return iou - (rho2 / c2 + v * alpha);
 }
 
+// x ** e as torch.pow evaluates it for a float tensor and a Python scalar: sqrt for 0.5, products for 1 / 2 / 3, powf else
+// (the defaults alpha = 0.5, beta = 6 take sqrtf and powf: the arithmetic the golden fixtures were matched with)
+__device__ __forceinline__ float pow_like_torch(float x, float e) {
+  if (e == 0.5f) return sqrtf(x);
+  if (e == 1.f) return x;
+  if (e == 2.f) return x * x;
+  if (e == 3.f) return x * x * x;
+  return powf(x, e);
+}
+
 // ---- one CTA per label: metrics over all anchors of its image + top-k ------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_tal_metric(const TalArgs a) {
   extern __shared__ float s_metric[];                       // [A] metric * in_gt, then -1 for taken entries
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) k_tal_metric(const TalArgs a) {
     float4 pb = reinterpret_cast<const float4*>(a.pbox)[(int64_t)b * a.A + an];
     pb.x *= st; pb.y *= st; pb.z *= st; pb.w *= st;
     const float ov = fmaxf(ciou(gt, pb), 0.f);
-    const float al = sqrtf(score) * powf(ov, 6.f);          // alpha 0.5, beta 6 (utils/loss_tal.py:136-137)
+    const float al = pow_like_torch(score, a.alpha) * pow_like_torch(ov, a.beta);   // (utils/tal/assigner.py:121)
     const float ax = ((float)(pix % a.nx[l]) + 0.5f) * st, ay = ((float)(pix / a.nx[l]) + 0.5f) * st;
     const bool in = fminf(fminf(ax - gt.x, ay - gt.y), fminf(gt.z - ax, gt.w - ay)) > kAssignEps;
     a.ov[(int64_t)q * a.A + an] = ov;
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) k_tal_metric(const TalArgs a) {
   }
   __syncthreads();
   if (!valid) return;                                       // padded / degenerate labels never become positive
-  for (int r = 0; r < kTopK && r < a.A; ++r) {
+  for (int r = 0; r < a.topk && r < a.A; ++r) {
     float bv = -2.f;
     int bi = 0x7fffffff;
     for (int an = threadIdx.x; an < a.A; an += kThreads) {
@@ -442,8 +453,8 @@ extern "C" size_t ecsy_tal_loss_ws_bytes(int nl, int64_t N, int64_t nt, const in
 
 extern "C" int ecsy_tal_loss(const float* const* feats, float* const* gfeats, const float* targets, int64_t nt, int nl,
                              int64_t N, int nc, const int* ny, const int* nx, const float* strides, float cls_pw,
-                             float gain_box, float gain_cls, float gain_dfl, float fl_gamma, float* out, void* ws,
-                             size_t ws_bytes, void* stream) {
+                             float gain_box, float gain_cls, float gain_dfl, float fl_gamma, int topk, float alpha,
+                             float beta, float* out, void* ws, size_t ws_bytes, void* stream) {
   ECSY_CHECK_ARG(nl >= 1 && nl <= kMaxLevels, "tal_loss: 1..%d detection levels, got %d", kMaxLevels, nl);
   ECSY_CHECK_ARG(feats && ny && nx && strides && out, "tal_loss: null argument");
   ECSY_CHECK_ARG(N >= 1 && nc >= 1 && nt >= 0 && (nt == 0 || targets), "tal_loss: bad sizes N=%lld nc=%d nt=%lld",
@@ -452,6 +463,9 @@ extern "C" int ecsy_tal_loss(const float* const* feats, float* const* gfeats, co
   TalArgs a{};
   a.nl = nl; a.nc = nc; a.no = nc + 4 * kReg; a.N = N; a.nt = nt; a.targets = targets; a.out = out;
   a.cls_pw = cls_pw; a.gain_box = gain_box; a.gain_cls = gain_cls; a.gain_dfl = gain_dfl; a.fl_gamma = fl_gamma;
+  ECSY_CHECK_ARG(topk >= 1 && alpha >= 0.f && beta >= 0.f, "tal_loss: assigner topk=%d alpha=%g beta=%g", topk, (double)alpha,
+                 (double)beta);
+  a.topk = topk; a.alpha = alpha; a.beta = beta;
   a.a_base[0] = 0;
   for (int l = 0; l < nl; ++l) {
     ECSY_CHECK_ARG(feats[l] && ny[l] >= 1 && nx[l] >= 1 && strides[l] > 0.f, "tal_loss: level %d: bad grid / stride", l);
@@ -463,7 +477,7 @@ extern "C" int ecsy_tal_loss(const float* const* feats, float* const* gfeats, co
   a.img_w = (float)nx[0] * strides[0];                      // feats[0].shape[2:] * stride[0] (:172)
   a.img_h = (float)ny[0] * strides[0];
   const size_t metric_smem = (size_t)a.A * 5;
-  ECSY_CHECK_ARG(a.A >= kTopK && metric_smem <= 200 * 1024, "tal_loss: %d anchors per image unsupported", a.A);
+  ECSY_CHECK_ARG(a.A >= topk && metric_smem <= 200 * 1024, "tal_loss: %d anchors per image unsupported (topk = %d)", a.A, topk);
   ECSY_CHECK_ARG(N * a.A < (1LL << 31) && nt * (int64_t)a.A < (1LL << 40) && N < 12000, "tal_loss: sizes too large");
   const TalWs w = tal_ws(N, a.A, nt);
   if (!ws || ws_bytes < w.total) {

@@ -6,9 +6,11 @@ C-ABI call (`ecsy_tal_loss`): no per-image Python loop, no padded [batch, max la
     loss, loss_items = compute_loss(pred, targets)          # pred: list of [N, 64 + nc, ny, nx]; targets [nt, 6] (GPU)
     loss.backward()
 
-fl_gamma > 0 wraps the class BCE in FocalLoss like the reference; use_dfl=False raises NotImplementedError.  The assigner's hyper-parameters are read from
-the YOLOM / YOLOA / YOLOB environment variables like the reference (:134-137), but only its defaults (10, 0.5, 6.0) are
-built into the kernel.
+fl_gamma > 0 wraps the class BCE in FocalLoss like the reference.  The assigner's hyper-parameters (topk, alpha, beta) are read
+from the YOLOM / YOLOA / YOLOB environment variables at construction like the reference (:134-137).  use_dfl=False raises
+NotImplementedError: the reference's own DDetect head (reg_max = 16, 64 box channels) cannot be trained that way either --
+without the DFL decode `bbox_decode` hands the 64-channel distribution to dist2bbox, which expects 4 (:103-113 of the
+reference's ComputeLoss.bbox_decode).
 """
 from __future__ import annotations
 
@@ -23,11 +25,12 @@ from .functional import _chk_cuda, _st, _timed
 
 REG_MAX = 16
 GAINS = (7.5, 0.5, 1.5)      # box, cls, dfl (utils/loss_tal.py:210-212)
+ASSIGNER = (10, 0.5, 6.0)    # TaskAlignedAssigner topk, alpha, beta (utils/loss_tal.py:134-137 defaults)
 
 
 def tal_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides: Sequence[float], cls_pw: float = 1.0,
-             gains: Sequence[float] = GAINS, need_grad: bool = True, fl_gamma: float = 0.0
-             ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+             gains: Sequence[float] = GAINS, need_grad: bool = True, fl_gamma: float = 0.0,
+             assigner: Sequence[float] = ASSIGNER) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """-> (out [6] = (loss, box, cls, dfl, foreground anchors, target_scores.sum()), gradients per level or [])."""
     feats = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in feats]
     _chk_cuda(*feats, targets)
@@ -56,7 +59,7 @@ def tal_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides: Sequ
     with _timed("loss", 9 if nt else 7):
         _cabi.check(L.ecsy_tal_loss(fp, gp, tg.data_ptr() if nt else None, nt, nl, N, no - 4 * REG_MAX, ny, nx, st,
                                     float(cls_pw), float(gains[0]), float(gains[1]), float(gains[2]), float(fl_gamma),
-                                    out.data_ptr(),
+                                    int(assigner[0]), float(assigner[1]), float(assigner[2]), out.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _st()), "tal_loss")
     return out, grads
 
@@ -85,9 +88,10 @@ class ComputeLoss:
         h = model.hyp
         self.fl_gamma = float(h.get("fl_gamma", 0.0))        # > 0: FocalLoss around the class BCE (:116-119)
         if not use_dfl:
-            raise NotImplementedError("use_dfl=False is not implemented on the device path")
-        if (int(os.getenv('YOLOM', 10)), float(os.getenv('YOLOA', 0.5)), float(os.getenv('YOLOB', 6.0))) != (10, 0.5, 6.0):
-            raise NotImplementedError("the kernel builds in the assigner defaults topk=10, alpha=0.5, beta=6.0")
+            raise NotImplementedError("use_dfl=False needs a 4-channel box head; the DDetect head of this path has reg_max = 16")
+        self.assigner = (int(os.getenv('YOLOM', 10)), float(os.getenv('YOLOA', 0.5)), float(os.getenv('YOLOB', 6.0)))
+        if self.assigner[0] < 1 or self.assigner[1] < 0 or self.assigner[2] < 0:
+            raise ValueError(f"TaskAlignedAssigner hyper-parameters (YOLOM, YOLOA, YOLOB) = {self.assigner}")
         m = model.module if hasattr(model, 'module') and hasattr(model.module, 'model') else model
         m = m.model[-1]
         if getattr(m, "reg_max", REG_MAX) != REG_MAX:
@@ -100,6 +104,6 @@ class ComputeLoss:
 
     def __call__(self, p, targets, img=None, epoch=0):
         feats = p[1] if isinstance(p, tuple) else p
-        cfg = dict(strides=self._strides, cls_pw=self.hyp["cls_pw"], fl_gamma=max(self.fl_gamma, 0.0))
+        cfg = dict(strides=self._strides, cls_pw=self.hyp["cls_pw"], fl_gamma=max(self.fl_gamma, 0.0), assigner=self.assigner)
         loss, out = _TalLossFn.apply(cfg, targets, *feats)
         return loss, out[1:4]

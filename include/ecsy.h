@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ECSY_ABI_VERSION 1
+#define ECSY_ABI_VERSION 2
 
 const char* ecsy_last_error(void);
 int ecsy_abi_version(void);
@@ -288,13 +288,15 @@ int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets
  * feats / gfeats: HOST arrays of nl DEVICE pointers to the raw DDetect training outputs [N][64 + nc][ny_l][nx_l]
  * (models/yolo_snn.py:117-119) and their gradients (gfeats or gfeats[l] may be null: forward only; otherwise
  * OVERWRITTEN, upstream gradient 1).  targets: device [nt][6] = (image, class, cx, cy, w, h) normalised; ny / nx /
- * strides: host arrays [nl]; gains: 7.5 / 0.5 / 1.5 in the reference (:210-212).
+ * strides: host arrays [nl]; gains: 7.5 / 0.5 / 1.5 in the reference (:210-212); topk / alpha / beta: the assigner's
+ * hyper-parameters (10 / 0.5 / 6.0 unless the YOLOM / YOLOA / YOLOB environment variables say otherwise, :134-137).
  * out: device [6] = loss (times the batch size), box, cls, dfl (the reference's loss_items), number of foreground
  * anchors, target_scores.sum().  Ties the reference leaves to torch.topk / argmax resolve to the lowest index. */
 size_t ecsy_tal_loss_ws_bytes(int nl, int64_t N, int64_t nt, const int* ny, const int* nx);
 int ecsy_tal_loss(const float* const* feats, float* const* gfeats, const float* targets, int64_t nt, int nl, int64_t N,
                   int nc, const int* ny, const int* nx, const float* strides, float cls_pw, float gain_box,
-                  float gain_cls, float gain_dfl, float fl_gamma, float* out, void* ws, size_t ws_bytes, void* stream);
+                  float gain_cls, float gain_dfl, float fl_gamma, int topk, float alpha, float beta, float* out, void* ws,
+                  size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

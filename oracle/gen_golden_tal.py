@@ -34,6 +34,10 @@ def main():
         nl = len(spec["grids"])
         det = types.SimpleNamespace(nl=nl, nc=spec["nc"], no=64 + spec["nc"], reg_max=16, stride=inp["strides"])
         hyp = dict(cls_pw=spec.get("cls_pw", 1.0), fl_gamma=spec.get("fl_gamma", 0.0), label_smoothing=spec.get("smooth", 0.0))
+        for k, v in zip(("YOLOM", "YOLOA", "YOLOB"), spec.get("assigner", (None, None, None))):
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = str(v)                  # read by ComputeLoss.__init__ (utils/loss_tal.py:134-137)
         crit = ComputeLoss(_Holder(det, hyp))
         fg = {}
         orig = crit.assigner.forward

@@ -67,18 +67,18 @@ def box_term_iou(b1, b2, eps=1e-7):
     return iou - (c_area - union) / c_area
 
 
-def assign_image(scores, boxes_px, pts_px, labels, gts):
+def assign_image(scores, boxes_px, pts_px, labels, gts, topk=TOPK, alpha=ALPHA, beta=BETA):
     """TaskAlignedAssigner for ONE image: scores [A, nc] (sigmoid), boxes_px [A, 4], pts_px [A, 2], labels [M] (long),
     gts [M, 4] xyxy pixels (all valid).  -> (gt index per anchor [A] long, fg [A] bool, normalised score per anchor [A])."""
     A, M = scores.shape[0], gts.shape[0]
     if M == 0:
         return torch.zeros(A, dtype=torch.long), torch.zeros(A, dtype=torch.bool), torch.zeros(A)
     ov = ciou_xyxy(gts[:, None, :], boxes_px[None, :, :]).clamp(0)                       # [M, A] (:120)
-    align = scores[:, labels].T.pow(ALPHA) * ov.pow(BETA)                               # (:121)
+    align = scores[:, labels].T.pow(alpha) * ov.pow(beta)                               # (:121)
     deltas = torch.cat((pts_px[None] - gts[:, None, :2], gts[:, None, 2:] - pts_px[None]), 2)
     in_gt = deltas.amin(2) > EPS                                                        # (:8-22)
     metric = align * in_gt
-    order = torch.sort(metric, dim=1, descending=True, stable=True).indices[:, :min(TOPK, A)]   # ties: lowest index
+    order = torch.sort(metric, dim=1, descending=True, stable=True).indices[:, :min(topk, A)]   # ties: lowest index
     in_top = torch.zeros(M, A, dtype=torch.bool)
     in_top[torch.arange(M)[:, None], order] = True
     pos = in_top & in_gt                                                                # (:105)
@@ -95,7 +95,8 @@ def assign_image(scores, boxes_px, pts_px, labels, gts):
     return gt_idx, fg, norm
 
 
-def compute_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides, cls_pw: float = 1.0, fl_gamma: float = 0.0):
+def compute_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides, cls_pw: float = 1.0, fl_gamma: float = 0.0,
+                 assigner=(TOPK, ALPHA, BETA)):
     """-> (loss [1]-shaped scalar tensor, loss_items [3] = (box, cls, dfl) detached, number of foreground anchors)."""
     N, no = feats[0].shape[:2]
     nc = no - 4 * REG_MAX
@@ -116,7 +117,7 @@ def compute_loss(feats: Sequence[torch.Tensor], targets: torch.Tensor, strides, 
             mine = targets[targets[:, 0] == b]
             xy, wh = mine[:, 2:4] * torch.tensor([W, H]), mine[:, 4:6] * torch.tensor([W, H])
             gts = torch.cat((xy - wh / 2, xy + wh / 2), 1)
-            gt_idx, fg, norm = assign_image(cls_logits[b].sigmoid(), boxes[b] * st, pts * st, mine[:, 1].long(), gts)
+            gt_idx, fg, norm = assign_image(cls_logits[b].sigmoid(), boxes[b] * st, pts * st, mine[:, 1].long(), gts, *assigner)
             if mine.shape[0]:
                 t_box[b] = gts[gt_idx] / st                                             # (:191)
                 t_score[b, torch.arange(A), mine[gt_idx, 1].long()] = norm * fg

@@ -423,6 +423,8 @@ TAL_CASES = {
     "tal_rect_nc1": dict(N=2, nc=1, grids=[(6, 10), (3, 5)], strides=[16.0, 32.0], nt=9, seed=904, wh=(0.4, 0.8)),
     "tal_small_boxes": dict(N=2, nc=4, grids=[(16, 16), (8, 8)], strides=[16.0, 32.0], nt=14, seed=905, wh=(0.04, 0.5)),
     "tal_focal": dict(N=2, nc=4, grids=[(8, 8), (4, 4)], strides=[16.0, 32.0], nt=10, seed=907, wh=(0.3, 0.7), fl_gamma=1.5),
+    "tal_assigner_hp": dict(N=2, nc=4, grids=[(10, 10), (5, 5)], strides=[16.0, 32.0], nt=16, seed=908, wh=(0.3, 0.8),
+                            assigner=(13, 1.0, 4.0)),           # YOLOM / YOLOA / YOLOB (utils/loss_tal.py:134-137)
     "tal_nl3_uneven": dict(N=4, nc=6, grids=[(16, 16), (8, 8), (4, 4)], strides=[8.0, 16.0, 32.0], nt=20, seed=906,
                            wh=(0.3, 0.9), skip_image=2, smooth=0.0, cls_pw=1.3),
 }

@@ -25,7 +25,7 @@ def test_library_exports_header_symbols():
     assert len(syms) >= 20
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ecsy.h but not exported"
-    assert lib.ecsy_abi_version() == 1
+    assert lib.ecsy_abi_version() == 2
 
 
 def test_ctypes_table_matches_header():

@@ -288,18 +288,21 @@ class _TalHolder(torch.nn.Module):
 
 
 @pytest.mark.parametrize("name", list(S.TAL_CASES))
-def test_tal_loss_golden(name):
+def test_tal_loss_golden(name, monkeypatch):
     """ecs.loss_tal.ComputeLoss (ecsy_tal_loss through autograd) against utils.loss_tal.ComputeLoss of the unmodified
     reference: same number of foreground anchors, loss / loss_items within 1e-5 relative, gradients within 1e-4."""
     E = ecsy()
     gold = _load("post_tal")[name]
     spec = S.TAL_CASES[name]
     inp = S.tal_inputs(spec)
+    hp = spec.get("assigner", (10, 0.5, 6.0))
+    for k, v in zip(("YOLOM", "YOLOA", "YOLOB"), hp):       # read at construction like the reference (utils/loss_tal.py:134-137)
+        monkeypatch.setenv(k, str(v))
     crit = E.loss_tal.ComputeLoss(_TalHolder(spec, inp["strides"]))
     feats = [x.cuda().requires_grad_(True) for x in inp["feats"]]
     loss, items = crit(feats, inp["targets"].cuda())
     out, _ = E.loss_tal.tal_loss([x.detach() for x in feats], inp["targets"].cuda(), spec["strides"],
-                                 spec.get("cls_pw", 1.0), need_grad=False, fl_gamma=spec.get("fl_gamma", 0.0))
+                                 spec.get("cls_pw", 1.0), need_grad=False, fl_gamma=spec.get("fl_gamma", 0.0), assigner=hp)
     assert int(out[4]) == gold["fg"], (int(out[4]), gold["fg"])
     assert abs(float(out[5]) - gold["score_sum"]) <= 1e-5 * max(gold["score_sum"], 1.0)
     assert loss.dim() == 0 and items.shape == (3,) and not items.requires_grad

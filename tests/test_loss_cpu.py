@@ -52,9 +52,15 @@ def test_tal_compute_loss_constructor():
         E.loss_tal.ComputeLoss(_Holder(det8, dict(cls_pw=1.0, fl_gamma=0.0)))
 
 
-def test_assigner_env_overrides_are_rejected(monkeypatch):
+def test_assigner_env_overrides(monkeypatch):
+    """utils/loss_tal.py:134-137: topk / alpha / beta from YOLOM / YOLOA / YOLOB at construction."""
     E = ecsy()
     det = types.SimpleNamespace(nl=2, nc=3, no=67, reg_max=16, stride=torch.tensor([16.0, 32.0]))
-    monkeypatch.setenv("YOLOM", "13")                                    # utils/loss_tal.py:134: topk from the environment
-    with pytest.raises(NotImplementedError):
+    assert E.loss_tal.ComputeLoss(_Holder(det, dict(cls_pw=1.0, fl_gamma=0.0))).assigner == (10, 0.5, 6.0)
+    monkeypatch.setenv("YOLOM", "13")
+    monkeypatch.setenv("YOLOA", "1.0")
+    monkeypatch.setenv("YOLOB", "4.0")
+    assert E.loss_tal.ComputeLoss(_Holder(det, dict(cls_pw=1.0, fl_gamma=0.0))).assigner == (13, 1.0, 4.0)
+    monkeypatch.setenv("YOLOM", "0")
+    with pytest.raises(ValueError):
         E.loss_tal.ComputeLoss(_Holder(det, dict(cls_pw=1.0, fl_gamma=0.0)))

@@ -104,7 +104,7 @@ def test_tal_loss_oracle(name):
     assert abs(S.checksum(*inp["feats"], inp["targets"]) - gold["chk"]) <= 1e-6 * abs(gold["chk"])
     feats = [x.clone().requires_grad_(True) for x in inp["feats"]]
     loss, items, n_fg = TO.compute_loss(feats, inp["targets"], spec["strides"], spec.get("cls_pw", 1.0),
-                                        spec.get("fl_gamma", 0.0))
+                                        spec.get("fl_gamma", 0.0), spec.get("assigner", (10, 0.5, 6.0)))
     assert n_fg == gold["fg"]
     assert torch.allclose(loss, gold["loss"], rtol=2e-6, atol=1e-6), (float(loss), float(gold["loss"]))
     assert torch.allclose(items, gold["items"], rtol=2e-6, atol=1e-6)
