@@ -76,6 +76,9 @@ SIGNATURES = {
     "ecsy_tal_loss_ws_bytes": (_z, [_i, _l, _l, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ecsy_tal_loss": (_i, [C.POINTER(_p), C.POINTER(_p), _p, _l, _i, _l, _i, C.POINTER(C.c_int), C.POINTER(C.c_int),
                            C.POINTER(C.c_float), _f, _f, _f, _f, _f, _i, _f, _f, _p, _p, _z, _p]),
+    "ecsy_stem_conv_supported": (_i, [_i, _i, _i, _i]),
+    "ecsy_stem_conv_ws_bytes": (_z, [_l, _i, _i]),
+    "ecsy_stem_conv": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _z, _p]),
     "ecsy_ddetect_decode": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _l, _l, _p]),
 }
 

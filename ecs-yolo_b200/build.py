@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libecsy.so")
-SOURCES = ["cabi.cu", "elementwise.cu", "conv_misc.cu", "lif.cu", "umma_gemm.cu", "umma_xty.cu", "lif_bwd.cu", "lif_fused.cu", "lif_wave.cu", "nms.cu", "optim.cu", "events.cu", "loss.cu", "tal_loss.cu"]
+SOURCES = ["cabi.cu", "elementwise.cu", "conv_misc.cu", "lif.cu", "umma_gemm.cu", "umma_xty.cu", "lif_bwd.cu", "lif_fused.cu", "lif_wave.cu", "stem_conv.cu", "nms.cu", "optim.cu", "events.cu", "loss.cu", "tal_loss.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -27,7 +27,8 @@ _state = {"splits": 2, "conv_ts": os.environ.get("ECSY_CONV_TS", "auto"),
           "lif_fused": os.environ.get("ECSY_LIF_FUSED", "0") == "1",
           "lif_wave": {"1": "auto", "0": "off"}.get(os.environ.get("ECSY_LIF_WAVE", "auto"), os.environ.get("ECSY_LIF_WAVE", "auto")),
           "lif_store": os.environ.get("ECSY_LIF_STORE", "1") == "1",
-          "dispatch": os.environ.get("ECSY_DISPATCH", "ops")}
+          "dispatch": os.environ.get("ECSY_DISPATCH", "ops"),
+          "stem_kernel": os.environ.get("ECSY_STEM_KERNEL", "1") == "1"}
 
 # ---- launch accounting / per-operator CUDA-event timing (used by bench.py) ----
 launches = {"n": 0}
@@ -298,6 +299,7 @@ class ConvW:
     splits: int
     dense_groups: bool = False   # `packed` holds the block-diagonal dense form of a grouped weight
     packed_ts: Optional[torch.Tensor] = None   # spike-conv form for the tensor-memory path (ecsy_pack_spike_conv_weight)
+    stem: Optional[torch.Tensor] = None        # real-image stem form for ecsy_stem_conv (pack_stem_weight)
 
 
 def densify_grouped(weight: torch.Tensor, groups: int) -> torch.Tensor:
@@ -322,6 +324,16 @@ def pack_spike_conv_weight(w: torch.Tensor, splits: int) -> torch.Tensor:
     return out
 
 
+def pack_stem_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[64, Ci <= 4, k, k] -> bf16 [64][ceil(k/2) * 64] for ecsy_stem_conv: K entry kb*64 + part*32 + kx*4 + ci holds
+    W[co][ci][2*kb + part][kx] (a kernel ROW is 8 pixels x 4 channels of the NHWC4 image = 32 K entries), zeros elsewhere."""
+    Co, Ci, k, _ = weight.shape
+    KB = (k + 1) // 2
+    t = torch.zeros(Co, 2 * KB, 8, 4, device=weight.device, dtype=torch.float32)
+    t[:, :k, :k, :Ci] = weight.detach().float().permute(0, 2, 3, 1)
+    return t.reshape(Co, KB * 64).to(torch.bfloat16).contiguous()
+
+
 def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, umma: bool, simt: bool,
                 densify: bool = False) -> ConvW:
     splits = get_splits()
@@ -335,6 +347,8 @@ def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, 
     if (packed is not None and bias is None and (groups == 1 or densify)
             and _cabi.lib().ecsy_spike_conv_ts_supported(Cig * groups, Co)):
         cw.packed_ts = pack_spike_conv_weight(dense, splits)
+    if umma and bias is None and groups == 1 and kh == kw and _cabi.lib().ecsy_stem_conv_supported(Cig, Co, kh, splits):
+        cw.stem = pack_stem_weight(weight)
     return cw
 
 
@@ -693,6 +707,14 @@ def real_conv(x: Act, w: ConvW, scale=None, shift=None, bias_mul: float = 1.0) -
     Wo = (W + 2 * w.pad - w.k) // w.stride + 1
     out = torch.empty(Tp, N, Ho, Wo, w.co, device=x.data.device, dtype=torch.float32)
     L = _cabi.lib()
+    if w.stem is not None and w.splits == 1 and _state["stem_kernel"]:
+        # the image stem (3 -> 64, 7x7 / 2) in fast precision: dedicated tcgen05 kernel on the NHWC4 bf16 image
+        ws = torch.empty(L.ecsy_stem_conv_ws_bytes(Tp * N, H, W), device=x.data.device, dtype=torch.uint8)
+        flops["real_conv"] += 2.0 * Tp * N * Ho * Wo * w.co * w.ci * w.k * w.k
+        with _timed("real_conv", 2):
+            _cabi.check(L.ecsy_stem_conv(_p(x.data), Tp * N, H, W, w.ci, _p(w.stem), _p(out), _p(scale), _p(shift), w.co, w.k,
+                                         w.stride, w.pad, _p(ws), ws.numel(), _st()), "stem_conv")
+        return Act(out, x.T)
     use_umma = w.packed is not None and w.groups == 1 and w.co % 64 == 0 and w.bias is None
     if w.splits == 2 and w.ci < 64 and w.simt is not None:
         use_umma = False  # parity mode: the tiny-K stem runs in plain fp32 (the 3-term bf16 split leaves ~6e-6)

@@ -280,6 +280,16 @@ int ecsy_yolo_loss(const float* const* p, float* const* gp, const float* targets
                    float obj, float cls, float cls_pw, float obj_pw, float cp, float cn, float anchor_t, float gr,
                    float fl_gamma, float* slide_state, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* Stem convolution of the real-valued image, fast precision (one bf16 plane): Conv_1 / Snn_Conv2d on a non-spike input,
+ * /root/reference/models/common.py:409-425 with :609-624 (F.conv2d per timestep; a T-broadcast image is convolved once).
+ * x: device [imgs][H][W][Cin] fp32 (Cin <= 4); w_stem: device bf16 [64][ceil(k/2) * 64], entry (co, kb*64 + part*32 + kx*4 + ci)
+ * = W[co][ci][2*kb + part][kx], zero elsewhere; out: [imgs][Ho][Wo][64] fp32 = conv * scale + shift (scale / shift optional,
+ * per output channel: the folded tdBN of inference).  ecsy_stem_conv_supported: Cin <= 4, Cout == 64, k <= 8, splits == 1. */
+int ecsy_stem_conv_supported(int Cin, int Cout, int k, int splits);
+size_t ecsy_stem_conv_ws_bytes(int64_t imgs, int H, int W);
+int ecsy_stem_conv(const float* x, int64_t imgs, int H, int W, int Cin, const void* w_stem, float* out, const float* scale,
+                   const float* shift, int Cout, int k, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Stack-B training loss, forward + gradient in one call: replaces ComputeLoss.__call__ of
  * utils/loss_tal.py:162-215 with TaskAlignedAssigner (utils/tal/assigner.py:51-179; topk 10, alpha 0.5, beta 6, CIoU
  * overlaps), BCE class term with pos_weight, the box term as the reference evaluates it (GIoU: utils/metrics2.py:282

@@ -497,3 +497,31 @@ def test_spread_dw_versions(C, N, H, W):
     got = (h2.float() + l2.float()).cpu()
     assert float((got - want).abs().max()) < 4e-5      # hi + lo planes carry ~16 mantissa bits
     assert float((h2.float().cpu() - want).abs().max()) < 2 ** -8 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96, 7, 2, 3), (1, 3, 50, 70, 7, 2, 3), (2, 1, 33, 130, 3, 1, 1), (1, 4, 40, 40, 5, 2, 2),
+                                   (3, 3, 64, 64, 8, 2, 3)])
+def test_stem_conv_kernel(shape):
+    """ecsy_stem_conv (fast precision: bf16 image x bf16 weights, fp32 accumulation on tcgen05) against F.conv2d in fp32 on
+    the SAME bf16-rounded operands (models/common.py:609-624 semantics), with a folded scale / shift; ragged tiles (Wo not a
+    multiple of 64, odd Ho), every supported Cin, even and odd kernel sizes."""
+    import torch.nn.functional as tF
+    E = ecsy()
+    F_ = E.functional
+    N, Ci, H, W, k, s, p = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(N, Ci, H, W, generator=g)
+    w = torch.randn(64, Ci, k, k, generator=g) * 0.2
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g)
+    want = tF.conv2d(x.bfloat16().float(), w.bfloat16().float(), None, s, p) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    E.set_precision("fast")
+    try:
+        cw = F_.make_conv_w(w.cuda(), None, s, p, 1, True, True)
+        assert cw.stem is not None
+        a = F_.Act.from_ref(x.cuda().unsqueeze(0))
+        got = F_.real_conv(a, cw, scale.cuda(), shift.cuda()).data[0].permute(0, 3, 1, 2).cpu()
+    finally:
+        E.set_precision("parity")
+    assert got.shape == want.shape
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 2e-6, err
