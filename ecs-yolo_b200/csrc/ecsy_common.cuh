@@ -266,6 +266,19 @@ __device__ __forceinline__ float ldg_stream_f(const float* p) {
   return r;
 }
 
+// Fast-precision tanh (one MUFU op, absolute error ~2^-11): the same instruction as elementwise.cu's tanh_fast, shared with
+// the GEMM-epilogue ECS step (ECSY_ACCURATE_TANH selects the accurate form at compile time in both).
+__device__ __forceinline__ float tanh_hw(float v) {
+#ifdef ECSY_ACCURATE_TANH
+  const float y = __expf(2.f * v);
+  return 1.f - __fdividef(2.f, y + 1.f);
+#else
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+#endif
+}
+
 // Round-to-nearest ops that ptxas may not contract into FMAs: the LIF update reproduces the
 // reference's separately rounded element-wise products and sums (models/common.py:306-309).
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }

@@ -82,6 +82,14 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
       float* spread_c = spread;
       __nv_bfloat16* a_hi_c = a_hi;
       __nv_bfloat16* a_lo_c = a_lo;
+      // fast precision, opt-in (ECSY_ECS_GEMM=1): the ECS step as the EPILOGUE of the point-wise GEMM (k_ecs_gemm: `spread`
+      // never reaches HBM, -4 B per element-step, same spikes bit for bit -- tests/test_gpu_ops.py).  MEASURED SLOWER
+      // (resnet34, batch 64: lif_ecs 29.8 ms two kernels, 32.5 ms fused): the step's x / membrane / trace loads land in
+      // the registers of 8 epilogue warps (45 KB in flight per SM at 168 registers per thread), half of what the
+      // stand-alone streaming kernel keeps in flight with 2048 threads per SM, so the fused epilogue runs below the HBM rate
+      // and the saved bytes do not pay for it.
+      static const bool ecs_gemm_env = getenv("ECSY_ECS_GEMM") != nullptr && getenv("ECSY_ECS_GEMM")[0] == '1';
+      const bool ecs_gemm = ecs_gemm_env && half_state && !fused_dw && Mc >= 128;
       if (fused_dw) {
         // experimental: depth-wise spread computed by the GEMM's producer warps (no A round trip through HBM);
         // measured slower than the two-kernel path at 1 CTA/SM (producer address math + 8 warps of ALU work)
@@ -90,8 +98,10 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
       } else {
         rc = ecsy_launch_spread_dw(spikes + t * words + wo, dw_w, dw_b, a_hi_c, a_lo_c, (int)nc, H, W, C, st);
         if (rc) return rc;
-        rc = ecsy_umma_dense(a_hi_c, a_lo_c, Mc, C, pw_packed, splits, spread_c, C, nullptr, nullptr, nullptr, 0, st, half_state);
-        if (rc) return rc;
+        if (!ecs_gemm) {
+          rc = ecsy_umma_dense(a_hi_c, a_lo_c, Mc, C, pw_packed, splits, spread_c, C, nullptr, nullptr, nullptr, 0, st, half_state);
+          if (rc) return rc;
+        }
       }
       EcsStep s{};
       s.spread = spread_c; s.pw_b = pw_b;
@@ -113,7 +123,7 @@ extern "C" int ecsy_lif_ecs_fwd(const float* x, int64_t x_tstride, const float* 
       s.first = (t == 0) ? 1 : 0;
       s.half_state = half_state;
       s.thresh = thresh; s.decay = decay; s.alpha = alpha; s.beta = beta; s.kappa = kappa;
-      rc = ecsy_launch_ecs_step(s, Mc, C, st);
+      rc = ecs_gemm ? ecsy_umma_ecs_step(a_hi_c, Mc, C, pw_packed, s, st) : ecsy_launch_ecs_step(s, Mc, C, st);
       if (rc) return rc;
     }
   }

@@ -1607,6 +1607,224 @@ k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Point-wise spread GEMM with the ECS step as its EPILOGUE (fast precision):
+//     S = A[M][C] (bf16, the depth-wise output) * Wpw[C][C]^T   stays in tensor memory / shared memory, and the epilogue
+//     runs   e_t = alpha (S + b) + kappa e_{t-1};  m_{t+1} = decay m_t (1 - s_t) + x_{t+1} + beta tanh(e_t);  s_{t+1} = m_{t+1} > th
+// (models/common.py:263-281) on it: `spread` never exists in HBM (-4 B per element-step, one launch less per timestep).
+// The arithmetic is k_ecs_step<true>'s, value for value -- S is rounded to fp16 exactly where the two-kernel path stored
+// it -- so this kernel and the two-kernel path produce the SAME spikes (the BPTT recompute relies on that).
+// Mainloop of k_dense_tma_h (A and B by TMA, SS-mode MMA, two accumulator buffers); warps 0-3 / 4-7: epilogue groups
+// (group g owns buffer g = every other tile), 8 TMA, 9 MMA.  An epilogue warp owns 32 rows: tcgen05.ld (a row per lane)
+// -> padded staging tile -> 16 lanes per row: x, membrane, trace and spike word of 2 rows x 64 channels are 2 x 256-byte
+// runs per request, four requests of each in flight per lane.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEgRow = 68;   // floats per staged row (64 + 4: conflict-free 128-bit accesses both ways)
+
+struct EgArgs {
+  int m_tiles, n_tiles, kb_total, stages;
+  uint32_t stg_off, ctl_off;
+  int64_t M;
+  int C;
+  EcsStep s;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kDtThreads, 1)
+k_ecs_gemm(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const EgArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  constexpr int kTmemCols = 2 * BN;
+  constexpr int kSlices = BN / 64;
+  DtCtl* ctl = reinterpret_cast<DtCtl*>(smem + g.ctl_off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->tmem_full[b], 1);
+      mbar_init(&ctl->tmem_empty[b], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<kTmemCols>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 8) {
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* st = smem + (size_t)stage * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)kStageBytes);
+          tma_load_2d(st, &tm_a, &ctl->full[stage], kb * 64, m_tile * 128);
+          tma_load_2d(st + kATileBytes, &tm_b, &ctl->full[stage], kb * 64, n_tile * BN);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      mbar_wait(&ctl->tmem_empty[buf], bphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        mbar_wait(&ctl->full[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&ctl->empty[stage]);
+          if (kb == g.kb_total - 1) umma_commit(&ctl->tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---- epilogue groups: TMEM -> staging tile -> ECS step on coalesced rows ----
+    const uint32_t ge = (uint32_t)warp >> 2;
+    const int q = warp & 3;
+    float* stg = reinterpret_cast<float*>(smem + g.stg_off) + warp * (32 * kEgRow);
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ge * BN;
+    const EcsStep& p = g.s;
+    const int C = g.C;
+    const int lr = lane >> 4, c4 = (lane & 15) * 4, sub = lane & 7;
+    uint32_t git = 0;
+    for (int tile = (int)blockIdx.x + (int)ge * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, ++git) {
+      const int m_tile = tile / g.n_tiles, n_tile = tile - m_tile * g.n_tiles;
+      const int64_t pix0 = (int64_t)m_tile * 128 + q * 32;
+      mbar_wait(&ctl->tmem_full[ge], git & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int j = 0; j < kSlices; ++j) {
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_row + j * 64, v0);
+          tmem_ld_32x32(t_row + j * 64 + 32, v1);
+          tmem_ld_wait();
+          if (j == kSlices - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&ctl->tmem_empty[ge]);
+          }
+          float* my = stg + lane * kEgRow;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<uint4*>(my + 4 * c) = make_uint4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+            *reinterpret_cast<uint4*>(my + 32 + 4 * c) = make_uint4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+          }
+        }
+        __syncwarp();
+        const int ch = n_tile * BN + j * 64 + c4;
+        const float4 pb = *reinterpret_cast<const float4*>(p.pw_b + ch);
+        float4 isc = make_float4(1.f, 1.f, 1.f, 1.f), ish = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.in_scale != nullptr) {
+          isc = *reinterpret_cast<const float4*>(p.in_scale + ch);
+          ish = *reinterpret_cast<const float4*>(p.in_shift + ch);
+        }
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 4) {
+          float4 xv[4], mv[4];
+          uint2 eh[4];
+          uint32_t wd[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = (i0 + u) * 2 + lr;
+            const int64_t pix = pix0 + r;
+            xv[u] = mv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            eh[u] = make_uint2(0u, 0u);
+            wd[u] = 0u;
+            if (pix < g.M) {
+              const int64_t idx = pix * C + ch;
+              xv[u] = ldg_stream(reinterpret_cast<const float4*>(p.x_next + idx));
+              mv[u] = *reinterpret_cast<const float4*>(p.mem_in + idx);
+              if (!p.first) eh[u] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.ecs) + idx);
+              wd[u] = p.bits_t[idx >> 5];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = (i0 + u) * 2 + lr;
+            const int64_t pix = pix0 + r;
+            const bool ok = pix < g.M;
+            const int64_t idx = pix * C + ch;
+            const float4 sv4 = *reinterpret_cast<const float4*>(stg + r * kEgRow + c4);
+            float xin[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+            if (p.in_scale != nullptr) {
+              xin[0] = add_rn(mul_rn(xin[0], isc.x), ish.x); xin[1] = add_rn(mul_rn(xin[1], isc.y), ish.y);
+              xin[2] = add_rn(mul_rn(xin[2], isc.z), ish.z); xin[3] = add_rn(mul_rn(xin[3], isc.w), ish.w);
+            }
+            // the two-kernel path stores S as fp16 between the GEMM and the step: same rounding here
+            const float2 s01 = __half22float2(__floats2half2_rn(sv4.x, sv4.y)), s23 = __half22float2(__floats2half2_rn(sv4.z, sv4.w));
+            const float sp[4] = {s01.x, s01.y, s23.x, s23.y};
+            const float2 e01 = __half22float2(*reinterpret_cast<const __half2*>(&eh[u].x));
+            const float2 e23 = __half22float2(*reinterpret_cast<const __half2*>(&eh[u].y));
+            const float eo[4] = {e01.x, e01.y, e23.x, e23.y};
+            const float mo[4] = {mv[u].x, mv[u].y, mv[u].z, mv[u].w};
+            const float bb[4] = {pb.x, pb.y, pb.z, pb.w};
+            const uint32_t pw = wd[u] >> (4 * sub);
+            float mn[4], en[4];
+            uint32_t nib = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float s_acc = add_rn(sp[k], bb[k]);
+              en[k] = add_rn(mul_rn(p.alpha, s_acc), mul_rn(p.kappa, eo[k]));
+              const float fecs = mul_rn(p.beta, tanh_hw(en[k]));
+              const float keep = ((pw >> k) & 1u) ? 0.f : 1.f;
+              mn[k] = add_rn(add_rn(mul_rn(mul_rn(mo[k], p.decay), keep), xin[k]), fecs);
+              nib |= (mn[k] > p.thresh ? 1u : 0u) << k;
+            }
+            if (ok) {
+              if (p.mem_out != nullptr) *reinterpret_cast<float4*>(p.mem_out + idx) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+              if (p.store_ecs) {
+                const __half2 h01 = __floats2half2_rn(en[0], en[1]), h23 = __floats2half2_rn(en[2], en[3]);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.ecs) + idx) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+              }
+              if (p.ecs_save != nullptr) *reinterpret_cast<float4*>(p.ecs_save + idx) = make_float4(en[0], en[1], en[2], en[3]);
+            } else {
+              nib = 0;
+            }
+            uint32_t w = nib << (4 * sub);
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+            if (ok && sub == 0) p.bits_next[idx >> 5] = w;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Weight gradient of the spike convolution:  dW[co][(tap, ci)] += sum_pixels gy[p][co] * s[p*stride + tap - pad][ci]
 // The contraction runs over PIXELS, i.e. over the rows of both operands, so both are fed to the tensor
 // core as MN-major tiles: A = gy tile [128 pixels x 128 co] (bf16 hi [+ lo], 4-D TMA boxes in the tile's
@@ -2214,6 +2432,61 @@ int launch_dense_tma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return ECSY_OK;
 }
 }  // namespace
+
+namespace {
+template <int BN>
+int launch_ecs_gemm(const CUtensorMap& ta, const CUtensorMap& tb, EgArgs g, cudaStream_t st) {
+  auto kern = k_ecs_gemm<BN>;
+  static bool attr = false;
+  if (!attr) {
+    ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr = true;
+  }
+  constexpr int stage_bytes = kATileBytes + BN * 128;
+  constexpr int stg_bytes = 8 * 32 * kEgRow * (int)sizeof(float);
+  const int fixed = 1024 + (int)sizeof(DtCtl) + 128 + stg_bytes;
+  int stages = (kSmemLimit - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    ecsy_set_error("ecs_gemm: shared memory budget allows only %d stage(s)", stages);
+    return ECSY_ERR_UNSUPPORTED;
+  }
+  g.stages = stages;
+  g.stg_off = (uint32_t)stages * stage_bytes;
+  g.ctl_off = g.stg_off + (uint32_t)stg_bytes;
+  const int smem = 1024 + (int)g.ctl_off + (int)sizeof(DtCtl) + 64;
+  int grid = g.m_tiles * g.n_tiles;
+  const int sms = ecsy_num_sms();
+  if (grid > sms) grid = sms;
+  kern<<<grid, kDtThreads, smem, st>>>(ta, tb, g);
+  ECSY_LAUNCH_CHECK();
+  return ECSY_OK;
+}
+}  // namespace
+
+// One ECS timestep with the point-wise spread GEMM fused in front of it (fast precision: s.half_state): a_hi [M][C] bf16 =
+// dw(s_t), pw_packed [C][C] bf16; everything else as ecsy_launch_ecs_step (s.spread is not used).
+int ecsy_umma_ecs_step(const void* a_hi, int64_t M, int C, const void* pw_packed, const EcsStep& s, cudaStream_t st) {
+  ECSY_CHECK_ARG(a_hi && pw_packed && C % 64 == 0 && M >= 128 && s.half_state, "ecs_gemm: bad arguments");
+  const int BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
+  CUtensorMap ta, tb;
+  int rc = ecsy_tensor_map_bf16(a_hi, (uint64_t)M, (uint64_t)C, 128, &ta);
+  if (rc) return rc;
+  rc = ecsy_tensor_map_bf16(pw_packed, (uint64_t)C, (uint64_t)C, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  EgArgs g{};
+  g.m_tiles = (int)((M + 127) / 128);
+  g.n_tiles = C / BN;
+  g.kb_total = C / 64;
+  g.M = M;
+  g.C = C;
+  g.s = s;
+  switch (BN) {
+    case 64: return launch_ecs_gemm<64>(ta, tb, g, st);
+    case 128: return launch_ecs_gemm<128>(ta, tb, g, st);
+    default: return launch_ecs_gemm<256>(ta, tb, g, st);
+  }
+}
 
 // Dense GEMM on a bf16 A matrix (hi [+ lo]) : out[M][Cout] = A * W^T (*scale + shift) (+ residual)
 int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const void* w_packed, int splits, float* out,

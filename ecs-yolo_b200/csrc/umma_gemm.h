@@ -34,6 +34,7 @@ struct EcsStep {
   float thresh, decay, alpha, beta, kappa;
 };
 int ecsy_launch_ecs_step(const EcsStep& s, int64_t pixels, int C, cudaStream_t st);
+int ecsy_umma_ecs_step(const void* a_hi, int64_t M, int C, const void* pw_packed, const EcsStep& s, cudaStream_t st);
 int ecsy_launch_spread_dw(const uint32_t* bits, const float* dw_w, const float* dw_b, __nv_bfloat16* a_hi,
                           __nv_bfloat16* a_lo, int N, int H, int W, int C, cudaStream_t st);
 

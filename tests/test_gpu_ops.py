@@ -1,11 +1,14 @@
 """GPU parity tests of the individual C-ABI operators against the golden reference outputs
 (tests/golden, produced by the unmodified reference) and the CPU oracle."""
+import os
+import sys
+
 import pytest
 import torch
 
 import ecs_oracle as O
 import seeded as S
-from util import agree, ecsy, load_golden, nhwc, rel_l2
+from util import ROOT, agree, ecsy, load_golden, nhwc, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -525,3 +528,18 @@ def test_stem_conv_kernel(shape):
     assert got.shape == want.shape
     err = float((got - want).abs().max() / want.abs().max())
     assert err < 2e-6, err
+
+
+def test_ecs_step_as_gemm_epilogue_equals_two_kernels():
+    """k_ecs_gemm (the ECS step as the epilogue of the point-wise spread GEMM, fast precision) must produce the SAME spikes,
+    membranes and traces, bit for bit, as spread GEMM -> fp16 -> k_ecs_step (the BPTT recompute relies on it): ragged row
+    counts, every tile width, folded input affine, stored state.  The switch is read once per process: two subprocesses."""
+    import subprocess
+    digests = []
+    for v in ("0", "1"):
+        env = dict(os.environ, ECSY_ECS_GEMM=v)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "lif_hash.py")], env=env, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1] and len(digests[0]) == 64
