@@ -553,6 +553,69 @@ __global__ void k_gy_to_bf16(const float* __restrict__ g, const float* __restric
   }
 }
 
+// The un-strided case (every 3x3 / stride-1 conv of the backbone) of k_gy_to_bf16: blockDim is a multiple of C/4, so a thread
+// keeps one channel quad -- coefficients in registers, no index division -- and has two rows of loads in flight.
+__global__ void __launch_bounds__(256)
+k_gy_to_bf16_plain(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ A,
+                   const float* __restrict__ B, const float* __restrict__ Cv, __nv_bfloat16* __restrict__ hi,
+                   __nv_bfloat16* __restrict__ lo, int64_t rows, int C) {
+  const int c4 = C >> 2;
+  const int tq = threadIdx.x % c4, ty = threadIdx.x / c4, nty = blockDim.x / c4;
+  float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f), c = b;
+  if (A != nullptr) {
+    a = *reinterpret_cast<const float4*>(A + tq * 4);
+    b = *reinterpret_cast<const float4*>(B + tq * 4);
+    c = *reinterpret_cast<const float4*>(Cv + tq * 4);
+  }
+  const int64_t rstep = (int64_t)gridDim.x * nty;
+  auto emit = [&](int64_t i, float4 v, float4 yv) {
+    if (A != nullptr) {
+      v.x = fmaf(a.x, v.x, fmaf(b.x, yv.x, c.x)); v.y = fmaf(a.y, v.y, fmaf(b.y, yv.y, c.y));
+      v.z = fmaf(a.z, v.z, fmaf(b.z, yv.z, c.z)); v.w = fmaf(a.w, v.w, fmaf(b.w, yv.w, c.w));
+    }
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (lo != nullptr) {
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      reinterpret_cast<uint2*>(lo)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+  };
+  int64_t r = (int64_t)blockIdx.x * nty + ty;
+  for (; r + rstep < rows; r += 2 * rstep) {
+    const int64_t i0 = r * c4 + tq, i1 = (r + rstep) * c4 + tq;
+    const float4 v0 = ecsy::ldg_stream(reinterpret_cast<const float4*>(g) + i0);
+    const float4 v1 = ecsy::ldg_stream(reinterpret_cast<const float4*>(g) + i1);
+    float4 y0 = v0, y1 = v1;
+    if (A != nullptr) {
+      y0 = ecsy::ldg_stream(reinterpret_cast<const float4*>(y) + i0);
+      y1 = ecsy::ldg_stream(reinterpret_cast<const float4*>(y) + i1);
+    }
+    emit(i0, v0, y0);
+    emit(i1, v1, y1);
+  }
+  if (r < rows) {
+    const int64_t i0 = r * c4 + tq;
+    const float4 v0 = ecsy::ldg_stream(reinterpret_cast<const float4*>(g) + i0);
+    float4 y0 = v0;
+    if (A != nullptr) y0 = ecsy::ldg_stream(reinterpret_cast<const float4*>(y) + i0);
+    emit(i0, v0, y0);
+  }
+}
+
+static void launch_gy_plain(const float* g, const float* y, const float* A, const float* B, const float* Cv, __nv_bfloat16* hi,
+                            __nv_bfloat16* lo, int64_t rows, int C, cudaStream_t st) {
+  const int c4 = C / 4;
+  const int bd = (256 / c4) * c4;
+  const int nty = bd / c4;
+  int64_t blocks = (rows + 2 * nty - 1) / (2 * nty);
+  const int64_t cap = (int64_t)ecsy_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_gy_to_bf16_plain<<<(int)blocks, bd, 0, st>>>(g, y, A, B, Cv, hi, lo, rows, C);
+}
+
 static bool dgrad_plain(int H, int W, int k, int stride, int pad) {
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   return stride == 1 && H - k + 1 + 2 * pad == Ho && W - k + 1 + 2 * pad == Wo;
@@ -593,8 +656,11 @@ extern "C" int ecsy_spike_conv_bwd(const float* g, const float* y, const float* 
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base); base += al256c(n * 2);
   __nv_bfloat16* lo = nullptr;
   if (splits == 2) { lo = reinterpret_cast<__nv_bfloat16*>(base); base += al256c(n * 2); }
-  k_gy_to_bf16<<<grid_for((int64_t)n / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(g, y, A, B, Cv, hi, lo, imgs, Ho,
-                                                                                         Wo, Cout, Ho, Wo, 1);
+  if (Cout <= 1024)
+    launch_gy_plain(g, y, A, B, Cv, hi, lo, imgs * Ho * Wo, Cout, st);
+  else
+    k_gy_to_bf16<<<grid_for((int64_t)n / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(g, y, A, B, Cv, hi, lo, imgs, Ho,
+                                                                                           Wo, Cout, Ho, Wo, 1);
   ECSY_LAUNCH_CHECK();
   int rc = ecsy_umma_spike_wgrad(hi, lo, spikes, dw, (int)imgs, H, W, Cin, Cout, k, stride, pad, st);
   if (rc) return rc;

@@ -406,11 +406,7 @@ __global__ void k_colsum2(const float* __restrict__ g, const float* __restrict__
   // row of x (a T-broadcast x repeats every x_rows rows) tracked incrementally: no 64-bit modulo per row
   int64_t xr = r0 + ty < r1 ? (r0 + ty) % x_rows : 0;
   const int64_t xstep = nty % x_rows;
-  for (int64_t r = r0 + ty; r < r1; r += nty) {
-    const float4 a = reinterpret_cast<const float4*>(g + r * C)[tq];
-    const float4 b = reinterpret_cast<const float4*>(x + xr * C)[tq];
-    xr += xstep;
-    if (xr >= x_rows) xr -= x_rows;
+  auto add_row = [&](const float4& a, const float4& b) {
     fg[0] += a.x; fg[1] += a.y; fg[2] += a.z; fg[3] += a.w;
     fx[0] += a.x * b.x; fx[1] += a.y * b.y; fx[2] += a.z * b.z; fx[3] += a.w * b.w;
     if (++cnt == 32) {
@@ -418,6 +414,24 @@ __global__ void k_colsum2(const float* __restrict__ g, const float* __restrict__
       for (int k = 0; k < 4; ++k) { sg[k] += fg[k]; sx[k] += fx[k]; fg[k] = 0; fx[k] = 0; }
       cnt = 0;
     }
+  };
+  int64_t r = r0 + ty;
+  for (; r + nty < r1; r += 2 * nty) {   // two rows of loads in flight per thread (same summation order as one at a time)
+    int64_t xr2 = xr + xstep;
+    if (xr2 >= x_rows) xr2 -= x_rows;
+    const float4 a0 = ecsy::ldg_stream(reinterpret_cast<const float4*>(g + r * C) + tq);
+    const float4 a1 = ecsy::ldg_stream(reinterpret_cast<const float4*>(g + (r + nty) * C) + tq);
+    const float4 b0 = reinterpret_cast<const float4*>(x + xr * C)[tq];
+    const float4 b1 = reinterpret_cast<const float4*>(x + xr2 * C)[tq];
+    xr = xr2 + xstep;
+    if (xr >= x_rows) xr -= x_rows;
+    add_row(a0, b0);
+    add_row(a1, b1);
+  }
+  if (r < r1) {
+    const float4 a = reinterpret_cast<const float4*>(g + r * C)[tq];
+    const float4 b = reinterpret_cast<const float4*>(x + xr * C)[tq];
+    add_row(a, b);
   }
   extern __shared__ double dred[];  // [nty][2][C]
 #pragma unroll
