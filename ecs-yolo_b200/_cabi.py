@@ -54,6 +54,8 @@ SIGNATURES = {
                                 _p, _z, _p]),
     "ecsy_tdbn_stats_ws_bytes": (_z, [_l, _i]),
     "ecsy_tdbn_stats": (_i, [_p, _l, _i, _p, _p, _p, _z, _p]),
+    "ecsy_tdbn_finish": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p, _i, _p]),
+    "ecsy_tdbn_bwd_coef": (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p]),
     "ecsy_affine_add": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _p, _l, _l, _i, _p]),
     "ecsy_resample": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ecsy_maxpool_bwd": (_i, [_p, _l, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),

@@ -58,12 +58,32 @@ def _acc(grads, p, g):
 # tdBN (train mode)
 # ------------------------------------------------------------------------------------------------
 def bn_train_fwd(bn_mod, y: Act):
-    """-> (scale, shift, mean, rstd); updates running statistics like _tdbn.scale_shift."""
+    """-> (scale, shift, mean, rstd); updates running statistics like _tdbn.scale_shift.  One launch after the batch
+    statistics (ecsy_tdbn_finish) instead of ~11 element-wise torch kernels on [C] vectors."""
     bn = bn_mod.bn
     mean, var = F_.bn_stats(y)
+    C = y.C
+    n = float(y.T * y.N * y.H * y.W)
+    track = bool(bn.track_running_stats) and bn.running_mean is not None
+    if (track and bn.momentum is None) or bn.weight is None:
+        return _bn_train_fwd_torch(bn_mod, y, mean, var, n)     # cumulative average: needs the step count on the host
+    scale = torch.empty(C, device=mean.device, dtype=torch.float32)
+    shift, rstd = torch.empty_like(scale), torch.empty_like(scale)
+    with torch.no_grad():
+        F_._cabi.check(F_._cabi.lib().ecsy_tdbn_finish(
+            F_._p(mean), F_._p(var), F_._p(bn.weight), F_._p(bn.bias),
+            F_._p(bn.running_mean) if track else None, F_._p(bn.running_var) if track else None,
+            F_._p(bn.num_batches_tracked) if track else None, float(bn.momentum or 0.0), n / max(n - 1.0, 1.0), float(bn.eps),
+            int(bn_mod.stat_updates) if track else 0, F_._p(scale), F_._p(shift), F_._p(rstd), C, F_._st()), "tdbn_finish")
+        if track:   # the kernel wrote the buffers through raw pointers
+            torch._C._increment_version([bn.running_mean, bn.running_var, bn.num_batches_tracked])
+    return scale, shift, mean, rstd
+
+
+def _bn_train_fwd_torch(bn_mod, y: Act, mean, var, n):
+    bn = bn_mod.bn
     with torch.no_grad():
         if bn.track_running_stats:
-            n = float(y.T * y.N * y.H * y.W)
             for _ in range(bn_mod.stat_updates):
                 bn.num_batches_tracked += 1
                 m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
@@ -77,19 +97,17 @@ def bn_train_fwd(bn_mod, y: Act):
 
 def bn_train_bwd_coeffs(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
     """Batch sums of the tdBN backward -> per-channel (A, B, C) with g_y = A*g_yn + B*y + C; accumulates the
-    gradients of the tdBN weight / bias."""
+    gradients of the tdBN weight / bias.  colsum2 + ONE launch for the [C]-vector algebra (ecsy_tdbn_bwd_coef)."""
     bn = bn_mod.bn
     C = y.C
     n = float(y.T * y.N * y.H * y.W)
     tfac = float(y.T) / float(y.Tp)
     sg, sgy = F_.colsum2(g_yn, y.data, C)
+    A = torch.empty(C, device=sg.device, dtype=torch.float32)
+    B, Cc, sgx = torch.empty_like(A), torch.empty_like(A), torch.empty_like(A)
     with torch.no_grad():
-        sgx = rstd * (sgy - mean * sg)
-        A = (bn.weight * rstd).contiguous()
-        B = (-A * rstd * sgx / n)
-        Cc = (-A * sg / n - B * mean)
-        B = (B * tfac).contiguous()
-        Cc = (Cc * tfac).contiguous()
+        F_._cabi.check(F_._cabi.lib().ecsy_tdbn_bwd_coef(F_._p(sg), F_._p(sgy), F_._p(mean), F_._p(rstd), F_._p(bn.weight), n, tfac,
+                                                         F_._p(A), F_._p(B), F_._p(Cc), F_._p(sgx), C, F_._st()), "tdbn_bwd_coef")
     _acc(grads, bn.weight, sgx)
     _acc(grads, bn.bias, sg)
     return A, B, Cc

@@ -140,6 +140,17 @@ int ecsy_real_conv_fwd(const float* x, int64_t x_imgs, const void* w_packed, con
 size_t ecsy_tdbn_stats_ws_bytes(int64_t rows, int C);
 int ecsy_tdbn_stats(const float* x, int64_t rows, int C, float* mean, float* var_biased, void* ws, size_t ws_bytes,
                     void* stream);
+/* Train-mode tdBN after ecsy_tdbn_stats, one launch (nn.BatchNorm3d inside batch_norm_2d, models/common.py:668-700):
+ * running statistics updated `updates` times with `momentum` (unbias = n / (n - 1); running_* / num_batches_tracked may be
+ * NULL), rstd = rsqrt(var + eps), scale = weight * rstd, shift = bias - mean * scale -- all device [C] vectors. */
+int ecsy_tdbn_finish(const float* mean, const float* var_biased, const float* weight, const float* bias, float* running_mean,
+                     float* running_var, long long* num_batches_tracked, float momentum, float unbias, float eps, int updates,
+                     float* scale, float* shift, float* rstd, int C, void* stream);
+/* tdBN backward coefficients, one launch: from sg = sum g and sgy = sum g*y (ecsy_colsum2) the per-channel A, B, C of
+ * g_y = A g + B y + C (B and C times tfac = T / Tp for a T-broadcast y) and the weight gradient; the bias gradient is sg. */
+int ecsy_tdbn_bwd_coef(const float* sg, const float* sgy, const float* mean, const float* rstd, const float* weight, float n,
+                       float tfac, float* A, float* B, float* Cc, float* g_weight, int C, void* stream);
+
 
 /* ---- block output `residual_function(x) + shortcut(x)` (models/common.py:1074,1216,1484) with the pending
  * tdBN affines of both operands: out = a*sa+ba (+ b*sb+bb). */
