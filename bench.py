@@ -334,6 +334,14 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
                                     "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                                     "traffic": None, "kernel_ms_per_step": lb_ms,
                                     "algorithmic_bytes_per_step": lif_elems * 12.0}
+    # tdBN batch statistics (train mode): every conv output read once (4 B per element)
+    bn_elems = flops.get("tdbn_elems", 0.0) / args.steps
+    bn_ms = per_op.get("tdbn_stats", 0.0) / args.steps
+    if bn_ms > 0 and bn_elems > 0:
+        gbs = bn_elems * 4.0 / (bn_ms * 1e-3) / 1e9
+        line["roofline_tdbn"] = {"kernel": "ecsy_tdbn_stats (k_bn_partial + k_bn_final: per-channel mean / variance)", "bound": "hbm",
+                                 "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                                 "kernel_ms_per_step": bn_ms, "algorithmic_bytes_per_step": bn_elems * 4.0}
     if comm is not None:
         line["allreduce"] = comm
     line["launches_by_op_per_step"] = {k: v / args.steps for k, v in sorted(launch_by_op.items(), key=lambda kv: -kv[1])}

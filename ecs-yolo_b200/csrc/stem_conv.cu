@@ -24,10 +24,11 @@ namespace {
 constexpr int kCout = 64;
 constexpr int kMaxKB = 4;                         // K blocks of 64 = two kernel rows each: k <= 8
 constexpr int kProdWarps = 16;                    // two groups of 8
-constexpr int kThreads = (6 + kProdWarps) * 32;   // 4 epilogue + TMA + MMA + producers
+constexpr int kEpiWarps = 8;                      // two epilogue groups of 4
+constexpr int kThreads = (kEpiWarps + 2 + kProdWarps) * 32;   // epilogue + TMA + MMA + producers
 constexpr int kTile = 128 * 128;                  // bytes of a [128 rows][64 bf16] operand block
 constexpr int kWBlk = kCout * 128;                // bytes of a [64 co][64 k] weight block
-constexpr int kStageRow = kCout + 4;              // floats per staged output row (padding: conflict-free float4 access)
+constexpr int kStageRow = 36;                     // floats per staged row of a 32-column chunk (padding: conflict-free float4 access)
 
 struct StemCtl {
   uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], w_full;
@@ -40,6 +41,7 @@ struct StemArgs {
   const float* scale;   // optional folded tdBN
   const float* shift;
   int imgs, H, W, Ho, Wo, k, stride, pad, KB, tiles_h, tiles_w, total_tiles;
+  int dbg;   // profiling only (ECSY_STEM_DBG): 1 = no global stores, 2 = no global loads
 };
 
 __global__ void __launch_bounds__(256) k_to_nhwc4_bf16(const float* __restrict__ x, uint2* __restrict__ out, int64_t pixels,
@@ -58,13 +60,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_stem_umma(const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;                                        // 2 slots x kMaxKB blocks
   uint8_t* w_smem = a_smem + 2 * kMaxKB * kTile;                 // kMaxKB blocks
-  float* o_smem = reinterpret_cast<float*>(w_smem + kMaxKB * kWBlk);   // 4 warps x 32 rows x kStageRow
-  StemCtl* ctl = reinterpret_cast<StemCtl*>(o_smem + 4 * 32 * kStageRow);
+  float* o_smem = reinterpret_cast<float*>(w_smem + kMaxKB * kWBlk);   // 8 warps x 32 rows x kStageRow
+  StemCtl* ctl = reinterpret_cast<StemCtl*>(o_smem + kEpiWarps * 32 * kStageRow);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = (int)blockIdx.x < g.total_tiles ? (g.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int tiles_hw = g.tiles_h * g.tiles_w;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kEpiWarps && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->a_full[s], kProdWarps / 2);
       mbar_init(&ctl->a_empty[s], 1);
@@ -74,18 +76,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_stem_umma(const __grid_constant
     mbar_init(&ctl->w_full, 1);
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc<128>(&ctl->tmem_base);
+  if (warp == kEpiWarps + 1) tmem_alloc<128>(&ctl->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     if (lane == 0 && my_tiles > 0) {
       mbar_arrive_expect_tx(&ctl->w_full, (uint32_t)(g.KB * kWBlk));
       for (int kb = 0; kb < g.KB; ++kb) tma_load_2d(w_smem + kb * kWBlk, &tm_w, &ctl->w_full, kb * 64, 0);
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = umma_idesc_bf16(128, kCout);
     if (my_tiles > 0) mbar_wait(&ctl->w_full, 0);
@@ -110,14 +112,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_stem_umma(const __grid_constant
       }
       __syncwarp();
     }
-  } else if (warp >= 6) {
+  } else if (warp >= kEpiWarps + 2) {
     // =============================== operand producers ===============================
-    const int pw = warp - 6, grp = pw >> 3;
+    const int pw = warp - (kEpiWarps + 2), grp = pw >> 3;
     const int t = (pw & 7) * 32 + lane;
     const int row = t & 127, part = t >> 7;
     const int h_l = row >> 6, w_l = row & 63;
     const uint32_t sw = (uint32_t)row & 7u;
     uint8_t* slot_base = a_smem + grp * kMaxKB * kTile + (uint32_t)row * 128u;
+    uint32_t coff[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) coff[m] = (((uint32_t)(part * 4 + m)) ^ sw) << 4;
     for (int it = grp; it < my_tiles; it += 2) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int img = tile / tiles_hw;
@@ -126,27 +131,59 @@ __global__ void __launch_bounds__(kThreads, 1) k_stem_umma(const __grid_constant
       const int ho = th * 2 + h_l, wo = tw * 64 + w_l;
       const bool valid = ho < g.Ho && wo < g.Wo;
       const int hi0 = ho * g.stride - g.pad, wi0 = wo * g.stride - g.pad;
-      uint2 v[kMaxKB][8];
+      // interior pixels (all 8 columns of the kernel row inside the image, even image width): the 64 bytes of a row are
+      // fetched with 16-byte loads where they are aligned -- 4 or 5 load instructions and one address per row instead of
+      // 8 predicated 8-byte loads
+      const bool w_in = valid && wi0 >= 0 && wi0 + 8 <= g.W && (g.W & 1) == 0;
+      const bool odd = (wi0 & 1) != 0;
+      const uint2* img_base = g.xq + (int64_t)img * g.H * g.W;
+      // two K blocks (= four kernel rows per row pair of threads) at a time: 32 registers of loads in flight
 #pragma unroll
-      for (int kb = 0; kb < kMaxKB; ++kb) {
-        const int ky = 2 * kb + part, hi = hi0 + ky;
-        const bool rok = valid && kb < g.KB && ky < g.k && (unsigned)hi < (unsigned)g.H;
-        const uint2* src = g.xq + ((int64_t)img * g.H + (rok ? hi : 0)) * g.W;
+      for (int half = 0; half < kMaxKB / 2; ++half) {
+        uint2 v[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int wi = wi0 + j;
-          v[kb][j] = (rok && (unsigned)wi < (unsigned)g.W) ? __ldg(src + wi) : make_uint2(0u, 0u);
+        for (int q = 0; q < 2; ++q) {
+          const int kb = 2 * half + q;
+          const int ky = 2 * kb + part, hi = hi0 + ky;
+          const bool rok = valid && kb < g.KB && ky < g.k && (unsigned)hi < (unsigned)g.H && !(g.dbg & 2);
+          const uint2* src = img_base + (rok ? hi : 0) * g.W;
+          if (rok && w_in) {
+            const uint2* p = src + wi0;
+            if (odd) {
+              v[q][0] = __ldg(p);
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(p + 1));
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 3));
+              const uint4 c = __ldg(reinterpret_cast<const uint4*>(p + 5));
+              v[q][7] = __ldg(p + 7);
+              v[q][1] = make_uint2(a.x, a.y); v[q][2] = make_uint2(a.z, a.w);
+              v[q][3] = make_uint2(b.x, b.y); v[q][4] = make_uint2(b.z, b.w);
+              v[q][5] = make_uint2(c.x, c.y); v[q][6] = make_uint2(c.z, c.w);
+            } else {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(p + 2 * m));
+                v[q][2 * m] = make_uint2(a.x, a.y);
+                v[q][2 * m + 1] = make_uint2(a.z, a.w);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int wi = wi0 + j;
+              v[q][j] = (rok && (unsigned)wi < (unsigned)g.W) ? __ldg(src + wi) : make_uint2(0u, 0u);
+            }
+          }
         }
-      }
-      mbar_wait(&ctl->a_empty[grp], ((it >> 1) & 1) ^ 1);
+        if (half == 0) mbar_wait(&ctl->a_empty[grp], ((it >> 1) & 1) ^ 1);
 #pragma unroll
-      for (int kb = 0; kb < kMaxKB; ++kb) {
-        if (kb < g.KB) {
-          uint8_t* dst = slot_base + kb * kTile;
+        for (int q = 0; q < 2; ++q) {
+          const int kb = 2 * half + q;
+          if (kb < g.KB) {
+            uint8_t* dst = slot_base + kb * kTile;
 #pragma unroll
-          for (int m = 0; m < 4; ++m)   // pixels 2m, 2m+1 of this kernel row = K entries part*32 + 8m .. +7
-            *reinterpret_cast<uint4*>(dst + ((((uint32_t)(part * 4 + m)) ^ sw) << 4)) =
-                make_uint4(v[kb][2 * m].x, v[kb][2 * m].y, v[kb][2 * m + 1].x, v[kb][2 * m + 1].y);
+            for (int m = 0; m < 4; ++m)   // pixels 2m, 2m+1 of this kernel row = K entries part*32 + 8m .. +7
+              *reinterpret_cast<uint4*>(dst + coff[m]) = make_uint4(v[q][2 * m].x, v[q][2 * m].y, v[q][2 * m + 1].x, v[q][2 * m + 1].y);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -154,54 +191,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_stem_umma(const __grid_constant
       if (lane == 0) mbar_arrive(&ctl->a_full[grp]);
     }
   } else {
-    // =============================== epilogue ===============================
+    // =============================== epilogue: two groups of 4 warps, group ge drains accumulator buffer ge ===============
+    const int ge = warp >> 2, q = warp & 3;
     float* stage = o_smem + warp * 32 * kStageRow;
-    const int h_l = warp >> 1, w_l0 = (warp & 1) * 32;   // the warp's 32 rows are 32 consecutive pixels of one output row
-    for (int it = 0; it < my_tiles; ++it) {
-      const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+    const int h_l = q >> 1, w_l0 = (q & 1) * 32;   // the warp's 32 rows are 32 consecutive pixels of one output row
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    // the folded tdBN is applied in the write-out phase, where a lane owns FIXED channels: 4 registers of scale / shift per
+    // 32-column chunk instead of 16 loads per chunk in the dependent chain of the staging phase
+    float4 sc[2], sf[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      sc[c] = make_float4(1.f, 1.f, 1.f, 1.f);
+      sf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g.scale != nullptr) {
+        sc[c] = __ldg(reinterpret_cast<const float4*>(g.scale + c * 32 + c4));
+        sf[c] = __ldg(reinterpret_cast<const float4*>(g.shift + c * 32 + c4));
+      }
+    }
+    for (int it = ge; it < my_tiles; it += 2) {
+      const uint32_t ph = (it >> 1) & 1;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int img = tile / tiles_hw;
       const int rem = tile - img * tiles_hw;
       const int th = rem / g.tiles_w, tw = rem - th * g.tiles_w;
-      mbar_wait(&ctl->t_full[slot], ph);
+      const int ho = th * 2 + h_l, wo0 = tw * 64 + w_l0;
+      float* dst = g.out + (((int64_t)img * g.Ho + ho) * g.Wo + wo0) * kCout;
+      const bool row_ok = ho < g.Ho && !(g.dbg & 1);
+      mbar_wait(&ctl->t_full[ge], ph);
       tc_fence_after_sync();
-#pragma unroll
-      for (int c0 = 0; c0 < kCout; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * kCout + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (g.scale != nullptr) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(g.scale + c0 + j));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(g.shift + c0 + j));
-            o.x = add_rn(mul_rn(o.x, s.x), b.x); o.y = add_rn(mul_rn(o.y, s.y), b.y);
-            o.z = add_rn(mul_rn(o.z, s.z), b.z); o.w = add_rn(mul_rn(o.w, s.w), b.w);
-          }
-          *reinterpret_cast<float4*>(stage + lane * kStageRow + c0 + j) = o;
-        }
-      }
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * kCout, v0);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * kCout + 32, v1);
+      tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->t_empty[slot]);
-      const int ho = th * 2 + h_l, wo0 = tw * 64 + w_l0;
-      if (ho < g.Ho) {
-        float* dst = g.out + (((int64_t)img * g.Ho + ho) * g.Wo + wo0) * kCout;
+      if (lane == 0) mbar_arrive(&ctl->t_empty[ge]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = i * 2 + (lane >> 4), c4 = lane & 15;
-          if (wo0 + r < g.Wo)
-            *reinterpret_cast<float4*>(dst + r * kCout + c4 * 4) = *reinterpret_cast<const float4*>(stage + r * kStageRow + c4 * 4);
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t* v = c == 0 ? v0 : v1;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(stage + lane * kStageRow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + sub;
+            float4 o = *reinterpret_cast<const float4*>(stage + r * kStageRow + c4);
+            if (g.scale != nullptr) {
+              o.x = add_rn(mul_rn(o.x, sc[c].x), sf[c].x); o.y = add_rn(mul_rn(o.y, sc[c].y), sf[c].y);
+              o.z = add_rn(mul_rn(o.z, sc[c].z), sf[c].z); o.w = add_rn(mul_rn(o.w, sc[c].w), sf[c].w);
+            }
+            if (wo0 + r < g.Wo) *reinterpret_cast<float4*>(dst + r * kCout + c * 32 + c4) = o;
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kEpiWarps + 1) {
     tc_fence_after_sync();
     tmem_dealloc<128>(tmem_base);
   }
@@ -248,10 +298,12 @@ extern "C" int ecsy_stem_conv(const float* x, int64_t imgs, int H, int W, int Ci
   const int64_t total = imgs * g.tiles_h * g.tiles_w;
   ECSY_CHECK_ARG(total < (1LL << 31), "stem_conv: too many tiles");
   g.total_tiles = (int)total;
+  static const int dbg = getenv("ECSY_STEM_DBG") ? atoi(getenv("ECSY_STEM_DBG")) : 0;
+  g.dbg = dbg;
   CUtensorMap tw;
   int rc = ecsy_tensor_map_bf16(w_stem, (uint64_t)kCout, (uint64_t)g.KB * 64, (uint32_t)kCout, &tw);
   if (rc) return rc;
-  const int smem = 1024 + 2 * kMaxKB * kTile + kMaxKB * kWBlk + 4 * 32 * kStageRow * (int)sizeof(float) + (int)sizeof(StemCtl) + 64;
+  const int smem = 1024 + 2 * kMaxKB * kTile + kMaxKB * kWBlk + kEpiWarps * 32 * kStageRow * (int)sizeof(float) + (int)sizeof(StemCtl) + 64;
   static bool attr = false;
   if (!attr) {
     ECSY_CUDA(cudaFuncSetAttribute(k_stem_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
