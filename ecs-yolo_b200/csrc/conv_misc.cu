@@ -616,6 +616,25 @@ static void launch_gy_plain(const float* g, const float* y, const float* A, cons
   k_gy_to_bf16_plain<<<(int)blocks, bd, 0, st>>>(g, y, A, B, Cv, hi, lo, rows, C);
 }
 
+// Zero-inserted copy of the bf16 gradient planes for the dgrad of a strided conv: dst [imgs][Hu][Wu][C] (already zeroed) gets
+// src [imgs][Ho][Wo][C] at (ho * s, wo * s).  The planes were formed once by k_gy_to_bf16_plain (tdBN backward folded in): the
+// strided case used to recompute A g + B y + C per UP-SAMPLED element with three 64-bit divisions each (0.9 ms per launch).
+__global__ void __launch_bounds__(256)
+k_bf16_scatter_up(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t items, int Ho, int Wo, int Hu, int Wu, int c8,
+                  int s) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = items < (int64_t(1) << 32);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += stride) {
+    const int q = static_cast<int>(ecsy::mod_u(i, (uint32_t)c8, small));
+    int64_t p = ecsy::div_u(i, (uint32_t)c8, small);
+    const int wo = static_cast<int>(ecsy::mod_u(p, (uint32_t)Wo, small));
+    p = ecsy::div_u(p, (uint32_t)Wo, small);
+    const int ho = static_cast<int>(ecsy::mod_u(p, (uint32_t)Ho, small));
+    const int64_t img = ecsy::div_u(p, (uint32_t)Ho, small);
+    dst[((img * Hu + (int64_t)ho * s) * Wu + (int64_t)wo * s) * c8 + q] = src[i];
+  }
+}
+
 static bool dgrad_plain(int H, int W, int k, int stride, int pad) {
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   return stride == 1 && H - k + 1 + 2 * pad == Ho && W - k + 1 + 2 * pad == Wo;
@@ -669,9 +688,25 @@ extern "C" int ecsy_spike_conv_bwd(const float* g, const float* y, const float* 
     const size_t nu = static_cast<size_t>(imgs) * Hu * Wu * Cout;
     dhi = reinterpret_cast<__nv_bfloat16*>(base); base += al256c(nu * 2);
     dlo = splits == 2 ? reinterpret_cast<__nv_bfloat16*>(base) : nullptr;
-    k_gy_to_bf16<<<grid_for((int64_t)nu / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(g, y, A, B, Cv, dhi, dlo, imgs,
-                                                                                            Ho, Wo, Cout, Hu, Wu, stride);
-    ECSY_LAUNCH_CHECK();
+    if (Cout <= 1024) {
+      // zero planes + scatter of the values formed above (2 B per element read, full 16-byte rows written)
+      const int64_t items = (int64_t)(n / 8);
+      const int sgrid = grid_for(items, kThreads, ecsy_num_sms() * 8);
+      ECSY_CUDA(cudaMemsetAsync(dhi, 0, nu * 2, st));
+      k_bf16_scatter_up<<<sgrid, kThreads, 0, st>>>(reinterpret_cast<const uint4*>(hi), reinterpret_cast<uint4*>(dhi), items, Ho,
+                                                    Wo, Hu, Wu, Cout / 8, stride);
+      ECSY_LAUNCH_CHECK();
+      if (dlo != nullptr) {
+        ECSY_CUDA(cudaMemsetAsync(dlo, 0, nu * 2, st));
+        k_bf16_scatter_up<<<sgrid, kThreads, 0, st>>>(reinterpret_cast<const uint4*>(lo), reinterpret_cast<uint4*>(dlo), items,
+                                                      Ho, Wo, Hu, Wu, Cout / 8, stride);
+        ECSY_LAUNCH_CHECK();
+      }
+    } else {
+      k_gy_to_bf16<<<grid_for((int64_t)nu / 4, kThreads, ecsy_num_sms() * 8), kThreads, 0, st>>>(g, y, A, B, Cv, dhi, dlo, imgs,
+                                                                                              Ho, Wo, Cout, Hu, Wu, stride);
+      ECSY_LAUNCH_CHECK();
+    }
   }
   return ecsy_umma_conv_bf16(dhi, dlo, wT_packed, splits, gx, nullptr, nullptr, nullptr, 0, (int)imgs, Hu, Wu, Cout, Cin, k,
                              k - 1 - pad, st);
