@@ -2039,6 +2039,218 @@ k_umma_wgrad(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Weight gradient of the spike convolution, operand roles swapped (default):  D[(blk, ci)][co], i.e. the M side of the MMA is
+// a PAIR of expanded (tap, slab) spike blocks (128 = 2 x 64 input channels: always a full tile) and the N side is the
+// gy tile (NB = min(Cout, 128) output channels).  k_umma_wgrad read the whole gy tile (32 KB, half of it zero fill for
+// Cout = 64) from shared memory once per 64-channel spike block: 64 KB of shared-memory traffic per 256 MMA cycles, twice
+// what the SM delivers.  Here the gy tile is read once per PAIR of blocks and sized to the real Cout: 40 KB (Cout = 64) /
+// 48 KB (Cout >= 128) per block.  The epilogue lane is an input channel, so consecutive lanes add to consecutive dW addresses.
+// The (tap, slab) blocks of a CTA are padded to an even count with an all-zero block.
+// ---------------------------------------------------------------------------------------------
+struct WgtArgs {
+  int m_tiles;      // pixel tiles
+  int splits_m;     // CTAs along the pixel tiles
+  int bpc;          // (tap, slab) blocks per CTA, even
+  int nblk;         // real blocks (kh * kw * nslab); blocks >= nblk are zero padding
+  int Cout, K;      // dW is [Cout][K]
+  float* dw;
+};
+
+template <int G_SPLIT, int NB>
+__global__ void __launch_bounds__(kSpikeThreads, 1)
+k_umma_wgrad_t(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_g1, const WgtArgs g,
+               const SpikeGeom sg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kCoBlk = NB / 64;
+  constexpr int kABuf = G_SPLIT * kCoBlk * kATileBytes;   // planes x 64-co blocks x (128 pixels x 128 B)
+  uint8_t* a_smem = smem;                                  // 2 buffers of gy
+  uint8_t* b_smem = smem + 2 * kABuf;                      // kWgStages x 16 KB of expanded spikes
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(b_smem + kWgStages * kATileBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * NB;
+  const int blk0 = blockIdx.z * g.bpc;
+  const int per = (g.m_tiles + g.splits_m - 1) / g.splits_m;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(t_begin + per, g.m_tiles);
+  const int ntiles = max(t_end - t_begin, 0);
+  constexpr int kWpg = kExpWarps / kWgStages;  // expander warps per stage group
+
+  if (warp == 4 && lane == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->a_full[b], 1); mbar_init(&ctl->a_empty[b], 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&ctl->b_full[s], kWpg); mbar_init(&ctl->b_empty[s], 1); }
+    mbar_init(&ctl->done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<512>(&ctl->tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int tiles_hw = sg.tiles_h * sg.tiles_w;
+
+  if (warp == 4) {
+    // ---- TMA: gy tiles (kCoBlk 64-co blocks per plane), one per pixel tile ----
+    for (int i = 0; i < ntiles; ++i) {
+      const uint32_t ab = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&ctl->a_empty[ab], ph ^ 1);
+      if (lane == 0) {
+        const int m_tile = t_begin + i;
+        const int tn = m_tile / tiles_hw;
+        const int rem = m_tile - tn * tiles_hw;
+        const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+        uint8_t* dst = a_smem + ab * kABuf;
+        mbar_arrive_expect_tx(&ctl->a_full[ab], (uint32_t)kABuf);
+#pragma unroll
+        for (int sp = 0; sp < G_SPLIT; ++sp) {
+          const CUtensorMap* tm = sp == 0 ? &tm_g0 : &tm_g1;
+#pragma unroll
+          for (int cb = 0; cb < kCoBlk; ++cb)
+            tma_load_4d(dst + (sp * kCoBlk + cb) * kATileBytes, tm, &ctl->a_full[ab], co0 + cb * 64, tw * sg.tw_b,
+                        th * sg.th_b, tn * sg.tn_b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer: one 128 x NB MMA set per PAIR of spike blocks (stages 2p, 2p+1 are adjacent in shared memory) ----
+    const uint32_t idesc = umma_idesc_bf16_mn(128, NB);
+    uint32_t c = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      const uint32_t ab = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&ctl->a_full[ab], ph);
+      for (int b = 0; b < g.bpc; b += 2, c += 2) {
+        const uint32_t stage = c % kWgStages, sph = (c / kWgStages) & 1;
+        mbar_wait(&ctl->b_full[stage], sph);
+        mbar_wait(&ctl->b_full[stage + 1], sph);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(a_smem + ab * kABuf);
+          const uint32_t b_addr = smem_u32(b_smem + stage * kATileBytes);
+          uint32_t acc = i > 0 ? 1u : 0u;
+#pragma unroll
+          for (int sp = 0; sp < G_SPLIT; ++sp) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // 128 pixels = 8 K steps of 16 rows (2048 bytes each)
+              const uint64_t dm = umma_desc_sw128_mn(b_addr + k * 2048, kATileBytes);                      // spikes: M
+              const uint64_t dn = umma_desc_sw128_mn(a_addr + sp * kCoBlk * kATileBytes + k * 2048, kATileBytes);   // gy: N
+              umma_f16(tmem_base + (b >> 1) * NB, dm, dn, idesc, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&ctl->b_empty[stage]);
+          umma_commit(&ctl->b_empty[stage + 1]);
+          if (b + 2 >= g.bpc) {
+            umma_commit(&ctl->a_empty[ab]);
+            if (i == ntiles - 1) umma_commit(&ctl->done);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 6) {
+    // ---- spike expanders (same tile the forward conv builds; stage group = stage) ----
+    const int ew = warp - 6;
+    const int grp = ew / kWpg, sub = ew - grp * kWpg;
+    constexpr int rows_per_warp = 128 / kWpg;
+    constexpr int nrow = rows_per_warp >> 5;
+    int n_l[nrow], h_l[nrow], w_l[nrow];
+    uint32_t row_off[nrow];
+#pragma unroll
+    for (int i = 0; i < nrow; ++i) {
+      const int r = sub * rows_per_warp + i * 32 + lane;
+      w_l[i] = r & (sg.tw_b - 1);
+      h_l[i] = (r >> sg.tw_sh) & (sg.th_b - 1);
+      n_l[i] = r >> (sg.tw_sh + sg.th_sh);
+      row_off[i] = (uint32_t)r * 128u;
+    }
+    const uint32_t sw = (uint32_t)(lane & 7);
+    uint8_t* tile_b = b_smem + (size_t)grp * kATileBytes;
+    const uint32_t c_end = (uint32_t)ntiles * (uint32_t)g.bpc;
+
+    auto load_rows = [&](uint32_t c, uint2 (&wd)[nrow]) {
+      const uint32_t ti = c / (uint32_t)g.bpc;
+      const int blk = blk0 + (int)(c - ti * g.bpc);
+      const int m_tile = t_begin + (int)ti;
+      const int tn = m_tile / tiles_hw;
+      const int rem = m_tile - tn * tiles_hw;
+      const int th = rem / sg.tiles_w, tw = rem - th * sg.tiles_w;
+      const int tap = blk / sg.nslab, slab = blk - tap * sg.nslab;
+      const int ky = tap / sg.kw, kx = tap - ky * sg.kw;
+      const int img0 = tn * sg.tn_b;
+      const int hi0 = th * sg.th_b * sg.stride - sg.pad + ky;
+      const int wi0 = tw * sg.tw_b * sg.stride - sg.pad + kx;
+#pragma unroll
+      for (int i = 0; i < nrow; ++i) {
+        wd[i] = make_uint2(0u, 0u);
+        const int img = img0 + n_l[i], hi = hi0 + h_l[i] * sg.stride, wi = wi0 + w_l[i] * sg.stride;
+        if (blk < g.nblk && img < sg.imgs && hi >= 0 && hi < sg.H && wi >= 0 && wi < sg.W)
+          wd[i] = __ldg(reinterpret_cast<const uint2*>(sg.bits + (((int64_t)img * sg.H + hi) * sg.W + wi) * sg.Cw + slab * 2));
+      }
+    };
+
+    uint32_t c = (uint32_t)grp;
+    uint2 cur[nrow];
+    if (c < c_end) load_rows(c, cur);
+    while (c < c_end) {
+      uint2 nxt[nrow];
+      if (c + kWgStages < c_end) load_rows(c + kWgStages, nxt);
+      mbar_wait(&ctl->b_empty[grp], ((c / kWgStages) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < nrow; ++i) {
+        uint8_t* row = tile_b + row_off[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t byte = ((j < 4 ? cur[i].x : cur[i].y) >> (8 * (j & 3))) & 0xFFu;
+          uint4 o;
+          o.x = bits2_to_bf16x2(byte);
+          o.y = bits2_to_bf16x2(byte >> 2);
+          o.z = bits2_to_bf16x2(byte >> 4);
+          o.w = bits2_to_bf16x2(byte >> 6);
+          *reinterpret_cast<uint4*>(row + (((uint32_t)j ^ sw) << 4)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->b_full[grp]);
+#pragma unroll
+      for (int i = 0; i < nrow; ++i) cur[i] = nxt[i];
+      c += kWgStages;
+    }
+  } else {
+    // ---- epilogue: TMEM lane = (block of the pair, input channel), column = output channel -> red.global into dW ----
+    if (ntiles > 0) {
+      mbar_wait(&ctl->done, 0);
+      tc_fence_after_sync();
+      const int half = warp >> 1;                         // lanes 0-63: first block of the pair, 64-127: second
+      const int ci = (warp & 1) * 32 + lane;
+      for (int p = 0; p < g.bpc / 2; ++p) {
+        const int blk = blk0 + 2 * p + half;
+        const int64_t kbase = (int64_t)blk * 64 + ci;     // blk = tap * nslab + slab: K index (tap * nslab + slab) * 64 + ci
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + p * NB + c0, v);
+          tmem_ld_wait();
+          if (blk < g.nblk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int co = co0 + c0 + j;
+              if (co < g.Cout) atomicAdd(g.dw + (int64_t)co * g.K + kbase, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -2619,6 +2831,49 @@ int ecsy_umma_spike_wgrad(const void* gy_hi, const void* gy_lo, const uint32_t* 
   sg.tn_sh = ilog2(sg.tn_b); sg.th_sh = ilog2(sg.th_b); sg.tw_sh = ilog2(sg.tw_b);
   sg.tiles_h = (Ho + sg.th_b - 1) / sg.th_b; sg.tiles_w = (Wo + sg.tw_b - 1) / sg.tw_b;
   sg.nslab = Cin / 64;
+  const int gsplit_t = gy_lo ? 2 : 1;
+  static const bool wgrad_old = getenv("ECSY_WGRAD_V") != nullptr && getenv("ECSY_WGRAD_V")[0] == '0';
+  if (!wgrad_old) {
+    // role-swapped kernel: pairs of spike blocks on the M side, gy on the N side
+    const int NB = Cout >= 128 ? 128 : 64;
+    const int nblk = k * k * sg.nslab, nblk_even = (nblk + 1) & ~1;
+    const int max_bpc = NB == 128 ? 8 : 16;               // 512 TMEM columns = (bpc / 2) * NB
+    int bpc = max_bpc;
+    while (nblk_even % bpc != 0) bpc -= 2;
+    WgtArgs g{};
+    g.m_tiles = ((imgs + sg.tn_b - 1) / sg.tn_b) * sg.tiles_h * sg.tiles_w;
+    g.bpc = bpc; g.nblk = nblk; g.Cout = Cout; g.K = k * k * Cin; g.dw = dw;
+    const int co_tiles = (Cout + NB - 1) / NB, groups = nblk_even / bpc;
+    int sm = (2 * ecsy_num_sms()) / (co_tiles * groups);
+    if (sm < 1) sm = 1;
+    if (sm > g.m_tiles) sm = g.m_tiles;
+    g.splits_m = sm;
+    CUtensorMap t0, t1{};
+    int rc = ecsy_tensor_map_bf16_nhwc(gy_hi, imgs, Ho, Wo, Cout, sg.tn_b, sg.th_b, sg.tw_b, &t0);
+    if (rc) return rc;
+    if (gy_lo) {
+      rc = ecsy_tensor_map_bf16_nhwc(gy_lo, imgs, Ho, Wo, Cout, sg.tn_b, sg.th_b, sg.tw_b, &t1);
+      if (rc) return rc;
+    }
+    const int smem = 1024 + 2 * gsplit_t * (NB / 64) * kATileBytes + kWgStages * kATileBytes + (int)sizeof(WgCtl) + 64;
+    dim3 grid((unsigned)sm, co_tiles, groups);
+#define ECSY_WGT_LAUNCH(GS, NBV)                                                                                       \
+    {                                                                                                                  \
+      static bool done = false;                                                                                        \
+      if (!done) {                                                                                                     \
+        ECSY_CUDA(cudaFuncSetAttribute(k_umma_wgrad_t<GS, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); \
+        done = true;                                                                                                   \
+      }                                                                                                                \
+      k_umma_wgrad_t<GS, NBV><<<grid, kSpikeThreads, smem, st>>>(t0, t1, g, sg);                                       \
+    }
+    if (gsplit_t == 1 && NB == 64) ECSY_WGT_LAUNCH(1, 64)
+    else if (gsplit_t == 1) ECSY_WGT_LAUNCH(1, 128)
+    else if (NB == 64) ECSY_WGT_LAUNCH(2, 64)
+    else ECSY_WGT_LAUNCH(2, 128)
+#undef ECSY_WGT_LAUNCH
+    ECSY_LAUNCH_CHECK();
+    return ECSY_OK;
+  }
   WgArgs g{};
   g.m_tiles = ((imgs + sg.tn_b - 1) / sg.tn_b) * sg.tiles_h * sg.tiles_w;
   const int nblk = k * k * sg.nslab;
