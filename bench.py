@@ -264,7 +264,9 @@ def train_bench(args, E, F, model, x, x_host, rank, world, local, dist, workload
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         gbytes = sum(p.numel() * 4 for p in model.parameters() if p.requires_grad)
         try:
-            bucket_sizes = [int(v) for v in str(net._get_ddp_logging_data().get("bucket_sizes", "")).split(",") if v.strip()]
+            ld = net._get_ddp_logging_data()   # after the first iteration DDP re-buckets in gradient-ready order
+            raw = ld.get("rebuilt_bucket_sizes") or ld.get("bucket_sizes", "")
+            bucket_sizes = [int(v) for v in str(raw).split(",") if v.strip()]
         except Exception:
             bucket_sizes = []
         comm = {"collective": "NCCL all-reduce (sum) of the fp32 gradients through DistributedDataParallel, overlapped with "
