@@ -149,15 +149,18 @@ __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __re
 // of the per-block partials are summed in parallel (coalesced 128-byte rows, independent loads) and combined in a fixed
 // order -- deterministic, and ~8x shorter than one thread walking all ~600 partials of its output.
 __global__ void __launch_bounds__(256)
-k_lif_bwd_reduce_final(const float* __restrict__ part, int nblocks, float* __restrict__ g_pw_b,
+k_lif_bwd_reduce_final(const float* __restrict__ part, int nblocks0, int nblocks, float* __restrict__ g_pw_b,
                        float* __restrict__ g_dw_b, float* __restrict__ g_dw_w, int C, float alpha) {
+  // row 0 (sum ge) holds nblocks0 partials (grid of k_lif_bwd_pre), rows 1..10 nblocks (grid of k_lif_bwd_post)
   __shared__ double sm[8][32];
   const int ib = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ib;
   const int n_out = 11 * C;
   double t = 0;
-  if (i < n_out)
-    for (int b = sl; b < nblocks; b += 8) t += part[(size_t)b * n_out + i];
+  if (i < n_out) {
+    const int nb = i < C ? nblocks0 : nblocks;
+    for (int b = sl; b < nb; b += 8) t += part[(size_t)b * n_out + i];
+  }
   sm[sl][ib] = t;
   __syncthreads();
   if (sl != 0 || i >= n_out) return;
@@ -219,21 +222,28 @@ k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*nu
     }
     if (g1 != nullptr) {
       float4 g[9];
-      uint32_t okm = 0;
+      if ((unsigned)(h - 1) < (unsigned)(H - 2) && (unsigned)(w - 1) < (unsigned)(W - 2)) {
+        // interior pixel (97 % at 160 x 160): nine loads at fixed offsets from the running pointer, no tests
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int hh = h - (ky - 1), ww = w - (kx - 1);   // s[q] feeds out[q - off(tap)]
-          const bool ok = (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
-          const int off = ok ? (1 - ky) * WC + (1 - kx) * C : 0;   // 32-bit offset from the running pointer
-          g[ky * 3 + kx] = *reinterpret_cast<const float4*>(g1p + off);
-          okm |= (ok ? 1u : 0u) << (ky * 3 + kx);
+          for (int kx = 0; kx < 3; ++kx)
+            g[ky * 3 + kx] = *reinterpret_cast<const float4*>(g1p + ((1 - ky) * WC + (1 - kx) * C));   // s[q] feeds out[q - off(tap)]
+      } else {
+        uint32_t okm = 0;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int hh = h - (ky - 1), ww = w - (kx - 1);
+            const bool ok = (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+            const int off = ok ? (1 - ky) * WC + (1 - kx) * C : 0;   // 32-bit offset from the running pointer
+            g[ky * 3 + kx] = *reinterpret_cast<const float4*>(g1p + off);
+            okm |= (ok ? 1u : 0u) << (ky * 3 + kx);
+          }
         }
-      }
-      if (okm != 0x1FFu) {   // image border (rare): the taps outside contribute nothing
 #pragma unroll
-        for (int tp = 0; tp < 9; ++tp)
+        for (int tp = 0; tp < 9; ++tp)   // image border: the taps outside contribute nothing
           if (!((okm >> tp) & 1u)) g[tp] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -501,6 +511,10 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
   // run on the same grid and leave part[block][11][C]; the old separate pass (k_lif_bwd_reduce: 16 of 142 ms of a
   // resnet18 step, profiles/r02_launch_summary_train_r18_b32.txt) re-read ge, G1 and nine spike words per element
   const int egrid = grid_for(n4, rbd, ecsy_num_sms() * kPartBlocksPerSm);
+  // k_lif_bwd_post<2> is resident at two blocks per SM (128 registers): one wave of 2 x SMs blocks -- no tail, and a third of
+  // the per-block partials for k_lif_bwd_reduce_final to read
+  static const int post_bps = getenv("ECSY_POST_BPS") ? atoi(getenv("ECSY_POST_BPS")) : 2;
+  const int pgrid = grid_for(n4, rbd, ecsy_num_sms() * post_bps);
 
   for (int t = T - 1; t >= 0; --t) {
     const bool spread = t <= T - 2;
@@ -523,7 +537,7 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       k_lif_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, spikes + t * words, part,
                                                                                        (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
-      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
     const size_t psm = (spread && fused) ? (size_t)(rbd / c4) * 10 * C * sizeof(float) : 0;
@@ -531,13 +545,13 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
 #define ECSY_POST_ARGS gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc, spikes + t * words, \
         has_next ? gx + (size_t)(t + 1) * mc : nullptr, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, thresh, lens, \
         decay, alpha, pp
-    if (variant == 3) k_lif_bwd_post<3><<<egrid, rbd, psm, st>>>(ECSY_POST_ARGS);
-    else if (variant == 4) k_lif_bwd_post<4><<<egrid, rbd, psm, st>>>(ECSY_POST_ARGS);
-    else k_lif_bwd_post<2><<<egrid, rbd, psm, st>>>(ECSY_POST_ARGS);
+    if (variant == 3) k_lif_bwd_post<3><<<pgrid, rbd, psm, st>>>(ECSY_POST_ARGS);
+    else if (variant == 4) k_lif_bwd_post<4><<<pgrid, rbd, psm, st>>>(ECSY_POST_ARGS);
+    else k_lif_bwd_post<2><<<pgrid, rbd, psm, st>>>(ECSY_POST_ARGS);
 #undef ECSY_POST_ARGS
     ECSY_LAUNCH_CHECK();
     if (spread && fused) {
-      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, egrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, egrid, pgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
   }
@@ -621,7 +635,7 @@ extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const floa
       const int rgrid = grid_for(M, 64, ecsy_num_sms() * 4);
       k_silu_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, o_t, part, (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
-      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
     k_silu_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
