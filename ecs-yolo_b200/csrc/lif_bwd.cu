@@ -149,17 +149,22 @@ __global__ void k_lif_bwd_reduce(const float* __restrict__ ge, const float* __re
 // of the per-block partials are summed in parallel (coalesced 128-byte rows, independent loads) and combined in a fixed
 // order -- deterministic, and ~8x shorter than one thread walking all ~600 partials of its output.
 __global__ void __launch_bounds__(256)
-k_lif_bwd_reduce_final(const float* __restrict__ part, int nblocks0, int nblocks, float* __restrict__ g_pw_b,
-                       float* __restrict__ g_dw_b, float* __restrict__ g_dw_w, int C, float alpha) {
-  // row 0 (sum ge) holds nblocks0 partials (grid of k_lif_bwd_pre), rows 1..10 nblocks (grid of k_lif_bwd_post)
+k_lif_bwd_reduce_final(const float* __restrict__ part, const float* __restrict__ part0, int nblocks0, int nblocks,
+                       float* __restrict__ g_pw_b, float* __restrict__ g_dw_b, float* __restrict__ g_dw_w, int C, float alpha) {
+  // row 0 (sum ge) holds nblocks0 partials -- in part0 [nblocks0][C] when the ge came out of k_lif_bwd_post(t+1), else in
+  // row 0 of part (k_lif_bwd_pre) --, rows 1..10 nblocks (grid of k_lif_bwd_post)
   __shared__ double sm[8][32];
   const int ib = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ib;
   const int n_out = 11 * C;
   double t = 0;
   if (i < n_out) {
-    const int nb = i < C ? nblocks0 : nblocks;
-    for (int b = sl; b < nb; b += 8) t += part[(size_t)b * n_out + i];
+    if (i < C && part0 != nullptr) {
+      for (int b = sl; b < nblocks0; b += 8) t += part0[(size_t)b * C + i];
+    } else {
+      const int nb = i < C ? nblocks0 : nblocks;
+      for (int b = sl; b < nb; b += 8) t += part[(size_t)b * n_out + i];
+    }
   }
   sm[sl][ib] = t;
   __syncthreads();
@@ -173,6 +178,19 @@ k_lif_bwd_reduce_final(const float* __restrict__ part, int nblocks0, int nblocks
   else g_dw_w[(a - 2) * C + c] += v;
 }
 
+// k_lif_bwd_post(t) can also emit the ECS-trace gradient of the step BEFORE it (what k_lif_bwd_pre(t-1) computed from the
+// gx[t] this kernel has just formed): ge_{t-1} = gx_t * beta * (1 - tanh(e_{t-1})^2) + kappa * ge_t, its bf16 GEMM operand and
+// its per-channel sum -- gx[t] is not re-read, one launch less per timestep.
+struct PostEmit {
+  const float* ecs_prev;   // e_{t-1}; NULL = do not emit
+  float* ge;               // in: ge_t (if ge_has_next), out: ge_{t-1}
+  __nv_bfloat16* ge_hi;
+  __nv_bfloat16* ge_lo;    // parity precision: residual plane
+  float* part0;            // per-block partial of sum_p ge_{t-1}[p][c]: [grid][C]
+  int ge_has_next;
+  float beta, kappa;
+};
+
 // gs = gout + alpha*dw^T(G1); gm = gs*sigma'(m_t) + gm_next*decay*(1-s_t); writes gm carry and gx[t].
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
@@ -180,7 +198,7 @@ k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*nu
                                const float* __restrict__ dw_w, const float* __restrict__ mem_t,
                                const uint32_t* __restrict__ bits_t, const float* __restrict__ gm /*dL/dm_{t+1} = gx[t+1]*/,
                                int has_next, float* __restrict__ gx, int N, int H, int W, int C, float thresh,
-                               float lens, float decay, float alpha, float* __restrict__ part) {
+                               float lens, float decay, float alpha, float* __restrict__ part, const PostEmit em) {
   // blockDim is a multiple of C/4: a thread keeps ONE channel quad and walks pixels p = block*nty + ty + k*grid*nty with
   // (h, w) tracked incrementally -- no division, no 64-bit multiply per element (the index arithmetic of the first version
   // was ~580 instructions per float4 and the kernel was issue bound at a third of the HBM rate).
@@ -193,7 +211,7 @@ k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*nu
   // p - off(tap) of pixel p, and
   //   dWdw[tap][c] = sum_p' G1[p'][c] * s_t[p' + off(tap)][c] = sum_p s_t[p][c] * G1[p - off(tap)][c]
   // is the same nine values gated by the spike of the centre pixel: rows 2..10 of part[block][11][C]; row 1 = sum_p G1[p][c].
-  float aw[9][4], ab[4] = {0.f, 0.f, 0.f, 0.f};
+  float aw[9][4], ab[4] = {0.f, 0.f, 0.f, 0.f}, s0[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int a = 0; a < 9; ++a)
 #pragma unroll
@@ -219,6 +237,11 @@ k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*nu
     if (has_next) {
       gn = *reinterpret_cast<const float4*>(gm + e);
       nib = (*bp >> sh) & 0xFu;
+    }
+    float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), nv = ev;   // trace / carry of the emitted ge: in flight with the rest
+    if (em.ecs_prev != nullptr) {
+      ev = *reinterpret_cast<const float4*>(em.ecs_prev + e);
+      if (em.ge_has_next) nv = *reinterpret_cast<const float4*>(em.ge + e);
     }
     if (g1 != nullptr) {
       float4 g[9];
@@ -276,14 +299,44 @@ k_lif_bwd_post(const float* __restrict__ gout, const float* __restrict__ g1 /*nu
       o.w += (nib & 8u) ? 0.f : gn.w * decay;
     }
     *reinterpret_cast<float4*>(gx + e) = o;   // gx[t] IS the carry dL/dm_t of the next (earlier) step: no separate copy
+    if (em.ecs_prev != nullptr) {
+      float th;
+      float4 q4;
+      th = tanhf(ev.x); q4.x = o.x * em.beta * (1.0f - th * th) + em.kappa * nv.x;
+      th = tanhf(ev.y); q4.y = o.y * em.beta * (1.0f - th * th) + em.kappa * nv.y;
+      th = tanhf(ev.z); q4.z = o.z * em.beta * (1.0f - th * th) + em.kappa * nv.z;
+      th = tanhf(ev.w); q4.w = o.w * em.beta * (1.0f - th * th) + em.kappa * nv.w;
+      *reinterpret_cast<float4*>(em.ge + e) = q4;
+      s0[0] += q4.x; s0[1] += q4.y; s0[2] += q4.z; s0[3] += q4.w;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(q4.x), h1 = __float2bfloat16_rn(q4.y);
+      const __nv_bfloat16 h2 = __float2bfloat16_rn(q4.z), h3 = __float2bfloat16_rn(q4.w);
+      *reinterpret_cast<uint2*>(em.ge_hi + e) =
+          make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
+                     (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
+      if (em.ge_lo != nullptr)
+        *reinterpret_cast<uint2*>(em.ge_lo + e) =
+            make_uint2(pack_bf16x2(q4.x - __bfloat162float(h0), q4.y - __bfloat162float(h1)),
+                       pack_bf16x2(q4.z - __bfloat162float(h2), q4.w - __bfloat162float(h3)));
+    }
     w += dw_;
     h += dh_;
     if (w >= W) { w -= W; ++h; }
     if (h >= H) h -= H;
   }
+  extern __shared__ float sred[];  // [nty][10][C] (spread sums) / [nty][C] (sum of the emitted ge)
+  if (em.ecs_prev != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sred[ty * C + tq * 4 + k] = s0[k];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
+      double t = 0;
+      for (int y = 0; y < nty; ++y) t += sred[y * C + idx];
+      em.part0[(size_t)blockIdx.x * C + idx] = static_cast<float>(t);
+    }
+    __syncthreads();
+  }
   if (part == nullptr) return;
   // block reduction over the threads of a channel quad in shared memory (double), one per-block partial per (row, channel)
-  extern __shared__ float sred[];  // [nty][10][C]
 #pragma unroll
   for (int k = 0; k < 4; ++k) sred[(ty * 10 + 0) * C + tq * 4 + k] = ab[k];
 #pragma unroll
@@ -471,7 +524,7 @@ extern "C" size_t ecsy_lif_ecs_bwd_ws_bytes(int T, int64_t N, int H, int W, int 
   (void)T;
   // gm, ge, G1 (fp32) + ge planes + dw planes (bf16) + reduction scratch
   return 512 + 3 * al256(mc * 4) + 2 * static_cast<size_t>(splits) * al256(mc * 2) +
-         al256((size_t)ecsy_num_sms() * 8 * 11 * C * 4);   // per-block partial sums of the parameter gradients
+         al256((size_t)ecsy_num_sms() * 8 * 13 * C * 4);   // per-block partial sums of the parameter gradients (+ 2 x sum ge)
 }
 
 extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const float* mem, const float* ecs,
@@ -516,13 +569,21 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
   static const int post_bps = getenv("ECSY_POST_BPS") ? atoi(getenv("ECSY_POST_BPS")) : 2;
   const int pgrid = grid_for(n4, rbd, ecsy_num_sms() * post_bps);
 
+  // ECSY_LIF_BWD_V=0: the separate reduction pass of round 1 (k_lif_bwd_reduce); =1: ge from k_lif_bwd_pre (one more launch and
+  // a re-read of gx per timestep); default: k_lif_bwd_post(t) emits ge_{t-1} itself.  Kept for A/B measurements.
+  static const int variant = getenv("ECSY_LIF_BWD_V") ? atoi(getenv("ECSY_LIF_BWD_V")) : 2;
+  const bool fused = variant != 0;
+  const bool emit = variant >= 2;
+  float* part0 = part + (size_t)ecsy_num_sms() * 8 * 11 * C;   // [2][pgrid][C] behind the [grid][11][C] partials
   for (int t = T - 1; t >= 0; --t) {
     const bool spread = t <= T - 2;
     const bool has_next = t < T - 1;
     if (spread) {
-      k_lif_bwd_pre<<<egrid, rbd, (size_t)(rbd / c4) * C * sizeof(float), st>>>(
-          gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta, kappa, part, C);
-      ECSY_LAUNCH_CHECK();
+      if (!emit) {
+        k_lif_bwd_pre<<<egrid, rbd, (size_t)(rbd / c4) * C * sizeof(float), st>>>(
+            gx + (size_t)(t + 1) * mc, ecs + (size_t)t * mc, ge, t < T - 2 ? 1 : 0, ge_hi, ge_lo, n4, beta, kappa, part, C);
+        ECSY_LAUNCH_CHECK();
+      }
       int rc = ecsy_umma_dense(ge_hi, ge_lo, M, C, pwT_packed, splits, g1, C, nullptr, nullptr, nullptr, 0, st);
       if (rc) return rc;
       rc = ecsy_launch_spread_dw(spikes + t * words, dw_w, dw_b, d_hi, d_lo, (int)N, H, W, C, st);
@@ -530,28 +591,33 @@ extern "C" int ecsy_lif_ecs_bwd(const float* gout, const uint32_t* spikes, const
       rc = ecsy_umma_xty(ge_hi, ge_lo, d_hi, d_lo, M, C, C, alpha, g_pw_w, st);
       if (rc) return rc;
     }
-    static const int variant = getenv("ECSY_LIF_BWD_V") ? atoi(getenv("ECSY_LIF_BWD_V")) : 2;
-    const bool fused = variant != 0;
     if (spread && !fused) {
       const int rgrid = grid_for(M, 64, ecsy_num_sms() * 4);
       k_lif_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, spikes + t * words, part,
                                                                                        (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
-      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, nullptr, rgrid, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
-    const size_t psm = (spread && fused) ? (size_t)(rbd / c4) * 10 * C * sizeof(float) : 0;
+    PostEmit em{};
+    if (emit && t >= 1) {   // this step's gx[t] -> ge_{t-1}, consumed by the GEMM / xty of the next loop iteration
+      em.ecs_prev = ecs + (size_t)(t - 1) * mc;
+      em.ge = ge; em.ge_hi = ge_hi; em.ge_lo = ge_lo;
+      em.part0 = part0 + (size_t)((t - 1) & 1) * pgrid * C;
+      em.ge_has_next = has_next ? 1 : 0;   // ge_t exists iff step t had a spread
+      em.beta = beta; em.kappa = kappa;
+    }
+    size_t psm = (spread && fused) ? (size_t)(rbd / c4) * 10 * C * sizeof(float) : 0;
+    if (em.ecs_prev != nullptr && psm < (size_t)(rbd / c4) * C * sizeof(float)) psm = (size_t)(rbd / c4) * C * sizeof(float);
     float* pp = (spread && fused) ? part : nullptr;
-#define ECSY_POST_ARGS gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc, spikes + t * words, \
-        has_next ? gx + (size_t)(t + 1) * mc : nullptr, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, thresh, lens, \
-        decay, alpha, pp
-    if (variant == 3) k_lif_bwd_post<3><<<pgrid, rbd, psm, st>>>(ECSY_POST_ARGS);
-    else if (variant == 4) k_lif_bwd_post<4><<<pgrid, rbd, psm, st>>>(ECSY_POST_ARGS);
-    else k_lif_bwd_post<2><<<pgrid, rbd, psm, st>>>(ECSY_POST_ARGS);
-#undef ECSY_POST_ARGS
+    k_lif_bwd_post<2><<<pgrid, rbd, psm, st>>>(   // <3> / <4> blocks per SM spill and ran 20-30 % slower
+        gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc, spikes + t * words,
+        has_next ? gx + (size_t)(t + 1) * mc : nullptr, has_next ? 1 : 0, gx + (size_t)t * mc, (int)N, H, W, C, thresh, lens,
+        decay, alpha, pp, em);
     ECSY_LAUNCH_CHECK();
     if (spread && fused) {
-      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, egrid, pgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, emit ? part0 + (size_t)(t & 1) * pgrid * C : nullptr,
+                                                                 emit ? pgrid : egrid, pgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
   }
@@ -635,7 +701,7 @@ extern "C" int ecsy_lif_silu_bwd(const float* gout, const float* out, const floa
       const int rgrid = grid_for(M, 64, ecsy_num_sms() * 4);
       k_silu_bwd_reduce<<<rgrid, rbd, (size_t)(rbd / c4) * 11 * C * sizeof(float), st>>>(ge, g1, o_t, part, (int)N, H, W, C);
       ECSY_LAUNCH_CHECK();
-      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, rgrid, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
+      k_lif_bwd_reduce_final<<<(11 * C + 31) / 32, 256, 0, st>>>(part, nullptr, rgrid, rgrid, g_pw_b, g_dw_b, g_dw_w, C, alpha);
       ECSY_LAUNCH_CHECK();
     }
     k_silu_bwd_post<<<egrid, kThreads, 0, st>>>(gout + (size_t)t * mc, spread ? g1 : nullptr, dw_w, mem + (size_t)t * mc,
