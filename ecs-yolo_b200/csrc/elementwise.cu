@@ -225,6 +225,7 @@ __global__ void k_ecs_step(const EcsStep p, int64_t n4, int64_t n4_round, int C)
 // ------------------------------------------------------------------------------------------
 constexpr int kDwRun = 16;
 
+template <bool LO>
 __global__ void __launch_bounds__(256)
 k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*[9][C]*/,
             const float* __restrict__ dw_b, __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo,
@@ -273,12 +274,17 @@ k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*
       win[ky][1] = (rok[ky] && x0 - 1 >= 0) ? rowp[ky][(int64_t)(x0 - 1) * c8] : 0u;
       win[ky][2] = rok[ky] ? rowp[ky][(int64_t)x0 * c8] : 0u;
     }
+    int64_t o = ((img * H + h) * W + x0) * (int64_t)c8 + cg;
+    const uint8_t* nextp[3];   // byte of column x + 1 in the three rows: running pointers instead of a 64-bit multiply per load
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) nextp[ky] = rowp[ky] + (int64_t)(x0 + 1) * c8;
     for (int x = x0; x < x1; ++x) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         win[ky][0] = win[ky][1];
         win[ky][1] = win[ky][2];
-        win[ky][2] = (rok[ky] && x + 1 < W) ? rowp[ky][(int64_t)(x + 1) * c8] : 0u;
+        win[ky][2] = (rok[ky] && x + 1 < W) ? *nextp[ky] : 0u;
+        nextp[ky] += c8;
       }
       float acc[8];
 #pragma unroll
@@ -295,15 +301,17 @@ k_spread_dw(const uint32_t* __restrict__ bits, const float* __restrict__ dw_w /*
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * q]), h1 = __float2bfloat16_rn(acc[2 * q + 1]);
-        hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * q] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * q + 1] - __bfloat162float(h1));
-        lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);   // one packed cvt
+        hi[q] = *reinterpret_cast<const uint32_t*>(&hp);
+        if (LO) {   // the residual plane exists in parity precision only: fast precision used to compute and drop it
+          const float2 hf = __bfloat1622float2(hp);
+          const __nv_bfloat162 lp = __floats2bfloat162_rn(acc[2 * q] - hf.x, acc[2 * q + 1] - hf.y);
+          lo[q] = *reinterpret_cast<const uint32_t*>(&lp);
+        }
       }
-      const int64_t o = ((img * H + h) * W + x) * (int64_t)c8 + cg;
       reinterpret_cast<uint4*>(a_hi)[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (LO) reinterpret_cast<uint4*>(a_lo)[o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      o += c8;
     }
   }
 }
@@ -1004,7 +1012,10 @@ int ecsy_launch_spread_dw_v(const uint32_t* bits, const float* dw_w, const float
   const int bd = lcm <= 256 ? (256 / lcm) * lcm : (256 / c8) * c8;
   const int nseg = (W + kDwRun - 1) / kDwRun;
   const int64_t items = (int64_t)N * H * nseg * c8;
-  k_spread_dw<<<grid_for(items, bd, ecsy_num_sms() * 4), bd, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
+  if (a_lo)
+    k_spread_dw<true><<<grid_for(items, bd, ecsy_num_sms() * 4), bd, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
+  else
+    k_spread_dw<false><<<grid_for(items, bd, ecsy_num_sms() * 4), bd, 0, st>>>(bits, dw_w, dw_b, a_hi, a_lo, N, H, W, C);
   ECSY_LAUNCH_CHECK();
   return ECSY_OK;
 }
