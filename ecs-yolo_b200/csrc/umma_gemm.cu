@@ -689,10 +689,20 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = n_tile * BN + c0;
+        // the residual slice of this chunk is requested first: its loads are in flight while the accumulator is read and staged
+        float4 r4[8];
+        if (e.residual != nullptr) {
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rr = itr * 4 + sub;
+            r4[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rinfo[rr * 2] >= 0) r4[itr] = *reinterpret_cast<const float4*>(e.residual + rinfo[rr * 2 + 1] + n0 + c4);
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
         tmem_ld_wait();
-        const int n0 = n_tile * BN + c0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
@@ -706,22 +716,13 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ C
           *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) = o;
         }
         __syncwarp();
-        // all residual loads of the slice first (independent, in flight together), then add + store
-        float4 r4[8];
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rr = itr * 4 + sub;
-          r4[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.residual != nullptr && rinfo[rr * 2] >= 0)
-            r4[itr] = *reinterpret_cast<const float4*>(e.residual + rinfo[rr * 2 + 1] + n0 + c4);
-        }
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
           const int rr = itr * 4 + sub;                       // row of this warp's 32-row slice
           const long long ooff = rinfo[rr * 2];
           float4 o = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
           if (ooff >= 0) {
-            o.x += r4[itr].x; o.y += r4[itr].y; o.z += r4[itr].z; o.w += r4[itr].w;
+            if (e.residual != nullptr) { o.x += r4[itr].x; o.y += r4[itr].y; o.z += r4[itr].z; o.w += r4[itr].w; }
             if (e.out_half) {
               __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
               uint2 pk;

@@ -12,6 +12,7 @@ ap.add_argument("--mode", default="fast")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--only", type=int, default=-1)
 ap.add_argument("--N", type=int, default=64)
+ap.add_argument("--res", action="store_true", help="with a residual tensor added in the epilogue (block shortcut)")
 ap.add_argument("--ts", default="auto", help="auto | all (spike operand in tensor memory) | off (shared memory)")
 args = ap.parse_args()
 F.set_precision(args.mode)
@@ -34,13 +35,16 @@ for idx, (ci, co, k, s, H) in enumerate(SHAPES):
     sp = F.Spikes(bits, ci)
     sc = torch.rand(co, device="cuda") + 0.5
     sh = torch.rand(co, device="cuda")
+    resid = None
+    if args.res and s == 1:
+        resid = F.Act(torch.randn(T, N, H, H, co, device="cuda"), T)
     for _ in range(3):
-        out = F.spike_conv(sp, cw, sc, sh)
+        out = F.spike_conv(sp, cw, sc, sh, resid)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.reps):
-        out = F.spike_conv(sp, cw, sc, sh)
+        out = F.spike_conv(sp, cw, sc, sh, resid)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
