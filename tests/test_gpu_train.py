@@ -469,3 +469,52 @@ def test_model_loss_fast_precision(name):
     assert rel < 0.15, rel
     params = dict(m.named_parameters())
     assert all(torch.isfinite(p.grad).all() for p in params.values() if p.grad is not None)
+
+
+def test_tdbn_glue_kernels_match_torch():
+    """ecsy_tdbn_finish / ecsy_tdbn_bwd_coef (one launch each) against the element-wise torch formulas they replaced --
+    nn.BatchNorm3d's running-statistics update inside batch_norm_2d (models/common.py:668-700) and the batch-norm backward
+    coefficients: fp32, same operation order, so the results agree to the last bit or two."""
+    E = ecsy()
+    F_ = E.functional
+    L = F_._cabi.lib()
+    g = torch.Generator().manual_seed(5)
+    C, n, m, eps, ups = 192, 4.0 * 2 * 20 * 24, 0.1, 1e-5, 2
+    mean, var = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.1
+    w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5
+    nbt = torch.tensor(7, dtype=torch.int64)
+    # reference (the torch sequence of autograd._bn_train_fwd_torch)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    for _ in range(ups):
+        rm_ref.mul_(1.0 - m).add_(mean, alpha=m)
+        rv_ref.mul_(1.0 - m).add_(var, alpha=m * n / (n - 1.0))
+    rstd_ref = torch.rsqrt(var + eps)
+    scale_ref = w * rstd_ref
+    shift_ref = b - mean * scale_ref
+    d = lambda t: t.clone().cuda()
+    mean_d, var_d, w_d, b_d, rm_d, rv_d, nbt_d = d(mean), d(var), d(w), d(b), d(rm), d(rv), d(nbt)
+    scale, shift, rstd = (torch.empty(C, device="cuda") for _ in range(3))
+    F_._cabi.check(L.ecsy_tdbn_finish(F_._p(mean_d), F_._p(var_d), F_._p(w_d), F_._p(b_d), F_._p(rm_d), F_._p(rv_d), F_._p(nbt_d),
+                                      m, n / (n - 1.0), eps, ups, F_._p(scale), F_._p(shift), F_._p(rstd), C, F_._st()), "tdbn_finish")
+    assert int(nbt_d) == 7 + ups
+    for got, want in ((rm_d, rm_ref), (rv_d, rv_ref), (rstd, rstd_ref), (scale, scale_ref), (shift, shift_ref)):
+        assert torch.allclose(got.cpu(), want, rtol=3e-6, atol=1e-7), float((got.cpu() - want).abs().max())
+    # without running statistics (track_running_stats = False): only the affine
+    F_._cabi.check(L.ecsy_tdbn_finish(F_._p(mean_d), F_._p(var_d), F_._p(w_d), F_._p(b_d), None, None, None, m, 1.0, eps, 0,
+                                      F_._p(scale), F_._p(shift), F_._p(rstd), C, F_._st()), "tdbn_finish")
+    assert torch.allclose(scale.cpu(), scale_ref, rtol=3e-6)
+    # backward coefficients
+    sg, sgy = torch.randn(C, generator=g) * 10, torch.randn(C, generator=g) * 10
+    tfac = 4.0
+    sgx_ref = rstd_ref * (sgy - mean * sg)
+    A_ref = w * rstd_ref
+    B_ref = -A_ref * rstd_ref * sgx_ref / n
+    C_ref = (-A_ref * sg / n - B_ref * mean) * tfac
+    B_ref = B_ref * tfac
+    A, B, Cc, gw = (torch.empty(C, device="cuda") for _ in range(4))
+    sg_d, sgy_d, rstd_d = d(sg), d(sgy), d(rstd_ref)     # named: a temporary would be freed (and its block reused) before the launch
+    F_._cabi.check(L.ecsy_tdbn_bwd_coef(F_._p(sg_d), F_._p(sgy_d), F_._p(mean_d), F_._p(rstd_d), F_._p(w_d), n, tfac,
+                                        F_._p(A), F_._p(B), F_._p(Cc), F_._p(gw), C, F_._st()), "tdbn_bwd_coef")
+    for got, want in ((A, A_ref), (B, B_ref), (Cc, C_ref), (gw, sgx_ref)):
+        assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-7), float((got.cpu() - want).abs().max())
