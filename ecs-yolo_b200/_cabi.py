@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libecsy.so")
+LIB_PATH = os.environ.get("ECSY_LIB") or os.path.join(_HERE, "lib", "libecsy.so")   # ECSY_LIB: A/B builds of the same ABI
 
 _p, _i, _l, _f, _z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
