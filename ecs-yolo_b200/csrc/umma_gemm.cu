@@ -1471,7 +1471,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-template <int BN>
+// F32: fp32 output (the G1 = ge * Wpw GEMM of the LIF backward, fast precision): 32-column slices (128-byte rows of fp32).
+template <int BN, bool F32 = false>
 __global__ void __launch_bounds__(kDtThreads, 1)
 k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
               const __grid_constant__ CUtensorMap tm_out, const DtArgs g) {
@@ -1480,7 +1481,8 @@ k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = kATileBytes + kBTileBytes;
   constexpr int kTmemCols = 2 * BN;
-  constexpr int kSlices = BN / 64;
+  constexpr int kSliceCols = F32 ? 32 : 64;
+  constexpr int kSlices = BN / kSliceCols;
   DtCtl* ctl = reinterpret_cast<DtCtl*>(smem + g.ctl_off);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.m_tiles * g.n_tiles;
@@ -1567,6 +1569,20 @@ k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           tc_fence_after_sync();
         }
         named_bar_sync(1 + (int)ge, 128);
+        const uint32_t dst = my_row + b * (uint32_t)kATileBytes;
+        if constexpr (F32) {
+          uint32_t v0[32];
+          tmem_ld_32x32(t_row + j * 32, v0);
+          tmem_ld_wait();
+          if (j == kSlices - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&ctl->tmem_empty[ge]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)   // chunk c = 4 floats
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)c ^ sw) << 4)), "r"(v0[4 * c]),
+                         "r"(v0[4 * c + 1]), "r"(v0[4 * c + 2]), "r"(v0[4 * c + 3]) : "memory");
+        } else {
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(t_row + j * 64, v0);
         tmem_ld_32x32(t_row + j * 64 + 32, v1);
@@ -1575,7 +1591,6 @@ k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           tc_fence_before_sync();
           mbar_arrive(&ctl->tmem_empty[ge]);
         }
-        const uint32_t dst = my_row + b * (uint32_t)kATileBytes;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {   // chunk c = 8 halves
           const uint32_t* src = c < 4 ? &v0[8 * c] : &v1[8 * (c - 4)];
@@ -1588,10 +1603,11 @@ k_dense_tma_h(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)c ^ sw) << 4)), "r"(w[0]),
                        "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
         }
+        }
         fence_proxy_async_smem();
         named_bar_sync(1 + (int)ge, 128);
         if (leader) {
-          tma_store_2d(&tm_out, stg + (size_t)b * kATileBytes, n_tile * BN + j * 64, m_tile * 128);
+          tma_store_2d(&tm_out, stg + (size_t)b * kATileBytes, n_tile * BN + j * kSliceCols, m_tile * 128);
           bulk_commit_group();
         }
       }
@@ -2616,10 +2632,32 @@ static int ecsy_tensor_map_f16_2d(const void* ptr, uint64_t rows, uint64_t cols,
   return ECSY_OK;
 }
 
+static int ecsy_tensor_map_f32_2d(const void* ptr, uint64_t rows, uint64_t cols, CUtensorMap* out) {
+  ECSY_CHECK_ARG(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cols % 32 == 0, "f32 tensor map: alignment");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    ecsy_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECSY_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ecsy_set_error("cuTensorMapEncodeTiled(f32 2d) failed with %d (rows=%llu cols=%llu)", (int)r, (unsigned long long)rows,
+                   (unsigned long long)cols);
+    return ECSY_ERR_CUDA;
+  }
+  return ECSY_OK;
+}
+
 namespace {
-template <int BN>
+template <int BN, bool F32 = false>
 int launch_dense_tma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, DtArgs g, cudaStream_t st) {
-  auto kern = k_dense_tma_h<BN>;
+  auto kern = k_dense_tma_h<BN, F32>;
   static bool attr = false;
   if (!attr) {
     ECSY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -2732,6 +2770,22 @@ int ecsy_umma_dense(const void* a_hi, const void* a_lo, int64_t M, int K, const 
       case 64: return launch_dense_tma<64>(ta0, tb, to, d, st);
       case 128: return launch_dense_tma<128>(ta0, tb, to, d, st);
       case 256: return launch_dense_tma<256>(ta0, tb, to, d, st);
+    }
+  }
+  static const bool dense_f32 = getenv("ECSY_DENSE_TMA_F32") == nullptr || getenv("ECSY_DENSE_TMA_F32")[0] != '0';
+  if (dense_tma && dense_f32 && splits == 1 && !out_half && !scale && !residual && M >= 128) {
+    // fast precision, plain fp32 output (G1 = ge * Wpw of the LIF backward): the same two-group TMA-store epilogue
+    CUtensorMap to;
+    rc = ecsy_tensor_map_f32_2d(out, (uint64_t)M, (uint64_t)Cout, &to);
+    if (rc) return rc;
+    DtArgs d{};
+    d.m_tiles = (int)((M + 127) / 128);
+    d.n_tiles = Cout / BN;
+    d.kb_total = K / 64;
+    switch (BN) {
+      case 64: return launch_dense_tma<64, true>(ta0, tb, to, d, st);
+      case 128: return launch_dense_tma<128, true>(ta0, tb, to, d, st);
+      case 256: return launch_dense_tma<256, true>(ta0, tb, to, d, st);
     }
   }
   GemmArgs g{};
