@@ -64,6 +64,10 @@ def bn_train_fwd(bn_mod, y: Act):
     mean, var = F_.bn_stats(y)
     C = y.C
     n = float(y.T * y.N * y.H * y.W)
+    if isinstance(bn, torch.nn.SyncBatchNorm):      # the reference's --sync-bn (train.py:359-360): statistics of all ranks
+        from . import dist as D
+        mean, var, world = D.sync_bn_stats(mean, var)
+        n *= world
     track = bool(bn.track_running_stats) and bn.running_mean is not None
     if (track and bn.momentum is None) or bn.weight is None:
         return _bn_train_fwd_torch(bn_mod, y, mean, var, n)     # cumulative average: needs the step count on the host
@@ -103,13 +107,20 @@ def bn_train_bwd_coeffs(bn_mod, y: Act, mean, rstd, g_yn: torch.Tensor, grads):
     n = float(y.T * y.N * y.H * y.W)
     tfac = float(y.T) / float(y.Tp)
     sg, sgy = F_.colsum2(g_yn, y.data, C)
+    sg_l, sgy_l, world = sg, sgy, 1
+    if isinstance(bn, torch.nn.SyncBatchNorm):      # input gradient from the sums over all ranks, parameter gradients local
+        from . import dist as D
+        sg, sgy, world = D.sync_bn_sums(sg, sgy)
+        n *= world
     A = torch.empty(C, device=sg.device, dtype=torch.float32)
     B, Cc, sgx = torch.empty_like(A), torch.empty_like(A), torch.empty_like(A)
     with torch.no_grad():
         F_._cabi.check(F_._cabi.lib().ecsy_tdbn_bwd_coef(F_._p(sg), F_._p(sgy), F_._p(mean), F_._p(rstd), F_._p(bn.weight), n, tfac,
                                                          F_._p(A), F_._p(B), F_._p(Cc), F_._p(sgx), C, F_._st()), "tdbn_bwd_coef")
+        if world > 1:
+            sgx = rstd * (sgy_l - mean * sg_l)
     _acc(grads, bn.weight, sgx)
-    _acc(grads, bn.bias, sg)
+    _acc(grads, bn.bias, sg_l)
     return A, B, Cc
 
 

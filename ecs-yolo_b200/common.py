@@ -206,9 +206,13 @@ class _tdbn(nn.Module):
         bn = self.bn
         if bn.training or not bn.track_running_stats:
             mean, var = F_.bn_stats(y)
+            world = 1
+            if isinstance(bn, nn.SyncBatchNorm) and bn.training:   # --sync-bn (train.py:359-360)
+                from . import dist as D
+                mean, var, world = D.sync_bn_stats(mean, var)
             with torch.no_grad():
                 if bn.track_running_stats:
-                    n = float(y.T * y.N * y.H * y.W)
+                    n = float(y.T * y.N * y.H * y.W) * world
                     for _ in range(self.stat_updates):
                         bn.num_batches_tracked += 1
                         m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)

@@ -4,7 +4,9 @@ The hot path shards by batch (images are independent, reference train.py:368,419
 data-path collective; training has ONE exchange step per optimizer step, the gradient all-reduce
 (DDP in the reference, train.py:419).  ``allreduce_grads`` is the bucketed all-reduce used when the model
 is not wrapped in DistributedDataParallel; bench.py wraps with DDP so the reduction overlaps the backward
-kernels.  BN statistics stay per-GPU (reference default, train.py:814).
+kernels.  BN statistics stay per-GPU (reference default, train.py:814) unless the model went through
+``torch.nn.SyncBatchNorm.convert_sync_batchnorm`` like the reference's ``--sync-bn`` (train.py:359-360): then every tdBN
+exchanges one [2, C] all-reduce per direction (``sync_bn_stats`` / ``sync_bn_sums``).
 """
 from __future__ import annotations
 
@@ -77,3 +79,26 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64
             off += p.numel()
         n_coll += 1
     return n_coll
+
+
+def sync_bn_stats(mean: torch.Tensor, var: torch.Tensor):
+    """SyncBatchNorm forward (train.py:359-360): per-rank (mean, biased variance) over equal-sized shards -> the statistics
+    of the union, through ONE all-reduce of [E x, E x^2].  -> (mean, var, world)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return mean, var, 1
+    world = dist.get_world_size()
+    st = torch.stack([mean, var + mean * mean])
+    dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    st /= world
+    m = st[0].contiguous()
+    return m, (st[1] - m * m).clamp_min_(0).contiguous(), world
+
+
+def sync_bn_sums(sg: torch.Tensor, sgy: torch.Tensor):
+    """SyncBatchNorm backward: the batch sums of the input gradient (sum g, sum g*y) over ALL ranks (the weight / bias
+    gradients keep the local sums: DDP averages those like every other parameter gradient).  -> (sg, sgy, world)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return sg, sgy, 1
+    st = torch.stack([sg, sgy])
+    dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    return st[0].contiguous(), st[1].contiguous(), dist.get_world_size()

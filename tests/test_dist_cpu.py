@@ -66,3 +66,42 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _sync_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    D = importlib.import_module("ecs-yolo_b200").dist
+    D.init("gloo")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2 * 50, 6, generator=g) * 2 + 1          # rows of both ranks
+    gg = torch.randn(2 * 50, 6, generator=g)
+    xs, gs = x[rank * 50:(rank + 1) * 50], gg[rank * 50:(rank + 1) * 50]
+    mean, var, w = D.sync_bn_stats(xs.mean(0), xs.var(0, unbiased=False))
+    sg, sgy, w2 = D.sync_bn_sums(gs.sum(0), (gs * xs).sum(0))
+    out[rank] = dict(mean=mean, var=var, sg=sg, sgy=sgy, w=(w, w2))
+    torch.distributed.destroy_process_group()
+
+
+def test_sync_bn_statistics_world2():
+    """--sync-bn (train.py:359-360): the [2, C] all-reduces of a tdBN give the statistics / gradient sums of the UNION of the
+    ranks' shards; a single process gets its inputs back."""
+    D = ecsy().dist
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sync_worker, args=(world, port, out), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(100, 6, generator=g) * 2 + 1
+    gg = torch.randn(100, 6, generator=g)
+    for r in (0, 1):
+        assert out[r]["w"] == (2, 2)
+        assert torch.allclose(out[r]["mean"], x.mean(0), atol=1e-6)
+        assert torch.allclose(out[r]["var"], x.var(0, unbiased=False), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(out[r]["sg"], gg.sum(0), atol=1e-5)
+        assert torch.allclose(out[r]["sgy"], (gg * x).sum(0), rtol=1e-5, atol=1e-5)
+    m, v = torch.ones(3), torch.full((3,), 2.0)
+    assert D.sync_bn_stats(m, v) == (m, v, 1) or D.sync_bn_stats(m, v)[2] == 1

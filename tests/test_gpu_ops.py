@@ -183,6 +183,24 @@ def test_tdbn_module(name):
         assert rel_l2(m(inp["x"].cuda()).cpu(), gold[tag + "_eval"]) < 1e-5
 
 
+def test_tdbn_sync_bn_single_process():
+    """--sync-bn (train.py:359-360): a tdBN converted by SyncBatchNorm.convert_sync_batchnorm keeps its parameters and, in one
+    process (no exchange partner), the train / eval results and running statistics of the unconverted module."""
+    E = ecsy()
+    name = list(S.BN_CASES)[0]
+    spec, gold = S.BN_CASES[name], load_golden(name)
+    inp = S.bn_inputs(spec)
+    m = E.common.batch_norm_2d(spec["C"])
+    m.load_state_dict(inp["sd"])
+    m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m).cuda().train()
+    assert isinstance(m.bn, torch.nn.SyncBatchNorm)
+    assert rel_l2(m(inp["x"].cuda()).cpu(), gold["bn1_train"]) < 1e-5
+    for k, v in gold["bn1_sd_after"].items():
+        assert torch.allclose(m.state_dict()[k].cpu().float(), v.float(), rtol=1e-5, atol=1e-6), k
+    m.eval()
+    assert rel_l2(m(inp["x"].cuda()).cpu(), gold["bn1_eval"]) < 1e-5
+
+
 def test_resample_concat_tsum():
     E = ecsy()
     F = E.functional
