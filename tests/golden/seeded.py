@@ -475,6 +475,9 @@ CKPT_PLANS = {
 MODEL_LOSS_HYP = dict(box=0.05 * 3 / 2, cls=0.5 * 3 / 80 * 3 / 2, obj=1.0 * (64 / 640) ** 2 * 3 / 2, cls_pw=1.0, obj_pw=1.0,
                       anchor_t=4.0, fl_gamma=0.0, slide_ratio=0.0, label_smoothing=0.0)     # train.py:427-433 scaling
 
+# tier-4 training-curve fixtures (oracle/gen_golden_trajectory.py): the reference's SGD recipe on one fixed batch
+TRAJECTORY_HYP = dict(steps=6, lr=0.01, momentum=0.937, weight_decay=5e-4)
+
 
 def model_targets(spec, nc=3):
     """[nt, 6] labels for the whole-model loss cases: 3 boxes per image, sized to match the tiny plans' anchors."""

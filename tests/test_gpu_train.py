@@ -518,3 +518,56 @@ def test_tdbn_glue_kernels_match_torch():
                                         F_._p(A), F_._p(B), F_._p(Cc), F_._p(gw), C, F_._st()), "tdbn_bwd_coef")
     for got, want in ((A, A_ref), (B, B_ref), (Cc, C_ref), (gw, sgx_ref)):
         assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-7), float((got.cpu() - want).abs().max())
+
+
+# ---------------------------------------------------------------- tier 4: training curves against the reference
+@pytest.mark.parametrize("name", ["tiny_64", "tiny_b_64"])
+def test_training_trajectory_matches_reference(name):
+    """SURVEY 8c tier 4.  Six optimizer steps on one fixed batch from identical weights: our model (parity precision,
+    surrogate-gradient BPTT through the kernels), our device ComputeLoss and the fused SGD-Nesterov step, against the
+    UNMODIFIED reference doing the same with its own model / ComputeLoss / autograd / torch.optim.SGD over the three
+    parameter groups of train.py:262-287 (oracle/gen_golden_trajectory.py -> tests/golden/train_trajectory.pt).  The loss
+    of EVERY step, the head's parameters after the last step and how far every parameter moved must agree."""
+    E = ecsy()
+    E.set_precision("parity")
+    stack_b = name in S.MODEL_B_CASES
+    spec = (S.MODEL_B_CASES if stack_b else S.MODEL_CASES)[name]
+    gold = torch.load(os.path.join(S.GOLDEN_DIR, "train_trajectory.pt"), weights_only=False)[name]
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")))
+    inp = S.model_inputs(spec, O, cfg)
+    m = (E.yolo_snn.DetectionModel if stack_b else E.yolo.Model)(E.cfg_path(spec["cfg"]))
+    m.load_state_dict(inp["sd"])
+    m = m.cuda().train()
+    m.hyp = dict(S.MODEL_LOSS_HYP)
+    crit = (E.loss_tal if stack_b else E.loss).ComputeLoss(m)
+    hp = S.TRAJECTORY_HYP
+    opt = E.optim.SGDNesterovEMA(m, lr=hp["lr"], momentum=hp["momentum"], weight_decay=hp["weight_decay"], ema=False)
+    x, tg = inp["x"].cuda(), S.model_targets(spec, cfg["nc"]).cuda()
+    start = {k: p.detach().clone() for k, p in m.named_parameters()}
+    losses = []
+    for _ in range(hp["steps"]):
+        opt.zero_grad(set_to_none=True)
+        loss, _items = crit(m(x), tg)
+        loss.sum().backward()
+        opt.step()
+        losses.append(float(loss.sum()))
+    want = gold["losses"].tolist()
+    dev = [abs(a - b) / abs(b) for a, b in zip(losses, want)]
+    params = dict(m.named_parameters())
+    head_err = {k: rel_l2(params[k].detach().cpu(), v) for k, v in gold["head_params"].items()}
+    moved = {k: float((p.detach() - start[k]).norm()) for k, p in params.items()}
+    ratios = sorted(moved[k] / v for k, v in gold["moved"].items() if v > 1e-6)
+    med, lo10, hi90 = ratios[len(ratios) // 2], ratios[len(ratios) // 10], ratios[(9 * len(ratios)) // 10]
+    print(name, "losses", [round(v, 6) for v in losses], "reference", [round(v, 6) for v in want],
+          "rel dev", [f"{d:.1e}" for d in dev], "head param err", f"{max(head_err.values()):.1e}",
+          "displacement ratio (ours / reference) median", round(med, 4), "10 % / 90 % quantiles", round(lo10, 4), round(hi90, 4))
+    # Step 0 (identical weights) is the 1e-3 bar of test_model_loss_matches_reference.  From step 1 on the bar is the
+    # reference's own noise floor: a gradient that differs in the sixth digit moves a handful of near-threshold spikes and
+    # the loss by a few per cent (two CPU evaluation orders of the SAME fp32 arithmetic differ by 1.5 % at step 5,
+    # tests/test_oracle_post.py::test_training_trajectory_oracle; PyTorch-vs-PyTorch 1.3-2.8 %, SURVEY 8c tier 3), so the
+    # curves must OVERLAP, not coincide.  Measured on B200: tiny_64 2.7e-6 then 2.4-6.4 %; tiny_b_64 2.3e-6 then 0.4-9.7 %
+    # along a loss that falls 175 -> 30.
+    assert dev[0] < 1e-4, dev
+    assert max(dev) < 0.15 and sum(dev) / len(dev) < 0.08, dev
+    assert max(head_err.values()) < 0.15, head_err      # measured: 7.5e-3 (tiny_64), 6.0e-2 (tiny_b_64: a bias of the box branch)
+    assert 0.9 < med < 1.1 and lo10 > 0.6 and hi90 < 1.6, (med, lo10, hi90)

@@ -132,3 +132,46 @@ def test_model_plus_loss_oracle(name):
     assert min(counts) > 0
     assert torch.allclose(loss.reshape(-1), gold["loss"], rtol=1e-5), (float(loss), float(gold["loss"]))
     assert torch.allclose(items, gold["items"], rtol=1e-5, atol=1e-7)
+
+
+def test_training_trajectory_oracle():
+    """SURVEY 8c tier 4 on the CPU: ecs_oracle.forward (train mode, autograd = surrogate-gradient BPTT) ->
+    loss_oracle.compute_loss -> torch.optim.SGD over the reference's three parameter groups follows the UNMODIFIED
+    reference's six-step training curve on the tiny Stack-A plan (oracle/gen_golden_trajectory.py)."""
+    import yaml
+    import ecs_oracle as O
+    import loss_oracle as LO
+    from util import ROOT
+    name = "tiny_64"
+    spec, hp = S.MODEL_CASES[name], S.TRAJECTORY_HYP
+    gold = _load("train_trajectory")[name]
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "ecs-yolo_b200", "cfg", spec["cfg"] + ".yaml")))
+    inp = S.model_inputs(spec, O, cfg)
+    sd = {k: v.clone() for k, v in inp["sd"].items()}
+    anchors = [v for k, v in sd.items() if k.endswith("anchors")][0]
+    buffers = ("running_mean", "running_var", "num_batches_tracked", "anchors")
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and not k.endswith(buffers)}
+    assert set(params) == set(gold["moved"]), set(params) ^ set(gold["moved"])
+    g0 = [v for k, v in params.items() if k.endswith(".bn.weight")]
+    g2 = [v for k, v in params.items() if k.endswith(".bias")]
+    g1 = [v for k, v in params.items() if not k.endswith((".bn.weight", ".bias"))]
+    opt = torch.optim.SGD(g0, lr=hp["lr"], momentum=hp["momentum"], nesterov=True)
+    opt.add_param_group({'params': g1, 'weight_decay': hp["weight_decay"]})
+    opt.add_param_group({'params': g2})
+    tg = S.model_targets(spec, cfg["nc"])
+    losses = []
+    for _ in range(hp["steps"]):
+        opt.zero_grad()
+        out = O.forward(cfg, sd, inp["x"], spec["T"], True, stride=inp["stride"])
+        loss, _items, _counts, _ = LO.compute_loss(out, tg, anchors, S.MODEL_LOSS_HYP)
+        loss.sum().backward()
+        opt.step()
+        losses.append(float(loss.sum()))
+    want = gold["losses"].tolist()
+    dev = [abs(a - b) / abs(b) for a, b in zip(losses, want)]
+    err = {k: float((sd[k].detach() - v).norm() / v.norm()) for k, v in gold["head_params"].items()}
+    print("trajectory rel dev", dev, "head param rel-L2", err)
+    # measured here: steps 0-4 bit-identical, step 5 off by 1.5 % -- one near-threshold spike flips between two CPU
+    # evaluation orders of the same arithmetic (the reference's own PyTorch-vs-PyTorch noise floor, SURVEY 8c tier 3)
+    assert max(dev[:5]) <= 2e-4 and max(dev) <= 3e-2, (losses, want)
+    assert max(err.values()) < 2e-2, err
