@@ -11,3 +11,6 @@ run r34_parity --model resnet34 --precision parity --steps 3 --warmup 3
 run r34_gen1_T5 --model resnet34 --T 5 --events --batch 32 --steps 3 --warmup 3
 run r34_train --model resnet34 --mode train --batch 32 --steps 3 --warmup 2 --min-warmup 2
 run res18ee_infer --model res18-ee --batch 32 --steps 3 --warmup 3
+# BASELINE configs[3] also names TRAINING on Gen1 event frames (T = 5): only run with GEN1_TRAIN=1 or as the whole list
+run r34_gen1_T5_train --model resnet34 --T 5 --events --mode train --batch 16 --steps 3 --warmup 2 --min-warmup 2
+run res18ee_gen1_T5_train --model res18-ee --T 5 --events --mode train --batch 16 --steps 3 --warmup 2 --min-warmup 2
