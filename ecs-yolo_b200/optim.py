@@ -26,7 +26,7 @@ def param_groups_of(model: nn.Module):
     for v in model.modules():
         if hasattr(v, 'bias') and isinstance(v.bias, nn.Parameter):
             g2.append(v.bias)
-        if isinstance(v, nn.BatchNorm3d):
+        if isinstance(v, (nn.BatchNorm3d, nn.SyncBatchNorm)):   # --sync-bn converts after the reference built its groups (train.py:283, :359)
             g0.append(v.weight)
         elif hasattr(v, 'weight') and isinstance(v.weight, nn.Parameter):
             g1.append(v.weight)
