@@ -61,9 +61,16 @@ class Detect(nn.Module):
             tw = _cached(self.w[i], "tw", (wt,), lambda: wt.detach().reshape(-1).float().contiguous())
             feat = F_.tsum(a, tw, 1.0)                                   # [N,H,W,C]
             conv = self.m[i]
-            cw = _cached(conv, "detw", (conv.weight, conv.bias, wt), lambda: F_.make_conv_w(
-                conv.weight, conv.bias * wt.detach().sum(), 1, 0, 1, False, True))
-            y = F_.real_conv(Act(feat.unsqueeze(0), 1), cw).data[0]      # [N,H,W,na*no]
+            if conv.in_channels % 64 == 0:
+                # tensor-core path: output channels zero-padded to the 64-column tile, bias * sum(w) as the epilogue's shift,
+                # ALWAYS the three-term bf16 split (hi*hi + lo*hi + hi*lo, ~1e-6): the head stays at fp32 accuracy in fast
+                # precision too.  (The one-thread-per-output SIMT conv took 0.84 ms per batch-64 forward for 3.5 GFLOP.)
+                cw, sc1, sh1 = _cached(conv, "detw_umma", (conv.weight, conv.bias, wt), lambda: _detect_conv_w(conv, wt))
+                y = F_.real_conv(Act(feat.unsqueeze(0), 1), cw, sc1, sh1).data[0][..., :conv.out_channels].contiguous()
+            else:
+                cw = _cached(conv, "detw", (conv.weight, conv.bias, wt), lambda: F_.make_conv_w(
+                    conv.weight, conv.bias * wt.detach().sum(), 1, 0, 1, False, True))
+                y = F_.real_conv(Act(feat.unsqueeze(0), 1), cw).data[0]      # [N,H,W,na*no]
             st = getattr(self, "_strides", None)
             stride_i = (st[i] if st else float(self.stride[i])) if z is not None else 1.0
             x[i] = F_.detect_decode(y, self.na, self.no, self.anchors[i].contiguous(), stride_i, z, off)
@@ -87,6 +94,16 @@ class Detect(nn.Module):
             bs, _, ny, nx = y.shape
             out.append(y.view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous())
         return out
+
+
+def _detect_conv_w(conv, wt):
+    """Detect's 1x1 conv (+ bias) for the dense tcgen05 GEMM: [co, ci] zero-padded to a multiple of 64 output channels,
+    packed as bf16 hi + lo planes; (scale = 1, shift = bias * sum of the T-fusion weights) for the epilogue."""
+    co, cop = conv.out_channels, F_.pad64(conv.out_channels)
+    w = torch.nn.functional.pad(conv.weight.detach().float(), (0, 0, 0, 0, 0, 0, 0, cop - co))
+    cw = F_.ConvW(F_.pack_conv_weight(w, 2), None, None, cop, conv.in_channels, 1, 1, 0, 1, 2)
+    shift = F_.pad_channels((conv.bias.detach().float() * wt.detach().float().sum()).contiguous(), cop).contiguous()
+    return cw, torch.ones(cop, device=w.device, dtype=torch.float32), shift
 
 
 class Model(nn.Module):
