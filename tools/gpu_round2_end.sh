@@ -17,8 +17,10 @@ PROF="python bench.py --steps 2 --warmup 1 --min-warmup 1 --no-e2e --no-cpu-base
 timeout -k 10 300 $PROF > gpurun_out/prof_plain.log 2>&1 &&
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r02_launches_bench_b64.csv $PROF > gpurun_out/ncu_launches.log 2>&1
 echo "ncu infer launches rc=$?"
+if [ -z "$NO_NCU_TRAIN" ]; then
 PROF="python bench.py --mode train --model resnet18 --batch 32 --steps 1 --warmup 1 --min-warmup 1 --no-e2e --no-cpu-baseline"
 timeout -k 10 300 $PROF > gpurun_out/prof_train_plain.log 2>&1 &&
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/r02_launches_train_r18_b32.csv $PROF > gpurun_out/ncu_launches_train.log 2>&1
 echo "ncu train launches rc=$?"
+fi
 fi
