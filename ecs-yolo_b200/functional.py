@@ -352,6 +352,22 @@ def make_conv_w(weight: torch.Tensor, bias, stride: int, pad: int, groups: int, 
     return cw
 
 
+def make_head_conv_w(weight: torch.Tensor, bias: Optional[torch.Tensor], groups: int = 1, bias_mul=1.0):
+    """A detection head's 1x1 conv (+ bias) on real features for the dense tcgen05 GEMM: a grouped weight becomes its
+    block-diagonal dense form, the output channels are zero-padded to the 64-column tile, and the weight is ALWAYS packed as
+    bf16 hi + lo planes (three-term split hi*hi + lo*hi + hi*lo, ~1e-6: head outputs keep fp32 accuracy in fast precision).
+    -> (ConvW, scale = 1, shift = bias * bias_mul) for real_conv; the caller slices the first `co` output channels."""
+    dense = densify_grouped(weight, groups) if groups > 1 else weight.detach().float()
+    co, ci = dense.shape[0], dense.shape[1]
+    cop = pad64(co)
+    w = torch.nn.functional.pad(dense, (0, 0, 0, 0, 0, 0, 0, cop - co))
+    cw = ConvW(pack_conv_weight(w, 2), None, None, cop, ci, 1, 1, 0, 1, 2)
+    shift = torch.zeros(cop, device=w.device, dtype=torch.float32)
+    if bias is not None:
+        shift[:co] = bias.detach().float() * bias_mul
+    return cw, torch.ones(cop, device=w.device, dtype=torch.float32), shift
+
+
 @dataclass
 class LifW:
     dw_w: torch.Tensor   # [9, C]

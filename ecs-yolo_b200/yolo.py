@@ -97,13 +97,8 @@ class Detect(nn.Module):
 
 
 def _detect_conv_w(conv, wt):
-    """Detect's 1x1 conv (+ bias) for the dense tcgen05 GEMM: [co, ci] zero-padded to a multiple of 64 output channels,
-    packed as bf16 hi + lo planes; (scale = 1, shift = bias * sum of the T-fusion weights) for the epilogue."""
-    co, cop = conv.out_channels, F_.pad64(conv.out_channels)
-    w = torch.nn.functional.pad(conv.weight.detach().float(), (0, 0, 0, 0, 0, 0, 0, cop - co))
-    cw = F_.ConvW(F_.pack_conv_weight(w, 2), None, None, cop, conv.in_channels, 1, 1, 0, 1, 2)
-    shift = F_.pad_channels((conv.bias.detach().float() * wt.detach().float().sum()).contiguous(), cop).contiguous()
-    return cw, torch.ones(cop, device=w.device, dtype=torch.float32), shift
+    """Detect's 1x1 conv (+ bias * sum of the T-fusion weights) for the dense tcgen05 GEMM (functional.make_head_conv_w)."""
+    return F_.make_head_conv_w(conv.weight, conv.bias, 1, wt.detach().float().sum())
 
 
 class Model(nn.Module):

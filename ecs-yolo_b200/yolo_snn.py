@@ -55,6 +55,11 @@ class DDetect(nn.Module):
         y2 = seq[1].run(y1)
         feat = F_.tsum(y2, None, float(y2.T))          # [N,H,W,C]
         conv = seq[2]
+        if conv.in_channels % 64 == 0 and conv.kernel_size[0] == 1 and not self.training:
+            # inference: the last 1x1 (+ bias, grouped in the box branch) on the dense tcgen05 GEMM instead of the SIMT conv
+            cw, sc1, sh1 = _cached(conv, "headw_umma", (conv.weight, conv.bias),
+                                   lambda: F_.make_head_conv_w(conv.weight, conv.bias, conv.groups))
+            return F_.real_conv(Act(feat.unsqueeze(0), 1), cw, sc1, sh1).data[0][..., :conv.out_channels].contiguous()
         out = conv.conv_real(Act(feat.unsqueeze(0), 1))
         return out.data[0]                              # [N,H,W,Cout]
 
