@@ -567,7 +567,10 @@ def test_training_trajectory_matches_reference(name):
     # tests/test_oracle_post.py::test_training_trajectory_oracle; PyTorch-vs-PyTorch 1.3-2.8 %, SURVEY 8c tier 3), so the
     # curves must OVERLAP, not coincide.  Measured on B200: tiny_64 2.7e-6 then 2.4-6.4 %; tiny_b_64 2.3e-6 then 0.4-9.7 %
     # along a loss that falls 175 -> 30.
+    # The bounds leave a factor ~3 over the measured deviations: the gradient reductions use floating-point atomics, so WHICH
+    # near-threshold spikes flip differs from run to run; a wrong learning rate, momentum, weight decay or parameter group
+    # moves the curve / the displacements by far more.
     assert dev[0] < 1e-4, dev
-    assert max(dev) < 0.15 and sum(dev) / len(dev) < 0.08, dev
-    assert max(head_err.values()) < 0.15, head_err      # measured: 7.5e-3 (tiny_64), 6.0e-2 (tiny_b_64: a bias of the box branch)
-    assert 0.9 < med < 1.1 and lo10 > 0.6 and hi90 < 1.6, (med, lo10, hi90)
+    assert max(dev) < 0.30 and sum(dev) / len(dev) < 0.15, dev
+    assert max(head_err.values()) < 0.30, head_err      # measured: 7.5e-3 (tiny_64), 6.0e-2 (tiny_b_64: a bias of the box branch)
+    assert 0.85 < med < 1.15 and lo10 > 0.5 and hi90 < 2.0, (med, lo10, hi90)
