@@ -105,3 +105,26 @@ def test_sync_bn_statistics_world2():
         assert torch.allclose(out[r]["sgy"], (gg * x).sum(0), rtol=1e-5, atol=1e-5)
     m, v = torch.ones(3), torch.full((3,), 2.0)
     assert D.sync_bn_stats(m, v) == (m, v, 1) or D.sync_bn_stats(m, v)[2] == 1
+
+
+def test_param_groups_follow_reference_with_and_without_sync_bn():
+    """train.py:262-277: BatchNorm3d weights -> g0 (no decay), other weights -> g1 (decay), biases -> g2.  The reference
+    builds the groups BEFORE --sync-bn converts the model (train.py:283 vs :359), so the tdBN weights stay in g0; the
+    package's optimizer gives the same split whether it is built before or after the conversion."""
+    E = ecsy()
+    blk = E.common.BasicBlock_2(64, 128, 3, 2)
+    ref = dict(g0=[], g1=[], g2=[])
+    for v in blk.modules():                      # the reference's loop, statement for statement
+        if hasattr(v, 'bias') and isinstance(v.bias, torch.nn.Parameter):
+            ref["g2"].append(v.bias)
+        if isinstance(v, (torch.nn.BatchNorm3d)):
+            ref["g0"].append(v.weight)
+        elif hasattr(v, 'weight') and isinstance(v.weight, torch.nn.Parameter):
+            ref["g1"].append(v.weight)
+    ids = lambda ps: sorted(id(p) for p in ps)
+    g0, g1, g2 = E.optim.param_groups_of(blk)
+    assert (ids(g0), ids(g1), ids(g2)) == (ids(ref["g0"]), ids(ref["g1"]), ids(ref["g2"]))
+    assert len(g0) == 3 and all(p.dim() == 1 for p in g0)
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(blk)
+    h0, h1, h2 = E.optim.param_groups_of(conv)
+    assert (ids(h0), ids(h1), ids(h2)) == (ids(g0), ids(g1), ids(g2))     # the conversion keeps the Parameter objects
