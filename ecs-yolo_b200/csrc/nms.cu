@@ -6,8 +6,14 @@
 //                      above the threshold (general.py:697-702), optional class filter (:705-706).  A candidate is
 //                      a 64-bit key (~score bits << 32 | row * nc + class): ascending key order = descending score,
 //                      ties by prediction order -- the order of the stable sort inside torchvision's nms.
-//   k_nms_select     : one CTA per image: bitonic sort of the keys (shared memory up to 8192 candidates; above that the
-//                      large strides run over the L2-resident workspace and the small ones chunk-wise in shared memory), truncation to max_nms (general.py:716-717), then the
+//   k_nms_select     : one CTA per image.  Up to 8192 candidates: one bitonic sort of the keys in shared memory.  More (the
+//                      val setting conf_thres = 0.001 + multi_label: ~78 000 per image): the candidates are consumed in
+//                      score order in BATCHES of 8192 -- a radix select (eight 8-bit passes over the L2-resident keys) finds
+//                      the 8192-th smallest key above the previous batch, the batch is gathered and sorted in shared memory
+//                      and scanned; the next batch is only formed if fewer than max_det boxes survived so far (the first
+//                      max_det survivors of a greedy scan do not depend on anything after them, so a full sort of 131 072
+//                      padded keys -- 11.9 ms per batch of 64 images, nearly all of the call -- is never needed).
+//                      Truncation to max_nms (general.py:716-717), then the
 //                      greedy scan in chunks of 256 candidates: every thread tests one candidate against the boxes
 //                      kept so far, the chunk's own 256 x 256 suppression bit matrix resolves the order dependence
 //                      inside the chunk, and the scan stops at max_det kept boxes (general.py:723-724: the first
@@ -21,7 +27,8 @@
 namespace {
 
 constexpr int kChunk = 256;         // candidates resolved per round of the greedy scan
-constexpr int kSelThreads = 256;
+constexpr int kSplit = 4;           // threads per candidate of a chunk: the kept list / the chunk's columns are split kSplit ways
+constexpr int kSelThreads = kChunk * kSplit;
 constexpr int kSortSmemKeys = 8192; // 64 KB of keys sorted in shared memory
 constexpr float kMaxWh = 4096.f;    // general.py:667
 
@@ -89,45 +96,39 @@ __device__ void bitonic_chunk(unsigned long long* s, int base, int CH, int lsize
   }
 }
 
-// Ascending bitonic sort of P = 2^lp keys by one CTA.  P <= CH: entirely in shared memory (`s` holds the keys).
-// P > CH: the keys stay in `g` (global, L2 resident); every stage runs its strides >= CH as passes over global memory
-// and finishes its strides < CH chunk by chunk in shared memory (10 global passes instead of 153 at P = 131072).
-__device__ void bitonic_sort_hybrid(unsigned long long* g, unsigned long long* s, int P, int CH) {
-  int lp = 0, lch = 0;
-  while ((1 << lp) < P) ++lp;
-  while ((1 << lch) < CH) ++lch;
-  if (P <= CH) {
-    for (int lsize = 1; lsize <= lp; ++lsize) bitonic_chunk(s, 0, P, lsize, lsize - 1);
-    return;
-  }
-  for (int base = 0; base < P; base += CH) {
-    for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[base + i];
+// k-th smallest (k >= 1) of the keys in g[0, n) that are > prev (all of them when !have_prev): MSB-first radix select with
+// 8-bit digits, one histogram pass over the keys per digit.  Keys are unique (the low word is the candidate index), so the
+// result identifies exactly k keys in (prev, result].  Every thread of the CTA must call it; all return the same value.
+__device__ unsigned long long radix_select_kth(const unsigned long long* __restrict__ g, int n, bool have_prev,
+                                               unsigned long long prev, int k, uint32_t* s_hist /*[256]*/,
+                                               unsigned long long* s_prefix, int* s_k) {
+  unsigned long long prefix = 0, mask = 0;
+  for (int d = 7; d >= 0; --d) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s_hist[b] = 0;
     __syncthreads();
-    for (int lsize = 1; lsize <= lch; ++lsize) bitonic_chunk(s, base, CH, lsize, lsize - 1);
-    for (int i = threadIdx.x; i < CH; i += blockDim.x) g[base + i] = s[i];
+    const int sh = 8 * d;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = g[i];
+      if ((!have_prev || key > prev) && (key & mask) == prefix) atomicAdd(&s_hist[(uint32_t)(key >> sh) & 255u], 1u);
+    }
     __syncthreads();
-  }
-  for (int lsize = lch + 1; lsize <= lp; ++lsize) {
-    const int size = 1 << lsize;
-    for (int ls = lsize - 1; ls >= lch; --ls) {
-      const int stride = 1 << ls;
-      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-        const int lo = ((i >> ls) << (ls + 1)) | (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const unsigned long long x = g[lo], y = g[hi];
-        if ((x > y) == up) { g[lo] = y; g[hi] = x; }
+    if (threadIdx.x == 0) {
+      int kk = k, b = 0;
+      for (; b < 255; ++b) {
+        const int h = (int)s_hist[b];
+        if (kk <= h) break;
+        kk -= h;
       }
-      __syncthreads();
+      *s_k = kk;
+      *s_prefix = prefix | ((unsigned long long)b << sh);
     }
-    for (int base = 0; base < P; base += CH) {
-      for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[base + i];
-      __syncthreads();
-      bitonic_chunk(s, base, CH, lsize, lch - 1);
-      for (int i = threadIdx.x; i < CH; i += blockDim.x) g[base + i] = s[i];
-      __syncthreads();
-    }
+    __syncthreads();
+    k = *s_k;
+    prefix = *s_prefix;
+    mask |= 0xffull << sh;
+    __syncthreads();
   }
+  return prefix;
 }
 
 struct Cand {
@@ -139,6 +140,9 @@ __device__ __forceinline__ bool iou_gt(const Cand& a, const Cand& b, double thr)
   const float xx1 = fmaxf(a.x1, b.x1), yy1 = fmaxf(a.y1, b.y1);
   const float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  // no overlap (nearly every pair: the class offset separates classes): inter = 0, the reference's quotient is 0 (or NaN for
+  // two empty boxes) and never exceeds a threshold >= 0 -- same answer without the IEEE division and the double compare
+  if (!(w > 0.f && h > 0.f)) return false;
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
   return (double)ovr > thr;
@@ -150,7 +154,10 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
   __shared__ uint32_t s_sup[kChunk][kChunk / 32];   // s_sup[i]: candidates of the chunk that i suppresses
   __shared__ uint32_t s_alive[kChunk / 32];
   __shared__ int s_newk[kChunk];
-  __shared__ int s_nnew, s_kept;
+  __shared__ int s_dead[kChunk];
+  __shared__ int s_nnew, s_kept, s_cnt, s_k;
+  __shared__ uint32_t s_hist[256];
+  __shared__ unsigned long long s_prefix;
   const int img = blockIdx.x;
   const int no = 5 + a.nc;
   unsigned long long* gkeys = a.keys + (size_t)img * a.cap;
@@ -164,23 +171,44 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
     if (threadIdx.x == 0) a.out_count[img] = 0;
     return;
   }
-  int P = 1;
-  while (P < n) P <<= 1;
-  unsigned long long* keys = gkeys;
-  if (P <= kSortSmemKeys) {
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < n ? gkeys[i] : ~0ull;
-    keys = s_keys;
-  } else {
-    for (int i = n + threadIdx.x; i < P; i += blockDim.x) gkeys[i] = ~0ull;   // cap is a power of two >= P
-  }
-  __syncthreads();
-  bitonic_sort_hybrid(gkeys, s_keys, P, kSortSmemKeys);
-  if (n > a.max_nms) n = a.max_nms;
-
+  const int n_lim = n > a.max_nms ? a.max_nms : n;   // general.py:716-717
+  const bool small = n <= kSortSmemKeys;
+  const int n_all = n;
+  const unsigned long long* keys = s_keys;
   const float* pred = a.pred + (size_t)img * a.R * no;
   float* out = a.out + (size_t)img * a.max_det * 6;
+  int processed = 0;
+  bool have_prev = false;
+  unsigned long long prev = 0;
+  while (processed < n_lim) {
+  // ---- the next batch of candidates in score order: s_keys[0, nb) ascending ----
+  int nb, nsort;
+  if (small) {
+    nsort = n_all;
+    nb = n_lim;
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) s_keys[i] = gkeys[i];
+  } else {
+    nb = nsort = (n_lim - processed) < kSortSmemKeys ? (n_lim - processed) : kSortSmemKeys;
+    const unsigned long long kth = radix_select_kth(gkeys, n_all, have_prev, prev, nb, s_hist, &s_prefix, &s_k);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+      const unsigned long long key = gkeys[i];
+      if ((!have_prev || key > prev) && key <= kth) s_keys[atomicAdd(&s_cnt, 1)] = key;
+    }
+    prev = kth;
+    have_prev = true;
+  }
+  {
+    int P = 1, lp = 0;
+    while (P < nsort) { P <<= 1; ++lp; }
+    for (int i = nsort + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = ~0ull;
+    __syncthreads();
+    for (int lsize = 1; lsize <= lp; ++lsize) bitonic_chunk(s_keys, 0, P, lsize, lsize - 1);
+  }
+  n = nb;   // the scan below runs over this batch
   for (int base = 0; base < n; base += kChunk) {
-    const int t = threadIdx.x;
+    const int t = threadIdx.x % kChunk, part = threadIdx.x / kChunk;   // kSplit threads share candidate t
     const int c = base + t;
     const bool valid = c < n;
     Cand me{0.f, 0.f, 0.f, 0.f, 0.f};
@@ -201,20 +229,31 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
       me.x2 = __fadd_rn(bx2, off); me.y2 = __fadd_rn(by2, off);
       me.area = __fmul_rn(__fsub_rn(me.x2, me.x1), __fsub_rn(me.y2, me.y1));
     }
-    s_chunk[t] = me;
-    // (a) against the boxes kept by earlier chunks
-    bool alive = valid;
-    const int kept0 = s_kept;
-    for (int k = 0; alive && k < kept0; ++k)
-      if (iou_gt(s_keep[k], me, a.iou_thres)) alive = false;
-    const uint32_t ball = __ballot_sync(0xffffffffu, alive);
-    if ((t & 31) == 0) s_alive[t >> 5] = ball;
+    if (part == 0) {
+      s_chunk[t] = me;
+      s_dead[t] = 0;
+    }
     __syncthreads();
+    // (a) against the boxes kept by earlier chunks: the kSplit threads of a candidate take every kSplit-th kept box
+    const int kept0 = s_kept;
+    if (valid) {
+      bool dead = false;
+      for (int k = part; !dead && k < kept0; k += kSplit)
+        if (iou_gt(s_keep[k], me, a.iou_thres)) dead = true;
+      if (dead) s_dead[t] = 1;
+    }
+    __syncthreads();
+    const bool alive = valid && s_dead[t] == 0;
+    if (part == 0) {   // threads 0 .. kChunk-1 = whole warps
+      const uint32_t ball = __ballot_sync(0xffffffffu, alive);
+      if ((t & 31) == 0) s_alive[t >> 5] = ball;
+    }
     // (b) the chunk's own suppression matrix: row t = later candidates of the chunk that t would suppress
     {
       // a candidate that is already dead never suppresses anything in the greedy scan: its row stays empty
+      // thread `part` of the candidate fills the words of its kChunk / kSplit columns
       uint32_t word = 0;
-      for (int u = 0; u < kChunk; ++u) {
+      for (int u = part * (kChunk / kSplit); u < (part + 1) * (kChunk / kSplit); ++u) {
         const bool s = alive && u > t && (base + u) < n && iou_gt(me, s_chunk[u], a.iou_thres);
         word |= (s ? 1u : 0u) << (u & 31);
         if ((u & 31) == 31) { s_sup[t][u >> 5] = word; word = 0; }
@@ -222,7 +261,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
     }
     __syncthreads();
     // (c) sequential resolution by one thread: 256 steps over 8-word masks
-    if (t == 0) {
+    if (threadIdx.x == 0) {
       uint32_t al[kChunk / 32];
 #pragma unroll
       for (int w = 0; w < kChunk / 32; ++w) al[w] = s_alive[w];
@@ -242,7 +281,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
     __syncthreads();
     // (d) append the survivors (in score order) to the kept list and the output
     const int nn = s_nnew, kept = s_kept;
-    for (int j = 0; j < nn; ++j) {
+    for (int j = 0; part == 0 && j < nn; ++j) {
       if (s_newk[j] == t) {
         s_keep[kept + j] = me;
         float* o = out + (size_t)(kept + j) * 6;
@@ -250,10 +289,14 @@ __global__ void __launch_bounds__(kSelThreads, 1) k_nms_select(const NmsArgs a) 
       }
     }
     __syncthreads();
-    if (t == 0) s_kept = kept + nn;
+    if (threadIdx.x == 0) s_kept = kept + nn;
     __syncthreads();
     if (s_kept >= a.max_det) break;
   }
+  processed += nb;
+  __syncthreads();
+  if (s_kept >= a.max_det) break;
+  }   // batches
   if (threadIdx.x == 0) a.out_count[img] = s_kept;
 }
 

@@ -66,6 +66,25 @@ def test_nms_full_size_properties():
     assert again.shape[0] == d.shape[0]
 
 
+def test_nms_many_batches_equals_oracle():
+    """More than 8192 candidates per image are consumed in score-ordered batches (radix select + shared-memory sort per
+    batch).  With max_det far above what survives early, the scan has to walk through SEVERAL batches up to the max_nms
+    truncation: same boxes, same order, same values as the CPU oracle (itself pinned to utils.general.non_max_suppression
+    by the golden fixtures); max_det = 300 on the same input stops inside the first batch and must give the same prefix."""
+    E = ecsy()
+    spec = dict(N=2, R=6000, nc=13, seed=778)
+    pred = S.nms_inputs(spec)
+    conf, iou = 0.001, 0.6
+    want = P.non_max_suppression(pred.clone(), conf, iou, multi_label=True, max_det=3000)
+    got = E.general.non_max_suppression(pred.cuda(), conf, iou, multi_label=True, max_det=3000)
+    short = E.general.non_max_suppression(pred.cuda(), conf, iou, multi_label=True, max_det=300)
+    for i in range(spec["N"]):
+        assert want[i].shape[0] > 300, "the case must need more than the first batch's survivors"
+        assert tuple(got[i].shape) == tuple(want[i].shape), (got[i].shape, want[i].shape)
+        assert torch.equal(got[i].cpu(), want[i])
+        assert torch.equal(short[i].cpu(), want[i][:300])
+
+
 def test_nms_rejects_bad_arguments():
     E = ecsy()
     with pytest.raises(AssertionError):
